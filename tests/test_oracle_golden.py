@@ -1,0 +1,85 @@
+"""The oracle (oracle/imgcomp_oracle.py, numpy) against the golden vectors that
+were produced by running the reference's own modules on the TF1 shim
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden, symbol_margin
+from oracle import imgcomp_oracle as O
+
+
+@pytest.mark.parametrize('name', sorted(GOLDEN_CASES))
+def test_val_graph_matches_reference_run(name, synth):
+    ae_name, _ = GOLDEN_CASES[name]
+    ae_cfg, pc_cfg, W = synth(ae_name)
+    g = load_golden(name)
+    r = O.val_forward(g['x_u8'], W, ae_cfg.num_chan_bn)
+    r64 = O.encode(g['x_u8'].astype(np.float64), W, ae_cfg.num_chan_bn, dtype=np.float64)
+    enc = r['enc']
+    np.testing.assert_allclose(enc['z'], g['z'], atol=2e-4, rtol=0)
+    # symbols: identical wherever the float64 latent is not within eps of a decision boundary
+    margin = symbol_margin(r64['z'], W['autoencoder/encoder/centers'])
+    safe = margin > 1e-4
+    assert (enc['symbols'][safe] == g['symbols'][safe]).all()
+    assert (enc['symbols'] != g['symbols']).mean() < 1e-3
+    same = enc['symbols'] == g['symbols']
+    np.testing.assert_allclose(enc['qbar'][same], g['qbar'][same], atol=1e-6)
+    np.testing.assert_allclose(r['bitcost'][same], g['bitcost'][same], atol=2e-3)
+    np.testing.assert_allclose(r['bpp'], g['bpp'], atol=1e-4)
+    np.testing.assert_allclose(r['ms_ssim'], g['ms_ssim_np'], atol=1e-4)
+    if 'x_out' in g:
+        np.testing.assert_allclose(r['x_out'], g['x_out'], atol=5e-3)
+        assert (r['x_out_u8'] != g['x_out_u8']).mean() < 1e-3
+    if 'ms_ssim_tf_raises' in g:
+        with pytest.raises((RuntimeError, ValueError)):
+            O.ms_ssim_tf(g['x_u8'].astype(np.float32), r['x_out'])
+    else:
+        v = O.ms_ssim_tf(g['x_u8'].astype(np.float32), r['x_out'])[0]
+        np.testing.assert_allclose(v, g['ms_ssim_tf'], atol=1e-4)
+
+
+def test_real_bpp_frequencies_match_reference_loop(synth):
+    """One batched pass == the reference's per-symbol PredictionNetwork loop
+    (probclass.py:441-476 driven by bit_counter.py:85-134)."""
+    ae_cfg, pc_cfg, W = synth('cvpr/low')
+    g = load_golden('tiny_low_1x64x64')
+    syms = g['symbols'][0].astype(np.int64)
+    centers = W['autoencoder/encoder/centers']
+    f = O.pc_freqs_volume(syms, W, centers)
+    assert f.shape == g['freqs'].shape
+    # float32 softmax * 1e9 truncated: allow the last float32 ulp (~60 counts at p~1)
+    assert np.abs(f - g['freqs']).max() <= 128
+    # literal per-context evaluation agrees with the batched pass
+    sp = O.pad_for_probclass3d(syms, 9, 0)
+    for (c, y, x) in ((0, 0, 0), (3, 2, 5), (31, 7, 7), (17, 0, 7)):
+        fc = O.pc_freqs_context(sp[c:c + 5, y:y + 9, x:x + 9], W, centers)
+        assert np.abs(fc - f[c, y, x]).max() <= 128
+    bits_theory = -np.log2(f / f.sum(-1, keepdims=True))
+    picked = np.take_along_axis(bits_theory, syms[..., None], -1).sum()
+    assert abs(picked - float(g['theory_bits'])) < 1.0
+    assert abs(int(g['real_bits']) - picked) < 50          # bit_counter.py:51
+
+
+def test_msssim_pairs_match_reference_functions():
+    g = load_golden('msssim_pairs')
+    for tag in 'abc':
+        x, y = g['x_' + tag], g['y_' + tag]
+        for i in range(x.shape[0]):
+            v = O.ms_ssim_np(x[i:i + 1].transpose(0, 2, 3, 1), y[i:i + 1].transpose(0, 2, 3, 1))[0]
+            np.testing.assert_allclose(v, g['np_' + tag][i], atol=1e-9)
+        v = O.ms_ssim_tf(x.astype(np.float32), y.astype(np.float32))[0]
+        np.testing.assert_allclose(v, g['tf_' + tag], atol=2e-6)
+        v64 = O.ms_ssim_tf(x.astype(np.float64), y.astype(np.float64), dtype=np.float64)[0]
+        np.testing.assert_allclose(v64, g['tf_' + tag], atol=2e-5)
+
+
+def test_float64_truth_agrees_with_float32_oracle(synth):
+    ae_cfg, pc_cfg, W = synth('cvpr/low')
+    g = load_golden('cfg1_low_1x128x128')
+    r32 = O.val_forward(g['x_u8'], W, 32)
+    r64 = O.val_forward(g['x_u8'], W, 32, dtype=np.float64)
+    margin = symbol_margin(r64['enc']['z'], W['autoencoder/encoder/centers'])
+    safe = margin > 1e-4
+    assert (r32['enc']['symbols'][safe] == r64['enc']['symbols'][safe]).all()
+    np.testing.assert_allclose(r32['bpp'], r64['bpp'], atol=1e-4)
+    np.testing.assert_allclose(r32['ms_ssim'], r64['ms_ssim'], atol=1e-4)
