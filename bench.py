@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: MPix/s of encoder + context-model (probclass) forward.
+
+    python bench.py --gpus N --steps K --warmup W [--workload kodak24|b64_512|cfg1|cfg4] [--mode fp32|exact|fast]
+    python bench.py --impl reference ...      # the restated CPU path on the host cores
+
+One "step" = ae.encode(x) + pc.bitcost(qbar, symbols) over one batch of synthetic
+uint8 images (BASELINE.json metric "MPix/s encode+probclass fwd").  Prints ONE
+JSON line (see DESIGN.md "Measurement").  N>1: launched under torchrun, one rank
+per GPU, images sharded by batch (weak scaling: every rank runs the full
+per-GPU batch), one NCCL all-reduce of the metric sums per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (ae config, N per GPU, H, W)      BASELINE.json configs
+    'cfg1': ('cvpr/low', 1, 128, 128),         # configs[0]
+    'kodak24': ('cvpr/low', 24, 768, 512),     # configs[1]  (default: the config the metric is quoted on)
+    'b64_512': ('cvpr/low', 64, 512, 512),     # north_star headline shape
+    'cfg4': ('cvpr/hi', 32, 512, 512),         # configs[3], per-GPU share of B=256
+}
+L2_FLUSH_BYTES = 256 << 20
+
+
+def encoder_macs_per_pixel(C):
+    """h1 1200 + h2 12800 + 32 x 9216 + to_bn 25*128*(C+1)/64."""
+    return 1200 + 12800 + 32 * 9216 + 25 * 128 * (C + 1) / 64.0
+
+
+def probclass_macs(C, h, w, k=24, L=6):
+    """non-masked taps, exact per-layer output shapes incl. halo."""
+    d0 = (C + 3) * (h + 6) * (w + 6) * 13 * k
+    d1 = (C + 2) * (h + 4) * (w + 4) * 14 * k * k
+    d2 = (C + 1) * (h + 2) * (w + 2) * 14 * k * k
+    d3 = C * h * w * 14 * k * L
+    return d0 + d1 + d2 + d3
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_models(ae_name, mode):
+    from imgcomp_cvpr_b200 import autoencoder, config, probclass, weights
+    a, p = config.ae_config(ae_name), config.pc_config('cvpr/res_shallow')
+    W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
+    ae = autoencoder.get_network_cls(a)(a, weights=W, mode=mode)
+    pc = probclass.get_network_cls(p)(p, num_centers=a.num_centers, weights=W)
+    return a, p, W, ae, pc
+
+
+def cpu_reference_step(x_u8, W, C):
+    """The restated CPU path (oracle, torch-CPU conv kernels): encode + probclass bitcost."""
+    from oracle import imgcomp_oracle as O
+    enc = O.encode(x_u8.astype(np.float32), W, C)
+    bc, _ = O.pc_bitcost(enc['qbar'], enc['symbols'], W, W['autoencoder/encoder/centers'][0])
+    return float(bc.sum())
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path is TF-1.4 and cannot run here;
+    the oracle's restatement is timed on the host cores on a bounded sample of the workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from imgcomp_cvpr_b200 import config, weights
+    from oracle import imgcomp_oracle as O
+    ae_name, N, H, Wd = WORKLOADS[args.workload]
+    a, p = config.ae_config(ae_name), config.pc_config('cvpr/res_shallow')
+    W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    O.set_backend('torch')
+    n_sample = 1
+    x = weights.synthetic_images(n_sample, H, Wd, seed=1234)
+    for _ in range(args.warmup):
+        cpu_reference_step(x, W, a.num_chan_bn)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(x, W, a.num_chan_bn)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_sample * H * Wd / dt / 1e6
+    sample = '%d of %d images of %dx%d per step' % (n_sample, N, H, Wd)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'MPix/s encode+probclass fwd', 'value': val, 'unit': 'MPix/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'ae': ae_name, 'pc': 'cvpr/res_shallow', 'batch_per_gpu': N,
+                   'H': H, 'W': Wd, 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': 'MPix/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'MPix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='kodak24', choices=sorted(WORKLOADS))
+    ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'fp32'), choices=['fp32', 'exact', 'fast'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('IC_BENCH_ALLOW_SHORT'), 'W >= 3 required'
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from imgcomp_cvpr_b200 import _lib, weights
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl')
+    L = _lib.lib()
+    ae_name, N, H, Wd = WORKLOADS[args.workload]
+    a, p, W, ae, pc = make_models(ae_name, args.mode)
+    C = a.num_chan_bn
+    # every rank gets its own shard of the (virtual) global batch: different seeds per rank
+    x_host = torch.from_numpy(weights.synthetic_images(N, H, Wd, seed=1234 + rank)).pin_memory()
+    x_dev = x_host.cuda()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device='cuda')
+    metric = torch.zeros(2, dtype=torch.float64, device='cuda')
+    bits_host = torch.empty(N, dtype=torch.float64).pin_memory()
+
+    def step(x):
+        enc = ae.encode(x, is_training=False)
+        pc.bitcost(enc.qbar, enc.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
+        if world > 1:      # the final metric all-reduce of a sharded val run: [sum bits, sum pixels]
+            metric[0] = pc.last_bits_per_image.sum()
+            metric[1] = float(N * H * Wd)
+            dist.all_reduce(metric)
+        return pc.last_bits_per_image
+
+    def timed(fn, steps):
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                     # L2 flush between timed iterations (not timed)
+            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_ev.record()
+            fn()
+            b_ev.record()
+            b_ev.synchronize()
+            total += a_ev.elapsed_time(b_ev)
+        return total / steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    barrier()
+    # ---- device-resident throughput (`value`) with live per-kernel-class timing
+    L.ic_profile_reset()
+    L.ic_profile_enable(1)
+    launches0 = L.ic_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(lambda: step(x_dev), args.steps)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = L.ic_launch_count() - launches0
+    L.ic_profile_enable(0)
+    prof = {}
+    for cls, name in enumerate(['conv3x3', 'conv_other', 'elementwise', 'probclass', 'msssim']):
+        t, n = _lib.c_double(), _lib.c_longlong()
+        _lib.check(L.ic_profile_get(cls, t, n))
+        prof[name] = (t.value, n.value)
+    # ---- end to end: pinned host uint8 -> H2D -> step -> D2H of the per-image bit sums
+
+    def e2e_step():
+        xd = x_host.cuda(non_blocking=True)
+        bits = step(xd)
+        bits_host.copy_(bits, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ms_e2e = timed(e2e_step, args.steps)
+    barrier()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pix = N * H * Wd
+    value = world * pix / (ms * 1e-3) / 1e6
+    e2e = world * pix / (ms_e2e * 1e-3) / 1e6
+    peaks, peak_src = load_peaks()
+    # roofline of the dominant kernel class: the 32 3x3 128->128 convs
+    t3, n3 = prof['conv3x3']
+    m_rows = N * (H // 4) * (Wd // 4)
+    flop_per_launch = 2.0 * m_rows * 128 * 1152
+    avg_ms = t3 / max(n3, 1)
+    achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if n3 else 0.0
+    peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    step_flop = 2.0 * (encoder_macs_per_pixel(C) * pix + N * probclass_macs(C, H // 8, Wd // 8, p.arch_param__k))
+    out = {
+        'metric': 'MPix/s encode+probclass fwd', 'value': value, 'unit': 'MPix/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'fp32': 'f32', 'exact': 'f16x3 (fp32-class, fp32 accumulate)', 'fast': 'f16'}[args.mode],
+        'data': 'synthetic',
+        'config': {'workload': args.workload, 'ae': ae_name, 'pc': 'cvpr/res_shallow', 'batch_per_gpu': N,
+                   'H': H, 'W': Wd, 'mode': args.mode, 'parallelism': 'batch-shard x%d' % world,
+                   'l2': 'flushed between timed iterations (%d MiB write)' % (L2_FLUSH_BYTES >> 20)},
+        'e2e': {'value': e2e, 'unit': 'MPix/s', 'h2d_bytes_per_step': int(x_host.numel()),
+                'd2h_bytes_per_step': int(bits_host.numel() * 8), 'ms_per_step': ms_e2e},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_128x128 (%s)' % args.mode, 'achieved': achieved,
+                     'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
+                     'peak_source': '%s bf16_tflops_sustained' % peak_src, 'traffic': None,
+                     'flop_per_launch': flop_per_launch, 'avg_launch_ms': avg_ms, 'launches': n3,
+                     'share_of_step': t3 / (ms * args.steps) if ms else None,
+                     'step_algorithmic_tflop': step_flop / 1e12,
+                     'step_tflops': step_flop / (ms * 1e-3) / 1e12},
+        'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
+    }
+    if not args.no_cpu_baseline:
+        import torch as _t
+        from oracle import imgcomp_oracle as O
+        cores = os.cpu_count()
+        _t.set_num_threads(cores)
+        O.set_backend('torch')
+        xs = weights.synthetic_images(1, H, Wd, seed=1234)
+        cpu_reference_step(xs, W, C)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 20):
+            cpu_reference_step(xs, W, C)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        O.set_backend('numpy')
+        out['cpu_baseline'] = {'value': H * Wd / dt / 1e6, 'unit': 'MPix/s', 'cores': cores, 'kind': 'port',
+                               'sample': '1 of %d images of %dx%d, %d repetitions' % (N, H, Wd, reps)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,566 @@
+// C ABI of imgcomp_b200 (include/imgcomp_b200.h): handles, weight re-layout,
+// layer orchestration.  No kernels here.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "probclass.cuh"
+
+namespace ic {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+size_t msssim_workspace_bytes(int N, int H, int W, int is_double);
+int msssim_tf(const float* a, const float* b, int N, int H, int W, float* out, float* levels, void* ws,
+              size_t ws_bytes, cudaStream_t s);
+int msssim_np(const uint8_t* a, const uint8_t* b, int N, int H, int W, double* out, void* ws, size_t ws_bytes,
+              cudaStream_t s);
+
+namespace {
+
+constexpr int kArchN = 128;       // code/autoencoder.py:210
+constexpr float kBnEps = 1e-5f;   // code/autoencoder.py:118
+
+struct LayerSpec {
+    std::string scope;
+    int k, stride, cin, cout;
+    bool transposed, relu;
+};
+
+// execution-order list of the autoencoder convs (code/autoencoder.py:218-268)
+std::vector<LayerSpec> ae_layers(const ic_ae_config& c, bool decoder) {
+    std::vector<LayerSpec> v;
+    const int n = kArchN, C = c.num_chan_bn, CB = c.heatmap ? C + 1 : C;
+    const std::string P = decoder ? "autoencoder/decoder" : "autoencoder/encoder";
+    const char* tag = decoder ? "dec" : "enc";
+    if (!decoder) {
+        v.push_back({P + "/h1", 5, 2, 3, n / 2, false, true});
+        v.push_back({P + "/h2", 5, 2, n / 2, n, false, true});
+    } else {
+        v.push_back({P + "/from_bn", 3, 2, C, n, true, true});
+    }
+    char buf[128];
+    for (int b = 0; b < c.arch_param_B; ++b)
+        for (int i = 1; i <= 3; ++i)
+            for (int j = 1; j <= 2; ++j) {
+                snprintf(buf, sizeof(buf), "/res_block_%s_%d/%s_%d_%d/conv%d", tag, b, tag, b, i, j);
+                v.push_back({P + buf, 3, 1, n, n, false, j == 1});
+            }
+    const char* fin = decoder ? "/dec_after_res" : "/res_block_enc_final";
+    v.push_back({P + fin + "/conv1", 3, 1, n, n, false, false});   // activation_fn=None for both (autoencoder.py:232-233)
+    v.push_back({P + fin + "/conv2", 3, 1, n, n, false, false});
+    if (!decoder) {
+        v.push_back({P + "/to_bn", 5, 2, n, CB, false, false});
+    } else {
+        v.push_back({P + "/h12", 5, 2, n, n / 2, true, true});
+        v.push_back({P + "/h13", 5, 2, n / 2, 3, true, false});
+    }
+    return v;
+}
+
+const char* kBnNames[4] = {"gamma", "beta", "moving_mean", "moving_variance"};
+
+struct TensorInfo {
+    std::string name;
+    int64_t numel;
+};
+
+std::vector<TensorInfo> ae_tensors(const ic_ae_config& c) {
+    std::vector<TensorInfo> t;
+    for (int dec = 0; dec < 2; ++dec) {
+        for (const auto& l : ae_layers(c, dec)) {
+            t.push_back({l.scope + "/weights", (int64_t)l.k * l.k * l.cin * l.cout});
+            for (int i = 0; i < 4; ++i) t.push_back({l.scope + "/BatchNorm/" + kBnNames[i], l.cout});
+        }
+        if (!dec) t.push_back({"autoencoder/encoder/centers", c.num_centers});
+    }
+    return t;
+}
+
+struct DevLayer {
+    LayerSpec spec;
+    int cin_pad, ldw;
+    float *w = nullptr, *scale = nullptr, *shift = nullptr;
+};
+
+int upload(const std::vector<float>& h, float** d) {
+    IC_CHECK_CUDA(cudaMalloc((void**)d, h.size() * sizeof(float)));
+    IC_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return IC_OK;
+}
+
+bool cfg_ok(const ic_ae_config* c) {
+    return c && (c->num_chan_bn % 4 == 0) && c->num_chan_bn > 0 && c->num_chan_bn <= 256 && c->arch_param_B >= 0 &&
+           c->arch_param_B <= 16 && c->num_centers >= 1 && c->num_centers <= 8;
+}
+
+}  // namespace
+}  // namespace ic
+
+using namespace ic;
+
+struct ic_ae {
+    ic_ae_config cfg;
+    std::vector<DevLayer> enc, dec;
+    float* d_centers = nullptr;
+    float h_centers[8];
+};
+
+struct ic_pc {
+    ic_pc_config cfg;
+    PcWeights w;
+    std::vector<float*> owned;
+};
+
+extern "C" {
+
+const char* ic_last_error(void) { return g_err; }
+int ic_abi_version(void) { return IC_ABI_VERSION; }
+
+int ic_device_ok(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return 0;
+    }
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+
+// ------------------------------------------------------------------ autoencoder
+int ic_ae_num_tensors(const ic_ae_config* cfg) { return cfg_ok(cfg) ? (int)ae_tensors(*cfg).size() : IC_ERR_INVALID; }
+
+const char* ic_ae_tensor_name(const ic_ae_config* cfg, int i) {
+    static thread_local std::string s;
+    if (!cfg_ok(cfg)) return nullptr;
+    auto t = ae_tensors(*cfg);
+    if (i < 0 || i >= (int)t.size()) return nullptr;
+    s = t[i].name;
+    return s.c_str();
+}
+
+int64_t ic_ae_tensor_numel(const ic_ae_config* cfg, int i) {
+    if (!cfg_ok(cfg)) return IC_ERR_INVALID;
+    auto t = ae_tensors(*cfg);
+    if (i < 0 || i >= (int)t.size()) return IC_ERR_INVALID;
+    return t[i].numel;
+}
+
+int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_tensors, ic_ae_t** out) {
+    IC_REQUIRE(cfg_ok(cfg) && h_tensors && out, IC_ERR_INVALID, "ic_ae_create: bad config / NULL argument");
+    IC_REQUIRE(cfg->normalization == 0 || cfg->normalization == 1, IC_ERR_UNSUPPORTED, "normalization must be OFF(0) or FIXED(1)");
+    auto tensors = ae_tensors(*cfg);
+    IC_REQUIRE(n_tensors == (int)tensors.size(), IC_ERR_INVALID, "ic_ae_create: expected %zu tensors, got %d",
+               tensors.size(), n_tensors);
+    for (int i = 0; i < n_tensors; ++i) IC_REQUIRE(h_tensors[i], IC_ERR_INVALID, "ic_ae_create: tensor %d (%s) is NULL", i, tensors[i].name.c_str());
+    ic_ae* ae = new ic_ae();
+    ae->cfg = *cfg;
+    int ti = 0;
+    for (int dec = 0; dec < 2; ++dec) {
+        auto& dst = dec ? ae->dec : ae->enc;
+        for (const auto& l : ae_layers(*cfg, dec)) {
+            DevLayer d;
+            d.spec = l;
+            d.cin_pad = (int)align_up(l.cin, 4);
+            d.ldw = (int)align_up(l.cout, 4);
+            const float* w = h_tensors[ti];
+            const float *g = h_tensors[ti + 1], *be = h_tensors[ti + 2], *mu = h_tensors[ti + 3], *var = h_tensors[ti + 4];
+            ti += 5;
+            // GEMM B matrix [(ky,kx,ci)][co]; conv2d weights are HWIO, conv2d_transpose weights [kh,kw,Cout,Cin]
+            std::vector<float> wm((size_t)l.k * l.k * d.cin_pad * d.ldw, 0.f), sc(d.ldw, 0.f), sh(d.ldw, 0.f);
+            for (int t = 0; t < l.k * l.k; ++t)
+                for (int ci = 0; ci < l.cin; ++ci)
+                    for (int co = 0; co < l.cout; ++co) {
+                        float v = l.transposed ? w[((size_t)t * l.cout + co) * l.cin + ci] : w[((size_t)t * l.cin + ci) * l.cout + co];
+                        wm[((size_t)t * d.cin_pad + ci) * d.ldw + co] = v;
+                    }
+            for (int co = 0; co < l.cout; ++co) {   // fused batch norm, inference
+                float inv = 1.0f / sqrtf(var[co] + kBnEps);
+                sc[co] = g[co] * inv;
+                sh[co] = be[co] - mu[co] * sc[co];
+            }
+            int rc = upload(wm, &d.w);
+            if (rc == IC_OK) rc = upload(sc, &d.scale);
+            if (rc == IC_OK) rc = upload(sh, &d.shift);
+            dst.push_back(d);
+            if (rc != IC_OK) {
+                ic_ae_destroy(ae);
+                return rc;
+            }
+        }
+        if (!dec) {
+            std::vector<float> c(h_tensors[ti], h_tensors[ti] + cfg->num_centers);
+            memset(ae->h_centers, 0, sizeof(ae->h_centers));
+            memcpy(ae->h_centers, c.data(), sizeof(float) * cfg->num_centers);
+            ++ti;
+            int rc = upload(c, &ae->d_centers);
+            if (rc != IC_OK) {
+                ic_ae_destroy(ae);
+                return rc;
+            }
+        }
+    }
+    *out = ae;
+    return IC_OK;
+}
+
+void ic_ae_destroy(ic_ae_t* ae) {
+    if (!ae) return;
+    for (auto* v : {&ae->enc, &ae->dec})
+        for (auto& l : *v) {
+            cudaFree(l.w);
+            cudaFree(l.scale);
+            cudaFree(l.shift);
+        }
+    cudaFree(ae->d_centers);
+    delete ae;
+}
+
+int ic_ae_centers(const ic_ae_t* ae, float* d_centers, void* stream) {
+    IC_REQUIRE(ae && d_centers, IC_ERR_INVALID, "ic_ae_centers: NULL argument");
+    IC_CHECK_CUDA(cudaMemcpyAsync(d_centers, ae->d_centers, sizeof(float) * ae->cfg.num_centers, cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
+    return IC_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+ConvDesc make_desc(const DevLayer& L, const float* in, int N, int Hi, int Wi, float* out) {
+    ConvDesc d;
+    memset(&d, 0, sizeof(d));
+    const LayerSpec& s = L.spec;
+    d.in = in;
+    d.w = L.w;
+    d.scale = L.scale;
+    d.shift = L.shift;
+    d.out = out;
+    d.N = N;
+    d.Hi = Hi;
+    d.Wi = Wi;
+    d.Cin = L.cin_pad;
+    d.Cout = s.cout;
+    d.ldw = L.ldw;
+    d.KH = d.KW = s.k;
+    d.stride = s.stride;
+    d.transposed = s.transposed;
+    d.relu = s.relu;
+    if (!s.transposed) {
+        d.Ho = (Hi + s.stride - 1) / s.stride;
+        d.Wo = (Wi + s.stride - 1) / s.stride;
+        d.pad_t = same_pad_before(Hi, s.k, s.stride);
+        d.pad_l = same_pad_before(Wi, s.k, s.stride);
+    } else {   // gradient of the SAME conv from stride*n -> n
+        d.Ho = Hi * s.stride;
+        d.Wo = Wi * s.stride;
+        d.pad_t = same_pad_before(d.Ho, s.k, s.stride);
+        d.pad_l = same_pad_before(d.Wo, s.k, s.stride);
+    }
+    return d;
+}
+
+// 15 residual blocks (+5 group skips) + final no-ReLU block + long skip
+// (code/autoencoder.py:224-234 / :252-262).  `layers` points at the first 3x3 conv.
+// pool: 5 trunk-sized buffers, pool[0] holds the input on entry.  Returns the output buffer.
+int run_res_stack(const DevLayer* layers, int B, int N, int H, int W, float* pool[5], float** result, cudaStream_t s) {
+    bool busy[5] = {true, false, false, false, false};
+    auto grab = [&]() {
+        for (int i = 0; i < 5; ++i)
+            if (!busy[i]) {
+                busy[i] = true;
+                return i;
+            }
+        return -1;
+    };
+    const int r0 = 0;
+    int x = 0, li = 0;
+    for (int b = 0; b <= B; ++b) {
+        const bool final_block = (b == B);
+        const int rb = x;
+        for (int i = 0; i < (final_block ? 1 : 3); ++i) {
+            int t1 = grab();
+            ConvDesc d1 = make_desc(layers[li++], pool[x], N, H, W, pool[t1]);
+            int rc = launch_conv_simt(d1, s);
+            if (rc != IC_OK) return rc;
+            int y = grab();
+            ConvDesc d2 = make_desc(layers[li++], pool[t1], N, H, W, pool[y]);
+            d2.res1 = pool[x];                                         // residual_block: x + residual_input
+            const bool last = final_block || i == 2;
+            if (last) d2.res2 = pool[final_block ? r0 : rb];           // net = net + residual_input_{b,0}
+            rc = launch_conv_simt(d2, s);
+            if (rc != IC_OK) return rc;
+            busy[t1] = false;
+            if (x != rb && x != r0) busy[x] = false;
+            x = y;
+        }
+        if (rb != r0 && rb != x) busy[rb] = false;
+    }
+    *result = pool[x];
+    return IC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ic_encode_workspace_bytes(const ic_ae_t* ae, int N, int H, int W, int mode) {
+    if (!ae || N <= 0 || H <= 0 || W <= 0) return 0;
+    (void)mode;
+    const size_t n = N;
+    const int CB = ae->cfg.heatmap ? ae->cfg.num_chan_bn + 1 : ae->cfg.num_chan_bn;
+    size_t b = 0;
+    b += align_up(n * H * W * 4 * 4, 256);
+    b += align_up(n * (H / 2) * (W / 2) * 64 * 4, 256);
+    b += 5 * align_up(n * (H / 4) * (W / 4) * 128 * 4, 256);
+    b += align_up(n * (H / 8) * (W / 8) * CB * 4, 256);
+    return b + 4096;
+}
+
+int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H, int W, float* d_z, float* d_heatmap,
+                  float* d_qbar, float* d_qhard, int64_t* d_symbols, uint8_t* d_symbols_u8, float* d_qsoft,
+                  void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+    IC_REQUIRE(ae && d_x && d_workspace, IC_ERR_INVALID, "ic_encode_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, IC_ERR_INVALID,
+               "ic_encode_fwd: N=%d H=%d W=%d; H and W must be positive multiples of the subsampling factor 8", N, H, W);
+    IC_REQUIRE(mode == IC_MODE_FP32, IC_ERR_UNSUPPORTED, "ic_encode_fwd: mode %d not available in this build", mode);
+    cudaStream_t s = (cudaStream_t)stream;
+    const ic_ae_config& c = ae->cfg;
+    const int CB = c.heatmap ? c.num_chan_bn + 1 : c.num_chan_bn;
+    Arena ar(d_workspace, workspace_bytes);
+    const size_t n = N;
+    float* xin = ar.get<float>(n * H * W * 4);
+    float* a1 = ar.get<float>(n * (H / 2) * (W / 2) * 64);
+    float* pool[5];
+    for (int i = 0; i < 5; ++i) pool[i] = ar.get<float>(n * (H / 4) * (W / 4) * 128);
+    float* bn = ar.get<float>(n * (H / 8) * (W / 8) * CB);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_encode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
+
+    int rc = launch_prep_input(d_x, x_is_u8, N, H, W, c.normalization, xin, s);
+    if (rc != IC_OK) return rc;
+    const DevLayer* L = ae->enc.data();
+    rc = launch_conv_simt(make_desc(L[0], xin, N, H, W, a1), s);
+    if (rc != IC_OK) return rc;
+    rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[0]), s);
+    if (rc != IC_OK) return rc;
+    float* trunk = nullptr;
+    rc = run_res_stack(L + 2, c.arch_param_B, N, H / 4, W / 4, pool, &trunk, s);
+    if (rc != IC_OK) return rc;
+    const DevLayer& tobn = ae->enc.back();
+    rc = launch_conv_simt(make_desc(tobn, trunk, N, H / 4, W / 4, bn), s);
+    if (rc != IC_OK) return rc;
+    return launch_heatmap_quantize(bn, N, H / 8, W / 8, c.num_chan_bn, c.heatmap, ae->d_centers, c.num_centers, d_z,
+                                   d_heatmap, d_qbar, d_qhard, d_symbols, d_symbols_u8, d_qsoft, s);
+}
+
+size_t ic_decode_workspace_bytes(const ic_ae_t* ae, int N, int h, int w, int mode) {
+    if (!ae || N <= 0 || h <= 0 || w <= 0) return 0;
+    (void)mode;
+    const size_t n = N;
+    size_t b = 0;
+    b += align_up(n * h * w * ae->cfg.num_chan_bn * 4, 256);
+    b += 5 * align_up(n * (2 * h) * (2 * w) * 128 * 4, 256);
+    b += align_up(n * (4 * h) * (4 * w) * 64 * 4, 256);
+    return b + 4096;
+}
+
+int ic_decode_fwd(const ic_ae_t* ae, const float* d_q, int N, int h, int w, float* d_x_out, uint8_t* d_x_out_u8,
+                  void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+    IC_REQUIRE(ae && d_q && d_x_out && d_workspace, IC_ERR_INVALID, "ic_decode_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_decode_fwd: bad shape N=%d h=%d w=%d", N, h, w);
+    IC_REQUIRE(mode == IC_MODE_FP32, IC_ERR_UNSUPPORTED, "ic_decode_fwd: mode %d not available in this build", mode);
+    cudaStream_t s = (cudaStream_t)stream;
+    const ic_ae_config& c = ae->cfg;
+    Arena ar(d_workspace, workspace_bytes);
+    const size_t n = N;
+    float* qn = ar.get<float>(n * h * w * c.num_chan_bn);
+    float* pool[5];
+    for (int i = 0; i < 5; ++i) pool[i] = ar.get<float>(n * (2 * h) * (2 * w) * 128);
+    float* a12 = ar.get<float>(n * (4 * h) * (4 * w) * 64);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_decode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
+    int rc = launch_nchw_to_nhwc(d_q, N, c.num_chan_bn, h, w, qn, s);
+    if (rc != IC_OK) return rc;
+    const DevLayer* L = ae->dec.data();
+    rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[0]), s);
+    if (rc != IC_OK) return rc;
+    float* trunk = nullptr;
+    rc = run_res_stack(L + 1, c.arch_param_B, N, 2 * h, 2 * w, pool, &trunk, s);
+    if (rc != IC_OK) return rc;
+    const size_t nl = ae->dec.size();
+    rc = launch_conv_simt(make_desc(L[nl - 2], trunk, N, 2 * h, 2 * w, a12), s);
+    if (rc != IC_OK) return rc;
+    ConvDesc d = make_desc(L[nl - 1], a12, N, 4 * h, 4 * w, d_x_out);
+    d.out_nchw = 1;
+    d.denorm = c.normalization;
+    d.out_u8 = d_x_out_u8;
+    return launch_conv_simt(d, s);
+}
+
+int ic_quantize_fwd(const float* d_x, const float* d_centers, int L, float sigma, int64_t n, float* d_qsoft,
+                    float* d_qhard, int64_t* d_symbols, void* stream) {
+    IC_REQUIRE(d_x && d_centers && n >= 0 && L >= 1, IC_ERR_INVALID, "ic_quantize_fwd: bad argument");
+    return launch_quantize(d_x, d_centers, L, sigma, n, d_qsoft, d_qhard, d_symbols, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------- probclass
+static const char* kPcScopes[4] = {"probclass3d/logits/conv3d_conv0_mask", "probclass3d/logits/res1/conv3d_conv1_mask",
+                                   "probclass3d/logits/res1/conv3d_conv2_mask", "probclass3d/logits/conv3d_conv2_mask"};
+
+static bool pc_cfg_ok(const ic_pc_config* c) {
+    return c && c->kernel_size == 3 && (c->arch_param_k == 24 || c->arch_param_k == 64) && c->num_centers >= 1 &&
+           c->num_centers <= 8;
+}
+
+static void pc_dims(const ic_pc_config* c, int layer, int* ci, int* co) {
+    *ci = layer == 0 ? 1 : c->arch_param_k;
+    *co = layer == 3 ? c->num_centers : c->arch_param_k;
+}
+
+int ic_pc_num_tensors(const ic_pc_config* cfg) { return pc_cfg_ok(cfg) ? 8 : IC_ERR_UNSUPPORTED; }
+
+const char* ic_pc_tensor_name(const ic_pc_config* cfg, int i) {
+    static thread_local std::string s;
+    if (!pc_cfg_ok(cfg) || i < 0 || i >= 8) return nullptr;
+    s = std::string(kPcScopes[i / 2]) + (i % 2 ? "/biases" : "/weights");
+    return s.c_str();
+}
+
+int64_t ic_pc_tensor_numel(const ic_pc_config* cfg, int i) {
+    if (!pc_cfg_ok(cfg) || i < 0 || i >= 8) return IC_ERR_INVALID;
+    int ci, co;
+    pc_dims(cfg, i / 2, &ci, &co);
+    return i % 2 ? co : (int64_t)18 * ci * co;
+}
+
+int ic_pc_create(const ic_pc_config* cfg, const float* const* h_tensors, int n_tensors, ic_pc_t** out) {
+    IC_REQUIRE(cfg && h_tensors && out, IC_ERR_INVALID, "ic_pc_create: NULL argument");
+    IC_REQUIRE(pc_cfg_ok(cfg), IC_ERR_UNSUPPORTED,
+               "ic_pc_create: only arch res_shallow with kernel_size 3, arch_param__k in {24,64}, num_centers <= 8 is on the hot path");
+    IC_REQUIRE(n_tensors == 8, IC_ERR_INVALID, "ic_pc_create: expected 8 tensors, got %d", n_tensors);
+    for (int i = 0; i < 8; ++i) IC_REQUIRE(h_tensors[i], IC_ERR_INVALID, "ic_pc_create: tensor %d is NULL", i);
+    ic_pc* pc = new ic_pc();
+    pc->cfg = *cfg;
+    pc->w.K = cfg->arch_param_k;
+    pc->w.L = cfg->num_centers;
+    const float** wdst[4] = {&pc->w.w0, &pc->w.w1, &pc->w.w2, &pc->w.w3};
+    const float** bdst[4] = {&pc->w.b0, &pc->w.b1, &pc->w.b2, &pc->w.b3};
+    for (int l = 0; l < 4; ++l) {
+        int ci, co;
+        pc_dims(cfg, l, &ci, &co);
+        const float* w = h_tensors[2 * l];     // [2][3][3][ci][co]
+        std::vector<float> packed;
+        // keep only the taps the mask leaves (code/probclass.py:150-176), raster (fd,fy,fx) order
+        for (int fd = 0; fd < 2; ++fd)
+            for (int fy = 0; fy < 3; ++fy)
+                for (int fx = 0; fx < 3; ++fx) {
+                    bool masked = fd == 1 && (fy > 1 || (fy == 1 && (l == 0 ? fx >= 1 : fx > 1)));
+                    if (masked) continue;
+                    const float* src = w + ((size_t)(fd * 3 + fy) * 3 + fx) * ci * co;
+                    packed.insert(packed.end(), src, src + (size_t)ci * co);
+                }
+        std::vector<float> bias(h_tensors[2 * l + 1], h_tensors[2 * l + 1] + co);
+        float *dw = nullptr, *db = nullptr;
+        int rc = upload(packed, &dw);
+        if (rc == IC_OK) rc = upload(bias, &db);
+        pc->owned.push_back(dw);
+        pc->owned.push_back(db);
+        if (rc != IC_OK) {
+            ic_pc_destroy(pc);
+            return rc;
+        }
+        *wdst[l] = dw;
+        *bdst[l] = db;
+    }
+    *out = pc;
+    return IC_OK;
+}
+
+void ic_pc_destroy(ic_pc_t* pc) {
+    if (!pc) return;
+    for (float* p : pc->owned) cudaFree(p);
+    delete pc;
+}
+
+size_t ic_pc_workspace_bytes(const ic_pc_t* pc, int N, int D, int H, int W) {
+    if (!pc || N <= 0) return 0;
+    // sized for the padded case (bitcost / freqs); logits() on a bare volume needs less
+    return pc_workspace_bytes(pc->cfg.arch_param_k, N, D, H, W, 4, 4);
+}
+
+int ic_pc_bitcost_fwd(const ic_pc_t* pc, const float* d_q, const int64_t* d_symbols, float pad_value, int N, int C, int h,
+                      int w, float* d_bits, double* d_bits_sum, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_q && d_symbols && d_bits && d_workspace, IC_ERR_INVALID, "ic_pc_bitcost_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_pc_bitcost_fwd: bad shape");
+    PcInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.D = C; in.H = h; in.W = w;
+    in.pad_d = 4; in.pad_hw = 4;
+    in.q = d_q;
+    in.pad_value = pad_value;
+    in.target_symbols = d_symbols;
+    return pc_forward(pc->w, in, PC_HEAD_BITCOST, d_bits, nullptr, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ic_pc_logits_fwd(const ic_pc_t* pc, const float* d_q, int N, int D, int H, int W, float* d_logits, void* d_workspace,
+                     size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_q && d_logits && d_workspace, IC_ERR_INVALID, "ic_pc_logits_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && D >= 5 && H >= 9 && W >= 9, IC_ERR_INVALID,
+               "ic_pc_logits_fwd: volume %dx%dx%d is smaller than the 5x9x9 context", D, H, W);
+    PcInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.D = D; in.H = H; in.W = W;
+    in.q = d_q;
+    return pc_forward(pc->w, in, PC_HEAD_LOGITS, d_logits, nullptr, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_centers, int N, int C, int h, int w,
+                    int64_t* d_freqs, double* d_bits_sum, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_symbols && d_centers && d_freqs && d_workspace, IC_ERR_INVALID, "ic_pc_freqs_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_pc_freqs_fwd: bad shape");
+    PcInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.D = C; in.H = h; in.W = w;
+    in.pad_d = 4; in.pad_hw = 4;
+    in.symbols = d_symbols;
+    in.target_symbols = d_symbols;
+    // centres are tiny: read them back once so the gather table can travel as a kernel argument
+    IC_CHECK_CUDA(cudaMemcpyAsync(in.centers_host, d_centers, sizeof(float) * pc->cfg.num_centers, cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+    IC_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, d_freqs, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------- MS-SSIM
+size_t ic_msssim_workspace_bytes(int N, int H, int W, int is_double) {
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    return msssim_workspace_bytes(N, H, W, is_double) + 256 + align_up(sizeof(double) * 10 * (size_t)N, 256);
+}
+
+int ic_msssim_tf_fwd(const float* d_img1, const float* d_img2, int N, int H, int W, float* d_out, float* d_levels,
+                     void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_img1 && d_img2 && d_out && d_workspace, IC_ERR_INVALID, "ic_msssim_tf_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_msssim_tf_fwd: bad shape");
+    return msssim_tf(d_img1, d_img2, N, H, W, d_out, d_levels, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ic_msssim_np_fwd(const uint8_t* d_img1, const uint8_t* d_img2, int N, int H, int W, double* d_out, void* d_workspace,
+                     size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_img1 && d_img2 && d_out && d_workspace, IC_ERR_INVALID, "ic_msssim_np_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_msssim_np_fwd: bad shape");
+    return msssim_np(d_img1, d_img2, N, H, W, d_out, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

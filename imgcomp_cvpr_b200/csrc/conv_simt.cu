@@ -1,0 +1,162 @@
+// float32 FFMA implicit-GEMM convolution (IC_MODE_FP32).
+//
+// Computes what slim.conv2d / slim.conv2d_transpose + fused batch norm + ReLU
+// compute in the reference (code/autoencoder.py:106-125,222-237,251,264-265),
+// plus the residual additions of residual_block (:274-287) and the skip
+// connections of _CVPR._encode/_decode (:231,234,259,262), and for h13 the
+// _denormalize + _clip_to_image_range epilogue (:146-158).
+//
+// GEMM view: M = N*Ho*Wo output pixels, N = Cout, K = KH*KW*Cin.
+// 64x64 block tile, BK = 16, 256 threads, 4x4 register tile, double buffered.
+#include "common.cuh"
+
+namespace ic {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+__constant__ float c_norm_mean[3] = {121.853699f, 113.588608f, 100.637154f};
+// np.sqrt(var + 1e-10) evaluated in float32 (code/autoencoder.py:143,153,160-169)
+__constant__ float c_norm_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};
+
+__global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+    const int t = threadIdx.x;
+    const int64_t M = (int64_t)d.N * d.Ho * d.Wo;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int K = d.KH * d.KW * d.Cin;
+
+    // A-load assignment: one output pixel row, 4 consecutive k
+    const int am = t >> 2, ak = (t & 3) * 4;
+    const int64_t mrow = m0 + am;
+    const bool mvalid = mrow < M;
+    int pn = 0, oy = 0, ox = 0;
+    if (mvalid) {
+        pn = (int)(mrow / ((int64_t)d.Ho * d.Wo));
+        int r = (int)(mrow - (int64_t)pn * d.Ho * d.Wo);
+        oy = r / d.Wo;
+        ox = r - oy * d.Wo;
+    }
+    // B-load assignment
+    const int bk = t >> 4, bn = (t & 15) * 4;
+
+    auto load_a = [&](int k0) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = k0 + ak;
+        if (mvalid && k < K) {
+            int tap = k / d.Cin, ci = k - tap * d.Cin;
+            int ky = tap / d.KW, kx = tap - ky * d.KW;
+            int iy, ix;
+            bool ok;
+            if (!d.transposed) {
+                iy = oy * d.stride - d.pad_t + ky;
+                ix = ox * d.stride - d.pad_l + kx;
+                ok = iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi;
+            } else {
+                int ny = oy + d.pad_t - ky, nx = ox + d.pad_l - kx;
+                ok = ny >= 0 && nx >= 0 && (ny % d.stride) == 0 && (nx % d.stride) == 0;
+                iy = ny / d.stride;
+                ix = nx / d.stride;
+                ok = ok && iy < d.Hi && ix < d.Wi;
+            }
+            if (ok) v = *reinterpret_cast<const float4*>(d.in + (((int64_t)pn * d.Hi + iy) * d.Wi + ix) * d.Cin + ci);
+        }
+        return v;
+    };
+    auto load_b = [&](int k0) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = k0 + bk;
+        if (k < K && n0 + bn < d.ldw) v = *reinterpret_cast<const float4*>(d.w + (int64_t)k * d.ldw + n0 + bn);
+        return v;
+    };
+    auto store = [&](int buf, float4 a, float4 b) {
+        As[buf][ak + 0][am] = a.x;
+        As[buf][ak + 1][am] = a.y;
+        As[buf][ak + 2][am] = a.z;
+        As[buf][ak + 3][am] = a.w;
+        *reinterpret_cast<float4*>(&Bs[buf][bk][bn]) = b;
+    };
+
+    const int tx = t & 15, ty = t >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float4 ra = load_a(0), rb = load_b(0);
+    store(0, ra, rb);
+    __syncthreads();
+    const int nk = (K + BK - 1) / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) {
+            ra = load_a((kt + 1) * BK);
+            rb = load_b((kt + 1) * BK);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            store(buf ^ 1, ra, rb);
+            __syncthreads();
+        }
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= d.Cout) continue;
+            float v = fmaf(acc[i][j], d.scale[n], d.shift[n]);
+            if (d.relu) v = fmaxf(v, 0.f);
+            int64_t o = m * d.Cout + n;
+            if (d.res1) v += d.res1[o];
+            if (d.res2) v += d.res2[o];
+            if (!d.out_nchw) {
+                d.out[o] = v;
+            } else {
+                if (d.denorm) {
+                    v = __fadd_rn(__fmul_rn(v, c_norm_std[n]), c_norm_mean[n]);
+                    v = fminf(fmaxf(v, 0.f), 255.f);
+                }
+                int64_t hw = (int64_t)d.Ho * d.Wo;
+                int64_t img = m / hw, r = m - img * hw;
+                int64_t oo = (img * d.Cout + n) * hw + r;
+                d.out[oo] = v;
+                if (d.out_u8) d.out_u8[oo] = (uint8_t)v;   // tf.cast truncation (val.py:91); v in [0,255]
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_conv_simt(const ConvDesc& d, cudaStream_t stream) {
+    IC_REQUIRE(d.Cin % 4 == 0 && d.ldw % 4 == 0, IC_ERR_INVALID, "conv_simt: Cin (%d) and ldw (%d) must be multiples of 4",
+               d.Cin, d.ldw);
+    int64_t M = (int64_t)d.N * d.Ho * d.Wo;
+    dim3 grid(cdiv(M, BM), cdiv(d.Cout, BN));
+    const bool res_conv = d.KH == 3 && !d.transposed && d.Cin == 128 && d.Cout == 128;
+    ProfScope ps(res_conv ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER, stream);
+    conv_simt_kernel<<<grid, NT, 0, stream>>>(d);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+}  // namespace ic

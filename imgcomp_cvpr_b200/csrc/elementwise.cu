@@ -1,0 +1,192 @@
+// HBM-bound elementwise stages of the encoder: input normalisation / layout
+// change, importance-map (heatmap) masking and the nearest-centre quantizer.
+#include "common.cuh"
+
+namespace ic {
+
+namespace {
+
+__constant__ float c_mean[3] = {121.853699f, 113.588608f, 100.637154f};
+__constant__ float c_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};   // float32 sqrt(var + 1e-10)
+
+// _Network._normalize (code/autoencoder.py:136-144) fused with tf.to_float
+// (val.py:83) and the NCHW -> NHWC(4) layout change.  One thread per pixel.
+template <typename TIn>
+__global__ void prep_input_kernel(const TIn* __restrict__ x, int64_t npix_per_img, int64_t total, int normalize,
+                                  float4* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t n = i / npix_per_img, r = i - n * npix_per_img;
+    const TIn* p = x + n * 3 * npix_per_img + r;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float f = (float)p[c * npix_per_img];
+        v[c] = normalize ? __fdiv_rn(__fsub_rn(f, c_mean[c]), c_std[c]) : f;
+    }
+    out[i] = make_float4(v[0], v[1], v[2], 0.f);
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t hw, int64_t total,
+                                    float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in NHWC order
+    if (i >= total) return;
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int64_t n = p / hw, r = p - n * hw;
+    out[i] = in[(n * C + c) * hw + r];
+}
+
+// quantizer._quantize1d for one value (code/quantizer.py:72-95).
+//   dist_j  = square(abs(x - c_j))                       two roundings, no FMA
+//   symbol  = argmax_j softmax(-1e7 * dist)_j            first index among maxima; the
+//             softmax is monotone in fl(-1e7*dist_j) and exp(l_j - max) < 1 whenever
+//             l_j < max, so this is the first j minimising fl(1e7 * dist_j)
+//   qhard   = sum_j onehot_j * c_j = c[symbol] exactly
+//   qsoft   = sum_j softmax(-sigma*dist)_j * c_j         summed in index order
+template <int MAXL>
+__device__ __forceinline__ void quantize_one(float x, const float* __restrict__ c, int L, float sigma,
+                                             float& qsoft, float& qhard, int& sym) {
+    float dist[MAXL];
+    float best = 0.f;
+    int bi = 0;
+    float lmax = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) {
+        if (j < L) {
+            float df = fabsf(__fsub_rn(x, c[j]));
+            dist[j] = __fmul_rn(df, df);
+            float lh = __fmul_rn(1e7f, dist[j]);
+            float ls = __fmul_rn(-sigma, dist[j]);
+            if (j == 0 || lh < best) { best = lh; bi = j; }
+            if (j == 0 || ls > lmax) lmax = ls;
+        }
+    }
+    float e[MAXL];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j)
+        if (j < L) {
+            e[j] = expf(__fsub_rn(__fmul_rn(-sigma, dist[j]), lmax));
+            s = __fadd_rn(s, e[j]);
+        }
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j)
+        if (j < L) {
+            float term = __fmul_rn(__fdiv_rn(e[j], s), c[j]);
+            acc = (j == 0) ? term : __fadd_rn(acc, term);
+        }
+    qsoft = acc;
+    qhard = c[bi];
+    sym = bi;
+}
+
+constexpr int kMaxL = 8;
+
+// _get_heatmap3D + _mask_with_heatmap + _quantize (code/autoencoder.py:127-134,171-200)
+// in: to_bn output NHWC (N,h,w,C+1); out: NCHW tensors.  One thread per (n,c,y,x).
+__global__ void heatmap_quantize_kernel(const float* __restrict__ bn, int h, int w, int C, int heatmap,
+                                        const float* __restrict__ centers, int L, int64_t total,
+                                        float* __restrict__ z_out, float* __restrict__ hm_out,
+                                        float* __restrict__ qbar_out, float* __restrict__ qhard_out,
+                                        int64_t* __restrict__ sym_out, uint8_t* __restrict__ sym8_out,
+                                        float* __restrict__ qsoft_out) {
+    __shared__ float sc[kMaxL];
+    if (threadIdx.x < L) sc[threadIdx.x] = centers[threadIdx.x];
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // NCHW index
+    if (i >= total) return;
+    int64_t hw = (int64_t)h * w;
+    int64_t r = i % hw;
+    int64_t nc = i / hw;
+    int c = (int)(nc % C);
+    int64_t n = nc / C;
+    int CB = heatmap ? C + 1 : C;
+    const float* px = bn + (n * hw + r) * CB;
+    float z, hm = 1.f;
+    if (heatmap) {
+        float h0 = px[0];
+        // tf.nn.sigmoid(x) * C ; heatmap3D = max(min(hm2D - c, 1), 0)
+        float sg = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-h0)));
+        float hm2d = __fmul_rn(sg, (float)C);
+        hm = fmaxf(fminf(__fsub_rn(hm2d, (float)c), 1.f), 0.f);
+        z = __fmul_rn(hm, px[1 + c]);
+    } else {
+        z = px[c];
+    }
+    float qsoft, qhard;
+    int sym;
+    quantize_one<kMaxL>(z, sc, L, 1.f, qsoft, qhard, sym);
+    if (z_out) z_out[i] = z;
+    if (hm_out) hm_out[i] = hm;
+    if (qsoft_out) qsoft_out[i] = qsoft;
+    if (qhard_out) qhard_out[i] = qhard;
+    // qbar = qsoft + stop_gradient(qhard - qsoft)   (code/autoencoder.py:133)
+    if (qbar_out) qbar_out[i] = __fadd_rn(qsoft, __fsub_rn(qhard, qsoft));
+    if (sym_out) sym_out[i] = sym;
+    if (sym8_out) sym8_out[i] = (uint8_t)sym;
+}
+
+__global__ void quantize_kernel(const float* __restrict__ x, const float* __restrict__ centers, int L, float sigma,
+                                int64_t n, float* __restrict__ qsoft_out, float* __restrict__ qhard_out,
+                                int64_t* __restrict__ sym_out) {
+    __shared__ float sc[kMaxL];
+    if (threadIdx.x < L) sc[threadIdx.x] = centers[threadIdx.x];
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float qsoft, qhard;
+    int sym;
+    quantize_one<kMaxL>(x[i], sc, L, sigma, qsoft, qhard, sym);
+    if (qsoft_out) qsoft_out[i] = qsoft;
+    if (qhard_out) qhard_out[i] = qhard;
+    if (sym_out) sym_out[i] = sym;
+}
+
+}  // namespace
+
+int launch_prep_input(const void* x, int is_u8, int N, int H, int W, int normalize, float* out_nhwc4,
+                      cudaStream_t s) {
+    int64_t hw = (int64_t)H * W, total = hw * N;
+    int nb = cdiv(total, 256);
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    if (is_u8)
+        prep_input_kernel<uint8_t><<<nb, 256, 0, s>>>((const uint8_t*)x, hw, total, normalize, (float4*)out_nhwc4);
+    else
+        prep_input_kernel<float><<<nb, 256, 0, s>>>((const float*)x, hw, total, normalize, (float4*)out_nhwc4);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int launch_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, cudaStream_t s) {
+    int64_t hw = (int64_t)H * W, total = hw * N * C;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, C, hw, total, out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int launch_heatmap_quantize(const float* bn_nhwc, int N, int h, int w, int C, int heatmap, const float* centers,
+                            int L, float* z, float* hm, float* qbar, float* qhard, int64_t* sym, uint8_t* sym8,
+                            float* qsoft, cudaStream_t s) {
+    IC_REQUIRE(L <= kMaxL, IC_ERR_UNSUPPORTED, "num_centers %d > %d", L, kMaxL);
+    int64_t total = (int64_t)N * C * h * w;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    heatmap_quantize_kernel<<<cdiv(total, 256), 256, 0, s>>>(bn_nhwc, h, w, C, heatmap, centers, L, total, z, hm,
+                                                             qbar, qhard, sym, sym8, qsoft);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int launch_quantize(const float* x, const float* centers, int L, float sigma, int64_t n, float* qsoft,
+                    float* qhard, int64_t* sym, cudaStream_t s) {
+    IC_REQUIRE(L <= kMaxL, IC_ERR_UNSUPPORTED, "num_centers %d > %d", L, kMaxL);
+    if (n == 0) return IC_OK;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    quantize_kernel<<<cdiv(n, 256), 256, 0, s>>>(x, centers, L, sigma, n, qsoft, qhard, sym);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+}  // namespace ic

@@ -1,0 +1,338 @@
+// Multi-scale SSIM, both variants of the reference:
+//   * ic_msssim_tf_fwd : code/ms_ssim.py:16-186 (float32, one scalar per batch, the training loss)
+//   * ic_msssim_np_fwd : code/ms_ssim_np.py:51-200 (float64 on uint8, one value per image, val.py:93)
+// Per level one fused kernel: separable Gaussian blur (VALID) of x, y, x*x, y*y, x*y
+// in shared memory -> ssim / cs maps -> block partial sums (double); a 2x2 box
+// downsample kernel feeds the next level.  All reductions are deterministic
+// (fixed-order partial sums, no atomics).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ic {
+
+namespace {
+
+constexpr int TW = 16, TH = 16, MAXK = 11;
+
+template <typename T>
+struct LevelParams {
+    int H, W;          // plane size at this level
+    int K;             // taps
+    int p1, p2;        // REFLECT padding before/after on both axes (tf variant), 0 for np
+    int Ho, Wo;        // VALID output size
+    T taps[MAXK];
+    T c1, c2;
+};
+
+__device__ __forceinline__ int reflect_idx(int u, int n) {   // tf.pad REFLECT (no edge repeat)
+    if (u < 0) u = -u;
+    if (u >= n) u = 2 * (n - 1) - u;
+    return u;
+}
+
+template <typename T, typename TIn>
+__global__ void __launch_bounds__(TW* TH) ssim_level_kernel(const TIn* __restrict__ a, const TIn* __restrict__ b,
+                                                            LevelParams<T> p, double* __restrict__ partial) {
+    __shared__ T sx[TH + MAXK - 1][TW + MAXK - 1];
+    __shared__ T sy[TH + MAXK - 1][TW + MAXK - 1];
+    __shared__ T hq[5][TH + MAXK - 1][TW];
+    __shared__ double red[2][TW * TH / 32];
+
+    const int plane = blockIdx.z;
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+    const int tid = threadIdx.y * TW + threadIdx.x;
+    const TIn* pa = a + (int64_t)plane * p.H * p.W;
+    const TIn* pb = b + (int64_t)plane * p.H * p.W;
+    const int rows = TH + p.K - 1, cols = TW + p.K - 1;
+    for (int i = tid; i < rows * cols; i += TW * TH) {
+        int r = i / cols, c = i - r * cols;
+        int uy = oy0 + r, ux = ox0 + c;             // padded coordinates
+        T vx = 0, vy = 0;
+        if (uy < p.H + p.p1 + p.p2 && ux < p.W + p.p1 + p.p2) {
+            int yy = reflect_idx(uy - p.p1, p.H), xx = reflect_idx(ux - p.p1, p.W);
+            vx = (T)pa[(int64_t)yy * p.W + xx];
+            vy = (T)pb[(int64_t)yy * p.W + xx];
+        }
+        sx[r][c] = vx;
+        sy[r][c] = vy;
+    }
+    __syncthreads();
+    for (int i = tid; i < rows * TW; i += TW * TH) {
+        int r = i / TW, c = i - r * TW;
+        T h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+        for (int t = 0; t < p.K; ++t) {
+            T x = sx[r][c + t], y = sy[r][c + t], k = p.taps[t];
+            T xx = x * x, yy = y * y, xy = x * y;   // img1*img1 etc. are materialised in the reference
+            h0 += x * k;
+            h1 += y * k;
+            h2 += xx * k;
+            h3 += yy * k;
+            h4 += xy * k;
+        }
+        hq[0][r][c] = h0;
+        hq[1][r][c] = h1;
+        hq[2][r][c] = h2;
+        hq[3][r][c] = h3;
+        hq[4][r][c] = h4;
+    }
+    __syncthreads();
+    double s_ssim = 0.0, s_cs = 0.0;
+    const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x;
+    if (oy < p.Ho && ox < p.Wo) {
+        T mu1 = 0, mu2 = 0, s11 = 0, s22 = 0, s12 = 0;
+        for (int t = 0; t < p.K; ++t) {
+            T k = p.taps[t];
+            mu1 += hq[0][threadIdx.y + t][threadIdx.x] * k;
+            mu2 += hq[1][threadIdx.y + t][threadIdx.x] * k;
+            s11 += hq[2][threadIdx.y + t][threadIdx.x] * k;
+            s22 += hq[3][threadIdx.y + t][threadIdx.x] * k;
+            s12 += hq[4][threadIdx.y + t][threadIdx.x] * k;
+        }
+        T mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
+        s11 -= mu11;
+        s22 -= mu22;
+        s12 -= mu12;
+        T v1 = (T)2.0 * s12 + p.c2;
+        T v2 = s11 + s22 + p.c2;
+        T ssim = (((T)2.0 * mu12 + p.c1) * v1) / ((mu11 + mu22 + p.c1) * v2);
+        T cs = v1 / v2;
+        s_ssim = (double)ssim;
+        s_cs = (double)cs;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s_ssim += __shfl_down_sync(0xffffffffu, s_ssim, o);
+        s_cs += __shfl_down_sync(0xffffffffu, s_cs, o);
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = s_ssim;
+        red[1][tid >> 5] = s_cs;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a0 = 0, a1 = 0;
+        for (int i = 0; i < TW * TH / 32; ++i) {
+            a0 += red[0][i];
+            a1 += red[1][i];
+        }
+        int64_t blk = ((int64_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partial[2 * blk] = a0;
+        partial[2 * blk + 1] = a1;
+    }
+}
+
+// sums the block partials of `planes_per_group` consecutive planes in fixed order
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int blocks_per_plane, int planes_per_group,
+                                       double inv_count, double* __restrict__ out /* [groups][2] */) {
+    __shared__ double r0[256], r1[256];
+    const int g = blockIdx.x;
+    const int64_t n = (int64_t)blocks_per_plane * planes_per_group;
+    const double* p = partial + 2 * (int64_t)g * n;
+    double a0 = 0, a1 = 0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
+        a0 += p[2 * i];
+        a1 += p[2 * i + 1];
+    }
+    r0[threadIdx.x] = a0;
+    r1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            r0[threadIdx.x] += r0[threadIdx.x + s];
+            r1[threadIdx.x] += r1[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[2 * g] = r0[0] * inv_count;
+        out[2 * g + 1] = r1[0] * inv_count;
+    }
+}
+
+// 2x2 box downsample.
+//   tf: kernel_blur(pad=True) REFLECT pad (0,1) + [.5,.5] separable + [::2, ::2]  (code/ms_ssim.py:46-64,179-181)
+//   np: ndimage.convolve(ones(2,2)/4, mode='reflect')[::2, ::2]                    (code/ms_ssim_np.py:96,106-108)
+template <typename T, typename TIn, bool TF>
+__global__ void downsample_kernel(const TIn* __restrict__ in, int H, int W, int Hd, int Wd, int64_t total,
+                                  T* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int x = (int)(i % Wd);
+    int64_t r = i / Wd;
+    int y = (int)(r % Hd);
+    int64_t plane = r / Hd;
+    const TIn* p = in + plane * H * W;
+    int y0 = 2 * y, x0 = 2 * x;
+    int y1 = y0 + 1, x1 = x0 + 1;
+    if (TF) {
+        if (y1 >= H) y1 = H - 2;    // REFLECT
+        if (x1 >= W) x1 = W - 2;
+    } else {
+        if (y1 >= H) y1 = H - 1;    // scipy 'reflect' duplicates the edge sample
+        if (x1 >= W) x1 = W - 1;
+    }
+    T a = (T)p[(int64_t)y0 * W + x0], b = (T)p[(int64_t)y0 * W + x1];
+    T c = (T)p[(int64_t)y1 * W + x0], d = (T)p[(int64_t)y1 * W + x1];
+    if (TF) {
+        T h0 = (T)0.5 * a + (T)0.5 * b, h1 = (T)0.5 * c + (T)0.5 * d;
+        out[i] = (T)0.5 * h0 + (T)0.5 * h1;
+    } else {
+        out[i] = (a + c + b + d) / (T)4.0;
+    }
+}
+
+__global__ void combine_tf_kernel(const double* __restrict__ lv /* [5][2] */, float* out, float* levels) {
+    if (threadIdx.x != 0) return;
+    const float w[5] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
+    float prod = 1.f;
+    for (int l = 0; l < 4; ++l) prod *= powf((float)lv[2 * l + 1], w[l]);
+    out[0] = prod * powf((float)lv[2 * 4], w[4]);
+    if (levels)
+        for (int l = 0; l < 5; ++l) {
+            levels[l] = (float)lv[2 * l];
+            levels[5 + l] = (float)lv[2 * l + 1];
+        }
+}
+
+__global__ void combine_np_kernel(const double* __restrict__ lv /* [5][N][2] */, int N, double* out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const double w[5] = {0.0448, 0.2856, 0.3001, 0.2363, 0.1333};
+    double prod = 1.0;
+    for (int l = 0; l < 4; ++l) prod *= pow(lv[((int64_t)l * N + n) * 2 + 1], w[l]);
+    out[n] = prod * pow(lv[((int64_t)4 * N + n) * 2], w[4]);
+}
+
+template <typename T>
+int fill_level(LevelParams<T>& p, int H, int W, bool tf) {
+    p.H = H;
+    p.W = W;
+    const int size = std::min(11, std::min(H, W));
+    const double sigma = size * 1.5 / 11;
+    double g[MAXK];
+    double sum = 0;
+    if (tf) {   // ms_ssim.gauss_kernel: 2*(size//2)+1 taps (code/ms_ssim.py:5-13)
+        const int n = size / 2;
+        p.K = 2 * n + 1;
+        for (int i = 0; i < p.K; ++i) {
+            double x = i - n;
+            g[i] = exp(-x * x / (2 * sigma * sigma));
+            sum += fabs(g[i]);
+        }
+        // gaussian_blur pads by the W-derived amount on BOTH axes; "total_pad + 1 // 2" (code/ms_ssim.py:24-29)
+        int total_pad = std::max(p.K - W, 0);
+        p.p1 = total_pad + 1 / 2;
+        p.p2 = total_pad / 2;
+    } else {    // _FSpecialGauss, `size` taps, half-sample offset when even (code/ms_ssim_np.py:113-124)
+        p.K = size;
+        const double off = (size % 2 == 0) ? 0.5 : 0.0;
+        for (int i = 0; i < p.K; ++i) {
+            double x = off - size / 2 + i;
+            g[i] = exp(-(x * x) / (2.0 * sigma * sigma));
+            sum += g[i];
+        }
+        p.p1 = p.p2 = 0;
+    }
+    for (int i = 0; i < p.K; ++i) p.taps[i] = (T)(g[i] / sum);
+    p.Ho = H + p.p1 + p.p2 - p.K + 1;
+    p.Wo = W + p.p1 + p.p2 - p.K + 1;
+    p.c1 = (T)((0.01 * 255) * (0.01 * 255));
+    p.c2 = (T)((0.03 * 255) * (0.03 * 255));
+    if (p.Ho <= 0 || p.Wo <= 0 || p.p1 >= H || p.p1 >= W) return IC_ERR_INVALID;
+    return IC_OK;
+}
+
+template <typename T, typename TIn, bool TF>
+int run_msssim(const TIn* img1, const TIn* img2, int N, int H, int W, void* ws, size_t ws_bytes, double* lv_out,
+               cudaStream_t s) {
+    const int P = N * 3;
+    Arena ar(ws, ws_bytes);
+    // level buffers (levels 1..4), both images
+    T* bufA[5] = {nullptr};
+    T* bufB[5] = {nullptr};
+    int hs[5], wsz[5];
+    hs[0] = H;
+    wsz[0] = W;
+    for (int l = 1; l < 5; ++l) {
+        hs[l] = (hs[l - 1] + 1) / 2;
+        wsz[l] = (wsz[l - 1] + 1) / 2;
+        bufA[l] = ar.get<T>((size_t)P * hs[l] * wsz[l]);
+        bufB[l] = ar.get<T>((size_t)P * hs[l] * wsz[l]);
+    }
+    size_t max_blocks = (size_t)P * cdiv(H, TH) * cdiv(W, TW);
+    double* partial = ar.get<double>(2 * max_blocks);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ms-ssim workspace too small: need %zu, have %zu", ar.off, ws_bytes);
+    const int groups = TF ? 1 : N;
+    ProfScope ps(IC_PROF_MSSSIM, s, 5 * 2 + 4 * 2 + 1);
+    for (int l = 0; l < 5; ++l) {
+        LevelParams<T> p;
+        int rc = fill_level<T>(p, hs[l], wsz[l], TF);
+        IC_REQUIRE(rc == IC_OK, IC_ERR_INVALID,
+                   "ms-ssim: level %d is %dx%d, too small for the %d-tap blur (the reference raises here)", l, hs[l],
+                   wsz[l], p.K);
+        dim3 grid(cdiv(p.Wo, TW), cdiv(p.Ho, TH), P), block(TW, TH);
+        if (l == 0)
+            ssim_level_kernel<T, TIn><<<grid, block, 0, s>>>(img1, img2, p, partial);
+        else
+            ssim_level_kernel<T, T><<<grid, block, 0, s>>>(bufA[l], bufB[l], p, partial);
+        IC_CHECK_LAUNCH();
+        int bpp = grid.x * grid.y;
+        double inv = 1.0 / ((double)p.Ho * p.Wo * (TF ? P : 3));
+        reduce_partials_kernel<<<groups, 256, 0, s>>>(partial, bpp, TF ? P : 3, inv, lv_out + (size_t)l * groups * 2);
+        IC_CHECK_LAUNCH();
+        if (l < 4) {
+            int64_t total = (int64_t)P * hs[l + 1] * wsz[l + 1];
+            if (TF) IC_REQUIRE(hs[l] >= 2 && wsz[l] >= 2, IC_ERR_INVALID, "ms-ssim: cannot REFLECT-pad a %dx%d level", hs[l], wsz[l]);
+            if (l == 0) {
+                downsample_kernel<T, TIn, TF><<<cdiv(total, 256), 256, 0, s>>>(img1, hs[l], wsz[l], hs[l + 1], wsz[l + 1], total, bufA[l + 1]);
+                downsample_kernel<T, TIn, TF><<<cdiv(total, 256), 256, 0, s>>>(img2, hs[l], wsz[l], hs[l + 1], wsz[l + 1], total, bufB[l + 1]);
+            } else {
+                downsample_kernel<T, T, TF><<<cdiv(total, 256), 256, 0, s>>>(bufA[l], hs[l], wsz[l], hs[l + 1], wsz[l + 1], total, bufA[l + 1]);
+                downsample_kernel<T, T, TF><<<cdiv(total, 256), 256, 0, s>>>(bufB[l], hs[l], wsz[l], hs[l + 1], wsz[l + 1], total, bufB[l + 1]);
+            }
+            IC_CHECK_LAUNCH();
+        }
+    }
+    return IC_OK;
+}
+
+}  // namespace
+
+size_t msssim_workspace_bytes(int N, int H, int W, int is_double) {
+    size_t e = is_double ? 8 : 4;
+    size_t b = 0;
+    int h = H, w = W;
+    for (int l = 1; l < 5; ++l) {
+        h = (h + 1) / 2;
+        w = (w + 1) / 2;
+        b += 2 * (align_up((size_t)N * 3 * h * w * e, 256) + 256);
+    }
+    b += 2 * sizeof(double) * (size_t)N * 3 * cdiv(H, TH) * cdiv(W, TW) + 256;
+    b += sizeof(double) * 2 * 5 * (size_t)std::max(N, 1) + 256;
+    return b + 1024;
+}
+
+int msssim_tf(const float* a, const float* b, int N, int H, int W, float* out, float* levels, void* ws,
+              size_t ws_bytes, cudaStream_t s) {
+    IC_REQUIRE(ws_bytes >= 256, IC_ERR_WORKSPACE, "ms-ssim workspace too small");
+    double* lv = (double*)ws;    // first 256 B: level means
+    int rc = run_msssim<float, float, true>(a, b, N, H, W, (char*)ws + 256, ws_bytes - 256, lv, s);
+    if (rc != IC_OK) return rc;
+    combine_tf_kernel<<<1, 32, 0, s>>>(lv, out, levels);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int msssim_np(const uint8_t* a, const uint8_t* b, int N, int H, int W, double* out, void* ws, size_t ws_bytes,
+              cudaStream_t s) {
+    size_t lvb = align_up(sizeof(double) * 10 * (size_t)N, 256);
+    IC_REQUIRE(ws_bytes >= lvb, IC_ERR_WORKSPACE, "ms-ssim workspace too small");
+    double* lv = (double*)ws;
+    int rc = run_msssim<double, uint8_t, false>(a, b, N, H, W, (char*)ws + lvb, ws_bytes - lvb, lv, s);
+    if (rc != IC_OK) return rc;
+    combine_np_kernel<<<cdiv(N, 128), 128, 0, s>>>(lv, N, out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+}  // namespace ic

@@ -1,0 +1,32 @@
+// Internal interface of the context-model kernels (probclass.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ic {
+
+// Device weights, masked taps only, raster (fd,fy,fx) tap order:
+//   w0 [13][K]      first mask (code/probclass.py:150-162), Cin = 1
+//   w1,w2 [14][K][K] other mask (code/probclass.py:164-176)
+//   w3 [14][K][L]
+struct PcWeights {
+    int K, L;
+    const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3;
+};
+
+struct PcInput {
+    int N, D, H, W;              // un-padded volume
+    int pad_d, pad_hw;           // 4,4 for bitcost/freqs (pad_for_probclass3d), 0,0 for logits()
+    const float* q;              // float source (N,D,H,W) or nullptr
+    float pad_value;
+    const int64_t* symbols;      // symbol source (gathered through centers) or nullptr
+    float centers_host[8];
+    const int64_t* target_symbols;   // for the bitcost / freqs heads (N,D,H,W)
+};
+
+enum { PC_HEAD_LOGITS = 0, PC_HEAD_BITCOST = 1, PC_HEAD_FREQS = 2 };
+
+size_t pc_workspace_bytes(int KC, int N, int D, int H, int W, int pad_d, int pad_hw);
+int pc_forward(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs,
+               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s);
+
+}  // namespace ic

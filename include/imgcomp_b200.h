@@ -1,0 +1,205 @@
+/*
+ * imgcomp_b200 -- C ABI of the B200-native hot path of fab-jul/imgcomp-cvpr.
+ *
+ * The reference has no FFI: its boundary is the Python object API that
+ * code/val.py and code/train.py call while building a TF graph.
+ * Each entry point below replaces the *execution* of one of those calls; the
+ * Python mirror classes in imgcomp_cvpr_b200/ keep the reference's names and
+ * argument order and forward to these functions through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ic_status otherwise;
+ *     ic_last_error() gives a thread-local message.
+ *   - pointers named d_* are DEVICE pointers (owned by the caller, e.g. torch
+ *     tensors), h_* are HOST pointers.  No torch / C++ types cross the boundary.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises unless stated.
+ *   - layouts at the boundary are the reference's: images / latents NCHW
+ *     float32, symbols int64, conv2d weights HWIO, conv2d_transpose weights
+ *     [kh,kw,Cout,Cin], conv3d weights [D,H,W,in,out].
+ *   - handles own only the (re-laid-out) weights; activations live in a caller
+ *     provided workspace sized by the matching *_workspace_bytes().
+ *   - handles are immutable after creation: any number of threads/streams may
+ *     use one handle concurrently with distinct workspaces.
+ */
+#ifndef IMGCOMP_B200_H_
+#define IMGCOMP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IC_ABI_VERSION 1
+
+typedef enum {
+    IC_OK = 0,
+    IC_ERR_INVALID = -1,     /* bad argument (shape, dtype, NULL, not multiple of 8 ...) */
+    IC_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+    IC_ERR_WORKSPACE = -3,   /* workspace too small */
+    IC_ERR_UNSUPPORTED = -4, /* configuration outside the hot path (arch, kernel size ...) */
+    IC_ERR_STATE = -5        /* call order violated (e.g. decoder not fed) */
+} ic_status;
+
+/* Precision mode of the tensor-core convolutions (ic_encode_fwd/ic_decode_fwd):
+ *   IC_MODE_FP32   plain float32 FFMA kernels (reference arithmetic class)
+ *   IC_MODE_EXACT  tcgen05 fp16 x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate):
+ *                  float32-class results, the mode the parity gate runs in
+ *   IC_MODE_FAST   tcgen05 single fp16 pass (reported with its symbol flip rate) */
+typedef enum { IC_MODE_FP32 = 0, IC_MODE_EXACT = 1, IC_MODE_FAST = 2 } ic_mode;
+
+const char* ic_last_error(void);
+int ic_abi_version(void);
+/* 1 if a CUDA device with compute capability 10.x is usable from this process. */
+int ic_device_ok(void);
+
+/* ------------------------------------------------------------------ autoencoder
+ * replaces: autoencoder.get_network_cls(config)(config)      code/autoencoder.py:26-43
+ * config attributes used by the reference: arch, num_chan_bn, heatmap,
+ * normalization, arch_param_B, num_centers (code/autoencoder.py:32-43,218-268). */
+typedef struct ic_ae ic_ae_t;
+
+typedef struct {
+    int32_t num_chan_bn;      /* C: 32 (cvpr/low, med) or 64 (cvpr/hi) */
+    int32_t arch_param_B;     /* 5 */
+    int32_t num_centers;      /* L = 6 */
+    int32_t heatmap;          /* 1 (ae_configs/base:5) */
+    int32_t normalization;    /* 1 = FIXED, 0 = OFF (ae_configs/base:3-4) */
+} ic_ae_config;
+
+/* Weight tensors are passed as an array of host pointers in a fixed order;
+ * ic_ae_tensor_name(i) is the TF variable name of entry i,
+ * ic_ae_tensor_numel(i) its element count.  i in [0, ic_ae_num_tensors). */
+int ic_ae_num_tensors(const ic_ae_config* cfg);
+const char* ic_ae_tensor_name(const ic_ae_config* cfg, int i);
+int64_t ic_ae_tensor_numel(const ic_ae_config* cfg, int i);
+int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_tensors, ic_ae_t** out);
+void ic_ae_destroy(ic_ae_t* ae);
+
+/* replaces: ae.encode(x, is_training=False) -> EncoderOutput(qbar,qhard,symbols,z,heatmap)
+ *           code/autoencoder.py:50-58,218-244 (+ quantizer.py:37-95 inside)
+ * d_x: N x 3 x H x W, float32 in [0,255] (x_is_u8 = 0) or uint8 (x_is_u8 = 1; the
+ *      tf.to_float of val.py:83 is fused).  H, W multiples of 8 (val.py:157 pads).
+ * outputs N x C x H/8 x W/8; any output pointer may be NULL to skip it.
+ * d_symbols_u8 is an extra compact copy of `symbols` for the context model. */
+size_t ic_encode_workspace_bytes(const ic_ae_t* ae, int N, int H, int W, int mode);
+int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H, int W,
+                  float* d_z, float* d_heatmap, float* d_qbar, float* d_qhard,
+                  int64_t* d_symbols, uint8_t* d_symbols_u8, float* d_qsoft,
+                  void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* replaces: ae.decode(q, is_training=False) -> x_out      code/autoencoder.py:60-63,246-268
+ * d_q: N x C x h x w float32; d_x_out: N x 3 x 8h x 8w float32, clipped to [0,255];
+ * d_x_out_u8 (optional): tf.cast(x_out, uint8) of val.py:91 (truncation). */
+size_t ic_decode_workspace_bytes(const ic_ae_t* ae, int N, int h, int w, int mode);
+int ic_decode_fwd(const ic_ae_t* ae, const float* d_q, int N, int h, int w,
+                  float* d_x_out, uint8_t* d_x_out_u8,
+                  void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* The centres variable, copied to a device buffer of num_centers floats
+ * (ae.get_centers_variable(), code/autoencoder.py:65-68). */
+int ic_ae_centers(const ic_ae_t* ae, float* d_centers, void* stream);
+
+/* replaces: quantizer.quantize(x, centers, sigma) -> (qsoft, qhard, symbols)
+ *           code/quantizer.py:37-95.  Elementwise over n values; layout-agnostic. */
+int ic_quantize_fwd(const float* d_x, const float* d_centers, int L, float sigma, int64_t n,
+                    float* d_qsoft, float* d_qhard, int64_t* d_symbols, void* stream);
+
+/* ------------------------------------------------------------------- probclass
+ * replaces: probclass.get_network_cls(pc_config)(pc_config, num_centers)
+ *           code/probclass.py:11-15,30-41 ('res_shallow', kernel_size 3). */
+typedef struct ic_pc ic_pc_t;
+
+typedef struct {
+    int32_t kernel_size;      /* 3 (pc_configs/cvpr/res_shallow:4) */
+    int32_t arch_param_k;     /* 24 (pc_configs/base:19) or 64 */
+    int32_t num_centers;      /* L = 6 */
+} ic_pc_config;
+
+int ic_pc_num_tensors(const ic_pc_config* cfg);                 /* 8: 4 x (weights, biases) */
+const char* ic_pc_tensor_name(const ic_pc_config* cfg, int i);
+int64_t ic_pc_tensor_numel(const ic_pc_config* cfg, int i);
+int ic_pc_create(const ic_pc_config* cfg, const float* const* h_tensors, int n_tensors, ic_pc_t** out);
+void ic_pc_destroy(ic_pc_t* pc);
+
+/* replaces: pc.bitcost(q, target_symbols, is_training=False, pad_value)   code/probclass.py:63-106
+ * d_q N x C x h x w float32, d_symbols int64 (same shape) -> d_bits float32 (same shape).
+ * d_bits_sum (optional, N doubles): per-image sum of bits (feeds bits.bitcost_to_bpp,
+ * code/bits.py:4-14). */
+size_t ic_pc_workspace_bytes(const ic_pc_t* pc, int N, int D, int H, int W);  /* D,H,W of the q volume */
+int ic_pc_bitcost_fwd(const ic_pc_t* pc, const float* d_q, const int64_t* d_symbols, float pad_value,
+                      int N, int C, int h, int w, float* d_bits, double* d_bits_sum,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: pc.logits(q, is_training=False) on an UN-padded N x D x H x W (x1) volume
+ *           code/probclass.py:130-135 -> N x (D-4) x (H-8) x (W-8) x L float32. */
+int ic_pc_logits_fwd(const ic_pc_t* pc, const float* d_q, int N, int D, int H, int W, float* d_logits,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* replaces the per-symbol loop of probclass.PredictionNetwork.get_freqs
+ *           (code/probclass.py:441-476, driven by code/bit_counter.py:103-134):
+ * ONE batched pass: symbols (N x C x h x w, int64) are padded with symbol 0,
+ * gathered through `centers`, run through the context model; output
+ * N x C x h x w x L int64 = max(int64(softmax * 1e9), 1) in the coder's raster order.
+ * d_bits_sum (optional, N doubles) = sum -log2 p[symbol] (ProbclassNetworkTesting,
+ * code/probclass.py:393-421). */
+int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_centers,
+                    int N, int C, int h, int w, int64_t* d_freqs, double* d_bits_sum,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------- MS-SSIM
+ * replaces: ms_ssim.MultiScaleSSIM(img1, img2, data_format='NCHW')   code/ms_ssim.py:115-186
+ * float32, ONE scalar for the batch.  d_out: 1 float; d_levels (optional): 10 floats
+ * = ssim_l (5) then cs_l (5).  Returns IC_ERR_INVALID where the reference raises
+ * (a level whose height is below the blur's tap count, code/ms_ssim.py:24-29). */
+size_t ic_msssim_workspace_bytes(int N, int H, int W, int is_double);
+int ic_msssim_tf_fwd(const float* d_img1, const float* d_img2, int N, int H, int W,
+                     float* d_out, float* d_levels,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: ms_ssim_np.MultiScaleSSIM on uint8 (through tf_msssim_np, val.py:93)
+ *           code/ms_ssim_np.py:25-110.  float64, one value PER IMAGE (d_out: N doubles). */
+int ic_msssim_np_fwd(const uint8_t* d_img1, const uint8_t* d_img2, int N, int H, int W,
+                     double* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------- launch accounting
+ * Not part of the reference's surface: lets bench.py count this library's kernel
+ * launches (`gpu_launches`) and time one kernel class live with CUDA events on the
+ * launching stream (`roofline.achieved`). */
+enum {
+    IC_PROF_CONV3X3 = 0,     /* the 3x3 128->128 residual convs (95 % of the FLOPs) */
+    IC_PROF_CONV_OTHER = 1,  /* h1, h2, to_bn, from_bn, h12, h13 */
+    IC_PROF_ELEMENTWISE = 2, /* input prep, heatmap+quantizer, layout changes */
+    IC_PROF_PROBCLASS = 3,
+    IC_PROF_MSSSIM = 4,
+    IC_PROF_NUM_CLASSES = 5
+};
+long long ic_launch_count(void);
+void ic_profile_enable(int on);
+void ic_profile_reset(void);
+int ic_profile_get(int cls, double* total_ms, long long* launches);
+
+/* ------------------------------------------------------ host arithmetic coder
+ * restates: arithmetic_coding.ArithmeticEncoder / ArithmeticDecoder with
+ * SimpleFrequencyTable (code/arithmetic_coding.py:39-222,323-424), 32-bit state.
+ * Pure host code (the north star keeps the coder on the host). */
+typedef struct ic_ac_enc ic_ac_enc_t;
+typedef struct ic_ac_dec ic_ac_dec_t;
+int ic_ac_enc_create(ic_ac_enc_t** out);
+/* write n symbols; h_freqs is n x L int64 (one table per symbol, as produced by ic_pc_freqs_fwd) */
+int ic_ac_enc_write(ic_ac_enc_t* e, const int64_t* h_freqs, int L, const int64_t* h_symbols, int64_t n);
+/* finish(): flushes like ArithmeticEncoder.finish + BitOutputStream.close; returns the byte
+ * stream (owned by the encoder until destroy) and the exact bit count before byte padding. */
+int ic_ac_enc_finish(ic_ac_enc_t* e, const uint8_t** h_bytes, int64_t* n_bytes, int64_t* n_bits);
+void ic_ac_enc_destroy(ic_ac_enc_t* e);
+int ic_ac_dec_create(const uint8_t* h_bytes, int64_t n_bytes, ic_ac_dec_t** out);
+/* decode n symbols with n tables (teacher-forced / pre-computed tables) */
+int ic_ac_dec_read(ic_ac_dec_t* d, const int64_t* h_freqs, int L, int64_t* h_symbols, int64_t n);
+void ic_ac_dec_destroy(ic_ac_dec_t* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMGCOMP_B200_H_ */

@@ -50,3 +50,22 @@ def symbol_margin(z64, centers):
     c = np.sort(centers.astype(np.float64))
     mids = (c[1:] + c[:-1]) / 2
     return np.abs(z64[..., None] - mids).min(axis=-1)
+
+
+@pytest.fixture(scope='session')
+def gpu_models(synth):
+    """(ae_name, mode) -> (ae, pc, weights) on cuda:0, cached."""
+    import torch
+    from imgcomp_cvpr_b200 import autoencoder, probclass
+    cache = {}
+
+    def get(ae_name='cvpr/low', mode='fp32', pc_name='cvpr/res_shallow'):
+        key = (ae_name, mode, pc_name)
+        if key not in cache:
+            a, p, W = synth(ae_name, pc_name)
+            ae = autoencoder.get_network_cls(a)(a, weights=W, mode=mode)
+            pc = probclass.get_network_cls(p)(p, num_centers=a.num_centers, weights=W)
+            cache[key] = (ae, pc, W)
+        return cache[key]
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return get

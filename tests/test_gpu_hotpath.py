@@ -1,0 +1,211 @@
+"""GPU parity tests of the hot path (run with -m gpu on the B200 box).
+
+Every check calls the product through its public host API, i.e. through the
+C ABI of libimgcomp_b200.so, and compares with
+  * the golden vectors produced by the reference's own modules (tests/golden), and
+  * the numpy oracle (oracle/imgcomp_oracle.py) on the same seeded inputs.
+Tolerances: symbols bit-exact wherever the float64 latent is further than
+EPS_MARGIN from a quantizer decision boundary (two float32 implementations of a
+34-layer conv stack differ by summation order), bpp and MS-SSIM
+within 1e-4 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden, symbol_margin
+from oracle import imgcomp_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS_MARGIN = 1e-4
+MODES = ['fp32']
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', sorted(GOLDEN_CASES))
+def test_val_graph_against_reference_goldens(name, mode, gpu_models):
+    """encode -> decode(qhard) -> bitcost(qbar) -> bpp / MS-SSIM, as code/val.py:81-94."""
+    from imgcomp_cvpr_b200 import bits, ms_ssim, ms_ssim_np
+    ae_name, _ = GOLDEN_CASES[name]
+    ae, pc, W = gpu_models(ae_name, mode)
+    g = load_golden(name)
+    x_u8 = _cuda(g['x_u8'])
+    enc = ae.encode(x_u8, is_training=False)
+    x_out = ae.decode(enc.qhard, is_training=False)
+    bc = pc.bitcost(enc.qbar, enc.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
+    sym = enc.symbols.cpu().numpy()
+    z = enc.z.cpu().numpy()
+    np.testing.assert_allclose(z, g['z'], atol=3e-4, rtol=0)
+    z64 = O.encode(g['x_u8'].astype(np.float64), W, ae.config.num_chan_bn, dtype=np.float64)['z']
+    safe = symbol_margin(z64, W['autoencoder/encoder/centers']) > EPS_MARGIN
+    assert (sym[safe] == g['symbols'][safe]).all(), 'symbol flipped away from a decision boundary'
+    mism = sym != g['symbols']
+    assert mism.mean() <= 2e-4, mism.sum()
+    same = ~mism
+    assert np.array_equal(enc.symbols.cpu().numpy(), ae.extra['symbols_u8'].cpu().numpy().astype(np.int64))
+    centers = W['autoencoder/encoder/centers']
+    assert np.array_equal(enc.qhard.cpu().numpy(), centers[sym])          # qhard = centers[symbols] exactly
+    np.testing.assert_allclose(enc.qbar.cpu().numpy()[same], g['qbar'][same], atol=1e-6)
+    if 'heatmap' in g:
+        np.testing.assert_allclose(enc.heatmap.cpu().numpy(), g['heatmap'], atol=2e-4)
+    np.testing.assert_allclose(bc.cpu().numpy()[same], g['bitcost'][same], atol=3e-3)
+    # per image bpp (val.py runs batch = 1)
+    for i in range(x_u8.shape[0]):
+        bpp = bits.bitcost_to_bpp(bc[i:i + 1], x_u8[i:i + 1]).item()
+        assert abs(bpp - g['bpp'][i]) < 1e-4
+        assert abs(pc.last_bits_per_image[i].item() / (x_u8.shape[2] * x_u8.shape[3]) - g['bpp'][i]) < 1e-4
+    if 'x_out' in g:
+        np.testing.assert_allclose(x_out.cpu().numpy(), g['x_out'], atol=1e-2)
+    x_out_u8 = ae.extra['x_out_u8']
+    assert (x_out_u8.cpu().numpy() != g['x_out_u8']).mean() < 2e-3
+    assert torch.equal(x_out_u8, x_out.to(torch.uint8))                   # tf.cast truncation (val.py:91)
+    ms = ms_ssim_np.MultiScaleSSIM_batch(x_u8, x_out_u8, data_format='NCHW').cpu().numpy()
+    np.testing.assert_allclose(ms, g['ms_ssim_np'], atol=1e-4)
+    if 'ms_ssim_tf_raises' in g:
+        with pytest.raises(RuntimeError):
+            ms_ssim.MultiScaleSSIM(x_u8.float(), x_out, data_format='NCHW')
+    else:
+        v = ms_ssim.MultiScaleSSIM(x_u8.float(), x_out, data_format='NCHW').item()
+        assert abs(v - float(g['ms_ssim_tf'])) < 1e-4
+
+
+def test_quantizer_bit_exact_on_identical_input(gpu_models):
+    """quantizer.quantize on the same z: symbols and qhard bit-exact incl. exact
+    midpoints (ties -> first index) and exact centres; qsoft to float32 rounding."""
+    from imgcomp_cvpr_b200 import quantizer
+    ae, pc, W = gpu_models('cvpr/low')
+    centers = W['autoencoder/encoder/centers']
+    g = load_golden('cfg1_low_1x128x128')
+    rng = np.random.RandomState(3)
+    cs = np.sort(centers)
+    mids = ((cs[1:] + cs[:-1]) / 2).astype(np.float32)
+    special = np.concatenate([centers, mids, np.nextafter(mids, np.float32(10)), np.nextafter(mids, np.float32(-10)),
+                              np.float32([0, -0.0, 5, -5, 1e-30, 100, -100])])
+    z = np.concatenate([g['z'].ravel(), rng.uniform(-2.5, 2.5, 100000).astype(np.float32), special.astype(np.float32)])
+    z = np.resize(z, (1, 4, 128, z.size // 512 + 1)).astype(np.float32)
+    qsoft, qhard, sym = quantizer.quantize(_cuda(z), _cuda(centers), sigma=1)
+    osoft, ohard, osym = O.quantize(z, centers, 1)
+    assert np.array_equal(sym.cpu().numpy(), osym)
+    assert np.array_equal(qhard.cpu().numpy(), ohard)
+    np.testing.assert_allclose(qsoft.cpu().numpy(), osoft, atol=5e-7)
+    with pytest.raises(AssertionError):
+        quantizer.quantize(_cuda(z).double(), _cuda(centers), 1)
+    with pytest.raises(AssertionError):
+        quantizer.quantize(_cuda(z)[0], _cuda(centers), 1)
+
+
+def test_probclass_batched_freqs_match_reference_loop_and_are_causal(gpu_models):
+    ae, pc, W = gpu_models('cvpr/low')
+    from imgcomp_cvpr_b200 import probclass
+    g = load_golden('tiny_low_1x64x64')
+    syms = g['symbols'][0].astype(np.int64)
+    centers = _cuda(W['autoencoder/encoder/centers'])
+    f, bits = pc.freqs(_cuda(syms)[None], centers)
+    f = f[0].cpu().numpy()
+    assert f.shape == g['freqs'].shape and f.min() >= 1
+    assert np.abs(f - g['freqs']).max() <= 256              # float32 exp ulps * 1e9
+    assert abs(bits.item() - float(g['theory_bits'])) < 0.5
+    # the per-context network of the reference (PredictionNetwork.get_freqs) is bit-identical
+    # to the batched pass at the same position
+    ae.encode(_cuda(g['x_u8']), False)
+    pred = probclass.PredictionNetwork(pc, pc.config, ae.get_centers_variable(), None)
+    sp = pred.pad_symbols_volume(syms)
+    assert pred.input_ctx_shape == (5, 9, 9)
+    for (c, y, x) in ((0, 0, 0), (0, 0, 1), (5, 3, 2), (31, 7, 7), (12, 0, 7), (31, 0, 0)):
+        fc = pred.get_freqs(sp[c:c + 5, y:y + 9, x:x + 9])
+        assert np.array_equal(fc, f[c, y, x]), (c, y, x)
+    # causality: tables before position p do not change when symbols at/after p change
+    rng = np.random.RandomState(0)
+    flat = syms.reshape(-1).copy()
+    p = flat.size // 2 + 13
+    flat[p:] = rng.randint(0, 6, flat.size - p)
+    f2, _ = pc.freqs(_cuda(flat.reshape(syms.shape))[None], centers)
+    f2 = f2[0].cpu().numpy().reshape(-1, 6)
+    assert np.array_equal(f2[:p + 1], f.reshape(-1, 6)[:p + 1])
+    assert not np.array_equal(f2[p + 1:], f.reshape(-1, 6)[p + 1:])
+
+
+def test_real_bpp_round_trip(gpu_models):
+    """--real_bpp (val.py:161-175): coded bits ~ theoretical bits ~ loss bpp; stream decodes."""
+    from imgcomp_cvpr_b200 import bit_counter, bpp_helpers, probclass
+    ae, pc, W = gpu_models('cvpr/low')
+    g = load_golden('tiny_low_1x64x64')
+    x = _cuda(g['x_u8'])
+    enc = ae.encode(x, False)
+    bc = pc.bitcost(enc.qbar, enc.symbols, False, pad_value=pc.auto_pad_value(ae))
+    pred = probclass.PredictionNetwork(pc, pc.config, ae.get_centers_variable(), None)
+    checker = probclass.ProbclassNetworkTesting(pc, ae, None)
+    fetcher = bpp_helpers.BppFetcher(pred, checker)
+    sym = enc.symbols.cpu().numpy()
+    num_pixels = bpp_helpers.num_pixels_in_image(g['x_u8'][0])
+    bpp_real, bpp_theory = fetcher.get_bpp(sym, num_pixels)
+    bpp_loss = bc.sum().item() / num_pixels
+    assert abs(bpp_theory - bpp_loss) < 1e-3                      # val.py:174
+    assert abs(bpp_real - bpp_theory) * num_pixels < 50           # bit_counter.py:51
+    if np.array_equal(sym[0], g['symbols'][0]):
+        assert abs(bpp_real * num_pixels - int(g['real_bits'])) <= 16
+
+
+def test_msssim_pairs(gpu_models):
+    from imgcomp_cvpr_b200 import ms_ssim, ms_ssim_np
+    g = load_golden('msssim_pairs')
+    for tag in 'abc':
+        x, y = _cuda(g['x_' + tag]), _cuda(g['y_' + tag])
+        v = ms_ssim_np.MultiScaleSSIM_batch(x, y).cpu().numpy()
+        np.testing.assert_allclose(v, g['np_' + tag], atol=1e-9)
+        t = ms_ssim.MultiScaleSSIM(x.float(), y.float(), data_format='NCHW').item()
+        assert abs(t - float(g['tf_' + tag])) < 2e-5
+        t2 = ms_ssim.MultiScaleSSIM(x.float().permute(0, 2, 3, 1), y.float().permute(0, 2, 3, 1)).item()
+        assert t2 == t
+    assert ms_ssim_np.tf_msssim_np(x, y, 'NCHW').dtype == torch.float32
+    with pytest.raises(RuntimeError):
+        ms_ssim.MultiScaleSSIM(x.float(), y.float()[:, :, :-8], data_format='NCHW')
+    with pytest.raises(RuntimeError):
+        ms_ssim.MultiScaleSSIM(x.float()[0], y.float()[0], data_format='NCHW')
+    # identical images -> exactly 1
+    assert abs(ms_ssim_np.MultiScaleSSIM_batch(x, x).item() - 1.0) < 1e-12
+
+
+def test_api_errors_mirror_reference(gpu_models, synth):
+    from imgcomp_cvpr_b200 import autoencoder, probclass
+    a, p, W = synth('cvpr/low')
+    ae = autoencoder.get_network_cls(a)(a, weights=W)
+    with pytest.raises(ValueError):
+        ae.get_centers_variable()                                  # autoencoder.py:66-67
+    x = torch.zeros((1, 3, 36, 64), dtype=torch.uint8, device='cuda')
+    with pytest.raises(ValueError):
+        ae.encode(x, False)                                        # not a multiple of 8
+    with pytest.raises(AssertionError):
+        ae.encode(x.double(), False)                               # autoencoder.py:51
+    with pytest.raises(RuntimeError):
+        autoencoder.get_network_cls(a)(a).encode(x[:, :, :32], False)     # no weights
+    pc = probclass.get_network_cls(p)(p, num_centers=6, weights=W)
+    with pytest.raises(AssertionError):
+        pc.logits(torch.zeros((1, 5, 9, 9, 1), device='cuda'))     # bitcost first (probclass.py:132)
+    assert ae.get_subsampling_factor() == 8
+    assert pc.get_context_size(p) == 9 and pc.get_context_shape(p) == (5, 9, 9)
+    with pytest.raises(KeyError):
+        autoencoder.get_network_cls(type('C', (), {'arch': 'TwoLayerNet'}))
+
+
+def test_batch_and_position_independence(gpu_models):
+    """Size-independent properties at a larger shape: an image encodes to the same bits
+    alone or inside a batch, runs are deterministic, and float32 vs uint8 input agree."""
+    from imgcomp_cvpr_b200 import weights as wm
+    ae, pc, W = gpu_models('cvpr/low')
+    x = _cuda(wm.synthetic_images(3, 96, 160, seed=5))
+    e_all = ae.encode(x, False)
+    sym_all, z_all = e_all.symbols.clone(), e_all.z.clone()
+    e1 = ae.encode(x[1:2].contiguous(), False)
+    assert torch.equal(e1.symbols, sym_all[1:2]) and torch.equal(e1.z, z_all[1:2])
+    e_f = ae.encode(x.float(), False)
+    assert torch.equal(e_f.symbols, sym_all) and torch.equal(e_f.z, z_all)
+    bc_all = pc.bitcost(e_f.qbar, e_f.symbols, False, pad_value=pc.auto_pad_value(ae)).clone()
+    bc1 = pc.bitcost(e1.qbar, e1.symbols, False, pad_value=pc.auto_pad_value(ae))
+    assert torch.equal(bc1, bc_all[1:2])
+    xo = ae.decode(e_f.qhard, False).clone()
+    assert torch.equal(ae.decode(e1.qhard, False), xo[1:2])
+    assert xo.min().item() >= 0 and xo.max().item() <= 255
