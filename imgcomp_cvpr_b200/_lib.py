@@ -61,6 +61,8 @@ SIGNATURES = {
     'ic_msssim_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'ic_msssim_tf_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_np_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_debug_conv3x3': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                 c_void_p, c_size_t, c_int, c_void_p]),
     'ic_launch_count': (c_longlong, []),
     'ic_profile_enable': (None, [c_int]),
     'ic_profile_reset': (None, []),

@@ -85,7 +85,9 @@ class _Network(object):
         ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
-            self._ws = {key: ws} if len(self._ws) > 4 else dict(self._ws, **{key: ws})
+            if len(self._ws) > 4:
+                self._ws.clear()
+            self._ws[key] = ws
         return ws
 
     # -- reference API -----------------------------------------------------

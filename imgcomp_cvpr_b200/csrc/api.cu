@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "probclass.cuh"
 
 namespace ic {
@@ -92,6 +93,10 @@ struct DevLayer {
     LayerSpec spec;
     int cin_pad, ldw;
     float *w = nullptr, *scale = nullptr, *shift = nullptr;
+    // tensor-core path (3x3 128->128 layers only): packed fp16 hi/lo weights and the BN scale
+    // divided by the power-of-two weight pre-scale
+    __half* w_tc = nullptr;
+    float* scale_tc = nullptr;
 };
 
 int upload(const std::vector<float>& h, float** d) {
@@ -195,6 +200,16 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
             int rc = upload(wm, &d.w);
             if (rc == IC_OK) rc = upload(sc, &d.scale);
             if (rc == IC_OK) rc = upload(sh, &d.shift);
+            if (rc == IC_OK && l.k == 3 && l.stride == 1 && !l.transposed && l.cin == 128 && l.cout == 128) {
+                std::vector<__half> packed;
+                float inv = 1.f;
+                tc::pack_weights_3x3(w, packed, &inv);
+                std::vector<float> sct(sc);
+                for (auto& v : sct) v *= inv;                 // exact: inv is a power of two
+                IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc, packed.size() * sizeof(__half)));
+                IC_CHECK_CUDA(cudaMemcpy(d.w_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                rc = upload(sct, &d.scale_tc);
+            }
             dst.push_back(d);
             if (rc != IC_OK) {
                 ic_ae_destroy(ae);
@@ -224,6 +239,8 @@ void ic_ae_destroy(ic_ae_t* ae) {
             cudaFree(l.w);
             cudaFree(l.scale);
             cudaFree(l.shift);
+            cudaFree(l.w_tc);
+            cudaFree(l.scale_tc);
         }
     cudaFree(ae->d_centers);
     delete ae;
@@ -275,8 +292,10 @@ ConvDesc make_desc(const DevLayer& L, const float* in, int N, int Hi, int Wi, fl
 
 // 15 residual blocks (+5 group skips) + final no-ReLU block + long skip
 // (code/autoencoder.py:224-234 / :252-262).  `layers` points at the first 3x3 conv.
-// pool: 5 trunk-sized buffers, pool[0] holds the input on entry.  Returns the output buffer.
-int run_res_stack(const DevLayer* layers, int B, int N, int H, int W, float* pool[5], float** result, cudaStream_t s) {
+// pool: 5 trunk-sized buffers, pool[0] holds the input on entry.  `conv(layer, in, out, res1, res2)`
+// launches one fused conv.  Returns the index of the output buffer.
+template <typename ConvFn>
+int run_res_stack(const DevLayer* layers, int B, ConvFn conv, int* result) {
     bool busy[5] = {true, false, false, false, false};
     auto grab = [&]() {
         for (int i = 0; i < 5; ++i)
@@ -293,15 +312,12 @@ int run_res_stack(const DevLayer* layers, int B, int N, int H, int W, float* poo
         const int rb = x;
         for (int i = 0; i < (final_block ? 1 : 3); ++i) {
             int t1 = grab();
-            ConvDesc d1 = make_desc(layers[li++], pool[x], N, H, W, pool[t1]);
-            int rc = launch_conv_simt(d1, s);
+            int rc = conv(layers[li++], x, t1, -1, -1);
             if (rc != IC_OK) return rc;
             int y = grab();
-            ConvDesc d2 = make_desc(layers[li++], pool[t1], N, H, W, pool[y]);
-            d2.res1 = pool[x];                                         // residual_block: x + residual_input
             const bool last = final_block || i == 2;
-            if (last) d2.res2 = pool[final_block ? r0 : rb];           // net = net + residual_input_{b,0}
-            rc = launch_conv_simt(d2, s);
+            // residual_block: x + residual_input ; then net = net + residual_input_{b,0}
+            rc = conv(layers[li++], t1, y, x, last ? (final_block ? r0 : rb) : -1);
             if (rc != IC_OK) return rc;
             busy[t1] = false;
             if (x != rb && x != r0) busy[x] = false;
@@ -309,8 +325,53 @@ int run_res_stack(const DevLayer* layers, int B, int N, int H, int W, float* poo
         }
         if (rb != r0 && rb != x) busy[rb] = false;
     }
-    *result = pool[x];
+    *result = x;
     return IC_OK;
+}
+
+int run_res_stack_simt(const DevLayer* layers, int B, int N, int H, int W, float* pool[5], float** result, cudaStream_t s) {
+    int idx = 0;
+    int rc = run_res_stack(layers, B, [&](const DevLayer& L, int in, int out, int r1, int r2) {
+        ConvDesc d = make_desc(L, pool[in], N, H, W, pool[out]);
+        d.res1 = r1 >= 0 ? pool[r1] : nullptr;
+        d.res2 = r2 >= 0 ? pool[r2] : nullptr;
+        return launch_conv_simt(d, s);
+    }, &idx);
+    *result = pool[idx];
+    return rc;
+}
+
+int conv_tc_layer(const DevLayer& L, const __half* in, __half* out, const __half* r1, const __half* r2, int N, int H, int W,
+                  bool exact, cudaStream_t s) {
+    tc::ConvTcArgs a;
+    a.in = in;
+    a.weights = L.w_tc;
+    a.scale = L.scale_tc;
+    a.shift = L.shift;
+    a.res1 = r1;
+    a.res2 = r2;
+    a.out = out;
+    a.N = N;
+    a.H = H;
+    a.W = W;
+    a.relu = L.spec.relu;
+    a.exact = exact;
+    return tc::launch_conv3x3_tc(a, s);
+}
+
+// tensor-core res stack: pool buffers hold fp16 hi/lo planes; f32_in (NHWC fp32) is split into
+// pool[0] first and the result is merged back into f32_out.
+int run_res_stack_tc(const DevLayer* layers, int B, int N, int H, int W, __half* pool[5], const float* f32_in,
+                     float* f32_out, bool exact, cudaStream_t s) {
+    int rc = tc::launch_split_from_nhwc(f32_in, N, H, W, pool[0], exact, s);
+    if (rc != IC_OK) return rc;
+    int idx = 0;
+    rc = run_res_stack(layers, B, [&](const DevLayer& L, int in, int out, int r1, int r2) {
+        return conv_tc_layer(L, pool[in], pool[out], r1 >= 0 ? pool[r1] : nullptr, r2 >= 0 ? pool[r2] : nullptr, N, H, W,
+                             exact, s);
+    }, &idx);
+    if (rc != IC_OK) return rc;
+    return tc::launch_merge_to_nhwc(pool[idx], N, H, W, f32_out, exact, s);
 }
 
 }  // namespace
@@ -319,13 +380,12 @@ extern "C" {
 
 size_t ic_encode_workspace_bytes(const ic_ae_t* ae, int N, int H, int W, int mode) {
     if (!ae || N <= 0 || H <= 0 || W <= 0) return 0;
-    (void)mode;
     const size_t n = N;
     const int CB = ae->cfg.heatmap ? ae->cfg.num_chan_bn + 1 : ae->cfg.num_chan_bn;
     size_t b = 0;
     b += align_up(n * H * W * 4 * 4, 256);
     b += align_up(n * (H / 2) * (W / 2) * 64 * 4, 256);
-    b += 5 * align_up(n * (H / 4) * (W / 4) * 128 * 4, 256);
+    b += (mode == IC_MODE_FP32 ? 5 : 7) * align_up(n * (H / 4) * (W / 4) * 128 * 4, 256);
     b += align_up(n * (H / 8) * (W / 8) * CB * 4, 256);
     return b + 4096;
 }
@@ -336,7 +396,7 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
     IC_REQUIRE(ae && d_x && d_workspace, IC_ERR_INVALID, "ic_encode_fwd: NULL argument");
     IC_REQUIRE(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, IC_ERR_INVALID,
                "ic_encode_fwd: N=%d H=%d W=%d; H and W must be positive multiples of the subsampling factor 8", N, H, W);
-    IC_REQUIRE(mode == IC_MODE_FP32, IC_ERR_UNSUPPORTED, "ic_encode_fwd: mode %d not available in this build", mode);
+    IC_REQUIRE(mode == IC_MODE_FP32 || mode == IC_MODE_EXACT || mode == IC_MODE_FAST, IC_ERR_INVALID, "ic_encode_fwd: bad mode %d", mode);
     cudaStream_t s = (cudaStream_t)stream;
     const ic_ae_config& c = ae->cfg;
     const int CB = c.heatmap ? c.num_chan_bn + 1 : c.num_chan_bn;
@@ -344,8 +404,8 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
     const size_t n = N;
     float* xin = ar.get<float>(n * H * W * 4);
     float* a1 = ar.get<float>(n * (H / 2) * (W / 2) * 64);
-    float* pool[5];
-    for (int i = 0; i < 5; ++i) pool[i] = ar.get<float>(n * (H / 4) * (W / 4) * 128);
+    float* pool[7];
+    for (int i = 0; i < (mode == IC_MODE_FP32 ? 5 : 7); ++i) pool[i] = ar.get<float>(n * (H / 4) * (W / 4) * 128);
     float* bn = ar.get<float>(n * (H / 8) * (W / 8) * CB);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_encode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
 
@@ -354,10 +414,19 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
     const DevLayer* L = ae->enc.data();
     rc = launch_conv_simt(make_desc(L[0], xin, N, H, W, a1), s);
     if (rc != IC_OK) return rc;
-    rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[0]), s);
-    if (rc != IC_OK) return rc;
     float* trunk = nullptr;
-    rc = run_res_stack(L + 2, c.arch_param_B, N, H / 4, W / 4, pool, &trunk, s);
+    if (mode == IC_MODE_FP32) {
+        rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[0]), s);
+        if (rc != IC_OK) return rc;
+        rc = run_res_stack_simt(L + 2, c.arch_param_B, N, H / 4, W / 4, pool, &trunk, s);
+    } else {
+        rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[5]), s);
+        if (rc != IC_OK) return rc;
+        __half* hp[5];
+        for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
+        trunk = pool[6];
+        rc = run_res_stack_tc(L + 2, c.arch_param_B, N, H / 4, W / 4, hp, pool[5], trunk, mode == IC_MODE_EXACT, s);
+    }
     if (rc != IC_OK) return rc;
     const DevLayer& tobn = ae->enc.back();
     rc = launch_conv_simt(make_desc(tobn, trunk, N, H / 4, W / 4, bn), s);
@@ -368,11 +437,10 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
 
 size_t ic_decode_workspace_bytes(const ic_ae_t* ae, int N, int h, int w, int mode) {
     if (!ae || N <= 0 || h <= 0 || w <= 0) return 0;
-    (void)mode;
     const size_t n = N;
     size_t b = 0;
     b += align_up(n * h * w * ae->cfg.num_chan_bn * 4, 256);
-    b += 5 * align_up(n * (2 * h) * (2 * w) * 128 * 4, 256);
+    b += (mode == IC_MODE_FP32 ? 5 : 7) * align_up(n * (2 * h) * (2 * w) * 128 * 4, 256);
     b += align_up(n * (4 * h) * (4 * w) * 64 * 4, 256);
     return b + 4096;
 }
@@ -381,23 +449,32 @@ int ic_decode_fwd(const ic_ae_t* ae, const float* d_q, int N, int h, int w, floa
                   void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
     IC_REQUIRE(ae && d_q && d_x_out && d_workspace, IC_ERR_INVALID, "ic_decode_fwd: NULL argument");
     IC_REQUIRE(N > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_decode_fwd: bad shape N=%d h=%d w=%d", N, h, w);
-    IC_REQUIRE(mode == IC_MODE_FP32, IC_ERR_UNSUPPORTED, "ic_decode_fwd: mode %d not available in this build", mode);
+    IC_REQUIRE(mode == IC_MODE_FP32 || mode == IC_MODE_EXACT || mode == IC_MODE_FAST, IC_ERR_INVALID, "ic_decode_fwd: bad mode %d", mode);
     cudaStream_t s = (cudaStream_t)stream;
     const ic_ae_config& c = ae->cfg;
     Arena ar(d_workspace, workspace_bytes);
     const size_t n = N;
     float* qn = ar.get<float>(n * h * w * c.num_chan_bn);
-    float* pool[5];
-    for (int i = 0; i < 5; ++i) pool[i] = ar.get<float>(n * (2 * h) * (2 * w) * 128);
+    float* pool[7];
+    for (int i = 0; i < (mode == IC_MODE_FP32 ? 5 : 7); ++i) pool[i] = ar.get<float>(n * (2 * h) * (2 * w) * 128);
     float* a12 = ar.get<float>(n * (4 * h) * (4 * w) * 64);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_decode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
     int rc = launch_nchw_to_nhwc(d_q, N, c.num_chan_bn, h, w, qn, s);
     if (rc != IC_OK) return rc;
     const DevLayer* L = ae->dec.data();
-    rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[0]), s);
-    if (rc != IC_OK) return rc;
     float* trunk = nullptr;
-    rc = run_res_stack(L + 1, c.arch_param_B, N, 2 * h, 2 * w, pool, &trunk, s);
+    if (mode == IC_MODE_FP32) {
+        rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[0]), s);
+        if (rc != IC_OK) return rc;
+        rc = run_res_stack_simt(L + 1, c.arch_param_B, N, 2 * h, 2 * w, pool, &trunk, s);
+    } else {
+        rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[5]), s);
+        if (rc != IC_OK) return rc;
+        __half* hp[5];
+        for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
+        trunk = pool[6];
+        rc = run_res_stack_tc(L + 1, c.arch_param_B, N, 2 * h, 2 * w, hp, pool[5], trunk, mode == IC_MODE_EXACT, s);
+    }
     if (rc != IC_OK) return rc;
     const size_t nl = ae->dec.size();
     rc = launch_conv_simt(make_desc(L[nl - 2], trunk, N, 2 * h, 2 * w, a12), s);
@@ -407,6 +484,39 @@ int ic_decode_fwd(const ic_ae_t* ae, const float* d_q, int N, int h, int w, floa
     d.denorm = c.normalization;
     d.out_u8 = d_x_out_u8;
     return launch_conv_simt(d, s);
+}
+
+// test hook: one fused 3x3 128->128 conv of the encoder (layer index into the 32 residual convs),
+// fp32 NHWC in / out, through the chosen path.  Workspace: 4 trunk-sized buffers.
+int ic_debug_conv3x3(const ic_ae_t* ae, int decoder, int layer, const float* d_in, const float* d_res1, const float* d_res2,
+                     int N, int H, int W, float* d_out, void* d_workspace, size_t workspace_bytes, int mode, void* stream) {
+    IC_REQUIRE(ae && d_in && d_out, IC_ERR_INVALID, "ic_debug_conv3x3: NULL argument");
+    const auto& layers = decoder ? ae->dec : ae->enc;
+    const int first = decoder ? 1 : 2;
+    IC_REQUIRE(layer >= 0 && first + layer < (int)layers.size() && layers[first + layer].w_tc, IC_ERR_INVALID,
+               "ic_debug_conv3x3: layer %d is not a 3x3 128->128 conv", layer);
+    const DevLayer& L = layers[first + layer];
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == IC_MODE_FP32) {
+        ConvDesc d = make_desc(L, d_in, N, H, W, d_out);
+        d.res1 = d_res1;
+        d.res2 = d_res2;
+        return launch_conv_simt(d, s);
+    }
+    const bool exact = mode == IC_MODE_EXACT;
+    Arena ar(d_workspace, workspace_bytes);
+    const size_t elems = (size_t)N * H * W * 128 * 2;
+    __half* bi = ar.get<__half>(elems);
+    __half* b1 = ar.get<__half>(elems);
+    __half* b2 = ar.get<__half>(elems);
+    __half* bo = ar.get<__half>(elems);
+    IC_REQUIRE(d_workspace && ar.ok(), IC_ERR_WORKSPACE, "ic_debug_conv3x3: workspace too small (need %zu)", ar.off);
+    int rc = tc::launch_split_from_nhwc(d_in, N, H, W, bi, exact, s);
+    if (rc == IC_OK && d_res1) rc = tc::launch_split_from_nhwc(d_res1, N, H, W, b1, exact, s);
+    if (rc == IC_OK && d_res2) rc = tc::launch_split_from_nhwc(d_res2, N, H, W, b2, exact, s);
+    if (rc == IC_OK) rc = conv_tc_layer(L, bi, bo, d_res1 ? b1 : nullptr, d_res2 ? b2 : nullptr, N, H, W, exact, s);
+    if (rc == IC_OK) rc = tc::launch_merge_to_nhwc(bo, N, H, W, d_out, exact, s);
+    return rc;
 }
 
 int ic_quantize_fwd(const float* d_x, const float* d_centers, int L, float sigma, int64_t n, float* d_qsoft,

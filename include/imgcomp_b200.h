@@ -164,6 +164,15 @@ int ic_msssim_tf_fwd(const float* d_img1, const float* d_img2, int N, int H, int
 int ic_msssim_np_fwd(const uint8_t* d_img1, const uint8_t* d_img2, int N, int H, int W,
                      double* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------- test hooks
+ * One fused 3x3 128->128 residual conv (conv + BN + ReLU + residual adds) of the
+ * encoder/decoder through the path selected by `mode`; fp32 NHWC (N,H,W,128) in/out.
+ * Lets tests compare the tcgen05 kernel with the FFMA kernel layer by layer.
+ * Workspace: 4 * N*H*W*128*4 bytes (+1 KB) for the tensor-core modes. */
+int ic_debug_conv3x3(const ic_ae_t* ae, int decoder, int layer, const float* d_in, const float* d_res1,
+                     const float* d_res2, int N, int H, int W, float* d_out,
+                     void* d_workspace, size_t workspace_bytes, int mode, void* stream);
+
 /* ------------------------------------------------------- launch accounting
  * Not part of the reference's surface: lets bench.py count this library's kernel
  * launches (`gpu_launches`) and time one kernel class live with CUDA events on the
