@@ -58,6 +58,8 @@ SIGNATURES = {
     'ic_pc_logits_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_pc_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_pc_context_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'ic_msssim_tf_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_np_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -653,6 +653,21 @@ int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_
     return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, d_freqs, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int ic_pc_context_freqs_fwd(const ic_pc_t* pc, const int64_t* d_ctx_symbols, const float* d_centers, int N, int D, int H,
+                            int W, int64_t* d_freqs, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_ctx_symbols && d_centers && d_freqs && d_workspace, IC_ERR_INVALID, "ic_pc_context_freqs_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && D >= 5 && H >= 9 && W >= 9, IC_ERR_INVALID,
+               "ic_pc_context_freqs_fwd: volume %dx%dx%d is smaller than the 5x9x9 context", D, H, W);
+    PcInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.D = D; in.H = H; in.W = W;
+    in.symbols = d_ctx_symbols;
+    IC_CHECK_CUDA(cudaMemcpyAsync(in.centers_host, d_centers, sizeof(float) * pc->cfg.num_centers, cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+    IC_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, d_freqs, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 // --------------------------------------------------------------------- MS-SSIM
 size_t ic_msssim_workspace_bytes(int N, int H, int W, int is_double) {
     if (N <= 0 || H <= 0 || W <= 0) return 0;

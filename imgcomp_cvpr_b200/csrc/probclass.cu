@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(128) pc_final_kernel(const float* __restrict__
                     e[l] = expf(__fsub_rn(lg[l], m));
                     s = __fadd_rn(s, e[l]);
                 }
-            int sym = (int)symbols[v];
+            int sym = symbols ? (int)symbols[v] : 0;
             float lsel = 0.f;
 #pragma unroll
             for (int l = 0; l < 8; ++l)

@@ -247,10 +247,20 @@ class PredictionNetwork(object):
         return torch.softmax(self._ctx_logits(input_ctx), -1).cpu().numpy()
 
     def get_freqs(self, input_ctx):
-        """input_ctx: symbols CHW (5,9,9) -> int64 freqs (L,) (code/probclass.py:461-476)"""
-        pr = torch.softmax(self._ctx_logits(input_ctx), -1)
-        f = (pr * 1e9).to(torch.int64).cpu().numpy()
-        f = np.maximum(f, 1)
+        """input_ctx: symbols CHW (5,9,9) -> int64 freqs (L,) (code/probclass.py:461-476).
+        Same kernel arithmetic as get_all_freqs: bit-identical to the batched table."""
+        ctx = np.asarray(input_ctx)
+        assert ctx.shape == tuple(self.input_ctx_shape), '{} != {}'.format(ctx.shape, self.input_ctx_shape)
+        s = torch.from_numpy(np.ascontiguousarray(ctx.astype(np.int64))).cuda()
+        pc = self.pc
+        pc._need_handle()
+        out = torch.empty(pc.L, dtype=torch.int64, device='cuda')
+        ws = pc._workspace(1, *ctx.shape)
+        centers = self.centers.contiguous().float()
+        _lib.check(_lib.lib().ic_pc_context_freqs_fwd(pc._handle, _lib.ptr(s), _lib.ptr(centers), 1, ctx.shape[0],
+                                                      ctx.shape[1], ctx.shape[2], _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                                      _lib.stream_ptr()))
+        f = out.cpu().numpy()
         assert np.all(f > 0), 'We do not want zero frequencies!: {}'.format(f)
         return f
 

@@ -149,6 +149,14 @@ int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_
                     int N, int C, int h, int w, int64_t* d_freqs, double* d_bits_sum,
                     void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* replaces ONE PredictionNetwork.get_freqs call (code/probclass.py:441-444,461-476): an UN-padded
+ * block of context symbols N x D x H x W (the reference feeds D,H,W = 5,9,9) is gathered through
+ * `centers`, run through the context model -> int64 freqs N x (D-4) x (H-8) x (W-8) x L.  Same
+ * arithmetic as ic_pc_freqs_fwd: the table of a position is bit-identical either way. */
+int ic_pc_context_freqs_fwd(const ic_pc_t* pc, const int64_t* d_ctx_symbols, const float* d_centers,
+                            int N, int D, int H, int W, int64_t* d_freqs,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* --------------------------------------------------------------------- MS-SSIM
  * replaces: ms_ssim.MultiScaleSSIM(img1, img2, data_format='NCHW')   code/ms_ssim.py:115-186
  * float32, ONE scalar for the batch.  d_out: 1 float; d_levels (optional): 10 floats

@@ -1,0 +1,72 @@
+"""tcgen05 3x3 conv (csrc/conv_tc.cu) against the float32 FFMA kernel, layer by layer,
+through the C-ABI test hook ic_debug_conv3x3; then the whole encoder in EXACT / FAST mode."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, symbol_margin
+from oracle import imgcomp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv(ae, decoder, layer, x, r1, r2, mode):
+    from imgcomp_cvpr_b200 import _lib
+    L = _lib.lib()
+    N, H, W, _ = x.shape
+    out = torch.full_like(x, float('nan'))
+    ws = torch.empty(4 * x.numel() * 4 + 4096, dtype=torch.uint8, device='cuda')
+    _lib.check(L.ic_debug_conv3x3(ae._handle, decoder, layer, _lib.ptr(x), _lib.ptr(r1), _lib.ptr(r2), N, H, W,
+                                  _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.MODES[mode], _lib.stream_ptr()))
+    return out
+
+
+@pytest.mark.parametrize('shape', [(1, 16, 8), (1, 16, 16), (2, 40, 40), (3, 48, 24), (1, 8, 8), (1, 17, 9), (2, 192, 128)])
+@pytest.mark.parametrize('mode', ['exact', 'fast'])
+def test_layer_matches_ffma(shape, mode, gpu_models):
+    ae, pc, W = gpu_models('cvpr/low')
+    N, H, Wd = shape
+    g = torch.Generator(device='cuda').manual_seed(N * 1000 + H * 10 + Wd)
+    x, r1, r2 = (torch.randn((N, H, Wd, 128), device='cuda', generator=g) * s for s in (1.0, 3.0, 0.5))
+    for decoder, layer, use_res in ((0, 0, False), (0, 5, True), (1, 31, True)):
+        a, b = (r1, r2) if use_res else (None, None)
+        ref = _conv(ae, decoder, layer, x, a, b, 'fp32')
+        out = _conv(ae, decoder, layer, x, a, b, mode)
+        assert not torch.isnan(out).any()
+        scale = max(1.0, ref.abs().max().item())
+        err = (out - ref).abs().max().item()
+        # exact: float32-class (fp16x3 split, fp32 accumulate in TMEM); fast: one fp16 pass
+        assert err < (1e-4 if mode == 'exact' else 2e-2) * scale, (decoder, layer, err, scale)
+
+
+def test_layer_against_float64(gpu_models):
+    """EXACT mode vs a float64 convolution: same error class as the FFMA float32 kernel."""
+    ae, pc, W = gpu_models('cvpr/low')
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = torch.randn((1, 32, 32, 128), device='cuda', generator=g)
+    scope = 'autoencoder/encoder/res_block_enc_0/enc_0_1/conv1'
+    w = torch.from_numpy(W[scope + '/weights']).double().cuda().permute(3, 2, 0, 1)
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w, padding=1)
+    bn = {k: torch.from_numpy(W[scope + '/BatchNorm/' + k]).double().cuda() for k in
+          ('gamma', 'beta', 'moving_mean', 'moving_variance')}
+    y = (y - bn['moving_mean'][None, :, None, None]) / torch.sqrt(bn['moving_variance'] + 1e-5)[None, :, None, None] \
+        * bn['gamma'][None, :, None, None] + bn['beta'][None, :, None, None]
+    y = torch.relu(y).permute(0, 2, 3, 1)
+    e_ffma = (_conv(ae, 0, 0, x, None, None, 'fp32').double() - y).abs().mean().item()
+    e_tc = (_conv(ae, 0, 0, x, None, None, 'exact').double() - y).abs().mean().item()
+    e_fast = (_conv(ae, 0, 0, x, None, None, 'fast').double() - y).abs().mean().item()
+    print('mean |err| vs float64: ffma %.3e  tc-exact %.3e  tc-fast %.3e' % (e_ffma, e_tc, e_fast))
+    assert e_tc < 1e-5 and e_tc < 20 * max(e_ffma, 1e-8)
+    assert e_fast < 1e-2
+
+
+@pytest.mark.parametrize('name,ae_name', [('cfg1_low_1x128x128', 'cvpr/low'), ('ragged_low_2x48x72', 'cvpr/low'),
+                                          ('tiny_hi_1x40x24', 'cvpr/hi')])
+def test_fast_mode_flip_rate_is_reported(name, ae_name, gpu_models):
+    """FAST mode is NOT the parity mode: it is reported with its symbol flip rate."""
+    ae, pc, W = gpu_models(ae_name, 'fast')
+    g = load_golden(name)
+    enc = ae.encode(torch.from_numpy(g['x_u8']).cuda(), False)
+    flips = (enc.symbols.cpu().numpy() != g['symbols']).mean()
+    print('fast mode: %s symbol flip rate %.4f, max |dz| %.3e' % (name, flips, np.abs(enc.z.cpu().numpy() - g['z']).max()))
+    assert flips < 0.05

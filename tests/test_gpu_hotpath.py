@@ -17,7 +17,7 @@ from oracle import imgcomp_oracle as O
 
 pytestmark = pytest.mark.gpu
 EPS_MARGIN = 1e-4
-MODES = ['fp32']
+MODES = ['fp32', 'exact']
 
 
 def _cuda(a):
@@ -117,6 +117,15 @@ def test_probclass_batched_freqs_match_reference_loop_and_are_causal(gpu_models)
     for (c, y, x) in ((0, 0, 0), (0, 0, 1), (5, 3, 2), (31, 7, 7), (12, 0, 7), (31, 0, 0)):
         fc = pred.get_freqs(sp[c:c + 5, y:y + 9, x:x + 9])
         assert np.array_equal(fc, f[c, y, x]), (c, y, x)
+        pr = pred.get_pr(sp[c:c + 5, y:y + 9, x:x + 9])
+        np.testing.assert_allclose(pr, f[c, y, x] / 1e9, atol=2e-7)
+    # pc.logits on the manually padded volume (code/probclass.py:130-135) == per-context logits, bit for bit
+    qpad = torch.from_numpy(W['autoencoder/encoder/centers'][sp]).cuda()[None]
+    full = pc.logits(qpad)[0]
+    assert tuple(full.shape) == syms.shape + (6,)
+    for (c, y, x) in ((0, 0, 0), (5, 3, 2), (31, 7, 7)):
+        one = pc.logits(qpad[:, c:c + 5, y:y + 9, x:x + 9].contiguous())[0, 0, 0, 0]
+        assert torch.equal(one, full[c, y, x])
     # causality: tables before position p do not change when symbols at/after p change
     rng = np.random.RandomState(0)
     flat = syms.reshape(-1).copy()
