@@ -160,7 +160,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='kodak24', choices=sorted(WORKLOADS))
-    ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'fp32'), choices=['fp32', 'exact', 'fast'])
+    ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'exact'), choices=['fp32', 'exact', 'fast'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('IC_BENCH_ALLOW_SHORT'), 'W >= 3 required'

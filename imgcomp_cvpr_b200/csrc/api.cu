@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -97,6 +98,8 @@ struct DevLayer {
     // divided by the power-of-two weight pre-scale
     __half* w_tc = nullptr;
     float* scale_tc = nullptr;
+    tc::GroupTable gt;
+    int nout_tc = 0;
 };
 
 int upload(const std::vector<float>& h, float** d) {
@@ -200,15 +203,33 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
             int rc = upload(wm, &d.w);
             if (rc == IC_OK) rc = upload(sc, &d.scale);
             if (rc == IC_OK) rc = upload(sh, &d.shift);
-            if (rc == IC_OK && l.k == 3 && l.stride == 1 && !l.transposed && l.cin == 128 && l.cout == 128) {
+            // tensor-core path: the 3x3 128->128 residual convs, h2 (5x5 s2 64->128) and to_bn (5x5 s2 128->C+1 <= 48)
+            const bool tc_res = l.k == 3 && l.stride == 1 && !l.transposed && l.cin == 128 && l.cout == 128;
+            const bool tc_s2 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin % 64 == 0 && (l.cout == 128 || l.cout <= 48);
+            if (rc == IC_OK && (tc_res || tc_s2)) {
                 std::vector<__half> packed;
                 float inv = 1.f;
-                tc::pack_weights_3x3(w, packed, &inv);
-                std::vector<float> sct(sc);
-                for (auto& v : sct) v *= inv;                 // exact: inv is a power of two
-                IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc, packed.size() * sizeof(__half)));
-                IC_CHECK_CUDA(cudaMemcpy(d.w_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
-                rc = upload(sct, &d.scale_tc);
+                d.nout_tc = l.cout == 128 ? 128 : 48;
+                rc = tc::pack_weights(w, l.k, l.stride, l.cin, l.cout, d.nout_tc, packed, d.gt, &inv);
+                if (rc == IC_OK) {
+                    std::vector<float> sct(128, 0.f), sht(128, 0.f);
+                    for (int co = 0; co < l.cout; ++co) {
+                        sct[co] = sc[co] * inv;               // exact: inv is a power of two
+                        sht[co] = sh[co];
+                    }
+                    IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc, packed.size() * sizeof(__half)));
+                    IC_CHECK_CUDA(cudaMemcpy(d.w_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                    rc = upload(sct, &d.scale_tc);
+                    if (rc == IC_OK) {       // padded shift for the tensor-core epilogue
+                        cudaFree(d.shift);
+                        std::vector<float> shp(std::max<size_t>(128, sh.size()), 0.f);
+                        for (size_t i = 0; i < sh.size(); ++i) shp[i] = sh[i];
+                        rc = upload(shp, &d.shift);
+                    }
+                } else {
+                    d.nout_tc = 0;
+                    rc = IC_OK;
+                }
             }
             dst.push_back(d);
             if (rc != IC_OK) {
@@ -341,37 +362,43 @@ int run_res_stack_simt(const DevLayer* layers, int B, int N, int H, int W, float
     return rc;
 }
 
-int conv_tc_layer(const DevLayer& L, const __half* in, __half* out, const __half* r1, const __half* r2, int N, int H, int W,
-                  bool exact, cudaStream_t s) {
+int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, int Win, __half* out, float* out_f32,
+                  const __half* r1, const __half* r2, int N, int H, int W, bool exact, cudaStream_t s) {
     tc::ConvTcArgs a;
+    memset(&a, 0, sizeof(a));
     a.in = in;
+    a.Nimg = N;
+    a.in_chunks = in_chunks;
+    a.Hin = Hin;
+    a.Win = Win;
     a.weights = L.w_tc;
+    a.groups = &L.gt;
     a.scale = L.scale_tc;
     a.shift = L.shift;
     a.res1 = r1;
     a.res2 = r2;
     a.out = out;
+    a.out_f32 = out_f32;
     a.N = N;
     a.H = H;
     a.W = W;
     a.relu = L.spec.relu;
+    a.cout = L.spec.cout;
+    a.nout = L.nout_tc;
+    a.halo0 = -1;
+    a.img_mul = 1;
     a.exact = exact;
-    return tc::launch_conv3x3_tc(a, s);
+    a.prof_class = L.spec.k == 3 ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER;
+    return tc::launch_conv_tc(a, s);
 }
 
-// tensor-core res stack: pool buffers hold fp16 hi/lo planes; f32_in (NHWC fp32) is split into
-// pool[0] first and the result is merged back into f32_out.
-int run_res_stack_tc(const DevLayer* layers, int B, int N, int H, int W, __half* pool[5], const float* f32_in,
-                     float* f32_out, bool exact, cudaStream_t s) {
-    int rc = tc::launch_split_from_nhwc(f32_in, N, H, W, pool[0], exact, s);
-    if (rc != IC_OK) return rc;
-    int idx = 0;
-    rc = run_res_stack(layers, B, [&](const DevLayer& L, int in, int out, int r1, int r2) {
-        return conv_tc_layer(L, pool[in], pool[out], r1 >= 0 ? pool[r1] : nullptr, r2 >= 0 ? pool[r2] : nullptr, N, H, W,
-                             exact, s);
-    }, &idx);
-    if (rc != IC_OK) return rc;
-    return tc::launch_merge_to_nhwc(pool[idx], N, H, W, f32_out, exact, s);
+// tensor-core res stack over fp16 hi/lo plane buffers; pool[0] holds the input.  Returns the output index.
+int run_res_stack_tc(const DevLayer* layers, int B, int N, int H, int W, __half* pool[5], bool exact, int* result,
+                     cudaStream_t s) {
+    return run_res_stack(layers, B, [&](const DevLayer& L, int in, int out, int r1, int r2) {
+        return conv_tc_layer(L, pool[in], 16, H, W, pool[out], nullptr, r1 >= 0 ? pool[r1] : nullptr,
+                             r2 >= 0 ? pool[r2] : nullptr, N, H, W, exact, s);
+    }, result);
 }
 
 }  // namespace
@@ -385,7 +412,8 @@ size_t ic_encode_workspace_bytes(const ic_ae_t* ae, int N, int H, int W, int mod
     size_t b = 0;
     b += align_up(n * H * W * 4 * 4, 256);
     b += align_up(n * (H / 2) * (W / 2) * 64 * 4, 256);
-    b += (mode == IC_MODE_FP32 ? 5 : 7) * align_up(n * (H / 4) * (W / 4) * 128 * 4, 256);
+    (void)mode;
+    b += 5 * align_up(n * (H / 4) * (W / 4) * 128 * 4, 256);
     b += align_up(n * (H / 8) * (W / 8) * CB * 4, 256);
     return b + 4096;
 }
@@ -404,8 +432,8 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
     const size_t n = N;
     float* xin = ar.get<float>(n * H * W * 4);
     float* a1 = ar.get<float>(n * (H / 2) * (W / 2) * 64);
-    float* pool[7];
-    for (int i = 0; i < (mode == IC_MODE_FP32 ? 5 : 7); ++i) pool[i] = ar.get<float>(n * (H / 4) * (W / 4) * 128);
+    float* pool[5];
+    for (int i = 0; i < 5; ++i) pool[i] = ar.get<float>(n * (H / 4) * (W / 4) * 128);
     float* bn = ar.get<float>(n * (H / 8) * (W / 8) * CB);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_encode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
 
@@ -414,23 +442,41 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
     const DevLayer* L = ae->enc.data();
     rc = launch_conv_simt(make_desc(L[0], xin, N, H, W, a1), s);
     if (rc != IC_OK) return rc;
-    float* trunk = nullptr;
+    const DevLayer& tobn = ae->enc.back();
     if (mode == IC_MODE_FP32) {
+        float* trunk = nullptr;
         rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[0]), s);
         if (rc != IC_OK) return rc;
         rc = run_res_stack_simt(L + 2, c.arch_param_B, N, H / 4, W / 4, pool, &trunk, s);
-    } else {
-        rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[5]), s);
         if (rc != IC_OK) return rc;
+        rc = launch_conv_simt(make_desc(tobn, trunk, N, H / 4, W / 4, bn), s);
+        if (rc != IC_OK) return rc;
+    } else {
+        const bool exact = mode == IC_MODE_EXACT;
+        const int H4 = H / 4, W4 = W / 4;
         __half* hp[5];
         for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
-        trunk = pool[6];
-        rc = run_res_stack_tc(L + 2, c.arch_param_B, N, H / 4, W / 4, hp, pool[5], trunk, mode == IC_MODE_EXACT, s);
+        // h1 output (N,H/2,W/2,64) -> space-to-depth planes [pl][N][32][H/4][W/4][8] (2 trunk units: pool[1..2])
+        rc = tc::launch_split_from_nhwc(a1, N, H / 2, W / 2, 64, 1, hp[1], exact, s);
+        if (rc != IC_OK) return rc;
+        rc = conv_tc_layer(L[1], hp[1], 32, H4, W4, hp[0], nullptr, nullptr, nullptr, N, H4, W4, exact, s);   // h2
+        if (rc != IC_OK) return rc;
+        int ti = 0;
+        rc = run_res_stack_tc(L + 2, c.arch_param_B, N, H4, W4, hp, exact, &ti, s);
+        if (rc != IC_OK) return rc;
+        const int f1 = (ti + 1) % 5;
+        if (tobn.nout_tc) {
+            // trunk planes -> space-to-depth [pl][N][64][H/8][W/8][8], then to_bn on tensor cores -> fp32 NHWC
+            rc = tc::launch_s2d_planes(hp[ti], N, H4, W4, 128, exact ? 2 : 1, hp[f1], s);
+            if (rc != IC_OK) return rc;
+            rc = conv_tc_layer(tobn, hp[f1], 64, H / 8, W / 8, nullptr, bn, nullptr, nullptr, N, H / 8, W / 8, exact, s);
+        } else {
+            rc = tc::launch_merge_to_nhwc(hp[ti], N, H4, W4, 128, pool[f1], exact, s);
+            if (rc != IC_OK) return rc;
+            rc = launch_conv_simt(make_desc(tobn, pool[f1], N, H4, W4, bn), s);
+        }
+        if (rc != IC_OK) return rc;
     }
-    if (rc != IC_OK) return rc;
-    const DevLayer& tobn = ae->enc.back();
-    rc = launch_conv_simt(make_desc(tobn, trunk, N, H / 4, W / 4, bn), s);
-    if (rc != IC_OK) return rc;
     return launch_heatmap_quantize(bn, N, H / 8, W / 8, c.num_chan_bn, c.heatmap, ae->d_centers, c.num_centers, d_z,
                                    d_heatmap, d_qbar, d_qhard, d_symbols, d_symbols_u8, d_qsoft, s);
 }
@@ -470,10 +516,16 @@ int ic_decode_fwd(const ic_ae_t* ae, const float* d_q, int N, int h, int w, floa
     } else {
         rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[5]), s);
         if (rc != IC_OK) return rc;
+        const bool exact = mode == IC_MODE_EXACT;
         __half* hp[5];
         for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
+        rc = tc::launch_split_from_nhwc(pool[5], N, 2 * h, 2 * w, 128, 0, hp[0], exact, s);
+        if (rc != IC_OK) return rc;
+        int ti = 0;
+        rc = run_res_stack_tc(L + 1, c.arch_param_B, N, 2 * h, 2 * w, hp, exact, &ti, s);
+        if (rc != IC_OK) return rc;
         trunk = pool[6];
-        rc = run_res_stack_tc(L + 1, c.arch_param_B, N, 2 * h, 2 * w, hp, pool[5], trunk, mode == IC_MODE_EXACT, s);
+        rc = tc::launch_merge_to_nhwc(hp[ti], N, 2 * h, 2 * w, 128, trunk, exact, s);
     }
     if (rc != IC_OK) return rc;
     const size_t nl = ae->dec.size();
@@ -493,7 +545,7 @@ int ic_debug_conv3x3(const ic_ae_t* ae, int decoder, int layer, const float* d_i
     IC_REQUIRE(ae && d_in && d_out, IC_ERR_INVALID, "ic_debug_conv3x3: NULL argument");
     const auto& layers = decoder ? ae->dec : ae->enc;
     const int first = decoder ? 1 : 2;
-    IC_REQUIRE(layer >= 0 && first + layer < (int)layers.size() && layers[first + layer].w_tc, IC_ERR_INVALID,
+    IC_REQUIRE(layer >= 0 && first + layer < (int)layers.size() && layers[first + layer].w_tc && layers[first + layer].spec.k == 3, IC_ERR_INVALID,
                "ic_debug_conv3x3: layer %d is not a 3x3 128->128 conv", layer);
     const DevLayer& L = layers[first + layer];
     cudaStream_t s = (cudaStream_t)stream;
@@ -511,11 +563,12 @@ int ic_debug_conv3x3(const ic_ae_t* ae, int decoder, int layer, const float* d_i
     __half* b2 = ar.get<__half>(elems);
     __half* bo = ar.get<__half>(elems);
     IC_REQUIRE(d_workspace && ar.ok(), IC_ERR_WORKSPACE, "ic_debug_conv3x3: workspace too small (need %zu)", ar.off);
-    int rc = tc::launch_split_from_nhwc(d_in, N, H, W, bi, exact, s);
-    if (rc == IC_OK && d_res1) rc = tc::launch_split_from_nhwc(d_res1, N, H, W, b1, exact, s);
-    if (rc == IC_OK && d_res2) rc = tc::launch_split_from_nhwc(d_res2, N, H, W, b2, exact, s);
-    if (rc == IC_OK) rc = conv_tc_layer(L, bi, bo, d_res1 ? b1 : nullptr, d_res2 ? b2 : nullptr, N, H, W, exact, s);
-    if (rc == IC_OK) rc = tc::launch_merge_to_nhwc(bo, N, H, W, d_out, exact, s);
+    int rc = tc::launch_split_from_nhwc(d_in, N, H, W, 128, 0, bi, exact, s);
+    if (rc == IC_OK && d_res1) rc = tc::launch_split_from_nhwc(d_res1, N, H, W, 128, 0, b1, exact, s);
+    if (rc == IC_OK && d_res2) rc = tc::launch_split_from_nhwc(d_res2, N, H, W, 128, 0, b2, exact, s);
+    if (rc == IC_OK)
+        rc = conv_tc_layer(L, bi, 16, H, W, bo, nullptr, d_res1 ? b1 : nullptr, d_res2 ? b2 : nullptr, N, H, W, exact, s);
+    if (rc == IC_OK) rc = tc::launch_merge_to_nhwc(bo, N, H, W, 128, d_out, exact, s);
     return rc;
 }
 

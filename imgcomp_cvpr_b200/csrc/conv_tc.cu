@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "conv_tc.cuh"
@@ -47,14 +48,15 @@ namespace {
 constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels = M 128
 constexpr int WSTAGES = 3;
 constexpr int NTHREADS = 7 * 32;
-constexpr int W_STAGE_PLANE_BYTES = 4 * 128 * 16;   // 4 chunks x 128 cout x 8 cin fp16
-constexpr uint32_t kIdesc = (1u << 4) /* D fp32 */ | (0u << 7) /* A f16 */ | (0u << 10) /* B f16 */ |
-                            ((128u >> 3) << 17) /* N */ | ((128u >> 4) << 24) /* M */;
 
-template <int T>
+template <int T, int NOUT>
 struct Cfg {
     static constexpr int HALO_W = TW * T + 2, HALO_H = TH + 2, HALO_PIX = HALO_W * HALO_H;
-    static constexpr int A_PLANE_BYTES = 8 * HALO_PIX * 16;       // 8 chunks of one 64-channel half
+    static constexpr int A_PLANE_BYTES = 8 * HALO_PIX * 16;       // one group = 8 chunks = 64 channels
+    static constexpr int W_PLANE_BYTES = 4 * NOUT * 16;           // one stage = 32 channels of one tap
+    static constexpr int NCOL = NOUT > 64 ? 128 : 64;             // TMEM columns per accumulator tile
+    static constexpr uint32_t IDESC = (1u << 4) /* D fp32 */ | (0u << 7) /* A f16 */ | (0u << 10) /* B f16 */ |
+                                      ((uint32_t)(NOUT >> 3) << 17) /* N */ | ((128u >> 4) << 24) /* M */;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -156,20 +158,68 @@ __device__ __forceinline__ void add_pair(const __half* hi_plane, const __half* l
     }
 }
 
-template <int T, int NPL>
+__device__ __forceinline__ float4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// residual operands of one 16-column step (2 chunks): res1 hi/lo, res2 hi/lo
+struct ResRegs {
+    float4 v[2][4];
+};
+
+template <int NPL>
+__device__ __forceinline__ void load_res(ResRegs& r, const ConvTcParams& p, size_t off0, size_t chunk_stride, size_t plane) {
+#pragma unroll
+    for (int hc = 0; hc < 2; ++hc) {
+        const size_t off = off0 + hc * chunk_stride;
+        if (p.res1) {
+            r.v[hc][0] = ldg16(p.res1 + off);
+            if (NPL == 2) r.v[hc][1] = ldg16(p.res1 + plane + off);
+        }
+        if (p.res2) {
+            r.v[hc][2] = ldg16(p.res2 + off);
+            if (NPL == 2) r.v[hc][3] = ldg16(p.res2 + plane + off);
+        }
+    }
+}
+
+__device__ __forceinline__ void add_h8(const float4& q, float (&v)[8]) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 a = __half22float2(h2[i]);
+        v[2 * i] += a.x;
+        v[2 * i + 1] += a.y;
+    }
+}
+
+// pair (hi, lo) -> float, added as (hi + lo) like a float32 residual read
+__device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, float (&v)[8]) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 a = __half22float2(h2[i]), b = __half22float2(l2[i]);
+        v[2 * i] += a.x + b.x;
+        v[2 * i + 1] += a.y + b.y;
+    }
+}
+
+// OUTMODE 0: fp16 hi/lo planes [plane][N][NOUT/8][H][W][8]; 1: float32 NHWC [N][H][W][cout]
+template <int T, int NPL, int NOUT, int OUTMODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
-    using C = Cfg<T>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p, const GroupTable gt) {
+    using C = Cfg<T, NOUT>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* a_buf = smem;                                              // [2 halves][NPL][A_PLANE_BYTES]
-    uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_STAGE_PLANE_BYTES]
-    float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * W_STAGE_PLANE_BYTES);
+    uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
+    uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE_BYTES]
+    float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * C::W_PLANE_BYTES);
     float* s_shift = s_scale + 128;
     Barriers* bars = reinterpret_cast<Barriers*>(s_shift + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (p.W + TW * T - 1) / (TW * T), tiles_y = (p.H + TH - 1) / TH;
     const int n_super = p.N * tiles_y * tiles_x;
+    constexpr uint32_t kTmemCols = (2 * T * C::NCOL <= 32) ? 32 : (2 * T * C::NCOL <= 64) ? 64 :
+                                   (2 * T * C::NCOL <= 128) ? 128 : (2 * T * C::NCOL <= 256) ? 256 : 512;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -185,13 +235,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 128) {
-        s_scale[threadIdx.x] = p.scale[threadIdx.x];
-        s_shift[threadIdx.x] = p.shift[threadIdx.x];
+        s_scale[threadIdx.x] = threadIdx.x < NOUT ? p.scale[threadIdx.x] : 0.f;
+        s_shift[threadIdx.x] = threadIdx.x < NOUT ? p.shift[threadIdx.x] : 0.f;
     }
-    if (warp == 2) {   // TMEM: 2 accumulator sets x T tiles x 128 fp32 columns (power of two >= 32)
-        constexpr uint32_t ncols = (2 * T * 128 <= 256) ? 256 : 512;
+    if (warp == 2) {   // TMEM: 2 accumulator sets x T tiles x NCOL fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                     "n"(ncols));
+                     "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -202,17 +251,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
     if (warp == 0) {
         // ===================== activation producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+            uint32_t gi = 0;     // running group counter -> A slot / phase
+            for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
                 const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
                 const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW * T;
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(smem_u32(&bars->a_empty[h]), (it & 1) ^ 1);
-                    const uint32_t full = smem_u32(&bars->a_full[h]);
+                for (int g = 0; g < gt.ngroups; ++g, ++gi) {
+                    const uint32_t slot = gi & 1, ph = (gi >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bars->a_full[slot]);
                     mbar_expect_tx(full, NPL * C::A_PLANE_BYTES);
                     for (int pl = 0; pl < NPL; ++pl)
-                        tma_load_5d(smem_u32(a_buf + (h * NPL + pl) * C::A_PLANE_BYTES), &in_map, full, (x0 - 1) * 8,
-                                    y0 - 1, h * 8, n, pl);
+                        tma_load_5d(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
+                                    (x0 + p.halo0) * 8, y0 + p.halo0, g * 8, n * p.img_mul + gt.img_off[g], pl);
                 }
             }
         }
@@ -221,61 +271,64 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
         if (lane == 0) {
             uint32_t ws = 0;     // running stage counter
             for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
-                for (int s = 0; s < 36; ++s, ++ws) {      // (half, tap, cin32 block) in MMA order
+                for (int s = 0; s < gt.nstages; ++s, ++ws) {      // (group, tap, cin32 block) in MMA order
                     const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
                     mbar_wait(smem_u32(&bars->w_empty[slot]), ph ^ 1);
                     const uint32_t full = smem_u32(&bars->w_full[slot]);
-                    mbar_expect_tx(full, NPL * W_STAGE_PLANE_BYTES);
-                    // global stage = [2 planes][8 KB]; FAST mode copies the hi plane only
-                    bulk_load(smem_u32(w_buf + slot * NPL * W_STAGE_PLANE_BYTES),
-                              p.weights + (size_t)s * 2 * W_STAGE_PLANE_BYTES, NPL * W_STAGE_PLANE_BYTES, full);
+                    mbar_expect_tx(full, NPL * C::W_PLANE_BYTES);
+                    // global stage = [2 planes][W_PLANE_BYTES]; FAST mode copies the hi plane only
+                    bulk_load(smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES),
+                              p.weights + (size_t)s * 2 * C::W_PLANE_BYTES, NPL * C::W_PLANE_BYTES, full);
                 }
             }
         }
     } else if (warp == 2) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t it = 0, ws = 0;
+            uint32_t it = 0, ws = 0, gi = 0;
             for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
                 const uint32_t set = it & 1;
                 mbar_wait(smem_u32(&bars->acc_empty[set]), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(smem_u32(&bars->a_full[h]), it & 1);
+                for (int g = 0; g < gt.ngroups; ++g, ++gi) {
+                    const uint32_t aslot = gi & 1;
+                    mbar_wait(smem_u32(&bars->a_full[aslot]), (gi >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_buf + h * NPL * C::A_PLANE_BYTES);
-                    for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t a_base = smem_u32(a_buf + aslot * NPL * C::A_PLANE_BYTES);
+                    const int nt = gt.ntaps[g];
+                    for (int ti = 0; ti < nt; ++ti) {
+                        const int tap = gt.taps[g][ti];
                         const int dy = tap / 3, dx = tap - dy * 3;
                         for (int j = 0; j < 2; ++j, ++ws) {
                             const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
                             mbar_wait(smem_u32(&bars->w_full[slot]), ph);
                             tc_fence_after();
-                            const uint32_t w_base = smem_u32(w_buf + slot * NPL * W_STAGE_PLANE_BYTES);
+                            const uint32_t w_base = smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES);
 #pragma unroll
                             for (int t = 0; t < T; ++t) {
-                                const uint32_t d_tmem = tmem_base + (set * T + t) * 128;
+                                const uint32_t d_tmem = tmem_base + (set * T + t) * C::NCOL;
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks) {
                                     const uint32_t a_off = (uint32_t)(j * 4 + ks * 2) * (C::HALO_PIX * 16) +
                                                            (uint32_t)(dy * C::HALO_W + dx + t * TW) * 16;
-                                    const uint32_t w_off = (uint32_t)(ks * 2) * (128 * 16);
+                                    const uint32_t w_off = (uint32_t)(ks * 2) * (NOUT * 16);
                                     const uint64_t a_hi = make_desc(a_base + a_off, C::HALO_PIX * 16, C::HALO_W * 16);
-                                    const uint64_t w_hi = make_desc(w_base + w_off, 128 * 16, 128);
-                                    const uint32_t first = (h | tap | j | ks) == 0 ? 0u : 1u;
-                                    umma_f16(d_tmem, a_hi, w_hi, kIdesc, first);
+                                    const uint64_t w_hi = make_desc(w_base + w_off, NOUT * 16, 128);
+                                    const uint32_t first = (g | ti | j | ks) == 0 ? 0u : 1u;
+                                    umma_f16(d_tmem, a_hi, w_hi, C::IDESC, first);
                                     if (NPL == 2) {
                                         const uint64_t a_lo = make_desc(a_base + C::A_PLANE_BYTES + a_off, C::HALO_PIX * 16,
                                                                         C::HALO_W * 16);
-                                        const uint64_t w_lo = make_desc(w_base + W_STAGE_PLANE_BYTES + w_off, 128 * 16, 128);
-                                        umma_f16(d_tmem, a_hi, w_lo, kIdesc, 1u);
-                                        umma_f16(d_tmem, a_lo, w_hi, kIdesc, 1u);
+                                        const uint64_t w_lo = make_desc(w_base + C::W_PLANE_BYTES + w_off, NOUT * 16, 128);
+                                        umma_f16(d_tmem, a_hi, w_lo, C::IDESC, 1u);
+                                        umma_f16(d_tmem, a_lo, w_hi, C::IDESC, 1u);
                                     }
                                 }
                             }
                             umma_commit(smem_u32(&bars->w_empty[slot]));    // stage free once these MMAs retire
                         }
                     }
-                    umma_commit(smem_u32(&bars->a_empty[h]));
+                    umma_commit(smem_u32(&bars->a_empty[aslot]));
                 }
                 umma_commit(smem_u32(&bars->acc_full[set]));
             }
@@ -285,7 +338,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
         const int ty = m >> 3, tx = m & 7;
-        const size_t plane = (size_t)p.N * 16 * p.H * p.W * 8;      // elements per hi/lo plane
+        constexpr int NCH = NOUT / 8;                 // output chunks (OUTMODE 0)
+        const size_t chunk_stride = (size_t)p.H * p.W * 8;
+        const size_t plane = (size_t)p.N * NCH * chunk_stride;      // elements per hi/lo plane
         uint32_t it = 0;
         for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
             const uint32_t set = it & 1;
@@ -297,36 +352,70 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
             for (int t = 0; t < T; ++t) {
                 const int x = (r % tiles_x) * TW * T + t * TW + tx;
                 const bool inside = y < p.H && x < p.W;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * T + t) * 128;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * T + t) * C::NCOL;
+                if (OUTMODE == 0) {
+                    const size_t pix_off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;   // chunk 0
+                    const bool has_res = (p.res1 != nullptr) || (p.res2 != nullptr);
+                    ResRegs cur, nxt;
+                    if (inside && has_res) load_res<NPL>(cur, p, pix_off, chunk_stride, plane);
 #pragma unroll 1
-                for (int cc = 0; cc < 8; ++cc) {
-                    uint32_t rr[16];
-                    tmem_ld16(taddr + cc * 16, rr);
-                    tmem_ld_wait();
-                    if (inside) {
+                    for (int cc = 0; cc < NOUT / 16; ++cc) {
+                        uint32_t rr[16];
+                        tmem_ld16(taddr + cc * 16, rr);
+                        if (inside && has_res && cc + 1 < NOUT / 16)
+                            load_res<NPL>(nxt, p, pix_off + (size_t)(cc + 1) * 2 * chunk_stride, chunk_stride, plane);
+                        tmem_ld_wait();
+                        if (inside) {
 #pragma unroll
-                        for (int hc = 0; hc < 2; ++hc) {
-                            const int chunk = cc * 2 + hc;
-                            float v[8];
+                            for (int hc = 0; hc < 2; ++hc) {
+                                const int chunk = cc * 2 + hc;
+                                float v[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                float a = __uint_as_float(rr[hc * 8 + e]);
-                                a = fmaf(a, s_scale[chunk * 8 + e], s_shift[chunk * 8 + e]);
-                                v[e] = p.relu ? fmaxf(a, 0.f) : a;
+                                for (int e = 0; e < 8; ++e) {
+                                    float a = __uint_as_float(rr[hc * 8 + e]);
+                                    a = fmaf(a, s_scale[chunk * 8 + e], s_shift[chunk * 8 + e]);
+                                    v[e] = p.relu ? fmaxf(a, 0.f) : a;
+                                }
+                                if (p.res1) {
+                                    if (NPL == 2) add_h8_pair(cur.v[hc][0], cur.v[hc][1], v);
+                                    else add_h8(cur.v[hc][0], v);
+                                }
+                                if (p.res2) {
+                                    if (NPL == 2) add_h8_pair(cur.v[hc][2], cur.v[hc][3], v);
+                                    else add_h8(cur.v[hc][2], v);
+                                }
+                                __align__(16) __half2 hi[4];
+                                __align__(16) __half2 lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    hi[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                                    float2 hf = __half22float2(hi[e]);
+                                    lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                                }
+                                const size_t off = pix_off + (size_t)chunk * chunk_stride;
+                                *reinterpret_cast<float4*>(p.out + off) = *reinterpret_cast<const float4*>(hi);
+                                if (NPL == 2)
+                                    *reinterpret_cast<float4*>(p.out + plane + off) = *reinterpret_cast<const float4*>(lo);
                             }
-                            const size_t off = ((((size_t)n * 16 + chunk) * p.H + y) * p.W + x) * 8;
-                            if (p.res1) add_pair(p.res1, p.res1 + plane, off, NPL == 2, v);
-                            if (p.res2) add_pair(p.res2, p.res2 + plane, off, NPL == 2, v);
-                            __align__(16) __half2 hi[4];
-                            __align__(16) __half2 lo[4];
+                        }
+                        cur = nxt;
+                    }
+                } else {
+                    float* o = p.out_f32 + (((size_t)n * p.H + y) * p.W + x) * p.cout;
+#pragma unroll 1
+                    for (int cc = 0; cc < NOUT / 16; ++cc) {
+                        uint32_t rr[16];
+                        tmem_ld16(taddr + cc * 16, rr);
+                        tmem_ld_wait();
+                        if (inside) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                hi[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                                float2 hf = __half22float2(hi[e]);
-                                lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                            for (int e = 0; e < 16; ++e) {
+                                const int c = cc * 16 + e;
+                                if (c < p.cout) {
+                                    float a = fmaf(__uint_as_float(rr[e]), s_scale[c], s_shift[c]);
+                                    o[c] = p.relu ? fmaxf(a, 0.f) : a;
+                                }
                             }
-                            *reinterpret_cast<float4*>(p.out + off) = *reinterpret_cast<const float4*>(hi);
-                            if (NPL == 2) *reinterpret_cast<float4*>(p.out + plane + off) = *reinterpret_cast<const float4*>(lo);
                         }
                     }
                 }
@@ -339,51 +428,82 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, ConvTcParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
-        constexpr uint32_t ncols = (2 * T * 128 <= 256) ? 256 : 512;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ncols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
     }
 }
 
 // ------------------------------------------------------------- layout changes
-// fp32 NHWC (N,H,W,128) <-> fp16 hi/lo planes [2][N][16][H][W][8]
-__global__ void split_from_nhwc_kernel(const float* __restrict__ in, int H, int W, int64_t total_chunks, int64_t plane,
-                                       __half* __restrict__ out, int write_lo) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (pixel, chunk), chunk fastest
-    if (i >= total_chunks) return;
-    int chunk = (int)(i & 15);
-    int64_t pix = i >> 4;                 // n*H*W + y*W + x
-    int64_t hw = (int64_t)H * W;
-    int64_t n = pix / hw, r = pix - n * hw;
-    const float4* src = reinterpret_cast<const float4*>(in + pix * 128 + chunk * 8);
-    float4 a = src[0], b = src[1];
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    __align__(16) __half2 hi[4];
-    __align__(16) __half2 lo[4];
+// All activations of the tensor-core path live as fp16 hi/lo planes [plane][N][CH][H][W][8]
+// (CH = channels/8).  "s2d" = space-to-depth by 2: [plane][N][4*CH][H/2][W/2][8] with
+// chunk' = ((y&1)*2 + (x&1))*CH + chunk, which turns a stride-2 5x5 conv into a stride-1 conv
+// with <= 3x3 taps per phase (the tap -> (phase, offset) table is built on the host).
+__device__ __forceinline__ void split8(const float (&v)[8], float4& hi4, float4& lo4) {
+    __half2* hi = reinterpret_cast<__half2*>(&hi4);
+    __half2* lo = reinterpret_cast<__half2*>(&lo4);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         hi[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
         float2 hf = __half22float2(hi[e]);
         lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
     }
-    size_t off = (((size_t)n * 16 + chunk) * hw + r) * 8;
-    *reinterpret_cast<float4*>(out + off) = *reinterpret_cast<const float4*>(hi);
-    if (write_lo) *reinterpret_cast<float4*>(out + plane + off) = *reinterpret_cast<const float4*>(lo);
 }
 
-__global__ void merge_to_nhwc_kernel(const __half* __restrict__ in, int H, int W, int64_t total_chunks, int64_t plane,
+// fp32 NHWC (N,H,W,C) -> planes (optionally space-to-depth).  One thread per (chunk, pixel), pixel fastest.
+__global__ void split_from_nhwc_kernel(const float* __restrict__ in, int H, int W, int CH, int s2d, int64_t total,
+                                       int64_t plane, __half* __restrict__ out, int write_lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t hw = (int64_t)H * W;
+    const int64_t r = i % hw;
+    const int64_t nc = i / hw;
+    const int chunk = (int)(nc % CH);
+    const int64_t n = nc / CH;
+    const float4* src = reinterpret_cast<const float4*>(in + ((n * hw + r) * CH + chunk) * 8);
+    float4 a = src[0], b = src[1];
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float4 hi, lo;
+    split8(v, hi, lo);
+    size_t off;
+    if (!s2d) {
+        off = (((size_t)n * CH + chunk) * hw + r) * 8;
+    } else {
+        const int y = (int)(r / W), x = (int)(r - (int64_t)y * W);
+        const int ph = (y & 1) * 2 + (x & 1);
+        off = ((((size_t)n * 4 * CH + ph * CH + chunk) * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * 8;
+    }
+    *reinterpret_cast<float4*>(out + off) = hi;
+    if (write_lo) *reinterpret_cast<float4*>(out + plane + off) = lo;
+}
+
+// planes [pl][N][CH][H][W][8] -> fp32 NHWC.  One thread per (pixel, chunk), chunk fastest (coalesced writes).
+__global__ void merge_to_nhwc_kernel(const __half* __restrict__ in, int H, int W, int CH, int64_t total, int64_t plane,
                                      float* __restrict__ out, int has_lo) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total_chunks) return;
-    int chunk = (int)(i & 15);
-    int64_t pix = i >> 4;
-    int64_t hw = (int64_t)H * W;
-    int64_t n = pix / hw, r = pix - n * hw;
-    size_t off = (((size_t)n * 16 + chunk) * hw + r) * 8;
+    if (i >= total) return;
+    const int chunk = (int)(i % CH);
+    const int64_t pix = i / CH;
+    const int64_t hw = (int64_t)H * W;
+    const int64_t n = pix / hw, r = pix - n * hw;
+    const size_t off = (((size_t)n * CH + chunk) * hw + r) * 8;
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     add_pair(in, in + plane, off, has_lo != 0, v);
-    float4* dst = reinterpret_cast<float4*>(out + pix * 128 + chunk * 8);
+    float4* dst = reinterpret_cast<float4*>(out + (pix * CH + chunk) * 8);
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
     dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// planes [pl][N][CH][H][W][8] -> space-to-depth planes [pl][N][4CH][H/2][W/2][8].  Thread per (plane, n, chunk, y, x).
+__global__ void s2d_planes_kernel(const float4* __restrict__ in, int H, int W, int CH, int64_t total, float4* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // index into the INPUT (16-byte units)
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    int64_t r = i / W;
+    const int y = (int)(r % H);
+    r /= H;
+    const int chunk = (int)(r % CH);
+    const int64_t pn = r / CH;            // plane * N + n
+    const int ph = (y & 1) * 2 + (x & 1);
+    out[(((pn * 4 * CH + ph * CH + chunk) * (H / 2)) + (y >> 1)) * (W / 2) + (x >> 1)] = in[i];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -402,21 +522,23 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int T, int NPL>
+template <int T, int NPL, int NOUT, int OUTMODE>
 int launch_t(const ConvTcArgs& a, cudaStream_t s) {
-    using C = Cfg<T>;
+    using C = Cfg<T, NOUT>;
     EncodeTiledFn enc = get_encode_fn();
     IC_REQUIRE(enc, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap map;
-    const cuuint64_t dims[5] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.H, 16, (cuuint64_t)a.N, (cuuint64_t)NPL};
-    const cuuint64_t strides[4] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16, (cuuint64_t)16 * a.H * a.W * 16,
-                                   (cuuint64_t)a.N * 16 * a.H * a.W * 16};
+    const cuuint64_t hw16 = (cuuint64_t)a.Hin * a.Win * 16;
+    const cuuint64_t dims[5] = {(cuuint64_t)a.Win * 8, (cuuint64_t)a.Hin, (cuuint64_t)a.in_chunks, (cuuint64_t)a.Nimg,
+                                (cuuint64_t)NPL};
+    const cuuint64_t strides[4] = {(cuuint64_t)a.Win * 16, hw16, hw16 * a.in_chunks, hw16 * a.in_chunks * a.Nimg};
     const cuuint32_t box[5] = {(cuuint32_t)C::HALO_W * 8, (cuuint32_t)C::HALO_H, 8, 1, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)a.in, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    IC_REQUIRE(r == CUDA_SUCCESS, IC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d (N=%d H=%d W=%d)", (int)r, a.N, a.H, a.W);
+    IC_REQUIRE(r == CUDA_SUCCESS, IC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d (N=%d H=%d W=%d chunks=%d)", (int)r, a.Nimg,
+               a.Hin, a.Win, a.in_chunks);
     ConvTcParams p;
     p.weights = (const uint8_t*)a.weights;
     p.scale = a.scale;
@@ -424,14 +546,19 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.res1 = a.res1;
     p.res2 = a.res2;
     p.out = a.out;
+    p.out_f32 = a.out_f32;
     p.N = a.N;
     p.H = a.H;
     p.W = a.W;
     p.relu = a.relu;
-    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + WSTAGES * NPL * W_STAGE_PLANE_BYTES + 1024 + sizeof(Barriers) + 64;
+    p.cout = a.cout;
+    p.halo0 = a.halo0;
+    p.img_mul = a.img_mul;
+    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + WSTAGES * NPL * C::W_PLANE_BYTES + 1024 + sizeof(Barriers) + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        IC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<T, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
         attr_set = true;
     }
     const int tiles_x = (a.W + TW * T - 1) / (TW * T), tiles_y = (a.H + TH - 1) / TH;
@@ -440,43 +567,68 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_super < sms ? n_super : sms;
-    ProfScope ps(IC_PROF_CONV3X3, s);
-    conv3x3_tc_kernel<T, NPL><<<grid, NTHREADS, smem, s>>>(map, p);
+    ProfScope ps(a.prof_class, s);
+    conv_tc_kernel<T, NPL, NOUT, OUTMODE><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
     IC_CHECK_LAUNCH();
     return IC_OK;
+}
+
+template <int NOUT, int OUTMODE>
+int launch_n(const ConvTcArgs& a, cudaStream_t s) {
+    const bool wide = a.W > 8;
+    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE>(a, s) : launch_t<1, 2, NOUT, OUTMODE>(a, s);
+    return wide ? launch_t<2, 1, NOUT, OUTMODE>(a, s) : launch_t<1, 1, NOUT, OUTMODE>(a, s);
 }
 
 }  // namespace
 
-int launch_conv3x3_tc(const ConvTcArgs& a, cudaStream_t s) {
-    IC_REQUIRE(a.N > 0 && a.H > 0 && a.W > 0, IC_ERR_INVALID, "conv3x3_tc: bad shape");
-    IC_REQUIRE(((uintptr_t)a.in & 15) == 0 && ((uintptr_t)a.out & 15) == 0, IC_ERR_INVALID, "conv3x3_tc: unaligned buffers");
-    const bool wide = a.W > 8;
-    if (a.exact) return wide ? launch_t<2, 2>(a, s) : launch_t<1, 2>(a, s);
-    return wide ? launch_t<2, 1>(a, s) : launch_t<1, 1>(a, s);
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
+    IC_REQUIRE(a.N > 0 && a.H > 0 && a.W > 0 && a.groups, IC_ERR_INVALID, "conv_tc: bad shape");
+    IC_REQUIRE(((uintptr_t)a.in & 15) == 0, IC_ERR_INVALID, "conv_tc: unaligned input");
+    if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
+    if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
+    set_error("conv_tc: unsupported output configuration (nout=%d)", a.nout);
+    return IC_ERR_UNSUPPORTED;
 }
 
-int launch_split_from_nhwc(const float* in, int N, int H, int W, __half* out, int write_lo, cudaStream_t s) {
-    int64_t total = (int64_t)N * H * W * 16, plane = (int64_t)N * H * W * 128;
+int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s) {
+    IC_REQUIRE(C % 8 == 0 && (!s2d || (H % 2 == 0 && W % 2 == 0)), IC_ERR_INVALID, "split_from_nhwc: bad shape");
+    int64_t total = (int64_t)N * H * W * (C / 8), plane = (int64_t)N * H * W * C;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
-    split_from_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, total, plane, out, write_lo);
+    split_from_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, s2d, total, plane, out, write_lo);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
 
-int launch_merge_to_nhwc(const __half* in, int N, int H, int W, float* out, int has_lo, cudaStream_t s) {
-    int64_t total = (int64_t)N * H * W * 16, plane = (int64_t)N * H * W * 128;
+int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s) {
+    int64_t total = (int64_t)N * H * W * (C / 8), plane = (int64_t)N * H * W * C;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
-    merge_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, total, plane, out, has_lo);
+    merge_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, total, plane, out, has_lo);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
 
-// Host: HWIO float weights (3,3,128,128) -> the kernel's stage order, fp16 hi/lo, scaled by 2^e.
-// Stage s = (half h, tap, cin32 block j) in MMA order; within a stage [plane][4 chunks][128 cout][8 cin].
-void pack_weights_3x3(const float* w_hwio, std::vector<__half>& packed, float* inv_scale_out) {
+int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s) {
+    IC_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, IC_ERR_INVALID, "s2d_planes: bad shape");
+    int64_t total = (int64_t)planes * N * (C / 8) * H * W;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    s2d_planes_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), H, W, C / 8, total,
+                                                       reinterpret_cast<float4*>(out));
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+// Host: conv2d HWIO float weights (k,k,cin,cout) -> the kernel's stage order (fp16 hi/lo, scaled by
+// 2^e) plus the group/tap table.
+//   k = 3, stride 1: groups = cin/64 halves, 9 taps each.
+//   k = 5, stride 2 (input in space-to-depth layout): groups = 4 phases x cin/64; tap ky belongs to
+//   phase (ky-1)&1 with halo row floor((ky-1)/2)+1 (TF SAME on an even size: pad_before = 1).
+// Stage = (group, tap, cin32 block j); within a stage [plane][4 chunks][nout rows][8 cin].
+int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int nout, std::vector<__half>& packed,
+                 GroupTable& gt, float* inv_scale_out) {
+    if (!((k == 3 && stride == 1) || (k == 5 && stride == 2)) || cin % 64 != 0 || cout > nout) return IC_ERR_UNSUPPORTED;
     float mx = 0.f;
-    for (int i = 0; i < 9 * 128 * 128; ++i) mx = fmaxf(mx, fabsf(w_hwio[i]));
+    for (size_t i = 0; i < (size_t)k * k * cin * cout; ++i) mx = fmaxf(mx, fabsf(w_hwio[i]));
     int e = 0;
     if (mx > 0.f) {
         int ex;
@@ -485,24 +637,68 @@ void pack_weights_3x3(const float* w_hwio, std::vector<__half>& packed, float* i
     }
     const float sc = ldexpf(1.f, e);
     *inv_scale_out = ldexpf(1.f, -e);
-    packed.assign((size_t)36 * 2 * 4 * 128 * 8, __float2half(0.f));
-    for (int h = 0; h < 2; ++h)
-        for (int tap = 0; tap < 9; ++tap)
-            for (int j = 0; j < 2; ++j) {
-                const int s = (h * 9 + tap) * 2 + j;
+    const int halves = cin / 64;
+    memset(&gt, 0, sizeof(gt));
+    struct Tap { int ky, kx; };
+    std::vector<std::vector<Tap>> gtaps;
+    std::vector<int> ghalf;
+    if (stride == 1) {
+        for (int h = 0; h < halves; ++h) {
+            std::vector<Tap> t;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) t.push_back({ky, kx});
+            gtaps.push_back(t);
+            ghalf.push_back(h);
+        }
+    } else {
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px)
+                for (int h = 0; h < halves; ++h) {
+                    std::vector<Tap> t;
+                    for (int ky = 0; ky < 5; ++ky)
+                        for (int kx = 0; kx < 5; ++kx)
+                            if ((((ky - 1) & 1) == py) && (((kx - 1) & 1) == px)) t.push_back({ky, kx});
+                    gtaps.push_back(t);
+                    ghalf.push_back(h);
+                }
+    }
+    if (gtaps.size() > 16) return IC_ERR_UNSUPPORTED;
+    gt.ngroups = (int)gtaps.size();
+    const size_t plane_elems = (size_t)4 * nout * 8;
+    packed.clear();
+    int nst = 0;
+    for (size_t g = 0; g < gtaps.size(); ++g) {
+        gt.ntaps[g] = (uint8_t)gtaps[g].size();
+        for (size_t ti = 0; ti < gtaps[g].size(); ++ti) {
+            const Tap tp = gtaps[g][ti];
+            int dy, dx;
+            if (stride == 1) {
+                dy = tp.ky;
+                dx = tp.kx;
+            } else {   // floor((k-1)/2) + 1 for k-1 in {-1,0,1,2,3}
+                dy = ((tp.ky - 1) >> 1) + 1;
+                dx = ((tp.kx - 1) >> 1) + 1;
+            }
+            gt.taps[g][ti] = (uint8_t)(dy * 3 + dx);
+            for (int j = 0; j < 2; ++j, ++nst) {
+                const size_t base = packed.size();
+                packed.resize(base + 2 * plane_elems, __float2half(0.f));
                 for (int ch = 0; ch < 4; ++ch)
-                    for (int co = 0; co < 128; ++co)
+                    for (int co = 0; co < cout; ++co)
                         for (int ei = 0; ei < 8; ++ei) {
-                            const int ci = h * 64 + j * 32 + ch * 8 + ei;
-                            const float v = w_hwio[((size_t)tap * 128 + ci) * 128 + co] * sc;
+                            const int ci = ghalf[g] * 64 + j * 32 + ch * 8 + ei;
+                            const float v = w_hwio[(((size_t)tp.ky * k + tp.kx) * cin + ci) * cout + co] * sc;
                             const __half hi = __float2half_rn(v);
                             const __half lo = __float2half_rn(v - __half2float(hi));
-                            const size_t base = (size_t)s * 2 * 4 * 128 * 8;
-                            const size_t idx = ((size_t)ch * 128 + co) * 8 + ei;
+                            const size_t idx = ((size_t)ch * nout + co) * 8 + ei;
                             packed[base + idx] = hi;
-                            packed[base + 4 * 128 * 8 + idx] = lo;
+                            packed[base + plane_elems + idx] = lo;
                         }
             }
+        }
+    }
+    gt.nstages = nst;
+    return IC_OK;
 }
 
 }  // namespace tc

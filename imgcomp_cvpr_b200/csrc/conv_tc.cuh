@@ -1,4 +1,4 @@
-// Internal interface of the tcgen05 3x3 convolution (conv_tc.cu).
+// Internal interface of the tcgen05 convolution (conv_tc.cu).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -9,31 +9,51 @@
 namespace ic {
 namespace tc {
 
+// which taps each 64-channel input group contributes (built by pack_weights)
+struct GroupTable {
+    int ngroups;             // A-buffer loads per super tile
+    int nstages;             // weight stages per super tile = 2 * total taps
+    uint8_t ntaps[16];
+    uint8_t taps[16][9];     // dy*3+dx halo offsets
+    uint8_t img_off[16];     // added to the image coordinate of the TMA load (0 for 2-D convs)
+};
+
 // kernel parameters (device pointers)
 struct ConvTcParams {
-    const uint8_t* weights;     // 36 stages x [2 planes][4 chunks][128 cout][8 cin] fp16
-    const float* scale;         // [128] BN scale / weight pre-scale
-    const float* shift;         // [128]
-    const __half* res1;         // [2][N][16][H][W][8] or nullptr
+    const uint8_t* weights;     // nstages x [2 planes][4 chunks][NOUT rows][8 cin] fp16
+    const float* scale;         // [NOUT] BN scale / weight pre-scale
+    const float* shift;         // [NOUT]
+    const __half* res1;         // same layout as out, or nullptr
     const __half* res2;
-    __half* out;                // [2][N][16][H][W][8]
-    int N, H, W, relu;
+    __half* out;                // OUTMODE 0: [2][N][NOUT/8][H][W][8]
+    float* out_f32;             // OUTMODE 1: [N][H][W][cout]
+    int N, H, W, relu, cout;
+    int halo0;                  // origin of the halo tile relative to the output tile (-1: SAME 3x3-like)
+    int img_mul;                // image coordinate = n * img_mul + img_off[group]
 };
 
 struct ConvTcArgs {
-    const __half* in;           // [planes][N][16][H][W][8]
+    const __half* in;           // [planes][Nimg][in_chunks][Hin][Win][8]
+    int Nimg, in_chunks, Hin, Win;
     const __half* weights;
+    const GroupTable* groups;
     const float *scale, *shift;
     const __half *res1, *res2;
     __half* out;
-    int N, H, W, relu;
+    float* out_f32;
+    int N, H, W;                // output tile grid
+    int relu, cout, nout;       // nout: padded output channels the weights were packed for (128 or 48)
+    int halo0, img_mul;
     int exact;                  // 1: hi/lo planes, 3 MMAs per product; 0: hi plane only
+    int prof_class;
 };
 
-int launch_conv3x3_tc(const ConvTcArgs& a, cudaStream_t s);
-int launch_split_from_nhwc(const float* in, int N, int H, int W, __half* out, int write_lo, cudaStream_t s);
-int launch_merge_to_nhwc(const __half* in, int N, int H, int W, float* out, int has_lo, cudaStream_t s);
-void pack_weights_3x3(const float* w_hwio, std::vector<__half>& packed, float* inv_scale_out);
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s);
+int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s);
+int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s);
+int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
+int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int nout, std::vector<__half>& packed,
+                 GroupTable& gt, float* inv_scale_out);
 
 }  // namespace tc
 }  // namespace ic
