@@ -162,6 +162,7 @@ def main():
     ap.add_argument('--workload', default='kodak24', choices=sorted(WORKLOADS))
     ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'exact'), choices=['fp32', 'exact', 'fast'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('IC_BENCH_ALLOW_SHORT'), 'W >= 3 required'
     if args.impl == 'reference':
@@ -216,6 +217,27 @@ def main():
 
     for _ in range(args.warmup):
         step(x_dev)
+    barrier()
+    # ---- parity evidence on THIS workload: the timed mode against the library's float32 FFMA path
+    # (which tests/test_gpu_hotpath.py pins to the oracle / reference goldens): symbol mismatches and bpp
+    parity = None
+    if args.mode != 'fp32' and rank == 0 and not args.no_parity:
+        nchk = min(N, 4)
+        a32, _, _, ae32, pc32 = make_models(ae_name, 'fp32')
+        xs = x_dev[:nchk].contiguous()
+        e_ref = ae32.encode(xs, is_training=False)
+        b_ref = pc32.bitcost(e_ref.qbar, e_ref.symbols, is_training=False, pad_value=pc32.auto_pad_value(ae32))
+        bpp_ref = (pc32.last_bits_per_image / (H * Wd)).cpu()
+        e_m = ae.encode(xs, is_training=False)
+        pc.bitcost(e_m.qbar, e_m.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
+        bpp_m = (pc.last_bits_per_image / (H * Wd)).cpu()
+        mism = (e_m.symbols != e_ref.symbols)
+        parity = {'against': 'fp32 FFMA path, same library', 'images': nchk,
+                  'symbol_mismatches': int(mism.sum().item()), 'symbols': int(mism.numel()),
+                  'max_abs_dz': float((e_m.z - e_ref.z).abs().max().item()),
+                  'max_abs_dbpp': float((bpp_m - bpp_ref).abs().max().item()), 'bpp': bpp_ref.tolist()}
+        del ae32, pc32, e_ref, b_ref, e_m
+        torch.cuda.empty_cache()
     barrier()
     # ---- device-resident throughput (`value`) with live per-kernel-class timing
     L.ic_profile_reset()
@@ -284,6 +306,7 @@ def main():
                      'step_algorithmic_tflop': step_flop / 1e12,
                      'step_tflops': step_flop / (ms * 1e-3) / 1e12},
         'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
+        'parity': parity,
     }
     if not args.no_cpu_baseline:
         import torch as _t

