@@ -224,3 +224,24 @@ def test_batch_and_position_independence(gpu_models):
     xo = ae.decode(e_f.qhard, False).clone()
     assert torch.equal(ae.decode(e1.qhard, False), xo[1:2])
     assert xo.min().item() >= 0 and xo.max().item() <= 255
+
+
+def test_val_driver_matches_goldens(gpu_models):
+    """imgcomp_cvpr_b200.val.validate (padding, same-size batching, metric aggregation) on the golden images."""
+    from imgcomp_cvpr_b200 import val
+    ae, pc, W = gpu_models('cvpr/low')
+    g1, g2 = load_golden('tiny_low_1x64x64'), load_golden('ragged_low_2x48x72')
+    imgs = [g1['x_u8'][0], g2['x_u8'][0], np.transpose(g2['x_u8'][1], (1, 2, 0))]    # CHW and HWC accepted
+    avgs, n, rows = val.validate(imgs, ae, pc, real_bpp=False, batch_size=2)
+    assert n == 3
+    want_bpp = [g1['bpp'][0], g2['bpp'][0], g2['bpp'][1]]
+    want_ms = [g1['ms_ssim_np'][0], g2['ms_ssim_np'][0], g2['ms_ssim_np'][1]]
+    for r, b, m in zip(rows, want_bpp, want_ms):
+        assert abs(r['bpp'] - b) < 1e-4 and abs(r['ms-ssim'] - m) < 1e-4
+    assert abs(avgs['bpp'] - np.mean(want_bpp)) < 1e-4
+    # an image that needs padding: 60x70 -> 64x72, centred (images_iterator.py:39-59)
+    odd = np.transpose(g2['x_u8'][0], (1, 2, 0))[:44, :70]
+    _, _, rows2 = val.validate([odd], ae, pc)
+    assert np.isfinite(rows2[0]['bpp'])
+    rows3 = val.measure_batch(torch.from_numpy(g1['x_u8']).cuda(), ae, pc, real_bpp=True)
+    assert abs(rows3[0]['bpp_real'] - rows3[0]['bpp_theory']) * 64 * 64 < 50
