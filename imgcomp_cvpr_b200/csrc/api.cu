@@ -2,6 +2,7 @@
 // layer orchestration.  No kernels here.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -129,6 +130,7 @@ struct ic_pc {
     ic_pc_config cfg;
     PcWeights w;
     std::vector<float*> owned;
+    std::vector<__half*> owned_h;
 };
 
 extern "C" {
@@ -387,6 +389,8 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
     a.nout = L.nout_tc;
     a.halo0 = -1;
     a.img_mul = 1;
+    a.head = -1;
+    a.cpg = 8;
     a.exact = exact;
     a.prof_class = L.spec.k == 3 ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER;
     return tc::launch_conv_tc(a, s);
@@ -646,6 +650,38 @@ int ic_pc_create(const ic_pc_config* cfg, const float* const* h_tensors, int n_t
         }
         *wdst[l] = dw;
         *bdst[l] = db;
+        // tensor-core packing of layers 1..3 (arch_param__k = 24 only)
+        if (l >= 1 && cfg->arch_param_k == 24 && !getenv("IC_PC_FFMA")) {
+            std::vector<float> masked((size_t)18 * ci * co);
+            memcpy(masked.data(), w, masked.size() * sizeof(float));
+            std::vector<__half> packed;
+            float inv = 1.f;
+            const int nout = l == 3 ? 16 : 32;
+            if (tc::pack_weights_pc(masked.data(), ci, co, nout, packed, pc->w.gt[l - 1], &inv) == IC_OK) {
+                __half* dp = nullptr;
+                IC_CHECK_CUDA(cudaMalloc((void**)&dp, packed.size() * sizeof(__half)));
+                IC_CHECK_CUDA(cudaMemcpy(dp, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                pc->owned_h.push_back(dp);
+                std::vector<float> sct(128, 0.f), sht(128, 0.f);
+                for (int o = 0; o < co; ++o) {
+                    sct[o] = inv;
+                    sht[o] = bias[o];
+                }
+                float *ds = nullptr, *dh = nullptr;
+                rc = upload(sct, &ds);
+                if (rc == IC_OK) rc = upload(sht, &dh);
+                pc->owned.push_back(ds);
+                pc->owned.push_back(dh);
+                if (rc != IC_OK) {
+                    ic_pc_destroy(pc);
+                    return rc;
+                }
+                pc->w.wt[l - 1] = dp;
+                pc->w.scale_t[l - 1] = ds;
+                pc->w.shift_t[l - 1] = dh;
+                if (l == 3) pc->w.tc = true;
+            }
+        }
     }
     *out = pc;
     return IC_OK;
@@ -654,6 +690,7 @@ int ic_pc_create(const ic_pc_config* cfg, const float* const* h_tensors, int n_t
 void ic_pc_destroy(ic_pc_t* pc) {
     if (!pc) return;
     for (float* p : pc->owned) cudaFree(p);
+    for (__half* p : pc->owned_h) cudaFree(p);
     delete pc;
 }
 

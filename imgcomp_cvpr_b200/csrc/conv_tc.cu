@@ -49,10 +49,10 @@ constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels 
 constexpr int WSTAGES = 3;
 constexpr int NTHREADS = 7 * 32;
 
-template <int T, int NOUT>
+template <int T, int NOUT, int CPG>
 struct Cfg {
     static constexpr int HALO_W = TW * T + 2, HALO_H = TH + 2, HALO_PIX = HALO_W * HALO_H;
-    static constexpr int A_PLANE_BYTES = 8 * HALO_PIX * 16;       // one group = 8 chunks = 64 channels
+    static constexpr int A_PLANE_BYTES = CPG * HALO_PIX * 16;     // one group = CPG chunks of 8 channels
     static constexpr int W_PLANE_BYTES = 4 * NOUT * 16;           // one stage = 32 channels of one tap
     static constexpr int NCOL = NOUT > 64 ? 128 : 64;             // TMEM columns per accumulator tile
     static constexpr uint32_t IDESC = (1u << 4) /* D fp32 */ | (0u << 7) /* A f16 */ | (0u << 10) /* B f16 */ |
@@ -166,17 +166,17 @@ struct ResRegs {
 };
 
 template <int NPL>
-__device__ __forceinline__ void load_res(ResRegs& r, const ConvTcParams& p, size_t off0, size_t chunk_stride, size_t plane) {
+__device__ __forceinline__ void load_res(ResRegs& r, const ConvTcParams& p, size_t off1, size_t stride1, size_t plane1,
+                                         size_t off2, size_t stride2, size_t plane2) {
 #pragma unroll
     for (int hc = 0; hc < 2; ++hc) {
-        const size_t off = off0 + hc * chunk_stride;
         if (p.res1) {
-            r.v[hc][0] = ldg16(p.res1 + off);
-            if (NPL == 2) r.v[hc][1] = ldg16(p.res1 + plane + off);
+            r.v[hc][0] = ldg16(p.res1 + off1 + hc * stride1);
+            if (NPL == 2) r.v[hc][1] = ldg16(p.res1 + plane1 + off1 + hc * stride1);
         }
         if (p.res2) {
-            r.v[hc][2] = ldg16(p.res2 + off);
-            if (NPL == 2) r.v[hc][3] = ldg16(p.res2 + plane + off);
+            r.v[hc][2] = ldg16(p.res2 + off2 + hc * stride2);
+            if (NPL == 2) r.v[hc][3] = ldg16(p.res2 + plane2 + off2 + hc * stride2);
         }
     }
 }
@@ -203,11 +203,12 @@ __device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, 
     }
 }
 
-// OUTMODE 0: fp16 hi/lo planes [plane][N][NOUT/8][H][W][8]; 1: float32 NHWC [N][H][W][cout]
-template <int T, int NPL, int NOUT, int OUTMODE>
+// OUTMODE 0: fp16 hi/lo planes [plane][N][NOUT/8][H][W][8]; 1: float32 NHWC [N][H][W][cout];
+// 2: context-model head (ReLU logits -> bit cost / coder frequencies / logits), code/probclass.py:100-104,443-444
+template <int T, int NPL, int NOUT, int OUTMODE, int CPG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p, const GroupTable gt) {
-    using C = Cfg<T, NOUT>;
+    using C = Cfg<T, NOUT, CPG>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
     uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE_BYTES]
@@ -260,9 +261,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                     mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
                     const uint32_t full = smem_u32(&bars->a_full[slot]);
                     mbar_expect_tx(full, NPL * C::A_PLANE_BYTES);
+                    const int img = n * p.img_mul + (p.img_div > 0 ? (n / p.img_div) * p.img_div_mul : 0) + gt.img_off[g];
                     for (int pl = 0; pl < NPL; ++pl)
                         tma_load_5d(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
-                                    (x0 + p.halo0) * 8, y0 + p.halo0, g * 8, n * p.img_mul + gt.img_off[g], pl);
+                                    (x0 + p.halo0) * 8, y0 + p.halo0, gt.chunk0[g], img, pl);
                 }
             }
         }
@@ -299,7 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                     for (int ti = 0; ti < nt; ++ti) {
                         const int tap = gt.taps[g][ti];
                         const int dy = tap / 3, dx = tap - dy * 3;
-                        for (int j = 0; j < 2; ++j, ++ws) {
+                        for (int j = 0; j < CPG / 4; ++j, ++ws) {
                             const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
                             mbar_wait(smem_u32(&bars->w_full[slot]), ph);
                             tc_fence_after();
@@ -356,14 +358,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                 if (OUTMODE == 0) {
                     const size_t pix_off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;   // chunk 0
                     const bool has_res = (p.res1 != nullptr) || (p.res2 != nullptr);
+                    // res1 may live in a larger tensor (context model: conv0 output cropped [2:, 2:-2, 2:-2])
+                    const int rimg = n + (p.img_div > 0 ? (n / p.img_div) * p.res_div_mul : 0) + p.res_img_off;
+                    const size_t rstride = (size_t)p.res_H * p.res_W * 8;
+                    const size_t roff = ((size_t)rimg * NCH * p.res_H + y + p.res_dy) * p.res_W * 8 + (size_t)(x + p.res_dx) * 8;
                     ResRegs cur, nxt;
-                    if (inside && has_res) load_res<NPL>(cur, p, pix_off, chunk_stride, plane);
+                    if (inside && has_res) load_res<NPL>(cur, p, roff, rstride, p.res_plane, pix_off, chunk_stride, plane);
 #pragma unroll 1
                     for (int cc = 0; cc < NOUT / 16; ++cc) {
                         uint32_t rr[16];
                         tmem_ld16(taddr + cc * 16, rr);
                         if (inside && has_res && cc + 1 < NOUT / 16)
-                            load_res<NPL>(nxt, p, pix_off + (size_t)(cc + 1) * 2 * chunk_stride, chunk_stride, plane);
+                            load_res<NPL>(nxt, p, roff + (size_t)(cc + 1) * 2 * rstride, rstride, p.res_plane,
+                                          pix_off + (size_t)(cc + 1) * 2 * chunk_stride, chunk_stride, plane);
                         tmem_ld_wait();
                         if (inside) {
 #pragma unroll
@@ -399,6 +406,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                             }
                         }
                         cur = nxt;
+                    }
+                } else if (OUTMODE == 2) {
+                    uint32_t rr[16];
+                    tmem_ld16(taddr, rr);
+                    tmem_ld_wait();
+                    const int L = p.cout;
+                    const size_t v = ((size_t)n * p.H + y) * p.W + x;         // (N, D, h, w) linear index
+                    float bits = 0.f;
+                    if (inside) {
+                        float lg[8], m = 0.f;
+#pragma unroll
+                        for (int l = 0; l < 8; ++l)
+                            if (l < L) {    // bias + ReLU: the last conv3d keeps the default activation (probclass.py:220,233)
+                                lg[l] = fmaxf(fmaf(__uint_as_float(rr[l]), s_scale[l], s_shift[l]), 0.f);
+                                m = (l == 0) ? lg[l] : fmaxf(m, lg[l]);
+                            }
+                        if (p.head == 0) {
+#pragma unroll
+                            for (int l = 0; l < 8; ++l)
+                                if (l < L) p.out_f32[v * L + l] = lg[l];
+                        } else {
+                            float e[8], ssum = 0.f;
+#pragma unroll
+                            for (int l = 0; l < 8; ++l)
+                                if (l < L) {
+                                    e[l] = expf(__fsub_rn(lg[l], m));
+                                    ssum = __fadd_rn(ssum, e[l]);
+                                }
+                            const int sym = p.symbols ? (int)p.symbols[v] : 0;
+                            float lsel = 0.f;
+#pragma unroll
+                            for (int l = 0; l < 8; ++l)
+                                if (l == sym) lsel = lg[l];
+                            bits = __fmul_rn(__fsub_rn(logf(ssum), __fsub_rn(lsel, m)), 1.44269502f);
+                            if (p.head == 1) {
+                                p.out_f32[v] = bits;
+                            } else {
+#pragma unroll
+                                for (int l = 0; l < 8; ++l)
+                                    if (l < L) {
+                                        long long f = (long long)__fmul_rn(__fdiv_rn(e[l], ssum), 1e9f);
+                                        p.out_freqs[v * L + l] = f < 1 ? 1 : f;
+                                    }
+                            }
+                        }
+                    }
+                    if (p.head != 0 && p.bits_sum) {     // per-image sum: the whole warp belongs to one (n, d) slice
+                        double b = inside && p.symbols ? (double)bits : 0.0;
+                        for (int o = 16; o > 0; o >>= 1) b += __shfl_down_sync(0xffffffffu, b, o);
+                        if (lane == 0 && b != 0.0) atomicAdd(p.bits_sum + (p.img_div > 0 ? n / p.img_div : n), b);
                     }
                 } else {
                     float* o = p.out_f32 + (((size_t)n * p.H + y) * p.W + x) * p.cout;
@@ -522,9 +579,9 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int T, int NPL, int NOUT, int OUTMODE>
+template <int T, int NPL, int NOUT, int OUTMODE, int CPG>
 int launch_t(const ConvTcArgs& a, cudaStream_t s) {
-    using C = Cfg<T, NOUT>;
+    using C = Cfg<T, NOUT, CPG>;
     EncodeTiledFn enc = get_encode_fn();
     IC_REQUIRE(enc, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap map;
@@ -532,7 +589,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     const cuuint64_t dims[5] = {(cuuint64_t)a.Win * 8, (cuuint64_t)a.Hin, (cuuint64_t)a.in_chunks, (cuuint64_t)a.Nimg,
                                 (cuuint64_t)NPL};
     const cuuint64_t strides[4] = {(cuuint64_t)a.Win * 16, hw16, hw16 * a.in_chunks, hw16 * a.in_chunks * a.Nimg};
-    const cuuint32_t box[5] = {(cuuint32_t)C::HALO_W * 8, (cuuint32_t)C::HALO_H, 8, 1, 1};
+    const cuuint32_t box[5] = {(cuuint32_t)C::HALO_W * 8, (cuuint32_t)C::HALO_H, (cuuint32_t)CPG, 1, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)a.in, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -554,10 +611,23 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.cout = a.cout;
     p.halo0 = a.halo0;
     p.img_mul = a.img_mul;
+    p.img_div = a.img_div;
+    p.img_div_mul = a.img_div_mul;
+    p.res_H = a.res_H ? a.res_H : a.H;
+    p.res_W = a.res_W ? a.res_W : a.W;
+    p.res_dy = a.res_dy;
+    p.res_dx = a.res_dx;
+    p.res_div_mul = a.res_div_mul;
+    p.res_img_off = a.res_img_off;
+    p.res_plane = a.res_plane ? a.res_plane : (size_t)a.N * (NOUT / 8) * a.H * a.W * 8;
+    p.head = a.head;
+    p.symbols = a.symbols;
+    p.out_freqs = a.out_freqs;
+    p.bits_sum = a.bits_sum;
     const size_t smem = 2 * NPL * C::A_PLANE_BYTES + WSTAGES * NPL * C::W_PLANE_BYTES + 1024 + sizeof(Barriers) + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
         attr_set = true;
     }
@@ -566,9 +636,10 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_super < sms ? n_super : sms;
+    const int ctas = smem <= 110 * 1024 ? 2 * sms : sms;       // small configurations fit two CTAs per SM
+    const int grid = n_super < ctas ? n_super : ctas;
     ProfScope ps(a.prof_class, s);
-    conv_tc_kernel<T, NPL, NOUT, OUTMODE><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
+    conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -576,8 +647,14 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
 template <int NOUT, int OUTMODE>
 int launch_n(const ConvTcArgs& a, cudaStream_t s) {
     const bool wide = a.W > 8;
-    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE>(a, s) : launch_t<1, 2, NOUT, OUTMODE>(a, s);
-    return wide ? launch_t<2, 1, NOUT, OUTMODE>(a, s) : launch_t<1, 1, NOUT, OUTMODE>(a, s);
+    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE, 8>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 8>(a, s);
+    return wide ? launch_t<2, 1, NOUT, OUTMODE, 8>(a, s) : launch_t<1, 1, NOUT, OUTMODE, 8>(a, s);
+}
+
+// context model: 32-channel (4 chunk) groups, always hi/lo planes
+template <int NOUT, int OUTMODE>
+int launch_pc(const ConvTcArgs& a, cudaStream_t s) {
+    return a.W > 8 ? launch_t<2, 2, NOUT, OUTMODE, 4>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4>(a, s);
 }
 
 }  // namespace
@@ -585,8 +662,14 @@ int launch_n(const ConvTcArgs& a, cudaStream_t s) {
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     IC_REQUIRE(a.N > 0 && a.H > 0 && a.W > 0 && a.groups, IC_ERR_INVALID, "conv_tc: bad shape");
     IC_REQUIRE(((uintptr_t)a.in & 15) == 0, IC_ERR_INVALID, "conv_tc: unaligned input");
-    if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
-    if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
+    if (a.cpg == 4) {
+        IC_REQUIRE(a.exact, IC_ERR_UNSUPPORTED, "conv_tc: the context model runs in hi/lo precision only");
+        if (a.nout == 32 && a.out) return launch_pc<32, 0>(a, s);
+        if (a.nout == 16 && a.head >= 0) return launch_pc<16, 2>(a, s);
+    } else {
+        if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
+        if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
+    }
     set_error("conv_tc: unsupported output configuration (nout=%d)", a.nout);
     return IC_ERR_UNSUPPORTED;
 }
@@ -664,6 +747,7 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
     }
     if (gtaps.size() > 16) return IC_ERR_UNSUPPORTED;
     gt.ngroups = (int)gtaps.size();
+    for (int g = 0; g < gt.ngroups; ++g) gt.chunk0[g] = (uint8_t)(g * 8);
     const size_t plane_elems = (size_t)4 * nout * 8;
     packed.clear();
     int nst = 0;
@@ -696,6 +780,54 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
                         }
             }
         }
+    }
+    gt.nstages = nst;
+    return IC_OK;
+}
+
+// Context-model layer: conv3d weights [2][3][3][ci][co] (code/probclass.py:249-257) with the "other" mask
+// (code/probclass.py:164-176) -> 2 groups (filter depth 0: 9 taps, depth 1: 5 taps) of one 32-channel stage
+// per tap; ci <= 32 and co <= nout are zero padded.
+int pack_weights_pc(const float* w, int ci, int co, int nout, std::vector<__half>& packed, GroupTable& gt,
+                    float* inv_scale_out) {
+    if (ci > 32 || co > nout) return IC_ERR_UNSUPPORTED;
+    float mx = 0.f;
+    for (int i = 0; i < 18 * ci * co; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    int e = 0;
+    if (mx > 0.f) {
+        int ex;
+        frexpf(mx, &ex);
+        e = 8 - ex;
+    }
+    const float sc = ldexpf(1.f, e);
+    *inv_scale_out = ldexpf(1.f, -e);
+    memset(&gt, 0, sizeof(gt));
+    gt.ngroups = 2;
+    const size_t plane_elems = (size_t)4 * nout * 8;
+    packed.clear();
+    int nst = 0;
+    for (int fd = 0; fd < 2; ++fd) {
+        int nt = 0;
+        gt.img_off[fd] = (uint8_t)fd;
+        gt.chunk0[fd] = 0;
+        for (int fy = 0; fy < 3; ++fy)
+            for (int fx = 0; fx < 3; ++fx) {
+                if (fd == 1 && (fy > 1 || (fy == 1 && fx > 1))) continue;
+                gt.taps[fd][nt++] = (uint8_t)(fy * 3 + fx);
+                const size_t base = packed.size();
+                packed.resize(base + 2 * plane_elems, __float2half(0.f));
+                for (int c = 0; c < ci; ++c)
+                    for (int o = 0; o < co; ++o) {
+                        const float v = w[((((size_t)fd * 3 + fy) * 3 + fx) * ci + c) * co + o] * sc;
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t idx = ((size_t)(c / 8) * nout + o) * 8 + (c % 8);
+                        packed[base + idx] = hi;
+                        packed[base + plane_elems + idx] = lo;
+                    }
+                ++nst;
+            }
+        gt.ntaps[fd] = (uint8_t)nt;
     }
     gt.nstages = nst;
     return IC_OK;

@@ -16,6 +16,7 @@ struct GroupTable {
     uint8_t ntaps[16];
     uint8_t taps[16][9];     // dy*3+dx halo offsets
     uint8_t img_off[16];     // added to the image coordinate of the TMA load (0 for 2-D convs)
+    uint8_t chunk0[16];      // first channel chunk of the group
 };
 
 // kernel parameters (device pointers)
@@ -28,8 +29,17 @@ struct ConvTcParams {
     __half* out;                // OUTMODE 0: [2][N][NOUT/8][H][W][8]
     float* out_f32;             // OUTMODE 1: [N][H][W][cout]
     int N, H, W, relu, cout;
-    int halo0;                  // origin of the halo tile relative to the output tile (-1: SAME 3x3-like)
-    int img_mul;                // image coordinate = n * img_mul + img_off[group]
+    int halo0;                  // origin of the halo tile relative to the output tile (-1: SAME 3x3-like, 0: VALID)
+    // input image coordinate = n * img_mul + (n / img_div) * img_div_mul + img_off[group]   (img_div = 0: off)
+    int img_mul, img_div, img_div_mul;
+    // geometry of res1 (context model: a crop of a larger tensor); res2 always has the output geometry
+    int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
+    size_t res_plane;
+    // OUTMODE 2 (context-model head): 0 logits, 1 bit cost, 2 coder frequencies (+ bit cost sums)
+    int head;
+    const int64_t* symbols;
+    int64_t* out_freqs;
+    double* bits_sum;
 };
 
 struct ConvTcArgs {
@@ -43,7 +53,14 @@ struct ConvTcArgs {
     float* out_f32;
     int N, H, W;                // output tile grid
     int relu, cout, nout;       // nout: padded output channels the weights were packed for (128 or 48)
-    int halo0, img_mul;
+    int halo0, img_mul, img_div, img_div_mul;
+    int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
+    size_t res_plane;
+    int head;                   // -1: none
+    const int64_t* symbols;
+    int64_t* out_freqs;
+    double* bits_sum;
+    int cpg;                    // chunks per group: 8 (64 channels) or 4 (context model)
     int exact;                  // 1: hi/lo planes, 3 MMAs per product; 0: hi plane only
     int prof_class;
 };
@@ -52,6 +69,8 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s);
 int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s);
 int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s);
 int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
+int pack_weights_pc(const float* w, int ci, int co, int nout, std::vector<__half>& packed, GroupTable& gt,
+                    float* inv_scale_out);
 int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int nout, std::vector<__half>& packed,
                  GroupTable& gt, float* inv_scale_out);
 

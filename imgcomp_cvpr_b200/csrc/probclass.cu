@@ -11,6 +11,9 @@
 // order, input channels ascending, bias last) and does not depend on the
 // position in the volume: the batched pass over a whole latent and the
 // per-context evaluation of code/probclass.py:441-476 give bit-identical logits.
+#include <cuda_fp16.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "probclass.cuh"
 
@@ -34,12 +37,14 @@ struct SrcSymbols {
     __device__ float at(int64_t idx) const { return centers[(int)sym[idx]]; }
 };
 
-template <int KC, typename Src>
+// SPLIT = false: float32 N,D0,H0,W0,KC.  SPLIT = true: fp16 hi/lo planes [plane][N*D0][4][H0][W0][8]
+// (channels padded to 32), the input layout of the tensor-core layers.
+template <int KC, typename Src, bool SPLIT>
 __global__ void __launch_bounds__(128) pc_conv0_kernel(Src src, int D, int H, int W, int pd, int ph,
                                                        const float* __restrict__ wgt,   // [13][KC]
                                                        const float* __restrict__ bias,  // [KC]
                                                        int D0, int H0, int W0, int64_t total,
-                                                       float* __restrict__ out) {       // N,D0,H0,W0,KC
+                                                       float* __restrict__ out, __half* __restrict__ out_split) {
     __shared__ float sw[13 * KC + KC];
     for (int i = threadIdx.x; i < 13 * KC; i += blockDim.x) sw[i] = wgt[i];
     for (int i = threadIdx.x; i < KC; i += blockDim.x) sw[13 * KC + i] = bias[i];
@@ -67,14 +72,45 @@ __global__ void __launch_bounds__(128) pc_conv0_kernel(Src src, int D, int H, in
                     val = src.at(((n * D + zd) * H + zy) * (int64_t)W + zx);
                 in[t++] = val;
             }
-    float* o = out + v * KC;
+    if (!SPLIT) {
+        float* o = out + v * KC;
 #pragma unroll 4
-    for (int co = 0; co < KC; ++co) {
-        float acc = 0.f;
+        for (int co = 0; co < KC; ++co) {
+            float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 13; ++k) acc = fmaf(in[k], sw[k * KC + co], acc);
-        acc += sw[13 * KC + co];
-        o[co] = fmaxf(acc, 0.f);
+            for (int k = 0; k < 13; ++k) acc = fmaf(in[k], sw[k * KC + co], acc);
+            acc += sw[13 * KC + co];
+            o[co] = fmaxf(acc, 0.f);
+        }
+    } else {
+        const size_t cs = (size_t)H0 * W0 * 8;                         // chunk stride (elements)
+        const size_t plane = (size_t)(total / ((int64_t)H0 * W0)) * 4 * cs;
+        const size_t base = (((size_t)(n * D0 + d) * 4) * H0 + y) * W0 * 8 + (size_t)x * 8;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            __align__(16) __half2 hi[4];
+            __align__(16) __half2 lo[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                float r[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int co = c * 8 + e2 * 2 + u;
+                    float acc = 0.f;
+                    if (co < KC) {
+#pragma unroll
+                        for (int k = 0; k < 13; ++k) acc = fmaf(in[k], sw[k * KC + co], acc);
+                        acc = fmaxf(acc + sw[13 * KC + co], 0.f);
+                    }
+                    r[u] = acc;
+                }
+                hi[e2] = __floats2half2_rn(r[0], r[1]);
+                float2 hf = __half22float2(hi[e2]);
+                lo[e2] = __floats2half2_rn(r[0] - hf.x, r[1] - hf.y);
+            }
+            *reinterpret_cast<float4*>(out_split + base + c * cs) = *reinterpret_cast<const float4*>(hi);
+            *reinterpret_cast<float4*>(out_split + plane + base + c * cs) = *reinterpret_cast<const float4*>(lo);
+        }
     }
 }
 
@@ -281,10 +317,10 @@ int run_pc(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_
         src.sym = in.symbols;
         for (int i = 0; i < 8; ++i) src.centers[i] = i < L ? in.centers_host[i] : 0.f;
         src.pad_value = in.centers_host[0];
-        pc_conv0_kernel<KC, SrcSymbols><<<cdiv(t0, 128), 128, 0, s>>>(src, D, H, W, pd, ph, w.w0, w.b0, D0, H0, W0, t0, a0);
+        pc_conv0_kernel<KC, SrcSymbols, false><<<cdiv(t0, 128), 128, 0, s>>>(src, D, H, W, pd, ph, w.w0, w.b0, D0, H0, W0, t0, a0, nullptr);
     } else {
         SrcFloat src{in.q, in.pad_value};
-        pc_conv0_kernel<KC, SrcFloat><<<cdiv(t0, 128), 128, 0, s>>>(src, D, H, W, pd, ph, w.w0, w.b0, D0, H0, W0, t0, a0);
+        pc_conv0_kernel<KC, SrcFloat, false><<<cdiv(t0, 128), 128, 0, s>>>(src, D, H, W, pd, ph, w.w0, w.b0, D0, H0, W0, t0, a0, nullptr);
     }
     IC_CHECK_LAUNCH();
     int64_t t1 = (int64_t)N * D1 * H1 * W1;
@@ -306,22 +342,120 @@ int run_pc(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_
     return IC_OK;
 }
 
+
+// ---------------------------------------------------------------- tensor-core path (K = 24)
+// conv0 stays FFMA (Cin = 1, 13 taps) but writes the hi/lo plane layout; layers 1..3 run on the
+// grouped-tap tcgen05 kernel (conv_tc.cu): "image" = one (n, depth) slice, group = filter depth,
+// VALID taps, 24 -> 32 padded channels, float32-class hi/lo arithmetic.
+int run_pc_tc(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs, double* bits_sum,
+              void* ws, size_t ws_bytes, cudaStream_t s) {
+    const int N = in.N, D = in.D, H = in.H, W = in.W, pd = in.pad_d, ph = in.pad_hw, L = w.L;
+    const int Dp = D + pd, Hp = H + 2 * ph, Wp = W + 2 * ph;
+    IC_REQUIRE(Dp >= 5 && Hp >= 9 && Wp >= 9, IC_ERR_INVALID, "probclass: volume %dx%dx%d smaller than the 5x9x9 context",
+               Dp, Hp, Wp);
+    int Dl[4], Hl[4], Wl[4];
+    Dl[0] = Dp - 1; Hl[0] = Hp - 2; Wl[0] = Wp - 2;
+    for (int l = 1; l < 4; ++l) {
+        Dl[l] = Dl[l - 1] - 1; Hl[l] = Hl[l - 1] - 2; Wl[l] = Wl[l - 1] - 2;
+    }
+    Arena ar(ws, ws_bytes);
+    __half* a[3];
+    size_t plane[3];
+    for (int l = 0; l < 3; ++l) {
+        plane[l] = (size_t)N * Dl[l] * 4 * Hl[l] * Wl[l] * 8;
+        a[l] = ar.get<__half>(2 * plane[l]);
+    }
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "probclass workspace too small: need %zu, have %zu", ar.off, ws_bytes);
+    const int64_t t0 = (int64_t)N * Dl[0] * Hl[0] * Wl[0];
+    {
+        ProfScope ps(IC_PROF_PROBCLASS, s, 1);
+        if (in.symbols) {
+            SrcSymbols src;
+            src.sym = in.symbols;
+            for (int i = 0; i < 8; ++i) src.centers[i] = i < L ? in.centers_host[i] : 0.f;
+            src.pad_value = in.centers_host[0];
+            pc_conv0_kernel<24, SrcSymbols, true><<<cdiv(t0, 128), 128, 0, s>>>(src, D, H, W, pd, ph, w.w0, w.b0, Dl[0], Hl[0],
+                                                                                Wl[0], t0, nullptr, a[0]);
+        } else {
+            SrcFloat src{in.q, in.pad_value};
+            pc_conv0_kernel<24, SrcFloat, true><<<cdiv(t0, 128), 128, 0, s>>>(src, D, H, W, pd, ph, w.w0, w.b0, Dl[0], Hl[0],
+                                                                              Wl[0], t0, nullptr, a[0]);
+        }
+        IC_CHECK_LAUNCH();
+    }
+    if (bits_sum && head != PC_HEAD_LOGITS) IC_CHECK_CUDA(cudaMemsetAsync(bits_sum, 0, sizeof(double) * N, s));
+    for (int l = 1; l <= 3; ++l) {
+        tc::ConvTcArgs c;
+        memset(&c, 0, sizeof(c));
+        c.in = a[l - 1];
+        c.Nimg = N * Dl[l - 1];
+        c.in_chunks = 4;
+        c.Hin = Hl[l - 1];
+        c.Win = Wl[l - 1];
+        c.weights = w.wt[l - 1];
+        c.groups = &w.gt[l - 1];
+        c.scale = w.scale_t[l - 1];
+        c.shift = w.shift_t[l - 1];
+        c.N = N * Dl[l];
+        c.H = Hl[l];
+        c.W = Wl[l];
+        c.halo0 = 0;
+        c.img_mul = 1;
+        c.img_div = Dl[l];
+        c.img_div_mul = 1;                      // D_in - D_out
+        c.cpg = 4;
+        c.exact = 1;
+        c.head = -1;
+        c.prof_class = IC_PROF_PROBCLASS;
+        if (l < 3) {
+            c.out = a[l];
+            c.nout = 32;
+            c.cout = 24;
+            c.relu = (l == 1);
+            if (l == 2) {                       // + residual_input[..., 2:, 2:-2, 2:-2, :]  (code/probclass.py:196)
+                c.res1 = a[0];
+                c.res_H = Hl[0];
+                c.res_W = Wl[0];
+                c.res_dy = 2;
+                c.res_dx = 2;
+                c.res_div_mul = 2;              // D_res - D_out
+                c.res_img_off = 2;
+                c.res_plane = plane[0];
+            }
+        } else {
+            c.nout = 16;
+            c.cout = L;
+            c.relu = 1;
+            c.head = head;
+            c.symbols = in.target_symbols;
+            c.out_f32 = out_f;
+            c.out_freqs = out_freqs;
+            c.bits_sum = bits_sum;
+        }
+        int rc = tc::launch_conv_tc(c, s);
+        if (rc != IC_OK) return rc;
+    }
+    return IC_OK;
+}
+
 }  // namespace
 
 size_t pc_workspace_bytes(int KC, int N, int D, int H, int W, int pad_d, int pad_hw) {
     const int64_t Dp = D + pad_d, Hp = H + 2 * pad_hw, Wp = W + 2 * pad_hw;
     size_t b = 0;
     int64_t d = Dp, h = Hp, w = Wp;
+    const size_t per_voxel = KC == 24 ? 32 * 4 : KC * sizeof(float);     // tensor-core path: 32 ch x (hi+lo)
     for (int l = 0; l < 3; ++l) {
         d -= 1; h -= 2; w -= 2;
         if (d <= 0 || h <= 0 || w <= 0) return 0;
-        b = align_up(b, 256) + (size_t)N * d * h * w * KC * sizeof(float);
+        b = align_up(b, 256) + (size_t)N * d * h * w * per_voxel;
     }
     return b + 1024;
 }
 
 int pc_forward(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs,
                double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s) {
+    if (w.K == 24 && w.tc) return run_pc_tc(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
     if (w.K == 24) return run_pc<24>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
     if (w.K == 64) return run_pc<64>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
     set_error("probclass: arch_param__k = %d not built (24 and 64 are)", w.K);

@@ -1,6 +1,7 @@
 // Internal interface of the context-model kernels (probclass.cu).
 #pragma once
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace ic {
 
@@ -11,6 +12,12 @@ namespace ic {
 struct PcWeights {
     int K, L;
     const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3;
+    // tensor-core path (K = 24): layers 1..3 packed for conv_tc (fp16 hi/lo, 32-channel stages)
+    bool tc = false;
+    const __half* wt[3] = {nullptr, nullptr, nullptr};
+    const float* scale_t[3] = {nullptr, nullptr, nullptr};   // [128] weight pre-scale inverse
+    const float* shift_t[3] = {nullptr, nullptr, nullptr};   // [128] bias, zero padded
+    tc::GroupTable gt[3];
 };
 
 struct PcInput {
