@@ -390,7 +390,7 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
     a.halo0 = -1;
     a.img_mul = 1;
     a.head = -1;
-    a.cpg = 8;
+    a.cpg = 4;
     a.exact = exact;
     a.prof_class = L.spec.k == 3 ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER;
     return tc::launch_conv_tc(a, s);

@@ -46,13 +46,16 @@ namespace tc {
 namespace {
 
 constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels = M 128
-constexpr int WSTAGES = 3;
+constexpr int MAX_WSTAGES = 8;
 constexpr int NTHREADS = 7 * 32;
 
 template <int T, int NOUT, int CPG>
 struct Cfg {
     static constexpr int HALO_W = TW * T + 2, HALO_H = TH + 2, HALO_PIX = HALO_W * HALO_H;
     static constexpr int A_PLANE_BYTES = CPG * HALO_PIX * 16;     // one group = CPG chunks of 8 channels
+    // weight pipeline depth: a refill takes ~1 us (commit -> producer -> L2 -> smem) while a stage is consumed in
+    // 0.3-0.5 us, so >= 4 stages must be in flight; 8 x 16 KB fits beside two 41 KB activation groups
+    static constexpr int WSTAGES = NOUT == 128 ? 8 : 6;
     static constexpr int W_PLANE_BYTES = 4 * NOUT * 16;           // one stage = 32 channels of one tap
     static constexpr int NCOL = NOUT > 64 ? 128 : 64;             // TMEM columns per accumulator tile
     static constexpr uint32_t IDESC = (1u << 4) /* D fp32 */ | (0u << 7) /* A f16 */ | (0u << 10) /* B f16 */ |
@@ -128,7 +131,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 struct __align__(8) Barriers {
-    uint64_t a_full[2], a_empty[2], w_full[WSTAGES], w_empty[WSTAGES], acc_full[2], acc_empty[2];
+    uint64_t a_full[2], a_empty[2], w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
@@ -211,6 +214,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
     using C = Cfg<T, NOUT, CPG>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
+    constexpr int WSTAGES = C::WSTAGES;
     uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE_BYTES]
     float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * C::W_PLANE_BYTES);
     float* s_shift = s_scale + 128;
@@ -624,7 +628,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.symbols = a.symbols;
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
-    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + WSTAGES * NPL * C::W_PLANE_BYTES + 1024 + sizeof(Barriers) + 64;
+    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + C::WSTAGES * NPL * C::W_PLANE_BYTES + 1024 + sizeof(Barriers) + 64;
     static bool attr_set = false;
     if (!attr_set) {
         IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -636,7 +640,9 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ctas = smem <= 110 * 1024 ? 2 * sms : sms;       // small configurations fit two CTAs per SM
+    // two CTAs per SM only if both shared memory and TMEM (512 columns per SM) allow it
+    const int tmem_cols = 2 * T * C::NCOL;
+    const int ctas = (smem <= 110 * 1024 && tmem_cols <= 256) ? 2 * sms : sms;
     const int grid = n_super < ctas ? n_super : ctas;
     ProfScope ps(a.prof_class, s);
     conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
@@ -647,8 +653,8 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
 template <int NOUT, int OUTMODE>
 int launch_n(const ConvTcArgs& a, cudaStream_t s) {
     const bool wide = a.W > 8;
-    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE, 8>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 8>(a, s);
-    return wide ? launch_t<2, 1, NOUT, OUTMODE, 8>(a, s) : launch_t<1, 1, NOUT, OUTMODE, 8>(a, s);
+    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE, 4>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4>(a, s);
+    return wide ? launch_t<2, 1, NOUT, OUTMODE, 4>(a, s) : launch_t<1, 1, NOUT, OUTMODE, 4>(a, s);
 }
 
 // context model: 32-channel (4 chunk) groups, always hi/lo planes
@@ -662,14 +668,12 @@ int launch_pc(const ConvTcArgs& a, cudaStream_t s) {
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     IC_REQUIRE(a.N > 0 && a.H > 0 && a.W > 0 && a.groups, IC_ERR_INVALID, "conv_tc: bad shape");
     IC_REQUIRE(((uintptr_t)a.in & 15) == 0, IC_ERR_INVALID, "conv_tc: unaligned input");
-    if (a.cpg == 4) {
-        IC_REQUIRE(a.exact, IC_ERR_UNSUPPORTED, "conv_tc: the context model runs in hi/lo precision only");
-        if (a.nout == 32 && a.out) return launch_pc<32, 0>(a, s);
-        if (a.nout == 16 && a.head >= 0) return launch_pc<16, 2>(a, s);
-    } else {
-        if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
-        if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
-    }
+    IC_REQUIRE(a.cpg == 4, IC_ERR_UNSUPPORTED, "conv_tc: groups are 32 channels (4 chunks)");
+    if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
+    if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
+    if (a.nout == 32 || a.nout == 16) IC_REQUIRE(a.exact, IC_ERR_UNSUPPORTED, "conv_tc: the context model runs in hi/lo precision only");
+    if (a.nout == 32 && a.out) return launch_pc<32, 0>(a, s);
+    if (a.nout == 16 && a.head >= 0) return launch_pc<16, 2>(a, s);
     set_error("conv_tc: unsupported output configuration (nout=%d)", a.nout);
     return IC_ERR_UNSUPPORTED;
 }
@@ -709,7 +713,7 @@ int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, 
 // Stage = (group, tap, cin32 block j); within a stage [plane][4 chunks][nout rows][8 cin].
 int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int nout, std::vector<__half>& packed,
                  GroupTable& gt, float* inv_scale_out) {
-    if (!((k == 3 && stride == 1) || (k == 5 && stride == 2)) || cin % 64 != 0 || cout > nout) return IC_ERR_UNSUPPORTED;
+    if (!((k == 3 && stride == 1) || (k == 5 && stride == 2)) || cin % 32 != 0 || cout > nout) return IC_ERR_UNSUPPORTED;
     float mx = 0.f;
     for (size_t i = 0; i < (size_t)k * k * cin * cout; ++i) mx = fmaxf(mx, fabsf(w_hwio[i]));
     int e = 0;
@@ -720,40 +724,40 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
     }
     const float sc = ldexpf(1.f, e);
     *inv_scale_out = ldexpf(1.f, -e);
-    const int halves = cin / 64;
+    const int quarters = cin / 32;            // one group = 32 input channels (4 chunks)
     memset(&gt, 0, sizeof(gt));
     struct Tap { int ky, kx; };
     std::vector<std::vector<Tap>> gtaps;
-    std::vector<int> ghalf;
+    std::vector<int> gq;
     if (stride == 1) {
-        for (int h = 0; h < halves; ++h) {
+        for (int q = 0; q < quarters; ++q) {
             std::vector<Tap> t;
             for (int ky = 0; ky < 3; ++ky)
                 for (int kx = 0; kx < 3; ++kx) t.push_back({ky, kx});
             gtaps.push_back(t);
-            ghalf.push_back(h);
+            gq.push_back(q);
         }
     } else {
         for (int py = 0; py < 2; ++py)
             for (int px = 0; px < 2; ++px)
-                for (int h = 0; h < halves; ++h) {
+                for (int q = 0; q < quarters; ++q) {
                     std::vector<Tap> t;
                     for (int ky = 0; ky < 5; ++ky)
                         for (int kx = 0; kx < 5; ++kx)
                             if ((((ky - 1) & 1) == py) && (((kx - 1) & 1) == px)) t.push_back({ky, kx});
                     gtaps.push_back(t);
-                    ghalf.push_back(h);
+                    gq.push_back(q);
                 }
     }
     if (gtaps.size() > 16) return IC_ERR_UNSUPPORTED;
     gt.ngroups = (int)gtaps.size();
-    for (int g = 0; g < gt.ngroups; ++g) gt.chunk0[g] = (uint8_t)(g * 8);
+    for (int g = 0; g < gt.ngroups; ++g) gt.chunk0[g] = (uint8_t)(g * 4);
     const size_t plane_elems = (size_t)4 * nout * 8;
     packed.clear();
     int nst = 0;
     for (size_t g = 0; g < gtaps.size(); ++g) {
         gt.ntaps[g] = (uint8_t)gtaps[g].size();
-        for (size_t ti = 0; ti < gtaps[g].size(); ++ti) {
+        for (size_t ti = 0; ti < gtaps[g].size(); ++ti, ++nst) {
             const Tap tp = gtaps[g][ti];
             int dy, dx;
             if (stride == 1) {
@@ -764,21 +768,19 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
                 dx = ((tp.kx - 1) >> 1) + 1;
             }
             gt.taps[g][ti] = (uint8_t)(dy * 3 + dx);
-            for (int j = 0; j < 2; ++j, ++nst) {
-                const size_t base = packed.size();
-                packed.resize(base + 2 * plane_elems, __float2half(0.f));
-                for (int ch = 0; ch < 4; ++ch)
-                    for (int co = 0; co < cout; ++co)
-                        for (int ei = 0; ei < 8; ++ei) {
-                            const int ci = ghalf[g] * 64 + j * 32 + ch * 8 + ei;
-                            const float v = w_hwio[(((size_t)tp.ky * k + tp.kx) * cin + ci) * cout + co] * sc;
-                            const __half hi = __float2half_rn(v);
-                            const __half lo = __float2half_rn(v - __half2float(hi));
-                            const size_t idx = ((size_t)ch * nout + co) * 8 + ei;
-                            packed[base + idx] = hi;
-                            packed[base + plane_elems + idx] = lo;
-                        }
-            }
+            const size_t base = packed.size();
+            packed.resize(base + 2 * plane_elems, __float2half(0.f));
+            for (int ch = 0; ch < 4; ++ch)
+                for (int co = 0; co < cout; ++co)
+                    for (int ei = 0; ei < 8; ++ei) {
+                        const int ci = gq[g] * 32 + ch * 8 + ei;
+                        const float v = w_hwio[(((size_t)tp.ky * k + tp.kx) * cin + ci) * cout + co] * sc;
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t idx = ((size_t)ch * nout + co) * 8 + ei;
+                        packed[base + idx] = hi;
+                        packed[base + plane_elems + idx] = lo;
+                    }
         }
     }
     gt.nstages = nst;
