@@ -47,6 +47,7 @@ namespace {
 
 constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels = M 128
 constexpr int MAX_WSTAGES = 8;
+constexpr int MAX_RES_STAGES = 14;          // resident-weight mode: the context model has 14 non-masked taps
 constexpr int NTHREADS = 7 * 32;
 
 template <int T, int NOUT, int CPG>
@@ -208,13 +209,14 @@ __device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, 
 
 // OUTMODE 0: fp16 hi/lo planes [plane][N][NOUT/8][H][W][8]; 1: float32 NHWC [N][H][W][cout];
 // 2: context-model head (ReLU logits -> bit cost / coder frequencies / logits), code/probclass.py:100-104,443-444
-template <int T, int NPL, int NOUT, int OUTMODE, int CPG>
+// WRES: all weight stages of the layer stay resident in shared memory (loaded once per CTA; context model)
+template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p, const GroupTable gt) {
     using C = Cfg<T, NOUT, CPG>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
-    constexpr int WSTAGES = C::WSTAGES;
+    constexpr int WSTAGES = WRES ? MAX_RES_STAGES : C::WSTAGES;
     uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE_BYTES]
     float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * C::W_PLANE_BYTES);
     float* s_shift = s_scale + 128;
@@ -275,64 +277,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
     } else if (warp == 1) {
         // ===================== weight producer =====================
         if (lane == 0) {
-            uint32_t ws = 0;     // running stage counter
-            for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
-                for (int s = 0; s < gt.nstages; ++s, ++ws) {      // (group, tap, cin32 block) in MMA order
-                    const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
-                    mbar_wait(smem_u32(&bars->w_empty[slot]), ph ^ 1);
-                    const uint32_t full = smem_u32(&bars->w_full[slot]);
-                    mbar_expect_tx(full, NPL * C::W_PLANE_BYTES);
-                    // global stage = [2 planes][W_PLANE_BYTES]; FAST mode copies the hi plane only
-                    bulk_load(smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES),
-                              p.weights + (size_t)s * 2 * C::W_PLANE_BYTES, NPL * C::W_PLANE_BYTES, full);
+            if (WRES) {
+                // every stage of the layer fits: one load, one barrier (w_full[0]), never refilled
+                const uint32_t full = smem_u32(&bars->w_full[0]);
+                mbar_expect_tx(full, gt.nstages * NPL * C::W_PLANE_BYTES);
+                for (int s = 0; s < gt.nstages; ++s)
+                    bulk_load(smem_u32(w_buf + s * NPL * C::W_PLANE_BYTES), p.weights + (size_t)s * 2 * C::W_PLANE_BYTES,
+                              NPL * C::W_PLANE_BYTES, full);
+            } else {
+                uint32_t ws = 0;     // running stage counter
+                for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+                    for (int s = 0; s < gt.nstages; ++s, ++ws) {      // (group, tap) in MMA order
+                        const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
+                        mbar_wait(smem_u32(&bars->w_empty[slot]), ph ^ 1);
+                        const uint32_t full = smem_u32(&bars->w_full[slot]);
+                        mbar_expect_tx(full, NPL * C::W_PLANE_BYTES);
+                        // global stage = [2 planes][W_PLANE_BYTES]; FAST mode copies the hi plane only
+                        bulk_load(smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES),
+                                  p.weights + (size_t)s * 2 * C::W_PLANE_BYTES, NPL * C::W_PLANE_BYTES, full);
+                    }
                 }
             }
         }
     } else if (warp == 2) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
+            // Descriptors are 64-bit words whose low 14 bits hold (address >> 4): every tap / k-step / tile /
+            // plane variant is the base descriptor plus a small constant, so the issue loop is adds + MMAs only.
+            constexpr uint32_t kALbo = C::HALO_PIX * 16, kASbo = C::HALO_W * 16;
+            constexpr uint64_t kAPlane = C::A_PLANE_BYTES >> 4, kWPlane = C::W_PLANE_BYTES >> 4;
+            constexpr uint64_t kAKs = (2 * C::HALO_PIX * 16) >> 4, kWKs = (2 * NOUT * 16) >> 4;
+            const uint64_t a_desc0 = make_desc(smem_u32(a_buf), kALbo, kASbo);
+            const uint64_t w_desc0 = make_desc(smem_u32(w_buf), NOUT * 16, 128);
             uint32_t it = 0, ws = 0, gi = 0;
+            if (WRES) {
+                mbar_wait(smem_u32(&bars->w_full[0]), 0);
+                tc_fence_after();
+            }
             for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
                 const uint32_t set = it & 1;
                 mbar_wait(smem_u32(&bars->acc_empty[set]), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
+                uint32_t sidx = 0;      // stage index within the layer (resident mode)
                 for (int g = 0; g < gt.ngroups; ++g, ++gi) {
                     const uint32_t aslot = gi & 1;
                     mbar_wait(smem_u32(&bars->a_full[aslot]), (gi >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_buf + aslot * NPL * C::A_PLANE_BYTES);
+                    const uint64_t a_g = a_desc0 + (uint64_t)aslot * (NPL * kAPlane);
                     const int nt = gt.ntaps[g];
-                    for (int ti = 0; ti < nt; ++ti) {
+                    for (int ti = 0; ti < nt; ++ti, ++ws, ++sidx) {
                         const int tap = gt.taps[g][ti];
                         const int dy = tap / 3, dx = tap - dy * 3;
-                        for (int j = 0; j < CPG / 4; ++j, ++ws) {
-                            const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
-                            mbar_wait(smem_u32(&bars->w_full[slot]), ph);
+                        uint32_t slot;
+                        if (WRES) {
+                            slot = sidx;
+                        } else {
+                            slot = ws % WSTAGES;
+                            mbar_wait(smem_u32(&bars->w_full[slot]), (ws / WSTAGES) & 1);
                             tc_fence_after();
-                            const uint32_t w_base = smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES);
+                        }
+                        const uint64_t a_t = a_g + (uint64_t)(dy * C::HALO_W + dx);
+                        const uint64_t w_t = w_desc0 + (uint64_t)slot * (NPL * kWPlane);
 #pragma unroll
-                            for (int t = 0; t < T; ++t) {
-                                const uint32_t d_tmem = tmem_base + (set * T + t) * C::NCOL;
+                        for (int t = 0; t < T; ++t) {
+                            const uint32_t d_tmem = tmem_base + (set * T + t) * C::NCOL;
 #pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {
-                                    const uint32_t a_off = (uint32_t)(j * 4 + ks * 2) * (C::HALO_PIX * 16) +
-                                                           (uint32_t)(dy * C::HALO_W + dx + t * TW) * 16;
-                                    const uint32_t w_off = (uint32_t)(ks * 2) * (NOUT * 16);
-                                    const uint64_t a_hi = make_desc(a_base + a_off, C::HALO_PIX * 16, C::HALO_W * 16);
-                                    const uint64_t w_hi = make_desc(w_base + w_off, NOUT * 16, 128);
-                                    const uint32_t first = (g | ti | j | ks) == 0 ? 0u : 1u;
-                                    umma_f16(d_tmem, a_hi, w_hi, C::IDESC, first);
-                                    if (NPL == 2) {
-                                        const uint64_t a_lo = make_desc(a_base + C::A_PLANE_BYTES + a_off, C::HALO_PIX * 16,
-                                                                        C::HALO_W * 16);
-                                        const uint64_t w_lo = make_desc(w_base + C::W_PLANE_BYTES + w_off, NOUT * 16, 128);
-                                        umma_f16(d_tmem, a_hi, w_lo, C::IDESC, 1u);
-                                        umma_f16(d_tmem, a_lo, w_hi, C::IDESC, 1u);
-                                    }
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t a_hi = a_t + (uint64_t)(t * TW) + ks * kAKs;
+                                const uint64_t w_hi = w_t + ks * kWKs;
+                                const uint32_t first = (g | ti | ks) == 0 ? 0u : 1u;
+                                umma_f16(d_tmem, a_hi, w_hi, C::IDESC, first);
+                                if (NPL == 2) {
+                                    umma_f16(d_tmem, a_hi, w_hi + kWPlane, C::IDESC, 1u);
+                                    umma_f16(d_tmem, a_hi + kAPlane, w_hi, C::IDESC, 1u);
                                 }
                             }
-                            umma_commit(smem_u32(&bars->w_empty[slot]));    // stage free once these MMAs retire
                         }
+                        if (!WRES) umma_commit(smem_u32(&bars->w_empty[slot]));    // stage free once these MMAs retire
                     }
                     umma_commit(smem_u32(&bars->a_empty[aslot]));
                 }
@@ -583,9 +604,10 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int T, int NPL, int NOUT, int OUTMODE, int CPG>
+template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES>
 int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     using C = Cfg<T, NOUT, CPG>;
+    IC_REQUIRE(!WRES || a.groups->nstages <= MAX_RES_STAGES, IC_ERR_UNSUPPORTED, "conv_tc: too many stages for resident weights");
     EncodeTiledFn enc = get_encode_fn();
     IC_REQUIRE(enc, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap map;
@@ -628,10 +650,11 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.symbols = a.symbols;
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
-    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + C::WSTAGES * NPL * C::W_PLANE_BYTES + 1024 + sizeof(Barriers) + 64;
+    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + (WRES ? MAX_RES_STAGES : C::WSTAGES) * NPL * C::W_PLANE_BYTES + 1024 +
+                        sizeof(Barriers) + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
         attr_set = true;
     }
@@ -645,7 +668,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     const int ctas = (smem <= 110 * 1024 && tmem_cols <= 256) ? 2 * sms : sms;
     const int grid = n_super < ctas ? n_super : ctas;
     ProfScope ps(a.prof_class, s);
-    conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
+    conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -653,14 +676,14 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
 template <int NOUT, int OUTMODE>
 int launch_n(const ConvTcArgs& a, cudaStream_t s) {
     const bool wide = a.W > 8;
-    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE, 4>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4>(a, s);
-    return wide ? launch_t<2, 1, NOUT, OUTMODE, 4>(a, s) : launch_t<1, 1, NOUT, OUTMODE, 4>(a, s);
+    if (a.exact) return wide ? launch_t<2, 2, NOUT, OUTMODE, 4, false>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4, false>(a, s);
+    return wide ? launch_t<2, 1, NOUT, OUTMODE, 4, false>(a, s) : launch_t<1, 1, NOUT, OUTMODE, 4, false>(a, s);
 }
 
 // context model: 32-channel (4 chunk) groups, always hi/lo planes
 template <int NOUT, int OUTMODE>
 int launch_pc(const ConvTcArgs& a, cudaStream_t s) {
-    return a.W > 8 ? launch_t<2, 2, NOUT, OUTMODE, 4>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4>(a, s);
+    return a.W > 8 ? launch_t<2, 2, NOUT, OUTMODE, 4, true>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4, true>(a, s);
 }
 
 }  // namespace
