@@ -47,6 +47,7 @@ namespace {
 
 constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels = M 128
 constexpr int MAX_WSTAGES = 8;
+static_assert(MAX_WSTAGES >= 8, "Cfg::WSTAGES must fit the barrier arrays");
 constexpr int MAX_RES_STAGES = 14;          // resident-weight mode: the context model has 14 non-masked taps
 constexpr int NTHREADS = 7 * 32;
 
@@ -235,7 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
             mbar_init(smem_u32(&bars->acc_empty[i]), 128);
         }
-        for (int i = 0; i < WSTAGES; ++i) {
+        for (int i = 0; i < (WRES ? 1 : WSTAGES); ++i) {      // resident mode uses w_full[0] only
             mbar_init(smem_u32(&bars->w_full[i]), 1);
             mbar_init(smem_u32(&bars->w_empty[i]), 1);
         }
