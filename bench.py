@@ -179,6 +179,7 @@ def main():
     ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'exact'), choices=['fp32', 'exact', 'fast'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--with-decode', action='store_true', help='also time ae.decode(qhard) (configs[1] lists it; not part of the metric)')
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('IC_BENCH_ALLOW_SHORT'), 'W >= 3 required'
     if args.impl == 'reference':
@@ -270,6 +271,15 @@ def main():
         t, n = _lib.c_double(), _lib.c_longlong()
         _lib.check(L.ic_profile_get(cls, t, n))
         prof[name] = (t.value, n.value)
+    decode_ms = None
+    if args.with_decode:
+        enc = ae.encode(x_dev, is_training=False)
+        qh = enc.qhard.clone()
+        for _ in range(2):
+            ae.decode(qh, is_training=False)
+        barrier()
+        decode_ms = timed(lambda: ae.decode(qh, is_training=False), args.steps)
+        barrier()
     # ---- end to end: pinned host uint8 -> H2D -> step -> D2H of the per-image bit sums
 
     def e2e_step():
@@ -323,6 +333,7 @@ def main():
                      'step_tflops': step_flop / (ms * 1e-3) / 1e12},
         'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
         'parity': parity,
+        'decode': None if decode_ms is None else {'ms_per_step': decode_ms, 'MPix_per_s': world * pix / (decode_ms * 1e-3) / 1e6},
     }
     if not args.no_cpu_baseline:
         import torch as _t

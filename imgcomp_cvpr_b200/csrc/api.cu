@@ -205,13 +205,13 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
             int rc = upload(wm, &d.w);
             if (rc == IC_OK) rc = upload(sc, &d.scale);
             if (rc == IC_OK) rc = upload(sh, &d.shift);
-            // tensor-core path: the 3x3 128->128 residual convs, h2 (5x5 s2 64->128) and to_bn (5x5 s2 128->C+1 <= 48)
+            // tensor-core path: the 3x3 128->128 residual convs, h2 (5x5 s2 64->128) and to_bn (5x5 s2 128->C+1, padded to 48 or 80)
             const bool tc_res = l.k == 3 && l.stride == 1 && !l.transposed && l.cin == 128 && l.cout == 128;
-            const bool tc_s2 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin % 64 == 0 && (l.cout == 128 || l.cout <= 48);
+            const bool tc_s2 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin % 64 == 0 && (l.cout == 128 || l.cout <= 80);
             if (rc == IC_OK && (tc_res || tc_s2)) {
                 std::vector<__half> packed;
                 float inv = 1.f;
-                d.nout_tc = l.cout == 128 ? 128 : 48;
+                d.nout_tc = l.cout == 128 ? 128 : (l.cout <= 48 ? 48 : 80);
                 rc = tc::pack_weights(w, l.k, l.stride, l.cin, l.cout, d.nout_tc, packed, d.gt, &inv);
                 if (rc == IC_OK) {
                     std::vector<float> sct(128, 0.f), sht(128, 0.f);

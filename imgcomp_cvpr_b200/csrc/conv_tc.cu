@@ -695,6 +695,7 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     IC_REQUIRE(a.cpg == 4, IC_ERR_UNSUPPORTED, "conv_tc: groups are 32 channels (4 chunks)");
     if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
     if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
+    if (a.nout == 80 && a.out_f32) return launch_n<80, 1>(a, s);
     if (a.nout == 32 || a.nout == 16) IC_REQUIRE(a.exact, IC_ERR_UNSUPPORTED, "conv_tc: the context model runs in hi/lo precision only");
     if (a.nout == 32 && a.out) return launch_pc<32, 0>(a, s);
     if (a.nout == 16 && a.head >= 0) return launch_pc<16, 2>(a, s);
