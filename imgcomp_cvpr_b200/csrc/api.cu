@@ -208,11 +208,13 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
             // tensor-core path: the 3x3 128->128 residual convs, h2 (5x5 s2 64->128) and to_bn (5x5 s2 128->C+1, padded to 48 or 80)
             const bool tc_res = l.k == 3 && l.stride == 1 && !l.transposed && l.cin == 128 && l.cout == 128;
             const bool tc_s2 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin % 64 == 0 && (l.cout == 128 || l.cout <= 80);
-            if (rc == IC_OK && (tc_res || tc_s2)) {
+            const bool tc_h1 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin == 3 && l.cout == 64;
+            if (rc == IC_OK && (tc_res || tc_s2 || tc_h1)) {
                 std::vector<__half> packed;
                 float inv = 1.f;
-                d.nout_tc = l.cout == 128 ? 128 : (l.cout <= 48 ? 48 : 80);
-                rc = tc::pack_weights(w, l.k, l.stride, l.cin, l.cout, d.nout_tc, packed, d.gt, &inv);
+                d.nout_tc = tc_h1 ? 64 : (l.cout == 128 ? 128 : (l.cout <= 48 ? 48 : 80));
+                rc = tc_h1 ? tc::pack_weights_h1(w, l.cin, l.cout, d.nout_tc, packed, d.gt, &inv)
+                           : tc::pack_weights(w, l.k, l.stride, l.cin, l.cout, d.nout_tc, packed, d.gt, &inv);
                 if (rc == IC_OK) {
                     std::vector<float> sct(128, 0.f), sht(128, 0.f);
                     for (int co = 0; co < l.cout; ++co) {
@@ -365,7 +367,7 @@ int run_res_stack_simt(const DevLayer* layers, int B, int N, int H, int W, float
 }
 
 int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, int Win, __half* out, float* out_f32,
-                  const __half* r1, const __half* r2, int N, int H, int W, bool exact, cudaStream_t s) {
+                  const __half* r1, const __half* r2, int N, int H, int W, bool exact, cudaStream_t s, int out_s2d = 0) {
     tc::ConvTcArgs a;
     memset(&a, 0, sizeof(a));
     a.in = in;
@@ -390,6 +392,7 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
     a.halo0 = -1;
     a.img_mul = 1;
     a.head = -1;
+    a.out_s2d = out_s2d;
     a.cpg = 4;
     a.exact = exact;
     a.prof_class = L.spec.k == 3 ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER;
@@ -397,11 +400,13 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
 }
 
 // tensor-core res stack over fp16 hi/lo plane buffers; pool[0] holds the input.  Returns the output index.
+// last_s2d: the final conv writes its output in space-to-depth form (the input layout of the stride-2 to_bn)
 int run_res_stack_tc(const DevLayer* layers, int B, int N, int H, int W, __half* pool[5], bool exact, int* result,
-                     cudaStream_t s) {
+                     cudaStream_t s, bool last_s2d = false) {
+    const DevLayer* last = layers + (6 * B + 2 - 1);
     return run_res_stack(layers, B, [&](const DevLayer& L, int in, int out, int r1, int r2) {
         return conv_tc_layer(L, pool[in], 16, H, W, pool[out], nullptr, r1 >= 0 ? pool[r1] : nullptr,
-                             r2 >= 0 ? pool[r2] : nullptr, N, H, W, exact, s);
+                             r2 >= 0 ? pool[r2] : nullptr, N, H, W, exact, s, (last_s2d && &L == last) ? 1 : 0);
     }, result);
 }
 
@@ -441,13 +446,14 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
     float* bn = ar.get<float>(n * (H / 8) * (W / 8) * CB);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_encode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
 
-    int rc = launch_prep_input(d_x, x_is_u8, N, H, W, c.normalization, xin, s);
-    if (rc != IC_OK) return rc;
     const DevLayer* L = ae->enc.data();
-    rc = launch_conv_simt(make_desc(L[0], xin, N, H, W, a1), s);
-    if (rc != IC_OK) return rc;
     const DevLayer& tobn = ae->enc.back();
+    int rc;
     if (mode == IC_MODE_FP32) {
+        rc = launch_prep_input(d_x, x_is_u8, N, H, W, c.normalization, xin, s);
+        if (rc != IC_OK) return rc;
+        rc = launch_conv_simt(make_desc(L[0], xin, N, H, W, a1), s);
+        if (rc != IC_OK) return rc;
         float* trunk = nullptr;
         rc = launch_conv_simt(make_desc(L[1], a1, N, H / 2, W / 2, pool[0]), s);
         if (rc != IC_OK) return rc;
@@ -457,23 +463,25 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
         if (rc != IC_OK) return rc;
     } else {
         const bool exact = mode == IC_MODE_EXACT;
-        const int H4 = H / 4, W4 = W / 4;
+        const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
         __half* hp[5];
         for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
-        // h1 output (N,H/2,W/2,64) -> space-to-depth planes [pl][N][32][H/4][W/4][8] (2 trunk units: pool[1..2])
-        rc = tc::launch_split_from_nhwc(a1, N, H / 2, W / 2, 64, 1, hp[1], exact, s);
+        // image -> normalised, space-to-depth hi/lo planes [pl][N][4][H/2][W/2][8]  (fits in `a1`)
+        __half* x2 = reinterpret_cast<__half*>(a1);
+        rc = launch_prep_input_s2d(d_x, x_is_u8, N, H, W, c.normalization, x2, exact, s);
+        if (rc != IC_OK) return rc;
+        // h1 on tensor cores, output (64 ch at H/2) written space-to-depth [pl][N][32][H/4][W/4][8] into pool[1..2]
+        rc = conv_tc_layer(L[0], x2, 4, H2, W2, hp[1], nullptr, nullptr, nullptr, N, H2, W2, exact, s, 1);
         if (rc != IC_OK) return rc;
         rc = conv_tc_layer(L[1], hp[1], 32, H4, W4, hp[0], nullptr, nullptr, nullptr, N, H4, W4, exact, s);   // h2
         if (rc != IC_OK) return rc;
         int ti = 0;
-        rc = run_res_stack_tc(L + 2, c.arch_param_B, N, H4, W4, hp, exact, &ti, s);
+        rc = run_res_stack_tc(L + 2, c.arch_param_B, N, H4, W4, hp, exact, &ti, s, tobn.nout_tc != 0);
         if (rc != IC_OK) return rc;
         const int f1 = (ti + 1) % 5;
         if (tobn.nout_tc) {
-            // trunk planes -> space-to-depth [pl][N][64][H/8][W/8][8], then to_bn on tensor cores -> fp32 NHWC
-            rc = tc::launch_s2d_planes(hp[ti], N, H4, W4, 128, exact ? 2 : 1, hp[f1], s);
-            if (rc != IC_OK) return rc;
-            rc = conv_tc_layer(tobn, hp[f1], 64, H / 8, W / 8, nullptr, bn, nullptr, nullptr, N, H / 8, W / 8, exact, s);
+            // the last residual conv already wrote [pl][N][64][H/8][W/8][8]: to_bn on tensor cores -> fp32 NHWC
+            rc = conv_tc_layer(tobn, hp[ti], 64, H / 8, W / 8, nullptr, bn, nullptr, nullptr, N, H / 8, W / 8, exact, s);
         } else {
             rc = tc::launch_merge_to_nhwc(hp[ti], N, H4, W4, 128, pool[f1], exact, s);
             if (rc != IC_OK) return rc;

@@ -1,5 +1,6 @@
 // Shared helpers for the imgcomp_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -92,6 +93,8 @@ int launch_conv_simt(const ConvDesc& d, cudaStream_t stream);
 // elementwise helpers (elementwise.cu)
 int launch_prep_input(const void* x, int is_u8, int N, int H, int W, int normalize, float* out_nhwc4,
                       cudaStream_t s);
+int launch_prep_input_s2d(const void* x, int is_u8, int N, int H, int W, int normalize, __half* out, int write_lo,
+                          cudaStream_t s);
 int launch_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, cudaStream_t s);
 int launch_heatmap_quantize(const float* bn_nhwc, int N, int h, int w, int C, int heatmap,
                             const float* centers, int L,

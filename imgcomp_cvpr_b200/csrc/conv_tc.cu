@@ -367,8 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
         const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
         const int ty = m >> 3, tx = m & 7;
         constexpr int NCH = NOUT / 8;                 // output chunks (OUTMODE 0)
-        const size_t chunk_stride = (size_t)p.H * p.W * 8;
-        const size_t plane = (size_t)p.N * NCH * chunk_stride;      // elements per hi/lo plane
+        const size_t plane = (size_t)p.N * NCH * p.H * p.W * 8;     // elements per hi/lo plane
         uint32_t it = 0;
         for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
             const uint32_t set = it & 1;
@@ -382,21 +381,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                 const bool inside = y < p.H && x < p.W;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * T + t) * C::NCOL;
                 if (OUTMODE == 0) {
-                    const size_t pix_off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;   // chunk 0
+                    // chunk-0 offset of this pixel; optionally written in space-to-depth form for the next stride-2 conv
+                    size_t pix_off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;
+                    size_t chunk_stride = (size_t)p.H * p.W * 8;
+                    if (p.out_s2d) {
+                        const int ph = (y & 1) * 2 + (x & 1);
+                        chunk_stride = (size_t)(p.H >> 1) * (p.W >> 1) * 8;
+                        pix_off = (((size_t)n * 4 * NCH + ph * NCH) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) * 8 + (size_t)(x >> 1) * 8;
+                    }
                     const bool has_res = (p.res1 != nullptr) || (p.res2 != nullptr);
                     // res1 may live in a larger tensor (context model: conv0 output cropped [2:, 2:-2, 2:-2])
                     const int rimg = n + (p.img_div > 0 ? (n / p.img_div) * p.res_div_mul : 0) + p.res_img_off;
                     const size_t rstride = (size_t)p.res_H * p.res_W * 8;
                     const size_t roff = ((size_t)rimg * NCH * p.res_H + y + p.res_dy) * p.res_W * 8 + (size_t)(x + p.res_dx) * 8;
                     ResRegs cur, nxt;
-                    if (inside && has_res) load_res<NPL>(cur, p, roff, rstride, p.res_plane, pix_off, chunk_stride, plane);
+                    const size_t r2off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;     // res2: output geometry
+                    const size_t r2stride = (size_t)p.H * p.W * 8;
+                    if (inside && has_res) load_res<NPL>(cur, p, roff, rstride, p.res_plane, r2off, r2stride, plane);
 #pragma unroll 1
                     for (int cc = 0; cc < NOUT / 16; ++cc) {
                         uint32_t rr[16];
                         tmem_ld16(taddr + cc * 16, rr);
                         if (inside && has_res && cc + 1 < NOUT / 16)
                             load_res<NPL>(nxt, p, roff + (size_t)(cc + 1) * 2 * rstride, rstride, p.res_plane,
-                                          pix_off + (size_t)(cc + 1) * 2 * chunk_stride, chunk_stride, plane);
+                                          r2off + (size_t)(cc + 1) * 2 * r2stride, r2stride, plane);
                         tmem_ld_wait();
                         if (inside) {
 #pragma unroll
@@ -648,6 +656,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.res_img_off = a.res_img_off;
     p.res_plane = a.res_plane ? a.res_plane : (size_t)a.N * (NOUT / 8) * a.H * a.W * 8;
     p.head = a.head;
+    p.out_s2d = a.out_s2d;
     p.symbols = a.symbols;
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
@@ -694,6 +703,7 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     IC_REQUIRE(((uintptr_t)a.in & 15) == 0, IC_ERR_INVALID, "conv_tc: unaligned input");
     IC_REQUIRE(a.cpg == 4, IC_ERR_UNSUPPORTED, "conv_tc: groups are 32 channels (4 chunks)");
     if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
+    if (a.nout == 64 && a.out) return launch_n<64, 0>(a, s);
     if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
     if (a.nout == 80 && a.out_f32) return launch_n<80, 1>(a, s);
     if (a.nout == 32 || a.nout == 16) IC_REQUIRE(a.exact, IC_ERR_UNSUPPORTED, "conv_tc: the context model runs in hi/lo precision only");
@@ -809,6 +819,52 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
         }
     }
     gt.nstages = nst;
+    return IC_OK;
+}
+
+// h1: conv2d 5x5 stride 2 with cin <= 8 (RGB) on a space-to-depth input whose 4 phases x 8 padded channels form
+// ONE 32-channel group: 9 stride-1 taps; tap (dy,dx) carries, for phase (py,px), the weights of
+// ky = 2(dy-1)+py+1, kx = 2(dx-1)+px+1 when those are inside the 5x5 window (zero otherwise).
+int pack_weights_h1(const float* w_hwio, int cin, int cout, int nout, std::vector<__half>& packed, GroupTable& gt,
+                    float* inv_scale_out) {
+    if (cin > 8 || cout > nout) return IC_ERR_UNSUPPORTED;
+    float mx = 0.f;
+    for (int i = 0; i < 25 * cin * cout; ++i) mx = fmaxf(mx, fabsf(w_hwio[i]));
+    int e = 0;
+    if (mx > 0.f) {
+        int ex;
+        frexpf(mx, &ex);
+        e = 8 - ex;
+    }
+    const float sc = ldexpf(1.f, e);
+    *inv_scale_out = ldexpf(1.f, -e);
+    memset(&gt, 0, sizeof(gt));
+    gt.ngroups = 1;
+    gt.ntaps[0] = 9;
+    gt.nstages = 9;
+    const size_t plane_elems = (size_t)4 * nout * 8;
+    packed.assign((size_t)9 * 2 * plane_elems, __float2half(0.f));
+    for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) {
+            const int tap = dy * 3 + dx;
+            gt.taps[0][tap] = (uint8_t)tap;
+            const size_t base = (size_t)tap * 2 * plane_elems;
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    const int ky = 2 * (dy - 1) + py + 1, kx = 2 * (dx - 1) + px + 1;
+                    if (ky < 0 || ky > 4 || kx < 0 || kx > 4) continue;
+                    const int chunk = py * 2 + px;                  // phase = chunk of the s2d input
+                    for (int c = 0; c < cin; ++c)
+                        for (int o = 0; o < cout; ++o) {
+                            const float v = w_hwio[(((size_t)ky * 5 + kx) * cin + c) * cout + o] * sc;
+                            const __half hi = __float2half_rn(v);
+                            const __half lo = __float2half_rn(v - __half2float(hi));
+                            const size_t idx = ((size_t)chunk * nout + o) * 8 + c;
+                            packed[base + idx] = hi;
+                            packed[base + plane_elems + idx] = lo;
+                        }
+                }
+        }
     return IC_OK;
 }
 

@@ -40,6 +40,7 @@ struct ConvTcParams {
     const int64_t* symbols;
     int64_t* out_freqs;
     double* bits_sum;
+    int out_s2d;                // OUTMODE 0: write the output in space-to-depth form [plane][N][4*NOUT/8][H/2][W/2][8]
 };
 
 struct ConvTcArgs {
@@ -56,6 +57,7 @@ struct ConvTcArgs {
     int halo0, img_mul, img_div, img_div_mul;
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;
+    int out_s2d;
     int head;                   // -1: none
     const int64_t* symbols;
     int64_t* out_freqs;
@@ -69,6 +71,8 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s);
 int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s);
 int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s);
 int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
+int pack_weights_h1(const float* w_hwio, int cin, int cout, int nout, std::vector<__half>& packed, GroupTable& gt,
+                    float* inv_scale_out);
 int pack_weights_pc(const float* w, int ci, int co, int nout, std::vector<__half>& packed, GroupTable& gt,
                     float* inv_scale_out);
 int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int nout, std::vector<__half>& packed,

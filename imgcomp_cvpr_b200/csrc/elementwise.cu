@@ -1,5 +1,7 @@
 // HBM-bound elementwise stages of the encoder: input normalisation / layout
 // change, importance-map (heatmap) masking and the nearest-centre quantizer.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ic {
@@ -25,6 +27,37 @@ __global__ void prep_input_kernel(const TIn* __restrict__ x, int64_t npix_per_im
         v[c] = normalize ? __fdiv_rn(__fsub_rn(f, c_mean[c]), c_std[c]) : f;
     }
     out[i] = make_float4(v[0], v[1], v[2], 0.f);
+}
+
+// Same normalisation, but written as the input of the tensor-core h1: fp16 hi/lo planes in
+// space-to-depth form [plane][N][4 phases][H/2][W/2][8] (channels 0..2 = RGB, 3..7 = 0), so that the
+// 5x5 stride-2 conv becomes 9 stride-1 taps over ONE 32-channel group.
+template <typename TIn>
+__global__ void prep_input_s2d_kernel(const TIn* __restrict__ x, int H, int W, int64_t total, int normalize,
+                                      __half* __restrict__ out, int write_lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per input pixel
+    if (i >= total) return;
+    const int64_t hw = (int64_t)H * W;
+    const int64_t n = i / hw, r = i - n * hw;
+    const int y = (int)(r / W), xx = (int)(r - (int64_t)y * W);
+    const TIn* p = x + n * 3 * hw + r;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float v = 0.f;
+        if (c < 3) {
+            float f = (float)p[c * hw];
+            v = normalize ? __fdiv_rn(__fsub_rn(f, c_mean[c]), c_std[c]) : f;
+        }
+        hi[c] = __float2half_rn(v);
+        lo[c] = __float2half_rn(v - __half2float(hi[c]));
+    }
+    const int ph = (y & 1) * 2 + (xx & 1);
+    const size_t off = ((((size_t)n * 4 + ph) * (H / 2) + (y >> 1)) * (W / 2) + (xx >> 1)) * 8;
+    const size_t plane = (size_t)(total / hw) * hw * 8;              // N * 4 * (H/2) * (W/2) * 8
+    *reinterpret_cast<float4*>(out + off) = *reinterpret_cast<const float4*>(hi);
+    if (write_lo) *reinterpret_cast<float4*>(out + plane + off) = *reinterpret_cast<const float4*>(lo);
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t hw, int64_t total,
@@ -155,6 +188,18 @@ int launch_prep_input(const void* x, int is_u8, int N, int H, int W, int normali
         prep_input_kernel<uint8_t><<<nb, 256, 0, s>>>((const uint8_t*)x, hw, total, normalize, (float4*)out_nhwc4);
     else
         prep_input_kernel<float><<<nb, 256, 0, s>>>((const float*)x, hw, total, normalize, (float4*)out_nhwc4);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int launch_prep_input_s2d(const void* x, int is_u8, int N, int H, int W, int normalize, __half* out, int write_lo,
+                          cudaStream_t s) {
+    int64_t total = (int64_t)N * H * W;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    if (is_u8)
+        prep_input_s2d_kernel<uint8_t><<<cdiv(total, 256), 256, 0, s>>>((const uint8_t*)x, H, W, total, normalize, out, write_lo);
+    else
+        prep_input_s2d_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)x, H, W, total, normalize, out, write_lo);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
