@@ -98,6 +98,7 @@ struct DevLayer {
     // tensor-core path (3x3 128->128 layers only): packed fp16 hi/lo weights and the BN scale
     // divided by the power-of-two weight pre-scale
     __half* w_tc = nullptr;
+    __half* w_tc_pair = nullptr;   // pair-packed copy for the cta_group::2 kernel (IC_CONV_PAIR=1)
     float* scale_tc = nullptr;
     tc::GroupTable gt;
     int nout_tc = 0;
@@ -223,6 +224,12 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
                     }
                     IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc, packed.size() * sizeof(__half)));
                     IC_CHECK_CUDA(cudaMemcpy(d.w_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                    if (d.nout_tc == 128 && getenv("IC_CONV_PAIR") && atoi(getenv("IC_CONV_PAIR"))) {
+                        std::vector<__half> pp;
+                        tc::repack_pair(packed, d.gt.nstages, pp);
+                        IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc_pair, pp.size() * sizeof(__half)));
+                        IC_CHECK_CUDA(cudaMemcpy(d.w_tc_pair, pp.data(), pp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                    }
                     rc = upload(sct, &d.scale_tc);
                     if (rc == IC_OK) {       // padded shift for the tensor-core epilogue
                         cudaFree(d.shift);
@@ -265,6 +272,7 @@ void ic_ae_destroy(ic_ae_t* ae) {
             cudaFree(l.scale);
             cudaFree(l.shift);
             cudaFree(l.w_tc);
+            cudaFree(l.w_tc_pair);
             cudaFree(l.scale_tc);
         }
     cudaFree(ae->d_centers);
@@ -376,6 +384,7 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
     a.Hin = Hin;
     a.Win = Win;
     a.weights = L.w_tc;
+    a.weights_pair = L.w_tc_pair;
     a.groups = &L.gt;
     a.scale = L.scale_tc;
     a.shift = L.shift;

@@ -126,6 +126,62 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) helpers: the leader CTA (cluster rank 0) issues M=256 MMAs over both CTAs'
+// A tiles and half of B from each CTA; barriers the leader waits on are signalled remotely by the peer.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar_local) {      // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_local),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -211,33 +267,44 @@ __device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, 
 // OUTMODE 0: fp16 hi/lo planes [plane][N][NOUT/8][H][W][8]; 1: float32 NHWC [N][H][W][cout];
 // 2: context-model head (ReLU logits -> bit cost / coder frequencies / logits), code/probclass.py:100-104,443-444
 // WRES: all weight stages of the layer stay resident in shared memory (loaded once per CTA; context model)
-template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES>
+// PAIR: 2-CTA clusters, cta_group::2 MMAs (M = 256 over both CTAs, each CTA holds half of B); w_map is the
+//       tensor map of the pair-packed weights [stage][half][plane][4][64][8] (unused otherwise).
+template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p, const GroupTable gt) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const ConvTcParams p,
+               const GroupTable gt) {
     using C = Cfg<T, NOUT, CPG>;
+    static_assert(!PAIR || (NOUT == 128 && OUTMODE == 0 && !WRES), "pair mode is built for the 128->128 convs");
+    constexpr int W_ROWS = PAIR ? NOUT / 2 : NOUT;                 // B rows held by this CTA
+    constexpr int W_PLANE = 4 * W_ROWS * 16;                       // bytes of one plane of one stage in this CTA
+    constexpr uint32_t IDESC = PAIR ? ((C::IDESC & ~(0x1Fu << 24)) | ((256u >> 4) << 24)) : C::IDESC;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // work-loop start
+    const int cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
     constexpr int WSTAGES = WRES ? MAX_RES_STAGES : C::WSTAGES;
-    uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE_BYTES]
-    float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * C::W_PLANE_BYTES);
+    uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE]
+    float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * W_PLANE);
     float* s_shift = s_scale + 128;
     Barriers* bars = reinterpret_cast<Barriers*>(s_shift + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (p.W + TW * T - 1) / (TW * T), tiles_y = (p.H + TH - 1) / TH;
     const int n_super = p.N * tiles_y * tiles_x;
+    const int n_work = PAIR ? (n_super + 1) / 2 : n_super;        // pair mode: one work item = two super tiles
     constexpr uint32_t kTmemCols = (2 * T * C::NCOL <= 32) ? 32 : (2 * T * C::NCOL <= 64) ? 64 :
                                    (2 * T * C::NCOL <= 128) ? 128 : (2 * T * C::NCOL <= 256) ? 256 : 512;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), 1);
+            mbar_init(smem_u32(&bars->a_full[i]), PAIR ? 2 : 1);       // pair: both CTAs' producers arrive on the leader
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
-            mbar_init(smem_u32(&bars->acc_empty[i]), 128);
+            mbar_init(smem_u32(&bars->acc_empty[i]), PAIR ? 256 : 128);
         }
         for (int i = 0; i < (WRES ? 1 : WSTAGES); ++i) {      // resident mode uses w_full[0] only
-            mbar_init(smem_u32(&bars->w_full[i]), 1);
+            mbar_init(smem_u32(&bars->w_full[i]), PAIR ? 2 : 1);
             mbar_init(smem_u32(&bars->w_empty[i]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -247,12 +314,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
         s_shift[threadIdx.x] = threadIdx.x < NOUT ? p.shift[threadIdx.x] : 0.f;
     }
     if (warp == 2) {   // TMEM: 2 accumulator sets x T tiles x NCOL fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                     "n"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                         "n"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                         "n"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -260,18 +334,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
         // ===================== activation producer =====================
         if (lane == 0) {
             uint32_t gi = 0;     // running group counter -> A slot / phase
-            for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+            for (int wi = cta_id; wi < n_work; wi += cta_stride) {
+                const int st = PAIR ? 2 * wi + (int)rank : wi;      // past-the-end super tiles load zeros (TMA OOB)
                 const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
                 const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW * T;
                 for (int g = 0; g < gt.ngroups; ++g, ++gi) {
                     const uint32_t slot = gi & 1, ph = (gi >> 1) & 1;
                     mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
-                    const uint32_t full = smem_u32(&bars->a_full[slot]);
-                    mbar_expect_tx(full, NPL * C::A_PLANE_BYTES);
                     const int img = n * p.img_mul + (p.img_div > 0 ? (n / p.img_div) * p.img_div_mul : 0) + gt.img_off[g];
-                    for (int pl = 0; pl < NPL; ++pl)
-                        tma_load_5d(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
-                                    (x0 + p.halo0) * 8, y0 + p.halo0, gt.chunk0[g], img, pl);
+                    if (PAIR) {
+                        const uint32_t full = mapa_rank(smem_u32(&bars->a_full[slot]), 0);     // the leader's barrier
+                        mbar_expect_tx_cluster(full, NPL * C::A_PLANE_BYTES);
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_5d_2sm(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
+                                            (x0 + p.halo0) * 8, y0 + p.halo0, gt.chunk0[g], img, pl);
+                    } else {
+                        const uint32_t full = smem_u32(&bars->a_full[slot]);
+                        mbar_expect_tx(full, NPL * C::A_PLANE_BYTES);
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_5d(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
+                                        (x0 + p.halo0) * 8, y0 + p.halo0, gt.chunk0[g], img, pl);
+                    }
                 }
             }
         }
@@ -287,35 +370,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                               NPL * C::W_PLANE_BYTES, full);
             } else {
                 uint32_t ws = 0;     // running stage counter
-                for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+                for (int wi = cta_id; wi < n_work; wi += cta_stride) {
                     for (int s = 0; s < gt.nstages; ++s, ++ws) {      // (group, tap) in MMA order
                         const uint32_t slot = ws % WSTAGES, ph = (ws / WSTAGES) & 1;
                         mbar_wait(smem_u32(&bars->w_empty[slot]), ph ^ 1);
-                        const uint32_t full = smem_u32(&bars->w_full[slot]);
-                        mbar_expect_tx(full, NPL * C::W_PLANE_BYTES);
-                        // global stage = [2 planes][W_PLANE_BYTES]; FAST mode copies the hi plane only
-                        bulk_load(smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES),
-                                  p.weights + (size_t)s * 2 * C::W_PLANE_BYTES, NPL * C::W_PLANE_BYTES, full);
+                        if (PAIR) {
+                            // this CTA's half of the stage (64 of the 128 B rows), signalled on the leader's barrier;
+                            // pair-packed global layout [stage][half][plane][4][64][8] seen as [stage*2+half][16][256]
+                            const uint32_t full = mapa_rank(smem_u32(&bars->w_full[slot]), 0);
+                            mbar_expect_tx_cluster(full, NPL * W_PLANE);
+                            tma_load_3d_2sm(smem_u32(w_buf + slot * NPL * W_PLANE), &w_map, full, 0, 0, s * 2 + (int)rank);
+                        } else {
+                            const uint32_t full = smem_u32(&bars->w_full[slot]);
+                            mbar_expect_tx(full, NPL * C::W_PLANE_BYTES);
+                            // global stage = [2 planes][W_PLANE_BYTES]; FAST mode copies the hi plane only
+                            bulk_load(smem_u32(w_buf + slot * NPL * C::W_PLANE_BYTES),
+                                      p.weights + (size_t)s * 2 * C::W_PLANE_BYTES, NPL * C::W_PLANE_BYTES, full);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 2) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {      // pair mode: only the leader CTA issues MMAs (for both CTAs)
             // Descriptors are 64-bit words whose low 14 bits hold (address >> 4): every tap / k-step / tile /
             // plane variant is the base descriptor plus a small constant, so the issue loop is adds + MMAs only.
             constexpr uint32_t kALbo = C::HALO_PIX * 16, kASbo = C::HALO_W * 16;
-            constexpr uint64_t kAPlane = C::A_PLANE_BYTES >> 4, kWPlane = C::W_PLANE_BYTES >> 4;
-            constexpr uint64_t kAKs = (2 * C::HALO_PIX * 16) >> 4, kWKs = (2 * NOUT * 16) >> 4;
+            constexpr uint64_t kAPlane = C::A_PLANE_BYTES >> 4, kWPlane = W_PLANE >> 4;
+            constexpr uint64_t kAKs = (2 * C::HALO_PIX * 16) >> 4, kWKs = (2 * W_ROWS * 16) >> 4;
             const uint64_t a_desc0 = make_desc(smem_u32(a_buf), kALbo, kASbo);
-            const uint64_t w_desc0 = make_desc(smem_u32(w_buf), NOUT * 16, 128);
+            const uint64_t w_desc0 = make_desc(smem_u32(w_buf), W_ROWS * 16, 128);
             uint32_t it = 0, ws = 0, gi = 0;
             if (WRES) {
                 mbar_wait(smem_u32(&bars->w_full[0]), 0);
                 tc_fence_after();
             }
-            for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+            for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
                 const uint32_t set = it & 1;
                 mbar_wait(smem_u32(&bars->acc_empty[set]), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -347,18 +438,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                                 const uint64_t a_hi = a_t + (uint64_t)(t * TW) + ks * kAKs;
                                 const uint64_t w_hi = w_t + ks * kWKs;
                                 const uint32_t first = (g | ti | ks) == 0 ? 0u : 1u;
-                                umma_f16(d_tmem, a_hi, w_hi, C::IDESC, first);
-                                if (NPL == 2) {
-                                    umma_f16(d_tmem, a_hi, w_hi + kWPlane, C::IDESC, 1u);
-                                    umma_f16(d_tmem, a_hi + kAPlane, w_hi, C::IDESC, 1u);
+                                if (PAIR) {
+                                    umma_f16_2sm(d_tmem, a_hi, w_hi, IDESC, first);
+                                    if (NPL == 2) {
+                                        umma_f16_2sm(d_tmem, a_hi, w_hi + kWPlane, IDESC, 1u);
+                                        umma_f16_2sm(d_tmem, a_hi + kAPlane, w_hi, IDESC, 1u);
+                                    }
+                                } else {
+                                    umma_f16(d_tmem, a_hi, w_hi, IDESC, first);
+                                    if (NPL == 2) {
+                                        umma_f16(d_tmem, a_hi, w_hi + kWPlane, IDESC, 1u);
+                                        umma_f16(d_tmem, a_hi + kAPlane, w_hi, IDESC, 1u);
+                                    }
                                 }
                             }
                         }
-                        if (!WRES) umma_commit(smem_u32(&bars->w_empty[slot]));    // stage free once these MMAs retire
+                        if (!WRES) {                          // stage free (in both CTAs) once these MMAs retire
+                            if (PAIR) umma_commit_2sm(smem_u32(&bars->w_empty[slot]));
+                            else umma_commit(smem_u32(&bars->w_empty[slot]));
+                        }
                     }
-                    umma_commit(smem_u32(&bars->a_empty[aslot]));
+                    if (PAIR) umma_commit_2sm(smem_u32(&bars->a_empty[aslot]));
+                    else umma_commit(smem_u32(&bars->a_empty[aslot]));
                 }
-                umma_commit(smem_u32(&bars->acc_full[set]));
+                if (PAIR) umma_commit_2sm(smem_u32(&bars->acc_full[set]));
+                else umma_commit(smem_u32(&bars->acc_full[set]));
             }
         }
     } else {
@@ -369,8 +473,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
         constexpr int NCH = NOUT / 8;                 // output chunks (OUTMODE 0)
         const size_t plane = (size_t)p.N * NCH * p.H * p.W * 8;     // elements per hi/lo plane
         uint32_t it = 0;
-        for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+        for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
             const uint32_t set = it & 1;
+            const int st = PAIR ? 2 * wi + (int)rank : wi;
             const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
             const int y = (r / tiles_x) * TH + ty;
             mbar_wait(smem_u32(&bars->acc_full[set]), (it >> 1) & 1);
@@ -378,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int x = (r % tiles_x) * TW * T + t * TW + tx;
-                const bool inside = y < p.H && x < p.W;
+                const bool inside = y < p.H && x < p.W && n < p.N;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * T + t) * C::NCOL;
                 if (OUTMODE == 0) {
                     // chunk-0 offset of this pixel; optionally written in space-to-depth form for the next stride-2 conv
@@ -512,14 +617,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p,
                 }
             }
             tc_fence_before();
-            mbar_arrive(smem_u32(&bars->acc_empty[set]));
+            if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&bars->acc_empty[set]), 0));    // the leader waits for both epilogues
+            else mbar_arrive(smem_u32(&bars->acc_empty[set]));
         }
     }
     // teardown
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // neither CTA may exit (or free TMEM) while the peer can still touch it
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
     }
 }
 
@@ -613,7 +721,7 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES>
+template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES, bool PAIR = false>
 int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     using C = Cfg<T, NOUT, CPG>;
     IC_REQUIRE(!WRES || a.groups->nstages <= MAX_RES_STAGES, IC_ERR_UNSUPPORTED, "conv_tc: too many stages for resident weights");
@@ -660,12 +768,26 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.symbols = a.symbols;
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
-    const size_t smem = 2 * NPL * C::A_PLANE_BYTES + (WRES ? MAX_RES_STAGES : C::WSTAGES) * NPL * C::W_PLANE_BYTES + 1024 +
+    const size_t smem = 2 * NPL * C::A_PLANE_BYTES +
+                        (WRES ? MAX_RES_STAGES : C::WSTAGES) * NPL * (C::W_PLANE_BYTES / (PAIR ? 2 : 1)) + 1024 +
                         sizeof(Barriers) + 64;
+    CUtensorMap wmap = map;        // placeholder unless PAIR
+    if (PAIR) {
+        // pair-packed weights [stage][half][plane][4][64][8] as a 3-D tensor [stage*2+half][16][256] of fp16;
+        // a CTA's half stage = NPL planes = 8*NPL rows of 256 elements
+        const cuuint64_t wd[3] = {256, 16, (cuuint64_t)a.groups->nstages * 2};
+        const cuuint64_t wst[2] = {512, 8192};
+        const cuuint32_t wbox[3] = {256, (cuuint32_t)(8 * NPL), 1};
+        const cuuint32_t we[3] = {1, 1, 1};
+        CUresult wr = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)a.weights_pair, wd, wst, wbox, we,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IC_REQUIRE(wr == CUDA_SUCCESS, IC_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: %d", (int)wr);
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
+        IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int tiles_x = (a.W + TW * T - 1) / (TW * T), tiles_y = (a.H + TH - 1) / TH;
@@ -676,9 +798,28 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     // two CTAs per SM only if both shared memory and TMEM (512 columns per SM) allow it
     const int tmem_cols = 2 * T * C::NCOL;
     const int ctas = (smem <= 110 * 1024 && tmem_cols <= 256) ? 2 * sms : sms;
-    const int grid = n_super < ctas ? n_super : ctas;
+    int grid = n_super < ctas ? n_super : ctas;
     ProfScope ps(a.prof_class, s);
-    conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES><<<grid, NTHREADS, smem, s>>>(map, p, *a.groups);
+    if (PAIR) {
+        const int n_work = (n_super + 1) / 2;
+        grid = 2 * (n_work < sms / 2 ? n_work : sms / 2);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        IC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR>, map, wmap, p, *a.groups));
+    } else {
+        conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR><<<grid, NTHREADS, smem, s>>>(map, wmap, p, *a.groups);
+    }
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -702,6 +843,9 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     IC_REQUIRE(a.N > 0 && a.H > 0 && a.W > 0 && a.groups, IC_ERR_INVALID, "conv_tc: bad shape");
     IC_REQUIRE(((uintptr_t)a.in & 15) == 0, IC_ERR_INVALID, "conv_tc: unaligned input");
     IC_REQUIRE(a.cpg == 4, IC_ERR_UNSUPPORTED, "conv_tc: groups are 32 channels (4 chunks)");
+    if (a.nout == 128 && a.out && a.weights_pair && a.W > 8) {       // 2-CTA pairs (cta_group::2)
+        return a.exact ? launch_t<2, 2, 128, 0, 4, false, true>(a, s) : launch_t<2, 1, 128, 0, 4, false, true>(a, s);
+    }
     if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
     if (a.nout == 64 && a.out) return launch_n<64, 0>(a, s);
     if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
@@ -820,6 +964,20 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
     }
     gt.nstages = nst;
     return IC_OK;
+}
+
+// standard stage layout [plane][4][128][8] -> pair layout [half][plane][4][64][8] (each CTA of a pair holds 64 B rows)
+void repack_pair(const std::vector<__half>& packed, int nstages, std::vector<__half>& out) {
+    out.resize(packed.size());
+    const size_t stage = 2 * 4 * 128 * 8;
+    for (int s = 0; s < nstages; ++s)
+        for (int half = 0; half < 2; ++half)
+            for (int pl = 0; pl < 2; ++pl)
+                for (int ch = 0; ch < 4; ++ch)
+                    for (int r = 0; r < 64; ++r)
+                        for (int e = 0; e < 8; ++e)
+                            out[s * stage + ((((size_t)half * 2 + pl) * 4 + ch) * 64 + r) * 8 + e] =
+                                packed[s * stage + (((size_t)pl * 4 + ch) * 128 + half * 64 + r) * 8 + e];
 }
 
 // h1: conv2d 5x5 stride 2 with cin <= 8 (RGB) on a space-to-depth input whose 4 phases x 8 padded channels form

@@ -47,6 +47,7 @@ struct ConvTcArgs {
     const __half* in;           // [planes][Nimg][in_chunks][Hin][Win][8]
     int Nimg, in_chunks, Hin, Win;
     const __half* weights;
+    const __half* weights_pair;   // pair-packed copy (cta_group::2 path) or nullptr
     const GroupTable* groups;
     const float *scale, *shift;
     const __half *res1, *res2;
@@ -71,6 +72,7 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s);
 int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s);
 int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s);
 int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
+void repack_pair(const std::vector<__half>& packed, int nstages, std::vector<__half>& out);
 int pack_weights_h1(const float* w_hwio, int cin, int cout, int nout, std::vector<__half>& packed, GroupTable& gt,
                     float* inv_scale_out);
 int pack_weights_pc(const float* w, int ci, int co, int nout, std::vector<__half>& packed, GroupTable& gt,
