@@ -102,6 +102,9 @@ struct DevLayer {
     float* scale_tc = nullptr;
     tc::GroupTable gt;
     int nout_tc = 0;
+    // transposed convs (decoder): depth-to-space packing; from_bn needs two launches (output rows 2m and 2m+1)
+    __half* w_tc_b = nullptr;
+    tc::GroupTable gt_b;
 };
 
 int upload(const std::vector<float>& h, float** d) {
@@ -209,6 +212,45 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
             // tensor-core path: the 3x3 128->128 residual convs, h2 (5x5 s2 64->128) and to_bn (5x5 s2 128->C+1, padded to 48 or 80)
             const bool tc_res = l.k == 3 && l.stride == 1 && !l.transposed && l.cin == 128 && l.cout == 128;
             const bool tc_s2 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin % 64 == 0 && (l.cout == 128 || l.cout <= 80);
+            const bool tc_t = l.transposed && l.stride == 2 && l.cin % 32 == 0 &&
+                              ((l.k == 3 && l.cout == 128) || (l.k == 5 && (l.cout == 64 || l.cout == 3)));
+            if (rc == IC_OK && tc_t) {
+                std::vector<float> sct(128, 0.f), sht(128, 0.f);
+                float inv = 1.f;
+                const int all[4] = {0, 1, 2, 3};
+                std::vector<__half> packed;
+                d.nout_tc = l.cout == 3 ? 16 : 256;
+                if (l.cout == 128) {       // from_bn: 4 phases x 128 = 512 columns -> two launches of 256
+                    rc = tc::pack_weights_tconv(w, l.k, l.cin, l.cout, all, 2, 256, packed, d.gt, &inv);
+                    if (rc == IC_OK) {
+                        std::vector<__half> pb;
+                        float inv2;
+                        rc = tc::pack_weights_tconv(w, l.k, l.cin, l.cout, all + 2, 2, 256, pb, d.gt_b, &inv2);
+                        if (rc == IC_OK) {
+                            IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc_b, pb.size() * sizeof(__half)));
+                            IC_CHECK_CUDA(cudaMemcpy(d.w_tc_b, pb.data(), pb.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                        }
+                    }
+                } else {
+                    rc = tc::pack_weights_tconv(w, l.k, l.cin, l.cout, all, 4, d.nout_tc, packed, d.gt, &inv);
+                }
+                if (rc == IC_OK) {
+                    for (int co = 0; co < l.cout; ++co) {
+                        sct[co] = sc[co] * inv;
+                        sht[co] = sh[co];
+                    }
+                    IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc, packed.size() * sizeof(__half)));
+                    IC_CHECK_CUDA(cudaMemcpy(d.w_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                    rc = upload(sct, &d.scale_tc);
+                    if (rc == IC_OK) {
+                        cudaFree(d.shift);
+                        rc = upload(sht, &d.shift);
+                    }
+                } else {
+                    d.nout_tc = 0;
+                    rc = IC_OK;
+                }
+            }
             const bool tc_h1 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin == 3 && l.cout == 64;
             if (rc == IC_OK && (tc_res || tc_s2 || tc_h1)) {
                 std::vector<__half> packed;
@@ -273,6 +315,7 @@ void ic_ae_destroy(ic_ae_t* ae) {
             cudaFree(l.shift);
             cudaFree(l.w_tc);
             cudaFree(l.w_tc_pair);
+            cudaFree(l.w_tc_b);
             cudaFree(l.scale_tc);
         }
     cudaFree(ae->d_centers);
@@ -409,6 +452,43 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
 }
 
 // tensor-core res stack over fp16 hi/lo plane buffers; pool[0] holds the input.  Returns the output index.
+// one depth-to-space launch of a stride-2 transposed conv on tensor cores (see tc::pack_weights_tconv)
+int tconv_tc_layer(const DevLayer& L, bool second, const __half* in, int in_chunks, int N, int Hin, int Win, __half* out,
+                   float* out_img, uint8_t* out_u8, int denorm, bool exact, cudaStream_t s) {
+    tc::ConvTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in;
+    a.Nimg = N;
+    a.in_chunks = in_chunks;
+    a.Hin = Hin;
+    a.Win = Win;
+    a.weights = second ? L.w_tc_b : L.w_tc;
+    a.groups = second ? &L.gt_b : &L.gt;
+    a.scale = L.scale_tc;
+    a.shift = L.shift;
+    a.out = out;
+    a.out_f32 = out_img;
+    a.out_u8 = out_u8;
+    a.denorm = denorm;
+    a.N = N;
+    a.H = Hin;
+    a.W = Win;
+    a.relu = L.spec.relu;
+    a.cout = L.spec.cout;
+    a.nout = L.nout_tc;
+    a.halo0 = -1;
+    a.img_mul = 1;
+    a.head = -1;
+    a.cpg = 4;
+    a.exact = exact;
+    a.prof_class = IC_PROF_CONV_OTHER;
+    if (out) {
+        a.d2s_cch = L.spec.cout / 8;
+        a.d2s_ph0 = second ? 2 : 0;
+    }
+    return tc::launch_conv_tc(a, s);
+}
+
 // last_s2d: the final conv writes its output in space-to-depth form (the input layout of the stride-2 to_bn)
 int run_res_stack_tc(const DevLayer* layers, int B, int N, int H, int W, __half* pool[5], bool exact, int* result,
                      cudaStream_t s, bool last_s2d = false) {
@@ -526,20 +606,42 @@ int ic_decode_fwd(const ic_ae_t* ae, const float* d_q, int N, int h, int w, floa
     for (int i = 0; i < (mode == IC_MODE_FP32 ? 5 : 7); ++i) pool[i] = ar.get<float>(n * (2 * h) * (2 * w) * 128);
     float* a12 = ar.get<float>(n * (4 * h) * (4 * w) * 64);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_decode_fwd: workspace too small: need %zu, have %zu", ar.off, workspace_bytes);
-    int rc = launch_nchw_to_nhwc(d_q, N, c.num_chan_bn, h, w, qn, s);
-    if (rc != IC_OK) return rc;
+    int rc = IC_OK;
     const DevLayer* L = ae->dec.data();
     float* trunk = nullptr;
     if (mode == IC_MODE_FP32) {
+        rc = launch_nchw_to_nhwc(d_q, N, c.num_chan_bn, h, w, qn, s);
+        if (rc != IC_OK) return rc;
         rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[0]), s);
         if (rc != IC_OK) return rc;
         rc = run_res_stack_simt(L + 1, c.arch_param_B, N, 2 * h, 2 * w, pool, &trunk, s);
     } else {
-        rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[5]), s);
-        if (rc != IC_OK) return rc;
         const bool exact = mode == IC_MODE_EXACT;
+        const size_t nl = ae->dec.size();
         __half* hp[5];
         for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
+        const bool all_tc = L[0].nout_tc && L[nl - 2].nout_tc && L[nl - 1].nout_tc;
+        if (all_tc) {
+            // q (NCHW fp32) -> hi/lo planes; from_bn / h12 / h13 as depth-to-space convs on tensor cores
+            __half* qp = reinterpret_cast<__half*>(qn);
+            rc = tc::launch_split_from_nchw(d_q, N, c.num_chan_bn, h, w, qp, exact, s);
+            if (rc != IC_OK) return rc;
+            for (int half = 0; half < 2 && rc == IC_OK; ++half)
+                rc = tconv_tc_layer(L[0], half == 1, qp, c.num_chan_bn / 8, N, h, w, hp[0], nullptr, nullptr, 0, exact, s);
+            if (rc != IC_OK) return rc;
+            int ti = 0;
+            rc = run_res_stack_tc(L + 1, c.arch_param_B, N, 2 * h, 2 * w, hp, exact, &ti, s);
+            if (rc != IC_OK) return rc;
+            const int a0 = ti >= 2 ? 0 : 3;           // two adjacent free trunk buffers hold the 64-ch 4h x 4w tensor
+            rc = tconv_tc_layer(L[nl - 2], false, hp[ti], 16, N, 2 * h, 2 * w, hp[a0], nullptr, nullptr, 0, exact, s);
+            if (rc != IC_OK) return rc;
+            return tconv_tc_layer(L[nl - 1], false, hp[a0], 8, N, 4 * h, 4 * w, nullptr, d_x_out, d_x_out_u8, c.normalization,
+                                  exact, s);
+        }
+        rc = launch_nchw_to_nhwc(d_q, N, c.num_chan_bn, h, w, qn, s);
+        if (rc != IC_OK) return rc;
+        rc = launch_conv_simt(make_desc(L[0], qn, N, h, w, pool[5]), s);
+        if (rc != IC_OK) return rc;
         rc = tc::launch_split_from_nhwc(pool[5], N, 2 * h, 2 * w, 128, 0, hp[0], exact, s);
         if (rc != IC_OK) return rc;
         int ti = 0;

@@ -57,9 +57,9 @@ struct Cfg {
     static constexpr int A_PLANE_BYTES = CPG * HALO_PIX * 16;     // one group = CPG chunks of 8 channels
     // weight pipeline depth: a refill takes ~1 us (commit -> producer -> L2 -> smem) while a stage is consumed in
     // 0.3-0.5 us, so >= 4 stages must be in flight; 8 x 16 KB fits beside two 41 KB activation groups
-    static constexpr int WSTAGES = NOUT == 128 ? 8 : 6;
+    static constexpr int WSTAGES = NOUT == 256 ? 4 : (NOUT == 128 ? 8 : 6);
     static constexpr int W_PLANE_BYTES = 4 * NOUT * 16;           // one stage = 32 channels of one tap
-    static constexpr int NCOL = NOUT > 64 ? 128 : 64;             // TMEM columns per accumulator tile
+    static constexpr int NCOL = NOUT > 128 ? 256 : (NOUT > 64 ? 128 : 64);   // TMEM columns per accumulator tile
     static constexpr uint32_t IDESC = (1u << 4) /* D fp32 */ | (0u << 7) /* A f16 */ | (0u << 10) /* B f16 */ |
                                       ((uint32_t)(NOUT >> 3) << 17) /* N */ | ((128u >> 4) << 24) /* M */;
 };
@@ -187,6 +187,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+
+__constant__ float c_img_mean[3] = {121.853699f, 113.588608f, 100.637154f};
+__constant__ float c_img_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};   // float32 sqrt(var + 1e-10)
 
 struct __align__(8) Barriers {
     uint64_t a_full[2], a_empty[2], w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES], acc_full[2], acc_empty[2];
@@ -515,11 +518,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
 #pragma unroll
                             for (int hc = 0; hc < 2; ++hc) {
                                 const int chunk = cc * 2 + hc;
+                                // depth-to-space output (transposed convs): column block = (output phase, channel chunk)
+                                const int sch = p.d2s_cch ? chunk % p.d2s_cch : chunk;
                                 float v[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     float a = __uint_as_float(rr[hc * 8 + e]);
-                                    a = fmaf(a, s_scale[chunk * 8 + e], s_shift[chunk * 8 + e]);
+                                    a = fmaf(a, s_scale[sch * 8 + e], s_shift[sch * 8 + e]);
                                     v[e] = p.relu ? fmaxf(a, 0.f) : a;
                                 }
                                 if (p.res1) {
@@ -538,10 +543,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                                     float2 hf = __half22float2(hi[e]);
                                     lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
                                 }
-                                const size_t off = pix_off + (size_t)chunk * chunk_stride;
+                                size_t off = pix_off + (size_t)chunk * chunk_stride, oplane = plane;
+                                if (p.d2s_cch) {
+                                    const int phs = p.d2s_ph0 + chunk / p.d2s_cch;
+                                    const int yo = 2 * y + (phs >> 1), xo = 2 * x + (phs & 1);
+                                    off = ((((size_t)n * p.d2s_cch + sch) * (2 * p.H) + yo) * (2 * p.W) + xo) * 8;
+                                    oplane = (size_t)p.N * p.d2s_cch * (2 * p.H) * (2 * p.W) * 8;
+                                }
                                 *reinterpret_cast<float4*>(p.out + off) = *reinterpret_cast<const float4*>(hi);
                                 if (NPL == 2)
-                                    *reinterpret_cast<float4*>(p.out + plane + off) = *reinterpret_cast<const float4*>(lo);
+                                    *reinterpret_cast<float4*>(p.out + oplane + off) = *reinterpret_cast<const float4*>(lo);
                             }
                         }
                         cur = nxt;
@@ -595,6 +606,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                         double b = inside && p.symbols ? (double)bits : 0.0;
                         for (int o = 16; o > 0; o >>= 1) b += __shfl_down_sync(0xffffffffu, b, o);
                         if (lane == 0 && b != 0.0) atomicAdd(p.bits_sum + (p.img_div > 0 ? n / p.img_div : n), b);
+                    }
+                } else if (OUTMODE == 3) {
+                    // h13: 4 output phases x 3 channels -> BN, _denormalize, clip (code/autoencoder.py:146-158), NCHW image
+                    uint32_t rr[16];
+                    tmem_ld16(taddr, rr);
+                    tmem_ld_wait();
+                    if (inside) {
+                        const size_t H2 = 2 * (size_t)p.H, W2 = 2 * (size_t)p.W;
+#pragma unroll
+                        for (int phs = 0; phs < 4; ++phs)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                float v = fmaf(__uint_as_float(rr[phs * 3 + c]), s_scale[c], s_shift[c]);
+                                if (p.denorm) {
+                                    v = __fadd_rn(__fmul_rn(v, c_img_std[c]), c_img_mean[c]);
+                                    v = fminf(fmaxf(v, 0.f), 255.f);
+                                }
+                                const size_t o = (((size_t)n * 3 + c) * H2 + 2 * y + (phs >> 1)) * W2 + 2 * x + (phs & 1);
+                                p.out_f32[o] = v;
+                                if (p.out_u8) p.out_u8[o] = (uint8_t)v;     // tf.cast truncation (val.py:91)
+                            }
                     }
                 } else {
                     float* o = p.out_f32 + (((size_t)n * p.H + y) * p.W + x) * p.cout;
@@ -672,6 +704,22 @@ __global__ void split_from_nhwc_kernel(const float* __restrict__ in, int H, int 
     }
     *reinterpret_cast<float4*>(out + off) = hi;
     if (write_lo) *reinterpret_cast<float4*>(out + plane + off) = lo;
+}
+
+// fp32 NCHW (N,C,H,W) -> planes [pl][N][C/8][H][W][8].  One thread per (n, chunk, pixel).
+__global__ void split_from_nchw_kernel(const float* __restrict__ in, int CH, int64_t hw, int64_t total, int64_t plane,
+                                       __half* __restrict__ out, int write_lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t r = i % hw;
+    const int64_t nc = i / hw;          // n * CH + chunk
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = in[(nc * 8 + e) * hw + r];
+    float4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<float4*>(out + i * 8) = hi;
+    if (write_lo) *reinterpret_cast<float4*>(out + plane + i * 8) = lo;
 }
 
 // planes [pl][N][CH][H][W][8] -> fp32 NHWC.  One thread per (pixel, chunk), chunk fastest (coalesced writes).
@@ -765,6 +813,10 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.res_plane = a.res_plane ? a.res_plane : (size_t)a.N * (NOUT / 8) * a.H * a.W * 8;
     p.head = a.head;
     p.out_s2d = a.out_s2d;
+    p.d2s_cch = a.d2s_cch;
+    p.d2s_ph0 = a.d2s_ph0;
+    p.denorm = a.denorm;
+    p.out_u8 = a.out_u8;
     p.symbols = a.symbols;
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
@@ -848,6 +900,9 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     }
     if (a.nout == 128 && a.out) return launch_n<128, 0>(a, s);
     if (a.nout == 64 && a.out) return launch_n<64, 0>(a, s);
+    if (a.nout == 256 && a.out && a.d2s_cch)      // depth-to-space transposed convs: one 256-column tile, T = 1
+        return a.exact ? launch_t<1, 2, 256, 0, 4, false>(a, s) : launch_t<1, 1, 256, 0, 4, false>(a, s);
+    if (a.nout == 16 && a.head < 0 && a.out_f32) return launch_n<16, 3>(a, s);
     if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
     if (a.nout == 80 && a.out_f32) return launch_n<80, 1>(a, s);
     if (a.nout == 32 || a.nout == 16) IC_REQUIRE(a.exact, IC_ERR_UNSUPPORTED, "conv_tc: the context model runs in hi/lo precision only");
@@ -862,6 +917,15 @@ int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d,
     int64_t total = (int64_t)N * H * W * (C / 8), plane = (int64_t)N * H * W * C;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
     split_from_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, s2d, total, plane, out, write_lo);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int launch_split_from_nchw(const float* in, int N, int C, int H, int W, __half* out, int write_lo, cudaStream_t s) {
+    IC_REQUIRE(C % 8 == 0, IC_ERR_INVALID, "split_from_nchw: C must be a multiple of 8");
+    int64_t hw = (int64_t)H * W, total = (int64_t)N * (C / 8) * hw, plane = total * 8;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    split_from_nchw_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, C / 8, hw, total, plane, out, write_lo);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -961,6 +1025,74 @@ int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int 
                         packed[base + plane_elems + idx] = lo;
                     }
         }
+    }
+    gt.nstages = nst;
+    return IC_OK;
+}
+
+// conv2d_transpose weights [k][k][Cout][Cin] (code/autoencoder.py:251,264-265), stride 2, as a stride-1 conv over the
+// INPUT grid whose output columns are (output phase, channel): y[2m+r] = sum_t x[m + (r+pb-t)/2] w[t] over taps with
+// (r+pb-t) even (pb = 0 for k = 3, 1 for k = 5).  `phases` lists the output phases (ry*2+rx) this
+// launch produces; halo offset of a tap = (r+pb-t)/2 + 1 in {0,1,2}.
+int pack_weights_tconv(const float* w, int k, int cin, int cout, const int* phases, int nphases, int nout,
+                       std::vector<__half>& packed, GroupTable& gt, float* inv_scale_out) {
+    if (!(k == 3 || k == 5) || cin % 32 != 0 || nphases * cout > nout) return IC_ERR_UNSUPPORTED;
+    const int pb = k == 3 ? 0 : 1;
+    float mx = 0.f;
+    for (size_t i = 0; i < (size_t)k * k * cin * cout; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    int e = 0;
+    if (mx > 0.f) {
+        int ex;
+        frexpf(mx, &ex);
+        e = 8 - ex;
+    }
+    const float sc = ldexpf(1.f, e);
+    *inv_scale_out = ldexpf(1.f, -e);
+    memset(&gt, 0, sizeof(gt));
+    const int quarters = cin / 32;
+    if (quarters > 16) return IC_ERR_UNSUPPORTED;
+    // tap positions (dy,dx) used by at least one phase of this launch
+    bool used[9] = {false};
+    for (int pi = 0; pi < nphases; ++pi) {
+        const int ry = phases[pi] >> 1, rx = phases[pi] & 1;
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ty = ry + pb - 2 * (dy - 1), tx = rx + pb - 2 * (dx - 1);
+                if (ty >= 0 && ty < k && tx >= 0 && tx < k) used[dy * 3 + dx] = true;
+            }
+    }
+    gt.ngroups = quarters;
+    const size_t plane_elems = (size_t)4 * nout * 8;
+    packed.clear();
+    int nst = 0;
+    for (int q = 0; q < quarters; ++q) {
+        gt.chunk0[q] = (uint8_t)(q * 4);
+        int nt = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+            if (!used[tap]) continue;
+            const int dy = tap / 3, dx = tap % 3;
+            gt.taps[q][nt++] = (uint8_t)tap;
+            const size_t base = packed.size();
+            packed.resize(base + 2 * plane_elems, __float2half(0.f));
+            for (int pi = 0; pi < nphases; ++pi) {
+                const int ry = phases[pi] >> 1, rx = phases[pi] & 1;
+                const int ty = ry + pb - 2 * (dy - 1), tx = rx + pb - 2 * (dx - 1);
+                if (ty < 0 || ty >= k || tx < 0 || tx >= k) continue;
+                for (int ch = 0; ch < 4; ++ch)
+                    for (int co = 0; co < cout; ++co)
+                        for (int ei = 0; ei < 8; ++ei) {
+                            const int ci = q * 32 + ch * 8 + ei;
+                            const float v = w[(((size_t)ty * k + tx) * cout + co) * cin + ci] * sc;
+                            const __half hi = __float2half_rn(v);
+                            const __half lo = __float2half_rn(v - __half2float(hi));
+                            const size_t idx = ((size_t)ch * nout + pi * cout + co) * 8 + ei;
+                            packed[base + idx] = hi;
+                            packed[base + plane_elems + idx] = lo;
+                        }
+            }
+            ++nst;
+        }
+        gt.ntaps[q] = (uint8_t)nt;
     }
     gt.nstages = nst;
     return IC_OK;

@@ -41,6 +41,11 @@ struct ConvTcParams {
     int64_t* out_freqs;
     double* bits_sum;
     int out_s2d;                // OUTMODE 0: write the output in space-to-depth form [plane][N][4*NOUT/8][H/2][W/2][8]
+    // OUTMODE 0 depth-to-space (transposed convs): column block = (phase, chunk); output [plane][N][d2s_cch][2H][2W][8]
+    int d2s_cch, d2s_ph0;
+    // OUTMODE 3 (h13): NCHW float32 image (+ truncated uint8 copy), optional denormalise + clip
+    int denorm;
+    uint8_t* out_u8;
 };
 
 struct ConvTcArgs {
@@ -58,7 +63,8 @@ struct ConvTcArgs {
     int halo0, img_mul, img_div, img_div_mul;
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;
-    int out_s2d;
+    int out_s2d, d2s_cch, d2s_ph0, denorm;
+    uint8_t* out_u8;
     int head;                   // -1: none
     const int64_t* symbols;
     int64_t* out_freqs;
@@ -72,6 +78,9 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s);
 int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s);
 int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s);
 int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
+int pack_weights_tconv(const float* w, int k, int cin, int cout, const int* phases, int nphases, int nout,
+                       std::vector<__half>& packed, GroupTable& gt, float* inv_scale_out);
+int launch_split_from_nchw(const float* in, int N, int C, int H, int W, __half* out, int write_lo, cudaStream_t s);
 void repack_pair(const std::vector<__half>& packed, int nstages, std::vector<__half>& out);
 int pack_weights_h1(const float* w_hwio, int cin, int cout, int nout, std::vector<__half>& packed, GroupTable& gt,
                     float* inv_scale_out);

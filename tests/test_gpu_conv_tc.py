@@ -70,3 +70,24 @@ def test_fast_mode_flip_rate_is_reported(name, ae_name, gpu_models):
     flips = (enc.symbols.cpu().numpy() != g['symbols']).mean()
     print('fast mode: %s symbol flip rate %.4f, max |dz| %.3e' % (name, flips, np.abs(enc.z.cpu().numpy() - g['z']).max()))
     assert flips < 0.05
+
+
+@pytest.mark.parametrize('name,ae_name', [('cfg1_low_1x128x128', 'cvpr/low'), ('ragged_low_2x48x72', 'cvpr/low'),
+                                          ('tiny_hi_1x40x24', 'cvpr/hi')])
+def test_decoder_tensor_core_transposed_convs(name, ae_name, gpu_models):
+    """decode in EXACT mode (from_bn / h12 / h13 as depth-to-space tcgen05 convs) vs the FFMA decoder
+    on the same qhard, and vs the reference-run golden image."""
+    ae32, _, W = gpu_models(ae_name, 'fp32')
+    aex, _, _ = gpu_models(ae_name, 'exact')
+    g = load_golden(name)
+    q = torch.from_numpy(W['autoencoder/encoder/centers'][g['symbols'].astype(np.int64)]).cuda()
+    x32 = ae32.decode(q, False).clone()
+    u32 = ae32.extra['x_out_u8'].clone()
+    xex = aex.decode(q, False)
+    uex = aex.extra['x_out_u8']
+    d = (xex - x32).abs().max().item()
+    print('%s: decode exact vs fp32 max |dx| %.3e, uint8 mismatches %.2e' % (name, d, (uex != u32).float().mean().item()))
+    assert d < 2e-2
+    assert (uex != u32).float().mean().item() < 2e-3
+    assert (uex.cpu().numpy() != g['x_out_u8']).mean() < 2e-3
+    assert torch.equal(uex, xex.to(torch.uint8))
