@@ -273,7 +273,7 @@ __device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, 
 // PAIR: 2-CTA clusters, cta_group::2 MMAs (M = 256 over both CTAs, each CTA holds half of B); w_map is the
 //       tensor map of the pair-packed weights [stage][half][plane][4][64][8] (unused otherwise).
 template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES, bool PAIR>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, (NOUT <= 32 && T == 1) ? 2 : 1)      // context model: two CTAs per SM
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const ConvTcParams p,
                const GroupTable gt) {
     using C = Cfg<T, NOUT, CPG>;
@@ -849,7 +849,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // two CTAs per SM only if both shared memory and TMEM (512 columns per SM) allow it
     const int tmem_cols = 2 * T * C::NCOL;
-    const int ctas = (smem <= 110 * 1024 && tmem_cols <= 256) ? 2 * sms : sms;
+    const int ctas = (2 * (smem + 1024) <= 232448 && tmem_cols <= 256) ? 2 * sms : sms;
     int grid = n_super < ctas ? n_super : ctas;
     ProfScope ps(a.prof_class, s);
     if (PAIR) {
@@ -886,7 +886,9 @@ int launch_n(const ConvTcArgs& a, cudaStream_t s) {
 // context model: 32-channel (4 chunk) groups, always hi/lo planes
 template <int NOUT, int OUTMODE>
 int launch_pc(const ConvTcArgs& a, cudaStream_t s) {
-    return a.W > 8 ? launch_t<2, 2, NOUT, OUTMODE, 4, true>(a, s) : launch_t<1, 2, NOUT, OUTMODE, 4, true>(a, s);
+    // 16x8 tiles (T = 1): 102 KB of shared memory and 128 TMEM columns per CTA, so two CTAs share an SM and
+    // overlap each other's pipeline bubbles (these layers have only 84 short MMAs per tile)
+    return launch_t<1, 2, NOUT, OUTMODE, 4, true>(a, s);
 }
 
 }  // namespace
