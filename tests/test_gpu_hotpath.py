@@ -246,3 +246,62 @@ def test_val_driver_matches_goldens(gpu_models):
     assert np.isfinite(rows2[0]['bpp'])
     rows3 = val.measure_batch(torch.from_numpy(g1['x_u8']).cuda(), ae, pc, real_bpp=True)
     assert abs(rows3[0]['bpp_real'] - rows3[0]['bpp_theory']) * 64 * 64 < 50
+
+
+@pytest.mark.parametrize('shape', [(1, 8, 8), (2, 16, 8), (1, 8, 40), (3, 24, 136)])
+def test_smallest_and_odd_tile_shapes_all_modes(shape, gpu_models):
+    """Edge shapes (one latent pixel, partial tensor-core tiles, W/4 <= 8): exact mode vs the float32 path vs the oracle."""
+    from imgcomp_cvpr_b200 import weights as wm
+    N, H, Wd = shape
+    x = wm.synthetic_images(N, H, Wd, seed=H * 100 + Wd)
+    xc = _cuda(x)
+    ae32, pc, W = gpu_models('cvpr/low', 'fp32')
+    aex, _, _ = gpu_models('cvpr/low', 'exact')
+    e32 = ae32.encode(xc, False)
+    z32, s32 = e32.z.clone(), e32.symbols.clone()
+    eex = aex.encode(xc, False)
+    ref = O.encode(x.astype(np.float32), W, 32)
+    np.testing.assert_allclose(z32.cpu().numpy(), ref['z'], atol=3e-4)
+    np.testing.assert_allclose(eex.z.cpu().numpy(), ref['z'], atol=1e-3)
+    z64 = O.encode(x.astype(np.float64), W, 32, dtype=np.float64)['z']
+    safe = symbol_margin(z64, W['autoencoder/encoder/centers']) > 6e-4
+    assert (s32.cpu().numpy()[safe] == ref['symbols'][safe]).all()
+    assert (eex.symbols.cpu().numpy()[safe] == ref['symbols'][safe]).all()
+    bc = pc.bitcost(e32.qbar, e32.symbols, False, pad_value=pc.auto_pad_value(ae32))
+    obc, _ = O.pc_bitcost(ref['qbar'], ref['symbols'], W, W['autoencoder/encoder/centers'][0])
+    same = s32.cpu().numpy() == ref['symbols']
+    np.testing.assert_allclose(bc.cpu().numpy()[same], obc[same], atol=3e-3)
+    xo32 = ae32.decode(e32.qhard, False).clone()
+    xoex = aex.decode(e32.qhard, False)
+    oref = O.decode(e32.qhard.cpu().numpy(), W)
+    np.testing.assert_allclose(xo32.cpu().numpy(), oref, atol=2e-2)
+    np.testing.assert_allclose(xoex.cpu().numpy(), oref, atol=5e-2)
+
+
+def test_full_size_properties_kodak_shape(gpu_models):
+    """BASELINE.json configs[1] shape (768x512, 2 images here): size-independent properties -- determinism,
+    batch independence in exact mode, symbols in range, qhard = centres[symbols], bits finite and positive,
+    coded size ~ theoretical size (the reference's own --real_bpp asserts), decode range."""
+    from imgcomp_cvpr_b200 import bit_counter, probclass, weights as wm
+    ae, pc, W = gpu_models('cvpr/low', 'exact')
+    x = _cuda(wm.synthetic_images(2, 768, 512, seed=77))
+    e = ae.encode(x, False)
+    sym, z, qhard, qbar = e.symbols.clone(), e.z.clone(), e.qhard.clone(), e.qbar.clone()
+    e2 = ae.encode(x, False)
+    assert torch.equal(e2.symbols, sym) and torch.equal(e2.z, z)                    # deterministic
+    e1 = ae.encode(x[1:2].contiguous(), False)
+    assert torch.equal(e1.symbols, sym[1:2]) and torch.equal(e1.z, z[1:2])           # batch independent
+    assert sym.min().item() >= 0 and sym.max().item() <= 5
+    centers = torch.from_numpy(W['autoencoder/encoder/centers']).cuda()
+    assert torch.equal(qhard, centers[sym])
+    assert (qbar - qhard).abs().max().item() <= 4e-7                                 # qbar = qsoft + (qhard - qsoft)
+    bc = pc.bitcost(qbar, sym, False, pad_value=pc.auto_pad_value(ae))
+    assert torch.isfinite(bc).all() and bc.min().item() >= 0
+    bits_img = pc.last_bits_per_image.clone()
+    np.testing.assert_allclose(bits_img.cpu().numpy(), bc.double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=1e-6)
+    pred = probclass.PredictionNetwork(pc, pc.config, ae.get_centers_variable(), None)
+    nbits = bit_counter.encode_decode_to_file_ctx(sym[0].cpu().numpy(), pred, syms_format='CHW')
+    f, theory = pred.get_all_freqs(sym[0])
+    assert abs(nbits - theory) < 50 and abs(theory - bits_img[0].item()) < 5e-3 * theory + 1
+    xo = ae.decode(qhard, False)
+    assert xo.min().item() >= 0 and xo.max().item() <= 255 and torch.isfinite(xo).all()
