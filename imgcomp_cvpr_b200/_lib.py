@@ -63,6 +63,9 @@ SIGNATURES = {
     'ic_msssim_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'ic_msssim_tf_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_np_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_loss_workspace_bytes': (c_size_t, []),
+    'ic_masked_sums_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_mse_per_image_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     'ic_debug_conv3x3': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_void_p, c_size_t, c_int, c_void_p]),
     'ic_launch_count': (c_longlong, []),

@@ -172,6 +172,17 @@ int ic_msssim_tf_fwd(const float* d_img1, const float* d_img2, int N, int H, int
 int ic_msssim_np_fwd(const uint8_t* d_img1, const uint8_t* d_img2, int N, int H, int W,
                      double* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------- training-loss forward
+ * replaces the reductions of train.get_loss (code/train.py:309-311: reduce_mean(bc), reduce_mean(bc * heatmap))
+ * d_out: 2 doubles = [sum bc, sum bc*heatmap] (heatmap may be NULL -> second sum 0). */
+size_t ic_loss_workspace_bytes(void);
+int ic_masked_sums_fwd(const float* d_bc, const float* d_heatmap, int64_t n, double* d_out,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+/* replaces Distortions.get_mse_per_img (code/train.py:400-418): per-image mean squared error of two float32
+ * NCHW batches, optionally after the int32 cast (truncation) the reference applies outside of training. */
+int ic_mse_per_image_fwd(const float* d_x, const float* d_x_out, int N, int64_t per_image, int cast_to_int,
+                         float* d_out, void* stream);
+
 /* ------------------------------------------------------------- test hooks
  * One fused 3x3 128->128 residual conv (conv + BN + ReLU + residual adds) of the
  * encoder/decoder through the path selected by `mode`; fp32 NHWC (N,H,W,128) in/out.

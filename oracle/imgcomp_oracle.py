@@ -511,3 +511,29 @@ def val_forward(x_u8, W, num_chan_bn=32, dtype=np.float32):
     return dict(enc=enc, x_out=x_out, x_out_u8=x_out_u8, bitcost=bc, logits=logits,
                 bpp=np.array([p[0] for p in per_img]), ms_ssim=np.array([p[1] for p in per_img]),
                 psnr=np.array([p[2] for p in per_img]))
+
+
+# ----------------------------------------------------------------------------
+# train.py loss (forward)
+# ----------------------------------------------------------------------------
+def get_loss(bc, heatmap, d_loss_scaled, H_target, beta, reg_enc=0.0, reg_dec=0.0, reg_pc=0.0):
+    """train.get_loss (train.py:303-336), float32."""
+    H_real = np.float32(bc.mean(dtype=np.float32))
+    H_mask = np.float32((bc * heatmap).mean(dtype=np.float32)) if heatmap is not None else H_real
+    H_soft = np.float32(0.5) * (H_mask + H_real)
+    pc_loss = np.float32(beta) * np.maximum(H_soft - np.float32(H_target), np.float32(0))
+    total = np.float32(d_loss_scaled) + pc_loss + np.float32(reg_pc + reg_enc + reg_dec)
+    return float(total), float(H_real), float(H_mask), float(pc_loss)
+
+
+def mse_per_img(inp, otp, cast_to_int):
+    """Distortions.get_mse_per_img (train.py:400-418)."""
+    if cast_to_int:
+        inp, otp = inp.astype(np.int32), otp.astype(np.int32)      # tf.cast truncates
+    se = np.square(otp - inp).astype(np.float32)
+    return se.mean(axis=(1, 2, 3), dtype=np.float32)
+
+
+def psnr_per_img(inp, otp, cast_to_int):
+    """Distortions.get_psnr_per_image (train.py:420-425)."""
+    return (10 * np.log(255.0 * 255.0 / mse_per_img(inp, otp, cast_to_int)) / np.log(10.0)).astype(np.float32)

@@ -305,3 +305,37 @@ def test_full_size_properties_kodak_shape(gpu_models):
     assert abs(nbits - theory) < 50 and abs(theory - bits_img[0].item()) < 5e-3 * theory + 1
     xo = ae.decode(qhard, False)
     assert xo.min().item() >= 0 and xo.max().item() <= 255 and torch.isfinite(xo).all()
+
+
+def test_training_loss_forward(gpu_models, synth):
+    """train.get_loss + Distortions, forward (code/train.py:303-336,352-431) against the oracle."""
+    from imgcomp_cvpr_b200 import train
+    a, p, W = synth('cvpr/low')
+    ae, pc, _ = gpu_models('cvpr/low', 'fp32')
+    g = load_golden('ragged_low_2x48x72')
+    x = _cuda(g['x_u8']).float()
+    enc = ae.encode(x, False)
+    x_out = ae.decode(enc.qbar, False)
+    bc = pc.bitcost(enc.qbar, enc.symbols, False, pad_value=pc.auto_pad_value(ae))
+    reg = train.regularization_losses(a, p, W)
+    assert reg[2] is None and reg[0] > 0 and reg[1] > 0
+    for is_training in (False, True):
+        d = train.Distortions(a, x, x_out, is_training)
+        xo = x_out.cpu().numpy()
+        xi = g['x_u8'].astype(np.float32)
+        np.testing.assert_allclose(d.mse, O.mse_per_img(xi, xo, True).mean(), rtol=1e-5)
+        np.testing.assert_allclose(d.psnr, O.psnr_per_img(xi, xo, True).mean(), rtol=1e-5)
+        # ms_ssim on a tiny ragged shape raises in the reference; use mse-minimising config for it
+    a_mse = type(a)(**dict(a.__dict__, distortion_to_minimize='mse'))
+    d = train.Distortions(a_mse, x, x_out, True)          # training + mse: NO int cast
+    np.testing.assert_allclose(d.mse, O.mse_per_img(g['x_u8'].astype(np.float32), x_out.cpu().numpy(), False).mean(), rtol=1e-5)
+    total, H_real, pc_comps, ae_comps = train.get_loss(a, ae, pc, d.d_loss_scaled, bc, enc.heatmap, reg)
+    o_total, o_real, o_mask, o_pcl = O.get_loss(bc.cpu().numpy(), enc.heatmap.cpu().numpy(), d.d_loss_scaled, a.H_target,
+                                                a.beta, reg[0], reg[1], 0.0)
+    assert abs(H_real - o_real) < 1e-5 and abs(dict(pc_comps)['H_mask'] - o_mask) < 1e-5
+    assert abs(dict(pc_comps)['pc_loss'] - o_pcl) < 1e-2 and abs(total - o_total) < 1e-3 * abs(o_total)
+    x160 = torch.rand((2, 3, 160, 160), device='cuda') * 255
+    y160 = (x160 + torch.randn_like(x160) * 4).clamp(0, 255)
+    dm = train.Distortions(a, x160, y160, True)           # ms_ssim config on the training crop size
+    assert abs(dm.d_loss_scaled - a.K_ms_ssim * (1 - dm.ms_ssim)) < 1e-3
+    assert abs(dm.ms_ssim - O.ms_ssim_tf(x160.cpu().numpy(), y160.cpu().numpy())[0]) < 1e-4
