@@ -12,7 +12,8 @@ namespace tc {
 // which taps each 64-channel input group contributes (built by pack_weights)
 struct GroupTable {
     int ngroups;             // A-buffer loads per super tile
-    int nstages;             // weight stages per super tile = 2 * total taps
+    int nstages;             // weight stages per super tile (one per (group, tap))
+    int eff_ksteps;          // (stage, k-step) pairs with non-zero weights: accumulate steps per output / products
     uint8_t ntaps[16];
     uint8_t taps[16][9];     // dy*3+dx halo offsets
     uint8_t img_off[16];     // added to the image coordinate of the TMA load (0 for 2-D convs)
@@ -29,6 +30,7 @@ struct ConvTcParams {
     __half* out;                // OUTMODE 0: [2][N][NOUT/8][H][W][8]
     float* out_f32;             // OUTMODE 1: [N][H][W][cout]
     int N, H, W, relu, cout;
+    float acc_gain;             // compensates the round-toward-zero bias of the tensor core's fp32 accumulation
     int halo0;                  // origin of the halo tile relative to the output tile (-1: SAME 3x3-like, 0: VALID)
     // input image coordinate = n * img_mul + (n / img_div) * img_div_mul + img_off[group]   (img_div = 0: off)
     int img_mul, img_div, img_div_mul;
