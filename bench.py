@@ -359,6 +359,9 @@ def main():
                      'peak_source': '%s bf16_tflops_sustained' % peak_src, 'traffic': None,
                      'flop_per_launch': flop_per_launch, 'avg_launch_ms': avg_ms, 'launches': n3,
                      'share_of_step': t3 / (ms * args.steps) if ms else None,
+                     'mma_flops_per_algorithmic_flop': {'exact': 3, 'fast': 1, 'fp32': 0}[args.mode],
+                     'tensor_issue_frac': (achieved * {'exact': 3, 'fast': 1, 'fp32': 0}[args.mode] / peak) if peak else None,
+                     'note': 'exact = fp16x3 split: 3 tensor-core FLOPs per algorithmic FLOP, so frac <= 1/3 by construction',
                      'step_algorithmic_tflop': step_flop / 1e12,
                      'step_tflops': step_flop / (ms * 1e-3) / 1e12},
         'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
