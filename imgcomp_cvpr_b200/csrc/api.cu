@@ -173,20 +173,20 @@ int64_t ic_ae_tensor_numel(const ic_ae_config* cfg, int i) {
     return t[i].numel;
 }
 
-int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_tensors, ic_ae_t** out) {
-    IC_REQUIRE(cfg_ok(cfg) && h_tensors && out, IC_ERR_INVALID, "ic_ae_create: bad config / NULL argument");
+static int ae_build(ic_ae* ae, const ic_ae_config* cfg, const float* const* h_tensors, int n_tensors) {
+    IC_REQUIRE(cfg_ok(cfg) && h_tensors, IC_ERR_INVALID, "ic_ae_create: bad config / NULL argument");
     IC_REQUIRE(cfg->normalization == 0 || cfg->normalization == 1, IC_ERR_UNSUPPORTED, "normalization must be OFF(0) or FIXED(1)");
     auto tensors = ae_tensors(*cfg);
     IC_REQUIRE(n_tensors == (int)tensors.size(), IC_ERR_INVALID, "ic_ae_create: expected %zu tensors, got %d",
                tensors.size(), n_tensors);
     for (int i = 0; i < n_tensors; ++i) IC_REQUIRE(h_tensors[i], IC_ERR_INVALID, "ic_ae_create: tensor %d (%s) is NULL", i, tensors[i].name.c_str());
-    ic_ae* ae = new ic_ae();
     ae->cfg = *cfg;
     int ti = 0;
     for (int dec = 0; dec < 2; ++dec) {
         auto& dst = dec ? ae->dec : ae->enc;
         for (const auto& l : ae_layers(*cfg, dec)) {
-            DevLayer d;
+            dst.emplace_back();            // owned by the handle from here on: early returns cannot leak
+            DevLayer& d = dst.back();
             d.spec = l;
             d.cin_pad = (int)align_up(l.cin, 4);
             d.ldw = (int)align_up(l.cout, 4);
@@ -284,11 +284,7 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
                     rc = IC_OK;
                 }
             }
-            dst.push_back(d);
-            if (rc != IC_OK) {
-                ic_ae_destroy(ae);
-                return rc;
-            }
+            if (rc != IC_OK) return rc;
         }
         if (!dec) {
             std::vector<float> c(h_tensors[ti], h_tensors[ti] + cfg->num_centers);
@@ -296,11 +292,21 @@ int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_t
             memcpy(ae->h_centers, c.data(), sizeof(float) * cfg->num_centers);
             ++ti;
             int rc = upload(c, &ae->d_centers);
-            if (rc != IC_OK) {
-                ic_ae_destroy(ae);
-                return rc;
-            }
+            if (rc != IC_OK) return rc;
         }
+    }
+    return IC_OK;
+}
+
+void ic_ae_destroy(ic_ae_t* ae);
+
+int ic_ae_create(const ic_ae_config* cfg, const float* const* h_tensors, int n_tensors, ic_ae_t** out) {
+    IC_REQUIRE(out, IC_ERR_INVALID, "ic_ae_create: NULL argument");
+    ic_ae* ae = new ic_ae();
+    int rc = ae_build(ae, cfg, h_tensors, n_tensors);
+    if (rc != IC_OK) {
+        ic_ae_destroy(ae);
+        return rc;
     }
     *out = ae;
     return IC_OK;
