@@ -216,16 +216,18 @@ def main():
         return pc.last_bits_per_image
 
     def timed(fn, steps):
-        total = 0.0
+        """K steps, each bracketed by its own CUDA-event pair on the launching stream; the L2 flush between
+        steps is enqueued outside the pairs (not timed); nothing synchronises with the host until the end."""
+        evs = []
         for _ in range(steps):
-            flush.fill_(1)                     # L2 flush between timed iterations (not timed)
+            flush.fill_(1)                     # L2 flush between timed iterations
             a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_ev.record()
             fn()
             b_ev.record()
-            b_ev.synchronize()
-            total += a_ev.elapsed_time(b_ev)
-        return total / steps
+            evs.append((a_ev, b_ev))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / steps
 
     def barrier():
         if world > 1:
