@@ -28,9 +28,10 @@ class _Network(object):
     """code/autoencoder.py:32-204.  ``weights``: dict TF-variable-name -> ndarray
     (see weights.py); the reference creates variables inside encode()/decode()
     and restores them from a checkpoint, here they are handed over explicitly
-    (constructor or load_weights)."""
+    (constructor or load_weights).  ``mode``: 'exact' (default; tcgen05 fp16x3, float32-class), 'fp32'
+    (float32 FFMA kernels, strict parity, ~10x slower) or 'fast' (single fp16 pass) -- DESIGN.md 4.2."""
 
-    def __init__(self, config, quantize=True, weights=None, mode='fp32'):
+    def __init__(self, config, quantize=True, weights=None, mode='exact'):
         if not quantize:
             raise NotImplementedError('quantize=False is not on the hot path')
         self.config = config
