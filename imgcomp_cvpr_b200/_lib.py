@@ -58,6 +58,11 @@ SIGNATURES = {
     'ic_pc_logits_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_pc_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_pc_codec_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_pc_decode_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    'ic_pc_decode_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_pc_context_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -868,6 +868,49 @@ int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_
     return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, d_freqs, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int ic_pc_codec_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_centers, int N, int C, int h, int w,
+                          int64_t* d_freqs, double* d_bits_sum, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_symbols && d_centers && d_freqs && d_workspace, IC_ERR_INVALID, "ic_pc_codec_freqs_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_pc_codec_freqs_fwd: bad shape");
+    PcInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.D = C; in.H = h; in.W = w;
+    in.pad_d = 4; in.pad_hw = 4;
+    in.symbols = d_symbols;
+    in.target_symbols = d_symbols;
+    IC_CHECK_CUDA(cudaMemcpyAsync(in.centers_host, d_centers, sizeof(float) * pc->cfg.num_centers, cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+    IC_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, d_freqs, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream,
+                      /*canonical=*/true);
+}
+
+size_t ic_pc_decode_workspace_bytes(const ic_pc_t* pc, int N, int C, int h, int w) {
+    if (!pc || N <= 0 || C <= 0 || h <= 0 || w <= 0) return 0;
+    return pc_decode_workspace_bytes(N, C, h, w);
+}
+
+int ic_pc_decode_fwd(const ic_pc_t* pc, const uint8_t* d_stream, const int64_t* d_stream_offsets, const int32_t* d_first_sym,
+                     const float* d_centers, int N, int C, int h, int w, uint8_t* d_symbols, const uint8_t* d_force_symbols,
+                     int64_t* d_freqs_seen, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_stream && d_stream_offsets && d_first_sym && d_centers && d_symbols && d_workspace, IC_ERR_INVALID,
+               "ic_pc_decode_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_pc_decode_fwd: bad shape");
+    PcDecodeInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.C = C; in.h = h; in.w = w;
+    in.stream = d_stream;
+    in.stream_off = d_stream_offsets;
+    in.first_sym = d_first_sym;
+    in.sym_out = d_symbols;
+    in.force_sym = d_force_symbols;
+    in.freqs_out = d_freqs_seen;
+    IC_CHECK_CUDA(cudaMemcpyAsync(in.centers_host, d_centers, sizeof(float) * pc->cfg.num_centers, cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+    IC_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return pc_decode(pc->w, in, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int ic_pc_context_freqs_fwd(const ic_pc_t* pc, const int64_t* d_ctx_symbols, const float* d_centers, int N, int D, int H,
                             int W, int64_t* d_freqs, void* d_workspace, size_t workspace_bytes, void* stream) {
     IC_REQUIRE(pc && d_ctx_symbols && d_centers && d_freqs && d_workspace, IC_ERR_INVALID, "ic_pc_context_freqs_fwd: NULL argument");

@@ -1,0 +1,443 @@
+// Decoder-side context model: the sequential half of --real_bpp
+// (code/bit_counter.py:137-163 `_decode`: for every symbol, in raster C -> H -> W
+// order, evaluate the context model on the 5x9x9 block of already decoded
+// symbols, hand the frequency table to the range decoder, write the symbol back).
+//
+// The reference pays one sess.run over a full context per symbol (README.md:65:
+// ~200 s per Kodak image).  Here one CTA owns one image and keeps the layer
+// activations of the causal network (code/probclass.py:214-221) cached, as
+// README.md:72-73 suggests: decoding a symbol only adds the terms that depend on
+// it.  The range decoder (code/arithmetic_coding.py:163-222) runs on the device
+// too, so nothing crosses PCIe per symbol.
+//
+// Bit consistency with the encoder: every layer output is ONE fmaf chain in the
+// order of the float32 batched kernels of probclass.cu (taps in (fd,fy,fx) raster
+// order, input channels ascending, then + bias).  That order is causal in the
+// decoder's own raster, so the chain of a position can be advanced as its
+// inputs appear:
+//   taps 0..8   previous latent channel          -> helper warps, one row ahead
+//   taps 9..11  row above, same channel          -> all warps, at row start
+//   tap  12     left neighbour                   -> decode warp, one step ahead
+//   tap  13     the position itself (layers 1-3) -> decode warp, critical path
+// and the table it ends in is bit-identical to ic_pc_codec_freqs_fwd's.
+#include <stdint.h>
+
+#include "common.cuh"
+#include "probclass.cuh"
+
+namespace ic {
+
+namespace {
+
+constexpr int KC = 24;            // arch_param__k
+constexpr int PROW = 80;          // floats per position in a partial-sum row: 24 (L0) + 24 (L1) + 24 (L2) + 8 (L3)
+constexpr int NT = 256;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct DecArgs {
+    const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3;
+    int C, h, w, L;
+    float centers[8];
+    const uint8_t* stream;          // concatenated bitstreams
+    const int64_t* stream_off;      // [N + 1] byte offsets
+    const int32_t* first_sym;       // [N] side information (code/bit_counter.py:118-121)
+    uint8_t* sym_out;               // N,C,h,w
+    float* act;                     // per image: [3 layers][2 channel slots][h+6][w+6][24]
+    float* p9;                      // per image: [w+6][PROW]
+    const uint8_t* force_sym;       // debug: teacher forcing, no range decoding
+    int64_t* freqs_out;             // debug: N,C,h,w,L tables as the decoder saw them
+};
+
+struct Smem {
+    float* w1;     // [14][24][24]
+    float* w2;     // [14][24][24]
+    float* w3;     // [14][24][8]   outputs zero padded to 8
+    float* w0;     // [13][24]
+    float* b;      // b0[24] b1[24] b2[24] b3[8]
+    float* cent;   // [8]
+    float* P;      // [w+6][PROW]  chains of the current row after taps 0..11
+};
+constexpr int SMEM_FIXED_FLOATS = 14 * 24 * 24 * 2 + 14 * 24 * 8 + 13 * 24 + PROW + 8;
+
+struct Geom {
+    int C, h, w, H6, W6;
+    size_t slot, layer;            // strides (floats) of one channel slot / one layer in `act`
+};
+
+__device__ __forceinline__ float* act_row(float* act_img, const Geom& g, int layer, int c, int y) {
+    return act_img + layer * g.layer + (size_t)((c + 4) & 1) * g.slot + (size_t)(y + 3) * g.W6 * KC;
+}
+
+// value of the (virtually padded) input volume, code/probclass.py:268-292 + :449-451
+__device__ __forceinline__ float in_val(const Geom& g, const float* cent, const uint8_t* syms, int c, int y, int x) {
+    if (c < 0 || y < 0 || y >= g.h || x < 0 || x >= g.w) return cent[0];
+    return cent[syms[((size_t)c * g.h + y) * g.w + x]];
+}
+
+// ------------------------------------------------------------------ chains, taps 0..11
+// FIRST: taps 0..8 (previous channel) from zero into the global row p9;
+// !FIRST: taps 9..11 (row above) continue p9 into the shared row P.
+template <bool FIRST, int LAYER>
+__device__ __forceinline__ void chain_mid(const Geom& g, const Smem& sm, int tid, int nthr, int c, int y, float* act_img,
+                                          float* p9) {
+    constexpr int NJG = LAYER == 3 ? 2 : 6;
+    constexpr int WOUT = LAYER == 3 ? 8 : 24;
+    const float* sW = LAYER == 1 ? sm.w1 : (LAYER == 2 ? sm.w2 : sm.w3);
+    const int xlo = -3 + LAYER, nx = g.w + 6 - 2 * LAYER;
+    float* dst = FIRST ? p9 : sm.P;
+    for (int it = tid; it < nx * NJG; it += nthr) {
+        const int xo = it / NJG, jg = it - xo * NJG;
+        const int xi = xlo + xo + 3;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!FIRST) {
+            const float4 v = *reinterpret_cast<const float4*>(p9 + (size_t)xi * PROW + LAYER * 24 + jg * 4);
+            acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
+        }
+#pragma unroll 1
+        for (int t = FIRST ? 0 : 9; t < (FIRST ? 9 : 12); ++t) {
+            const int dy = FIRST ? t / 3 - 1 : -1;
+            const int dx = FIRST ? t % 3 - 1 : t - 10;
+            const float4* ap = reinterpret_cast<const float4*>(act_row(act_img, g, LAYER - 1, FIRST ? c - 1 : c, y + dy) +
+                                                               (size_t)(xi + dx) * KC);
+            const float* wt = sW + (size_t)t * 24 * WOUT + jg * 4;
+#pragma unroll
+            for (int i4 = 0; i4 < 6; ++i4) {
+                const float4 av = ap[i4];
+                const float a[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wt + (i4 * 4 + u) * WOUT);
+                    acc[0] = fmaf(a[u], wv.x, acc[0]);
+                    acc[1] = fmaf(a[u], wv.y, acc[1]);
+                    acc[2] = fmaf(a[u], wv.z, acc[2]);
+                    acc[3] = fmaf(a[u], wv.w, acc[3]);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(dst + (size_t)xi * PROW + LAYER * 24 + jg * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void chain_l0(const Geom& g, const Smem& sm, int tid, int nthr, int c, int y,
+                                         const uint8_t* syms, float* p9) {
+    float* dst = FIRST ? p9 : sm.P;
+    for (int it = tid; it < g.W6 * 6; it += nthr) {
+        const int xi = it / 6, jg = it - xi * 6;
+        const int x = xi - 3;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!FIRST) {
+            const float4 v = *reinterpret_cast<const float4*>(p9 + (size_t)xi * PROW + jg * 4);
+            acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
+        }
+#pragma unroll 1
+        for (int t = FIRST ? 0 : 9; t < (FIRST ? 9 : 12); ++t) {
+            const int dy = FIRST ? t / 3 - 1 : -1;
+            const int dx = FIRST ? t % 3 - 1 : t - 10;
+            const float v = in_val(g, sm.cent, syms, FIRST ? c - 1 : c, y + dy, x + dx);
+            const float4 wv = *reinterpret_cast<const float4*>(sm.w0 + t * 24 + jg * 4);
+            acc[0] = fmaf(v, wv.x, acc[0]);
+            acc[1] = fmaf(v, wv.y, acc[1]);
+            acc[2] = fmaf(v, wv.z, acc[2]);
+            acc[3] = fmaf(v, wv.w, acc[3]);
+        }
+        *reinterpret_cast<float4*>(dst + (size_t)xi * PROW + jg * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+// which layers have an output in row (c, y): layer l lives on c >= l-3, y in [l-3, h+2-l]
+__device__ __forceinline__ bool row_has(const Geom& g, int layer, int c, int y) {
+    return c >= layer - 3 && y >= layer - 3 && y <= g.h + 2 - layer;
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void chains(const Geom& g, const Smem& sm, int tid, int nthr, int c, int y, const uint8_t* syms,
+                                       float* act_img, float* p9) {
+    if (row_has(g, 1, c, y)) chain_mid<FIRST, 1>(g, sm, tid, nthr, c, y, act_img, p9);
+    if (row_has(g, 2, c, y)) chain_mid<FIRST, 2>(g, sm, tid, nthr, c, y, act_img, p9);
+    if (row_has(g, 3, c, y)) chain_mid<FIRST, 3>(g, sm, tid, nthr, c, y, act_img, p9);
+    chain_l0<FIRST>(g, sm, tid, nthr, c, y, syms, p9);
+}
+
+// ------------------------------------------------------------------ range decoder state
+// code/arithmetic_coding.py:163-222 with 32-bit state; bits past the end read as zero (:217-222)
+struct Coder {
+    uint64_t low, high, code;
+    const uint8_t* p;
+    int64_t n, pos;
+    uint32_t cur, nxt;
+    int left;
+
+    __device__ __forceinline__ uint32_t word(int64_t at) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v = (v << 8) | (at + i < n ? (uint32_t)p[at + i] : 0u);
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t* bytes, int64_t nbytes) {
+        p = bytes;
+        n = nbytes;
+        low = 0;
+        high = 0xffffffffull;
+        code = word(0);                 // ArithmeticDecoder.__init__ reads STATE_SIZE bits (:176-178)
+        cur = word(4);
+        nxt = word(8);
+        pos = 12;
+        left = 32;
+    }
+    __device__ __forceinline__ uint32_t bit() {
+        if (left == 0) {
+            cur = nxt;
+            nxt = word(pos);
+            pos += 4;
+            left = 32;
+        }
+        --left;
+        return (cur >> left) & 1u;
+    }
+    // ArithmeticCoderBase.update (:80-115) + ArithmeticDecoder.shift/underflow (:204-213)
+    __device__ __forceinline__ void narrow(uint64_t lo_b, uint64_t hi_b) {
+        const uint64_t kMask = 0xffffffffull, kTop = 0x80000000ull, kSecond = 0x40000000ull;
+        const uint64_t base = low;
+        low = base + lo_b;
+        high = base + hi_b - 1;
+        for (int guard = 0; guard < 64 && ((low ^ high) & kTop) == 0; ++guard) {
+            code = ((code << 1) & kMask) | bit();
+            low = (low << 1) & kMask;
+            high = ((high << 1) & kMask) | 1;
+        }
+        for (int guard = 0; guard < 64 && (low & ~high & kSecond) != 0; ++guard) {
+            code = (code & kTop) | ((code << 1) & (kMask >> 1)) | bit();
+            low = (low << 1) & (kMask >> 1);
+            high = ((high << 1) & (kMask >> 1)) | kTop | 1;
+        }
+    }
+};
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src);
+    const uint32_t hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------ one row, symbol by symbol (warp 0)
+__device__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int lane, int c, int y, Coder& cd,
+                           uint8_t* sym_img, const uint8_t* force_img, float* act_img, int64_t* freqs_img, int first_sym) {
+    const int j = lane < KC ? lane : KC - 1;      // lanes 24..31 shadow lane 23; their stores are masked
+    const int j3 = lane & 7;
+    const int L = a.L;
+    float W1l[KC], W1c[KC], W2l[KC], W2c[KC], W3l[KC], W3c[KC];
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+        W1l[i] = sm.w1[(12 * 24 + i) * 24 + j];
+        W1c[i] = sm.w1[(13 * 24 + i) * 24 + j];
+        W2l[i] = sm.w2[(12 * 24 + i) * 24 + j];
+        W2c[i] = sm.w2[(13 * 24 + i) * 24 + j];
+        W3l[i] = sm.w3[(12 * 24 + i) * 8 + j3];
+        W3c[i] = sm.w3[(13 * 24 + i) * 8 + j3];
+    }
+    const float w0l = sm.w0[12 * 24 + j];
+    const float b0 = sm.b[j], b1 = sm.b[24 + j], b2 = sm.b[48 + j], b3 = sm.b[72 + j3];
+    const float pad = sm.cent[0];
+    const bool r1 = row_has(g, 1, c, y), r2 = row_has(g, 2, c, y), r3 = row_has(g, 3, c, y);
+    float* a0row = act_row(act_img, g, 0, c, y);
+    float* a1row = act_row(act_img, g, 1, c, y);
+    float* a2row = act_row(act_img, g, 2, c, y);
+    const float* P = sm.P;
+
+    float vleft = pad;                            // input at (c, y, -4)
+    float acc1 = P[24 + j], acc2 = P[48 + j], acc3 = P[72 + j3];
+    for (int xi = 0; xi < g.W6; ++xi) {
+        const int x = xi - 3;
+        float n1 = 0.f, n2 = 0.f, n3 = 0.f;       // chains of the next position after taps 0..11
+        if (xi + 1 < g.W6) {
+            const float* Pn = P + (size_t)(xi + 1) * PROW;
+            n1 = Pn[24 + j];
+            n2 = Pn[48 + j];
+            n3 = Pn[72 + j3];
+        }
+        // layer 0: tap 12 (left input), bias, ReLU
+        const float a0 = fmaxf(__fadd_rn(fmaf(vleft, w0l, P[(size_t)xi * PROW + j]), b0), 0.f);
+        // layer 1: tap 13 of this position, tap 12 of the next one
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            const float ai = __shfl_sync(FULL, a0, i);
+            acc1 = fmaf(ai, W1c[i], acc1);
+            n1 = fmaf(ai, W1l[i], n1);
+        }
+        const float a1 = fmaxf(__fadd_rn(acc1, b1), 0.f);
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            const float ai = __shfl_sync(FULL, a1, i);
+            acc2 = fmaf(ai, W2c[i], acc2);
+            n2 = fmaf(ai, W2l[i], n2);
+        }
+        const float a2 = __fadd_rn(__fadd_rn(acc2, b2), a0);      // + residual (code/probclass.py:196)
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            const float ai = __shfl_sync(FULL, a2, i);
+            acc3 = fmaf(ai, W3c[i], acc3);
+            n3 = fmaf(ai, W3l[i], n3);
+        }
+        const float lg = fmaxf(__fadd_rn(acc3, b3), 0.f);         // ReLU on the logits (code/probclass.py:220,233)
+        if (lane < KC) {
+            a0row[(size_t)xi * KC + lane] = a0;
+            if (r1) a1row[(size_t)xi * KC + lane] = a1;
+            if (r2) a2row[(size_t)xi * KC + lane] = a2;
+        }
+        float vnew = pad;
+        if (r3 && x >= 0 && x < g.w) {
+            // softmax -> int64(pr * 1e9) -> max(., 1): same operation order as pc_final_kernel<HEAD_FREQS>
+            float m = __shfl_sync(FULL, lg, 0);
+#pragma unroll
+            for (int l = 1; l < 8; ++l) {
+                const float v = __shfl_sync(FULL, lg, l);
+                if (l < L) m = fmaxf(m, v);
+            }
+            const float e = expf(__fsub_rn(lg, m));
+            float s = 0.f;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                const float v = __shfl_sync(FULL, e, l);
+                if (l < L) s = __fadd_rn(s, v);
+            }
+            long long f = (long long)__fmul_rn(__fdiv_rn(e, s), 1e9f);
+            if (f < 1) f = 1;
+            const uint32_t fown = lane < L ? (uint32_t)f : 0u;
+            uint32_t cum = 0, total = 0;          // lane k: sum of f_l, l < k
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                const uint32_t v = __shfl_sync(FULL, fown, l);
+                if (l < lane) cum += v;
+                total += v;
+            }
+            const size_t at = ((size_t)c * g.h + y) * g.w + x;
+            if (freqs_img && lane < L) freqs_img[at * L + lane] = (int64_t)fown;
+            int sym;
+            if (force_img) {
+                sym = force_img[at];
+            } else if (at == 0) {
+                sym = first_sym;
+            } else {
+                // ArithmeticDecoder.read (:181-201): lane k holds the lower bound of symbol k in the current range
+                const uint64_t range = cd.high - cd.low + 1;
+                const uint64_t offset = cd.code - cd.low;
+                const uint64_t bound = (uint64_t)cum * range / total;
+                const unsigned le = __ballot_sync(FULL, lane <= L && bound <= offset);
+                sym = __popc(le) - 1;
+                if (sym > L - 1) sym = L - 1;     // corrupt stream: stay inside the table
+                const uint64_t lo_b = shfl64(bound, sym), hi_b = shfl64(bound, sym + 1);
+                cd.narrow(lo_b, hi_b);
+            }
+            if (lane == 0) sym_img[at] = (uint8_t)sym;
+            vnew = sm.cent[sym];
+        }
+        vleft = vnew;
+        acc1 = n1;
+        acc2 = n2;
+        acc3 = n3;
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    Smem sm;
+    sm.w1 = smem;
+    sm.w2 = sm.w1 + 14 * 24 * 24;
+    sm.w3 = sm.w2 + 14 * 24 * 24;
+    sm.w0 = sm.w3 + 14 * 24 * 8;
+    sm.b = sm.w0 + 13 * 24;
+    sm.cent = sm.b + PROW;
+    sm.P = sm.cent + 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 14 * 24 * 24; i += NT) {
+        sm.w1[i] = a.w1[i];
+        sm.w2[i] = a.w2[i];
+    }
+    for (int i = tid; i < 14 * 24 * 8; i += NT) {
+        const int o = i & 7;
+        sm.w3[i] = o < a.L ? a.w3[(i >> 3) * a.L + o] : 0.f;
+    }
+    for (int i = tid; i < 13 * 24; i += NT) sm.w0[i] = a.w0[i];
+    if (tid < 24) {
+        sm.b[tid] = a.b0[tid];
+        sm.b[24 + tid] = a.b1[tid];
+        sm.b[48 + tid] = a.b2[tid];
+    }
+    if (tid < 8) {
+        sm.b[72 + tid] = tid < a.L ? a.b3[tid] : 0.f;
+        sm.cent[tid] = a.centers[tid];
+    }
+
+    Geom g;
+    g.C = a.C; g.h = a.h; g.w = a.w; g.H6 = a.h + 6; g.W6 = a.w + 6;
+    g.slot = (size_t)g.H6 * g.W6 * KC;
+    g.layer = 2 * g.slot;
+    const int n = blockIdx.x;
+    const size_t vol = (size_t)a.C * a.h * a.w;
+    uint8_t* sym_img = a.sym_out + n * vol;
+    const uint8_t* force_img = a.force_sym ? a.force_sym + n * vol : nullptr;
+    const uint8_t* syms = force_img ? force_img : sym_img;      // what the chains read back
+    float* act_img = a.act + (size_t)n * 3 * g.layer;
+    float* p9 = a.p9 + (size_t)n * g.W6 * PROW;
+    int64_t* freqs_img = a.freqs_out ? a.freqs_out + n * vol * a.L : nullptr;
+    Coder cd;
+    cd.init(a.stream + a.stream_off[n], a.stream_off[n + 1] - a.stream_off[n]);
+    const int first_sym = a.first_sym[n];
+
+    const int R = (a.C + 3) * g.H6;
+    for (int r = 0; r < R; ++r) {
+        const int c = r / g.H6 - 3, y = r % g.H6 - 3;
+        __syncthreads();            // row r-1 is decoded and stored; helper chains of row r are in p9
+        if (y == -3) {              // first row of a channel: nobody could run ahead
+            chains<true>(g, sm, tid, NT, c, y, syms, act_img, p9);
+            __syncthreads();
+        }
+        chains<false>(g, sm, tid, NT, c, y, syms, act_img, p9);
+        __syncthreads();
+        if (warp == 0)
+            decode_row(g, sm, a, lane, c, y, cd, sym_img, force_img, act_img, freqs_img, first_sym);
+        else if (y + 1 <= a.h + 2)
+            chains<true>(g, sm, tid - 32, NT - 32, c, y + 1, syms, act_img, p9);
+    }
+}
+
+}  // namespace
+
+size_t pc_decode_workspace_bytes(int N, int C, int h, int w) {
+    const size_t act = (size_t)3 * 2 * (h + 6) * (w + 6) * KC * sizeof(float);
+    const size_t p9 = (size_t)(w + 6) * PROW * sizeof(float);
+    return (size_t)N * (align_up(act, 256) + align_up(p9, 256)) + 1024;
+}
+
+int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_bytes, cudaStream_t s) {
+    IC_REQUIRE(w.K == KC, IC_ERR_UNSUPPORTED, "pc_decode: arch_param__k = %d not built (24 is)", w.K);
+    IC_REQUIRE(w.L >= 2 && w.L <= 8, IC_ERR_UNSUPPORTED, "pc_decode: num_centers = %d not built (2..8)", w.L);
+    const size_t smem = ((size_t)SMEM_FIXED_FLOATS + (size_t)(in.w + 6) * PROW) * sizeof(float);
+    IC_REQUIRE(smem <= 227 * 1024, IC_ERR_UNSUPPORTED, "pc_decode: latent width %d does not fit one CTA's shared memory (max %d)",
+               in.w, (int)((227 * 1024 / sizeof(float) - SMEM_FIXED_FLOATS) / PROW) - 6);
+    Arena ar(ws, ws_bytes);
+    const size_t act_img = (size_t)3 * 2 * (in.h + 6) * (in.w + 6) * KC;
+    float* act = ar.get<float>((size_t)in.N * act_img);
+    float* p9 = ar.get<float>((size_t)in.N * (in.w + 6) * PROW);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "pc_decode workspace too small: need %zu, have %zu", ar.off, ws_bytes);
+    DecArgs a;
+    a.w0 = w.w0; a.b0 = w.b0; a.w1 = w.w1; a.b1 = w.b1; a.w2 = w.w2; a.b2 = w.b2; a.w3 = w.w3; a.b3 = w.b3;
+    a.C = in.C; a.h = in.h; a.w = in.w; a.L = w.L;
+    for (int i = 0; i < 8; ++i) a.centers[i] = i < w.L ? in.centers_host[i] : 0.f;
+    a.stream = in.stream;
+    a.stream_off = in.stream_off;
+    a.first_sym = in.first_sym;
+    a.sym_out = in.sym_out;
+    a.act = act;
+    a.p9 = p9;
+    a.force_sym = in.force_sym;
+    a.freqs_out = in.freqs_out;
+    IC_CHECK_CUDA(cudaFuncSetAttribute(pc_seq_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(IC_PROF_PROBCLASS, s, 1);
+    pc_seq_decode_kernel<<<in.N, NT, smem, s>>>(a);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+}  // namespace ic

@@ -454,8 +454,8 @@ size_t pc_workspace_bytes(int KC, int N, int D, int H, int W, int pad_d, int pad
 }
 
 int pc_forward(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs,
-               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s) {
-    if (w.K == 24 && w.tc) return run_pc_tc(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
+               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s, bool canonical) {
+    if (w.K == 24 && w.tc && !canonical) return run_pc_tc(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
     if (w.K == 24) return run_pc<24>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
     if (w.K == 64) return run_pc<64>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
     set_error("probclass: arch_param__k = %d not built (24 and 64 are)", w.K);

@@ -33,7 +33,23 @@ struct PcInput {
 enum { PC_HEAD_LOGITS = 0, PC_HEAD_BITCOST = 1, PC_HEAD_FREQS = 2 };
 
 size_t pc_workspace_bytes(int KC, int N, int D, int H, int W, int pad_d, int pad_hw);
+// canonical = true: always the float32 FFMA kernels, whose per-output fmaf chain the sequential
+// decoder (pc_decode.cu) reproduces bit for bit
 int pc_forward(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs,
-               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s);
+               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s, bool canonical = false);
+
+// sequential decode of N bitstreams (pc_decode.cu); all pointers are device pointers
+struct PcDecodeInput {
+    int N, C, h, w;
+    float centers_host[8];
+    const uint8_t* stream;          // concatenated bitstreams
+    const int64_t* stream_off;      // [N + 1] byte offsets into `stream`
+    const int32_t* first_sym;       // [N]
+    uint8_t* sym_out;               // N,C,h,w
+    const uint8_t* force_sym;       // optional: teacher forcing (no range decoding)
+    int64_t* freqs_out;             // optional: N,C,h,w,L tables the decoder used
+};
+size_t pc_decode_workspace_bytes(int N, int C, int h, int w);
+int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_bytes, cudaStream_t s);
 
 }  // namespace ic

@@ -133,10 +133,11 @@ class _Network3D(object):
                                                ws.numel(), _lib.stream_ptr()))
         return out
 
-    def freqs(self, symbols, centers):
+    def freqs(self, symbols, centers, codec=False):
         """ONE batched pass replacing the reference's per-symbol PredictionNetwork loop
         (code/probclass.py:441-476 driven by code/bit_counter.py:103-134).
-        symbols NCHW int64 -> (freqs N,C,h,w,L int64 ; theoretical bits per image (N,) float64)."""
+        symbols NCHW int64 -> (freqs N,C,h,w,L int64 ; theoretical bits per image (N,) float64).
+        codec=True: the tables of a real bitstream, in the arithmetic decode_streams() reproduces."""
         self._need_handle()
         sym = symbols.contiguous().to(torch.int64)
         N, C, h, w = sym.shape
@@ -144,9 +145,41 @@ class _Network3D(object):
         sums = torch.empty(N, dtype=torch.float64, device=sym.device)
         ws = self._workspace(N, C, h, w)
         centers = centers.contiguous().float()
-        _lib.check(_lib.lib().ic_pc_freqs_fwd(self._handle, _lib.ptr(sym), _lib.ptr(centers), N, C, h, w, _lib.ptr(out),
-                                              _lib.ptr(sums), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        fn = _lib.lib().ic_pc_codec_freqs_fwd if codec else _lib.lib().ic_pc_freqs_fwd
+        _lib.check(fn(self._handle, _lib.ptr(sym), _lib.ptr(centers), N, C, h, w, _lib.ptr(out),
+                      _lib.ptr(sums), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         return out, sums
+
+    def decode_streams(self, streams, first_syms, shape, centers, force_symbols=None, return_freqs=False):
+        """The decoder half of --real_bpp (code/bit_counter.py:137-163), for N images at once:
+        streams = list of N byte strings written by ArithmeticEncoder over freqs(codec=True) tables,
+        first_syms = the N side-information symbols, shape = (C, h, w).
+        -> symbols N,C,h,w uint8 (CUDA).  One CTA per image: cached-activation context model +
+        range decoder on the device.  force_symbols / return_freqs are debug hooks."""
+        self._need_handle()
+        L = _lib.lib()
+        N = len(streams)
+        C, h, w = (int(v) for v in shape)
+        offs = np.zeros(N + 1, np.int64)
+        offs[1:] = np.cumsum([len(b) for b in streams])
+        blob = np.frombuffer(b''.join(bytes(b) for b in streams) + b'\0' * 16, dtype=np.uint8)
+        d_stream = torch.from_numpy(blob.copy()).cuda()
+        d_offs = torch.from_numpy(offs).cuda()
+        d_first = torch.tensor([int(v) for v in first_syms], dtype=torch.int32, device='cuda')
+        out = torch.zeros((N, C, h, w), dtype=torch.uint8, device='cuda')
+        force = None
+        if force_symbols is not None:
+            force = force_symbols.to('cuda', torch.uint8).contiguous()
+            assert tuple(force.shape) == (N, C, h, w)
+        seen = torch.zeros((N, C, h, w, self.L), dtype=torch.int64, device='cuda') if return_freqs else None
+        nbytes = L.ic_pc_decode_workspace_bytes(self._handle, N, C, h, w)
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
+        centers = centers.contiguous().float()
+        _lib.check(L.ic_pc_decode_fwd(self._handle, _lib.ptr(d_stream), _lib.ptr(d_offs), _lib.ptr(d_first), _lib.ptr(centers),
+                                      N, C, h, w, _lib.ptr(out), _lib.ptr(force) if force is not None else None,
+                                      _lib.ptr(seen) if seen is not None else None, _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()))
+        return (out, seen) if return_freqs else out
 
 
 class _ResShallow(_Network3D):
@@ -264,10 +297,17 @@ class PredictionNetwork(object):
         assert np.all(f > 0), 'We do not want zero frequencies!: {}'.format(f)
         return f
 
-    def get_all_freqs(self, symbols):
+    def get_all_freqs(self, symbols, codec=False):
         """symbols CHW (numpy or tensor) -> int64 (C,h,w,L) numpy, every position's table in
-        the coder's raster order, plus the theoretical bit cost."""
+        the coder's raster order, plus the theoretical bit cost.  codec=True: the tables
+        decode_symbols() re-derives bit for bit (use these to write a stream)."""
         s = torch.as_tensor(np.asarray(symbols) if not torch.is_tensor(symbols) else symbols)
         assert s.dim() == 3
-        f, bits = self.pc.freqs(s[None].to('cuda', torch.int64), self.centers)
+        f, bits = self.pc.freqs(s[None].to('cuda', torch.int64), self.centers, codec=codec)
         return f[0].cpu().numpy(), float(bits[0])
+
+    def decode_symbols(self, stream, first_sym, shape):
+        """bitstream + side information -> symbols CHW (numpy int64): code/bit_counter.py:137-163
+        without the per-symbol sess.run."""
+        out = self.pc.decode_streams([stream], [first_sym], shape, self.centers)
+        return out[0].cpu().numpy().astype(np.int64)

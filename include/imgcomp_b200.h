@@ -149,6 +149,30 @@ int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_
                     int N, int C, int h, int w, int64_t* d_freqs, double* d_bits_sum,
                     void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Codec pair for a real bitstream (the decoder half of code/bit_counter.py:137-163).
+ *
+ * ic_pc_codec_freqs_fwd: same contract as ic_pc_freqs_fwd, but always computed by the float32
+ * kernels whose operation order the sequential decoder reproduces: the tables an encoder
+ * feeds to the range coder must be the tables the decoder will derive, bit for bit.
+ *
+ * ic_pc_decode_fwd replaces `_decode` (code/bit_counter.py:137-163; README.md:65 "~200 s"):
+ * N independent bitstreams (concatenated in d_stream, stream n = bytes
+ * [d_stream_offsets[n], d_stream_offsets[n+1])), each written by ArithmeticEncoder
+ * (code/arithmetic_coding.py:127-159) over the symbols of one C x h x w volume in raster
+ * order, first symbol passed as side information (d_first_sym, code/bit_counter.py:118-121).
+ * One CTA per image decodes symbol by symbol: context model with cached activations
+ * (README.md:72-73) + range decoder on the device.  -> d_symbols N x C x h x w uint8.
+ * Debug hooks: d_force_symbols (same shape, optional) replaces range decoding by teacher
+ * forcing; d_freqs_seen (optional, N x C x h x w x L int64) receives every table used. */
+int ic_pc_codec_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_centers,
+                          int N, int C, int h, int w, int64_t* d_freqs, double* d_bits_sum,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+size_t ic_pc_decode_workspace_bytes(const ic_pc_t* pc, int N, int C, int h, int w);
+int ic_pc_decode_fwd(const ic_pc_t* pc, const uint8_t* d_stream, const int64_t* d_stream_offsets,
+                     const int32_t* d_first_sym, const float* d_centers, int N, int C, int h, int w,
+                     uint8_t* d_symbols, const uint8_t* d_force_symbols, int64_t* d_freqs_seen,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* replaces ONE PredictionNetwork.get_freqs call (code/probclass.py:441-444,461-476): an UN-padded
  * block of context symbols N x D x H x W (the reference feeds D,H,W = 5,9,9) is gathered through
  * `centers`, run through the context model -> int64 freqs N x (D-4) x (H-8) x (W-8) x L.  Same
