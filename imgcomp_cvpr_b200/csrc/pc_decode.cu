@@ -21,6 +21,7 @@
 //   tap  13     the position itself (layers 1-3) -> decode warp, critical path
 // and the table it ends in is bit-identical to ic_pc_codec_freqs_fwd's.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "probclass.cuh"
@@ -46,7 +47,9 @@ struct DecArgs {
     float* p9;                      // per image: [w+6][PROW]
     const uint8_t* force_sym;       // debug: teacher forcing, no range decoding
     int64_t* freqs_out;             // debug: N,C,h,w,L tables as the decoder saw them
+    long long* prof;                // debug (IC_PC_DECODE_PROF=1): cycle counters of image 0
 };
+
 
 struct Smem {
     float* w1;     // [14][24][24]
@@ -160,15 +163,24 @@ __device__ __forceinline__ void chains(const Geom& g, const Smem& sm, int tid, i
 }
 
 // ------------------------------------------------------------------ range decoder state
-// code/arithmetic_coding.py:163-222 with 32-bit state; bits past the end read as zero (:217-222)
+// code/arithmetic_coding.py:163-222 with 32-bit state, kept uniform across the warp.
+// Bits past the end of the stream read as zero (:217-222).
 struct Coder {
-    uint64_t low, high, code;
+    uint32_t low, high, code;
     const uint8_t* p;
     int64_t n, pos;
-    uint32_t cur, nxt;
-    int left;
+    uint64_t buf;        // next bits of the stream, MSB first
+    int avail;           // valid bits in buf
+    uint32_t nxt;        // prefetched word after buf
 
+    // big-endian 32-bit word at byte offset `at`
     __device__ __forceinline__ uint32_t word(int64_t at) const {
+        if (at + 8 <= n) {
+            const uintptr_t q = (uintptr_t)(p + at);
+            const uint32_t* al = reinterpret_cast<const uint32_t*>(q & ~(uintptr_t)3);
+            const uint32_t le = __funnelshift_r(al[0], al[1], 8 * (unsigned)(q & 3));
+            return __byte_perm(le, 0, 0x0123);
+        }
         uint32_t v = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) v = (v << 8) | (at + i < n ? (uint32_t)p[at + i] : 0u);
@@ -178,54 +190,71 @@ struct Coder {
         p = bytes;
         n = nbytes;
         low = 0;
-        high = 0xffffffffull;
+        high = 0xffffffffu;
         code = word(0);                 // ArithmeticDecoder.__init__ reads STATE_SIZE bits (:176-178)
-        cur = word(4);
+        buf = (uint64_t)word(4) << 32;
+        avail = 32;
         nxt = word(8);
         pos = 12;
-        left = 32;
     }
-    __device__ __forceinline__ uint32_t bit() {
-        if (left == 0) {
-            cur = nxt;
+    // next k bits, 1 <= k <= 32
+    __device__ __forceinline__ uint32_t bits(int k) {
+        if (avail < 32) {
+            buf |= (uint64_t)nxt << (32 - avail);
+            avail += 32;
             nxt = word(pos);
             pos += 4;
-            left = 32;
         }
-        --left;
-        return (cur >> left) & 1u;
+        const uint32_t v = (uint32_t)(buf >> (64 - k));
+        buf <<= k;
+        avail -= k;
+        return v;
     }
-    // ArithmeticCoderBase.update (:80-115) + ArithmeticDecoder.shift/underflow (:204-213)
-    __device__ __forceinline__ void narrow(uint64_t lo_b, uint64_t hi_b) {
-        const uint64_t kMask = 0xffffffffull, kTop = 0x80000000ull, kSecond = 0x40000000ull;
-        const uint64_t base = low;
-        low = base + lo_b;
-        high = base + hi_b - 1;
-        for (int guard = 0; guard < 64 && ((low ^ high) & kTop) == 0; ++guard) {
-            code = ((code << 1) & kMask) | bit();
-            low = (low << 1) & kMask;
-            high = ((high << 1) & kMask) | 1;
+    // ArithmeticCoderBase.update (:80-115) with ArithmeticDecoder.shift / underflow (:204-213).
+    // The reference shifts one bit per loop iteration; both loops are closed forms here:
+    //   loop 1 runs while the top bits of low and high agree   -> clz(low ^ high) iterations
+    //   loop 2 runs while low = 01..., high = 10...            -> leading ones of ((low & ~high) << 1)
+    __device__ __forceinline__ void narrow(uint32_t lo_b, uint64_t hi_b) {
+        uint32_t nl = low + lo_b;
+        uint32_t nh = (uint32_t)((uint64_t)low + hi_b - 1);
+        const int k = __clz((int)(nl ^ nh));
+        if (k == 32) {
+            nl = 0;
+            nh = 0xffffffffu;
+            code = bits(32);
+        } else if (k > 0) {
+            nl <<= k;
+            nh = (nh << k) | ((1u << k) - 1);
+            code = (code << k) | bits(k);
         }
-        for (int guard = 0; guard < 64 && (low & ~high & kSecond) != 0; ++guard) {
-            code = (code & kTop) | ((code << 1) & (kMask >> 1)) | bit();
-            low = (low << 1) & (kMask >> 1);
-            high = ((high << 1) & (kMask >> 1)) | kTop | 1;
+        const int m = __clz((int)~((nl & ~nh) << 1));
+        if (m > 0) {
+            nl = (nl << m) & 0x7fffffffu;
+            nh = ((nh << m) & 0x7fffffffu) | 0x80000000u | ((1u << m) - 1);
+            code = (code & 0x80000000u) | ((code << m) & 0x7fffffffu) | bits(m);
         }
+        low = nl;
+        high = nh;
     }
 };
 
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-    const uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src);
-    const uint32_t hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
-    return ((uint64_t)hi << 32) | lo;
+// floor(cum * range / total) for cum <= total < 2^31, range <= 2^32: double estimate + exact fix-up
+__device__ __forceinline__ uint64_t scale_bound(uint32_t cum, uint64_t range, uint32_t total, double inv_total) {
+    const uint64_t A = (uint64_t)cum * range;                       // < 2^63
+    uint64_t q = (uint64_t)__double2ull_rz(__ull2double_rz(A) * inv_total);
+    const int64_t r = (int64_t)(A - q * total);                      // |estimate - exact| < 1
+    if (r < 0) --q;
+    else if (r >= (int64_t)total) ++q;
+    return q;
 }
 
 // ------------------------------------------------------------------ one row, symbol by symbol (warp 0)
-__device__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int lane, int c, int y, Coder& cd,
-                           uint8_t* sym_img, const uint8_t* force_img, float* act_img, int64_t* freqs_img, int first_sym) {
+template <int L>
+__device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int lane, int c, int y, Coder& cd,
+                                           uint8_t* sym_img, const uint8_t* force_img, float* act_img, int64_t* freqs_img,
+                                           int first_sym, long long* lp) {
     const int j = lane < KC ? lane : KC - 1;      // lanes 24..31 shadow lane 23; their stores are masked
     const int j3 = lane & 7;
-    const int L = a.L;
     float W1l[KC], W1c[KC], W2l[KC], W2c[KC], W3l[KC], W3c[KC];
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
@@ -240,24 +269,24 @@ __device__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int 
     const float b0 = sm.b[j], b1 = sm.b[24 + j], b2 = sm.b[48 + j], b3 = sm.b[72 + j3];
     const float pad = sm.cent[0];
     const bool r1 = row_has(g, 1, c, y), r2 = row_has(g, 2, c, y), r3 = row_has(g, 3, c, y);
-    float* a0row = act_row(act_img, g, 0, c, y);
-    float* a1row = act_row(act_img, g, 1, c, y);
-    float* a2row = act_row(act_img, g, 2, c, y);
+    float* a0row = act_row(act_img, g, 0, c, y) + lane;
+    float* a1row = act_row(act_img, g, 1, c, y) + lane;
+    float* a2row = act_row(act_img, g, 2, c, y) + lane;
     const float* P = sm.P;
+    const bool prof = lp != nullptr;
 
     float vleft = pad;                            // input at (c, y, -4)
     float acc1 = P[24 + j], acc2 = P[48 + j], acc3 = P[72 + j3];
+    float p0 = P[j];
     for (int xi = 0; xi < g.W6; ++xi) {
         const int x = xi - 3;
-        float n1 = 0.f, n2 = 0.f, n3 = 0.f;       // chains of the next position after taps 0..11
-        if (xi + 1 < g.W6) {
-            const float* Pn = P + (size_t)(xi + 1) * PROW;
-            n1 = Pn[24 + j];
-            n2 = Pn[48 + j];
-            n3 = Pn[72 + j3];
-        }
+        const long long t0 = prof ? clock64() : 0;
+        // chains of the next position after taps 0..11 (the last iteration reads one row past: P has a spare row)
+        const float* Pn = P + (size_t)(xi + 1) * PROW;
+        float n1 = Pn[24 + j], n2 = Pn[48 + j], n3 = Pn[72 + j3];
+        const float p0n = Pn[j];
         // layer 0: tap 12 (left input), bias, ReLU
-        const float a0 = fmaxf(__fadd_rn(fmaf(vleft, w0l, P[(size_t)xi * PROW + j]), b0), 0.f);
+        const float a0 = fmaxf(__fadd_rn(fmaf(vleft, w0l, p0), b0), 0.f);
         // layer 1: tap 13 of this position, tap 12 of the next one
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
@@ -281,36 +310,42 @@ __device__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int 
         }
         const float lg = fmaxf(__fadd_rn(acc3, b3), 0.f);         // ReLU on the logits (code/probclass.py:220,233)
         if (lane < KC) {
-            a0row[(size_t)xi * KC + lane] = a0;
-            if (r1) a1row[(size_t)xi * KC + lane] = a1;
-            if (r2) a2row[(size_t)xi * KC + lane] = a2;
+            a0row[(size_t)xi * KC] = a0;
+            if (r1) a1row[(size_t)xi * KC] = a1;
+            if (r2) a2row[(size_t)xi * KC] = a2;
         }
+        const long long t1 = prof ? clock64() : 0;
         float vnew = pad;
         if (r3 && x >= 0 && x < g.w) {
             // softmax -> int64(pr * 1e9) -> max(., 1): same operation order as pc_final_kernel<HEAD_FREQS>
-            float m = __shfl_sync(FULL, lg, 0);
+            float lv[L];
 #pragma unroll
-            for (int l = 1; l < 8; ++l) {
-                const float v = __shfl_sync(FULL, lg, l);
-                if (l < L) m = fmaxf(m, v);
-            }
+            for (int l = 0; l < L; ++l) lv[l] = __shfl_sync(FULL, lg, l);
+            float m = lv[0];
+#pragma unroll
+            for (int l = 1; l < L; ++l) m = fmaxf(m, lv[l]);
             const float e = expf(__fsub_rn(lg, m));
+            float ev[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) ev[l] = __shfl_sync(FULL, e, l);
             float s = 0.f;
 #pragma unroll
-            for (int l = 0; l < 8; ++l) {
-                const float v = __shfl_sync(FULL, e, l);
-                if (l < L) s = __fadd_rn(s, v);
-            }
+            for (int l = 0; l < L; ++l) s = __fadd_rn(s, ev[l]);
+            // lane l < L: its own table entry (one IEEE division per lane, in parallel); then every lane
+            // gathers the table: lane k keeps the lower bound of symbol k (k = L: the total)
             long long f = (long long)__fmul_rn(__fdiv_rn(e, s), 1e9f);
             if (f < 1) f = 1;
             const uint32_t fown = lane < L ? (uint32_t)f : 0u;
-            uint32_t cum = 0, total = 0;          // lane k: sum of f_l, l < k
+            uint32_t fv[L];
 #pragma unroll
-            for (int l = 0; l < 8; ++l) {
-                const uint32_t v = __shfl_sync(FULL, fown, l);
-                if (l < lane) cum += v;
-                total += v;
+            for (int l = 0; l < L; ++l) fv[l] = __shfl_sync(FULL, fown, l);
+            uint32_t cum = 0, total = 0;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                if (l < lane) cum += fv[l];
+                total += fv[l];
             }
+            const long long t2 = prof ? clock64() : 0;
             const size_t at = ((size_t)c * g.h + y) * g.w + x;
             if (freqs_img && lane < L) freqs_img[at * L + lane] = (int64_t)fown;
             int sym;
@@ -320,25 +355,33 @@ __device__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int 
                 sym = first_sym;
             } else {
                 // ArithmeticDecoder.read (:181-201): lane k holds the lower bound of symbol k in the current range
-                const uint64_t range = cd.high - cd.low + 1;
-                const uint64_t offset = cd.code - cd.low;
-                const uint64_t bound = (uint64_t)cum * range / total;
-                const unsigned le = __ballot_sync(FULL, lane <= L && bound <= offset);
+                const uint64_t range = (uint64_t)cd.high - cd.low + 1;
+                const uint32_t offset = cd.code - cd.low;
+                const uint64_t bound = scale_bound(cum, range, total, __drcp_rn((double)total));
+                const unsigned le = __ballot_sync(FULL, lane <= L && bound <= (uint64_t)offset);
                 sym = __popc(le) - 1;
                 if (sym > L - 1) sym = L - 1;     // corrupt stream: stay inside the table
-                const uint64_t lo_b = shfl64(bound, sym), hi_b = shfl64(bound, sym + 1);
-                cd.narrow(lo_b, hi_b);
+                const uint32_t lo_b = __shfl_sync(FULL, (uint32_t)bound, sym);
+                const uint32_t hi32 = __shfl_sync(FULL, (uint32_t)bound, sym + 1);
+                cd.narrow(lo_b, sym + 1 == L ? range : (uint64_t)hi32);
             }
             if (lane == 0) sym_img[at] = (uint8_t)sym;
             vnew = sm.cent[sym];
+            if (prof) {
+                lp[1] += t2 - t1;
+                lp[2] += clock64() - t2;
+            }
         }
+        if (prof) lp[0] += t1 - t0;
         vleft = vnew;
         acc1 = n1;
         acc2 = n2;
         acc3 = n3;
+        p0 = p0n;
     }
 }
 
+template <int L>
 __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
     extern __shared__ __align__(16) float smem[];
     Smem sm;
@@ -356,7 +399,7 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
     }
     for (int i = tid; i < 14 * 24 * 8; i += NT) {
         const int o = i & 7;
-        sm.w3[i] = o < a.L ? a.w3[(i >> 3) * a.L + o] : 0.f;
+        sm.w3[i] = o < L ? a.w3[(i >> 3) * L + o] : 0.f;
     }
     for (int i = tid; i < 13 * 24; i += NT) sm.w0[i] = a.w0[i];
     if (tid < 24) {
@@ -365,7 +408,7 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
         sm.b[48 + tid] = a.b2[tid];
     }
     if (tid < 8) {
-        sm.b[72 + tid] = tid < a.L ? a.b3[tid] : 0.f;
+        sm.b[72 + tid] = tid < L ? a.b3[tid] : 0.f;
         sm.cent[tid] = a.centers[tid];
     }
 
@@ -373,6 +416,7 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
     g.C = a.C; g.h = a.h; g.w = a.w; g.H6 = a.h + 6; g.W6 = a.w + 6;
     g.slot = (size_t)g.H6 * g.W6 * KC;
     g.layer = 2 * g.slot;
+    for (int i = tid; i < PROW; i += NT) sm.P[(size_t)g.W6 * PROW + i] = 0.f;     // spare row read by the last step
     const int n = blockIdx.x;
     const size_t vol = (size_t)a.C * a.h * a.w;
     uint8_t* sym_img = a.sym_out + n * vol;
@@ -380,26 +424,51 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
     const uint8_t* syms = force_img ? force_img : sym_img;      // what the chains read back
     float* act_img = a.act + (size_t)n * 3 * g.layer;
     float* p9 = a.p9 + (size_t)n * g.W6 * PROW;
-    int64_t* freqs_img = a.freqs_out ? a.freqs_out + n * vol * a.L : nullptr;
+    int64_t* freqs_img = a.freqs_out ? a.freqs_out + n * vol * L : nullptr;
     Coder cd;
     cd.init(a.stream + a.stream_off[n], a.stream_off[n + 1] - a.stream_off[n]);
     const int first_sym = a.first_sym[n];
 
+    const bool prof = a.prof && n == 0 && tid == 0;
+    long long lpv[3] = {0, 0, 0}, rows[3] = {0, 0, 0};
+    long long* lp = (a.prof && n == 0) ? lpv : nullptr;
+    const long long tk0 = prof ? clock64() : 0;
     const int R = (a.C + 3) * g.H6;
     for (int r = 0; r < R; ++r) {
         const int c = r / g.H6 - 3, y = r % g.H6 - 3;
+        const long long ta = prof ? clock64() : 0;
         __syncthreads();            // row r-1 is decoded and stored; helper chains of row r are in p9
+        const long long tb = prof ? clock64() : 0;
         if (y == -3) {              // first row of a channel: nobody could run ahead
             chains<true>(g, sm, tid, NT, c, y, syms, act_img, p9);
             __syncthreads();
         }
         chains<false>(g, sm, tid, NT, c, y, syms, act_img, p9);
         __syncthreads();
+        const long long tc = prof ? clock64() : 0;
         if (warp == 0)
-            decode_row(g, sm, a, lane, c, y, cd, sym_img, force_img, act_img, freqs_img, first_sym);
+            decode_row<L>(g, sm, a, lane, c, y, cd, sym_img, force_img, act_img, freqs_img, first_sym, lp);
         else if (y + 1 <= a.h + 2)
             chains<true>(g, sm, tid - 32, NT - 32, c, y + 1, syms, act_img, p9);
+        if (prof) {
+            rows[0] += tb - ta;               // waiting for the helper warps
+            rows[1] += tc - tb;               // chains at row start
+            rows[2] += clock64() - tc;        // decode_row
+        }
     }
+    if (prof) {
+        a.prof[0] = lpv[0]; a.prof[1] = lpv[1]; a.prof[2] = lpv[2];
+        a.prof[3] = rows[0]; a.prof[4] = rows[1]; a.prof[5] = rows[2];
+        a.prof[6] = clock64() - tk0;
+    }
+}
+
+template <int L>
+int launch_decode(const DecArgs& a, int N, size_t smem, cudaStream_t s) {
+    IC_CHECK_CUDA(cudaFuncSetAttribute(pc_seq_decode_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pc_seq_decode_kernel<L><<<N, NT, smem, s>>>(a);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
 }
 
 }  // namespace
@@ -413,9 +482,9 @@ size_t pc_decode_workspace_bytes(int N, int C, int h, int w) {
 int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_bytes, cudaStream_t s) {
     IC_REQUIRE(w.K == KC, IC_ERR_UNSUPPORTED, "pc_decode: arch_param__k = %d not built (24 is)", w.K);
     IC_REQUIRE(w.L >= 2 && w.L <= 8, IC_ERR_UNSUPPORTED, "pc_decode: num_centers = %d not built (2..8)", w.L);
-    const size_t smem = ((size_t)SMEM_FIXED_FLOATS + (size_t)(in.w + 6) * PROW) * sizeof(float);
+    const size_t smem = ((size_t)SMEM_FIXED_FLOATS + (size_t)(in.w + 7) * PROW) * sizeof(float);
     IC_REQUIRE(smem <= 227 * 1024, IC_ERR_UNSUPPORTED, "pc_decode: latent width %d does not fit one CTA's shared memory (max %d)",
-               in.w, (int)((227 * 1024 / sizeof(float) - SMEM_FIXED_FLOATS) / PROW) - 6);
+               in.w, (int)((227 * 1024 / sizeof(float) - SMEM_FIXED_FLOATS) / PROW) - 7);
     Arena ar(ws, ws_bytes);
     const size_t act_img = (size_t)3 * 2 * (in.h + 6) * (in.w + 6) * KC;
     float* act = ar.get<float>((size_t)in.N * act_img);
@@ -433,11 +502,33 @@ int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_b
     a.p9 = p9;
     a.force_sym = in.force_sym;
     a.freqs_out = in.freqs_out;
-    IC_CHECK_CUDA(cudaFuncSetAttribute(pc_seq_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(IC_PROF_PROBCLASS, s, 1);
-    pc_seq_decode_kernel<<<in.N, NT, smem, s>>>(a);
-    IC_CHECK_LAUNCH();
-    return IC_OK;
+    a.prof = nullptr;
+    if (getenv("IC_PC_DECODE_PROF")) {
+        IC_CHECK_CUDA(cudaMalloc((void**)&a.prof, 8 * sizeof(long long)));
+        IC_CHECK_CUDA(cudaMemsetAsync(a.prof, 0, 8 * sizeof(long long), s));
+    }
+    int rc;
+    {
+        ProfScope ps(IC_PROF_PROBCLASS, s, 1);
+        switch (w.L) {
+            case 2: rc = launch_decode<2>(a, in.N, smem, s); break;
+            case 3: rc = launch_decode<3>(a, in.N, smem, s); break;
+            case 4: rc = launch_decode<4>(a, in.N, smem, s); break;
+            case 5: rc = launch_decode<5>(a, in.N, smem, s); break;
+            case 6: rc = launch_decode<6>(a, in.N, smem, s); break;
+            case 7: rc = launch_decode<7>(a, in.N, smem, s); break;
+            default: rc = launch_decode<8>(a, in.N, smem, s); break;
+        }
+    }
+    if (a.prof) {
+        long long h[8];
+        IC_CHECK_CUDA(cudaStreamSynchronize(s));
+        IC_CHECK_CUDA(cudaMemcpy(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(a.prof);
+        fprintf(stderr, "pc_decode cycles (image 0): total %lld | rows: helper wait %lld, row-start chains %lld, decode_row %lld | "
+                        "steps: layers %lld, head %lld, range decode %lld\n", h[6], h[3], h[4], h[5], h[0], h[1], h[2]);
+    }
+    return rc;
 }
 
 }  // namespace ic
