@@ -117,6 +117,12 @@ class _Network(object):
         self._need_handle()
         return self._decode(q.contiguous().float(), is_training)
 
+    def centers_tensor(self):
+        """the loaded centers (L,) float32 CUDA; unlike get_centers_variable it needs no encode() first --
+        a decoder process never encodes (codec.py)."""
+        self._need_handle()
+        return self._centers_value
+
     def get_centers_variable(self):
         if self._centers is None:
             raise ValueError('Call -encode(...) before trying to access centers')      # autoencoder.py:66-67
