@@ -33,7 +33,6 @@ namespace {
 constexpr int KC = 24;            // arch_param__k
 constexpr int PROW = 80;          // floats per position in a partial-sum row: 24 (L0) + 24 (L1) + 24 (L2) + 8 (L3)
 constexpr int NT = 256;
-constexpr unsigned FULL = 0xffffffffu;
 
 struct DecArgs {
     const float *w0, *b0, *w1, *b1, *w2, *b2, *w3, *b3;
@@ -45,6 +44,8 @@ struct DecArgs {
     uint8_t* sym_out;               // N,C,h,w
     float* act;                     // per image: [3 layers][2 channel slots][h+6][w+6][24]
     float* p9;                      // per image: [w+6][PROW]
+    uint32_t* words;                // per image: [words_img] zero padded big-endian copy of the stream
+    int words_img;
     const uint8_t* force_sym;       // debug: teacher forcing, no range decoding
     int64_t* freqs_out;             // debug: N,C,h,w,L tables as the decoder saw them
     long long* prof;                // debug (IC_PC_DECODE_PROF=1): cycle counters of image 0
@@ -58,9 +59,10 @@ struct Smem {
     float* w0;     // [13][24]
     float* b;      // b0[24] b1[24] b2[24] b3[8]
     float* cent;   // [8]
-    float* P;      // [w+6][PROW]  chains of the current row after taps 0..11
+    float* bc;     // [120] broadcast scratch of the decode warp, [128..139] CoderShared
+    float* P;      // [w+7][PROW]  chains of the current row after taps 0..11 (+ one spare row)
 };
-constexpr int SMEM_FIXED_FLOATS = 14 * 24 * 24 * 2 + 14 * 24 * 8 + 13 * 24 + PROW + 8;
+constexpr int SMEM_FIXED_FLOATS = 14 * 24 * 24 * 2 + 14 * 24 * 8 + 13 * 24 + PROW + 8 + 144;
 
 struct Geom {
     int C, h, w, H6, W6;
@@ -162,96 +164,122 @@ __device__ __forceinline__ void chains(const Geom& g, const Smem& sm, int tid, i
     chain_l0<FIRST>(g, sm, tid, nthr, c, y, syms, p9);
 }
 
-// ------------------------------------------------------------------ range decoder state
-// code/arithmetic_coding.py:163-222 with 32-bit state, kept uniform across the warp.
-// Bits past the end of the stream read as zero (:217-222).
+// ------------------------------------------------------------------ range decoder
+// code/arithmetic_coding.py:163-222 with 32-bit state.  Decoding a symbol has two halves and only
+// the first one sits between two symbols:
+//   find   (decode warp): value = ((code - low + 1) * total - 1) / range, symbol = last k with
+//          cum_k <= value (ArithmeticDecoder.read :181-197) -- one multiplication by 1/range;
+//   settle (coder warp):  ArithmeticCoderBase.update (:80-115) for that symbol -- two divisions by
+//          `total`, the shifts, the bit reads, the next 1/range -- while the decode warp already
+//          runs the network for the next position.
+// The two warps hand over through shared memory and two named barriers.
+struct CoderShared {
+    uint64_t range;          // high - low + 1
+    double inv_range;
+    uint32_t low, code;
+    uint32_t p_lo, p_hi, p_total;     // cumulative bounds of the symbol just found
+    uint32_t pad_;
+};
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+constexpr int BAR_FOUND = 1;      // decode warp -> coder warp: p_lo / p_hi / p_total are written
+constexpr int BAR_STATE = 2;      // coder warp -> decode warp: low / code / range / inv_range are written
+
+// floor(num / den) from a double estimate, |estimate - exact| < 1; den <= 2^32, num < 2^63
+__device__ __forceinline__ uint64_t div_fix(uint64_t num, uint64_t den, double inv_den) {
+    uint64_t q = __double2ull_rz(__ull2double_rz(num) * inv_den);
+    const int64_t r = (int64_t)(num - q * den);
+    q = r < 0 ? q - 1 : (r >= (int64_t)den ? q + 1 : q);
+    return q;
+}
+
+// The stream has been copied to a zero padded, word aligned scratch (big-endian words), so "bits
+// past the end read as zero" (:217-222) needs no test.
 struct Coder {
     uint32_t low, high, code;
-    const uint8_t* p;
-    int64_t n, pos;
-    uint64_t buf;        // next bits of the stream, MSB first
-    int avail;           // valid bits in buf
-    uint32_t nxt;        // prefetched word after buf
+    const uint32_t* words;   // padded stream as big-endian 32-bit words
+    int nwords, pos;         // pos: next word to load into nxt
+    uint64_t buf;            // next bits of the stream, MSB first
+    int avail;               // valid bits in buf
+    uint32_t nxt;            // prefetched word after buf
 
-    // big-endian 32-bit word at byte offset `at`
-    __device__ __forceinline__ uint32_t word(int64_t at) const {
-        if (at + 8 <= n) {
-            const uintptr_t q = (uintptr_t)(p + at);
-            const uint32_t* al = reinterpret_cast<const uint32_t*>(q & ~(uintptr_t)3);
-            const uint32_t le = __funnelshift_r(al[0], al[1], 8 * (unsigned)(q & 3));
-            return __byte_perm(le, 0, 0x0123);
-        }
-        uint32_t v = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v = (v << 8) | (at + i < n ? (uint32_t)p[at + i] : 0u);
-        return v;
-    }
-    __device__ __forceinline__ void init(const uint8_t* bytes, int64_t nbytes) {
-        p = bytes;
-        n = nbytes;
+    __device__ __forceinline__ void init(const uint32_t* w, int n) {
+        words = w;
+        nwords = n;
         low = 0;
         high = 0xffffffffu;
-        code = word(0);                 // ArithmeticDecoder.__init__ reads STATE_SIZE bits (:176-178)
-        buf = (uint64_t)word(4) << 32;
+        code = w[0];                    // ArithmeticDecoder.__init__ reads STATE_SIZE bits (:176-178)
+        buf = (uint64_t)w[1] << 32;
         avail = 32;
-        nxt = word(8);
-        pos = 12;
+        nxt = w[2];
+        pos = 3;
     }
-    // next k bits, 1 <= k <= 32
+    // next k bits, 0 <= k <= 32
     __device__ __forceinline__ uint32_t bits(int k) {
         if (avail < 32) {
             buf |= (uint64_t)nxt << (32 - avail);
             avail += 32;
-            nxt = word(pos);
-            pos += 4;
+            nxt = words[pos];
+            pos = min(pos + 1, nwords - 1);       // the last word of the scratch is zero
         }
-        const uint32_t v = (uint32_t)(buf >> (64 - k));
+        const uint32_t v = (uint32_t)((buf >> 32) >> (32 - k));
         buf <<= k;
         avail -= k;
         return v;
     }
-    // ArithmeticCoderBase.update (:80-115) with ArithmeticDecoder.shift / underflow (:204-213).
-    // The reference shifts one bit per loop iteration; both loops are closed forms here:
+    // The reference shifts one bit per loop iteration (:99-115, :204-213); both loops in closed form:
     //   loop 1 runs while the top bits of low and high agree   -> clz(low ^ high) iterations
     //   loop 2 runs while low = 01..., high = 10...            -> leading ones of ((low & ~high) << 1)
-    __device__ __forceinline__ void narrow(uint32_t lo_b, uint64_t hi_b) {
-        uint32_t nl = low + lo_b;
+    __device__ __forceinline__ void settle(uint32_t p_lo, uint32_t p_hi, uint32_t p_total) {
+        const uint64_t range = (uint64_t)high - low + 1;
+        const double inv_t = __drcp_rn((double)p_total);
+        const uint64_t lo_b = div_fix((uint64_t)p_lo * range, p_total, inv_t);
+        const uint64_t hi_b = p_hi == p_total ? range : div_fix((uint64_t)p_hi * range, p_total, inv_t);
+        uint32_t nl = low + (uint32_t)lo_b;
         uint32_t nh = (uint32_t)((uint64_t)low + hi_b - 1);
-        const int k = __clz((int)(nl ^ nh));
-        if (k == 32) {
-            nl = 0;
-            nh = 0xffffffffu;
-            code = bits(32);
-        } else if (k > 0) {
-            nl <<= k;
-            nh = (nh << k) | ((1u << k) - 1);
-            code = (code << k) | bits(k);
+        const int k = __clz((int)(nl ^ nh));                               // 0..32
+        code = (uint32_t)((uint64_t)code << k) | bits(k);
+        nl = (uint32_t)((uint64_t)nl << k);
+        nh = (uint32_t)(((uint64_t)nh << k) | ((1ull << k) - 1));
+        const int m = __clz((int)~((nl & ~nh) << 1));                      // 0..31
+        code = (code & 0x80000000u) | ((code << m) & 0x7fffffffu) | bits(m);
+        low = (nl << m) & 0x7fffffffu;
+        high = ((nh << m) & 0x7fffffffu) | 0x80000000u | ((1u << m) - 1);
+    }
+    __device__ __forceinline__ void publish(CoderShared* cs, int lane) const {
+        if (lane == 0) {
+            const uint64_t range = (uint64_t)high - low + 1;
+            cs->range = range;
+            cs->inv_range = __drcp_rn((double)range);
+            cs->low = low;
+            cs->code = code;
         }
-        const int m = __clz((int)~((nl & ~nh) << 1));
-        if (m > 0) {
-            nl = (nl << m) & 0x7fffffffu;
-            nh = ((nh << m) & 0x7fffffffu) | 0x80000000u | ((1u << m) - 1);
-            code = (code & 0x80000000u) | ((code << m) & 0x7fffffffu) | bits(m);
-        }
-        low = nl;
-        high = nh;
     }
 };
 
-// floor(cum * range / total) for cum <= total < 2^31, range <= 2^32: double estimate + exact fix-up
-__device__ __forceinline__ uint64_t scale_bound(uint32_t cum, uint64_t range, uint32_t total, double inv_total) {
-    const uint64_t A = (uint64_t)cum * range;                       // < 2^63
-    uint64_t q = (uint64_t)__double2ull_rz(__ull2double_rz(A) * inv_total);
-    const int64_t r = (int64_t)(A - q * total);                      // |estimate - exact| < 1
-    if (r < 0) --q;
-    else if (r >= (int64_t)total) ++q;
-    return q;
+// coder warp: one settle per decoded symbol of row (c, y)
+__device__ __forceinline__ void coder_row(const Geom& g, int lane, int c, int y, Coder& cd, CoderShared* cs) {
+    if (!row_has(g, 3, c, y)) return;
+    const size_t vol = (size_t)g.C * g.h * g.w;
+    for (int x = 0; x < g.w; ++x) {
+        const size_t at = ((size_t)c * g.h + y) * g.w + x;
+        if (at == 0) continue;                    // side information, never coded
+        bar_sync(BAR_FOUND);
+        cd.settle(cs->p_lo, cs->p_hi, cs->p_total);
+        if (at + 1 < vol) {
+            cd.publish(cs, lane);
+            bar_arrive(BAR_STATE);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ one row, symbol by symbol (warp 0)
+// Broadcasts go through shared memory: a lone warp issues one SHFL per 8 cycles (tools/ubench), a
+// 24-vector by shuffles costs twice the fmaf chain it feeds.
 template <int L>
-__device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int lane, int c, int y, Coder& cd,
-                                           uint8_t* sym_img, const uint8_t* force_img, float* act_img, int64_t* freqs_img,
+__device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const DecArgs& a, int lane, int c, int y,
+                                           CoderShared* cs, uint8_t* sym_img, const uint8_t* force_img, float* act_img, int64_t* freqs_img,
                                            int first_sym, long long* lp) {
     const int j = lane < KC ? lane : KC - 1;      // lanes 24..31 shadow lane 23; their stores are masked
     const int j3 = lane & 7;
@@ -267,12 +295,16 @@ __device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const 
     }
     const float w0l = sm.w0[12 * 24 + j];
     const float b0 = sm.b[j], b1 = sm.b[24 + j], b2 = sm.b[48 + j], b3 = sm.b[72 + j3];
-    const float pad = sm.cent[0];
+    float cent[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) cent[l] = sm.cent[l];
+    const float pad = cent[0];
     const bool r1 = row_has(g, 1, c, y), r2 = row_has(g, 2, c, y), r3 = row_has(g, 3, c, y);
     float* a0row = act_row(act_img, g, 0, c, y) + lane;
     float* a1row = act_row(act_img, g, 1, c, y) + lane;
     float* a2row = act_row(act_img, g, 2, c, y) + lane;
     const float* P = sm.P;
+    float* bc = sm.bc;                            // [3][32] layer outputs, [3][8] head rounds (then CoderShared)
     const bool prof = lp != nullptr;
 
     float vleft = pad;                            // input at (c, y, -4)
@@ -281,32 +313,50 @@ __device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const 
     for (int xi = 0; xi < g.W6; ++xi) {
         const int x = xi - 3;
         const long long t0 = prof ? clock64() : 0;
-        // chains of the next position after taps 0..11 (the last iteration reads one row past: P has a spare row)
+        // chains of the next position after taps 0..11 (the last iteration reads the spare row of P)
         const float* Pn = P + (size_t)(xi + 1) * PROW;
         float n1 = Pn[24 + j], n2 = Pn[48 + j], n3 = Pn[72 + j3];
         const float p0n = Pn[j];
         // layer 0: tap 12 (left input), bias, ReLU
         const float a0 = fmaxf(__fadd_rn(fmaf(vleft, w0l, p0), b0), 0.f);
+        bc[lane] = a0;
+        __syncwarp();
         // layer 1: tap 13 of this position, tap 12 of the next one
 #pragma unroll
-        for (int i = 0; i < KC; ++i) {
-            const float ai = __shfl_sync(FULL, a0, i);
-            acc1 = fmaf(ai, W1c[i], acc1);
-            n1 = fmaf(ai, W1l[i], n1);
+        for (int i4 = 0; i4 < KC / 4; ++i4) {
+            const float4 v = reinterpret_cast<const float4*>(bc)[i4];
+            const float ai[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc1 = fmaf(ai[u], W1c[i4 * 4 + u], acc1);
+                n1 = fmaf(ai[u], W1l[i4 * 4 + u], n1);
+            }
         }
         const float a1 = fmaxf(__fadd_rn(acc1, b1), 0.f);
+        bc[32 + lane] = a1;
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < KC; ++i) {
-            const float ai = __shfl_sync(FULL, a1, i);
-            acc2 = fmaf(ai, W2c[i], acc2);
-            n2 = fmaf(ai, W2l[i], n2);
+        for (int i4 = 0; i4 < KC / 4; ++i4) {
+            const float4 v = reinterpret_cast<const float4*>(bc + 32)[i4];
+            const float ai[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc2 = fmaf(ai[u], W2c[i4 * 4 + u], acc2);
+                n2 = fmaf(ai[u], W2l[i4 * 4 + u], n2);
+            }
         }
         const float a2 = __fadd_rn(__fadd_rn(acc2, b2), a0);      // + residual (code/probclass.py:196)
+        bc[64 + lane] = a2;
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < KC; ++i) {
-            const float ai = __shfl_sync(FULL, a2, i);
-            acc3 = fmaf(ai, W3c[i], acc3);
-            n3 = fmaf(ai, W3l[i], n3);
+        for (int i4 = 0; i4 < KC / 4; ++i4) {
+            const float4 v = reinterpret_cast<const float4*>(bc + 64)[i4];
+            const float ai[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc3 = fmaf(ai[u], W3c[i4 * 4 + u], acc3);
+                n3 = fmaf(ai[u], W3l[i4 * 4 + u], n3);
+            }
         }
         const float lg = fmaxf(__fadd_rn(acc3, b3), 0.f);         // ReLU on the logits (code/probclass.py:220,233)
         if (lane < KC) {
@@ -317,34 +367,39 @@ __device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const 
         const long long t1 = prof ? clock64() : 0;
         float vnew = pad;
         if (r3 && x >= 0 && x < g.w) {
-            // softmax -> int64(pr * 1e9) -> max(., 1): same operation order as pc_final_kernel<HEAD_FREQS>
-            float lv[L];
-#pragma unroll
-            for (int l = 0; l < L; ++l) lv[l] = __shfl_sync(FULL, lg, l);
+            // softmax -> int64(pr * 1e9) -> max(., 1): same operation order as pc_final_kernel<HEAD_FREQS>.
+            // lane l < 8 owns logit l (lanes 8..31 repeat them); three broadcast rounds
+            float* hb = bc + 96;
+            if (lane < 8) hb[lane] = lg;
+            __syncwarp();
+            float lv[8];
+            *reinterpret_cast<float4*>(lv) = reinterpret_cast<const float4*>(hb)[0];
+            *reinterpret_cast<float4*>(lv + 4) = reinterpret_cast<const float4*>(hb)[1];
             float m = lv[0];
 #pragma unroll
             for (int l = 1; l < L; ++l) m = fmaxf(m, lv[l]);
             const float e = expf(__fsub_rn(lg, m));
-            float ev[L];
-#pragma unroll
-            for (int l = 0; l < L; ++l) ev[l] = __shfl_sync(FULL, e, l);
+            if (lane < 8) hb[8 + lane] = e;
+            __syncwarp();
+            float ev[8];
+            *reinterpret_cast<float4*>(ev) = reinterpret_cast<const float4*>(hb + 8)[0];
+            *reinterpret_cast<float4*>(ev + 4) = reinterpret_cast<const float4*>(hb + 8)[1];
             float s = 0.f;
 #pragma unroll
             for (int l = 0; l < L; ++l) s = __fadd_rn(s, ev[l]);
-            // lane l < L: its own table entry (one IEEE division per lane, in parallel); then every lane
-            // gathers the table: lane k keeps the lower bound of symbol k (k = L: the total)
             long long f = (long long)__fmul_rn(__fdiv_rn(e, s), 1e9f);
             if (f < 1) f = 1;
-            const uint32_t fown = lane < L ? (uint32_t)f : 0u;
-            uint32_t fv[L];
+            const uint32_t fown = (uint32_t)f;
+            if (lane < 8) reinterpret_cast<uint32_t*>(hb)[16 + lane] = fown;
+            __syncwarp();
+            uint32_t fv[8];
+            *reinterpret_cast<uint4*>(fv) = reinterpret_cast<const uint4*>(hb + 16)[0];
+            *reinterpret_cast<uint4*>(fv + 4) = reinterpret_cast<const uint4*>(hb + 16)[1];
+            uint32_t cums[L + 1];             // cums[k] = sum of f_l, l < k
+            cums[0] = 0;
 #pragma unroll
-            for (int l = 0; l < L; ++l) fv[l] = __shfl_sync(FULL, fown, l);
-            uint32_t cum = 0, total = 0;
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                if (l < lane) cum += fv[l];
-                total += fv[l];
-            }
+            for (int l = 0; l < L; ++l) cums[l + 1] = cums[l] + fv[l];
+            const uint32_t total = cums[L];
             const long long t2 = prof ? clock64() : 0;
             const size_t at = ((size_t)c * g.h + y) * g.w + x;
             if (freqs_img && lane < L) freqs_img[at * L + lane] = (int64_t)fown;
@@ -354,19 +409,30 @@ __device__ __forceinline__ void decode_row(const Geom& g, const Smem& sm, const 
             } else if (at == 0) {
                 sym = first_sym;
             } else {
-                // ArithmeticDecoder.read (:181-201): lane k holds the lower bound of symbol k in the current range
-                const uint64_t range = (uint64_t)cd.high - cd.low + 1;
-                const uint32_t offset = cd.code - cd.low;
-                const uint64_t bound = scale_bound(cum, range, total, __drcp_rn((double)total));
-                const unsigned le = __ballot_sync(FULL, lane <= L && bound <= (uint64_t)offset);
-                sym = __popc(le) - 1;
-                if (sym > L - 1) sym = L - 1;     // corrupt stream: stay inside the table
-                const uint32_t lo_b = __shfl_sync(FULL, (uint32_t)bound, sym);
-                const uint32_t hi32 = __shfl_sync(FULL, (uint32_t)bound, sym + 1);
-                cd.narrow(lo_b, sym + 1 == L ? range : (uint64_t)hi32);
+                // ArithmeticDecoder.read (:181-197); the coder warp has applied the previous symbol
+                bar_sync(BAR_STATE);
+                const uint64_t range = cs->range;
+                const uint64_t num = ((uint64_t)(cs->code - cs->low) + 1) * total - 1;
+                const uint64_t value = div_fix(num, range, cs->inv_range);
+                sym = 0;
+#pragma unroll
+                for (int l = 1; l < L; ++l) sym += (uint64_t)cums[l] <= value ? 1 : 0;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    lo = l == sym ? cums[l] : lo;
+                    hi = l == sym ? cums[l + 1] : hi;
+                }
+                if (lane == 0) {
+                    cs->p_lo = lo;
+                    cs->p_hi = hi;
+                    cs->p_total = total;
+                }
+                bar_arrive(BAR_FOUND);
             }
             if (lane == 0) sym_img[at] = (uint8_t)sym;
-            vnew = sm.cent[sym];
+#pragma unroll
+            for (int l = 0; l < L; ++l) vnew = l == sym ? cent[l] : vnew;
             if (prof) {
                 lp[1] += t2 - t1;
                 lp[2] += clock64() - t2;
@@ -391,7 +457,8 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
     sm.w0 = sm.w3 + 14 * 24 * 8;
     sm.b = sm.w0 + 13 * 24;
     sm.cent = sm.b + PROW;
-    sm.P = sm.cent + 8;
+    sm.bc = sm.cent + 8;
+    sm.P = sm.bc + 144;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 14 * 24 * 24; i += NT) {
         sm.w1[i] = a.w1[i];
@@ -425,8 +492,28 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
     float* act_img = a.act + (size_t)n * 3 * g.layer;
     float* p9 = a.p9 + (size_t)n * g.W6 * PROW;
     int64_t* freqs_img = a.freqs_out ? a.freqs_out + n * vol * L : nullptr;
+    // stream -> word aligned, zero padded scratch (the coder never tests for the end of the stream)
+    const int64_t nbytes = a.stream_off[n + 1] - a.stream_off[n];
+    const int nwords = (int)min((int64_t)a.words_img, (nbytes + 3) / 4 + 8);
+    {
+        const uint8_t* sp = a.stream + a.stream_off[n];
+        uint32_t* wd = a.words + (size_t)n * a.words_img;
+        for (int i = tid; i < nwords; i += NT) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v = (v << 8) | ((int64_t)i * 4 + k < nbytes ? (uint32_t)sp[(int64_t)i * 4 + k] : 0u);
+            wd[i] = v;
+        }
+    }
+    __syncthreads();
+    CoderShared* cs = reinterpret_cast<CoderShared*>(sm.bc + 128);
     Coder cd;
-    cd.init(a.stream + a.stream_off[n], a.stream_off[n + 1] - a.stream_off[n]);
+    cd.init(a.words + (size_t)n * a.words_img, nwords);
+    const bool coding = !a.force_sym && vol > 1;       // at least one symbol goes through the range decoder
+    if (warp == 1 && coding) {
+        cd.publish(cs, lane);
+        bar_arrive(BAR_STATE);
+    }
     const int first_sym = a.first_sym[n];
 
     const bool prof = a.prof && n == 0 && tid == 0;
@@ -447,9 +534,11 @@ __global__ void __launch_bounds__(NT, 1) pc_seq_decode_kernel(const DecArgs a) {
         __syncthreads();
         const long long tc = prof ? clock64() : 0;
         if (warp == 0)
-            decode_row<L>(g, sm, a, lane, c, y, cd, sym_img, force_img, act_img, freqs_img, first_sym, lp);
-        else if (y + 1 <= a.h + 2)
-            chains<true>(g, sm, tid - 32, NT - 32, c, y + 1, syms, act_img, p9);
+            decode_row<L>(g, sm, a, lane, c, y, cs, sym_img, force_img, act_img, freqs_img, first_sym, lp);
+        else if (warp == 1) {
+            if (coding) coder_row(g, lane, c, y, cd, cs);
+        } else if (y + 1 <= a.h + 2)
+            chains<true>(g, sm, tid - 64, NT - 64, c, y + 1, syms, act_img, p9);
         if (prof) {
             rows[0] += tb - ta;               // waiting for the helper warps
             rows[1] += tc - tb;               // chains at row start
@@ -473,10 +562,14 @@ int launch_decode(const DecArgs& a, int N, size_t smem, cudaStream_t s) {
 
 }  // namespace
 
+// a range coder with total <= 2^30 + 2 spends at most ~30 bits on a symbol: 4 bytes per symbol + slack
+static int stream_words(int C, int h, int w) { return C * h * w + 16; }
+
 size_t pc_decode_workspace_bytes(int N, int C, int h, int w) {
     const size_t act = (size_t)3 * 2 * (h + 6) * (w + 6) * KC * sizeof(float);
     const size_t p9 = (size_t)(w + 6) * PROW * sizeof(float);
-    return (size_t)N * (align_up(act, 256) + align_up(p9, 256)) + 1024;
+    const size_t words = (size_t)stream_words(C, h, w) * sizeof(uint32_t);
+    return (size_t)N * (align_up(act, 256) + align_up(p9, 256) + align_up(words, 256)) + 1024;
 }
 
 int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_bytes, cudaStream_t s) {
@@ -489,6 +582,8 @@ int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_b
     const size_t act_img = (size_t)3 * 2 * (in.h + 6) * (in.w + 6) * KC;
     float* act = ar.get<float>((size_t)in.N * act_img);
     float* p9 = ar.get<float>((size_t)in.N * (in.w + 6) * PROW);
+    const int words_img = stream_words(in.C, in.h, in.w);
+    uint32_t* words = ar.get<uint32_t>((size_t)in.N * words_img);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "pc_decode workspace too small: need %zu, have %zu", ar.off, ws_bytes);
     DecArgs a;
     a.w0 = w.w0; a.b0 = w.b0; a.w1 = w.w1; a.b1 = w.b1; a.w2 = w.w2; a.b2 = w.b2; a.w3 = w.w3; a.b3 = w.b3;
@@ -500,6 +595,8 @@ int pc_decode(const PcWeights& w, const PcDecodeInput& in, void* ws, size_t ws_b
     a.sym_out = in.sym_out;
     a.act = act;
     a.p9 = p9;
+    a.words = words;
+    a.words_img = words_img;
     a.force_sym = in.force_sym;
     a.freqs_out = in.freqs_out;
     a.prof = nullptr;

@@ -102,7 +102,58 @@ __global__ void k(long long* out, float fa, double da, unsigned ua) {
     }
     t1 = clock64();
     if (lane == 0) out[11] = t1 - t0;
-    if (x + a + b + w + acc + d + q + g + e + h + r + u + m == 12345.678) out[15] = 1;
+    // 13. eight independent FFMA chains (issue rate of one warp)
+    float c0 = fa, c1 = fa + 1, c2 = fa + 2, c3 = fa + 3, c4 = fa + 4, c5 = fa + 5, c6 = fa + 6, c7 = fa + 7;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        c0 = fmaf(c0, fa, 1.f); c1 = fmaf(c1, fa, 1.f); c2 = fmaf(c2, fa, 1.f); c3 = fmaf(c3, fa, 1.f);
+        c4 = fmaf(c4, fa, 1.f); c5 = fmaf(c5, fa, 1.f); c6 = fmaf(c6, fa, 1.f); c7 = fmaf(c7, fa, 1.f);
+    }
+    t1 = clock64();
+    if (lane == 0) out[12] = (t1 - t0) / 8;
+    // 14. independent broadcast LDS.128 (issue interval)
+    __shared__ float4 sh4[64];
+    sh4[lane] = make_float4(x, a, b, w);
+    __syncwarp();
+    float s4 = 0;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        float4 v4 = sh4[i & 31];
+        s4 += v4.x + v4.w;
+    }
+    t1 = clock64();
+    if (lane == 0) out[13] = t1 - t0;
+    // 15. u64 multiply chain
+    unsigned long long mm = u | 1;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) mm = mm * (ua | 3) + 7;
+    t1 = clock64();
+    if (lane == 0) out[14] = t1 - t0;
+    if (x + a + b + w + acc + d + q + g + e + h + r + u + m + c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7 + s4 + mm == 12345.678) out[15] = 1;
+}
+
+// two warps ping-pong through named barriers (the decode / coder hand-over)
+__global__ void pingpong(long long* out) {
+    const int warp = threadIdx.x >> 5;
+    __shared__ volatile int box[2];
+    long long t0 = clock64();
+    if (warp == 0) {
+        for (int i = 0; i < N; ++i) {
+            box[0] = i;
+            asm volatile("bar.arrive 1, 64;" ::: "memory");
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+        }
+    } else {
+        for (int i = 0; i < N; ++i) {
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            box[1] = box[0];
+            asm volatile("bar.arrive 2, 64;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) out[0] = clock64() - t0;
 }
 
 int main() {
@@ -112,10 +163,15 @@ int main() {
     k<<<1, 32>>>(d, 1.0001f, 1.0000001, 12345u);
     long long h[16];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    pingpong<<<1, 64>>>(d);
+    long long pp = 0;
+    cudaMemcpy(&pp, d, sizeof(pp), cudaMemcpyDeviceToHost);
     const char* names[] = {"dependent FFMA", "SHFL + 2 FFMA chains (per step)", "dependent SHFL", "independent SHFL (+FADD)",
                            "dependent DFMA", "u64->f64, DMUL, f64->u64, +1", "f32->s64->f32", "expf, -1", "__fdiv_rn, +2",
-                           "__drcp_rn, +2", "u64 / u32 division, +c", "STS, syncwarp, LDS, syncwarp"};
-    for (int i = 0; i < 12; ++i) printf("%-36s %7.1f cycles/iter\n", names[i], (double)h[i] / N);
+                           "__drcp_rn, +2", "u64 / u32 division, +c", "STS, syncwarp, LDS, syncwarp", "independent FFMA (issue interval)",
+                           "independent broadcast LDS.128 (+2 FADD)", "u64 multiply-add chain"};
+    for (int i = 0; i < 15; ++i) printf("%-36s %7.1f cycles/iter\n", names[i], (double)h[i] / N);
+    printf("%-36s %7.1f cycles/iter\n", "named-barrier round trip, 2 warps", (double)pp / N);
     printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
