@@ -112,6 +112,33 @@ def validate(images_u8, ae, pc, real_bpp=False, batch_size=8, dist=None):
     return avgs, n, rows
 
 
+class MeasuresWriter(object):
+    """val_files.MeasuresWriter (code/val_files.py:62-77): out_dir/measures.csv, one row per image."""
+
+    def __init__(self, out_dir):
+        import os
+        os.makedirs(out_dir, exist_ok=True)
+        self.fout = open(os.path.join(out_dir, 'measures.csv'), 'w')
+        self.fout.write('img_name,bpp,ms-ssim,psnr\n')
+
+    def append(self, img_name, otp):
+        self.fout.write('{},{},{},{}\n'.format(img_name, otp['bpp'], otp['ms-ssim'], otp['psnr']))
+
+    def close(self):
+        self.fout.close()
+
+
+def load_images(pattern):
+    """images_iterator.ImagesIterator's file side (code/images_iterator.py:20-37): sorted glob, RGB uint8 HWC,
+    names without extension."""
+    import glob
+    import os
+    from PIL import Image
+    paths = sorted(glob.glob(pattern))
+    assert paths, 'no images match {}'.format(pattern)
+    return [np.asarray(Image.open(p).convert('RGB')) for p in paths], [os.path.splitext(os.path.basename(p))[0] for p in paths]
+
+
 def main():
     import argparse
     import os
@@ -126,17 +153,32 @@ def main():
     ap.add_argument('--width', type=int, default=768)
     ap.add_argument('--mode', default='exact', choices=['fp32', 'exact', 'fast'])
     ap.add_argument('--real_bpp', action='store_true')
+    ap.add_argument('--images', default=None, help='glob of image files instead of synthetic images')
+    ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array (default: seeded synthetic weights)')
+    ap.add_argument('--out_dir', default=None, help='write measures.csv here (rank 0 writes its own shard only)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     if world > 1:
         dist.init_process_group('nccl')
     a, p = config.ae_config(args.ae_config), config.pc_config(args.pc_config)
-    W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
+    W = dict(np.load(args.weights)) if args.weights else weights.synthetic_weights(
+        a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
     ae = autoencoder.get_network_cls(a)(a, weights=W, mode=args.mode)
     pc = probclass.get_network_cls(p)(p, num_centers=a.num_centers, weights=W)
-    imgs = list(weights.synthetic_images(args.synthetic, args.height, args.width))
-    avgs, n, _ = validate(imgs, ae, pc, args.real_bpp, dist=dist if world > 1 else None)
+    if args.images:
+        imgs, names = load_images(args.images)
+    else:
+        imgs = list(weights.synthetic_images(args.synthetic, args.height, args.width))
+        names = ['synthetic_%04d' % i for i in range(len(imgs))]
+    avgs, n, rows = validate(imgs, ae, pc, args.real_bpp, dist=dist if world > 1 else None)
+    if args.out_dir:
+        rank = int(os.environ.get('RANK', '0'))
+        lo, hi = shard_range(len(imgs), rank, world)
+        wr = MeasuresWriter(args.out_dir if world == 1 else os.path.join(args.out_dir, 'rank%d' % rank))
+        for name, row in zip(names[lo:hi], rows):
+            wr.append(name, row)
+        wr.close()
     if int(os.environ.get('RANK', '0')) == 0:
         print('%d images | Mean: %s' % (n, ', '.join('{}: {:.4f}'.format(k, avgs[k]) for k in METRICS)))
     if world > 1:

@@ -67,3 +67,15 @@ def test_two_rank_metric_reduce(n_items):
 def test_nan_metric_is_rejected():
     with pytest.raises(AssertionError):
         val.reduce_metric_sums([{'bpp': float('nan'), 'ms-ssim': 1.0, 'psnr': 30.0}])
+
+
+def test_measures_writer_format(tmp_path):
+    """measures.csv as the reference's MeasuresWriter / MeasuresReader exchange it (code/val_files.py:62-100)"""
+    from imgcomp_cvpr_b200 import val
+    w = val.MeasuresWriter(str(tmp_path))
+    w.append('kodim01', {'bpp': 0.25, 'ms-ssim': 0.97, 'psnr': 30.5})
+    w.close()
+    lines = open(str(tmp_path / 'measures.csv')).read().splitlines()
+    assert lines[0] == 'img_name,bpp,ms-ssim,psnr'
+    name, bpp, ms, ps = lines[1].split(',')
+    assert name == 'kodim01' and float(bpp) == 0.25 and float(ms) == 0.97 and float(ps) == 30.5
