@@ -83,3 +83,46 @@ def test_float64_truth_agrees_with_float32_oracle(synth):
     assert (r32['enc']['symbols'][safe] == r64['enc']['symbols'][safe]).all()
     np.testing.assert_allclose(r32['bpp'], r64['bpp'], atol=1e-4)
     np.testing.assert_allclose(r32['ms_ssim'], r64['ms_ssim'], atol=1e-4)
+
+
+def test_training_oracle_in_inference_mode_matches_golden(synth):
+    """oracle/train_oracle.py (torch autograd restatement of the training graph), with batch norm put in
+    inference mode, must reproduce the reference-run val graph: same symbols, bit cost, reconstruction."""
+    import torch
+    from oracle import train_oracle as T
+    ae_cfg, pc_cfg, W = synth('cvpr/low')
+    g = load_golden('tiny_low_1x64x64')
+    P = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in W.items()}
+    x = torch.tensor(g['x_u8'].astype(np.float64))
+    enc = T.encode(x, P, ae_cfg.arch_param_B, False, {})
+    x_out = T.decode(enc['qhard'], P, ae_cfg.arch_param_B, False, {})
+    bc, _ = T.pc_bitcost(enc['qbar'], enc['symbols'], P, float(W['autoencoder/encoder/centers'][0]))
+    assert np.array_equal(enc['symbols'].numpy(), g['symbols'])
+    np.testing.assert_allclose(enc['z'].numpy(), g['z'], atol=5e-5)
+    np.testing.assert_allclose(bc.numpy(), g['bitcost'], atol=2e-4)
+    np.testing.assert_allclose(x_out.numpy(), g['x_out'], atol=2e-3)
+    if 'ms_ssim_tf' in g:
+        v = T.ms_ssim_tf(x, torch.tensor(g['x_out'].astype(np.float64)))
+        np.testing.assert_allclose(float(v), float(g['ms_ssim_tf']), rtol=2e-5)
+
+
+def test_training_oracle_gradients_are_consistent(synth):
+    """finite differences on a few parameters of a tiny training step (float64)"""
+    import copy
+    from oracle import train_oracle as T
+    from imgcomp_cvpr_b200 import weights as wm
+    ae_cfg, pc_cfg, W = synth('cvpr/low')
+    x = wm.synthetic_images(2, 32, 32, seed=11).astype(np.float64)
+    r = T.training_step(x, W, ae_cfg, pc_cfg)
+    assert np.isfinite(r['total_loss'])
+    rng = np.random.RandomState(0)
+    for name in ['autoencoder/decoder/h13/weights', 'autoencoder/decoder/h13/BatchNorm/beta',
+                 'probclass3d/logits/conv3d_conv2_mask/biases']:
+        g = r['grads'][name]
+        idx = tuple(rng.randint(0, s) for s in g.shape)
+        eps = 1e-6
+        Wp, Wm = copy.copy(W), copy.copy(W)
+        Wp[name] = W[name].astype(np.float64).copy(); Wp[name][idx] += eps
+        Wm[name] = W[name].astype(np.float64).copy(); Wm[name][idx] -= eps
+        fd = (T.training_step(x, Wp, ae_cfg, pc_cfg)['total_loss'] - T.training_step(x, Wm, ae_cfg, pc_cfg)['total_loss']) / (2 * eps)
+        assert abs(fd - g[idx]) <= 2e-4 * max(1.0, abs(fd)), (name, fd, g[idx])
