@@ -65,6 +65,26 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_pc_context_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_conv2d_workspace_bytes': (c_size_t, [c_int] * 10),
+    'ic_nn_conv2d_fwd': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p]),
+    'ic_nn_conv2d_bwd_data': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_conv2d_bwd_filter': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_bn_workspace_bytes': (c_size_t, [c_int64, c_int]),
+    'ic_nn_bn_train_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_bn_train_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_hq_workspace_bytes': (c_size_t, [c_int64]),
+    'ic_nn_hq_bwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_denorm_clip_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ic_nn_denorm_clip_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ic_nn_nhwc_to_nchw': (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    'ic_nn_nchw_to_nhwc': (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    'ic_nn_axpby': (c_int, [c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_void_p]),
+    'ic_nn_mul': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'ic_nn_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
+                                c_float, c_void_p, c_void_p]),
     'ic_msssim_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'ic_msssim_tf_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_np_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -1,0 +1,729 @@
+// Training-step primitives (float32 FFMA): what tf.gradients + the two Adam optimisers of
+// code/train.py:339-349 execute for the graph of code/train.py:86-132, restated as explicit
+// forward / backward kernels.  Activations are NHWC float32 (channel counts padded to a
+// multiple of 4), convolution weights [KH][KW][Cin][Cout] in the orientation of the op.
+//
+//   convolution      forward: conv_simt.cu (scale 1, shift 0); backward-data: the same kernel in
+//                    the other mode over per-tap transposed weights; backward-filter: implicit
+//                    GEMM dW = A^T dY with a split reduction over the output pixels
+//   batch norm       slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125, A.1):
+//                    batch mean / biased variance, moving averages with the unbiased variance
+//   heatmap+quantize backward of _get_heatmap3D, _mask_with_heatmap, qsoft (autoencoder.py:171-200,
+//                    quantizer.py:60-100); qbar = qsoft + stop_gradient(qhard - qsoft)
+//   Adam             tf.train.AdamOptimizer._apply_dense
+// All reductions are fixed-order (partials + a finalize kernel), no float atomics.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ic {
+
+namespace {
+
+// ------------------------------------------------------------------ small helpers
+float* g_ones = nullptr;
+float* g_zeros = nullptr;
+constexpr int kConstLen = 1024;
+
+int ensure_consts() {
+    if (g_ones) return IC_OK;
+    float h[kConstLen];
+    for (int i = 0; i < kConstLen; ++i) h[i] = 1.f;
+    IC_CHECK_CUDA(cudaMalloc((void**)&g_ones, sizeof(h)));
+    IC_CHECK_CUDA(cudaMemcpy(g_ones, h, sizeof(h), cudaMemcpyHostToDevice));
+    IC_CHECK_CUDA(cudaMalloc((void**)&g_zeros, sizeof(h)));
+    IC_CHECK_CUDA(cudaMemset(g_zeros, 0, sizeof(h)));
+    return IC_OK;
+}
+
+struct Geo {
+    int N, Hi, Wi, Cin, KH, KW, stride, Cout, transposed, valid;
+    int Ho, Wo, pad_t, pad_l;
+};
+
+// SAME (TF, A.2) or VALID geometry of the op
+int make_geo(Geo& g) {
+    IC_REQUIRE(g.N > 0 && g.Hi > 0 && g.Wi > 0 && g.Cin > 0 && g.Cout > 0 && g.KH > 0 && g.KW > 0 && g.stride > 0,
+               IC_ERR_INVALID, "nn conv: bad geometry");
+    IC_REQUIRE(g.Cin % 4 == 0 && g.Cout % 4 == 0, IC_ERR_INVALID, "nn conv: Cin (%d) and Cout (%d) must be multiples of 4", g.Cin,
+               g.Cout);
+    IC_REQUIRE(g.Cout <= kConstLen && g.Cin <= kConstLen, IC_ERR_UNSUPPORTED, "nn conv: more than %d channels", kConstLen);
+    if (g.valid) {
+        IC_REQUIRE(!g.transposed && g.Hi >= g.KH && g.Wi >= g.KW, IC_ERR_INVALID, "nn conv: VALID needs input >= kernel");
+        g.Ho = (g.Hi - g.KH) / g.stride + 1;
+        g.Wo = (g.Wi - g.KW) / g.stride + 1;
+        g.pad_t = g.pad_l = 0;
+    } else if (!g.transposed) {
+        g.Ho = (g.Hi + g.stride - 1) / g.stride;
+        g.Wo = (g.Wi + g.stride - 1) / g.stride;
+        g.pad_t = same_pad_before(g.Hi, g.KH, g.stride);
+        g.pad_l = same_pad_before(g.Wi, g.KW, g.stride);
+    } else {
+        g.Ho = g.Hi * g.stride;
+        g.Wo = g.Wi * g.stride;
+        g.pad_t = same_pad_before(g.Ho, g.KH, g.stride);     // of the forward conv this op is the gradient of
+        g.pad_l = same_pad_before(g.Wo, g.KW, g.stride);
+    }
+    return IC_OK;
+}
+
+__global__ void transpose_taps_kernel(const float* __restrict__ w, float* __restrict__ wT, int taps, int Cin, int Cout) {
+    const int64_t total = (int64_t)taps * Cin * Cout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i / ((int64_t)Cin * Cout));
+        const int r = (int)(i - (int64_t)tap * Cin * Cout);
+        const int ci = r / Cout, co = r - ci * Cout;
+        wT[((int64_t)tap * Cout + co) * Cin + ci] = w[i];
+    }
+}
+
+// ------------------------------------------------------------------ backward filter
+// dW[k][co] = sum_m A[m][k] * dY[m][co]; A = the im2col gather of the forward op (same index
+// arithmetic as conv_simt.cu's load_a), m over the N*Ho*Wo output pixels.
+struct WgradDesc {
+    const float* x;
+    const float* dy;
+    float* part;           // [splits][K][Cout]
+    Geo g;
+    int64_t M;
+    int64_t m_per_split;
+};
+
+constexpr int WT = 64, WM = 16;
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradDesc d) {
+    __shared__ __align__(16) float As[WM][WT + 4];
+    __shared__ __align__(16) float Bs[WM][WT + 4];
+    const Geo& g = d.g;
+    const int t = threadIdx.x;
+    const int K = g.KH * g.KW * g.Cin;
+    const int k0 = blockIdx.x * WT, n0 = blockIdx.y * WT;
+    const int64_t m_begin = (int64_t)blockIdx.z * d.m_per_split;
+    const int64_t m_end = min(d.M, m_begin + d.m_per_split);
+    const int lm = t >> 4, l4 = (t & 15) * 4;
+    // this thread's 4 consecutive k (same tap: Cin % 4 == 0)
+    const int k = k0 + l4;
+    const bool kvalid = k < K;
+    int ky = 0, kx = 0, ci = 0;
+    if (kvalid) {
+        const int tap = k / g.Cin;
+        ci = k - tap * g.Cin;
+        ky = tap / g.KW;
+        kx = tap - ky * g.KW;
+    }
+    const bool nvalid = n0 + l4 < g.Cout;
+    const int tx = t & 15, ty = t >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int64_t hw = (int64_t)g.Ho * g.Wo;
+    for (int64_t mb = m_begin; mb < m_end; mb += WM) {
+        const int64_t m = mb + lm;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < m_end) {
+            const int pn = (int)(m / hw);
+            const int r = (int)(m - (int64_t)pn * hw);
+            const int oy = r / g.Wo, ox = r - oy * g.Wo;
+            if (kvalid) {
+                int iy, ix;
+                bool ok;
+                if (!g.transposed) {
+                    iy = oy * g.stride - g.pad_t + ky;
+                    ix = ox * g.stride - g.pad_l + kx;
+                    ok = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+                } else {
+                    const int ny = oy + g.pad_t - ky, nx = ox + g.pad_l - kx;
+                    ok = ny >= 0 && nx >= 0 && (ny % g.stride) == 0 && (nx % g.stride) == 0;
+                    iy = ny / g.stride;
+                    ix = nx / g.stride;
+                    ok = ok && iy < g.Hi && ix < g.Wi;
+                }
+                if (ok) a = *reinterpret_cast<const float4*>(d.x + (((int64_t)pn * g.Hi + iy) * g.Wi + ix) * g.Cin + ci);
+            }
+            if (nvalid) b = *reinterpret_cast<const float4*>(d.dy + m * g.Cout + n0 + l4);
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&As[lm][l4]) = a;
+        *reinterpret_cast<float4*>(&Bs[lm][l4]) = b;
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < WM; ++mm) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[mm][tx * 4]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+    }
+    float* out = d.part + (int64_t)blockIdx.z * K * g.Cout;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int kk = k0 + ty * 4 + i;
+        if (kk >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < g.Cout) out[(int64_t)kk * g.Cout + n] = acc[i][j];
+        }
+    }
+}
+
+__global__ void sum_splits_kernel(const float* __restrict__ part, int splits, int64_t count, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += part[(int64_t)k * count + i];
+        out[i] = s;
+    }
+}
+
+int wgrad_splits(const Geo& g) {
+    const int64_t M = (int64_t)g.N * g.Ho * g.Wo;
+    const int K = g.KH * g.KW * g.Cin;
+    const int tiles = cdiv(K, WT) * cdiv(g.Cout, WT);
+    int64_t s = (148 * 4 + tiles - 1) / tiles;
+    const int64_t smax = std::max<int64_t>(1, M / 256);
+    if (s > smax) s = smax;
+    if (s > 512) s = 512;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+// ------------------------------------------------------------------ column reductions (batch norm)
+// rows x C matrix, two per-column sums in double:
+//   mode 0: (x, x^2)              -> mean / variance
+//   mode 1: (dyr, dyr * xhat)     -> dbeta / dgamma, dyr = dy masked by the ReLU of the forward output
+struct ColArgs {
+    const float* x;
+    const float* dy;
+    const float *mean, *invstd, *gamma, *beta;
+    int64_t M;
+    int C, relu, mode;
+};
+
+__device__ __forceinline__ void col_terms(const ColArgs& a, int64_t row, int c, double& q1, double& q2) {
+    const float x = a.x[row * a.C + c];
+    if (a.mode == 0) {
+        q1 = x;
+        q2 = (double)x * x;
+    } else {
+        const float xh = (x - a.mean[c]) * a.invstd[c];
+        float dy = a.dy[row * a.C + c];
+        if (a.relu && fmaf(xh, a.gamma[c], a.beta[c]) <= 0.f) dy = 0.f;
+        q1 = dy;
+        q2 = (double)dy * xh;
+    }
+}
+
+constexpr int CR_ROWS = 256;      // rows per block
+
+__global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __restrict__ partial /* [blocks][C][2] */) {
+    __shared__ double red[8][128][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * CR_ROWS;
+    const int64_t r1 = min(a.M, r0 + CR_ROWS);
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = lane + 32 * u;
+            if (c < a.C) {
+                double q1, q2;
+                col_terms(a, r, c, q1, q2);
+                s1[u] += q1;
+                s2[u] += q2;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        red[warp][lane + 32 * u][0] = s1[u];
+        red[warp][lane + 32 * u][1] = s2[u];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += 256) {
+        double t1 = 0, t2 = 0;
+        for (int w = 0; w < 8; ++w) {
+            t1 += red[w][c][0];
+            t2 += red[w][c][1];
+        }
+        partial[((int64_t)blockIdx.x * a.C + c) * 2 + 0] = t1;
+        partial[((int64_t)blockIdx.x * a.C + c) * 2 + 1] = t2;
+    }
+}
+
+// mode 0: mean, invstd (+ moving averages); mode 1: dbeta, dgamma
+__global__ void col_finalize_kernel(const double* __restrict__ partial, int blocks, int C, int64_t M, int mode, float eps,
+                                    float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ mov_mean,
+                                    float* __restrict__ mov_var, float decay) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int b = 0; b < blocks; ++b) {
+        s1 += partial[((int64_t)b * C + c) * 2 + 0];
+        s2 += partial[((int64_t)b * C + c) * 2 + 1];
+    }
+    if (mode == 0) {
+        const double mean = s1 / (double)M;
+        double var = s2 / (double)M - mean * mean;
+        if (var < 0) var = 0;
+        o1[c] = (float)mean;
+        o2[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (mov_mean) {
+            // fused batch norm feeds the unbiased variance to the moving average (A.1)
+            const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+            mov_mean[c] = decay * mov_mean[c] + (1.f - decay) * (float)mean;
+            mov_var[c] = decay * mov_var[c] + (1.f - decay) * (float)unb;
+        }
+    } else {
+        o1[c] = (float)s1;
+        o2[c] = (float)s2;
+    }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                                const float* __restrict__ res1, const float* __restrict__ res2, int64_t total, int C,
+                                float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        float v = fmaf((x[i] - mean[c]) * invstd[c], gamma[c], beta[c]);
+        if (relu) v = fmaxf(v, 0.f);
+        if (res1) v += res1[i];
+        if (res2) v += res2[i];
+        out[i] = v;
+    }
+}
+
+// dx = gamma * invstd * (dyr - dbeta / M - xhat * dgamma / M); affine_only: dx = gamma * invstd * dyr
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ dbeta,
+                                    const float* __restrict__ dgamma, int relu, int affine_only, int64_t total, int C,
+                                    float inv_m, float* __restrict__ dx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float xh = (x[i] - mean[c]) * invstd[c];
+        float d = dy[i];
+        if (relu && fmaf(xh, gamma[c], beta[c]) <= 0.f) d = 0.f;
+        if (!affine_only) d = d - dbeta[c] * inv_m - xh * dgamma[c] * inv_m;
+        dx[i] = gamma[c] * invstd[c] * d;
+    }
+}
+
+// ------------------------------------------------------------------ heatmap + soft quantizer, backward
+// per latent pixel (n, y, x): bn[0] heatmap logit, bn[1 + c] features.
+//   hm2d = sigmoid(bn0) * C ; hm_c = max(min(hm2d - c, 1), 0) ; z_c = hm_c * bn[1 + c]
+//   qsoft_c = sum_j softmax_j(-(z_c - ctr_j)^2) ctr_j ; qbar = qsoft + stop_gradient(qhard - qsoft)
+// in: dq (NHWC, C) gradient w.r.t. qbar, dhm (NCHW, optional) extra gradient w.r.t. hm (from H_mask)
+// out: dbn (NHWC, Cb >= C + 1 channels, padding channels zeroed), per-block partial sums of dcenters
+constexpr int HQ_THREADS = 128;
+
+__global__ void __launch_bounds__(HQ_THREADS) hq_bwd_kernel(const float* __restrict__ bn, int Cb, int C, int heatmap,
+                                                           const float* __restrict__ centers, int L,
+                                                           const float* __restrict__ dq, const float* __restrict__ dhm, int h,
+                                                           int w, int64_t npix, float* __restrict__ dbn,
+                                                           double* __restrict__ dcent_partial /* [blocks][8] */) {
+    __shared__ double red[HQ_THREADS / 32][8];
+    float ctr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ctr[j] = j < L ? centers[j] : 0.f;
+    double dc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) {
+        const float* b = bn + p * Cb;
+        float* db = dbn + p * Cb;
+        const int64_t n = p / ((int64_t)h * w), yx = p - n * (int64_t)h * w;
+        float sg = 0.f, hm2d = 0.f;
+        if (heatmap) {
+            sg = 1.f / (1.f + expf(-b[0]));
+            hm2d = sg * (float)C;
+        }
+        float dhm2d = 0.f;
+        const int f0 = heatmap ? 1 : 0;
+        for (int c = 0; c < C; ++c) {
+            float hmc = 1.f;
+            const float t = hm2d - (float)c;
+            if (heatmap) hmc = fmaxf(fminf(t, 1.f), 0.f);
+            const float feat = b[f0 + c];
+            const float z = hmc * feat;
+            // softmax over -(z - ctr_j)^2
+            float e[8], m = -3.4e38f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < L) {
+                    const float dd = z - ctr[j];
+                    e[j] = -dd * dd;
+                    m = fmaxf(m, e[j]);
+                }
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < L) {
+                    e[j] = expf(e[j] - m);
+                    s += e[j];
+                }
+            float qs = 0.f, gbar = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < L) {
+                    e[j] /= s;                               // p_j
+                    qs += e[j] * ctr[j];
+                    gbar += e[j] * (-2.f * (z - ctr[j]));    // sum_k p_k g_k, g_k = d(-(z - c_k)^2)/dz
+                }
+            const float g = dq[p * C + c];
+            float dz = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < L) {
+                    const float gj = -2.f * (z - ctr[j]);
+                    dz += ctr[j] * e[j] * (gj - gbar);
+                    // d qsoft / d ctr_j = p_j + 2 (z - ctr_j) p_j (ctr_j - qsoft)
+                    dc[j] += (double)(g * (e[j] + 2.f * (z - ctr[j]) * e[j] * (ctr[j] - qs)));
+                }
+            dz *= g;
+            db[f0 + c] = dz * hmc;
+            if (heatmap) {
+                float dh = dz * feat;
+                if (dhm) dh += dhm[(n * C + c) * (int64_t)h * w + yx];
+                if (t >= 0.f && t <= 1.f) dhm2d += dh;      // gradient of maximum(minimum(t, 1), 0)
+            }
+        }
+        if (heatmap) db[0] = dhm2d * (float)C * sg * (1.f - sg);
+        for (int c = f0 + C; c < Cb; ++c) db[c] = 0.f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double v = dc[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0;
+        for (int wv = 0; wv < HQ_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        dcent_partial[(int64_t)blockIdx.x * 8 + threadIdx.x] = v;
+    }
+}
+
+__global__ void sum_double_partials_kernel(const double* __restrict__ partial, int blocks, int width, int n_out,
+                                           float* __restrict__ out) {
+    const int j = threadIdx.x;
+    if (j >= n_out) return;
+    double s = 0;
+    for (int b = 0; b < blocks; ++b) s += partial[(int64_t)b * width + j];
+    out[j] = (float)s;
+}
+
+// ------------------------------------------------------------------ image range: denormalise + clip, and back
+__constant__ float t_norm_mean[4] = {121.853699f, 113.588608f, 100.637154f, 0.f};
+__constant__ float t_norm_std[4] = {68.8939514f, 66.7393417f, 69.3702698f, 0.f};
+
+// v NHWC (4 channels, last is padding) -> x_out NCHW float [0,255] (code/autoencoder.py:146-158)
+__global__ void denorm_clip_fwd_kernel(const float* __restrict__ v, int64_t npix_img, int64_t total_pix, float* __restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total_pix; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = p / npix_img, r = p - n * npix_img;
+        const float4 q = *reinterpret_cast<const float4*>(v + p * 4);
+        const float qq[3] = {q.x, q.y, q.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t = __fadd_rn(__fmul_rn(qq[c], t_norm_std[c]), t_norm_mean[c]);
+            out[(n * 3 + c) * npix_img + r] = fminf(fmaxf(t, 0.f), 255.f);
+        }
+    }
+}
+
+// dx_out NCHW -> dv NHWC4: passes where the un-clipped value lies in [0,255] (gradient of clip_by_value)
+__global__ void denorm_clip_bwd_kernel(const float* __restrict__ v, const float* __restrict__ dout, int64_t npix_img,
+                                       int64_t total_pix, float* __restrict__ dv) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total_pix; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = p / npix_img, r = p - n * npix_img;
+        const float4 q = *reinterpret_cast<const float4*>(v + p * 4);
+        const float qq[3] = {q.x, q.y, q.z};
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t = __fadd_rn(__fmul_rn(qq[c], t_norm_std[c]), t_norm_mean[c]);
+            if (t >= 0.f && t <= 255.f) o[c] = dout[(n * 3 + c) * npix_img + r] * t_norm_std[c];
+        }
+        *reinterpret_cast<float4*>(dv + p * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------ layout + arithmetic helpers
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int C, int Cs, int64_t hw, int64_t total, float* __restrict__ out) {
+    // in N,hw,Cs (first C channels used) -> out N,C,hw
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / (C * hw), r = i - n * C * hw;
+        const int c = (int)(r / hw);
+        const int64_t p = r - c * hw;
+        out[i] = in[(n * hw + p) * Cs + c];
+    }
+}
+
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int C, int Cs, int64_t hw, int64_t total, float* __restrict__ out) {
+    // in N,C,hw -> out N,hw,Cs (channels >= C zero)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / (Cs * hw), r = i - n * Cs * hw;
+        const int64_t p = r / Cs;
+        const int c = (int)(r - p * Cs);
+        out[i] = c < C ? in[(n * C + c) * hw + p] : 0.f;
+    }
+}
+
+__global__ void axpby_kernel(float a, const float* __restrict__ x, float b, const float* __restrict__ y, int64_t n,
+                             float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a * x[i] + (y ? b * y[i] : 0.f);
+}
+
+__global__ void mul_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = x[i] * y[i];
+}
+
+// tf.train.AdamOptimizer._apply_dense; grad_scale folds the regulariser: g = grad + l2 * w
+__global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float lr_t, float beta1, float beta2, float eps, float l2, const float* __restrict__ mask) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] + l2 * w[i];
+        if (mask) gi *= mask[i];
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+inline int ew_grid(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); }
+
+}  // namespace
+}  // namespace ic
+
+using namespace ic;
+
+extern "C" {
+
+size_t ic_nn_conv2d_workspace_bytes(int N, int Hi, int Wi, int Cin, int KH, int KW, int stride, int Cout, int transposed, int valid) {
+    Geo g{N, Hi, Wi, Cin, KH, KW, stride, Cout, transposed, valid, 0, 0, 0, 0};
+    if (make_geo(g) != IC_OK) return 0;
+    const size_t wbytes = (size_t)KH * KW * Cin * Cout * sizeof(float);
+    return align_up(wbytes, 256) + align_up((size_t)wgrad_splits(g) * wbytes, 256) + 256;
+}
+
+int ic_nn_conv2d_fwd(const float* d_x, const float* d_w, int N, int Hi, int Wi, int Cin, int KH, int KW, int stride, int Cout,
+                     int transposed, int valid, float* d_y, void* stream) {
+    IC_REQUIRE(d_x && d_w && d_y, IC_ERR_INVALID, "ic_nn_conv2d_fwd: NULL argument");
+    Geo g{N, Hi, Wi, Cin, KH, KW, stride, Cout, transposed, valid, 0, 0, 0, 0};
+    int rc = make_geo(g);
+    if (rc != IC_OK) return rc;
+    rc = ensure_consts();
+    if (rc != IC_OK) return rc;
+    ConvDesc d;
+    memset(&d, 0, sizeof(d));
+    d.in = d_x; d.w = d_w; d.scale = g_ones; d.shift = g_zeros; d.out = d_y;
+    d.N = N; d.Hi = Hi; d.Wi = Wi; d.Cin = Cin; d.Ho = g.Ho; d.Wo = g.Wo; d.Cout = Cout; d.ldw = Cout;
+    d.KH = KH; d.KW = KW; d.stride = stride; d.pad_t = g.pad_t; d.pad_l = g.pad_l; d.transposed = transposed;
+    return launch_conv_simt(d, (cudaStream_t)stream);
+}
+
+int ic_nn_conv2d_bwd_data(const float* d_dy, const float* d_w, int N, int Hi, int Wi, int Cin, int KH, int KW, int stride,
+                          int Cout, int transposed, int valid, float* d_dx, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+    IC_REQUIRE(d_dy && d_w && d_dx && d_workspace, IC_ERR_INVALID, "ic_nn_conv2d_bwd_data: NULL argument");
+    Geo g{N, Hi, Wi, Cin, KH, KW, stride, Cout, transposed, valid, 0, 0, 0, 0};
+    int rc = make_geo(g);
+    if (rc != IC_OK) return rc;
+    rc = ensure_consts();
+    if (rc != IC_OK) return rc;
+    const size_t wcount = (size_t)KH * KW * Cin * Cout;
+    IC_REQUIRE(workspace_bytes >= wcount * sizeof(float), IC_ERR_WORKSPACE, "ic_nn_conv2d_bwd_data: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* wT = (float*)d_workspace;
+    transpose_taps_kernel<<<ew_grid((int64_t)wcount), 256, 0, s>>>(d_w, wT, KH * KW, Cin, Cout);
+    IC_CHECK_LAUNCH();
+    ConvDesc d;
+    memset(&d, 0, sizeof(d));
+    d.in = d_dy; d.w = wT; d.scale = g_ones; d.shift = g_zeros; d.out = d_dx;
+    d.N = N; d.Hi = g.Ho; d.Wi = g.Wo; d.Cin = Cout; d.Ho = Hi; d.Wo = Wi; d.Cout = Cin; d.ldw = Cin;
+    d.KH = KH; d.KW = KW; d.stride = stride; d.pad_t = g.pad_t; d.pad_l = g.pad_l;
+    d.transposed = transposed ? 0 : 1;       // the gradient of a conv is the other kind of conv
+    return launch_conv_simt(d, s);
+}
+
+int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, int Wi, int Cin, int KH, int KW, int stride,
+                            int Cout, int transposed, int valid, float* d_dw, void* d_workspace, size_t workspace_bytes,
+                            void* stream) {
+    IC_REQUIRE(d_x && d_dy && d_dw && d_workspace, IC_ERR_INVALID, "ic_nn_conv2d_bwd_filter: NULL argument");
+    Geo g{N, Hi, Wi, Cin, KH, KW, stride, Cout, transposed, valid, 0, 0, 0, 0};
+    int rc = make_geo(g);
+    if (rc != IC_OK) return rc;
+    const int64_t count = (int64_t)KH * KW * Cin * Cout;
+    const int splits = wgrad_splits(g);
+    IC_REQUIRE(workspace_bytes >= (size_t)splits * count * sizeof(float), IC_ERR_WORKSPACE,
+               "ic_nn_conv2d_bwd_filter: workspace too small (use ic_nn_conv2d_workspace_bytes)");
+    cudaStream_t s = (cudaStream_t)stream;
+    WgradDesc d;
+    d.x = d_x; d.dy = d_dy; d.part = (float*)d_workspace; d.g = g;
+    d.M = (int64_t)N * g.Ho * g.Wo;
+    d.m_per_split = (d.M + splits - 1) / splits;
+    d.m_per_split = (d.m_per_split + WM - 1) / WM * WM;
+    const int K = KH * KW * Cin;
+    dim3 grid(cdiv(K, WT), cdiv(Cout, WT), splits);
+    {
+        ProfScope ps(IC_PROF_CONV_OTHER, s, 2);
+        conv_wgrad_kernel<<<grid, 256, 0, s>>>(d);
+        IC_CHECK_LAUNCH();
+        sum_splits_kernel<<<ew_grid(count), 256, 0, s>>>((const float*)d_workspace, splits, count, d_dw);
+        IC_CHECK_LAUNCH();
+    }
+    return IC_OK;
+}
+
+size_t ic_nn_bn_workspace_bytes(int64_t M, int C) {
+    if (M <= 0 || C <= 0 || C > 128) return 0;
+    const int64_t blocks = (M + CR_ROWS - 1) / CR_ROWS;
+    return (size_t)blocks * C * 2 * sizeof(double) + 256;
+}
+
+/* slim.batch_norm(is_training=True): statistics of x (M rows, C channels), then
+ * out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2).  d_mean / d_invstd are saved
+ * for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update.
+ * gamma == NULL / beta == NULL: identity statistics are not computed -- pass use_stats = 0 for a
+ * plain affine layer y = relu?(x * gamma + beta) with d_mean = 0, d_invstd = 1 supplied by the caller. */
+int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps, int relu,
+                       int use_stats, const float* d_res1, const float* d_res2, float* d_mean, float* d_invstd,
+                       float* d_mov_mean, float* d_mov_var, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_x && d_gamma && d_beta && d_mean && d_invstd && d_out, IC_ERR_INVALID, "ic_nn_bn_train_fwd: NULL argument");
+    IC_REQUIRE(M > 0 && C > 0 && C <= 128, IC_ERR_INVALID, "ic_nn_bn_train_fwd: bad shape (C <= 128)");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (use_stats) {
+        IC_REQUIRE(d_workspace && workspace_bytes >= ic_nn_bn_workspace_bytes(M, C), IC_ERR_WORKSPACE, "ic_nn_bn_train_fwd: workspace");
+        const int blocks = (int)((M + CR_ROWS - 1) / CR_ROWS);
+        ColArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = d_x; a.M = M; a.C = C; a.mode = 0;
+        col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
+        IC_CHECK_LAUNCH();
+        col_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 0, eps, d_mean, d_invstd,
+                                                         d_mov_mean, d_mov_var, 0.9f);
+        IC_CHECK_LAUNCH();
+    }
+    bn_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_mean, d_invstd, d_gamma, d_beta, relu, d_res1, d_res2, M * C, C, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* backward of ic_nn_bn_train_fwd w.r.t. x, gamma, beta (the residual inputs receive d_dy unchanged). */
+int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, const float* d_gamma, const float* d_beta, int relu,
+                       int use_stats, const float* d_mean, const float* d_invstd, float* d_dx, float* d_dgamma, float* d_dbeta,
+                       void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_x && d_dy && d_gamma && d_beta && d_mean && d_invstd && d_dx && d_dgamma && d_dbeta && d_workspace,
+               IC_ERR_INVALID, "ic_nn_bn_train_bwd: NULL argument");
+    IC_REQUIRE(M > 0 && C > 0 && C <= 128, IC_ERR_INVALID, "ic_nn_bn_train_bwd: bad shape (C <= 128)");
+    IC_REQUIRE(workspace_bytes >= ic_nn_bn_workspace_bytes(M, C), IC_ERR_WORKSPACE, "ic_nn_bn_train_bwd: workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (int)((M + CR_ROWS - 1) / CR_ROWS);
+    ColArgs a;
+    a.x = d_x; a.dy = d_dy; a.mean = d_mean; a.invstd = d_invstd; a.gamma = d_gamma; a.beta = d_beta;
+    a.M = M; a.C = C; a.relu = relu; a.mode = 1;
+    col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
+    IC_CHECK_LAUNCH();
+    col_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 1, 0.f, d_dbeta, d_dgamma, nullptr,
+                                                     nullptr, 0.f);
+    IC_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_dy, d_mean, d_invstd, d_gamma, d_beta, d_dbeta, d_dgamma, relu,
+                                                       use_stats ? 0 : 1, M * C, C, 1.f / (float)M, d_dx);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+size_t ic_nn_hq_workspace_bytes(int64_t npix) { return (size_t)((npix + HQ_THREADS - 1) / HQ_THREADS) * 8 * sizeof(double) + 256; }
+
+/* backward of heatmap + mask + soft quantizer (code/autoencoder.py:127-134,171-200; quantizer.py:60-100).
+ * d_bn N,h,w,Cb (channel 0 heatmap logit, 1..C features); d_dq N,h,w,C gradient w.r.t. qbar;
+ * d_dhm N,C,h,w optional gradient w.r.t. heatmap3D -> d_dbn N,h,w,Cb and d_dcenters (L). */
+int ic_nn_hq_bwd(const float* d_bn, int N, int h, int w, int C, int Cb, int heatmap, const float* d_centers, int L,
+                 const float* d_dq, const float* d_dhm, float* d_dbn, float* d_dcenters, void* d_workspace,
+                 size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_bn && d_centers && d_dq && d_dbn && d_dcenters && d_workspace, IC_ERR_INVALID, "ic_nn_hq_bwd: NULL argument");
+    IC_REQUIRE(L >= 1 && L <= 8 && Cb >= C + (heatmap ? 1 : 0), IC_ERR_INVALID, "ic_nn_hq_bwd: bad shape");
+    const int64_t npix = (int64_t)N * h * w;
+    IC_REQUIRE(workspace_bytes >= ic_nn_hq_workspace_bytes(npix), IC_ERR_WORKSPACE, "ic_nn_hq_bwd: workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (int)((npix + HQ_THREADS - 1) / HQ_THREADS);
+    hq_bwd_kernel<<<blocks, HQ_THREADS, 0, s>>>(d_bn, Cb, C, heatmap, d_centers, L, d_dq, d_dhm, h, w, npix, d_dbn,
+                                                (double*)d_workspace);
+    IC_CHECK_LAUNCH();
+    sum_double_partials_kernel<<<1, 32, 0, s>>>((const double*)d_workspace, blocks, 8, L, d_dcenters);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_denorm_clip_fwd(const float* d_v_nhwc4, int N, int H, int W, float* d_x_out_nchw, void* stream) {
+    IC_REQUIRE(d_v_nhwc4 && d_x_out_nchw, IC_ERR_INVALID, "ic_nn_denorm_clip_fwd: NULL argument");
+    const int64_t hw = (int64_t)H * W;
+    denorm_clip_fwd_kernel<<<ew_grid(N * hw), 256, 0, (cudaStream_t)stream>>>(d_v_nhwc4, hw, N * hw, d_x_out_nchw);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_denorm_clip_bwd(const float* d_v_nhwc4, const float* d_dx_out_nchw, int N, int H, int W, float* d_dv_nhwc4, void* stream) {
+    IC_REQUIRE(d_v_nhwc4 && d_dx_out_nchw && d_dv_nhwc4, IC_ERR_INVALID, "ic_nn_denorm_clip_bwd: NULL argument");
+    const int64_t hw = (int64_t)H * W;
+    denorm_clip_bwd_kernel<<<ew_grid(N * hw), 256, 0, (cudaStream_t)stream>>>(d_v_nhwc4, d_dx_out_nchw, hw, N * hw, d_dv_nhwc4);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_nhwc_to_nchw(const float* d_in, int N, int C, int Cs, int64_t hw, float* d_out, void* stream) {
+    IC_REQUIRE(d_in && d_out && Cs >= C, IC_ERR_INVALID, "ic_nn_nhwc_to_nchw: bad argument");
+    nhwc_to_nchw_kernel<<<ew_grid(N * C * hw), 256, 0, (cudaStream_t)stream>>>(d_in, C, Cs, hw, N * C * hw, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_nchw_to_nhwc(const float* d_in, int N, int C, int Cs, int64_t hw, float* d_out, void* stream) {
+    IC_REQUIRE(d_in && d_out && Cs >= C, IC_ERR_INVALID, "ic_nn_nchw_to_nhwc: bad argument");
+    nchw_to_nhwc_pad_kernel<<<ew_grid(N * Cs * hw), 256, 0, (cudaStream_t)stream>>>(d_in, C, Cs, hw, N * Cs * hw, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* out = a * x + b * y (y optional); out may alias x or y */
+int ic_nn_axpby(float a, const float* d_x, float b, const float* d_y, int64_t n, float* d_out, void* stream) {
+    IC_REQUIRE(d_x && d_out && n >= 0, IC_ERR_INVALID, "ic_nn_axpby: bad argument");
+    if (n == 0) return IC_OK;
+    axpby_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(a, d_x, b, d_y, n, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_mul(const float* d_x, const float* d_y, int64_t n, float* d_out, void* stream) {
+    IC_REQUIRE(d_x && d_y && d_out && n >= 0, IC_ERR_INVALID, "ic_nn_mul: bad argument");
+    if (n == 0) return IC_OK;
+    mul_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* one tf.train.AdamOptimizer step on a flat tensor: g <- grad + l2 * w (slim l2 regulariser), optional 0/1 mask,
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), step t counts from 1. */
+int ic_nn_adam_step(float* d_w, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, int64_t step, float l2, const float* d_mask, void* stream) {
+    IC_REQUIRE(d_w && d_grad && d_m && d_v && n >= 0 && step >= 1, IC_ERR_INVALID, "ic_nn_adam_step: bad argument");
+    if (n == 0) return IC_OK;
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_w, d_grad, d_m, d_v, n, (float)lr_t, beta1, beta2, eps, l2, d_mask);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+}  // extern "C"

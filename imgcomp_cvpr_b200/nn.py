@@ -1,0 +1,162 @@
+"""Thin host wrappers of the training primitives (include/imgcomp_b200.h, ic_nn_*): torch CUDA tensors are
+containers, every operation runs in libimgcomp_b200.so.  Activations NHWC float32 with channel counts that
+are multiples of 4, convolution weights [KH][KW][Cin][Cout] in the orientation of the op."""
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5        # slim.batch_norm epsilon of the reference (code/autoencoder.py:121)
+
+
+def _f32(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'float32 contiguous CUDA tensor expected'
+    return t
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes):
+    ws = _ws_cache.get('ws')
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device='cuda')
+        _ws_cache['ws'] = ws
+    return ws
+
+
+def _geo(x_shape, w_shape, stride, transposed, valid):
+    N, Hi, Wi, Cin = x_shape
+    KH, KW, wi, Cout = w_shape
+    assert wi == Cin, 'weights are [KH][KW][Cin][Cout]: Cin %d != %d' % (wi, Cin)
+    if valid:
+        Ho, Wo = (Hi - KH) // stride + 1, (Wi - KW) // stride + 1
+    elif transposed:
+        Ho, Wo = Hi * stride, Wi * stride
+    else:
+        Ho, Wo = -(-Hi // stride), -(-Wi // stride)
+    return (N, Hi, Wi, Cin, KH, KW, stride, Cout, int(bool(transposed)), int(bool(valid))), (N, Ho, Wo, Cout)
+
+
+def conv2d_fwd(x, w, stride=1, transposed=False, valid=False):
+    g, oshape = _geo(x.shape, w.shape, stride, transposed, valid)
+    y = torch.empty(oshape, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ic_nn_conv2d_fwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(w)), *g, _lib.ptr(y), _lib.stream_ptr()))
+    return y
+
+
+def conv2d_bwd_data(dy, w, x_shape, stride=1, transposed=False, valid=False):
+    g, oshape = _geo(x_shape, w.shape, stride, transposed, valid)
+    assert tuple(dy.shape) == oshape, '{} != {}'.format(tuple(dy.shape), oshape)
+    dx = torch.empty(tuple(x_shape), dtype=torch.float32, device=dy.device)
+    ws = _workspace(_lib.lib().ic_nn_conv2d_workspace_bytes(*g))
+    _lib.check(_lib.lib().ic_nn_conv2d_bwd_data(_lib.ptr(_f32(dy)), _lib.ptr(_f32(w)), *g, _lib.ptr(dx), _lib.ptr(ws), ws.numel(),
+                                               _lib.stream_ptr()))
+    return dx
+
+
+def conv2d_bwd_filter(x, dy, w_shape, stride=1, transposed=False, valid=False):
+    g, oshape = _geo(x.shape, w_shape, stride, transposed, valid)
+    assert tuple(dy.shape) == oshape, '{} != {}'.format(tuple(dy.shape), oshape)
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    ws = _workspace(_lib.lib().ic_nn_conv2d_workspace_bytes(*g))
+    _lib.check(_lib.lib().ic_nn_conv2d_bwd_filter(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), *g, _lib.ptr(dw), _lib.ptr(ws), ws.numel(),
+                                                 _lib.stream_ptr()))
+    return dw
+
+
+def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None):
+    """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    out = torch.empty_like(x)
+    if stats is None:
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    else:
+        mean, invstd = stats
+    ws = _workspace(_lib.lib().ic_nn_bn_workspace_bytes(M, C))
+    _lib.check(_lib.lib().ic_nn_bn_train_fwd(_lib.ptr(_f32(x)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)), BN_EPS,
+                                            int(relu), int(stats is None), _lib.ptr(res1), _lib.ptr(res2), _lib.ptr(mean),
+                                            _lib.ptr(invstd), _lib.ptr(mov_mean), _lib.ptr(mov_var), _lib.ptr(out),
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return out, mean, invstd
+
+
+def bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu=False, use_stats=True):
+    """-> (dx, dgamma, dbeta)"""
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = _workspace(_lib.lib().ic_nn_bn_workspace_bytes(M, C))
+    _lib.check(_lib.lib().ic_nn_bn_train_bwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)),
+                                            int(relu), int(use_stats), _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(dx),
+                                            _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return dx, dgamma, dbeta
+
+
+def hq_bwd(bn, C, heatmap, centers, dq, dhm=None):
+    """bn N,h,w,Cb; dq N,h,w,C; dhm N,C,h,w or None -> (dbn N,h,w,Cb, dcenters (L,))"""
+    N, h, w, Cb = bn.shape
+    dbn = torch.empty_like(bn)
+    dcent = torch.empty(centers.numel(), dtype=torch.float32, device=bn.device)
+    ws = _workspace(_lib.lib().ic_nn_hq_workspace_bytes(N * h * w))
+    _lib.check(_lib.lib().ic_nn_hq_bwd(_lib.ptr(_f32(bn)), N, h, w, C, Cb, int(heatmap), _lib.ptr(_f32(centers)), centers.numel(),
+                                      _lib.ptr(_f32(dq)), _lib.ptr(dhm), _lib.ptr(dbn), _lib.ptr(dcent), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()))
+    return dbn, dcent
+
+
+def denorm_clip_fwd(v):
+    """v N,H,W,4 -> x_out N,3,H,W in [0,255]"""
+    N, H, W, _ = v.shape
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=v.device)
+    _lib.check(_lib.lib().ic_nn_denorm_clip_fwd(_lib.ptr(_f32(v)), N, H, W, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def denorm_clip_bwd(v, dx_out):
+    N, H, W, _ = v.shape
+    dv = torch.empty_like(v)
+    _lib.check(_lib.lib().ic_nn_denorm_clip_bwd(_lib.ptr(_f32(v)), _lib.ptr(_f32(dx_out)), N, H, W, _lib.ptr(dv), _lib.stream_ptr()))
+    return dv
+
+
+def nhwc_to_nchw(x, C=None):
+    N, H, W, Cs = x.shape
+    C = Cs if C is None else C
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ic_nn_nhwc_to_nchw(_lib.ptr(_f32(x)), N, C, Cs, H * W, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def nchw_to_nhwc(x, Cs=None):
+    N, C, H, W = x.shape
+    Cs = C if Cs is None else Cs
+    out = torch.empty((N, H, W, Cs), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ic_nn_nchw_to_nhwc(_lib.ptr(_f32(x)), N, C, Cs, H * W, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def axpby(a, x, b=0.0, y=None, out=None):
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().ic_nn_axpby(float(a), _lib.ptr(_f32(x)), float(b), _lib.ptr(y), x.numel(), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def add(x, y):
+    return axpby(1.0, x, 1.0, y)
+
+
+def mul(x, y):
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().ic_nn_mul(_lib.ptr(_f32(x)), _lib.ptr(_f32(y)), x.numel(), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def adam_step(w, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, l2=0.0, mask=None):
+    """in place on w, m, v"""
+    _lib.check(_lib.lib().ic_nn_adam_step(_lib.ptr(_f32(w)), _lib.ptr(_f32(grad)), _lib.ptr(_f32(m)), _lib.ptr(_f32(v)), w.numel(),
+                                         float(lr), float(beta1), float(beta2), float(eps), int(step), float(l2), _lib.ptr(mask),
+                                         _lib.stream_ptr()))

@@ -181,6 +181,66 @@ int ic_pc_context_freqs_fwd(const ic_pc_t* pc, const int64_t* d_ctx_symbols, con
                             int N, int D, int H, int W, int64_t* d_freqs,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* --------------------------------------------------------------------- training primitives
+ * What tf.gradients and the two Adam optimisers of code/train.py:339-349 execute for the graph of
+ * code/train.py:86-132 (cfg 3), as explicit float32 forward / backward kernels; the host side
+ * (imgcomp_cvpr_b200/train.py) strings them together in the order of the reference graph.
+ * Activations NHWC float32 with channel counts padded to a multiple of 4; convolution weights
+ * [KH][KW][Cin][Cout] in the orientation of the op (slim.conv2d's HWIO; for slim.conv2d_transpose the
+ * TF variable [kh][kw][out][in] with its last two axes swapped).  valid = 0: TF SAME padding
+ * (SURVEY.md A.2), transposed = 1: conv2d_transpose (output 2x); valid = 1: VALID, forward kind only. */
+size_t ic_nn_conv2d_workspace_bytes(int N, int Hi, int Wi, int Cin, int KH, int KW, int stride, int Cout,
+                                    int transposed, int valid);
+/* slim.conv2d / slim.conv2d_transpose without normaliser or activation (code/autoencoder.py:222-237,251-265) */
+int ic_nn_conv2d_fwd(const float* d_x, const float* d_w, int N, int Hi, int Wi, int Cin, int KH, int KW,
+                     int stride, int Cout, int transposed, int valid, float* d_y, void* stream);
+/* Conv2DBackpropInput / its transposed twin: d_dy (output shape of the op) -> d_dx (input shape) */
+int ic_nn_conv2d_bwd_data(const float* d_dy, const float* d_w, int N, int Hi, int Wi, int Cin, int KH, int KW,
+                          int stride, int Cout, int transposed, int valid, float* d_dx,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+/* Conv2DBackpropFilter: d_x (input), d_dy (output gradient) -> d_dw [KH][KW][Cin][Cout] */
+int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, int Wi, int Cin, int KH, int KW,
+                            int stride, int Cout, int transposed, int valid, float* d_dw,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+/* slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125): batch mean / biased variance over
+ * the M = N*H*W rows, out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2); d_mean / d_invstd are
+ * kept for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update with
+ * the unbiased variance.  use_stats = 0: plain affine layer with caller-supplied d_mean / d_invstd (bias + ReLU
+ * of the context model: mean 0, invstd 1, gamma 1, beta = bias). */
+size_t ic_nn_bn_workspace_bytes(int64_t M, int C);
+int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps,
+                       int relu, int use_stats, const float* d_res1, const float* d_res2, float* d_mean,
+                       float* d_invstd, float* d_mov_mean, float* d_mov_var, float* d_out,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, const float* d_gamma,
+                       const float* d_beta, int relu, int use_stats, const float* d_mean, const float* d_invstd,
+                       float* d_dx, float* d_dgamma, float* d_dbeta,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+/* backward of _get_heatmap3D + _mask_with_heatmap + the soft quantizer with
+ * qbar = qsoft + stop_gradient(qhard - qsoft) (code/autoencoder.py:127-134,171-200; quantizer.py:60-100):
+ * d_bn N,h,w,Cb (channel 0 = heatmap logit, 1..C = features), d_dq N,h,w,C = gradient w.r.t. qbar,
+ * d_dhm N,C,h,w (optional) = gradient w.r.t. heatmap3D (from H_mask, code/train.py:311-314)
+ * -> d_dbn N,h,w,Cb, d_dcenters (L). */
+size_t ic_nn_hq_workspace_bytes(int64_t npix);
+int ic_nn_hq_bwd(const float* d_bn, int N, int h, int w, int C, int Cb, int heatmap, const float* d_centers, int L,
+                 const float* d_dq, const float* d_dhm, float* d_dbn, float* d_dcenters,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+/* _denormalize + _clip_to_image_range (code/autoencoder.py:146-158) on the decoder's last NHWC (4-channel) map
+ * -> x_out NCHW, and the gradient back (passes where the un-clipped value is inside [0,255]). */
+int ic_nn_denorm_clip_fwd(const float* d_v_nhwc4, int N, int H, int W, float* d_x_out_nchw, void* stream);
+int ic_nn_denorm_clip_bwd(const float* d_v_nhwc4, const float* d_dx_out_nchw, int N, int H, int W,
+                          float* d_dv_nhwc4, void* stream);
+/* layout changes between the reference's NCHW tensors and the NHWC maps of the kernels (Cs = padded channels) */
+int ic_nn_nhwc_to_nchw(const float* d_in, int N, int C, int Cs, int64_t hw, float* d_out, void* stream);
+int ic_nn_nchw_to_nhwc(const float* d_in, int N, int C, int Cs, int64_t hw, float* d_out, void* stream);
+/* out = a * x + b * y (y optional; out may alias), out = x * y */
+int ic_nn_axpby(float a, const float* d_x, float b, const float* d_y, int64_t n, float* d_out, void* stream);
+int ic_nn_mul(const float* d_x, const float* d_y, int64_t n, float* d_out, void* stream);
+/* tf.train.AdamOptimizer._apply_dense on a flat tensor (code/training_helpers.py:38-48): g = grad + l2 * w
+ * (slim l2 regulariser, code/autoencoder.py:101-102), optional 0/1 mask on g, step counts from 1. */
+int ic_nn_adam_step(float* d_w, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, int64_t step, float l2, const float* d_mask, void* stream);
+
 /* --------------------------------------------------------------------- MS-SSIM
  * replaces: ms_ssim.MultiScaleSSIM(img1, img2, data_format='NCHW')   code/ms_ssim.py:115-186
  * float32, ONE scalar for the batch.  d_out: 1 float; d_levels (optional): 10 floats
