@@ -85,6 +85,16 @@ SIGNATURES = {
     'ic_nn_mul': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'ic_nn_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int64,
                                 c_float, c_void_p, c_void_p]),
+    'ic_nn_normalize_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ic_nn_hq_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int] + [c_void_p] * 7),
+    'ic_nn_pc_pad_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'ic_nn_pc_xent_fwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ic_nn_pc_xent_bwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                  c_void_p, c_void_p]),
+    'ic_nn_crop_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ic_nn_crop_bwd_add': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ic_msssim_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'ic_msssim_tf_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'ic_msssim_tf_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_msssim_np_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -99,8 +99,13 @@ int launch_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out,
 int launch_heatmap_quantize(const float* bn_nhwc, int N, int h, int w, int C, int heatmap,
                             const float* centers, int L,
                             float* z, float* hm, float* qbar, float* qhard, int64_t* sym, uint8_t* sym8,
-                            float* qsoft, cudaStream_t s);
+                            float* qsoft, cudaStream_t s, int cb_stride = 0);
 int launch_quantize(const float* x, const float* centers, int L, float sigma, int64_t n,
                     float* qsoft, float* qhard, int64_t* sym, cudaStream_t s);
+
+// ms-ssim (msssim.cu)
+size_t msssim_bwd_workspace_bytes(int N, int H, int W);
+int msssim_tf_bwd(const float* a, const float* b, int N, int H, int W, float grad_out, float* d_b, float* value_out, void* ws,
+                  size_t ws_bytes, cudaStream_t s);
 
 }  // namespace ic

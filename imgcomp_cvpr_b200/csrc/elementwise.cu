@@ -124,7 +124,7 @@ __global__ void heatmap_quantize_kernel(const float* __restrict__ bn, int h, int
                                         float* __restrict__ z_out, float* __restrict__ hm_out,
                                         float* __restrict__ qbar_out, float* __restrict__ qhard_out,
                                         int64_t* __restrict__ sym_out, uint8_t* __restrict__ sym8_out,
-                                        float* __restrict__ qsoft_out) {
+                                        float* __restrict__ qsoft_out, int cb_stride) {
     __shared__ float sc[kMaxL];
     if (threadIdx.x < L) sc[threadIdx.x] = centers[threadIdx.x];
     __syncthreads();
@@ -135,7 +135,7 @@ __global__ void heatmap_quantize_kernel(const float* __restrict__ bn, int h, int
     int64_t nc = i / hw;
     int c = (int)(nc % C);
     int64_t n = nc / C;
-    int CB = heatmap ? C + 1 : C;
+    int CB = cb_stride > 0 ? cb_stride : (heatmap ? C + 1 : C);
     const float* px = bn + (n * hw + r) * CB;
     float z, hm = 1.f;
     if (heatmap) {
@@ -214,12 +214,12 @@ int launch_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out,
 
 int launch_heatmap_quantize(const float* bn_nhwc, int N, int h, int w, int C, int heatmap, const float* centers,
                             int L, float* z, float* hm, float* qbar, float* qhard, int64_t* sym, uint8_t* sym8,
-                            float* qsoft, cudaStream_t s) {
+                            float* qsoft, cudaStream_t s, int cb_stride) {
     IC_REQUIRE(L <= kMaxL, IC_ERR_UNSUPPORTED, "num_centers %d > %d", L, kMaxL);
     int64_t total = (int64_t)N * C * h * w;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
     heatmap_quantize_kernel<<<cdiv(total, 256), 256, 0, s>>>(bn_nhwc, h, w, C, heatmap, centers, L, total, z, hm,
-                                                             qbar, qhard, sym, sym8, qsoft);
+                                                             qbar, qhard, sym, sym8, qsoft, cb_stride);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

@@ -11,6 +11,8 @@
 
 namespace ic {
 
+size_t msssim_workspace_bytes(int N, int H, int W, int is_double);
+
 namespace {
 
 constexpr int TW = 16, TH = 16, MAXK = 11;
@@ -242,9 +244,16 @@ int fill_level(LevelParams<T>& p, int H, int W, bool tf) {
     return IC_OK;
 }
 
+template <typename T>
+struct LevelBufs {
+    T* a[5];
+    T* b[5];
+    int h[5], w[5];
+};
+
 template <typename T, typename TIn, bool TF>
 int run_msssim(const TIn* img1, const TIn* img2, int N, int H, int W, void* ws, size_t ws_bytes, double* lv_out,
-               cudaStream_t s) {
+               cudaStream_t s, LevelBufs<T>* bufs_out = nullptr) {
     const int P = N * 3;
     Arena ar(ws, ws_bytes);
     // level buffers (levels 1..4), both images
@@ -293,9 +302,234 @@ int run_msssim(const TIn* img1, const TIn* img2, int N, int H, int W, void* ws, 
             IC_CHECK_LAUNCH();
         }
     }
+    if (bufs_out)
+        for (int l = 0; l < 5; ++l) {
+            bufs_out->a[l] = bufA[l];
+            bufs_out->b[l] = bufB[l];
+            bufs_out->h[l] = hs[l];
+            bufs_out->w[l] = wsz[l];
+        }
     return IC_OK;
 }
 
+// ------------------------------------------------------------------ backward of the tf variant (w.r.t. img2)
+// value = ssim_4^w4 * prod_{l<4} cs_l^wl with ssim_l / cs_l the batch means of the per-pixel maps
+// (code/ms_ssim.py:110-111,183-186): d value / d cs_l = w_l value / cs_l, spread evenly over the level's
+// count_l map entries.  coef[2l] multiplies the per-pixel ssim map of level l, coef[2l+1] its cs map.
+struct BwdCounts {
+    double count[5];
+};
+
+__global__ void bwd_coef_kernel(const double* __restrict__ lv /* [5][2] */, BwdCounts cnt, float grad_out, float* __restrict__ coef,
+                                float* __restrict__ value_out) {
+    if (threadIdx.x != 0) return;
+    const float w[5] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
+    double prod = 1.0;
+    for (int l = 0; l < 4; ++l) prod *= pow(lv[2 * l + 1], (double)w[l]);
+    const double val = prod * pow(lv[2 * 4], (double)w[4]);
+    for (int l = 0; l < 5; ++l) {
+        coef[2 * l] = (l == 4) ? (float)((double)grad_out * w[4] * val / lv[2 * 4] / cnt.count[4]) : 0.f;
+        coef[2 * l + 1] = (l < 4) ? (float)((double)grad_out * w[l] * val / lv[2 * l + 1] / cnt.count[l]) : 0.f;
+    }
+    if (value_out) value_out[0] = (float)val;
+}
+
+// Recomputes the blurred statistics of one level exactly like ssim_level_kernel and writes, per map entry, the
+// gradient w.r.t. mu2 = G*b, e22 = G*(b*b), e12 = G*(a*b)   (code/ms_ssim.py:86-109).
+__global__ void __launch_bounds__(TW* TH) ssim_level_bwd_maps_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                     LevelParams<float> p, const float* __restrict__ coef, int level,
+                                                                     float* __restrict__ g_mu, float* __restrict__ g_22,
+                                                                     float* __restrict__ g_12) {
+    __shared__ float sx[TH + MAXK - 1][TW + MAXK - 1];
+    __shared__ float sy[TH + MAXK - 1][TW + MAXK - 1];
+    __shared__ float hq[5][TH + MAXK - 1][TW];
+    const int plane = blockIdx.z;
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+    const int tid = threadIdx.y * TW + threadIdx.x;
+    const float* pa = a + (int64_t)plane * p.H * p.W;
+    const float* pb = b + (int64_t)plane * p.H * p.W;
+    const int rows = TH + p.K - 1, cols = TW + p.K - 1;
+    for (int i = tid; i < rows * cols; i += TW * TH) {
+        int r = i / cols, c = i - r * cols;
+        int uy = oy0 + r, ux = ox0 + c;
+        float vx = 0, vy = 0;
+        if (uy < p.H + p.p1 + p.p2 && ux < p.W + p.p1 + p.p2) {
+            int yy = reflect_idx(uy - p.p1, p.H), xx = reflect_idx(ux - p.p1, p.W);
+            vx = pa[(int64_t)yy * p.W + xx];
+            vy = pb[(int64_t)yy * p.W + xx];
+        }
+        sx[r][c] = vx;
+        sy[r][c] = vy;
+    }
+    __syncthreads();
+    for (int i = tid; i < rows * TW; i += TW * TH) {
+        int r = i / TW, c = i - r * TW;
+        float h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+        for (int t = 0; t < p.K; ++t) {
+            float x = sx[r][c + t], y = sy[r][c + t], k = p.taps[t];
+            h0 += x * k;
+            h1 += y * k;
+            h2 += (x * x) * k;
+            h3 += (y * y) * k;
+            h4 += (x * y) * k;
+        }
+        hq[0][r][c] = h0;
+        hq[1][r][c] = h1;
+        hq[2][r][c] = h2;
+        hq[3][r][c] = h3;
+        hq[4][r][c] = h4;
+    }
+    __syncthreads();
+    const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x;
+    if (oy >= p.Ho || ox >= p.Wo) return;
+    float mu1 = 0, mu2 = 0, e11 = 0, e22 = 0, e12 = 0;
+    for (int t = 0; t < p.K; ++t) {
+        float k = p.taps[t];
+        mu1 += hq[0][threadIdx.y + t][threadIdx.x] * k;
+        mu2 += hq[1][threadIdx.y + t][threadIdx.x] * k;
+        e11 += hq[2][threadIdx.y + t][threadIdx.x] * k;
+        e22 += hq[3][threadIdx.y + t][threadIdx.x] * k;
+        e12 += hq[4][threadIdx.y + t][threadIdx.x] * k;
+    }
+    const float gs = coef[2 * level], gcs = coef[2 * level + 1];
+    const float v1 = 2.f * (e12 - mu1 * mu2) + p.c2;
+    const float v2 = (e11 - mu1 * mu1) + (e22 - mu2 * mu2) + p.c2;
+    const float An = 2.f * mu1 * mu2 + p.c1, Bn = mu1 * mu1 + mu2 * mu2 + p.c1;
+    const float lum = An / Bn, cs = v1 / v2;
+    const float wcs = gcs + gs * lum;      // weight on the cs factor
+    const float wl = gs * cs;              // weight on the luminance factor
+    const float gv1 = wcs / v2, gv2 = -wcs * cs / v2;
+    const float dlum = (2.f * mu1 * Bn - An * 2.f * mu2) / (Bn * Bn);
+    const int64_t o = ((int64_t)plane * p.Ho + oy) * p.Wo + ox;
+    g_mu[o] = wl * dlum - 2.f * mu1 * gv1 - 2.f * mu2 * gv2;
+    g_22[o] = gv2;
+    g_12[o] = 2.f * gv1;
+}
+
+// rows of the REFLECT-padded plane that read source row y: y + p1, and the mirrored copies
+__device__ __forceinline__ int pad_preimages(int y, int n, int p1, int p2, int* u) {
+    int c = 0;
+    u[c++] = y + p1;
+    if (y >= 1 && y <= p1) u[c++] = p1 - y;
+    if (y <= n - 2 && y >= n - 1 - p2) u[c++] = p1 + 2 * (n - 1) - y;
+    return c;
+}
+
+// d loss / d b of one level: adjoint of the VALID separable blur of (b, b*b, a*b) (full correlation with the
+// same taps), folded through the REFLECT padding, plus the adjoint of the 2x2 box downsample that produced the
+// next level (code/ms_ssim.py:46-64,179-181).  One thread per source pixel, gather form: no atomics.
+__global__ void __launch_bounds__(256) ssim_level_bwd_input_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                    LevelParams<float> p, const float* __restrict__ g_mu,
+                                                                    const float* __restrict__ g_22, const float* __restrict__ g_12,
+                                                                    const float* __restrict__ d_next, int Hn, int Wn, int64_t total,
+                                                                    float* __restrict__ d_b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % p.W);
+    const int64_t r = i / p.W;
+    const int y = (int)(r % p.H);
+    const int64_t plane = r / p.H;
+    const float av = a[i], bv = b[i];
+    const float* pm = g_mu + plane * p.Ho * p.Wo;
+    const float* p22 = g_22 + plane * p.Ho * p.Wo;
+    const float* p12 = g_12 + plane * p.Ho * p.Wo;
+    int uys[3], uxs[3];
+    const int ny = pad_preimages(y, p.H, p.p1, p.p2, uys), nx = pad_preimages(x, p.W, p.p1, p.p2, uxs);
+    float s_mu = 0.f, s_22 = 0.f, s_12 = 0.f;
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            const int uy = uys[iy], ux = uxs[ix];
+            const int t0 = max(0, uy - (p.Ho - 1)), t1 = min(p.K - 1, uy);
+            const int q0 = max(0, ux - (p.Wo - 1)), q1 = min(p.K - 1, ux);
+            for (int t = t0; t <= t1; ++t) {
+                const int64_t row = (int64_t)(uy - t) * p.Wo;
+                float r_mu = 0.f, r_22 = 0.f, r_12 = 0.f;
+                for (int q = q0; q <= q1; ++q) {
+                    const float k = p.taps[q];
+                    const int64_t o = row + (ux - q);
+                    r_mu += k * pm[o];
+                    r_22 += k * p22[o];
+                    r_12 += k * p12[o];
+                }
+                s_mu += p.taps[t] * r_mu;
+                s_22 += p.taps[t] * r_22;
+                s_12 += p.taps[t] * r_12;
+            }
+        }
+    float acc = s_mu + 2.f * bv * s_22 + av * s_12;
+    if (d_next) {
+        // output (i, j) of the downsample read rows 2i and 2i+1 (REFLECT: row H -> H-2)
+        const float* dn = d_next + plane * Hn * Wn;
+        int is[2], js[2], ni = 0, nj = 0;
+        is[ni++] = y >> 1;
+        if ((p.H & 1) && y == p.H - 2) is[ni++] = (p.H - 1) >> 1;
+        js[nj++] = x >> 1;
+        if ((p.W & 1) && x == p.W - 2) js[nj++] = (p.W - 1) >> 1;
+        float s = 0.f;
+        for (int ii = 0; ii < ni; ++ii)
+            for (int jj = 0; jj < nj; ++jj) s += dn[(int64_t)is[ii] * Wn + js[jj]];
+        acc += 0.25f * s;
+    }
+    d_b[i] = acc;
+}
+
+}  // namespace
+
+size_t msssim_bwd_workspace_bytes(int N, int H, int W) {
+    const size_t P = (size_t)N * 3;
+    const size_t h1 = (H + 1) / 2, w1 = (W + 1) / 2;
+    size_t b = 256 + 256;                                        // level means, coefficients
+    b += 3 * (align_up(P * H * W * 4, 256) + 256);               // g maps of the largest level
+    b += 2 * (align_up(P * h1 * w1 * 4, 256) + 256);             // gradient ping-pong of levels >= 1
+    return b + msssim_workspace_bytes(N, H, W, 0) + 1024;
+}
+
+int msssim_tf_bwd(const float* a, const float* b, int N, int H, int W, float grad_out, float* d_b, float* value_out, void* ws,
+                  size_t ws_bytes, cudaStream_t s) {
+    IC_REQUIRE(ws_bytes >= msssim_bwd_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ms-ssim backward workspace too small: need %zu, have %zu",
+               msssim_bwd_workspace_bytes(N, H, W), ws_bytes);
+    const int P = N * 3;
+    Arena ar(ws, ws_bytes);
+    double* lv = ar.get<double>(32);
+    float* coef = ar.get<float>(64);
+    float* g[3];
+    for (int i = 0; i < 3; ++i) g[i] = ar.get<float>((size_t)P * H * W);
+    const size_t n1 = (size_t)P * ((H + 1) / 2) * ((W + 1) / 2);
+    float* dbuf[2] = {ar.get<float>(n1), ar.get<float>(n1)};
+    char* fws = (char*)ar.get<char>(0);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ms-ssim backward workspace too small");
+    LevelBufs<float> lb;
+    int rc = run_msssim<float, float, true>(a, b, N, H, W, fws, ws_bytes - ar.off, lv, s, &lb);
+    if (rc != IC_OK) return rc;
+    lb.a[0] = const_cast<float*>(a);
+    lb.b[0] = const_cast<float*>(b);
+    LevelParams<float> lp[5];
+    BwdCounts cnt;
+    for (int l = 0; l < 5; ++l) {
+        rc = fill_level<float>(lp[l], lb.h[l], lb.w[l], true);
+        IC_REQUIRE(rc == IC_OK, IC_ERR_INVALID, "ms-ssim backward: level %d too small", l);
+        cnt.count[l] = (double)lp[l].Ho * lp[l].Wo * P;
+    }
+    ProfScope ps(IC_PROF_MSSSIM, s, 1 + 5 * 2);
+    bwd_coef_kernel<<<1, 32, 0, s>>>(lv, cnt, grad_out, coef, value_out);
+    IC_CHECK_LAUNCH();
+    const float* d_next = nullptr;
+    for (int l = 4; l >= 0; --l) {
+        const LevelParams<float>& p = lp[l];
+        dim3 grid(cdiv(p.Wo, TW), cdiv(p.Ho, TH), P), block(TW, TH);
+        ssim_level_bwd_maps_kernel<<<grid, block, 0, s>>>(lb.a[l], lb.b[l], p, coef, l, g[0], g[1], g[2]);
+        IC_CHECK_LAUNCH();
+        float* out = (l == 0) ? d_b : dbuf[l & 1];
+        const int64_t total = (int64_t)P * p.H * p.W;
+        ssim_level_bwd_input_kernel<<<cdiv(total, 256), 256, 0, s>>>(lb.a[l], lb.b[l], p, g[0], g[1], g[2], d_next,
+                                                                     l < 4 ? lb.h[l + 1] : 0, l < 4 ? lb.w[l + 1] : 0, total, out);
+        IC_CHECK_LAUNCH();
+        d_next = out;
+    }
+    return IC_OK;
+}
+
+namespace {
 }  // namespace
 
 size_t msssim_workspace_bytes(int N, int H, int W, int is_double) {

@@ -504,6 +504,85 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
 
 inline int ew_grid(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); }
 
+
+// ------------------------------------------------------------------ context model in training mode
+// The latent volume is laid out depth-major: (D, N, H, W, C) -- one "image" per (depth slice, batch element) --
+// so that the (2,3,3) VALID conv3d of code/probclass.py:227-261 is two VALID conv2d passes over the contiguous
+// slice ranges [0, D-1) and [1, D) (filter depth 0 and 1), accumulated.
+// pad_for_probclass3d (code/probclass.py:268-292): q NCHW -> (C+4, N, h+8, w+8, 4), channel 0 = value, 1..3 = 0
+__global__ void pc_pad_kernel(const float* __restrict__ q, int N, int C, int h, int w, float pad_value, int64_t total,
+                              float4* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int Wp = w + 8, Hp = h + 8;
+    const int x = (int)(i % Wp);
+    int64_t r = i / Wp;
+    const int y = (int)(r % Hp);
+    r /= Hp;
+    const int n = (int)(r % N);
+    const int d = (int)(r / N);
+    float v = pad_value;
+    if (d >= 4 && y >= 4 && y < h + 4 && x >= 4 && x < w + 4)
+        v = q[(((int64_t)n * C + (d - 4)) * h + (y - 4)) * w + (x - 4)];
+    out[i] = make_float4(v, 0.f, 0.f, 0.f);
+}
+
+// softmax_cross_entropy_with_logits * log2(e) (code/probclass.py:99-104).  logits rows in (C, N, h, w) order with
+// Cs floats per row (first L valid); symbols / heatmap / bc in the reference's NCHW order.
+template <bool BWD>
+__global__ void pc_xent_kernel(const float* __restrict__ logits, int Cs, int L, const int64_t* __restrict__ symbols,
+                               const float* __restrict__ heatmap, int N, int C, int h, int w, float coef_real, float coef_mask,
+                               int64_t total, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // row in (C, N, h, w) order
+    if (i >= total) return;
+    const int64_t hw = (int64_t)h * w;
+    const int64_t yx = i % hw;
+    int64_t r = i / hw;
+    const int n = (int)(r % N);
+    const int c = (int)(r / N);
+    const int64_t j = ((int64_t)n * C + c) * hw + yx;                     // NCHW index
+    const float* lg = logits + i * Cs;
+    float m = lg[0];
+    for (int k = 1; k < L; ++k) m = fmaxf(m, lg[k]);
+    float s = 0.f;
+    for (int k = 0; k < L; ++k) s += expf(lg[k] - m);
+    const int sym = (int)symbols[j];
+    const float log2e = 1.4426950408889634f;
+    if (!BWD) {
+        out[j] = (logf(s) - (lg[sym] - m)) * log2e;
+    } else {
+        const float g = (coef_real + (heatmap ? coef_mask * heatmap[j] : coef_mask)) * log2e;
+        float* o = out + i * Cs;
+        for (int k = 0; k < Cs; ++k) o[k] = k < L ? g * (expf(lg[k] - m) / s - (k == sym ? 1.f : 0.f)) : 0.f;
+    }
+}
+
+// out[a][y][x][:] = in[a][y + crop][x + crop][:]   /   dx[a][y + crop][x + crop][:] += dy[a][y][x][:]
+template <bool BWD>
+__global__ void crop_kernel(const float4* __restrict__ src, int H, int W, int C4, int crop, int64_t total, float4* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over the cropped tensor (float4 units)
+    if (i >= total) return;
+    const int Ho = H - 2 * crop, Wo = W - 2 * crop;
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int x = (int)(r % Wo);
+    r /= Wo;
+    const int y = (int)(r % Ho);
+    const int64_t a = r / Ho;
+    const int64_t big = ((a * H + y + crop) * W + x + crop) * C4 + c;
+    if (!BWD) {
+        dst[i] = src[big];
+    } else {
+        float4 v = dst[big];
+        const float4 d = src[i];
+        v.x += d.x;
+        v.y += d.y;
+        v.z += d.z;
+        v.w += d.w;
+        dst[big] = v;
+    }
+}
+
 }  // namespace
 }  // namespace ic
 
@@ -724,6 +803,73 @@ int ic_nn_adam_step(float* d_w, const float* d_grad, float* d_m, float* d_v, int
     adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_w, d_grad, d_m, d_v, n, (float)lr_t, beta1, beta2, eps, l2, d_mask);
     IC_CHECK_LAUNCH();
     return IC_OK;
+}
+
+/* _normalize (code/autoencoder.py:136-144): x NCHW (uint8 or float32, [0,255]) -> normalised NHWC, 4 channels (last 0) */
+int ic_nn_normalize_fwd(const void* d_x_nchw, int x_is_u8, int N, int H, int W, float* d_out_nhwc4, void* stream) {
+    IC_REQUIRE(d_x_nchw && d_out_nhwc4 && N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_normalize_fwd: bad argument");
+    return launch_prep_input(d_x_nchw, x_is_u8, N, H, W, 1, d_out_nhwc4, (cudaStream_t)stream);
+}
+
+/* forward twin of ic_nn_hq_bwd: d_bn N,h,w,Cb -> NCHW z, heatmap3D, qbar, qhard, qsoft (each optional) and int64 symbols */
+int ic_nn_hq_fwd(const float* d_bn, int N, int h, int w, int C, int Cb, int heatmap, const float* d_centers, int L, float* d_z,
+                 float* d_heatmap, float* d_qbar, float* d_qhard, float* d_qsoft, int64_t* d_symbols, void* stream) {
+    IC_REQUIRE(d_bn && d_centers && L >= 1 && L <= 8 && Cb >= C + (heatmap ? 1 : 0), IC_ERR_INVALID, "ic_nn_hq_fwd: bad argument");
+    return launch_heatmap_quantize(d_bn, N, h, w, C, heatmap, d_centers, L, d_z, d_heatmap, d_qbar, d_qhard, d_symbols, nullptr,
+                                   d_qsoft, (cudaStream_t)stream, Cb);
+}
+
+int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pad_value, float* d_out, void* stream) {
+    IC_REQUIRE(d_q_nchw && d_out && N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_nn_pc_pad_fwd: bad argument");
+    const int64_t total = (int64_t)(C + 4) * N * (h + 8) * (w + 8);
+    pc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_q_nchw, N, C, h, w, pad_value, total, (float4*)d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_pc_xent_fwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, int N, int C, int h, int w, float* d_bc_nchw,
+                      void* stream) {
+    IC_REQUIRE(d_logits && d_symbols && d_bc_nchw && L >= 1 && Cs >= L, IC_ERR_INVALID, "ic_nn_pc_xent_fwd: bad argument");
+    const int64_t total = (int64_t)N * C * h * w;
+    pc_xent_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_logits, Cs, L, d_symbols, nullptr, N, C, h, w, 0.f, 0.f,
+                                                                            total, d_bc_nchw);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_pc_xent_bwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, const float* d_heatmap, int N, int C, int h,
+                      int w, float coef_real, float coef_mask, float* d_dlogits, void* stream) {
+    IC_REQUIRE(d_logits && d_symbols && d_dlogits && L >= 1 && Cs >= L, IC_ERR_INVALID, "ic_nn_pc_xent_bwd: bad argument");
+    const int64_t total = (int64_t)N * C * h * w;
+    pc_xent_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_logits, Cs, L, d_symbols, d_heatmap, N, C, h, w, coef_real,
+                                                                           coef_mask, total, d_dlogits);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_crop_fwd(const float* d_in, int64_t A, int H, int W, int C, int crop, float* d_out, void* stream) {
+    IC_REQUIRE(d_in && d_out && C % 4 == 0 && crop >= 0 && H > 2 * crop && W > 2 * crop, IC_ERR_INVALID, "ic_nn_crop_fwd: bad argument");
+    const int64_t total = A * (H - 2 * crop) * (W - 2 * crop) * (C / 4);
+    crop_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_in, H, W, C / 4, crop, total, (float4*)d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+int ic_nn_crop_bwd_add(const float* d_dy, int64_t A, int H, int W, int C, int crop, float* d_dx, void* stream) {
+    IC_REQUIRE(d_dy && d_dx && C % 4 == 0 && crop >= 0 && H > 2 * crop && W > 2 * crop, IC_ERR_INVALID, "ic_nn_crop_bwd_add: bad argument");
+    const int64_t total = A * (H - 2 * crop) * (W - 2 * crop) * (C / 4);
+    crop_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_dy, H, W, C / 4, crop, total, (float4*)d_dx);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+size_t ic_msssim_bwd_workspace_bytes(int N, int H, int W) { return msssim_bwd_workspace_bytes(N, H, W); }
+
+int ic_msssim_tf_bwd(const float* d_img1, const float* d_img2, int N, int H, int W, float grad_out, float* d_dimg2, float* d_value,
+                     void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_img1 && d_img2 && d_dimg2 && d_workspace, IC_ERR_INVALID, "ic_msssim_tf_bwd: NULL argument");
+    IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_msssim_tf_bwd: bad shape");
+    return msssim_tf_bwd(d_img1, d_img2, N, H, W, grad_out, d_dimg2, d_value, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -44,20 +44,22 @@ def conv2d_fwd(x, w, stride=1, transposed=False, valid=False):
     return y
 
 
-def conv2d_bwd_data(dy, w, x_shape, stride=1, transposed=False, valid=False):
+def conv2d_bwd_data(dy, w, x_shape, stride=1, transposed=False, valid=False, out=None):
     g, oshape = _geo(x_shape, w.shape, stride, transposed, valid)
     assert tuple(dy.shape) == oshape, '{} != {}'.format(tuple(dy.shape), oshape)
-    dx = torch.empty(tuple(x_shape), dtype=torch.float32, device=dy.device)
+    dx = torch.empty(tuple(x_shape), dtype=torch.float32, device=dy.device) if out is None else _f32(out)
+    assert tuple(dx.shape) == tuple(x_shape)
     ws = _workspace(_lib.lib().ic_nn_conv2d_workspace_bytes(*g))
     _lib.check(_lib.lib().ic_nn_conv2d_bwd_data(_lib.ptr(_f32(dy)), _lib.ptr(_f32(w)), *g, _lib.ptr(dx), _lib.ptr(ws), ws.numel(),
                                                _lib.stream_ptr()))
     return dx
 
 
-def conv2d_bwd_filter(x, dy, w_shape, stride=1, transposed=False, valid=False):
+def conv2d_bwd_filter(x, dy, w_shape, stride=1, transposed=False, valid=False, out=None):
     g, oshape = _geo(x.shape, w_shape, stride, transposed, valid)
     assert tuple(dy.shape) == oshape, '{} != {}'.format(tuple(dy.shape), oshape)
-    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device) if out is None else out
+    assert tuple(dw.shape) == tuple(w_shape)
     ws = _workspace(_lib.lib().ic_nn_conv2d_workspace_bytes(*g))
     _lib.check(_lib.lib().ic_nn_conv2d_bwd_filter(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), *g, _lib.ptr(dw), _lib.ptr(ws), ws.numel(),
                                                  _lib.stream_ptr()))
@@ -82,13 +84,13 @@ def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None
     return out, mean, invstd
 
 
-def bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu=False, use_stats=True):
+def bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu=False, use_stats=True, dgamma=None, dbeta=None):
     """-> (dx, dgamma, dbeta)"""
     C = x.shape[-1]
     M = x.numel() // C
     dx = torch.empty_like(x)
-    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if dgamma is None else dgamma
+    dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if dbeta is None else dbeta
     ws = _workspace(_lib.lib().ic_nn_bn_workspace_bytes(M, C))
     _lib.check(_lib.lib().ic_nn_bn_train_bwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)),
                                             int(relu), int(use_stats), _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(dx),
@@ -96,11 +98,33 @@ def bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu=False, use_stats=True):
     return dx, dgamma, dbeta
 
 
-def hq_bwd(bn, C, heatmap, centers, dq, dhm=None):
+def normalize_fwd(x):
+    """x N,3,H,W uint8 or float32 in [0,255] -> normalised N,H,W,4 (code/autoencoder.py:136-144)"""
+    assert x.is_cuda and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3 and x.dtype in (torch.uint8, torch.float32)
+    N, _, H, W = x.shape
+    out = torch.empty((N, H, W, 4), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ic_nn_normalize_fwd(_lib.ptr(x), int(x.dtype == torch.uint8), N, H, W, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def hq_fwd(bn, C, heatmap, centers):
+    """bn N,h,w,Cb -> dict of NCHW tensors z, heatmap, qbar, qhard, qsoft (float32) and symbols (int64)"""
+    N, h, w, Cb = bn.shape
+    o = {k: torch.empty((N, C, h, w), dtype=torch.float32, device=bn.device) for k in ('z', 'heatmap', 'qbar', 'qhard', 'qsoft')}
+    o['symbols'] = torch.empty((N, C, h, w), dtype=torch.int64, device=bn.device)
+    _lib.check(_lib.lib().ic_nn_hq_fwd(_lib.ptr(_f32(bn)), N, h, w, C, Cb, int(heatmap), _lib.ptr(_f32(centers)), centers.numel(),
+                                      _lib.ptr(o['z']), _lib.ptr(o['heatmap']), _lib.ptr(o['qbar']), _lib.ptr(o['qhard']),
+                                      _lib.ptr(o['qsoft']), _lib.ptr(o['symbols']), _lib.stream_ptr()))
+    if not heatmap:
+        o['heatmap'] = None
+    return o
+
+
+def hq_bwd(bn, C, heatmap, centers, dq, dhm=None, dcenters=None):
     """bn N,h,w,Cb; dq N,h,w,C; dhm N,C,h,w or None -> (dbn N,h,w,Cb, dcenters (L,))"""
     N, h, w, Cb = bn.shape
     dbn = torch.empty_like(bn)
-    dcent = torch.empty(centers.numel(), dtype=torch.float32, device=bn.device)
+    dcent = torch.empty(centers.numel(), dtype=torch.float32, device=bn.device) if dcenters is None else dcenters
     ws = _workspace(_lib.lib().ic_nn_hq_workspace_bytes(N * h * w))
     _lib.check(_lib.lib().ic_nn_hq_bwd(_lib.ptr(_f32(bn)), N, h, w, C, Cb, int(heatmap), _lib.ptr(_f32(centers)), centers.numel(),
                                       _lib.ptr(_f32(dq)), _lib.ptr(dhm), _lib.ptr(dbn), _lib.ptr(dcent), _lib.ptr(ws), ws.numel(),
@@ -149,8 +173,8 @@ def add(x, y):
     return axpby(1.0, x, 1.0, y)
 
 
-def mul(x, y):
-    out = torch.empty_like(x)
+def mul(x, y, out=None):
+    out = torch.empty_like(x) if out is None else out
     _lib.check(_lib.lib().ic_nn_mul(_lib.ptr(_f32(x)), _lib.ptr(_f32(y)), x.numel(), _lib.ptr(out), _lib.stream_ptr()))
     return out
 
@@ -160,3 +184,59 @@ def adam_step(w, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, l2=0.0,
     _lib.check(_lib.lib().ic_nn_adam_step(_lib.ptr(_f32(w)), _lib.ptr(_f32(grad)), _lib.ptr(_f32(m)), _lib.ptr(_f32(v)), w.numel(),
                                          float(lr), float(beta1), float(beta2), float(eps), int(step), float(l2), _lib.ptr(mask),
                                          _lib.stream_ptr()))
+
+
+def pc_pad_fwd(q, pad_value):
+    """pad_for_probclass3d (code/probclass.py:268-292): q N,C,h,w -> depth-major (C+4, N, h+8, w+8, 4), channel 0 = value"""
+    N, C, h, w = q.shape
+    out = torch.empty((C + 4, N, h + 8, w + 8, 4), dtype=torch.float32, device=q.device)
+    _lib.check(_lib.lib().ic_nn_pc_pad_fwd(_lib.ptr(_f32(q)), N, C, h, w, float(pad_value), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def pc_xent_fwd(logits, L, symbols):
+    """logits (C, N, h, w, Cs) -> bits N,C,h,w (code/probclass.py:99-104)"""
+    C, N, h, w, Cs = logits.shape
+    assert symbols.dtype == torch.int64 and symbols.is_contiguous() and tuple(symbols.shape) == (N, C, h, w)
+    bc = torch.empty((N, C, h, w), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().ic_nn_pc_xent_fwd(_lib.ptr(_f32(logits)), Cs, L, _lib.ptr(symbols), N, C, h, w, _lib.ptr(bc), _lib.stream_ptr()))
+    return bc
+
+
+def pc_xent_bwd(logits, L, symbols, heatmap, coef_real, coef_mask):
+    """-> d logits (C, N, h, w, Cs) for the upstream gradient (coef_real + coef_mask * heatmap) per symbol"""
+    C, N, h, w, Cs = logits.shape
+    d = torch.empty_like(logits)
+    _lib.check(_lib.lib().ic_nn_pc_xent_bwd(_lib.ptr(_f32(logits)), Cs, L, _lib.ptr(symbols), _lib.ptr(heatmap), N, C, h, w,
+                                           float(coef_real), float(coef_mask), _lib.ptr(d), _lib.stream_ptr()))
+    return d
+
+
+def crop_fwd(x, crop):
+    """x (..., H, W, C) -> x[..., crop:-crop, crop:-crop, :]"""
+    H, W, C = x.shape[-3:]
+    A = x.numel() // (H * W * C)
+    out = torch.empty(tuple(x.shape[:-3]) + (H - 2 * crop, W - 2 * crop, C), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ic_nn_crop_fwd(_lib.ptr(_f32(x)), A, H, W, C, crop, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def crop_bwd_add(dy, dx, crop):
+    """dx[..., crop:-crop, crop:-crop, :] += dy (in place)"""
+    H, W, C = dx.shape[-3:]
+    A = dx.numel() // (H * W * C)
+    assert dy.numel() == A * (H - 2 * crop) * (W - 2 * crop) * C
+    _lib.check(_lib.lib().ic_nn_crop_bwd_add(_lib.ptr(_f32(dy)), A, H, W, C, crop, _lib.ptr(_f32(dx)), _lib.stream_ptr()))
+    return dx
+
+
+def msssim_tf_bwd(img1, img2, grad_out):
+    """gradient of ms_ssim.MultiScaleSSIM(img1, img2) w.r.t. img2, times grad_out -> (d img2, value (1,) tensor)"""
+    assert img1.shape == img2.shape and img1.dim() == 4 and img1.shape[1] == 3
+    N, _, H, W = img1.shape
+    d = torch.empty_like(img2)
+    val = torch.empty(1, dtype=torch.float32, device=img1.device)
+    ws = _workspace(_lib.lib().ic_msssim_bwd_workspace_bytes(N, H, W))
+    _lib.check(_lib.lib().ic_msssim_tf_bwd(_lib.ptr(_f32(img1)), _lib.ptr(_f32(img2)), N, H, W, float(grad_out), _lib.ptr(d),
+                                          _lib.ptr(val), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return d, val

@@ -56,6 +56,18 @@ class _Network3D(object):
         """code/probclass.py:59-61"""
         return 0 if not self.config.use_centers_for_padding else ae.get_centers_variable()[0]
 
+    _pad_cache = (None, None)
+
+    def _pad_float(self, pad_value):
+        """The C ABI takes the pad value as a host float; a device scalar (centers[0]) is read back once per
+        version of its storage, not once per call (a read-back per call would drain the stream every step)."""
+        if not torch.is_tensor(pad_value):
+            return float(pad_value)
+        key = (pad_value.data_ptr(), pad_value._version, pad_value.device)
+        if self._pad_cache[0] != key:
+            self._pad_cache = (key, float(pad_value))
+        return self._pad_cache[1]
+
     # -- weights -----------------------------------------------------------
     def variable_names(self):
         L = _lib.lib()
@@ -112,7 +124,7 @@ class _Network3D(object):
         bits = torch.empty_like(q)
         sums = torch.empty(N, dtype=torch.float64, device=q.device)
         ws = self._workspace(N, C, h, w)
-        _lib.check(_lib.lib().ic_pc_bitcost_fwd(self._handle, _lib.ptr(q), _lib.ptr(sym), float(pad_value), N, C, h, w,
+        _lib.check(_lib.lib().ic_pc_bitcost_fwd(self._handle, _lib.ptr(q), _lib.ptr(sym), self._pad_float(pad_value), N, C, h, w,
                                                 _lib.ptr(bits), _lib.ptr(sums), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr()))
         self.last_bits_per_image = sums

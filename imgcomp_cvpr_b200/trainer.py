@@ -1,0 +1,521 @@
+"""The training step of code/train.py (cfg 3: forward + MS-SSIM / rate loss + backward + two Adam groups) on the
+float32 training primitives of libimgcomp_b200.so (include/imgcomp_b200.h, ic_nn_* / ic_msssim_tf_bwd).
+
+What the reference builds as a TF graph and differentiates with tf.gradients (code/train.py:86-132,303-349):
+
+    enc   = ae.encode(x, is_training=True)                                   autoencoder.py:218-244
+    x_out = ae.decode(enc.qbar, is_training=True)                            :246-268
+    bc    = pc.bitcost(stop_gradient(enc.qbar), enc.symbols, True, centers[0])   train.py:103-105
+    loss  = K_ms_ssim (1 - MS-SSIM(x, x_out)) + beta max(0.5 (mean(bc heatmap) + mean(bc)) - H_target, 0) + l2 terms
+    Adam_AE (lr_ae, staircase decay) on the autoencoder variables, Adam_PC (lr_pc) on probclass3d/*
+
+is executed here eagerly: every op below is one or two kernels of the library, a small tape records the backward
+closures in the order of the reference graph, parameters / gradients / Adam moments live in flat per-group buffers
+(one Adam launch per group).  torch tensors are containers only.  No CPU fallback.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, nn, weights as weights_mod
+
+ARCH_N = weights_mod.ARCH_N
+
+
+def _ceil4(n):
+    return (n + 3) // 4 * 4
+
+
+def _pc_masks():
+    """create_first_mask / create_other_mask of code/probclass.py:150-176 for kernel_size 3 -> two (2,3,3) 0/1 arrays:
+    filter depth 0 (previous channel): all 9 taps; depth 1 (current channel): row 0 and (1,0) [first] (+ (1,1) [other])."""
+    first = np.zeros((2, 3, 3), np.float32)
+    first[0] = 1
+    first[1, 0, :] = 1
+    first[1, 1, 0] = 1
+    other = first.copy()
+    other[1, 1, 1] = 1
+    return first, other
+
+
+class _Flat(object):
+    """Named float32 tensors packed into one flat buffer (+ gradient and Adam moment buffers of the same layout)."""
+
+    def __init__(self, with_opt=True):
+        self.entries = []          # (key, device-shape ndarray)
+        self.with_opt = with_opt
+
+    def add(self, key, arr):
+        self.entries.append((key, np.ascontiguousarray(arr, np.float32)))
+
+    def finish(self, device):
+        off, self.slots = 0, {}
+        for key, arr in self.entries:
+            self.slots[key] = (off, arr.shape)
+            off += (arr.size + 63) // 64 * 64           # 256-byte aligned views (float4 loads in the kernels)
+        host = np.zeros(max(off, 64), np.float32)
+        for key, arr in self.entries:
+            o, _ = self.slots[key]
+            host[o:o + arr.size] = arr.ravel()
+        self.w = torch.from_numpy(host).to(device)
+        if self.with_opt:
+            self.g = torch.zeros_like(self.w)
+            self.m = torch.zeros_like(self.w)
+            self.v = torch.zeros_like(self.w)
+        del self.entries
+
+    def view(self, buf, key):
+        o, shape = self.slots[key]
+        return buf[o:o + int(np.prod(shape))].view(shape)
+
+
+class _Tape(object):
+    def __init__(self):
+        self.fns, self.grads = [], {}
+
+    def add(self, fn):
+        self.fns.append(fn)
+
+    def acc(self, t, g, owned=False):
+        """accumulate g into the gradient of t; tensors that are not `owned` are never modified in place"""
+        k = id(t)
+        if k not in self.grads:
+            self.grads[k] = (t, g, owned)
+            return
+        _, old, old_owned = self.grads[k]
+        if old_owned:
+            nn.axpby(1.0, old, 1.0, g, out=old)
+        elif owned:
+            nn.axpby(1.0, g, 1.0, old, out=g)
+            self.grads[k] = (t, g, True)
+        else:
+            self.grads[k] = (t, nn.add(old, g), True)
+
+    def pop(self, t):
+        e = self.grads.pop(id(t), None)
+        return None if e is None else e[1]
+
+    def backward(self):
+        for fn in reversed(self.fns):
+            fn()
+        self.fns = []
+
+
+def ae_layer_table(C, B):
+    """(scope, k, stride, cin, cout, transposed) of every autoencoder conv (code/autoencoder.py:218-268)"""
+    n = ARCH_N
+    E, D = 'autoencoder/encoder', 'autoencoder/decoder'
+    enc_res, dec_res = weights_mod.conv_scopes(B)
+    t = [(E + '/h1', 5, 2, 3, n // 2, False), (E + '/h2', 5, 2, n // 2, n, False)]
+    t += [(s, 3, 1, n, n, False) for s in enc_res]
+    t += [(E + '/to_bn', 5, 2, n, C + 1, False), (D + '/from_bn', 3, 2, C, n, True)]
+    t += [(s, 3, 1, n, n, False) for s in dec_res]
+    t += [(D + '/h12', 5, 2, n, n // 2, True), (D + '/h13', 5, 2, n // 2, 3, True)]
+    return t
+
+
+PC_LAYERS = (('probclass3d/logits/conv3d_conv0_mask', 'first'), ('probclass3d/logits/res1/conv3d_conv1_mask', 'other'),
+             ('probclass3d/logits/res1/conv3d_conv2_mask', 'other'), ('probclass3d/logits/conv3d_conv2_mask', 'other'))
+
+
+class Trainer(object):
+    """One object = the variables of code/train.py's graph + its train_op.
+
+        tr = Trainer(ae_config, pc_config, weights, num_itr_per_epoch)
+        out = tr.step(x)            # x N,3,H,W uint8/float32 CUDA; one sess.run([train_op, ...]) of the reference
+        W = tr.weights()            # dict TF variable name -> ndarray (loads into autoencoder / probclass unchanged)
+    """
+
+    def __init__(self, ae_config, pc_config, weights, num_itr_per_epoch=1000, device='cuda'):
+        _lib.require_device()
+        assert ae_config.arch == 'CVPR' and pc_config.arch == 'res_shallow'
+        assert ae_config.normalization == 'FIXED'
+        assert ae_config.optimizer == 'ADAM' and pc_config.optimizer == 'ADAM', 'only the Adam of the published configs is built'
+        assert not pc_config.learn_pad_var
+        self.ae_config, self.pc_config = ae_config, pc_config
+        self.C, self.B, self.L = ae_config.num_chan_bn, ae_config.arch_param_B, ae_config.num_centers
+        self.k = pc_config.arch_param__k
+        self.heatmap = bool(ae_config.heatmap)
+        self.num_itr_per_epoch = num_itr_per_epoch
+        self.global_step = 0
+        self.device = torch.device(device)
+        self.table = ae_layer_table(self.C, self.B)
+        self._tr = {s: tr for s, _, _, _, _, tr in self.table}
+        self._shape = {s: (k, ci, co) for s, k, _, ci, co, _ in self.table}
+        self._stride = {s: st for s, _, st, _, _, _ in self.table}
+        # parameter groups: (l2 factor, which optimiser)
+        self.groups = {'ae_w': _Flat(), 'ae_bn': _Flat(), 'ae_centers': _Flat(), 'pc_w': _Flat(), 'pc_b': _Flat()}
+        self.stats = _Flat(with_opt=False)          # BN moving averages (not optimised)
+        self.consts = _Flat(with_opt=False)
+        for s, k, _, ci, co, tr in self.table:
+            w = np.asarray(weights[s + '/weights'], np.float32)
+            if tr:
+                assert w.shape == (k, k, co, ci), (s, w.shape)
+                w = w.transpose(0, 1, 3, 2)                               # -> [kh][kw][Cin of the op][Cout of the op]
+            assert w.shape == (k, k, ci, co), (s, w.shape)
+            wp = np.zeros((k, k, _ceil4(ci), _ceil4(co)), np.float32)
+            wp[:, :, :ci, :co] = w
+            self.groups['ae_w'].add(s + '/weights', wp)
+            for name, fill, grp in (('gamma', 0.0, self.groups['ae_bn']), ('beta', 0.0, self.groups['ae_bn']),
+                                    ('moving_mean', 0.0, self.stats), ('moving_variance', 1.0, self.stats)):
+                v = np.full(_ceil4(co), fill, np.float32)
+                v[:co] = np.asarray(weights[s + '/BatchNorm/' + name], np.float32)
+                grp.add(s + '/BatchNorm/' + name, v)
+        self.groups['ae_centers'].add('autoencoder/encoder/centers', np.asarray(weights['autoencoder/encoder/centers'], np.float32))
+        first, other = _pc_masks()
+        cin = 1
+        for i, (s, mk) in enumerate(PC_LAYERS):
+            cout = self.k if i < 3 else self.L
+            w = np.asarray(weights[s + '/weights'], np.float32)
+            assert w.shape == (2, 3, 3, cin, cout), (s, w.shape)
+            wp = np.zeros((2, 3, 3, _ceil4(cin), _ceil4(cout)), np.float32)
+            wp[..., :cin, :cout] = w
+            self.groups['pc_w'].add(s + '/weights', wp)
+            b = np.zeros(_ceil4(cout), np.float32)
+            b[:cout] = np.asarray(weights[s + '/biases'], np.float32)
+            self.groups['pc_b'].add(s + '/biases', b)
+            m = np.zeros_like(wp)
+            m[..., :cin, :cout] = (first if mk == 'first' else other)[:, :, :, None, None]
+            self.consts.add(s + '/mask', m)
+            cin = cout
+        self.consts.add('ones', np.ones(1024, np.float32))
+        self.consts.add('zeros', np.zeros(1024, np.float32))
+        for g in list(self.groups.values()) + [self.stats, self.consts]:
+            g.finish(self.device)
+        self._group_of = {}
+        for gname, g in self.groups.items():
+            for key in g.slots:
+                self._group_of[key] = gname
+        self.tape = None
+        self._adam_t = 0
+
+    # ------------------------------------------------------------------ parameter access
+    def _w(self, key):
+        g = self.groups[self._group_of[key]]
+        return g.view(g.w, key)
+
+    def _g(self, key):
+        g = self.groups[self._group_of[key]]
+        return g.view(g.g, key)
+
+    def _const(self, key, n=None):
+        v = self.consts.view(self.consts.w, key)
+        return v if n is None else v[:n]
+
+    def _export(self, buf_name):
+        out = {}
+        for s, k, _, ci, co, tr in self.table:
+            g = self.groups['ae_w']
+            w = g.view(getattr(g, buf_name), s + '/weights')[:, :, :ci, :co].cpu().numpy()
+            out[s + '/weights'] = np.ascontiguousarray(w.transpose(0, 1, 3, 2) if tr else w)
+            g = self.groups['ae_bn']
+            for name in ('gamma', 'beta'):
+                out[s + '/BatchNorm/' + name] = g.view(getattr(g, buf_name), s + '/BatchNorm/' + name)[:co].cpu().numpy()
+        g = self.groups['ae_centers']
+        out['autoencoder/encoder/centers'] = g.view(getattr(g, buf_name), 'autoencoder/encoder/centers').cpu().numpy()
+        cin = 1
+        for i, (s, _) in enumerate(PC_LAYERS):
+            cout = self.k if i < 3 else self.L
+            g = self.groups['pc_w']
+            out[s + '/weights'] = g.view(getattr(g, buf_name), s + '/weights')[..., :cin, :cout].cpu().numpy()
+            g = self.groups['pc_b']
+            out[s + '/biases'] = g.view(getattr(g, buf_name), s + '/biases')[:cout].cpu().numpy()
+            cin = cout
+        return out
+
+    def weights(self):
+        """dict TF variable name -> ndarray, in the reference's shapes"""
+        out = self._export('w')
+        for s, _, _, _, co, _ in self.table:
+            for name in ('moving_mean', 'moving_variance'):
+                out[s + '/BatchNorm/' + name] = self.stats.view(self.stats.w, s + '/BatchNorm/' + name)[:co].cpu().numpy()
+        return out
+
+    def gradients(self):
+        """d total_loss / d variable of the last forward_backward(), WITHOUT the l2 terms (those are added inside the
+        Adam kernel as l2 * w), same naming / shapes as weights()"""
+        return self._export('g')
+
+    # ------------------------------------------------------------------ ops (forward + recorded backward)
+    def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None):
+        y = nn.conv2d_fwd(x, w, stride, transposed, valid)
+        if self.tape is not None:
+            tape = self.tape
+
+            def bwd():
+                dy = tape.pop(y)
+                if dy is None:
+                    return
+                nn.conv2d_bwd_filter(x, dy, w.shape, stride, transposed, valid, out=gw)
+                if mask is not None:
+                    nn.mul(gw, mask, out=gw)
+                if need_dx:
+                    tape.acc(x, nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid), owned=True)
+            tape.add(bwd)
+        return y
+
+    def _bn(self, x, scope, relu, res1=None, res2=None):
+        gamma, beta = self._w(scope + '/BatchNorm/gamma'), self._w(scope + '/BatchNorm/beta')
+        mm = self.stats.view(self.stats.w, scope + '/BatchNorm/moving_mean')
+        mv = self.stats.view(self.stats.w, scope + '/BatchNorm/moving_variance')
+        if self.is_training:
+            upd = self.update_moving
+            out, mean, invstd = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, mm if upd else None, mv if upd else None)
+        else:           # moving statistics (code/autoencoder.py:115-125 with is_training=False)
+            mean, invstd = mm, torch.rsqrt(mv + nn.BN_EPS)
+            out, _, _ = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, stats=(mean, invstd))
+        if self.tape is not None:
+            tape, training = self.tape, self.is_training
+
+            def bwd():
+                dy = tape.pop(out)
+                if dy is None:
+                    return
+                dx, _, _ = nn.bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu, use_stats=training,
+                                           dgamma=self._g(scope + '/BatchNorm/gamma'), dbeta=self._g(scope + '/BatchNorm/beta'))
+                tape.acc(x, dx, owned=True)
+                if res1 is not None:
+                    tape.acc(res1, dy)
+                if res2 is not None:
+                    tape.acc(res2, dy)
+            tape.add(bwd)
+        return out
+
+    def _slim_conv(self, x, scope, relu, res1=None, res2=None, need_dx=True):
+        """slim.conv2d / conv2d_transpose under _batch_norm_scope: conv (no bias) -> BN -> activation (+ fused adds)"""
+        y = self._conv(x, self._w(scope + '/weights'), self._g(scope + '/weights'), self._stride[scope], self._tr[scope],
+                       need_dx=need_dx)
+        return self._bn(y, scope, relu, res1, res2)
+
+    def _res_stack(self, net, prefix, tag, final_scope):
+        """15 residual blocks with a skip every 3, a final block without ReLU and the long skip
+        (code/autoencoder.py:225-234,253-262,274-287); the adds are fused into the second conv's BN kernel."""
+        r0 = net
+        for b in range(self.B):
+            rb = net
+            for i in (1, 2, 3):
+                s = '{}/res_block_{}_{}/{}_{}_{}'.format(prefix, tag, b, tag, b, i)
+                y = self._slim_conv(net, s + '/conv1', True)
+                net = self._slim_conv(y, s + '/conv2', False, res1=net, res2=rb if i == 3 else None)
+        y = self._slim_conv(net, prefix + '/' + final_scope + '/conv1', False)
+        return self._slim_conv(y, prefix + '/' + final_scope + '/conv2', False, res1=net, res2=r0)
+
+    def _encode(self, x):
+        E = 'autoencoder/encoder'
+        net = nn.normalize_fwd(x)
+        net = self._slim_conv(net, E + '/h1', True, need_dx=False)
+        net = self._slim_conv(net, E + '/h2', True)
+        net = self._res_stack(net, E, 'enc', 'res_block_enc_final')
+        bn = self._slim_conv(net, E + '/to_bn', False)
+        centers = self._w(E + '/centers')
+        enc = nn.hq_fwd(bn, self.C, self.heatmap, centers)
+        enc['bn'] = bn
+        return enc
+
+    def _decode(self, q_nhwc):
+        D = 'autoencoder/decoder'
+        net = self._slim_conv(q_nhwc, D + '/from_bn', True)
+        net = self._res_stack(net, D, 'dec', 'dec_after_res')
+        net = self._slim_conv(net, D + '/h12', True)
+        v = self._slim_conv(net, D + '/h13', False)
+        x_out = nn.denorm_clip_fwd(v)
+        if self.tape is not None:
+            tape = self.tape
+
+            def bwd():
+                d = tape.pop(x_out)
+                if d is not None:
+                    tape.acc(v, nn.denorm_clip_bwd(v, d), owned=True)
+            tape.add(bwd)
+        return x_out
+
+    def _conv3d(self, x, scope, need_dx=True):
+        """masked (2,3,3) VALID conv3d (code/probclass.py:227-261) on the depth-major volume x (D, N, H, W, Cin):
+        two VALID conv2d passes (filter depth 0 over slices [0, D-1), depth 1 over [1, D)), accumulated."""
+        w, gw, mask = self._w(scope + '/weights'), self._g(scope + '/weights'), self._const(scope + '/mask')
+        weff = nn.mul(w, mask)
+        D, N, H, W, Ci = x.shape
+        xa, xb = x[:D - 1].reshape(-1, H, W, Ci), x[1:].reshape(-1, H, W, Ci)
+        y = nn.conv2d_fwd(xa, weff[0], valid=True)
+        y = nn.axpby(1.0, y, 1.0, nn.conv2d_fwd(xb, weff[1], valid=True), out=y)
+        y = y.view(D - 1, N, H - 2, W - 2, w.shape[-1])
+        if self.tape is not None:
+            tape = self.tape
+
+            def bwd():
+                dy = tape.pop(y)
+                if dy is None:
+                    return
+                dy4 = dy.reshape(-1, H - 2, W - 2, w.shape[-1])
+                nn.conv2d_bwd_filter(xa, dy4, weff[0].shape, valid=True, out=gw[0])
+                nn.conv2d_bwd_filter(xb, dy4, weff[1].shape, valid=True, out=gw[1])
+                nn.mul(gw, mask, out=gw)
+                if need_dx:
+                    dx = torch.empty_like(x)
+                    nn.conv2d_bwd_data(dy4, weff[0], xa.shape, valid=True, out=dx[:D - 1].reshape(-1, H, W, Ci))
+                    db = nn.conv2d_bwd_data(dy4, weff[1], xb.shape, valid=True).view(D - 1, N, H, W, Ci)
+                    if D > 2:
+                        nn.axpby(1.0, dx[1:D - 1], 1.0, db[:D - 2], out=dx[1:D - 1])
+                    nn.axpby(1.0, db[D - 2], out=dx[D - 1])
+                    tape.acc(x, dx, owned=True)
+            tape.add(bwd)
+        return y
+
+    def _bias_act(self, x, scope, relu, res1=None):
+        """tf.nn.bias_add + activation (code/probclass.py:259-261), + the residual add of the 3-D block"""
+        C = x.shape[-1]
+        bias, ones, zeros = self._w(scope + '/biases'), self._const('ones', C), self._const('zeros', C)
+        out, _, _ = nn.bn_train_fwd(x, ones, bias, relu, res1, None, stats=(zeros, ones))
+        if self.tape is not None:
+            tape = self.tape
+
+            def bwd():
+                dy = tape.pop(out)
+                if dy is None:
+                    return
+                dx, _, _ = nn.bn_train_bwd(x, dy, ones, bias, zeros, ones, relu, use_stats=False, dbeta=self._g(scope + '/biases'))
+                tape.acc(x, dx, owned=True)
+                if res1 is not None:
+                    tape.acc(res1, dy)
+            tape.add(bwd)
+        return out
+
+    def _pc_logits(self, q_nchw, pad_value):
+        """pad_for_probclass3d + _ResShallow._logits (code/probclass.py:214-221,268-292) -> logits (C, N, h, w, ceil4(L))"""
+        S = [s for s, _ in PC_LAYERS]
+        x0 = nn.pc_pad_fwd(q_nchw, pad_value)
+        a0 = self._bias_act(self._conv3d(x0, S[0], need_dx=False), S[0], True)
+        a1 = self._bias_act(self._conv3d(a0, S[1]), S[1], True)
+        c2 = self._conv3d(a1, S[2])
+        skip_src = a0[2:]
+        skip = nn.crop_fwd(skip_src, 2)                                    # x[:, 2:, 2:-2, 2:-2, :]  (:185-196)
+        if self.tape is not None:
+            tape = self.tape
+
+            def bwd():
+                d = tape.pop(skip)
+                if d is not None:
+                    g0 = torch.zeros_like(a0)
+                    nn.crop_bwd_add(d, g0[2:], 2)
+                    tape.acc(a0, g0, owned=True)
+            tape.add(bwd)
+        net = self._bias_act(c2, S[2], False, res1=skip)
+        return self._bias_act(self._conv3d(net, S[3]), S[3], True)
+
+    # ------------------------------------------------------------------ the graph of code/train.py:86-132
+    def forward_backward(self, x, is_training=True, update_moving=False, backward=True):
+        """-> dict of loss components (floats) and tensors; gradients are left in the groups' g buffers."""
+        cfg = self.ae_config
+        assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        assert H % 8 == 0 and W % 8 == 0
+        self.is_training, self.update_moving = is_training, update_moving
+        self.tape = tape = _Tape() if backward else None
+        centers = self._w('autoencoder/encoder/centers')
+        # pc.auto_pad_value(ae) = centers[0] (code/probclass.py:59-61); read before anything is enqueued (idle stream)
+        cvals = centers.detach().cpu().numpy().astype(np.float64)
+        pad_value = float(cvals[0]) if self.pc_config.use_centers_for_padding else 0.0
+        enc = self._encode(x)
+        n_enc = len(tape.fns) if backward else 0
+        q_nhwc = nn.nchw_to_nhwc(enc['qbar'])
+        x_out = self._decode(q_nhwc)
+        logits = self._pc_logits(enc['qbar'], pad_value)                 # stop_gradient(qbar): no backward into q
+        bc = nn.pc_xent_fwd(logits, self.L, enc['symbols'])
+        # ---- losses (code/train.py:303-336, 352-431)
+        xf = x if x.dtype == torch.float32 else x.float()
+        Lb = _lib.lib()
+        sums = torch.empty(8, dtype=torch.float64, device=x.device)
+        ws = torch.empty(Lb.ic_loss_workspace_bytes(), dtype=torch.uint8, device=x.device)
+        hm = enc['heatmap']
+        _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(bc), _lib.ptr(hm), bc.numel(), _lib.ptr(sums), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        gw = self.groups['ae_w']
+        _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(gw.w), _lib.ptr(gw.w), gw.w.numel(), _lib.ptr(sums[2:]), _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr()))
+        gp = self.groups['pc_w']
+        _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(gp.w), _lib.ptr(gp.w), gp.w.numel(), _lib.ptr(sums[4:]), _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr()))
+        if cfg.distortion_to_minimize != 'ms_ssim':
+            raise NotImplementedError('only distortion_to_minimize = ms_ssim (the published configs) has a backward kernel')
+        d_xout, msssim = nn.msssim_tf_bwd(xf, x_out, -float(cfg.K_ms_ssim))       # d/dx_out of K (1 - MS-SSIM)
+        host = sums.cpu().tolist()                                       # the step's one read-back (loss scalars)
+        msssim = float(msssim.item())
+        n = bc.numel()
+        H_real = host[0] / n
+        H_mask = host[1] / n if hm is not None else H_real
+        H_soft = 0.5 * (H_mask + H_real)
+        pc_loss = cfg.beta * max(H_soft - cfg.H_target, 0.0)
+        d_loss = cfg.K_ms_ssim * (1.0 - msssim)
+        reg_enc_dec = cfg.regularization_factor * 0.5 * host[3]
+        if cfg.regularization_factor_centers != 0:
+            reg_enc_dec += cfg.regularization_factor_centers * 0.5 * float((cvals ** 2).sum())
+        rf_pc = self.pc_config.regularization_factor
+        reg_pc = 0.0 if rf_pc is None else rf_pc * 0.5 * host[5]
+        out = dict(total_loss=d_loss + pc_loss + reg_enc_dec + reg_pc, d_loss_scaled=d_loss, pc_loss=pc_loss, H_real=H_real,
+                   H_mask=H_mask, ms_ssim=msssim, reg=reg_enc_dec + reg_pc, bpp=host[0] / (N * H * W),
+                   tensors=dict(bc=bc, heatmap=hm, x_out=x_out, symbols=enc['symbols'], qbar=enc['qbar'], z=enc['z']))
+        if not backward:
+            return out
+        # ---- backward, in reverse order of the graph
+        coef = cfg.beta * 0.5 / n if H_soft > cfg.H_target else 0.0
+        tape.acc(logits, nn.pc_xent_bwd(logits, self.L, enc['symbols'], hm, coef, coef), owned=True)
+        tape.acc(x_out, d_xout, owned=True)
+        bn = enc['bn']
+
+        def hq_bwd():
+            dq = tape.pop(q_nhwc)
+            dhm = nn.axpby(coef, bc) if (hm is not None and coef != 0.0) else None       # d pc_loss / d heatmap3D
+            dbn, _ = nn.hq_bwd(bn, self.C, self.heatmap, centers, dq, dhm, dcenters=self._g('autoencoder/encoder/centers'))
+            tape.acc(bn, dbn, owned=True)
+        # the tape so far: encoder ops, decoder ops, context-model ops.  The quantizer's backward must run after the
+        # decoder's and before the encoder's: insert it where the encoder ends.
+        tape.fns.insert(n_enc, hq_bwd)
+        tape.backward()
+        self.tape = None
+        return out
+
+    # ------------------------------------------------------------------ optimiser (code/train.py:339-349)
+    def learning_rates(self):
+        """training_helpers.create_learning_rate_tensor (code/training_helpers.py:22-35) at the current global step"""
+        def lr(cfg):
+            if cfg.lr_schedule == 'FIXED':
+                return cfg.lr_initial
+            p = self.global_step / float(self.num_itr_per_epoch * cfg.lr_schedule_decay_interval)
+            if cfg.lr_schedule_decay_staircase:
+                p = math.floor(p)
+            return cfg.lr_initial * cfg.lr_schedule_decay_rate ** p
+        return lr(self.ae_config), lr(self.pc_config)
+
+    def apply_gradients(self):
+        lr_ae, lr_pc = self.learning_rates()
+        self._adam_t += 1
+        cfg = self.ae_config
+        plan = []
+        if cfg.train_autoencoder:
+            plan += [('ae_w', lr_ae, cfg.regularization_factor), ('ae_bn', lr_ae, 0.0),
+                     ('ae_centers', lr_ae, cfg.regularization_factor_centers)]
+        if cfg.train_probclass:
+            plan += [('pc_w', lr_pc, self.pc_config.regularization_factor or 0.0), ('pc_b', lr_pc, 0.0)]
+        for name, lr, l2 in plan:
+            g = self.groups[name]
+            nn.adam_step(g.w, g.g, g.m, g.v, lr, self._adam_t, l2=l2)
+        self.global_step += 1
+
+    def step(self, x):
+        """one sess.run(train_op) of the reference: forward, loss, backward, BN moving averages, both Adam updates"""
+        out = self.forward_backward(x, is_training=True, update_moving=True)
+        self.apply_gradients()
+        return out
+
+
+def train_loop(trainer, batches, log_interval=100, log=print):
+    """code/train.py:216-269 without the TF session / summary plumbing: runs trainer.step over an iterable of batches"""
+    last = None
+    for x in batches:
+        last = trainer.step(x)
+        itr = trainer.global_step
+        if log_interval and itr % log_interval == 0:
+            log('{}: loss {:.4f}  d_loss {:.4f}  pc_loss {:.4f}  H_real {:.4f}  bpp {:.4f}  ms_ssim {:.5f}'.format(
+                itr, last['total_loss'], last['d_loss_scaled'], last['pc_loss'], last['H_real'], last['bpp'], last['ms_ssim']))
+    return last

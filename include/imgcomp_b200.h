@@ -241,6 +241,32 @@ int ic_nn_mul(const float* d_x, const float* d_y, int64_t n, float* d_out, void*
 int ic_nn_adam_step(float* d_w, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int64_t step, float l2, const float* d_mask, void* stream);
 
+/* _normalize (code/autoencoder.py:136-144,160-169): x NCHW (uint8 or float32 in [0,255]) -> normalised NHWC with 4
+ * channels (the 4th is zero padding) */
+int ic_nn_normalize_fwd(const void* d_x_nchw, int x_is_u8, int N, int H, int W, float* d_out_nhwc4, void* stream);
+/* forward twin of ic_nn_hq_bwd (code/autoencoder.py:127-134,171-200): d_bn N,h,w,Cb -> NCHW z, heatmap3D, qbar, qhard,
+ * qsoft (each optional) and int64 symbols */
+int ic_nn_hq_fwd(const float* d_bn, int N, int h, int w, int C, int Cb, int heatmap, const float* d_centers, int L, float* d_z,
+                 float* d_heatmap, float* d_qbar, float* d_qhard, float* d_qsoft, int64_t* d_symbols, void* stream);
+/* Context model in training mode (code/probclass.py:63-106 with is_training=True).  The padded volume is depth-major,
+ * (C+4, N, h+8, w+8, 4 channels: value, 0, 0, 0), so that the (2,3,3) VALID conv3d (code/probclass.py:227-261) is two
+ * VALID ic_nn_conv2d_* passes over the contiguous slice ranges [0, D-1) and [1, D), accumulated with ic_nn_axpby.
+ * ic_nn_pc_pad_fwd = pad_for_probclass3d (code/probclass.py:268-292). */
+int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pad_value, float* d_out, void* stream);
+/* softmax_cross_entropy_with_logits * log2(e) (code/probclass.py:99-104).  d_logits: rows in (C, N, h, w) order, Cs
+ * floats per row, the first L valid; d_symbols / d_heatmap / d_bc_nchw in the reference's NCHW order.
+ * backward: d_dlogits[row][k] = (coef_real + coef_mask * heatmap) * log2(e) * (softmax_k - [k == symbol]); these are
+ * the gradients of beta * max(0.5 * (mean(bc * heatmap) + mean(bc)) - H_target, 0) (code/train.py:309-316) with
+ * coef_* = beta * 0.5 / numel when the hinge is active, else 0. */
+int ic_nn_pc_xent_fwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, int N, int C, int h, int w, float* d_bc_nchw,
+                      void* stream);
+int ic_nn_pc_xent_bwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, const float* d_heatmap, int N, int C, int h,
+                      int w, float coef_real, float coef_mask, float* d_dlogits, void* stream);
+/* the residual crop of the 3-D residual block, x[:, 2:, 2:-2, 2:-2, :] (code/probclass.py:185-196), on A slices of
+ * H x W x C (C % 4 == 0): out = in[:, crop:-crop, crop:-crop, :]; backward ACCUMULATES into d_dx */
+int ic_nn_crop_fwd(const float* d_in, int64_t A, int H, int W, int C, int crop, float* d_out, void* stream);
+int ic_nn_crop_bwd_add(const float* d_dy, int64_t A, int H, int W, int C, int crop, float* d_dx, void* stream);
+
 /* --------------------------------------------------------------------- MS-SSIM
  * replaces: ms_ssim.MultiScaleSSIM(img1, img2, data_format='NCHW')   code/ms_ssim.py:115-186
  * float32, ONE scalar for the batch.  d_out: 1 float; d_levels (optional): 10 floats
@@ -250,6 +276,13 @@ size_t ic_msssim_workspace_bytes(int N, int H, int W, int is_double);
 int ic_msssim_tf_fwd(const float* d_img1, const float* d_img2, int N, int H, int W,
                      float* d_out, float* d_levels,
                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* gradient of ms_ssim.MultiScaleSSIM w.r.t. img2 (what tf.gradients derives from code/ms_ssim.py:16-186 for the
+ * distortion loss of code/train.py:392,431): d_dimg2 = grad_out * d value / d img2 (N,3,H,W); d_value (optional)
+ * receives the forward value.  The forward pass is recomputed inside. */
+size_t ic_msssim_bwd_workspace_bytes(int N, int H, int W);
+int ic_msssim_tf_bwd(const float* d_img1, const float* d_img2, int N, int H, int W, float grad_out, float* d_dimg2,
+                     float* d_value, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* replaces: ms_ssim_np.MultiScaleSSIM on uint8 (through tf_msssim_np, val.py:93)
  *           code/ms_ssim_np.py:25-110.  float64, one value PER IMAGE (d_out: N doubles). */
