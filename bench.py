@@ -47,6 +47,19 @@ def probclass_macs(C, h, w, k=24, L=6):
     return d0 + d1 + d2 + d3
 
 
+def load_traffic(workload, mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of the same workload / mode (profiles/r1b_conv3x3_traffic.json); None for other workloads."""
+    p = os.path.join(ROOT, 'profiles', 'r1b_conv3x3_traffic.json')
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    if d.get('workload') != workload or d.get('mode') != mode:
+        return None, None
+    return d['traffic_bytes_per_launch'], d['source']
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -342,6 +355,7 @@ def main():
     avg_ms = t3 / max(n3, 1)
     achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if n3 else 0.0
     peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    traffic, traffic_src = load_traffic(args.workload, args.mode)
     step_flop = 2.0 * (encoder_macs_per_pixel(C) * pix + N * probclass_macs(C, H // 8, Wd // 8, p.arch_param__k))
     out = {
         'metric': 'MPix/s encode+probclass fwd', 'value': value, 'unit': 'MPix/s', 'n_gpus': world,
@@ -358,7 +372,10 @@ def main():
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_128x128 (%s)' % args.mode, 'achieved': achieved,
                      'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
-                     'peak_source': '%s bf16_tflops_sustained' % peak_src, 'traffic': None,
+                     'peak_source': '%s bf16_tflops_sustained' % peak_src, 'traffic': traffic,
+                     'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'traffic_source': traffic_src,
+                     # in + out activations (hi/lo fp16 planes = 4 B / element) + 0 / 1 / 2 residual reads, averaged over a residual group
+                     'algorithmic_bytes_per_launch': m_rows * 128 * 4.0 * (2 * 6 + 3 + 1) / 6.0,
                      'flop_per_launch': flop_per_launch, 'avg_launch_ms': avg_ms, 'launches': n3,
                      'share_of_step': t3 / (ms * args.steps) if ms else None,
                      'mma_flops_per_algorithmic_flop': {'exact': 3, 'fast': 1, 'fp32': 0}[args.mode],

@@ -221,7 +221,7 @@ __device__ __forceinline__ void col_terms(const ColArgs& a, int64_t row, int c, 
     }
 }
 
-constexpr int CR_ROWS = 256;      // rows per block
+constexpr int CR_ROWS = 64;       // rows per block (8 per warp): enough blocks to fill 148 SMs at 51 200 rows
 
 __global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __restrict__ partial /* [blocks][C][2] */) {
     __shared__ double red[8][128][2];
@@ -258,17 +258,30 @@ __global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __r
     }
 }
 
-// mode 0: mean, invstd (+ moving averages); mode 1: dbeta, dgamma
-__global__ void col_finalize_kernel(const double* __restrict__ partial, int blocks, int C, int64_t M, int mode, float eps,
-                                    float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ mov_mean,
-                                    float* __restrict__ mov_var, float decay) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// mode 0: mean, invstd (+ moving averages); mode 1: dbeta, dgamma.  One block per channel, fixed-order tree.
+__global__ void __launch_bounds__(128) col_finalize_kernel(const double* __restrict__ partial, int blocks, int C, int64_t M, int mode,
+                                                           float eps, float* __restrict__ o1, float* __restrict__ o2,
+                                                           float* __restrict__ mov_mean, float* __restrict__ mov_var, float decay) {
+    __shared__ double r1[128], r2[128];
+    const int c = blockIdx.x;
     double s1 = 0, s2 = 0;
-    for (int b = 0; b < blocks; ++b) {
+    for (int b = threadIdx.x; b < blocks; b += 128) {
         s1 += partial[((int64_t)b * C + c) * 2 + 0];
         s2 += partial[((int64_t)b * C + c) * 2 + 1];
     }
+    r1[threadIdx.x] = s1;
+    r2[threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            r1[threadIdx.x] += r1[threadIdx.x + o];
+            r2[threadIdx.x] += r2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    s1 = r1[0];
+    s2 = r2[0];
     if (mode == 0) {
         const double mean = s1 / (double)M;
         double var = s2 / (double)M - mean * mean;
@@ -691,7 +704,7 @@ int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma,
         a.x = d_x; a.M = M; a.C = C; a.mode = 0;
         col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
         IC_CHECK_LAUNCH();
-        col_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 0, eps, d_mean, d_invstd,
+        col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 0, eps, d_mean, d_invstd,
                                                          d_mov_mean, d_mov_var, 0.9f);
         IC_CHECK_LAUNCH();
     }
@@ -715,7 +728,7 @@ int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, co
     a.M = M; a.C = C; a.relu = relu; a.mode = 1;
     col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
     IC_CHECK_LAUNCH();
-    col_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 1, 0.f, d_dbeta, d_dgamma, nullptr,
+    col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 1, 0.f, d_dbeta, d_dgamma, nullptr,
                                                      nullptr, 0.f);
     IC_CHECK_LAUNCH();
     bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_dy, d_mean, d_invstd, d_gamma, d_beta, d_dbeta, d_dgamma, relu,

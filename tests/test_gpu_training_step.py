@@ -53,9 +53,9 @@ def _setup(synth, ae_name, N, H, W, seed=21):
     return ae_cfg, pc_cfg, Wt, x, tr
 
 
-@pytest.mark.parametrize('ae_name,N,H,W', [('cvpr/low', 2, 64, 64), ('cvpr/hi', 2, 80, 48)])
-def test_training_step_matches_oracle(synth, ae_name, N, H, W):
-    ae_cfg, pc_cfg, Wt, x, tr = _setup(synth, ae_name, N, H, W)
+@pytest.mark.parametrize('ae_name,N,H,W,seed', [('cvpr/low', 2, 64, 64, 22), ('cvpr/hi', 2, 80, 48, 21)])
+def test_training_step_matches_oracle(synth, ae_name, N, H, W, seed):
+    ae_cfg, pc_cfg, Wt, x, tr = _setup(synth, ae_name, N, H, W, seed=seed)
     ref = T.training_step(x, Wt, ae_cfg, pc_cfg, dtype=torch.float64, training=True)
     out = tr.forward_backward(torch.from_numpy(x).cuda(), is_training=True, update_moving=False)
     sym = out['tensors']['symbols'].cpu().numpy()
@@ -87,13 +87,12 @@ def test_training_step_matches_oracle(synth, ae_name, N, H, W):
     for e, name in errs[:8]:
         print('  grad err %.2e  %s' % (e, name))
     print('  median gradient error %.2e over %d variables' % (errs[len(errs) // 2][0], len(errs)))
-    # float32 kernels against the float64 oracle: 1e-4 norm-wise in the median (measured 6e-6).  Individual layers may
-    # sit higher when one ReLU input / heatmap clip lands on the other side of zero in float32 than in float64 (a
-    # discrete event: measured 1.8e-2 on one layer of cvpr/low, 1.8e-5 everywhere on cvpr/hi): at most 5 % of the
-    # variables above 1e-3, none above 5e-2.
+    # float32 kernels against the float64 oracle: norm-wise 1e-3 on every variable, 1e-4 in the median (measured:
+    # worst 6e-5, median 6e-6).  The image seeds are ones where no ReLU input / heatmap clip lands on the other side
+    # of zero in float32 than in float64; such a flip is a discrete event that moves one layer's gradient by ~1e-2 and
+    # everything upstream of it by ~5e-3 (tools/train_seed_sweep.py: seeds 21, 24 of cvpr/low), like a symbol flip.
+    assert errs[0][0] < 1e-3, errs[:8]
     assert errs[len(errs) // 2][0] < 1e-4
-    assert sum(e > 1e-3 for e, _ in errs) <= len(errs) // 20, errs[:12]
-    assert errs[0][0] < 5e-2, errs[0]
 
 
 def test_step_applies_adam_and_moving_averages(synth):
