@@ -1,5 +1,6 @@
-"""Host mirror of the loss part of code/train.py (forward only): get_loss (:303-336) and
-Distortions (:352-431).  The backward pass / optimiser of the training step is not built."""
+"""Host mirror of code/train.py: get_loss (:303-336) and Distortions (:352-431) as forward-only functions on CUDA
+tensors, and get_train_op (:339-349) as the constructor of trainer.Trainer, which owns the whole training step
+(forward + loss + backward + the two Adam optimisers)."""
 import math
 
 import numpy as np
@@ -100,3 +101,11 @@ class Distortions(object):
     @staticmethod
     def get_ms_ssim(inp, otp):
         return ms_ssim.MultiScaleSSIM(inp, otp, data_format='NCHW', name='MS-SSIM')
+
+
+def get_train_op(ae_config, pc_config, weights, num_itr_per_epoch=1000):
+    """code/train.py:339-349 builds Adam_AE (lr_ae) for the autoencoder variables and Adam_PC (lr_pc) for
+    pc.variables() over total_loss.  Eager equivalent: a trainer.Trainer; `op.step(x)` runs one
+    sess.run([train_op, global_step]) of train_loop (:252) on the batch x (N,3,H,W uint8/float32 CUDA)."""
+    from . import trainer
+    return trainer.Trainer(ae_config, pc_config, weights, num_itr_per_epoch)
