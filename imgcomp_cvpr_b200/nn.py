@@ -66,6 +66,18 @@ def conv2d_bwd_filter(x, dy, w_shape, stride=1, transposed=False, valid=False, o
     return dw
 
 
+def conv3x3_tc(x, w, data_grad=False):
+    """3x3 stride-1 SAME 128 -> 128 convolution (data_grad: its data gradient, x = dy) on the tcgen05 kernel, EXACT mode;
+    x N,H,W,128 float32, w [3][3][128][128] float32 (both on the device)"""
+    N, H, W, C = x.shape
+    assert C == 128 and tuple(w.shape) == (3, 3, 128, 128)
+    y = torch.empty_like(x)
+    ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_workspace_bytes(N, H, W))
+    _lib.check(_lib.lib().ic_nn_conv3x3_tc(_lib.ptr(_f32(x)), _lib.ptr(_f32(w)), N, H, W, int(bool(data_grad)), _lib.ptr(y),
+                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return y
+
+
 def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None):
     """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics."""
     C = x.shape[-1]

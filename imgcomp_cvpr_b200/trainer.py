@@ -127,8 +127,12 @@ class Trainer(object):
         W = tr.weights()            # dict TF variable name -> ndarray (loads into autoencoder / probclass unchanged)
     """
 
-    def __init__(self, ae_config, pc_config, weights, num_itr_per_epoch=1000, device='cuda'):
+    def __init__(self, ae_config, pc_config, weights, num_itr_per_epoch=1000, device='cuda', mode='exact'):
+        """mode 'fp32': every kernel float32 FFMA (strict parity mode); 'exact': forward and data gradient of the 64
+        3x3 128->128 convs on the tcgen05 kernel in fp16 hi/lo arithmetic (float32-class)."""
         _lib.require_device()
+        assert mode in ('fp32', 'exact')
+        self.mode = mode
         assert ae_config.arch == 'CVPR' and pc_config.arch == 'res_shallow'
         assert ae_config.normalization == 'FIXED'
         assert ae_config.optimizer == 'ADAM' and pc_config.optimizer == 'ADAM', 'only the Adam of the published configs is built'
@@ -239,7 +243,8 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ ops (forward + recorded backward)
     def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None):
-        y = nn.conv2d_fwd(x, w, stride, transposed, valid)
+        tc = (self.mode == 'exact' and tuple(w.shape) == (3, 3, 128, 128) and stride == 1 and not transposed and not valid)
+        y = nn.conv3x3_tc(x, w) if tc else nn.conv2d_fwd(x, w, stride, transposed, valid)
         if self.tape is not None:
             tape = self.tape
 
@@ -251,7 +256,8 @@ class Trainer(object):
                 if mask is not None:
                     nn.mul(gw, mask, out=gw)
                 if need_dx:
-                    tape.acc(x, nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid), owned=True)
+                    dx = nn.conv3x3_tc(dy, w, data_grad=True) if tc else nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid)
+                    tape.acc(x, dx, owned=True)
             tape.add(bwd)
         return y
 

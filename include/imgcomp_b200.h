@@ -202,6 +202,13 @@ int ic_nn_conv2d_bwd_data(const float* d_dy, const float* d_w, int N, int Hi, in
 int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, int Wi, int Cin, int KH, int KW,
                             int stride, int Cout, int transposed, int valid, float* d_dw,
                             void* d_workspace, size_t workspace_bytes, void* stream);
+/* The 3x3 stride-1 SAME 128 -> 128 convolutions of the residual trunks (code/autoencoder.py:274-287) on the tcgen05
+ * kernel in EXACT (fp16 hi/lo, fp32 accumulate) arithmetic, float32 NHWC in / out: data_grad = 0 is ic_nn_conv2d_fwd,
+ * data_grad = 1 is ic_nn_conv2d_bwd_data (d_x = the output gradient) for that geometry.  d_w: float32 [3][3][128][128]
+ * on the device; it is re-packed for the kernel on the device at every call (weights change every step). */
+size_t ic_nn_conv3x3_tc_workspace_bytes(int N, int H, int W);
+int ic_nn_conv3x3_tc(const float* d_x, const float* d_w, int N, int H, int W, int data_grad, float* d_y,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
 /* slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125): batch mean / biased variance over
  * the M = N*H*W rows, out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2); d_mean / d_invstd are
  * kept for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update with
