@@ -71,6 +71,8 @@ SIGNATURES = {
     'ic_nn_conv2d_bwd_filter': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_conv3x3_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'ic_nn_conv3x3_tc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_conv3x3_tc_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'ic_nn_conv3x3_tc_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_bn_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'ic_nn_bn_train_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

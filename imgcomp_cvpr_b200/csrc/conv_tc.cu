@@ -39,6 +39,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace ic {
 namespace tc {
@@ -63,130 +64,6 @@ struct Cfg {
     static constexpr uint32_t IDESC = (1u << 4) /* D fp32 */ | (0u << 7) /* A f16 */ | (0u << 10) /* B f16 */ |
                                       ((uint32_t)(NOUT >> 3) << 17) /* N */ | ((128u >> 4) << 24) /* M */;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---- CTA-pair (cta_group::2) helpers: the leader CTA (cluster rank 0) issues M=256 MMAs over both CTAs'
-// A tiles and half of B from each CTA; barriers the leader waits on are signalled remotely by the peer.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
-                                                int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
-                                                int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar_local) {      // arrives on the barrier at this offset in BOTH CTAs
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_local),
-        "h"((uint16_t)3)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
 
 __constant__ float c_img_mean[3] = {121.853699f, 113.588608f, 100.637154f};
 __constant__ float c_img_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};   // float32 sqrt(var + 1e-10)
@@ -681,9 +558,10 @@ __device__ __forceinline__ void split8(const float (&v)[8], float4& hi4, float4&
 
 // fp32 NHWC (N,H,W,C) -> planes (optionally space-to-depth).  One thread per (chunk, pixel), pixel fastest.
 __global__ void split_from_nhwc_kernel(const float* __restrict__ in, int H, int W, int CH, int s2d, int64_t total,
-                                       int64_t plane, __half* __restrict__ out, int write_lo) {
+                                       int64_t plane, __half* __restrict__ out, int write_lo, const float* __restrict__ mul) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    const float g = mul ? mul[0] : 1.f;          // power-of-two pre-scale (training gradients), exact
     const int64_t hw = (int64_t)H * W;
     const int64_t r = i % hw;
     const int64_t nc = i / hw;
@@ -691,7 +569,7 @@ __global__ void split_from_nhwc_kernel(const float* __restrict__ in, int H, int 
     const int64_t n = nc / CH;
     const float4* src = reinterpret_cast<const float4*>(in + ((n * hw + r) * CH + chunk) * 8);
     float4 a = src[0], b = src[1];
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float v[8] = {a.x * g, a.y * g, a.z * g, a.w * g, b.x * g, b.y * g, b.z * g, b.w * g};
     float4 hi, lo;
     split8(v, hi, lo);
     size_t off;
@@ -724,7 +602,7 @@ __global__ void split_from_nchw_kernel(const float* __restrict__ in, int CH, int
 
 // planes [pl][N][CH][H][W][8] -> fp32 NHWC.  One thread per (pixel, chunk), chunk fastest (coalesced writes).
 __global__ void merge_to_nhwc_kernel(const __half* __restrict__ in, int H, int W, int CH, int64_t total, int64_t plane,
-                                     float* __restrict__ out, int has_lo) {
+                                     float* __restrict__ out, int has_lo, const float* __restrict__ mul) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int chunk = (int)(i % CH);
@@ -734,6 +612,11 @@ __global__ void merge_to_nhwc_kernel(const __half* __restrict__ in, int H, int W
     const size_t off = (((size_t)n * CH + chunk) * hw + r) * 8;
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     add_pair(in, in + plane, off, has_lo != 0, v);
+    if (mul) {                                   // undo a power-of-two pre-scale (training gradients), exact
+        const float g = mul[0];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= g;
+    }
     float4* dst = reinterpret_cast<float4*>(out + (pix * CH + chunk) * 8);
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
     dst[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -768,6 +651,27 @@ EncodeTiledFn get_encode_fn() {
     }
     return fn;
 }
+
+}  // namespace
+
+// 5-D tensor map of an fp16 plane tensor [planes][Nimg][chunks][H][W][8] with a box of box_w pixels x box_h rows x
+// box_chunks chunks (one image, one plane); out-of-bounds elements read as zero (TF SAME padding, ragged tiles)
+int encode_planes_map(CUtensorMap* map, const __half* base, int planes, int Nimg, int chunks, int H, int W, int box_w, int box_h,
+                      int box_chunks) {
+    EncodeTiledFn enc = get_encode_fn();
+    IC_REQUIRE(enc, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t hw16 = (cuuint64_t)H * W * 16;
+    const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)chunks, (cuuint64_t)Nimg, (cuuint64_t)planes};
+    const cuuint64_t strides[4] = {(cuuint64_t)W * 16, hw16, hw16 * chunks, hw16 * chunks * Nimg};
+    const cuuint32_t box[5] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, (cuuint32_t)box_chunks, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IC_REQUIRE(r == CUDA_SUCCESS, IC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d (N=%d H=%d W=%d chunks=%d)", (int)r, Nimg, H, W, chunks);
+    return IC_OK;
+}
+
+namespace {
 
 template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES, bool PAIR = false>
 int launch_t(const ConvTcArgs& a, cudaStream_t s) {
@@ -919,11 +823,12 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     return IC_ERR_UNSUPPORTED;
 }
 
-int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s) {
+int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s,
+                           const float* d_mul) {
     IC_REQUIRE(C % 8 == 0 && (!s2d || (H % 2 == 0 && W % 2 == 0)), IC_ERR_INVALID, "split_from_nhwc: bad shape");
     int64_t total = (int64_t)N * H * W * (C / 8), plane = (int64_t)N * H * W * C;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
-    split_from_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, s2d, total, plane, out, write_lo);
+    split_from_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, s2d, total, plane, out, write_lo, d_mul);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -937,10 +842,10 @@ int launch_split_from_nchw(const float* in, int N, int C, int H, int W, __half* 
     return IC_OK;
 }
 
-int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s) {
+int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s, const float* d_mul) {
     int64_t total = (int64_t)N * H * W * (C / 8), plane = (int64_t)N * H * W * C;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
-    merge_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, total, plane, out, has_lo);
+    merge_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, total, plane, out, has_lo, d_mul);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

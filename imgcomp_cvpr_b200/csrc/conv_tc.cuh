@@ -1,5 +1,6 @@
 // Internal interface of the tcgen05 convolution (conv_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <vector>
@@ -77,8 +78,12 @@ struct ConvTcArgs {
 };
 
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s);
-int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s);
-int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s);
+int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d, __half* out, int write_lo, cudaStream_t s,
+                           const float* d_mul = nullptr);
+int encode_planes_map(CUtensorMap* map, const __half* base, int planes, int Nimg, int chunks, int H, int W, int box_w, int box_h,
+                      int box_chunks);
+int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s,
+                         const float* d_mul = nullptr);
 int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
 int pack_weights_tconv(const float* w, int k, int cin, int cout, const int* phases, int nphases, int nout,
                        std::vector<__half>& packed, GroupTable& gt, float* inv_scale_out);

@@ -78,6 +78,19 @@ def conv3x3_tc(x, w, data_grad=False):
     return y
 
 
+def conv3x3_tc_bwd(x, dy, w, need_dx=True, dw_out=None):
+    """backward of conv3x3_tc(x, w): -> (dx or None, dw [3][3][128][128]); both gradients on the tcgen05 kernels"""
+    N, H, W, C = x.shape
+    assert C == 128 and tuple(w.shape) == (3, 3, 128, 128) and tuple(dy.shape) == tuple(x.shape)
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w) if dw_out is None else dw_out
+    assert tuple(dw.shape) == (3, 3, 128, 128)
+    ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W))
+    _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
+                                              _lib.ptr(_f32(dw)), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return dx, dw
+
+
 def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None):
     """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics."""
     C = x.shape[-1]

@@ -129,7 +129,8 @@ class Trainer(object):
 
     def __init__(self, ae_config, pc_config, weights, num_itr_per_epoch=1000, device='cuda', mode='exact'):
         """mode 'fp32': every kernel float32 FFMA (strict parity mode); 'exact': forward and data gradient of the 64
-        3x3 128->128 convs on the tcgen05 kernel in fp16 hi/lo arithmetic (float32-class)."""
+        3x3 128->128 convs AND their filter gradients on tcgen05 kernels in fp16 hi/lo arithmetic (float32-class,
+        DESIGN.md 4.2 / 4.6)."""
         _lib.require_device()
         assert mode in ('fp32', 'exact')
         self.mode = mode
@@ -252,12 +253,16 @@ class Trainer(object):
                 dy = tape.pop(y)
                 if dy is None:
                     return
+                if tc:        # both gradients on tensor cores (filter gradient: GEMM over pixels, csrc/train_tc.cu)
+                    dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw)
+                    if need_dx:
+                        tape.acc(x, dx, owned=True)
+                    return
                 nn.conv2d_bwd_filter(x, dy, w.shape, stride, transposed, valid, out=gw)
                 if mask is not None:
                     nn.mul(gw, mask, out=gw)
                 if need_dx:
-                    dx = nn.conv3x3_tc(dy, w, data_grad=True) if tc else nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid)
-                    tape.acc(x, dx, owned=True)
+                    tape.acc(x, nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid), owned=True)
             tape.add(bwd)
         return y
 

@@ -209,6 +209,13 @@ int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, 
 size_t ic_nn_conv3x3_tc_workspace_bytes(int N, int H, int W);
 int ic_nn_conv3x3_tc(const float* d_x, const float* d_w, int N, int H, int W, int data_grad, float* d_y,
                      void* d_workspace, size_t workspace_bytes, void* stream);
+/* Backward of y = conv3x3(x, w) for the same geometry, both gradients on tcgen05 (EXACT arithmetic; x, dy and w are
+ * pre-scaled by per-tensor powers of two so that small gradients keep float32-class precision in the fp16 hi/lo split):
+ * d_dx (optional) = ic_nn_conv2d_bwd_data, d_dw = ic_nn_conv2d_bwd_filter [3][3][128][128].  The filter gradient is a
+ * GEMM over pixels on MN-major operands (see csrc/train_tc.cu) with a fixed-order reduction over pixel splits. */
+size_t ic_nn_conv3x3_tc_bwd_workspace_bytes(int N, int H, int W);
+int ic_nn_conv3x3_tc_bwd(const float* d_x, const float* d_dy, const float* d_w, int N, int H, int W, float* d_dx, float* d_dw,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
 /* slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125): batch mean / biased variance over
  * the M = N*H*W rows, out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2); d_mean / d_invstd are
  * kept for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update with

@@ -72,6 +72,35 @@ def test_conv3x3_tensor_core_forward_and_data_gradient(N, H, W):
     assert float((y2 - y2_ref).abs().max()) <= 2e-5 * float(y2_ref.abs().max())
 
 
+@pytest.mark.parametrize('N,H,W,gscale', [(2, 16, 16, 1.0), (3, 40, 40, 1e-5), (1, 19, 27, 300.0), (4, 8, 8, 1.0)])
+def test_conv3x3_tensor_core_backward(N, H, W, gscale):
+    """ic_nn_conv3x3_tc_bwd: data gradient (conv_tc with flipped, transposed taps) and filter gradient (tcgen05 GEMM
+    over pixels on MN-major operands, split over pixel tiles) against the float32 FFMA primitives; gscale exercises the
+    per-tensor power-of-two pre-scaling (gradients of 1e-5 must keep float32-class precision in the fp16 hi/lo split)."""
+    from imgcomp_cvpr_b200 import nn
+    rng = np.random.RandomState(4)
+    x = torch.from_numpy(np.maximum(rng.randn(N, H, W, 128), 0).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.randn(3, 3, 128, 128) * 0.05).astype(np.float32)).cuda()
+    dy = torch.from_numpy((rng.randn(N, H, W, 128) * gscale).astype(np.float32)).cuda()
+    dx_ref = nn.conv2d_bwd_data(dy, w, x.shape)
+    dw_ref = nn.conv2d_bwd_filter(x, dy, w.shape)
+    dx, dw = nn.conv3x3_tc_bwd(x, dy, w)
+    e_dx = float((dx - dx_ref).abs().max()) / float(dx_ref.abs().max())
+    e_dw = float((dw - dw_ref).abs().max()) / float(dw_ref.abs().max())
+    print('conv3x3 tc bwd %s gscale %g: max err dx %.2e dw %.2e (of the range)' % ((N, H, W), gscale, e_dx, e_dw))
+    assert e_dx <= 2e-5 and e_dw <= 2e-5
+    # float64 truth for the filter gradient on the small case
+    if N * H * W <= 1024:
+        xt = torch.tensor(x.cpu().numpy().transpose(0, 3, 1, 2), dtype=torch.float64)
+        wt = torch.tensor(w.cpu().numpy(), dtype=torch.float64, requires_grad=True)
+        y = T.conv2d_same(xt, wt, 1)
+        (y * torch.tensor(dy.cpu().numpy().transpose(0, 3, 1, 2), dtype=torch.float64)).sum().backward()
+        ref = wt.grad.numpy()
+        assert np.abs(dw.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+    _, dw_only = nn.conv3x3_tc_bwd(x, dy, w, need_dx=False)
+    assert torch.equal(dw_only, dw)
+
+
 def test_exact_mode_step_matches_fp32_mode(synth):
     """Trainer(mode='exact') (3x3 convs' forward / data gradient on tensor cores) against Trainer(mode='fp32')"""
     ae_cfg, pc_cfg, Wt, x, tr32 = _setup(synth, 'cvpr/low', 2, 64, 64, seed=22)
