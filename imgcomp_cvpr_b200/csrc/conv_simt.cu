@@ -8,6 +8,9 @@
 //
 // GEMM view: M = N*Ho*Wo output pixels, N = Cout, K = KH*KW*Cin.
 // 64x64 block tile, BK = 16, 256 threads, 4x4 register tile, double buffered.
+// Stride-2 transposed convs: an output pixel of phase (oy & 1, ox & 1) only meets the taps of matching parity (9, 6, 6
+// or 4 of 25; 1, 2, 2 or 4 of 9), so blocks are formed over pixels of ONE phase and walk only those taps, in ascending
+// tap order: the same non-zero terms in the same order as the plain loop (bit-identical), a quarter of the work.
 #include "common.cuh"
 
 namespace ic {
@@ -25,22 +28,50 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
     __shared__ __align__(16) float Bs[2][BK][BN + 4];
 
     const int t = threadIdx.x;
-    const int64_t M = (int64_t)d.N * d.Ho * d.Wo;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const bool phased = d.transposed && d.stride == 2;
+    // phase (pa, pb) = (oy & 1, ox & 1) owns ceil((Ho - pa) / 2) x ceil((Wo - pb) / 2) pixels per image; the grid is the
+    // concatenation of the four phases' block ranges (launch_conv_simt computes the same counts)
+    int phase = 0, blk = blockIdx.x;
+    if (phased) {
+        for (; phase < 3; ++phase) {
+            const int64_t mp = (int64_t)d.N * ((d.Ho - (phase >> 1) + 1) / 2) * ((d.Wo - (phase & 1) + 1) / 2);
+            const int nb = (int)((mp + BM - 1) / BM);
+            if (blk < nb) break;
+            blk -= nb;
+        }
+    }
+    const int pa = phase >> 1, pb = phase & 1;
+    const int Hq = (d.Ho - pa + 1) / 2, Wq = (d.Wo - pb + 1) / 2;
+    const int64_t M = phased ? (int64_t)d.N * Hq * Wq : (int64_t)d.N * d.Ho * d.Wo;      // pixels (of this phase)
+    const int64_t m0 = (int64_t)blk * BM;
     const int n0 = blockIdx.y * BN;
-    const int K = d.KH * d.KW * d.Cin;
+    // taps this block walks: all, or those of the phase's parity
+    const int ky0 = phased ? ((pa + d.pad_t) & 1) : 0, kx0 = phased ? ((pb + d.pad_l) & 1) : 0;
+    const int kstep = phased ? 2 : 1;
+    const int nky = phased ? (d.KH - ky0 + 1) / 2 : d.KH, nkx = phased ? (d.KW - kx0 + 1) / 2 : d.KW;
+    const int K = nky * nkx * d.Cin;
+    // row of the tile -> (image, output y, output x); returns false past the end
+    auto row_pixel = [&](int64_t mrow, int& pn, int& oy, int& ox) -> bool {
+        if (mrow >= M) return false;
+        if (!phased) {
+            pn = (int)(mrow / ((int64_t)d.Ho * d.Wo));
+            int r = (int)(mrow - (int64_t)pn * d.Ho * d.Wo);
+            oy = r / d.Wo;
+            ox = r - oy * d.Wo;
+        } else {
+            pn = (int)(mrow / ((int64_t)Hq * Wq));
+            int r = (int)(mrow - (int64_t)pn * Hq * Wq);
+            int yq = r / Wq;
+            oy = 2 * yq + pa;
+            ox = 2 * (r - yq * Wq) + pb;
+        }
+        return true;
+    };
 
     // A-load assignment: one output pixel row, 4 consecutive k
     const int am = t >> 2, ak = (t & 3) * 4;
-    const int64_t mrow = m0 + am;
-    const bool mvalid = mrow < M;
     int pn = 0, oy = 0, ox = 0;
-    if (mvalid) {
-        pn = (int)(mrow / ((int64_t)d.Ho * d.Wo));
-        int r = (int)(mrow - (int64_t)pn * d.Ho * d.Wo);
-        oy = r / d.Wo;
-        ox = r - oy * d.Wo;
-    }
+    const bool mvalid = row_pixel(m0 + am, pn, oy, ox);
     // B-load assignment
     const int bk = t >> 4, bn = (t & 15) * 4;
 
@@ -49,7 +80,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
         int k = k0 + ak;
         if (mvalid && k < K) {
             int tap = k / d.Cin, ci = k - tap * d.Cin;
-            int ky = tap / d.KW, kx = tap - ky * d.KW;
+            int jy = tap / nkx;
+            int ky = ky0 + kstep * jy, kx = kx0 + kstep * (tap - jy * nkx);
             int iy, ix;
             bool ok;
             if (!d.transposed) {
@@ -70,7 +102,12 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
     auto load_b = [&](int k0) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = k0 + bk;
-        if (k < K && n0 + bn < d.ldw) v = *reinterpret_cast<const float4*>(d.w + (int64_t)k * d.ldw + n0 + bn);
+        if (k < K && n0 + bn < d.ldw) {
+            int tap = k / d.Cin, ci = k - tap * d.Cin;
+            int jy = tap / nkx;
+            int64_t row = (int64_t)((ky0 + kstep * jy) * d.KW + kx0 + kstep * (tap - jy * nkx)) * d.Cin + ci;
+            v = *reinterpret_cast<const float4*>(d.w + row * d.ldw + n0 + bn);
+        }
         return v;
     };
     auto store = [&](int buf, float4 a, float4 b) {
@@ -117,8 +154,9 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
     // epilogue
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int64_t m = m0 + ty * 4 + i;
-        if (m >= M) continue;
+        int en, ey, ex;
+        if (!row_pixel(m0 + ty * 4 + i, en, ey, ex)) continue;
+        const int64_t m = ((int64_t)en * d.Ho + ey) * d.Wo + ex;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int n = n0 + tx * 4 + j;
@@ -152,6 +190,12 @@ int launch_conv_simt(const ConvDesc& d, cudaStream_t stream) {
                d.Cin, d.ldw);
     int64_t M = (int64_t)d.N * d.Ho * d.Wo;
     dim3 grid(cdiv(M, BM), cdiv(d.Cout, BN));
+    if (d.transposed && d.stride == 2) {        // one block range per output phase
+        grid.x = 0;
+        for (int ph = 0; ph < 4; ++ph)
+            grid.x += cdiv((int64_t)d.N * ((d.Ho - (ph >> 1) + 1) / 2) * ((d.Wo - (ph & 1) + 1) / 2), BM);
+        if (grid.x == 0) return IC_OK;
+    }
     const bool res_conv = d.KH == 3 && !d.transposed && d.Cin == 128 && d.Cout == 128;
     ProfScope ps(res_conv ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER, stream);
     conv_simt_kernel<<<grid, NT, 0, stream>>>(d);

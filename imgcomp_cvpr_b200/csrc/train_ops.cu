@@ -122,9 +122,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradDesc d) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int64_t hw = (int64_t)g.Ho * g.Wo;
-    for (int64_t mb = m_begin; mb < m_end; mb += WM) {
+    // gathers this thread's float4 of the A (im2col) and B (output gradient) tiles of the 16 rows starting at mb
+    auto load = [&](int64_t mb, float4& a, float4& b) {
         const int64_t m = mb + lm;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+        b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < m_end) {
             const int pn = (int)(m / hw);
             const int r = (int)(m - (int64_t)pn * hw);
@@ -147,10 +149,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradDesc d) {
             }
             if (nvalid) b = *reinterpret_cast<const float4*>(d.dy + m * g.Cout + n0 + l4);
         }
+    };
+    float4 a, b;
+    load(m_begin, a, b);
+    for (int64_t mb = m_begin; mb < m_end; mb += WM) {
         __syncthreads();
         *reinterpret_cast<float4*>(&As[lm][l4]) = a;
         *reinterpret_cast<float4*>(&Bs[lm][l4]) = b;
         __syncthreads();
+        if (mb + WM < m_end) load(mb + WM, a, b);        // in flight while this tile is consumed
 #pragma unroll
         for (int mm = 0; mm < WM; ++mm) {
             const float4 av = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
@@ -607,7 +614,12 @@ size_t ic_nn_conv2d_workspace_bytes(int N, int Hi, int Wi, int Cin, int KH, int 
     Geo g{N, Hi, Wi, Cin, KH, KW, stride, Cout, transposed, valid, 0, 0, 0, 0};
     if (make_geo(g) != IC_OK) return 0;
     const size_t wbytes = (size_t)KH * KW * Cin * Cout * sizeof(float);
-    return align_up(wbytes, 256) + align_up((size_t)wgrad_splits(g) * wbytes, 256) + 256;
+    int splits = wgrad_splits(g);
+    if (transposed) {       // the filter gradient runs on the swapped (regular strided conv) geometry
+        Geo g2{N, g.Ho, g.Wo, Cout, KH, KW, stride, Cin, 0, 0, 0, 0, 0, 0};
+        if (make_geo(g2) == IC_OK) splits = std::max(splits, wgrad_splits(g2));
+    }
+    return 2 * align_up(wbytes, 256) + align_up((size_t)splits * wbytes, 256) + 256;
 }
 
 int ic_nn_conv2d_fwd(const float* d_x, const float* d_w, int N, int Hi, int Wi, int Cin, int KH, int KW, int stride, int Cout,
@@ -658,23 +670,44 @@ int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, 
     int rc = make_geo(g);
     if (rc != IC_OK) return rc;
     const int64_t count = (int64_t)KH * KW * Cin * Cout;
-    const int splits = wgrad_splits(g);
-    IC_REQUIRE(workspace_bytes >= (size_t)splits * count * sizeof(float), IC_ERR_WORKSPACE,
-               "ic_nn_conv2d_bwd_filter: workspace too small (use ic_nn_conv2d_workspace_bytes)");
     cudaStream_t s = (cudaStream_t)stream;
+    // conv2d_transpose: y[i*s - pad + tap] += x[i] w[tap], so dW[tap][ci][co] = sum_i x[i][ci] dy[i*s - pad + tap][co]:
+    // the filter gradient of the REGULAR strided conv dy-shaped -> x-shaped with the roles of the tensors swapped and
+    // the two channel axes transposed.  Iterating over the (4x fewer) input pixels i visits only taps that exist,
+    // where the output-pixel form would multiply 3 zeros out of 4.
+    Geo gr = g;
+    const float *a_src = d_x, *b_src = d_dy;
+    if (transposed) {
+        gr = Geo{N, g.Ho, g.Wo, Cout, KH, KW, stride, Cin, 0, 0, 0, 0, 0, 0};
+        rc = make_geo(gr);
+        if (rc != IC_OK) return rc;
+        IC_REQUIRE(gr.Ho == Hi && gr.Wo == Wi, IC_ERR_STATE, "ic_nn_conv2d_bwd_filter: transposed geometry");
+        a_src = d_dy;
+        b_src = d_x;
+    }
+    const int splits = wgrad_splits(gr);
+    const size_t wb = align_up((size_t)count * sizeof(float), 256);
+    IC_REQUIRE(workspace_bytes >= wb + (size_t)splits * count * sizeof(float), IC_ERR_WORKSPACE,
+               "ic_nn_conv2d_bwd_filter: workspace too small (use ic_nn_conv2d_workspace_bytes)");
+    float* tmp = (float*)d_workspace;                               // [tap][Cout][Cin] before the channel transpose
+    float* part = (float*)((char*)d_workspace + wb);
     WgradDesc d;
-    d.x = d_x; d.dy = d_dy; d.part = (float*)d_workspace; d.g = g;
-    d.M = (int64_t)N * g.Ho * g.Wo;
+    d.x = a_src; d.dy = b_src; d.part = part; d.g = gr;
+    d.M = (int64_t)N * gr.Ho * gr.Wo;
     d.m_per_split = (d.M + splits - 1) / splits;
     d.m_per_split = (d.m_per_split + WM - 1) / WM * WM;
-    const int K = KH * KW * Cin;
-    dim3 grid(cdiv(K, WT), cdiv(Cout, WT), splits);
+    const int K = KH * KW * gr.Cin;
+    dim3 grid(cdiv(K, WT), cdiv(gr.Cout, WT), splits);
     {
-        ProfScope ps(IC_PROF_CONV_OTHER, s, 2);
+        ProfScope ps(IC_PROF_CONV_OTHER, s, transposed ? 3 : 2);
         conv_wgrad_kernel<<<grid, 256, 0, s>>>(d);
         IC_CHECK_LAUNCH();
-        sum_splits_kernel<<<ew_grid(count), 256, 0, s>>>((const float*)d_workspace, splits, count, d_dw);
+        sum_splits_kernel<<<ew_grid(count), 256, 0, s>>>(part, splits, count, transposed ? tmp : d_dw);
         IC_CHECK_LAUNCH();
+        if (transposed) {
+            transpose_taps_kernel<<<ew_grid(count), 256, 0, s>>>(tmp, d_dw, KH * KW, Cout, Cin);
+            IC_CHECK_LAUNCH();
+        }
     }
     return IC_OK;
 }
