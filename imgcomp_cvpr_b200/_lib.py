@@ -91,10 +91,14 @@ SIGNATURES = {
                                 c_float, c_void_p, c_void_p]),
     'ic_nn_normalize_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ic_nn_hq_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int] + [c_void_p] * 7),
-    'ic_nn_pc_pad_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'ic_nn_pc_pad_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'ic_nn_pc_xent_fwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ic_nn_pc_xent_bwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
-                                  c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p]),
+    'ic_nn_rate_coef': (c_int, [c_void_p, c_int64, c_float, c_float, c_int, c_void_p, c_void_p]),
+    'ic_nn_scale_dev': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'ic_nn_adam_step_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float,
+                                    c_void_p, c_void_p]),
     'ic_nn_crop_fwd': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ic_nn_crop_bwd_add': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ic_msssim_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),

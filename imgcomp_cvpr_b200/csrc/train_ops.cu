@@ -506,13 +506,29 @@ __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, cons
         out[i] = a * x[i] + (y ? b * y[i] : 0.f);
 }
 
+// out = a[0] * x
+__global__ void scale_dev_kernel(const float* __restrict__ a, const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    const float s = a[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = s * x[i];
+}
+
+// d pc_loss / d bc coefficient of code/train.py:309-316: beta * 0.5 / n when 0.5 * (H_mask + H_real) > H_target, else 0
+__global__ void rate_coef_kernel(const double* __restrict__ sums, double n, float beta, float h_target, int has_heatmap,
+                                 float* __restrict__ coef) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double h_real = sums[0] / n, h_mask = has_heatmap ? sums[1] / n : h_real;
+    coef[0] = (0.5 * (h_mask + h_real) > (double)h_target) ? (float)((double)beta * 0.5 / n) : 0.f;
+}
+
 __global__ void mul_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, float* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = x[i] * y[i];
 }
 
 // tf.train.AdamOptimizer._apply_dense; grad_scale folds the regulariser: g = grad + l2 * w
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, float lr_t, float beta1, float beta2, float eps, float l2, const float* __restrict__ mask) {
+                            int64_t n, float lr_t, float beta1, float beta2, float eps, float l2, const float* __restrict__ mask,
+                            const float* __restrict__ lr_ptr) {
+    if (lr_ptr) lr_t = lr_ptr[0];      // bias-corrected step size written by the host before a CUDA-graph replay
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float gi = g[i] + l2 * w[i];
         if (mask) gi *= mask[i];
@@ -532,10 +548,11 @@ inline int ew_grid(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 1
 // so that the (2,3,3) VALID conv3d of code/probclass.py:227-261 is two VALID conv2d passes over the contiguous
 // slice ranges [0, D-1) and [1, D) (filter depth 0 and 1), accumulated.
 // pad_for_probclass3d (code/probclass.py:268-292): q NCHW -> (C+4, N, h+8, w+8, 4), channel 0 = value, 1..3 = 0
-__global__ void pc_pad_kernel(const float* __restrict__ q, int N, int C, int h, int w, float pad_value, int64_t total,
-                              float4* __restrict__ out) {
+__global__ void pc_pad_kernel(const float* __restrict__ q, int N, int C, int h, int w, float pad_value,
+                              const float* __restrict__ pad_ptr, int64_t total, float4* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    if (pad_ptr) pad_value = pad_ptr[0];
     const int Wp = w + 8, Hp = h + 8;
     const int x = (int)(i % Wp);
     int64_t r = i / Wp;
@@ -554,7 +571,7 @@ __global__ void pc_pad_kernel(const float* __restrict__ q, int N, int C, int h, 
 template <bool BWD>
 __global__ void pc_xent_kernel(const float* __restrict__ logits, int Cs, int L, const int64_t* __restrict__ symbols,
                                const float* __restrict__ heatmap, int N, int C, int h, int w, float coef_real, float coef_mask,
-                               int64_t total, float* __restrict__ out) {
+                               const float* __restrict__ coef_ptr, int64_t total, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // row in (C, N, h, w) order
     if (i >= total) return;
     const int64_t hw = (int64_t)h * w;
@@ -573,6 +590,7 @@ __global__ void pc_xent_kernel(const float* __restrict__ logits, int Cs, int L, 
     if (!BWD) {
         out[j] = (logf(s) - (lg[sym] - m)) * log2e;
     } else {
+        if (coef_ptr) coef_real = coef_mask = coef_ptr[0];
         const float g = (coef_real + (heatmap ? coef_mask * heatmap[j] : coef_mask)) * log2e;
         float* o = out + i * Cs;
         for (int k = 0; k < Cs; ++k) o[k] = k < L ? g * (expf(lg[k] - m) / s - (k == sym ? 1.f : 0.f)) : 0.f;
@@ -848,7 +866,37 @@ int ic_nn_adam_step(float* d_w, const float* d_grad, float* d_m, float* d_v, int
     IC_REQUIRE(d_w && d_grad && d_m && d_v && n >= 0 && step >= 1, IC_ERR_INVALID, "ic_nn_adam_step: bad argument");
     if (n == 0) return IC_OK;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_w, d_grad, d_m, d_v, n, (float)lr_t, beta1, beta2, eps, l2, d_mask);
+    adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_w, d_grad, d_m, d_v, n, (float)lr_t, beta1, beta2, eps, l2, d_mask,
+                                                              nullptr);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* the same update with the bias-corrected step size lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) read from device
+ * memory (d_lr_t[0]): the launch arguments do not change from step to step, so the step can live in a CUDA graph */
+int ic_nn_adam_step_dev(float* d_w, const float* d_grad, float* d_m, float* d_v, int64_t n, const float* d_lr_t, float beta1,
+                        float beta2, float eps, float l2, const float* d_mask, void* stream) {
+    IC_REQUIRE(d_w && d_grad && d_m && d_v && d_lr_t && n >= 0, IC_ERR_INVALID, "ic_nn_adam_step_dev: bad argument");
+    if (n == 0) return IC_OK;
+    adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_w, d_grad, d_m, d_v, n, 0.f, beta1, beta2, eps, l2, d_mask, d_lr_t);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* out = d_a[0] * x (scalar in device memory) */
+int ic_nn_scale_dev(const float* d_a, const float* d_x, int64_t n, float* d_out, void* stream) {
+    IC_REQUIRE(d_a && d_x && d_out && n >= 0, IC_ERR_INVALID, "ic_nn_scale_dev: bad argument");
+    if (n == 0) return IC_OK;
+    scale_dev_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_a, d_x, n, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* d pc_loss / d bitcost coefficient of code/train.py:309-316 from the sums of ic_masked_sums_fwd, on the device:
+ * d_coef[0] = beta * 0.5 / n if 0.5 * (mean(bc * heatmap) + mean(bc)) > H_target else 0 */
+int ic_nn_rate_coef(const double* d_sums, int64_t n, float beta, float h_target, int has_heatmap, float* d_coef, void* stream) {
+    IC_REQUIRE(d_sums && d_coef && n > 0, IC_ERR_INVALID, "ic_nn_rate_coef: bad argument");
+    rate_coef_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_sums, (double)n, beta, h_target, has_heatmap, d_coef);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -867,10 +915,12 @@ int ic_nn_hq_fwd(const float* d_bn, int N, int h, int w, int C, int Cb, int heat
                                    d_qsoft, (cudaStream_t)stream, Cb);
 }
 
-int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pad_value, float* d_out, void* stream) {
+int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pad_value, const float* d_pad_value, float* d_out,
+                     void* stream) {
     IC_REQUIRE(d_q_nchw && d_out && N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_nn_pc_pad_fwd: bad argument");
     const int64_t total = (int64_t)(C + 4) * N * (h + 8) * (w + 8);
-    pc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_q_nchw, N, C, h, w, pad_value, total, (float4*)d_out);
+    pc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_q_nchw, N, C, h, w, pad_value, d_pad_value, total,
+                                                                                      (float4*)d_out);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -880,17 +930,17 @@ int ic_nn_pc_xent_fwd(const float* d_logits, int Cs, int L, const int64_t* d_sym
     IC_REQUIRE(d_logits && d_symbols && d_bc_nchw && L >= 1 && Cs >= L, IC_ERR_INVALID, "ic_nn_pc_xent_fwd: bad argument");
     const int64_t total = (int64_t)N * C * h * w;
     pc_xent_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_logits, Cs, L, d_symbols, nullptr, N, C, h, w, 0.f, 0.f,
-                                                                            total, d_bc_nchw);
+                                                                            nullptr, total, d_bc_nchw);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
 
 int ic_nn_pc_xent_bwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, const float* d_heatmap, int N, int C, int h,
-                      int w, float coef_real, float coef_mask, float* d_dlogits, void* stream) {
+                      int w, float coef_real, float coef_mask, const float* d_coef, float* d_dlogits, void* stream) {
     IC_REQUIRE(d_logits && d_symbols && d_dlogits && L >= 1 && Cs >= L, IC_ERR_INVALID, "ic_nn_pc_xent_bwd: bad argument");
     const int64_t total = (int64_t)N * C * h * w;
     pc_xent_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_logits, Cs, L, d_symbols, d_heatmap, N, C, h, w, coef_real,
-                                                                           coef_mask, total, d_dlogits);
+                                                                           coef_mask, d_coef, total, d_dlogits);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

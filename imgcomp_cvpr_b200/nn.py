@@ -212,10 +212,13 @@ def adam_step(w, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, l2=0.0,
 
 
 def pc_pad_fwd(q, pad_value):
-    """pad_for_probclass3d (code/probclass.py:268-292): q N,C,h,w -> depth-major (C+4, N, h+8, w+8, 4), channel 0 = value"""
+    """pad_for_probclass3d (code/probclass.py:268-292): q N,C,h,w -> depth-major (C+4, N, h+8, w+8, 4), channel 0 = value.
+    pad_value: host float, or a CUDA tensor whose first element is read on the device (no host read-back)"""
     N, C, h, w = q.shape
     out = torch.empty((C + 4, N, h + 8, w + 8, 4), dtype=torch.float32, device=q.device)
-    _lib.check(_lib.lib().ic_nn_pc_pad_fwd(_lib.ptr(_f32(q)), N, C, h, w, float(pad_value), _lib.ptr(out), _lib.stream_ptr()))
+    dev = pad_value if torch.is_tensor(pad_value) else None
+    _lib.check(_lib.lib().ic_nn_pc_pad_fwd(_lib.ptr(_f32(q)), N, C, h, w, 0.0 if dev is not None else float(pad_value), _lib.ptr(dev),
+                                          _lib.ptr(out), _lib.stream_ptr()))
     return out
 
 
@@ -228,13 +231,35 @@ def pc_xent_fwd(logits, L, symbols):
     return bc
 
 
-def pc_xent_bwd(logits, L, symbols, heatmap, coef_real, coef_mask):
-    """-> d logits (C, N, h, w, Cs) for the upstream gradient (coef_real + coef_mask * heatmap) per symbol"""
+def pc_xent_bwd(logits, L, symbols, heatmap, coef_real=0.0, coef_mask=0.0, coef_dev=None):
+    """-> d logits (C, N, h, w, Cs) for the upstream gradient (coef_real + coef_mask * heatmap) per symbol;
+    coef_dev (1-element CUDA tensor from rate_coef) overrides both coefficients on the device"""
     C, N, h, w, Cs = logits.shape
     d = torch.empty_like(logits)
     _lib.check(_lib.lib().ic_nn_pc_xent_bwd(_lib.ptr(_f32(logits)), Cs, L, _lib.ptr(symbols), _lib.ptr(heatmap), N, C, h, w,
-                                           float(coef_real), float(coef_mask), _lib.ptr(d), _lib.stream_ptr()))
+                                           float(coef_real), float(coef_mask), _lib.ptr(coef_dev), _lib.ptr(d), _lib.stream_ptr()))
     return d
+
+
+def rate_coef(sums, n, beta, h_target, has_heatmap, out):
+    """out[0] = beta * 0.5 / n if the rate hinge of code/train.py:309-316 is active else 0, computed on the device"""
+    _lib.check(_lib.lib().ic_nn_rate_coef(_lib.ptr(sums), int(n), float(beta), float(h_target), int(bool(has_heatmap)), _lib.ptr(out),
+                                         _lib.stream_ptr()))
+    return out
+
+
+def scale_dev(a, x):
+    """a[0] * x with the scalar in device memory"""
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().ic_nn_scale_dev(_lib.ptr(a), _lib.ptr(_f32(x)), x.numel(), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def adam_step_dev(w, grad, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, l2=0.0, mask=None):
+    """in place on w, m, v; lr_t: 1-element CUDA tensor holding lr * sqrt(1 - beta2^t) / (1 - beta1^t)"""
+    _lib.check(_lib.lib().ic_nn_adam_step_dev(_lib.ptr(_f32(w)), _lib.ptr(_f32(grad)), _lib.ptr(_f32(m)), _lib.ptr(_f32(v)), w.numel(),
+                                             _lib.ptr(lr_t), float(beta1), float(beta2), float(eps), float(l2), _lib.ptr(mask),
+                                             _lib.stream_ptr()))
 
 
 def crop_fwd(x, crop):

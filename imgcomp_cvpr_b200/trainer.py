@@ -194,6 +194,13 @@ class Trainer(object):
                 self._group_of[key] = gname
         self.tape = None
         self._adam_t = 0
+        self._graph = None
+        self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)     # [sum bc, sum bc*hm, (sum w, sum w^2) x 3 groups]
+        self._coef = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._val = None
+        self._loss_ws = torch.empty(_lib.lib().ic_loss_workspace_bytes(), dtype=torch.uint8, device=self.device)
+        self._lr_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._lr_dev = torch.zeros(2, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ parameter access
     def _w(self, key):
@@ -415,8 +422,9 @@ class Trainer(object):
         return self._bias_act(self._conv3d(net, S[3]), S[3], True)
 
     # ------------------------------------------------------------------ the graph of code/train.py:86-132
-    def forward_backward(self, x, is_training=True, update_moving=False, backward=True):
-        """-> dict of loss components (floats) and tensors; gradients are left in the groups' g buffers."""
+    def _enqueue(self, x, is_training, update_moving, backward):
+        """Enqueues forward (+ backward) without any host read-back: the loss scalars stay in self._sums / self._val, the
+        rate hinge coefficient is computed on the device.  -> dict of tensors"""
         cfg = self.ae_config
         assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
         x = x.contiguous()
@@ -425,58 +433,41 @@ class Trainer(object):
         self.is_training, self.update_moving = is_training, update_moving
         self.tape = tape = _Tape() if backward else None
         centers = self._w('autoencoder/encoder/centers')
-        # pc.auto_pad_value(ae) = centers[0] (code/probclass.py:59-61); read before anything is enqueued (idle stream)
-        cvals = centers.detach().cpu().numpy().astype(np.float64)
-        pad_value = float(cvals[0]) if self.pc_config.use_centers_for_padding else 0.0
+        # pc.auto_pad_value(ae) = centers[0] (code/probclass.py:59-61), read on the device
+        pad_value = centers if self.pc_config.use_centers_for_padding else 0.0
         enc = self._encode(x)
         n_enc = len(tape.fns) if backward else 0
         q_nhwc = nn.nchw_to_nhwc(enc['qbar'])
         x_out = self._decode(q_nhwc)
         logits = self._pc_logits(enc['qbar'], pad_value)                 # stop_gradient(qbar): no backward into q
         bc = nn.pc_xent_fwd(logits, self.L, enc['symbols'])
-        # ---- losses (code/train.py:303-336, 352-431)
+        # ---- losses (code/train.py:303-336, 352-431): sums of bc, bc * heatmap, w^2 per regularised group
         xf = x if x.dtype == torch.float32 else x.float()
         Lb = _lib.lib()
-        sums = torch.empty(8, dtype=torch.float64, device=x.device)
-        ws = torch.empty(Lb.ic_loss_workspace_bytes(), dtype=torch.uint8, device=x.device)
+        sums, ws = self._sums, self._loss_ws
         hm = enc['heatmap']
-        _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(bc), _lib.ptr(hm), bc.numel(), _lib.ptr(sums), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
-        gw = self.groups['ae_w']
-        _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(gw.w), _lib.ptr(gw.w), gw.w.numel(), _lib.ptr(sums[2:]), _lib.ptr(ws), ws.numel(),
-                                         _lib.stream_ptr()))
-        gp = self.groups['pc_w']
-        _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(gp.w), _lib.ptr(gp.w), gp.w.numel(), _lib.ptr(sums[4:]), _lib.ptr(ws), ws.numel(),
-                                         _lib.stream_ptr()))
+
+        def masked_sums(a, b, n, out):
+            _lib.check(Lb.ic_masked_sums_fwd(_lib.ptr(a), _lib.ptr(b), n, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        masked_sums(bc, hm, bc.numel(), sums)
+        for i, g in enumerate((self.groups['ae_w'], self.groups['pc_w'], self.groups['ae_centers'])):
+            masked_sums(g.w, g.w, g.w.numel(), sums[2 + 2 * i:])
         if cfg.distortion_to_minimize != 'ms_ssim':
             raise NotImplementedError('only distortion_to_minimize = ms_ssim (the published configs) has a backward kernel')
-        d_xout, msssim = nn.msssim_tf_bwd(xf, x_out, -float(cfg.K_ms_ssim))       # d/dx_out of K (1 - MS-SSIM)
-        host = sums.cpu().tolist()                                       # the step's one read-back (loss scalars)
-        msssim = float(msssim.item())
-        n = bc.numel()
-        H_real = host[0] / n
-        H_mask = host[1] / n if hm is not None else H_real
-        H_soft = 0.5 * (H_mask + H_real)
-        pc_loss = cfg.beta * max(H_soft - cfg.H_target, 0.0)
-        d_loss = cfg.K_ms_ssim * (1.0 - msssim)
-        reg_enc_dec = cfg.regularization_factor * 0.5 * host[3]
-        if cfg.regularization_factor_centers != 0:
-            reg_enc_dec += cfg.regularization_factor_centers * 0.5 * float((cvals ** 2).sum())
-        rf_pc = self.pc_config.regularization_factor
-        reg_pc = 0.0 if rf_pc is None else rf_pc * 0.5 * host[5]
-        out = dict(total_loss=d_loss + pc_loss + reg_enc_dec + reg_pc, d_loss_scaled=d_loss, pc_loss=pc_loss, H_real=H_real,
-                   H_mask=H_mask, ms_ssim=msssim, reg=reg_enc_dec + reg_pc, bpp=host[0] / (N * H * W),
-                   tensors=dict(bc=bc, heatmap=hm, x_out=x_out, symbols=enc['symbols'], qbar=enc['qbar'], z=enc['z']))
+        d_xout, self._val = nn.msssim_tf_bwd(xf, x_out, -float(cfg.K_ms_ssim))    # d/dx_out of K (1 - MS-SSIM)
+        tensors = dict(bc=bc, heatmap=hm, x_out=x_out, symbols=enc['symbols'], qbar=enc['qbar'], z=enc['z'])
         if not backward:
-            return out
+            return tensors
         # ---- backward, in reverse order of the graph
-        coef = cfg.beta * 0.5 / n if H_soft > cfg.H_target else 0.0
-        tape.acc(logits, nn.pc_xent_bwd(logits, self.L, enc['symbols'], hm, coef, coef), owned=True)
+        n = bc.numel()
+        coef = nn.rate_coef(sums, n, cfg.beta, cfg.H_target, hm is not None, self._coef)
+        tape.acc(logits, nn.pc_xent_bwd(logits, self.L, enc['symbols'], hm, coef_dev=coef), owned=True)
         tape.acc(x_out, d_xout, owned=True)
         bn = enc['bn']
 
         def hq_bwd():
             dq = tape.pop(q_nhwc)
-            dhm = nn.axpby(coef, bc) if (hm is not None and coef != 0.0) else None       # d pc_loss / d heatmap3D
+            dhm = nn.scale_dev(coef, bc) if hm is not None else None                  # d pc_loss / d heatmap3D
             dbn, _ = nn.hq_bwd(bn, self.C, self.heatmap, centers, dq, dhm, dcenters=self._g('autoencoder/encoder/centers'))
             tape.acc(bn, dbn, owned=True)
         # the tape so far: encoder ops, decoder ops, context-model ops.  The quantizer's backward must run after the
@@ -484,7 +475,31 @@ class Trainer(object):
         tape.fns.insert(n_enc, hq_bwd)
         tape.backward()
         self.tape = None
-        return out
+        return tensors
+
+    def _read_losses(self, shape, n_symbols, tensors):
+        """the step's one read-back: loss scalars -> the components code/train.py logs"""
+        cfg = self.ae_config
+        N, _, H, W = shape
+        host = self._sums.cpu().tolist()
+        msssim = float(self._val.item())
+        H_real = host[0] / n_symbols
+        H_mask = host[1] / n_symbols if self.heatmap else H_real
+        H_soft = 0.5 * (H_mask + H_real)
+        pc_loss = cfg.beta * max(H_soft - cfg.H_target, 0.0)
+        d_loss = cfg.K_ms_ssim * (1.0 - msssim)
+        reg_enc_dec = cfg.regularization_factor * 0.5 * host[3]
+        if cfg.regularization_factor_centers != 0:
+            reg_enc_dec += cfg.regularization_factor_centers * 0.5 * host[7]
+        rf_pc = self.pc_config.regularization_factor
+        reg_pc = 0.0 if rf_pc is None else rf_pc * 0.5 * host[5]
+        return dict(total_loss=d_loss + pc_loss + reg_enc_dec + reg_pc, d_loss_scaled=d_loss, pc_loss=pc_loss, H_real=H_real,
+                    H_mask=H_mask, ms_ssim=msssim, reg=reg_enc_dec + reg_pc, bpp=host[0] / (N * H * W), tensors=tensors)
+
+    def forward_backward(self, x, is_training=True, update_moving=False, backward=True):
+        """-> dict of loss components (floats) and tensors; gradients are left in the groups' g buffers."""
+        tensors = self._enqueue(x, is_training, update_moving, backward)
+        return self._read_losses(x.shape, tensors['bc'].numel(), tensors)
 
     # ------------------------------------------------------------------ optimiser (code/train.py:339-349)
     def learning_rates(self):
@@ -498,26 +513,67 @@ class Trainer(object):
             return cfg.lr_initial * cfg.lr_schedule_decay_rate ** p
         return lr(self.ae_config), lr(self.pc_config)
 
-    def apply_gradients(self):
-        lr_ae, lr_pc = self.learning_rates()
-        self._adam_t += 1
+    def _adam_plan(self):
         cfg = self.ae_config
         plan = []
         if cfg.train_autoencoder:
-            plan += [('ae_w', lr_ae, cfg.regularization_factor), ('ae_bn', lr_ae, 0.0),
-                     ('ae_centers', lr_ae, cfg.regularization_factor_centers)]
+            plan += [('ae_w', 0, cfg.regularization_factor), ('ae_bn', 0, 0.0), ('ae_centers', 0, cfg.regularization_factor_centers)]
         if cfg.train_probclass:
-            plan += [('pc_w', lr_pc, self.pc_config.regularization_factor or 0.0), ('pc_b', lr_pc, 0.0)]
-        for name, lr, l2 in plan:
+            plan += [('pc_w', 1, self.pc_config.regularization_factor or 0.0), ('pc_b', 1, 0.0)]
+        return plan
+
+    def _stage_step_sizes(self):
+        """tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), t counting from 1; written to device memory
+        (pinned staging buffer, asynchronous copy) so that the Adam launches do not change from step to step"""
+        self._adam_t += 1
+        t = self._adam_t
+        corr = math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        lr_ae, lr_pc = self.learning_rates()
+        self._lr_host[0], self._lr_host[1] = lr_ae * corr, lr_pc * corr
+        self._lr_dev.copy_(self._lr_host, non_blocking=True)
+
+    def _enqueue_adam(self):
+        for name, which, l2 in self._adam_plan():
             g = self.groups[name]
-            nn.adam_step(g.w, g.g, g.m, g.v, lr, self._adam_t, l2=l2)
+            nn.adam_step_dev(g.w, g.g, g.m, g.v, self._lr_dev[which:], l2=l2)
+
+    def apply_gradients(self):
+        self._stage_step_sizes()
+        self._enqueue_adam()
         self.global_step += 1
 
     def step(self, x):
-        """one sess.run(train_op) of the reference: forward, loss, backward, BN moving averages, both Adam updates"""
-        out = self.forward_backward(x, is_training=True, update_moving=True)
+        """one sess.run(train_op) of the reference: forward, loss, backward, BN moving averages, both Adam updates.
+        With enable_cuda_graph() the whole step (~1250 kernel launches) is one graph replay."""
+        if self._graph is not None and tuple(x.shape) == tuple(self._x_static.shape) and x.dtype == self._x_static.dtype:
+            self._x_static.copy_(x, non_blocking=True)
+            self._stage_step_sizes()
+            self._graph.replay()
+            self.global_step += 1
+            return self._read_losses(x.shape, self._graph_tensors['bc'].numel(), self._graph_tensors)
+        tensors = self._enqueue(x, True, True, True)
         self.apply_gradients()
-        return out
+        return self._read_losses(x.shape, tensors['bc'].numel(), tensors)
+
+    def enable_cuda_graph(self, x_example):
+        """Captures forward + loss + backward + moving averages + Adam for batches of x_example's shape / dtype in ONE CUDA
+        graph.  Nothing in the step reads back to the host (the hinge coefficient, the pad value and the Adam step sizes
+        live in device memory), so a replay enqueues ~1250 kernels without per-launch host work.  The tensors of the
+        returned dicts are then views into graph memory: valid until the next step."""
+        self._x_static = x_example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                # warm-up: first-call initialisations, workspace growth (no state change)
+            for _ in range(2):
+                self._enqueue(self._x_static, True, False, True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._graph_tensors = self._enqueue(self._x_static, True, True, True)
+            self._enqueue_adam()
+        self._graph = graph
+        return self
 
 
 def train_loop(trainer, batches, log_interval=100, log=print):

@@ -254,6 +254,9 @@ int ic_nn_mul(const float* d_x, const float* d_y, int64_t n, float* d_out, void*
  * (slim l2 regulariser, code/autoencoder.py:101-102), optional 0/1 mask on g, step counts from 1. */
 int ic_nn_adam_step(float* d_w, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int64_t step, float l2, const float* d_mask, void* stream);
+/* same update, bias-corrected step size lr * sqrt(1 - beta2^t) / (1 - beta1^t) read from d_lr_t[0] (CUDA-graph friendly) */
+int ic_nn_adam_step_dev(float* d_w, const float* d_grad, float* d_m, float* d_v, int64_t n, const float* d_lr_t, float beta1,
+                        float beta2, float eps, float l2, const float* d_mask, void* stream);
 
 /* _normalize (code/autoencoder.py:136-144,160-169): x NCHW (uint8 or float32 in [0,255]) -> normalised NHWC with 4
  * channels (the 4th is zero padding) */
@@ -266,7 +269,8 @@ int ic_nn_hq_fwd(const float* d_bn, int N, int h, int w, int C, int Cb, int heat
  * (C+4, N, h+8, w+8, 4 channels: value, 0, 0, 0), so that the (2,3,3) VALID conv3d (code/probclass.py:227-261) is two
  * VALID ic_nn_conv2d_* passes over the contiguous slice ranges [0, D-1) and [1, D), accumulated with ic_nn_axpby.
  * ic_nn_pc_pad_fwd = pad_for_probclass3d (code/probclass.py:268-292). */
-int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pad_value, float* d_out, void* stream);
+int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pad_value, const float* d_pad_value, float* d_out,
+                     void* stream);   /* d_pad_value (optional): the pad value is read from device memory (centers[0]) */
 /* softmax_cross_entropy_with_logits * log2(e) (code/probclass.py:99-104).  d_logits: rows in (C, N, h, w) order, Cs
  * floats per row, the first L valid; d_symbols / d_heatmap / d_bc_nchw in the reference's NCHW order.
  * backward: d_dlogits[row][k] = (coef_real + coef_mask * heatmap) * log2(e) * (softmax_k - [k == symbol]); these are
@@ -275,7 +279,13 @@ int ic_nn_pc_pad_fwd(const float* d_q_nchw, int N, int C, int h, int w, float pa
 int ic_nn_pc_xent_fwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, int N, int C, int h, int w, float* d_bc_nchw,
                       void* stream);
 int ic_nn_pc_xent_bwd(const float* d_logits, int Cs, int L, const int64_t* d_symbols, const float* d_heatmap, int N, int C, int h,
-                      int w, float coef_real, float coef_mask, float* d_dlogits, void* stream);
+                      int w, float coef_real, float coef_mask, const float* d_coef, float* d_dlogits, void* stream);
+/* the hinge coefficient on the device (so that a training step needs no host read-back in its middle and can be
+ * captured in a CUDA graph): d_coef[0] = beta * 0.5 / n if 0.5 * (sums[1] / n + sums[0] / n) > H_target else 0, with
+ * d_sums from ic_masked_sums_fwd; pass d_coef to ic_nn_pc_xent_bwd (overrides coef_real / coef_mask) */
+int ic_nn_rate_coef(const double* d_sums, int64_t n, float beta, float h_target, int has_heatmap, float* d_coef, void* stream);
+/* out = d_a[0] * x, scalar in device memory */
+int ic_nn_scale_dev(const float* d_a, const float* d_x, int64_t n, float* d_out, void* stream);
 /* the residual crop of the 3-D residual block, x[:, 2:, 2:-2, 2:-2, :] (code/probclass.py:185-196), on A slices of
  * H x W x C (C % 4 == 0): out = in[:, crop:-crop, crop:-crop, :]; backward ACCUMULATES into d_dx */
 int ic_nn_crop_fwd(const float* d_in, int64_t A, int H, int W, int C, int crop, float* d_out, void* stream);

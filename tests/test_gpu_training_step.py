@@ -222,3 +222,21 @@ def test_inference_mode_matches_pinned_forward(synth):
     ref = O.val_forward(x, Wt, ae_cfg.num_chan_bn)
     assert (out['tensors']['symbols'].cpu().numpy() != ref['enc']['symbols']).sum() == 0
     assert abs(out['bpp'] - ref['bpp'][0]) < 1e-4
+
+
+def test_cuda_graph_step_is_the_eager_step(synth):
+    """enable_cuda_graph(): forward + loss + backward + moving averages + Adam replayed as one CUDA graph must give
+    exactly what the eager launches give (every reduction in the step has a fixed order)."""
+    ae_cfg, pc_cfg, Wt, x, tr_e = _setup(synth, 'cvpr/low', 2, 64, 64, seed=22, mode='exact')
+    _, _, _, _, tr_g = _setup(synth, 'cvpr/low', 2, 64, 64, seed=22, mode='exact')
+    from imgcomp_cvpr_b200 import weights
+    xs = [torch.from_numpy(weights.synthetic_images(2, 64, 64, seed=30 + i)).cuda() for i in range(3)]
+    tr_g.enable_cuda_graph(xs[0])
+    for xi in xs:
+        a, b = tr_e.step(xi), tr_g.step(xi)
+        for k in ('total_loss', 'd_loss_scaled', 'pc_loss', 'H_real', 'H_mask', 'ms_ssim', 'bpp'):
+            assert a[k] == b[k], (k, a[k], b[k])
+    assert tr_e.global_step == tr_g.global_step == 3
+    We, Wg = tr_e.weights(), tr_g.weights()
+    for k in We:
+        assert np.array_equal(We[k], Wg[k]), k

@@ -25,11 +25,14 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--ae', default='cvpr/med')
     ap.add_argument('--mode', default='exact', choices=['fp32', 'exact'])
+    ap.add_argument('--graph', action='store_true', help='replay the step as one CUDA graph')
     args = ap.parse_args()
     a, p = config.ae_config(args.ae), config.pc_config('cvpr/res_shallow')
     W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
     x = torch.from_numpy(weights.synthetic_images(args.batch, args.size, args.size, seed=77)).cuda()
     tr = trainer.Trainer(a, p, W, num_itr_per_epoch=1000, mode=args.mode)
+    if args.graph:
+        tr.enable_cuda_graph(x)
     L = _lib.lib()
     for _ in range(2):
         out = tr.step(x)
@@ -46,7 +49,7 @@ def main():
     ms = ev[0].elapsed_time(ev[1]) / args.steps
     pix = args.batch * args.size * args.size
     res = {'workload': 'cfg3 training step', 'ae': args.ae, 'batch': args.batch, 'H': args.size, 'W': args.size,
-           'ms_per_step': ms, 'wall_ms_per_step': wall, 'images_per_s': args.batch / (ms * 1e-3), 'MPix_per_s': pix / (ms * 1e-3) / 1e6,
+           'ms_per_step': ms, 'cuda_graph': bool(args.graph), 'wall_ms_per_step': wall, 'images_per_s': args.batch / (ms * 1e-3), 'MPix_per_s': pix / (ms * 1e-3) / 1e6,
            'dtype': {'fp32': 'f32 (FFMA kernels)', 'exact': 'f32 + f16x3 tensor-core 3x3 convs (fwd, dgrad)'}[args.mode], 'loss': out['total_loss'], 'bpp': out['bpp'], 'ms_ssim': out['ms_ssim'],
            'counted_launches_per_step': (L.ic_launch_count() - n0) / args.steps,
            # forward FLOPs of SURVEY.md 8(d) x 3 (forward + data gradient + filter gradient)
