@@ -194,7 +194,9 @@ def main():
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--with-decode', action='store_true', help='also time ae.decode(qhard) (configs[1] lists it; not part of the metric)')
     args = ap.parse_args()
-    assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('IC_BENCH_ALLOW_SHORT'), 'W >= 3 required'
+    if args.warmup < 3 and args.impl != 'reference' and not os.environ.get('IC_BENCH_ALLOW_SHORT'):
+        args.warmup = 3            # timing rule: at least three untimed warm-up steps (reported in the JSON line)
+    args.steps = max(args.steps, 1)
     if args.impl == 'reference':
         return run_reference(args)
 

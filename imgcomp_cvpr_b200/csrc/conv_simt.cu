@@ -17,15 +17,22 @@ namespace ic {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int BK = 16, NT = 256;
 
 __constant__ float c_norm_mean[3] = {121.853699f, 113.588608f, 100.637154f};
 // np.sqrt(var + 1e-10) evaluated in float32 (code/autoencoder.py:143,153,160-169)
 __constant__ float c_norm_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};
 
+// BN_ = 64: 64 pixels x 64 channels per block; BN_ = 32: 128 pixels x 32 channels (layers with <= 32 output channels:
+// the context model's 24, h13's 3, the data gradient into 4-channel inputs).  Per-output arithmetic (one fmaf chain over
+// k in ascending order) does not depend on the tile shape.
+template <int BN_>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
+    constexpr int BM = 64 * 64 / BN_;            // pixels per block
+    constexpr int TXN = BN_ / 4;                 // threads across the channel dimension
+    constexpr int AR = BM / 64;                  // A rows loaded per thread
     __shared__ __align__(16) float As[2][BK][BM + 4];
-    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN_ + 4];
 
     const int t = threadIdx.x;
     const bool phased = d.transposed && d.stride == 2;
@@ -44,7 +51,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
     const int Hq = (d.Ho - pa + 1) / 2, Wq = (d.Wo - pb + 1) / 2;
     const int64_t M = phased ? (int64_t)d.N * Hq * Wq : (int64_t)d.N * d.Ho * d.Wo;      // pixels (of this phase)
     const int64_t m0 = (int64_t)blk * BM;
-    const int n0 = blockIdx.y * BN;
+    const int n0 = blockIdx.y * BN_;
     // taps this block walks: all, or those of the phase's parity
     const int ky0 = phased ? ((pa + d.pad_t) & 1) : 0, kx0 = phased ? ((pb + d.pad_l) & 1) : 0;
     const int kstep = phased ? 2 : 1;
@@ -68,41 +75,47 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
         return true;
     };
 
-    // A-load assignment: one output pixel row, 4 consecutive k
+    // A-load assignment: AR output pixel rows (64 apart), 4 consecutive k
     const int am = t >> 2, ak = (t & 3) * 4;
-    int pn = 0, oy = 0, ox = 0;
-    const bool mvalid = row_pixel(m0 + am, pn, oy, ox);
-    // B-load assignment
-    const int bk = t >> 4, bn = (t & 15) * 4;
+    int pn[AR], oy[AR], ox[AR];
+    bool mvalid[AR];
+#pragma unroll
+    for (int j = 0; j < AR; ++j) {
+        pn[j] = oy[j] = ox[j] = 0;
+        mvalid[j] = row_pixel(m0 + am + 64 * j, pn[j], oy[j], ox[j]);
+    }
+    // B-load assignment (the first 4 * BN_ threads)
+    const int bk = t / TXN, bn = (t % TXN) * 4;
+    const bool bload = t < BK * TXN;
 
-    auto load_a = [&](int k0) -> float4 {
+    auto load_a = [&](int k0, int j) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = k0 + ak;
-        if (mvalid && k < K) {
+        if (mvalid[j] && k < K) {
             int tap = k / d.Cin, ci = k - tap * d.Cin;
             int jy = tap / nkx;
             int ky = ky0 + kstep * jy, kx = kx0 + kstep * (tap - jy * nkx);
             int iy, ix;
             bool ok;
             if (!d.transposed) {
-                iy = oy * d.stride - d.pad_t + ky;
-                ix = ox * d.stride - d.pad_l + kx;
+                iy = oy[j] * d.stride - d.pad_t + ky;
+                ix = ox[j] * d.stride - d.pad_l + kx;
                 ok = iy >= 0 && iy < d.Hi && ix >= 0 && ix < d.Wi;
             } else {
-                int ny = oy + d.pad_t - ky, nx = ox + d.pad_l - kx;
+                int ny = oy[j] + d.pad_t - ky, nx = ox[j] + d.pad_l - kx;
                 ok = ny >= 0 && nx >= 0 && (ny % d.stride) == 0 && (nx % d.stride) == 0;
                 iy = ny / d.stride;
                 ix = nx / d.stride;
                 ok = ok && iy < d.Hi && ix < d.Wi;
             }
-            if (ok) v = *reinterpret_cast<const float4*>(d.in + (((int64_t)pn * d.Hi + iy) * d.Wi + ix) * d.Cin + ci);
+            if (ok) v = *reinterpret_cast<const float4*>(d.in + (((int64_t)pn[j] * d.Hi + iy) * d.Wi + ix) * d.Cin + ci);
         }
         return v;
     };
     auto load_b = [&](int k0) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = k0 + bk;
-        if (k < K && n0 + bn < d.ldw) {
+        if (bload && k < K && n0 + bn < d.ldw) {
             int tap = k / d.Cin, ci = k - tap * d.Cin;
             int jy = tap / nkx;
             int64_t row = (int64_t)((ky0 + kstep * jy) * d.KW + kx0 + kstep * (tap - jy * nkx)) * d.Cin + ci;
@@ -110,29 +123,36 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
         }
         return v;
     };
-    auto store = [&](int buf, float4 a, float4 b) {
-        As[buf][ak + 0][am] = a.x;
-        As[buf][ak + 1][am] = a.y;
-        As[buf][ak + 2][am] = a.z;
-        As[buf][ak + 3][am] = a.w;
-        *reinterpret_cast<float4*>(&Bs[buf][bk][bn]) = b;
+    auto store = [&](int buf, const float4 (&a)[AR], float4 b) {
+#pragma unroll
+        for (int j = 0; j < AR; ++j) {
+            As[buf][ak + 0][am + 64 * j] = a[j].x;
+            As[buf][ak + 1][am + 64 * j] = a[j].y;
+            As[buf][ak + 2][am + 64 * j] = a[j].z;
+            As[buf][ak + 3][am + 64 * j] = a[j].w;
+        }
+        if (bload) *reinterpret_cast<float4*>(&Bs[buf][bk][bn]) = b;
     };
 
-    const int tx = t & 15, ty = t >> 4;
+    const int tx = t % TXN, ty = t / TXN;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    float4 ra = load_a(0), rb = load_b(0);
+    float4 ra[AR], rb;
+#pragma unroll
+    for (int j = 0; j < AR; ++j) ra[j] = load_a(0, j);
+    rb = load_b(0);
     store(0, ra, rb);
     __syncthreads();
     const int nk = (K + BK - 1) / BK;
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) {
-            ra = load_a((kt + 1) * BK);
+#pragma unroll
+            for (int j = 0; j < AR; ++j) ra[j] = load_a((kt + 1) * BK, j);
             rb = load_b((kt + 1) * BK);
         }
 #pragma unroll
@@ -188,6 +208,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvDesc d) {
 int launch_conv_simt(const ConvDesc& d, cudaStream_t stream) {
     IC_REQUIRE(d.Cin % 4 == 0 && d.ldw % 4 == 0, IC_ERR_INVALID, "conv_simt: Cin (%d) and ldw (%d) must be multiples of 4",
                d.Cin, d.ldw);
+    const bool narrow = d.Cout <= 32;
+    const int BN = narrow ? 32 : 64, BM = 64 * 64 / BN;
     int64_t M = (int64_t)d.N * d.Ho * d.Wo;
     dim3 grid(cdiv(M, BM), cdiv(d.Cout, BN));
     if (d.transposed && d.stride == 2) {        // one block range per output phase
@@ -198,7 +220,8 @@ int launch_conv_simt(const ConvDesc& d, cudaStream_t stream) {
     }
     const bool res_conv = d.KH == 3 && !d.transposed && d.Cin == 128 && d.Cout == 128;
     ProfScope ps(res_conv ? IC_PROF_CONV3X3 : IC_PROF_CONV_OTHER, stream);
-    conv_simt_kernel<<<grid, NT, 0, stream>>>(d);
+    if (narrow) conv_simt_kernel<32><<<grid, NT, 0, stream>>>(d);
+    else conv_simt_kernel<64><<<grid, NT, 0, stream>>>(d);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

@@ -92,70 +92,89 @@ struct WgradDesc {
     int64_t m_per_split;
 };
 
-constexpr int WT = 64, WM = 16;
+constexpr int WM = 16;
 
+// WTN = 64: 64 k x 64 output channels per block; WTN = 32: 128 k x 32 channels (layers with <= 32 output channels)
+template <int WTN>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradDesc d) {
-    __shared__ __align__(16) float As[WM][WT + 4];
-    __shared__ __align__(16) float Bs[WM][WT + 4];
+    constexpr int WTK = 64 * 64 / WTN;          // k (tap, cin) entries per block
+    constexpr int TXN = WTN / 4;                // threads across the channel dimension
+    constexpr int KQ = WTK / 4;                 // float4 per A row
+    constexpr int AL = WM * KQ / 256;           // A float4 loads per thread (1 or 2)
+    __shared__ __align__(16) float As[WM][WTK + 4];
+    __shared__ __align__(16) float Bs[WM][WTN + 4];
     const Geo& g = d.g;
     const int t = threadIdx.x;
     const int K = g.KH * g.KW * g.Cin;
-    const int k0 = blockIdx.x * WT, n0 = blockIdx.y * WT;
+    const int k0 = blockIdx.x * WTK, n0 = blockIdx.y * WTN;
     const int64_t m_begin = (int64_t)blockIdx.z * d.m_per_split;
     const int64_t m_end = min(d.M, m_begin + d.m_per_split);
-    const int lm = t >> 4, l4 = (t & 15) * 4;
-    // this thread's 4 consecutive k (same tap: Cin % 4 == 0)
-    const int k = k0 + l4;
-    const bool kvalid = k < K;
-    int ky = 0, kx = 0, ci = 0;
-    if (kvalid) {
-        const int tap = k / g.Cin;
-        ci = k - tap * g.Cin;
-        ky = tap / g.KW;
-        kx = tap - ky * g.KW;
+    // A-load assignment: AL x (row lm_a, 4 consecutive k: same tap since Cin % 4 == 0)
+    int lm_a[AL], l4_a[AL], ky[AL], kx[AL], ci[AL];
+    bool kvalid[AL];
+#pragma unroll
+    for (int j = 0; j < AL; ++j) {
+        const int idx = t + 256 * j;
+        lm_a[j] = idx / KQ;
+        l4_a[j] = (idx % KQ) * 4;
+        const int k = k0 + l4_a[j];
+        kvalid[j] = k < K;
+        ky[j] = kx[j] = ci[j] = 0;
+        if (kvalid[j]) {
+            const int tap = k / g.Cin;
+            ci[j] = k - tap * g.Cin;
+            ky[j] = tap / g.KW;
+            kx[j] = tap - ky[j] * g.KW;
+        }
     }
-    const bool nvalid = n0 + l4 < g.Cout;
-    const int tx = t & 15, ty = t >> 4;
+    // B-load assignment: the first WM * TXN threads
+    const int lm_b = t / TXN, l4_b = (t % TXN) * 4;
+    const bool bload = t < WM * TXN;
+    const bool nvalid = bload && n0 + l4_b < g.Cout;
+    const int tx = t % TXN, ty = t / TXN;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int64_t hw = (int64_t)g.Ho * g.Wo;
-    // gathers this thread's float4 of the A (im2col) and B (output gradient) tiles of the 16 rows starting at mb
-    auto load = [&](int64_t mb, float4& a, float4& b) {
-        const int64_t m = mb + lm;
-        a = make_float4(0.f, 0.f, 0.f, 0.f);
-        b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < m_end) {
-            const int pn = (int)(m / hw);
-            const int r = (int)(m - (int64_t)pn * hw);
-            const int oy = r / g.Wo, ox = r - oy * g.Wo;
-            if (kvalid) {
+    // gathers this thread's float4s of the A (im2col) and B (output gradient) tiles of the 16 rows starting at mb
+    auto load = [&](int64_t mb, float4 (&a)[AL], float4& b) {
+#pragma unroll
+        for (int j = 0; j < AL; ++j) {
+            a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t m = mb + lm_a[j];
+            if (m < m_end && kvalid[j]) {
+                const int pn = (int)(m / hw);
+                const int r = (int)(m - (int64_t)pn * hw);
+                const int oy = r / g.Wo, ox = r - oy * g.Wo;
                 int iy, ix;
                 bool ok;
                 if (!g.transposed) {
-                    iy = oy * g.stride - g.pad_t + ky;
-                    ix = ox * g.stride - g.pad_l + kx;
+                    iy = oy * g.stride - g.pad_t + ky[j];
+                    ix = ox * g.stride - g.pad_l + kx[j];
                     ok = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
                 } else {
-                    const int ny = oy + g.pad_t - ky, nx = ox + g.pad_l - kx;
+                    const int ny = oy + g.pad_t - ky[j], nx = ox + g.pad_l - kx[j];
                     ok = ny >= 0 && nx >= 0 && (ny % g.stride) == 0 && (nx % g.stride) == 0;
                     iy = ny / g.stride;
                     ix = nx / g.stride;
                     ok = ok && iy < g.Hi && ix < g.Wi;
                 }
-                if (ok) a = *reinterpret_cast<const float4*>(d.x + (((int64_t)pn * g.Hi + iy) * g.Wi + ix) * g.Cin + ci);
+                if (ok) a[j] = *reinterpret_cast<const float4*>(d.x + (((int64_t)pn * g.Hi + iy) * g.Wi + ix) * g.Cin + ci[j]);
             }
-            if (nvalid) b = *reinterpret_cast<const float4*>(d.dy + m * g.Cout + n0 + l4);
         }
+        b = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t mbr = mb + lm_b;
+        if (nvalid && mbr < m_end) b = *reinterpret_cast<const float4*>(d.dy + mbr * g.Cout + n0 + l4_b);
     };
-    float4 a, b;
+    float4 a[AL], b;
     load(m_begin, a, b);
     for (int64_t mb = m_begin; mb < m_end; mb += WM) {
         __syncthreads();
-        *reinterpret_cast<float4*>(&As[lm][l4]) = a;
-        *reinterpret_cast<float4*>(&Bs[lm][l4]) = b;
+#pragma unroll
+        for (int j = 0; j < AL; ++j) *reinterpret_cast<float4*>(&As[lm_a[j]][l4_a[j]]) = a[j];
+        if (bload) *reinterpret_cast<float4*>(&Bs[lm_b][l4_b]) = b;
         __syncthreads();
         if (mb + WM < m_end) load(mb + WM, a, b);        // in flight while this tile is consumed
 #pragma unroll
@@ -193,7 +212,8 @@ __global__ void sum_splits_kernel(const float* __restrict__ part, int splits, in
 int wgrad_splits(const Geo& g) {
     const int64_t M = (int64_t)g.N * g.Ho * g.Wo;
     const int K = g.KH * g.KW * g.Cin;
-    const int tiles = cdiv(K, WT) * cdiv(g.Cout, WT);
+    const int wtn = g.Cout <= 32 ? 32 : 64;
+    const int tiles = cdiv(K, 64 * 64 / wtn) * cdiv(g.Cout, wtn);
     int64_t s = (148 * 4 + tiles - 1) / tiles;
     const int64_t smax = std::max<int64_t>(1, M / 256);
     if (s > smax) s = smax;
@@ -717,10 +737,12 @@ int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, 
     d.m_per_split = (d.M + splits - 1) / splits;
     d.m_per_split = (d.m_per_split + WM - 1) / WM * WM;
     const int K = KH * KW * gr.Cin;
-    dim3 grid(cdiv(K, WT), cdiv(gr.Cout, WT), splits);
+    const int wtn = gr.Cout <= 32 ? 32 : 64;
+    dim3 grid(cdiv(K, 64 * 64 / wtn), cdiv(gr.Cout, wtn), splits);
     {
         ProfScope ps(IC_PROF_CONV_OTHER, s, transposed ? 3 : 2);
-        conv_wgrad_kernel<<<grid, 256, 0, s>>>(d);
+        if (wtn == 32) conv_wgrad_kernel<32><<<grid, 256, 0, s>>>(d);
+        else conv_wgrad_kernel<64><<<grid, 256, 0, s>>>(d);
         IC_CHECK_LAUNCH();
         sum_splits_kernel<<<ew_grid(count), 256, 0, s>>>(part, splits, count, transposed ? tmp : d_dw);
         IC_CHECK_LAUNCH();

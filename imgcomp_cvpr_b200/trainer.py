@@ -586,3 +586,80 @@ def train_loop(trainer, batches, log_interval=100, log=print):
             log('{}: loss {:.4f}  d_loss {:.4f}  pc_loss {:.4f}  H_real {:.4f}  bpp {:.4f}  ms_ssim {:.5f}'.format(
                 itr, last['total_loss'], last['d_loss_scaled'], last['pc_loss'], last['H_real'], last['bpp'], last['ms_ssim']))
     return last
+
+
+def random_crops(images, batch_size, crop, rng):
+    """What code/inputpipeline.py:147-213 feeds the graph: `batch_size` random crop_size crops with a random horizontal flip,
+    NCHW uint8.  images: list of H x W x 3 (or 3 x H x W) uint8 arrays at least as large as the crop."""
+    ch, cw = crop
+    out = np.empty((batch_size, 3, ch, cw), np.uint8)
+    for i in range(batch_size):
+        im = images[rng.randint(len(images))]
+        if im.shape[0] == 3 and im.ndim == 3 and im.shape[2] != 3:
+            im = im.transpose(1, 2, 0)
+        y, x = rng.randint(im.shape[0] - ch + 1), rng.randint(im.shape[1] - cw + 1)
+        c = im[y:y + ch, x:x + cw, :3]
+        if rng.randint(2):
+            c = c[:, ::-1]
+        out[i] = c.transpose(2, 0, 1)
+    return out
+
+
+def main():
+    """train.py-style run (code/train.py:471-527 without the TF session / checkpoint / TensorBoard plumbing):
+
+        python -m imgcomp_cvpr_b200.trainer --ae_config cvpr/med --steps 200 [--images 'train/*.png'] [--save out.npz]
+    """
+    import argparse
+    import glob
+    import time
+    from . import config
+    ap = argparse.ArgumentParser(description='training steps of code/train.py on one B200')
+    ap.add_argument('--ae_config', default='cvpr/med')
+    ap.add_argument('--pc_config', default='cvpr/res_shallow')
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--batch_size', type=int, default=None, help='default: the config value (30)')
+    ap.add_argument('--images', default=None, help='glob of training images (default: seeded synthetic images)')
+    ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array to start from (default: seeded synthetic weights)')
+    ap.add_argument('--save', default=None, help='write the trained variables (.npz, TF names) here')
+    ap.add_argument('--num_itr_per_epoch', type=int, default=1000, help='for the staircase LR decay (training_helpers.py:51-60)')
+    ap.add_argument('--log_interval', type=int, default=10)
+    ap.add_argument('--mode', default='exact', choices=['fp32', 'exact'])
+    ap.add_argument('--no_graph', action='store_true', help='do not capture the step in a CUDA graph')
+    ap.add_argument('--seed', type=int, default=0)
+    args = ap.parse_args()
+    a, p = config.ae_config(args.ae_config), config.pc_config(args.pc_config)
+    B = args.batch_size or a.batch_size
+    W = dict(np.load(args.weights)) if args.weights else weights_mod.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k,
+                                                                                       a.arch_param_B)
+    rng = np.random.RandomState(args.seed)
+    if args.images:
+        from PIL import Image
+        images = [np.asarray(Image.open(f).convert('RGB')) for f in sorted(glob.glob(args.images))]
+        images = [im for im in images if im.shape[0] >= a.crop_size[0] and im.shape[1] >= a.crop_size[1]]
+        assert images, 'no image at least as large as the crop %s' % (a.crop_size,)
+    else:
+        images = list(weights_mod.synthetic_images(64, 2 * a.crop_size[0], 2 * a.crop_size[1], seed=args.seed + 1))
+    tr = Trainer(a, p, W, num_itr_per_epoch=args.num_itr_per_epoch, mode=args.mode)
+    pinned = torch.empty((B, 3) + tuple(a.crop_size), dtype=torch.uint8).pin_memory()
+    x = torch.empty_like(pinned, device='cuda')
+    if not args.no_graph:
+        pinned.copy_(torch.from_numpy(random_crops(images, B, a.crop_size, rng)))
+        tr.enable_cuda_graph(x.copy_(pinned))
+    t0, n0 = time.perf_counter(), 0
+    for itr in range(1, args.steps + 1):
+        pinned.copy_(torch.from_numpy(random_crops(images, B, a.crop_size, rng)))
+        out = tr.step(x.copy_(pinned, non_blocking=True))
+        if itr % args.log_interval == 0 or itr == args.steps:
+            dt = time.perf_counter() - t0
+            print('{:6d}  loss {:9.3f}  d_loss {:9.3f}  pc_loss {:8.3f}  H_real {:.4f}  H_mask {:.4f}  bpp {:.4f}  ms_ssim {:.5f}'
+                  '  (img/s: {:.1f})'.format(itr, out['total_loss'], out['d_loss_scaled'], out['pc_loss'], out['H_real'], out['H_mask'],
+                                             out['bpp'], out['ms_ssim'], (itr - n0) * B / dt), flush=True)
+            t0, n0 = time.perf_counter(), itr
+    if args.save:
+        np.savez(args.save, **tr.weights())
+        print('saved', args.save)
+
+
+if __name__ == '__main__':
+    main()
