@@ -47,7 +47,7 @@ namespace tc {
 namespace {
 
 constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels = M 128
-constexpr int MAX_WSTAGES = 8;
+constexpr int MAX_WSTAGES = 16;
 static_assert(MAX_WSTAGES >= 8, "Cfg::WSTAGES must fit the barrier arrays");
 constexpr int MAX_RES_STAGES = 14;          // resident-weight mode: the context model has 14 non-masked taps
 constexpr int NTHREADS = 7 * 32;
@@ -163,7 +163,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     const int cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
-    constexpr int WSTAGES = WRES ? MAX_RES_STAGES : C::WSTAGES;
+    // pair mode: a stage is half the size per CTA and its hand-over crosses the cluster, so twice the stages are in flight
+    constexpr int WSTAGES = WRES ? MAX_RES_STAGES : (PAIR ? 2 * C::WSTAGES : C::WSTAGES);
     uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE]
     float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * W_PLANE);
     float* s_shift = s_scale + 128;
@@ -728,7 +729,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
     const size_t smem = 2 * NPL * C::A_PLANE_BYTES +
-                        (WRES ? MAX_RES_STAGES : C::WSTAGES) * NPL * (C::W_PLANE_BYTES / (PAIR ? 2 : 1)) + 1024 +
+                        (WRES ? MAX_RES_STAGES : (PAIR ? 2 * C::WSTAGES : C::WSTAGES)) * NPL * (C::W_PLANE_BYTES / (PAIR ? 2 : 1)) + 1024 +
                         sizeof(Barriers) + 64;
     CUtensorMap wmap = map;        // placeholder unless PAIR
     if (PAIR) {
