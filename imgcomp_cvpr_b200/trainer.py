@@ -119,6 +119,17 @@ PC_LAYERS = (('probclass3d/logits/conv3d_conv0_mask', 'first'), ('probclass3d/lo
              ('probclass3d/logits/res1/conv3d_conv2_mask', 'other'), ('probclass3d/logits/conv3d_conv2_mask', 'other'))
 
 
+def learning_rate_at(cfg, global_step, num_itr_per_epoch):
+    """training_helpers.create_learning_rate_tensor (code/training_helpers.py:22-35): FIXED, or exponential decay by
+    lr_schedule_decay_rate every lr_schedule_decay_interval epochs (staircase unless the config says otherwise)"""
+    if cfg.lr_schedule == 'FIXED':
+        return cfg.lr_initial
+    p = global_step / float(num_itr_per_epoch * cfg.lr_schedule_decay_interval)
+    if cfg.lr_schedule_decay_staircase:
+        p = math.floor(p)
+    return cfg.lr_initial * cfg.lr_schedule_decay_rate ** p
+
+
 class Trainer(object):
     """One object = the variables of code/train.py's graph + its train_op.
 
@@ -503,15 +514,9 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ optimiser (code/train.py:339-349)
     def learning_rates(self):
-        """training_helpers.create_learning_rate_tensor (code/training_helpers.py:22-35) at the current global step"""
-        def lr(cfg):
-            if cfg.lr_schedule == 'FIXED':
-                return cfg.lr_initial
-            p = self.global_step / float(self.num_itr_per_epoch * cfg.lr_schedule_decay_interval)
-            if cfg.lr_schedule_decay_staircase:
-                p = math.floor(p)
-            return cfg.lr_initial * cfg.lr_schedule_decay_rate ** p
-        return lr(self.ae_config), lr(self.pc_config)
+        """(lr_ae, lr_pc) at the current global step"""
+        return (learning_rate_at(self.ae_config, self.global_step, self.num_itr_per_epoch),
+                learning_rate_at(self.pc_config, self.global_step, self.num_itr_per_epoch))
 
     def _adam_plan(self):
         cfg = self.ae_config
