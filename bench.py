@@ -272,8 +272,11 @@ def main():
                   'max_abs_dbpp': float((bpp_m - bpp_ref).abs().max().item()), 'bpp': bpp_ref.tolist()}
         del ae32, pc32, e_ref, b_ref, e_m
         torch.cuda.empty_cache()
-        for _ in range(2):          # the emptied allocator cache makes the next step cudaMalloc its workspace again: not timed
-            step(x_dev)
+    barrier()
+    # EVERY rank (step() holds the all-reduce): rank 0's emptied allocator cache makes its next step cudaMalloc the workspace
+    # again, which must not land in the timed pass
+    for _ in range(2):
+        step(x_dev)
     barrier()
     # ---- device-resident throughput (`value`): K steps, nothing else on the stream
     launches0 = L.ic_launch_count()
@@ -282,9 +285,9 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = L.ic_launch_count() - launches0
-    # ---- live per-kernel-class timing (roofline): a second pass of K steps with every launch of the library bracketed by
-    # CUDA events on the launching stream.  Kept out of the pass above: 2 timing events per launch cost ~2-4 ms per
-    # step of stream serialisation (41 launches), which is not part of the path.
+    # ---- live per-kernel-class timing (roofline): a second pass of K steps (all ranks) with every launch of the library
+    # bracketed by CUDA events on the launching stream; kept out of the pass above so that the timed pass carries
+    # nothing but the path.
     L.ic_profile_reset()
     L.ic_profile_enable(1)
     ms_profiled = timed(lambda: step(x_dev), args.steps)
