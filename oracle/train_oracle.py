@@ -11,10 +11,14 @@ code/train.py:86-132 builds for is_training=True:
     total_loss = d.d_loss_scaled + beta * max(0.5 * (mean(bc * heatmap) + mean(bc)) - H_target, 0) + reg   :303-336
     two Adam optimisers (ae vars / probclass vars)  train.py:339-349, training_helpers.py:22-48
 
-The forward arithmetic follows oracle/imgcomp_oracle.py (pinned against the reference-run goldens in
-inference mode: tests/test_oracle_golden.py checks that this module, put in inference mode, reproduces
-it).  Training-mode batch norm and the gradients themselves have no reference-run fixture: TF 1.4 is not
-installable here -> "parity unpinned" for the backward pass beyond this restatement.
+The forward arithmetic follows oracle/imgcomp_oracle.py (pinned against the reference-run goldens in inference mode:
+tests/test_oracle_golden.py checks that this module, put in inference mode, reproduces it).
+Training mode is pinned at GRAPH LEVEL too: tests/golden/make_train_golden.py executes the UNMODIFIED reference modules
+(autoencoder, quantizer, probclass, ms_ssim, bits, and train.py's get_loss / Distortions) with is_training=True on
+tests/tf1_shim/autograd.py (a torch-autograd stand-in for the TF-1.4 symbols) and differentiates total_loss;
+tests/test_oracle_golden.py::test_training_oracle_matches_reference_training_graph holds this module to those vectors
+(loss components, batch statistics, the gradient of all 219 variables: agreement ~1e-14 in float64).  What stays
+unpinned is the kernel level, as for inference: no TF binary ever produced a number here (TF 1.4 is not installable).
 """
 import math
 
@@ -157,7 +161,7 @@ def _sep_valid(img, k):
 def ms_ssim_tf(a, b):
     """ms_ssim.MultiScaleSSIM (code/ms_ssim.py:115-186), NCHW, one scalar for the batch"""
     dt = a.dtype
-    w = torch.tensor(np.array(O.MSSSIM_WEIGHTS, np.float32), dtype=dt)
+    w = torch.tensor(np.array(O.MSSSIM_WEIGHTS), dtype=dt)         # tf.convert_to_tensor(weights, float32) (:168): rounded to `dt`
     box = torch.tensor([0.5, 0.5], dtype=dt)
     c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
     mssim, mcs = [], []

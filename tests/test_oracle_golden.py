@@ -126,3 +126,53 @@ def test_training_oracle_gradients_are_consistent(synth):
         Wm[name] = W[name].astype(np.float64).copy(); Wm[name][idx] -= eps
         fd = (T.training_step(x, Wp, ae_cfg, pc_cfg)['total_loss'] - T.training_step(x, Wm, ae_cfg, pc_cfg)['total_loss']) / (2 * eps)
         assert abs(fd - g[idx]) <= 2e-4 * max(1.0, abs(fd)), (name, fd, g[idx])
+
+
+# ----------------------------------------------------------------------------
+# training step: oracle/train_oracle.py against the reference's own graph code run on the autograd shim
+# ----------------------------------------------------------------------------
+def _proj(name, size):
+    seed = int.from_bytes(name.encode(), 'little') % (2 ** 31 - 1)
+    return np.random.RandomState(seed).standard_normal(size)
+
+
+@pytest.mark.parametrize('tag', ['train_low_2x64x64', 'train_hi_2x80x48'])
+def test_training_oracle_matches_reference_training_graph(tag, synth):
+    """tests/golden/make_train_golden.py executed the UNMODIFIED reference modules (autoencoder, quantizer, probclass,
+    ms_ssim, bits, train.get_loss / Distortions) with is_training=True on tests/tf1_shim/autograd.py and differentiated
+    total_loss; the training oracle (what the CUDA step is tested against) must reproduce loss, batch statistics and
+    the gradient of every one of the 219 variables (float64 both: 1e-6 relative, measured ~1e-12)."""
+    import torch
+    from imgcomp_cvpr_b200 import weights
+    from oracle import train_oracle as T
+    g = load_golden(tag)
+    ae_name, N, H, W_, seed = (str(v) for v in g['meta'])
+    ae_cfg, pc_cfg, Wt = synth(ae_name)
+    x = weights.synthetic_images(int(N), int(H), int(W_), seed=int(seed))
+    r = T.training_step(x, Wt, ae_cfg, pc_cfg, dtype=torch.float64, training=True)
+    for k_ref, k in (('total_loss', 'total_loss'), ('H_real', 'H_real'), ('H_mask', 'H_mask'), ('pc_loss', 'pc_loss'),
+                     ('d_loss_scaled', 'd_loss_scaled'), ('ms_ssim', 'ms_ssim')):
+        ref = float(g['loss/' + k_ref])
+        assert abs(r[k] - ref) <= 1e-9 * max(1.0, abs(ref)), (k, r[k], ref)
+    assert np.array_equal(r['tensors']['symbols'].astype(np.uint8), g['symbols'])
+    np.testing.assert_allclose(r['tensors']['bc'].sum(axis=(1, 2, 3)), g['bc_sum_per_image'], rtol=1e-10)
+    np.testing.assert_allclose(r['tensors']['x_out'].mean(axis=(1, 2, 3)), g['x_out_mean_per_image'], rtol=1e-10)
+    names = [str(n) for n in g['names']]
+    assert sorted(r['grads']) == names
+    worst = 0.0
+    for i, name in enumerate(names):
+        gr = np.asarray(r['grads'][name], np.float64)
+        nref, pref = float(g['grad_norm'][i]), float(g['grad_proj'][i])
+        assert abs(np.linalg.norm(gr) - nref) <= 1e-6 * max(nref, 1e-12), name
+        pr = float(np.dot(gr.ravel(), _proj(name, gr.size)))
+        assert abs(pr - pref) <= 1e-6 * max(nref * np.sqrt(gr.size), 1e-12), name
+        worst = max(worst, abs(np.linalg.norm(gr) - nref) / max(nref, 1e-300))
+    for key in list(g):
+        if key.startswith('grad/'):
+            ref = g[key]
+            np.testing.assert_allclose(r['grads'][key[5:]], ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+        if key.startswith('bn_mean/'):
+            s = key[len('bn_mean/'):]
+            np.testing.assert_allclose(r['bn_stats'][s][0], g[key], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(r['bn_stats'][s][1], g['bn_var_unbiased/' + s], rtol=1e-9)
+    print('%s: worst gradient-norm deviation %.1e over %d variables' % (tag, worst, len(names)))
