@@ -74,7 +74,43 @@ def run_reference_training_graph(x_u8, W, ae_cfg, pc_cfg):
         shim.uninstall()
 
 
+MSSSIM_SHAPES = [(2, 64, 64), (1, 70, 50), (3, 160, 160), (1, 47, 33)]      # the shapes of tests/test_gpu_training_step.py
+
+
+def msssim_pair(shape, seed=5):
+    N, H, W_ = shape
+    rng = np.random.RandomState(seed)
+    a = rng.uniform(0, 255, size=(N, 3, H, W_)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 12, size=a.shape), 0, 255).astype(np.float32)
+    return a, b
+
+
+def run_reference_msssim(a, b):
+    """value and d value / d img2 of the reference's ms_ssim.MultiScaleSSIM (code/ms_ssim.py:115-186), float64"""
+    shim.install({}, dtype=torch.float64)
+    try:
+        import ms_ssim
+        bt = torch.tensor(b.astype(np.float64), requires_grad=True)
+        v = ms_ssim.MultiScaleSSIM(shim.AT(torch.tensor(a.astype(np.float64))), shim.AT(bt), data_format='NCHW')
+        v.t.backward()
+        return float(v.t.detach()), bt.grad.numpy().copy()
+    finally:
+        shim.uninstall()
+
+
 def main():
+    blob = {}
+    for shape in MSSSIM_SHAPES:
+        a, b = msssim_pair(shape)
+        v, g = run_reference_msssim(a, b)
+        key = 'x'.join(str(s) for s in shape)
+        blob['value/' + key] = np.float64(v)
+        blob['grad_norm/' + key] = np.float64(np.linalg.norm(g))
+        blob['grad_proj/' + key] = np.float64(np.dot(g.ravel(), projection_vector('msssim' + key, g.size)))
+        blob['grad_corner/' + key] = g[0, :, :6, :6].copy()
+        blob['grad_tail/' + key] = g[-1, :, -6:, -6:].copy()
+        print('ms-ssim', shape, v, np.linalg.norm(g))
+    np.savez_compressed(os.path.join(HERE, 'train_msssim_grad.npz'), **blob)
     for tag, ae_name, N, H, W_, seed in CASES:
         a, p = config.ae_config(ae_name), config.pc_config('cvpr/res_shallow')
         Wt = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)

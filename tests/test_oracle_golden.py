@@ -176,3 +176,27 @@ def test_training_oracle_matches_reference_training_graph(tag, synth):
             np.testing.assert_allclose(r['bn_stats'][s][0], g[key], rtol=1e-9, atol=1e-12)
             np.testing.assert_allclose(r['bn_stats'][s][1], g['bn_var_unbiased/' + s], rtol=1e-9)
     print('%s: worst gradient-norm deviation %.1e over %d variables' % (tag, worst, len(names)))
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 64), (1, 70, 50), (3, 160, 160), (1, 47, 33)])
+def test_msssim_gradient_oracle_matches_reference_module(shape):
+    """value and gradient of oracle/train_oracle.ms_ssim_tf (what the CUDA MS-SSIM backward is tested against, odd sizes
+    with REFLECT-padded levels included) against the reference's ms_ssim.MultiScaleSSIM differentiated on the autograd shim"""
+    import torch
+    from oracle import train_oracle as T
+    g = load_golden('train_msssim_grad')
+    N, H, W_ = shape
+    rng = np.random.RandomState(5)
+    a = rng.uniform(0, 255, size=(N, 3, H, W_)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 12, size=a.shape), 0, 255).astype(np.float32)
+    bt = torch.tensor(b, dtype=torch.float64, requires_grad=True)
+    v = T.ms_ssim_tf(torch.tensor(a, dtype=torch.float64), bt)
+    v.backward()
+    gr = bt.grad.numpy()
+    key = 'x'.join(str(s) for s in shape)
+    assert abs(float(v.detach()) - float(g['value/' + key])) < 1e-12
+    nref = float(g['grad_norm/' + key])
+    assert abs(np.linalg.norm(gr) - nref) <= 1e-9 * nref
+    assert abs(float(np.dot(gr.ravel(), _proj('msssim' + key, gr.size))) - float(g['grad_proj/' + key])) <= 1e-8 * nref * np.sqrt(gr.size)
+    np.testing.assert_allclose(gr[0, :, :6, :6], g['grad_corner/' + key], rtol=1e-8, atol=1e-12 * nref)
+    np.testing.assert_allclose(gr[-1, :, -6:, -6:], g['grad_tail/' + key], rtol=1e-8, atol=1e-12 * nref)
