@@ -69,3 +69,40 @@ def gpu_models(synth):
         return cache[key]
     assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
     return get
+
+
+def golden_projection(name, size):
+    """the seeded vector tests/golden/make_train_golden.py projects the gradient of variable `name` on"""
+    seed = int.from_bytes(name.encode(), 'little') % (2 ** 31 - 1)
+    return np.random.RandomState(seed).standard_normal(size)
+
+
+def check_training_against_golden(losses, grads, golden, weights, ae_cfg, add_l2, loss_rtol, grad_rtol):
+    """A training step (loss components `losses`, gradients `grads` by TF variable name) against the reference-run golden
+    of tests/golden/make_train_golden.py.  add_l2: `grads` are without the l2 regularisation terms (the CUDA step adds
+    them inside the Adam kernel), add regularization_factor * w / regularization_factor_centers * centers first.
+    -> worst relative deviation of a gradient (norm-wise, estimated from norm and projection)."""
+    for k in ('total_loss', 'd_loss_scaled', 'pc_loss', 'H_real', 'H_mask', 'ms_ssim'):
+        ref = float(golden['loss/' + k])
+        assert abs(losses[k] - ref) <= loss_rtol * max(1.0, abs(ref)), (k, losses[k], ref)
+    names = [str(n) for n in golden['names']]
+    assert sorted(grads) == names
+    worst = 0.0
+    for i, name in enumerate(names):
+        g = np.asarray(grads[name], np.float64)
+        if add_l2:
+            w = np.asarray(weights[name], np.float64)
+            if name.startswith('autoencoder/') and name.endswith('/weights'):
+                g = g + ae_cfg.regularization_factor * w
+            elif name.endswith('/centers'):
+                g = g + ae_cfg.regularization_factor_centers * w
+        nref, pref = float(golden['grad_norm'][i]), float(golden['grad_proj'][i])
+        dn = abs(np.linalg.norm(g) - nref) / max(nref, 1e-300)
+        # the projection on a unit-variance random vector deviates by ~|g - g_ref| (norm-wise): scale by the norm
+        dp = abs(float(np.dot(g.ravel(), golden_projection(name, g.size))) - pref) / max(nref, 1e-300)
+        assert dn <= grad_rtol and dp <= 4 * grad_rtol, (name, dn, dp)
+        worst = max(worst, dn, dp / 4)
+        if 'grad/' + name in golden:
+            ref = golden['grad/' + name]
+            assert np.linalg.norm(g - ref) <= grad_rtol * max(np.linalg.norm(ref), 1e-300), name
+    return worst

@@ -161,6 +161,21 @@ def test_training_step_matches_oracle(synth, ae_name, N, H, W, seed):
     assert errs[len(errs) // 2][0] < 1e-4
 
 
+@pytest.mark.parametrize('tag,ae_name,N,H,W,seed', [('train_low_2x64x64', 'cvpr/low', 2, 64, 64, 22),
+                                                     ('train_hi_2x80x48', 'cvpr/hi', 2, 80, 48, 21)])
+def test_training_step_matches_reference_run_golden(synth, tag, ae_name, N, H, W, seed):
+    """The CUDA step against the vectors tests/golden/make_train_golden.py produced by executing the reference's own
+    training graph (unmodified modules on the autograd TF1 shim, float64): symbols identical, loss components within
+    1e-4 relative, every variable's gradient within 1e-3 norm-wise (norm and seeded projection; small variables in full)."""
+    from conftest import check_training_against_golden, load_golden
+    g = load_golden(tag)
+    ae_cfg, pc_cfg, Wt, x, tr = _setup(synth, ae_name, N, H, W, seed=seed)
+    out = tr.forward_backward(torch.from_numpy(x).cuda(), is_training=True, update_moving=False)
+    assert np.array_equal(out['tensors']['symbols'].cpu().numpy().astype(np.uint8), g['symbols'])
+    worst = check_training_against_golden(out, tr.gradients(), g, Wt, ae_cfg, True, 1e-4, 1e-3)
+    print('%s vs reference-run golden: worst gradient deviation %.2e' % (tag, worst))
+
+
 def test_step_applies_adam_and_moving_averages(synth):
     """tr.step = forward_backward + tf.train.AdamOptimizer._apply_dense per group (code/train.py:339-349,
     training_helpers.py:22-48) + the decay-0.9 moving averages of slim.batch_norm (autoencoder.py:115-125)."""

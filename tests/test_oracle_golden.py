@@ -200,3 +200,32 @@ def test_msssim_gradient_oracle_matches_reference_module(shape):
     assert abs(float(np.dot(gr.ravel(), _proj('msssim' + key, gr.size))) - float(g['grad_proj/' + key])) <= 1e-8 * nref * np.sqrt(gr.size)
     np.testing.assert_allclose(gr[0, :, :6, :6], g['grad_corner/' + key], rtol=1e-8, atol=1e-12 * nref)
     np.testing.assert_allclose(gr[-1, :, -6:, -6:], g['grad_tail/' + key], rtol=1e-8, atol=1e-12 * nref)
+
+
+def test_golden_check_helper_on_the_oracle(synth):
+    """conftest.check_training_against_golden (the helper the GPU training test uses) exercised on the CPU with the oracle's
+    output: once with the regularisation terms in the gradients, once with them stripped and re-added by the helper;
+    and it must reject a perturbed gradient."""
+    import torch
+    from conftest import check_training_against_golden
+    from imgcomp_cvpr_b200 import weights
+    from oracle import train_oracle as T
+    g = load_golden('train_hi_2x80x48')
+    ae_cfg, pc_cfg, Wt = synth('cvpr/hi')
+    x = weights.synthetic_images(2, 80, 48, seed=21)
+    r = T.training_step(x, Wt, ae_cfg, pc_cfg, dtype=torch.float64, training=True)
+    assert check_training_against_golden(r, r['grads'], g, Wt, ae_cfg, False, 1e-9, 1e-6) < 1e-9
+    stripped = {}
+    for k, v in r['grads'].items():
+        w = np.asarray(Wt[k], np.float64)
+        if k.startswith('autoencoder/') and k.endswith('/weights'):
+            v = v - ae_cfg.regularization_factor * w
+        elif k.endswith('/centers'):
+            v = v - ae_cfg.regularization_factor_centers * w
+        stripped[k] = v
+    assert check_training_against_golden(r, stripped, g, Wt, ae_cfg, True, 1e-9, 1e-6) < 1e-9
+    bad = dict(r['grads'])
+    k = 'autoencoder/decoder/h12/weights'
+    bad[k] = bad[k] * 1.01
+    with pytest.raises(AssertionError):
+        check_training_against_golden(r, bad, g, Wt, ae_cfg, False, 1e-9, 1e-6)
