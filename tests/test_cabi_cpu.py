@@ -150,3 +150,32 @@ def test_no_gpu_means_loud_failure():
     a = cfgmod.ae_config('cvpr/low')
     with pytest.raises(_lib.IcError):
         autoencoder.get_network_cls(a)(a, weights={})
+
+
+def test_library_sass_has_tcgen05_and_tma_and_no_legacy_mma():
+    """cuobjdump -sass of the built library (no GPU needed): the conv and filter-gradient kernels issue tcgen05 MMAs
+    (UTCHMMA), read accumulators with tcgen05.ld (LDTM) and are fed by TMA (UTMALDG); nothing falls back to the legacy
+    mma.sync path (HMMA).  B200_PROFILING.md lists these mnemonics as the evidence of a Blackwell-native kernel."""
+    import re
+    import shutil
+    import subprocess
+    from imgcomp_cvpr_b200 import _lib
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = set()
+        elif cur is not None:
+            for mn in ('UTCHMMA', 'LDTM', 'UTMALDG', 'HMMA'):
+                if re.search(r'\b' + mn + r'[\.\s]', line):
+                    per_kernel[cur].add(mn)
+    conv = [k for k in per_kernel if 'conv_tc_kernel' in k]
+    wgrad = [k for k in per_kernel if 'wgrad_tc_kernel' in k]
+    assert len(conv) >= 10 and len(wgrad) == 1
+    for k in conv + wgrad:
+        assert {'UTCHMMA', 'LDTM', 'UTMALDG'} <= per_kernel[k], (k, per_kernel[k])
+    assert not [k for k, v in per_kernel.items() if 'HMMA' in v]
