@@ -142,7 +142,9 @@ class Trainer(object):
         """mode 'fp32': every kernel float32 FFMA (strict parity mode); 'exact': forward and data gradient of the 64
         3x3 128->128 convs AND their filter gradients on tcgen05 kernels in fp16 hi/lo arithmetic (float32-class,
         DESIGN.md 4.2 / 4.6)."""
-        _lib.require_device()
+        self.device = torch.device(device)
+        if self.device.type == 'cuda':
+            _lib.require_device()        # device='cpu' builds the parameter buffers only (packing / export logic; no kernels)
         assert mode in ('fp32', 'exact')
         self.mode = mode
         assert ae_config.arch == 'CVPR' and pc_config.arch == 'res_shallow'
@@ -155,7 +157,6 @@ class Trainer(object):
         self.heatmap = bool(ae_config.heatmap)
         self.num_itr_per_epoch = num_itr_per_epoch
         self.global_step = 0
-        self.device = torch.device(device)
         self.table = ae_layer_table(self.C, self.B)
         self._tr = {s: tr for s, _, _, _, _, tr in self.table}
         self._shape = {s: (k, ci, co) for s, k, _, ci, co, _ in self.table}
@@ -210,7 +211,9 @@ class Trainer(object):
         self._coef = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._val = None
         self._loss_ws = torch.empty(_lib.lib().ic_loss_workspace_bytes(), dtype=torch.uint8, device=self.device)
-        self._lr_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._lr_host = torch.zeros(2, dtype=torch.float32)
+        if self.device.type == 'cuda':
+            self._lr_host = self._lr_host.pin_memory()
         self._lr_dev = torch.zeros(2, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ parameter access
@@ -254,6 +257,36 @@ class Trainer(object):
             for name in ('moving_mean', 'moving_variance'):
                 out[s + '/BatchNorm/' + name] = self.stats.view(self.stats.w, s + '/BatchNorm/' + name)[:co].cpu().numpy()
         return out
+
+    def state_dict(self):
+        """Everything needed to resume (the role of the reference's Saver, code/saver.py / restore_manager.py, without the
+        TF checkpoint format): the variables under their TF names, both Adam moments under '<name>/Adam' and '<name>/Adam_1'
+        (tf.train.AdamOptimizer's slot names) and the step counters."""
+        out = self.weights()
+        for slot, buf in (('Adam', 'm'), ('Adam_1', 'v')):
+            for k, v in self._export(buf).items():
+                out[k + '/' + slot] = v
+        out['global_step'] = np.asarray(self.global_step, np.int64)
+        out['adam_step'] = np.asarray(self._adam_t, np.int64)
+        return out
+
+    def load_state_dict(self, state):
+        """inverse of state_dict(); variables that are missing keep their current value (restore_skip_vars-like)"""
+        fresh = Trainer(self.ae_config, self.pc_config, {k: state.get(k, v) for k, v in self.weights().items()},
+                        self.num_itr_per_epoch, str(self.device), self.mode)
+        for name in self.groups:
+            self.groups[name].w.copy_(fresh.groups[name].w)
+        self.stats.w.copy_(fresh.stats.w)
+        for slot, buf in (('Adam', 'm'), ('Adam_1', 'v')):
+            sub = {k[:-len('/' + slot)]: v for k, v in state.items() if k.endswith('/' + slot)}
+            if sub:
+                tmp = Trainer(self.ae_config, self.pc_config, {k: sub.get(k, np.zeros_like(v)) for k, v in self.weights().items()},
+                              self.num_itr_per_epoch, str(self.device), self.mode)
+                for name in self.groups:
+                    getattr(self.groups[name], buf).copy_(tmp.groups[name].w)
+        self.global_step = int(state.get('global_step', self.global_step))
+        self._adam_t = int(state.get('adam_step', self._adam_t))
+        return self
 
     def gradients(self):
         """d total_loss / d variable of the last forward_backward(), WITHOUT the l2 terms (those are added inside the
@@ -627,6 +660,8 @@ def main():
     ap.add_argument('--images', default=None, help='glob of training images (default: seeded synthetic images)')
     ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array to start from (default: seeded synthetic weights)')
     ap.add_argument('--save', default=None, help='write the trained variables (.npz, TF names) here')
+    ap.add_argument('--save_state', default=None, help='write variables + Adam moments + step counters (.npz) here: --resume input')
+    ap.add_argument('--resume', default=None, help='.npz written by --save_state (the reference: --restore, code/train.py:487-499)')
     ap.add_argument('--num_itr_per_epoch', type=int, default=1000, help='for the staircase LR decay (training_helpers.py:51-60)')
     ap.add_argument('--log_interval', type=int, default=10)
     ap.add_argument('--mode', default='exact', choices=['fp32', 'exact'])
@@ -646,6 +681,9 @@ def main():
     else:
         images = list(weights_mod.synthetic_images(64, 2 * a.crop_size[0], 2 * a.crop_size[1], seed=args.seed + 1))
     tr = Trainer(a, p, W, num_itr_per_epoch=args.num_itr_per_epoch, mode=args.mode)
+    if args.resume:
+        tr.load_state_dict(dict(np.load(args.resume)))
+        print('resumed at global step', tr.global_step)
     pinned = torch.empty((B, 3) + tuple(a.crop_size), dtype=torch.uint8).pin_memory()
     x = torch.empty_like(pinned, device='cuda')
     if not args.no_graph:
@@ -664,6 +702,9 @@ def main():
     if args.save:
         np.savez(args.save, **tr.weights())
         print('saved', args.save)
+    if args.save_state:
+        np.savez(args.save_state, **tr.state_dict())
+        print('saved state', args.save_state)
 
 
 if __name__ == '__main__':

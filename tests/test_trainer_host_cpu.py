@@ -113,3 +113,54 @@ def test_tape_accumulation_rules():
         assert order == [2, 1]
     finally:
         trainer.nn = real
+
+
+def _cpu_trainer(ae_name='cvpr/low'):
+    a, p = config.ae_config(ae_name), config.pc_config('cvpr/res_shallow')
+    W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
+    return a, p, W, trainer.Trainer(a, p, W, num_itr_per_epoch=100, device='cpu')
+
+
+def test_parameter_packing_round_trip():
+    """TF-named variables -> padded, op-oriented flat device buffers -> back: exact, for every variable (transposed convs
+    swap their channel axes on the way in and out, 3 / C+1 / L channel counts are padded to multiples of 4)"""
+    for name in ('cvpr/low', 'cvpr/hi'):
+        a, p, W, tr = _cpu_trainer(name)
+        out = tr.weights()
+        assert sorted(out) == sorted(W)
+        for k in W:
+            assert out[k].shape == np.asarray(W[k]).shape and np.array_equal(out[k], W[k]), k
+        # the context-model masks sit next to the padded weights and match the reference masks
+        first, other = trainer._pc_masks()
+        m0 = tr._const('probclass3d/logits/conv3d_conv0_mask/mask').numpy()
+        assert m0.shape == (2, 3, 3, 4, 24) and np.array_equal(m0[..., 0, 0], first) and m0[..., 1:, :].sum() == 0
+        m3 = tr._const('probclass3d/logits/conv3d_conv2_mask/mask').numpy()
+        assert m3.shape == (2, 3, 3, 24, 8) and np.array_equal(m3[..., 0, 0], other) and m3[..., 6:].sum() == 0
+        # padded entries of the device weights are zero (so their gradients and Adam updates stay zero)
+        w_h1 = tr._w('autoencoder/encoder/h1/weights')
+        assert tuple(w_h1.shape) == (5, 5, 4, 64) and float(w_h1[:, :, 3].abs().sum()) == 0.0
+        w_h13 = tr._w('autoencoder/decoder/h13/weights')
+        assert tuple(w_h13.shape) == (5, 5, 64, 4) and float(w_h13[..., 3].abs().sum()) == 0.0
+
+
+def test_state_dict_round_trip():
+    a, p, W, tr = _cpu_trainer()
+    rng = np.random.RandomState(3)
+    for g in tr.groups.values():             # pretend some steps happened
+        g.m.copy_(torch.from_numpy(rng.randn(g.m.numel()).astype(np.float32)))
+        g.v.copy_(torch.from_numpy(np.abs(rng.randn(g.v.numel())).astype(np.float32)))
+    tr.global_step, tr._adam_t = 1234, 1234
+    sd = tr.state_dict()
+    assert 'autoencoder/encoder/h2/weights/Adam' in sd and 'probclass3d/logits/conv3d_conv0_mask/biases/Adam_1' in sd
+    _, _, _, tr2 = _cpu_trainer()
+    tr2.load_state_dict(sd)
+    assert tr2.global_step == 1234 and tr2._adam_t == 1234
+    sd2 = tr2.state_dict()
+    assert sorted(sd) == sorted(sd2)
+    for k in sd:
+        assert np.array_equal(sd[k], sd2[k]), k
+    # partial restore (restore_skip_vars-like): only the centres
+    _, _, _, tr3 = _cpu_trainer()
+    tr3.load_state_dict({'autoencoder/encoder/centers': np.arange(6, dtype=np.float32)})
+    assert np.array_equal(tr3.weights()['autoencoder/encoder/centers'], np.arange(6, dtype=np.float32))
+    assert np.array_equal(tr3.weights()['autoencoder/encoder/h1/weights'], W['autoencoder/encoder/h1/weights'])
