@@ -658,7 +658,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--batch_size', type=int, default=None, help='default: the config value (30)')
     ap.add_argument('--images', default=None, help='glob of training images (default: seeded synthetic images)')
-    ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array to start from (default: seeded synthetic weights)')
+    ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array, or a TensorFlow checkpoint prefix / directory, to start from (default: seeded synthetic weights)')
     ap.add_argument('--save', default=None, help='write the trained variables (.npz, TF names) here')
     ap.add_argument('--save_state', default=None, help='write variables + Adam moments + step counters (.npz) here: --resume input')
     ap.add_argument('--resume', default=None, help='.npz written by --save_state (the reference: --restore, code/train.py:487-499)')
@@ -670,7 +670,8 @@ def main():
     args = ap.parse_args()
     a, p = config.ae_config(args.ae_config), config.pc_config(args.pc_config)
     B = args.batch_size or a.batch_size
-    W = dict(np.load(args.weights)) if args.weights else weights_mod.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k,
+    from . import tf_checkpoint
+    W = tf_checkpoint.load_weights(args.weights) if args.weights else weights_mod.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k,
                                                                                        a.arch_param_B)
     rng = np.random.RandomState(args.seed)
     if args.images:

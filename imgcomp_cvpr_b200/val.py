@@ -144,7 +144,7 @@ def main():
     import os
     import torch
     import torch.distributed as dist
-    from . import autoencoder, config, probclass, weights
+    from . import autoencoder, config, probclass, tf_checkpoint, weights
     ap = argparse.ArgumentParser(description='val.py-style run on synthetic images / weights')
     ap.add_argument('--ae_config', default='cvpr/low')
     ap.add_argument('--pc_config', default='cvpr/res_shallow')
@@ -154,7 +154,8 @@ def main():
     ap.add_argument('--mode', default='exact', choices=['fp32', 'exact', 'fast'])
     ap.add_argument('--real_bpp', action='store_true')
     ap.add_argument('--images', default=None, help='glob of image files instead of synthetic images')
-    ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array (default: seeded synthetic weights)')
+    ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array, or a TensorFlow checkpoint prefix / ckpts directory of the '
+                    'reference (read without TensorFlow: tf_checkpoint.py); default: seeded synthetic weights')
     ap.add_argument('--out_dir', default=None, help='write measures.csv here (rank 0 writes its own shard only)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -162,7 +163,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl')
     a, p = config.ae_config(args.ae_config), config.pc_config(args.pc_config)
-    W = dict(np.load(args.weights)) if args.weights else weights.synthetic_weights(
+    W = tf_checkpoint.load_weights(args.weights) if args.weights else weights.synthetic_weights(
         a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
     ae = autoencoder.get_network_cls(a)(a, weights=W, mode=args.mode)
     pc = probclass.get_network_cls(p)(p, num_centers=a.num_centers, weights=W)
