@@ -58,9 +58,9 @@ def psnr_u8(a, b):
     return 10 * torch.log10(255.0 ** 2 / mse)
 
 
-def measure_batch(x_u8, ae, pc, real_bpp=False):
+def measure_batch(x_u8, ae, pc, real_bpp=False, keep_images=False):
     """The val.py fetch for a batch of same-sized uint8 images (code/val.py:81-94,161-175).
-    -> list of per-image dicts (bpp, ms-ssim, psnr[, bpp_real, bpp_theory])."""
+    -> list of per-image dicts (bpp, ms-ssim, psnr[, bpp_real, bpp_theory][, img_out: the padded uint8 CHW output])."""
     import torch
     from . import bpp_helpers, ms_ssim_np, probclass
     enc = ae.encode(x_u8, is_training=False)
@@ -72,6 +72,10 @@ def measure_batch(x_u8, ae, pc, real_bpp=False):
     ms = ms_ssim_np.MultiScaleSSIM_batch(x_u8, x_out_u8, data_format='NCHW').float().cpu().numpy()
     ps = psnr_u8(x_u8, x_out_u8).float().cpu().numpy()
     rows = [{'bpp': float(bpp[i]), 'ms-ssim': float(ms[i]), 'psnr': float(ps[i])} for i in range(x_u8.shape[0])]
+    if keep_images:                                                     # fetch_dict['img_out'] (val.py:108-109)
+        out_host = x_out_u8.cpu().numpy()
+        for i, row in enumerate(rows):
+            row['img_out'] = out_host[i]
     if real_bpp:
         pred = probclass.PredictionNetwork(pc, pc.config, ae.get_centers_variable(), None)
         checker = probclass.ProbclassNetworkTesting(pc, ae, None)
@@ -85,7 +89,7 @@ def measure_batch(x_u8, ae, pc, real_bpp=False):
     return rows
 
 
-def validate(images_u8, ae, pc, real_bpp=False, batch_size=8, dist=None):
+def validate(images_u8, ae, pc, real_bpp=False, batch_size=8, dist=None, keep_images=False):
     """images_u8: list of HWC or CHW uint8 arrays (any sizes).  Pads like the reference's
     ImagesIterator, shards over ranks, batches same-sized images.  -> (averages, n_images, local rows)."""
     import torch
@@ -106,7 +110,7 @@ def validate(images_u8, ae, pc, real_bpp=False, batch_size=8, dist=None):
         for s in range(0, len(idxs), batch_size):
             chunk = idxs[s:s + batch_size]
             x = torch.from_numpy(np.stack([padded[i] for i in chunk])).cuda()
-            for i, row in zip(chunk, measure_batch(x, ae, pc, real_bpp)):
+            for i, row in zip(chunk, measure_batch(x, ae, pc, real_bpp, keep_images)):
                 rows[i] = row
     avgs, n = reduce_metric_sums(rows, dist)
     return avgs, n, rows
@@ -126,6 +130,17 @@ class MeasuresWriter(object):
 
     def close(self):
         self.fout.close()
+
+
+def save_img(img_name, img_out_chw, out_dir):
+    """val.save_img (code/val.py:215-225): <out_dir>/imgs/<name>.png, the (padded) output image as the graph produced it"""
+    import os
+    from PIL import Image
+    img_dir = os.path.join(out_dir, 'imgs')
+    os.makedirs(img_dir, exist_ok=True)
+    p = os.path.join(img_dir, img_name if img_name.endswith('.png') else img_name + '.png')
+    Image.fromarray(np.ascontiguousarray(np.transpose(img_out_chw, (1, 2, 0)))).save(p)
+    return p
 
 
 def load_images(pattern):
@@ -157,6 +172,8 @@ def main():
     ap.add_argument('--weights', default=None, help='.npz of TF variable name -> array, or a TensorFlow checkpoint prefix / ckpts directory of the '
                     'reference (read without TensorFlow: tf_checkpoint.py); default: seeded synthetic weights')
     ap.add_argument('--out_dir', default=None, help='write measures.csv here (rank 0 writes its own shard only)')
+    ap.add_argument('--save_ours', '-o', action='store_true', help='store the output images in OUT_DIR/imgs (code/val.py:268-269)')
+    ap.add_argument('--how_many', type=int, default=None, help='number of images to use (code/val.py:270)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
@@ -172,13 +189,19 @@ def main():
     else:
         imgs = list(weights.synthetic_images(args.synthetic, args.height, args.width))
         names = ['synthetic_%04d' % i for i in range(len(imgs))]
-    avgs, n, rows = validate(imgs, ae, pc, args.real_bpp, dist=dist if world > 1 else None)
+    if args.how_many is not None:
+        imgs, names = imgs[:args.how_many], names[:args.how_many]
+    assert not args.save_ours or args.out_dir, '--save_ours needs --out_dir'
+    avgs, n, rows = validate(imgs, ae, pc, args.real_bpp, dist=dist if world > 1 else None, keep_images=args.save_ours)
     if args.out_dir:
         rank = int(os.environ.get('RANK', '0'))
         lo, hi = shard_range(len(imgs), rank, world)
-        wr = MeasuresWriter(args.out_dir if world == 1 else os.path.join(args.out_dir, 'rank%d' % rank))
+        wr_dir = args.out_dir if world == 1 else os.path.join(args.out_dir, 'rank%d' % rank)
+        wr = MeasuresWriter(wr_dir)
         for name, row in zip(names[lo:hi], rows):
             wr.append(name, row)
+            if args.save_ours:
+                save_img(name, row['img_out'], wr_dir)
         wr.close()
     if int(os.environ.get('RANK', '0')) == 0:
         print('%d images | Mean: %s' % (n, ', '.join('{}: {:.4f}'.format(k, avgs[k]) for k in METRICS)))

@@ -79,3 +79,15 @@ def test_measures_writer_format(tmp_path):
     assert lines[0] == 'img_name,bpp,ms-ssim,psnr'
     name, bpp, ms, ps = lines[1].split(',')
     assert name == 'kodim01' and float(bpp) == 0.25 and float(ms) == 0.97 and float(ps) == 30.5
+
+
+def test_save_img_writes_the_output_png(tmp_path):
+    """val.save_img (code/val.py:215-225): CHW uint8 -> <out_dir>/imgs/<name>.png, read back identical"""
+    from PIL import Image
+    from imgcomp_cvpr_b200 import val
+    img = np.random.RandomState(0).randint(0, 256, size=(3, 24, 40)).astype(np.uint8)
+    for name in ('kodim01', 'kodim02.png'):
+        p = val.save_img(name, img, str(tmp_path))
+        assert p.endswith('.png') and os.path.dirname(p) == os.path.join(str(tmp_path), 'imgs')
+        back = np.asarray(Image.open(p))
+        assert np.array_equal(back, img.transpose(1, 2, 0))
