@@ -529,9 +529,6 @@ int msssim_tf_bwd(const float* a, const float* b, int N, int H, int W, float gra
     return IC_OK;
 }
 
-namespace {
-}  // namespace
-
 size_t msssim_workspace_bytes(int N, int H, int W, int is_double) {
     size_t e = is_double ? 8 : 4;
     size_t b = 0;
