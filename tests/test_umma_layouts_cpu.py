@@ -1,0 +1,138 @@
+"""Executable statement of the shared-memory operand layouts the tcgen05 kernels rely on (csrc/conv_tc.cu,
+csrc/train_tc.cu), checked on the CPU with a small emulator of the UMMA SWIZZLE_NONE shared-memory descriptor
+(cute/atom/mma_traits_sm100.hpp "canonical layouts", in 16-byte units):
+
+    K-major  ((8,n),2):((1,SBO),LBO)        element (r, k) at  start + (r//8) SBO + (k//8) LBO + (r%8) 16 + (k%8) 2
+    MN-major ((1,n),(8,k)):((X,SBO),(1,LBO)) element (r, k) at  start + (r//8) SBO + (k//8) LBO + (k%8) 16 + (r%8) 2
+
+(r = M or N index, k = K index, fp16).  The tests rebuild the tiles exactly as TMA delivers them from the NC/8HW8
+planes, form the descriptors the way the kernels do, and compare the emulated operand matrices / products with plain
+numpy: the 3x3 conv (tap = 16-byte shift of A's start address), its weights stage, the filter gradient as a GEMM over
+pixels on MN-major operands, and the B-concatenation layout planned in DESIGN.md section 7 (so the next kernel can be
+desk-checked before it sees a GPU)."""
+import numpy as np
+
+
+def operand(smem, start, lbo, sbo, rows, major, kdim=16):
+    """the (rows x kdim) fp16 matrix one MMA reads through a SWIZZLE_NONE descriptor (smem: uint8 array)"""
+    assert start % 16 == 0 and lbo % 16 == 0 and sbo % 16 == 0, 'descriptor fields are in 16-byte units'
+    h = smem.view(np.float16)
+    out = np.empty((rows, kdim), np.float16)
+    for r in range(rows):
+        for k in range(kdim):
+            if major == 'K':
+                a = start + (r // 8) * sbo + (k // 8) * lbo + (r % 8) * 16 + (k % 8) * 2
+            else:
+                a = start + (r // 8) * sbo + (k // 8) * lbo + (k % 8) * 16 + (r % 8) * 2
+            out[r, k] = h[a // 2]
+    return out
+
+
+def tma_tile(planes, n, chunk0, nchunks, y0, x0, th, tw):
+    """what a TMA box {tw*8, th, nchunks, 1, 1} at (x0, y0, chunk0, n) of a [N][C/8][H][W][8] plane delivers:
+    [chunk][row][pixel][8] fp16, out-of-bounds elements zero"""
+    N, CH, H, W, _ = planes.shape
+    out = np.zeros((nchunks, th, tw, 8), np.float16)
+    for c in range(nchunks):
+        for r in range(th):
+            for p in range(tw):
+                y, x, ch = y0 + r, x0 + p, chunk0 + c
+                if 0 <= y < H and 0 <= x < W and 0 <= ch < CH:
+                    out[c, r, p] = planes[n, ch, y, x]
+    return out
+
+
+def to_planes(x_nhwc):
+    """float NHWC -> fp16 [N][C/8][H][W][8] (the hi plane; values chosen exactly representable)"""
+    N, H, W, C = x_nhwc.shape
+    return np.ascontiguousarray(x_nhwc.reshape(N, H, W, C // 8, 8).transpose(0, 3, 1, 2, 4).astype(np.float16))
+
+
+def _ints(rng, shape, lo=-4, hi=5):
+    return rng.randint(lo, hi, size=shape).astype(np.float32)
+
+
+TH, TW, T = 16, 8, 2                                    # conv_tc.cu: one MMA tile = 16 rows x 8 pixels, T tiles per super tile
+HALO_W, HALO_H = TW * T + 2, TH + 2
+HALO_PIX = HALO_W * HALO_H
+
+
+def test_conv3x3_tile_taps_are_descriptor_shifts():
+    rng = np.random.RandomState(0)
+    N, H, W, Cin, Cout = 1, 20, 19, 32, 128             # ragged: the tile hangs over the right / bottom edge
+    x = _ints(rng, (N, H, W, Cin))
+    w = _ints(rng, (3, 3, Cin, Cout), -2, 3)
+    planes = to_planes(x)
+    y0, x0 = 0, 0
+    a_tile = tma_tile(planes, 0, 0, 4, y0 - 1, x0 - 1, HALO_H, HALO_W)          # halo0 = -1: SAME padding by OOB zero fill
+    a_smem = a_tile.reshape(4, HALO_PIX, 8).view(np.uint8).reshape(-1)          # [chunk][halo pixel][8]
+    # one weight stage per tap: [4 chunks][Cout rows][8 cin]
+    acc = np.zeros((T, 128, Cout), np.float64)
+    for tap in range(9):
+        dy, dx = divmod(tap, 3)
+        w_stage = np.zeros((4, Cout, 8), np.float16)
+        for ch in range(4):
+            w_stage[ch] = w[dy, dx, ch * 8:(ch + 1) * 8, :].T
+        w_smem = w_stage.view(np.uint8).reshape(-1)
+        for t in range(T):
+            for ks in range(2):
+                a = operand(a_smem, (dy * HALO_W + dx + t * TW) * 16 + ks * 2 * HALO_PIX * 16, lbo=HALO_PIX * 16, sbo=HALO_W * 16,
+                            rows=128, major='K')
+                b = operand(w_smem, ks * 2 * Cout * 16, lbo=Cout * 16, sbo=128, rows=Cout, major='K')
+                acc[t] += a.astype(np.float64) @ b.astype(np.float64).T
+    # reference: SAME 3x3 conv at the tile's pixels (row m of the tile = pixel (m >> 3, (m & 7) + 8 t))
+    xp = np.pad(x[0], ((1, 1 + TH), (1, 1 + TW * T), (0, 0)))
+    for t in range(T):
+        for m in range(128):
+            ty, tx = m >> 3, (m & 7) + TW * t
+            ref = sum(xp[y0 + ty + dy, x0 + tx + dx] @ w[dy, dx] for dy in range(3) for dx in range(3))
+            if y0 + ty < H and x0 + tx < W:
+                assert np.array_equal(acc[t, m], ref), (t, m)
+
+
+WG_ROWS, WG_COLS = 4, 16                                # train_tc.cu: filter-gradient pixel tile
+
+
+def test_filter_gradient_is_a_gemm_over_pixels_on_mn_major_tiles():
+    rng = np.random.RandomState(1)
+    N, H, W, C = 2, 6, 21, 128                          # H not a multiple of 4, W not of 16
+    x = _ints(rng, (N, H, W, C), -3, 4)
+    dy = _ints(rng, (N, H, W, C), -3, 4)
+    xp, dyp = to_planes(x), to_planes(dy)
+    dw = np.zeros((3, 3, C, C), np.float64)
+    for ky in range(3):                                 # CTA (ky, split): taps (ky, 0..2); here one "split" walks every tile
+        for n in range(N):
+            for y0 in range(0, H, WG_ROWS):
+                for x0 in range(0, W, WG_COLS):
+                    xt = tma_tile(xp, n, 0, 16, y0 + ky - 1, x0 - 1, WG_ROWS, WG_COLS + 2).view(np.uint8).reshape(-1)
+                    yt = tma_tile(dyp, n, 0, 16, y0, x0, WG_ROWS, WG_COLS).view(np.uint8).reshape(-1)
+                    for r in range(WG_ROWS):
+                        b = operand(yt, r * WG_COLS * 16, lbo=128, sbo=WG_ROWS * WG_COLS * 16, rows=C, major='MN')       # (cout, pixel)
+                        for kx in range(3):
+                            a = operand(xt, (r * (WG_COLS + 2) + kx) * 16, lbo=128, sbo=WG_ROWS * (WG_COLS + 2) * 16, rows=C,
+                                        major='MN')                                                                        # (cin, pixel)
+                            dw[ky, kx] += a.astype(np.float64) @ b.astype(np.float64).T
+    # reference: dW[ky][kx][ci][co] = sum_p x[p + (ky-1, kx-1)][ci] dy[p][co]
+    xpad = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0))).astype(np.float64)
+    for ky in range(3):
+        for kx in range(3):
+            ref = np.einsum('nyxi,nyxo->io', xpad[:, ky:ky + H, kx:kx + W], dy.astype(np.float64))
+            assert np.array_equal(dw[ky, kx], ref), (ky, kx)
+
+
+def test_b_concatenation_layout_for_exact_mode():
+    """weights of one stage stored [chunk][plane hi|lo][rows][8] make [w_hi | w_lo] ONE K-major B operand
+    of N = 2 * rows (LBO = 2 * rows * 16), and w_hi alone the first `rows` rows of the same descriptor."""
+    rng = np.random.RandomState(2)
+    rows = 128
+    w_hi, w_lo = _ints(rng, (32, rows)), _ints(rng, (32, rows))                      # (cin within the group, cout)
+    stage = np.zeros((4, 2, rows, 8), np.float16)
+    for ch in range(4):
+        stage[ch, 0] = w_hi[ch * 8:(ch + 1) * 8].T
+        stage[ch, 1] = w_lo[ch * 8:(ch + 1) * 8].T
+    smem = stage.view(np.uint8).reshape(-1)
+    for ks in range(2):
+        b = operand(smem, ks * 2 * (2 * rows * 16), lbo=2 * rows * 16, sbo=128, rows=2 * rows, major='K')
+        k = slice(ks * 16, ks * 16 + 16)
+        assert np.array_equal(b[:rows], w_hi[k].T) and np.array_equal(b[rows:], w_lo[k].T)
+        assert np.array_equal(operand(smem, ks * 2 * (2 * rows * 16), lbo=2 * rows * 16, sbo=128, rows=rows, major='K'), w_hi[k].T)
