@@ -49,8 +49,11 @@ def probclass_macs(C, h, w, k=24, L=6):
 
 def load_traffic(workload, mode):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture of the same workload / mode (profiles/r1b_conv3x3_traffic.json); None for other workloads."""
-    p = os.path.join(ROOT, 'profiles', 'r1b_conv3x3_traffic.json')
+    capture of the same workload / mode (profiles/r2_conv3x3_traffic.json, written by tools/gpu_profile.sh from the
+    .ncu-rep of this round's kernel); None for other workloads / modes."""
+    p = os.path.join(ROOT, 'profiles', 'r2_conv3x3_traffic.json')
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, 'profiles', 'r1b_conv3x3_traffic.json')
     if not os.path.exists(p):
         return None, None
     with open(p) as f:
@@ -182,37 +185,69 @@ def run_reference(args):
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='kodak24', choices=sorted(WORKLOADS))
-    ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'exact'), choices=['fp32', 'exact', 'fast'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-parity', action='store_true')
-    ap.add_argument('--with-decode', action='store_true', help='also time ae.decode(qhard) (configs[1] lists it; not part of the metric)')
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl != 'reference' and not os.environ.get('IC_BENCH_ALLOW_SHORT'):
-        args.warmup = 3            # timing rule: at least three untimed warm-up steps (reported in the JSON line)
-    args.steps = max(args.steps, 1)
-    if args.impl == 'reference':
-        return run_reference(args)
+def oracle_parity(ae, pc, ae_name, mode, x_u8_dev, W, C, nchk=1):
+    """Parity evidence on THIS workload against the CPU oracle (oracle/imgcomp_oracle.py, torch-CPU backend): the first
+    `nchk` images through code/val.py:81-89 -- symbols, bpp -- for the timed mode AND the library's float32 FFMA mode.
+    `safe` = positions whose float64 latent is further than eps from a quantizer decision boundary (there a symbol may
+    not differ between two float32-class implementations)."""
+    import torch
+    from oracle import imgcomp_oracle as O
+    xs = x_u8_dev[:nchk].contiguous()
+    x_np = xs.cpu().numpy()
+    H, Wd = x_np.shape[2], x_np.shape[3]
+    centers = W['autoencoder/encoder/centers']
+    O.set_backend('torch')
+    try:
+        t0 = time.perf_counter()
+        enc = O.encode(x_np.astype(np.float32), W, C)
+        bc, _ = O.pc_bitcost(enc['qbar'], enc['symbols'], W, centers[0])
+        z64 = O.encode(x_np.astype(np.float64), W, C, dtype=np.float64)['z']
+        oracle_s = time.perf_counter() - t0
+    finally:
+        O.set_backend('numpy')
+    o_bpp = bc.reshape(nchk, -1).sum(axis=1, dtype=np.float64) / (H * Wd)
+    c = np.sort(centers.astype(np.float64))
+    margin = np.abs(z64[..., None] - (c[1:] + c[:-1]) / 2).min(axis=-1)
+    sym64 = np.abs(z64[..., None] - centers.astype(np.float64)).argmin(axis=-1)
+    out = {'against': 'oracle/imgcomp_oracle.py (float32 restatement of code/val.py:81-89, torch-CPU convs) + its float64 latent',
+           'images': nchk, 'symbols': int(enc['symbols'].size), 'oracle_seconds': oracle_s,
+           'oracle_f32_vs_f64_symbol_mismatches': int((enc['symbols'] != sym64).sum()), 'bpp_oracle': o_bpp.tolist()}
+    eps = {'fp32': 1e-4, 'exact': 2e-4, 'fast': 2e-2}
+    modes = [mode] + ([] if mode == 'fp32' else ['fp32'])
+    for m in modes:
+        if m == mode:
+            a_m, p_m = ae, pc
+        else:
+            _, _, _, a_m, p_m = make_models(ae_name, m)
+        e = a_m.encode(xs, is_training=False)
+        p_m.bitcost(e.qbar, e.symbols, is_training=False, pad_value=p_m.auto_pad_value(a_m))
+        bpp = (p_m.last_bits_per_image / (H * Wd)).cpu().numpy()
+        sym = e.symbols.cpu().numpy()
+        z = e.z.cpu().numpy()
+        mism = sym != enc['symbols']
+        safe = margin > eps[m]
+        out[m] = {'symbol_mismatches': int(mism.sum()), 'symbol_mismatches_safe_set': int((mism & safe).sum()),
+                  'safe_eps': eps[m], 'symbol_mismatches_vs_float64': int((sym != sym64).sum()),
+                  'max_abs_dz_vs_float64': float(np.abs(z - z64).max()), 'mean_abs_dz_vs_float64': float(np.abs(z - z64).mean()),
+                  'max_abs_dbpp': float(np.abs(bpp - o_bpp).max()), 'bpp': bpp.tolist()}
+        del e
+        if m != mode:
+            del a_m, p_m
+            torch.cuda.empty_cache()
+    out['symbol_mismatches'] = out[mode]['symbol_mismatches']
+    out['max_abs_dbpp'] = out[mode]['max_abs_dbpp']
+    return out
 
+
+def measure_encode_pc(workload, mode, steps, warmup, world, rank, local, with_parity, sample_clocks=True):
+    """One workload of the headline metric: K timed steps of ae.encode + pc.bitcost (device-resident `value`), the same
+    K steps with the library's per-launch events (roofline), and the end-to-end pass from pinned host memory."""
     import torch
     import torch.distributed as dist
     from imgcomp_cvpr_b200 import _lib, weights
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d' % args.gpus
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl')
     L = _lib.lib()
-    ae_name, N, H, Wd = WORKLOADS[args.workload]
-    a, p, W, ae, pc = make_models(ae_name, args.mode)
+    ae_name, N, H, Wd = WORKLOADS[workload]
+    a, p, W, ae, pc = make_models(ae_name, mode)
     C = a.num_chan_bn
     # every rank gets its own shard of the (virtual) global batch: different seeds per rank
     x_host = torch.from_numpy(weights.synthetic_images(N, H, Wd, seed=1234 + rank)).pin_memory()
@@ -230,11 +265,11 @@ def main():
             dist.all_reduce(metric)
         return pc.last_bits_per_image
 
-    def timed(fn, steps):
+    def timed(fn, k):
         """K steps, each bracketed by its own CUDA-event pair on the launching stream; the L2 flush between
         steps is enqueued outside the pairs (not timed); nothing synchronises with the host until the end."""
         evs = []
-        for _ in range(steps):
+        for _ in range(k):
             flush.fill_(1)                     # L2 flush between timed iterations
             a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_ev.record()
@@ -242,36 +277,19 @@ def main():
             b_ev.record()
             evs.append((a_ev, b_ev))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs) / steps
+        return sum(a.elapsed_time(b) for a, b in evs) / k
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(x_dev)
     barrier()
-    # ---- parity evidence on THIS workload: the timed mode against the library's float32 FFMA path
-    # (which tests/test_gpu_hotpath.py pins to the oracle / reference goldens): symbol mismatches and bpp
     parity = None
-    if args.mode != 'fp32' and rank == 0 and not args.no_parity:
-        nchk = min(N, 4)
-        a32, _, _, ae32, pc32 = make_models(ae_name, 'fp32')
-        xs = x_dev[:nchk].contiguous()
-        e_ref = ae32.encode(xs, is_training=False)
-        b_ref = pc32.bitcost(e_ref.qbar, e_ref.symbols, is_training=False, pad_value=pc32.auto_pad_value(ae32))
-        bpp_ref = (pc32.last_bits_per_image / (H * Wd)).cpu()
-        e_m = ae.encode(xs, is_training=False)
-        pc.bitcost(e_m.qbar, e_m.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
-        bpp_m = (pc.last_bits_per_image / (H * Wd)).cpu()
-        mism = (e_m.symbols != e_ref.symbols)
-        parity = {'against': 'fp32 FFMA path, same library', 'images': nchk,
-                  'symbol_mismatches': int(mism.sum().item()), 'symbols': int(mism.numel()),
-                  'max_abs_dz': float((e_m.z - e_ref.z).abs().max().item()),
-                  'max_abs_dbpp': float((bpp_m - bpp_ref).abs().max().item()), 'bpp': bpp_ref.tolist()}
-        del ae32, pc32, e_ref, b_ref, e_m
-        torch.cuda.empty_cache()
+    if with_parity and rank == 0:
+        parity = oracle_parity(ae, pc, ae_name, mode, x_dev, W, C)
     barrier()
     # EVERY rank (step() holds the all-reduce): rank 0's emptied allocator cache makes its next step cudaMalloc the workspace
     # again, which must not land in the timed pass
@@ -280,8 +298,8 @@ def main():
     barrier()
     # ---- device-resident throughput (`value`): K steps, nothing else on the stream
     launches0 = L.ic_launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms = timed(lambda: step(x_dev), args.steps)
+    sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
+    ms = timed(lambda: step(x_dev), steps)
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = L.ic_launch_count() - launches0
@@ -290,7 +308,7 @@ def main():
     # nothing but the path.
     L.ic_profile_reset()
     L.ic_profile_enable(1)
-    ms_profiled = timed(lambda: step(x_dev), args.steps)
+    ms_profiled = timed(lambda: step(x_dev), steps)
     barrier()
     L.ic_profile_enable(0)
     prof = {}
@@ -298,17 +316,7 @@ def main():
         t, n = _lib.c_double(), _lib.c_longlong()
         _lib.check(L.ic_profile_get(cls, t, n))
         prof[name] = (t.value, n.value)
-    decode_ms = None
-    if args.with_decode:
-        enc = ae.encode(x_dev, is_training=False)
-        qh = enc.qhard.clone()
-        for _ in range(2):
-            ae.decode(qh, is_training=False)
-        barrier()
-        decode_ms = timed(lambda: ae.decode(qh, is_training=False), args.steps)
-        barrier()
     # ---- end to end: pinned host uint8 -> H2D -> step -> D2H of the per-image bit sums
-
     # Double-buffered like a streaming val driver: the H2D copy of batch i+1 (copy stream) overlaps the compute of
     # batch i; every step still copies its own inputs from pinned host memory and reads its result back, all inside
     # the timed region.  (No explicit L2 flush here: each step touches > 2 GB of activations, far beyond the 126 MB L2.)
@@ -326,39 +334,33 @@ def main():
             dev_bufs[b].copy_(host_bufs[b], non_blocking=True)
             copied[b].record(copy_stream)
 
-    def e2e_run(steps):
-        main = torch.cuda.current_stream()
+    def e2e_run(k):
+        main_s = torch.cuda.current_stream()
         for b in range(2):
-            consumed[b].record(main)
+            consumed[b].record(main_s)
         issue_copy(0)
-        for i in range(steps):
+        for i in range(k):
             b = i & 1
-            if i + 1 < steps:
+            if i + 1 < k:
                 issue_copy(i + 1)
-            main.wait_event(copied[b])
+            main_s.wait_event(copied[b])
             bits = step(dev_bufs[b])
-            consumed[b].record(main)
+            consumed[b].record(main_s)
             bits_host.copy_(bits, non_blocking=True)
     e2e_run(2)
     barrier()
     a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a_ev.record()
-    e2e_run(args.steps)
+    e2e_run(steps)
     b_ev.record()
     b_ev.synchronize()
-    ms_e2e = a_ev.elapsed_time(b_ev) / args.steps
+    ms_e2e = a_ev.elapsed_time(b_ev) / steps
     barrier()
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     pix = N * H * Wd
-    value = world * pix / (ms * 1e-3) / 1e6
-    e2e = world * pix / (ms_e2e * 1e-3) / 1e6
     peaks, peak_src = load_peaks()
     # roofline of the dominant kernel class: the 32 3x3 128->128 convs
     t3, n3 = prof['conv3x3']
@@ -367,41 +369,209 @@ def main():
     avg_ms = t3 / max(n3, 1)
     achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if n3 else 0.0
     peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
-    traffic, traffic_src = load_traffic(args.workload, args.mode)
+    traffic, traffic_src = load_traffic(workload, mode)
     step_flop = 2.0 * (encoder_macs_per_pixel(C) * pix + N * probclass_macs(C, H // 8, Wd // 8, p.arch_param__k))
-    out = {
-        'metric': 'MPix/s encode+probclass fwd', 'value': value, 'unit': 'MPix/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'fp32': 'f32', 'exact': 'f16x3 (fp32-class, fp32 accumulate)', 'fast': 'f16'}[args.mode],
-        'data': 'synthetic',
-        'config': {'workload': args.workload, 'ae': ae_name, 'pc': 'cvpr/res_shallow', 'batch_per_gpu': N,
-                   'H': H, 'W': Wd, 'mode': args.mode, 'parallelism': 'batch-shard x%d' % world,
+    mmas = {'exact': 3, 'fast': 1, 'fp32': 0}[mode]
+    res = {
+        'value': world * pix / (ms * 1e-3) / 1e6, 'ms_per_step': ms,
+        'config': {'workload': workload, 'ae': ae_name, 'pc': 'cvpr/res_shallow', 'batch_per_gpu': N,
+                   'H': H, 'W': Wd, 'mode': mode, 'parallelism': 'batch-shard x%d' % world,
                    'l2': 'flushed between timed iterations (%d MiB write)' % (L2_FLUSH_BYTES >> 20)},
-        'e2e': {'value': e2e, 'unit': 'MPix/s', 'h2d_bytes_per_step': int(x_host.numel()),
+        'e2e': {'value': world * pix / (ms_e2e * 1e-3) / 1e6, 'unit': 'MPix/s', 'h2d_bytes_per_step': int(x_host.numel()),
                 'd2h_bytes_per_step': int(bits_host.numel() * 8), 'ms_per_step': ms_e2e},
-        'gpu_launches': int(launches),
-        'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_128x128 (%s)' % args.mode, 'achieved': achieved,
+        'gpu_launches': int(launches), 'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_128x128 (%s)' % mode, 'achieved': achieved,
                      'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
                      'peak_source': '%s bf16_tflops_sustained' % peak_src, 'traffic': traffic,
                      'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'traffic_source': traffic_src,
                      # in + out activations (hi/lo fp16 planes = 4 B / element) + 0 / 1 / 2 residual reads, averaged over a residual group
                      'algorithmic_bytes_per_launch': m_rows * 128 * 4.0 * (2 * 6 + 3 + 1) / 6.0,
                      'flop_per_launch': flop_per_launch, 'avg_launch_ms': avg_ms, 'launches': n3,
-                     'share_of_step': t3 / (ms_profiled * args.steps) if ms_profiled else None,
+                     'share_of_step': t3 / (ms_profiled * steps) if ms_profiled else None,
                      'ms_per_step_with_launch_events': ms_profiled,
-                     'mma_flops_per_algorithmic_flop': {'exact': 3, 'fast': 1, 'fp32': 0}[args.mode],
-                     'tensor_issue_frac': (achieved * {'exact': 3, 'fast': 1, 'fp32': 0}[args.mode] / peak) if peak else None,
+                     'mma_flops_per_algorithmic_flop': mmas,
+                     'tensor_issue_frac': (achieved * mmas / peak) if peak else None,
                      'note': 'exact = fp16x3 split: 3 tensor-core FLOPs per algorithmic FLOP, so frac <= 1/3 by construction',
                      'step_algorithmic_tflop': step_flop / 1e12,
-                     'step_tflops': step_flop / (ms * 1e-3) / 1e12},
-        'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
+                     'step_tflops': step_flop / (ms * 1e-3) / 1e12,
+                     'step_frac': step_flop / (ms * 1e-3) / 1e12 / peak if peak else None},
+        'kernel_ms_per_step': {k: v[0] / steps for k, v in prof.items()},
         'parity': parity,
-        'decode': None if decode_ms is None else {'ms_per_step': decode_ms, 'MPix_per_s': world * pix / (decode_ms * 1e-3) / 1e6},
     }
+    ctx = {'ae': ae, 'pc': pc, 'W': W, 'a': a, 'p': p, 'x_dev': x_dev, 'timed': timed, 'barrier': barrier}
+    return res, ctx
+
+
+def measure_train_step(steps):
+    """BASELINE.json configs[2]: one training step (forward + MS-SSIM / rate loss + backward + two Adam groups) at B = 32,
+    160x160, cvpr/med + res_shallow, replayed as one CUDA graph (code/train.py:86-132,252,339-349)."""
+    import torch
+    from imgcomp_cvpr_b200 import _lib, config, trainer, weights
+    a, p = config.ae_config('cvpr/med'), config.pc_config('cvpr/res_shallow')
+    W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
+    B, S = 32, 160
+    x = torch.from_numpy(weights.synthetic_images(B, S, S, seed=77)).cuda()
+    tr = trainer.Trainer(a, p, W, num_itr_per_epoch=1000, mode='exact')
+    L = _lib.lib()
+    n0 = L.ic_launch_count()
+    tr.step(x)                                    # eager once: counts the launches one step is made of
+    per_step = L.ic_launch_count() - n0
+    tr.enable_cuda_graph(x)
+    for _ in range(3):
+        out = tr.step(x)
+    torch.cuda.synchronize()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device='cuda')
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = tr.step(x)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a_.elapsed_time(b_) for a_, b_ in evs) / steps
+    pix = B * S * S
+    # forward MACs of SURVEY.md 8(d) (encoder + decoder + context model) x 3: forward, data gradient, filter gradient
+    tflop = 3 * 2 * (310562 + 309488 + 10470) * pix / 1e12
+    peaks, peak_src = load_peaks()
+    peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    del tr
+    torch.cuda.empty_cache()
+    return {'workload': 'cfg3: B=32 160x160 cvpr/med + res_shallow, forward + loss + backward + Adam (one CUDA graph replay)',
+            'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'MPix_per_s': pix / (ms * 1e-3) / 1e6,
+            'dtype': 'f32 + f16x3 tcgen05 3x3 convs (forward, data gradient, filter gradient)', 'steps': steps,
+            'gpu_launches_per_step': int(per_step), 'loss': out['total_loss'], 'bpp': out['bpp'], 'ms_ssim': out['ms_ssim'],
+            'roofline': {'bound': 'tensor', 'achieved': tflop / (ms * 1e-3), 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': tflop / (ms * 1e-3) / peak if peak else None, 'peak_source': '%s bf16_tflops_sustained' % peak_src,
+                         'algorithmic_tflop_per_step': tflop}}
+
+
+def measure_real_bpp(n_images=8):
+    """BASELINE.json configs[4] (--real_bpp, code/val.py:161-175, code/bit_counter.py:13-74) on Kodak-shaped inputs: the one
+    batched context-model pass that replaces the per-symbol loop, the host range coder, and the sequential decoder."""
+    import torch
+    from imgcomp_cvpr_b200 import autoencoder, codec, config, probclass, weights
+    a, p = config.ae_config('cvpr/low'), config.pc_config('cvpr/res_shallow')
+    W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
+    ae = autoencoder.get_network_cls(a)(a, weights=W, mode='exact')
+    pc = probclass.get_network_cls(p)(p, num_centers=a.num_centers, weights=W)
+    x = weights.synthetic_images(n_images, 768, 512, seed=3)
+    imgs = [np.transpose(xi, (1, 2, 0)) for xi in x]
+    threads = min(n_images, os.cpu_count() or 1)
+    xd = torch.from_numpy(x).cuda()
+    sym = ae.encode(xd, is_training=False).symbols.clone()
+    centers = ae.centers_tensor()
+    tables_ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pc.freqs(sym, centers, codec=True)
+        e1.record()
+        torch.cuda.synchronize()
+        tables_ms.append(e0.elapsed_time(e1))
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        blobs = codec.compress(imgs, ae, pc, batch_size=n_images, threads=threads)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        rec = codec.decompress(blobs, ae, pc, batch_size=n_images)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        cur = ((t1 - t0) * 1e3, (t2 - t1) * 1e3)
+        best = cur if best is None or sum(cur) < sum(best) else best
+    # what val.py reconstructs from the encoder's own symbols must be what comes back from the stream alone
+    ae.decode(centers[sym], is_training=False)
+    same = all(np.array_equal(rec[i], np.transpose(ae.extra['x_out_u8'][i].cpu().numpy(), (1, 2, 0))) for i in range(n_images))
+    items = [codec.unpack(b) for b in blobs]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pc.decode_streams([it['stream'] for it in items], [it['first_sym'] for it in items], (32, 96, 64), centers)
+    e1.record()
+    torch.cuda.synchronize()
+    coded_bpp = float(np.mean([8.0 * len(it['stream']) / (768 * 512) for it in items]))
+    return {'workload': 'cfg5: %d Kodak-shaped images (768x512), cvpr/low + res_shallow, real bitstreams' % n_images,
+            'symbols_per_image': int(sym[0].numel()), 'host_coder_threads': threads, 'coded_bpp': coded_bpp,
+            'tables_ms_all_images': min(tables_ms), 'tables_ms_per_image': min(tables_ms) / n_images,
+            'compress_ms_per_image': best[0] / n_images, 'decompress_ms_per_image': best[1] / n_images,
+            'sequential_decode_kernel_ms_all_images': e0.elapsed_time(e1), 'round_trip_bit_identical': bool(same),
+            'reference': 'README.md:65-66: ~350 s encode + ~200 s decode per Kodak image (one sess.run per symbol)'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='kodak24', choices=sorted(WORKLOADS))
+    ap.add_argument('--mode', default=os.environ.get('IC_BENCH_MODE', 'exact'), choices=['fp32', 'exact', 'fast'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the sub-records of the other BASELINE.json configs (N = 1 runs only)')
+    ap.add_argument('--with-decode', action='store_true', help='also time ae.decode(qhard) (configs[1] lists it; not part of the metric)')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != 'reference' and not os.environ.get('IC_BENCH_ALLOW_SHORT'):
+        args.warmup = 3            # timing rule: at least three untimed warm-up steps (reported in the JSON line)
+    args.steps = max(args.steps, 1)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from imgcomp_cvpr_b200 import weights
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl')
+    res, ctx = measure_encode_pc(args.workload, args.mode, args.steps, args.warmup, world, rank, local,
+                                 with_parity=not args.no_parity)
+    decode_ms = None
+    if args.with_decode:
+        ae = ctx['ae']
+        enc = ae.encode(ctx['x_dev'], is_training=False)
+        qh = enc.qhard.clone()
+        for _ in range(2):
+            ae.decode(qh, is_training=False)
+        ctx['barrier']()
+        decode_ms = ctx['timed'](lambda: ae.decode(qh, is_training=False), args.steps)
+        ctx['barrier']()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ae_name, N, H, Wd = WORKLOADS[args.workload]
+    W, C = ctx['W'], ctx['a'].num_chan_bn
+    del ctx
+    torch.cuda.empty_cache()
+    out = {
+        'metric': 'MPix/s encode+probclass fwd', 'value': res['value'], 'unit': 'MPix/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'fp32': 'f32', 'exact': 'f16x3 (fp32-class, fp32 accumulate)', 'fast': 'f16'}[args.mode],
+        'data': 'synthetic',
+    }
+    for k in ('config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'kernel_ms_per_step', 'parity'):
+        out[k] = res[k]
+    out['decode'] = None if decode_ms is None else {'ms_per_step': decode_ms, 'MPix_per_s': world * N * H * Wd / (decode_ms * 1e-3) / 1e6}
+    if world == 1 and not args.no_extras:
+        # the other BASELINE.json configs, each with its own numbers (N = 1 only: they are not part of the scaling run)
+        k = max(3, min(args.steps, 5))
+        if args.workload != 'b64_512':
+            h, _ = measure_encode_pc('b64_512', args.mode, k, 3, 1, 0, local, with_parity=not args.no_parity, sample_clocks=False)
+            out['headline'] = {'note': 'north-star target shape B=64 512x512 cvpr/low (BASELINE.json north_star)', 'steps': k,
+                               'value': h['value'], 'unit': 'MPix/s', 'ms_per_step': h['ms_per_step'], 'e2e': h['e2e'],
+                               'roofline': h['roofline'], 'kernel_ms_per_step': h['kernel_ms_per_step'], 'parity': h['parity']}
+            torch.cuda.empty_cache()
+        if args.mode == 'exact':
+            out['train_step'] = measure_train_step(k)
+            out['real_bpp'] = measure_real_bpp()
     if not args.no_cpu_baseline:
-        import torch as _t
         from oracle import imgcomp_oracle as O
         O.set_backend('torch')
         xs = weights.synthetic_images(1, H, Wd, seed=1234)

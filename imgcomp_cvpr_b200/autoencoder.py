@@ -18,6 +18,23 @@ SCOPE_AE = 'autoencoder'
 SCOPE_AE_ENC = SCOPE_AE + '/encoder'
 SCOPE_AE_DEC = SCOPE_AE + '/decoder'
 
+# A trainable variable as the reference's callers see one (tf.Variable: .name / value), code/autoencoder.py:71-79
+Variable = namedtuple('Variable', ['name', 'value'])
+
+# The reference keeps variables and regularisation terms in TF's global graph collections, which is why
+# encoder_variables() / *_regularization_loss() are static there (code/autoencoder.py:71-88).  Same here: the variables
+# of the last network whose weights were loaded, by TF name, and the config that carries the regularisation factors.
+_GRAPH = {'variables': {}, 'config': None}
+
+
+def _trainable(name):
+    return not (name.endswith('/moving_mean') or name.endswith('/moving_variance'))
+
+
+def _l2_loss(w):
+    """tf.nn.l2_loss: sum(w ** 2) / 2"""
+    return float(np.sum(np.asarray(w, np.float64) ** 2) / 2)
+
 
 def get_network_cls(config):
     """code/autoencoder.py:26-29"""
@@ -70,6 +87,10 @@ class _Network(object):
             L.ic_ae_destroy(self._handle)
         self._handle = h
         self._centers_value = torch.from_numpy(np.asarray(weights[SCOPE_AE_ENC + '/centers'], np.float32)).cuda()
+        self._weights = {n: a for n, a in zip(names, arrays)}
+        self._train = None
+        _GRAPH['variables'] = self._weights
+        _GRAPH['config'] = self.config
 
     def __del__(self):
         try:
@@ -100,22 +121,41 @@ class _Network(object):
         """-> EncoderOutput(qbar, qhard, symbols, z, heatmap) (code/autoencoder.py:50-58).
         x: CUDA tensor N x 3 x H x W, float32 in [0,255] (or uint8: tf.to_float of
         val.py:83 is fused)."""
-        if is_training:
-            raise NotImplementedError('is_training=True (batch-statistics BN + backward) is not built yet')
         if x.dtype not in (torch.float32, torch.uint8):
             raise AssertionError('Expected float32 for x, got {}'.format(x.dtype))     # autoencoder.py:51
         if x.dim() != 4 or x.shape[1] != 3 or not x.is_cuda:
             raise ValueError('expected a CUDA tensor N x 3 x H x W, got {}'.format(tuple(x.shape)))
         self._need_handle()
         self._centers = self._centers_value
+        if is_training:
+            return self._encode_training(x.contiguous())
         return self._encode(x.contiguous(), is_training)
 
     def decode(self, q, is_training):
         """-> x_out N x 3 x 8h x 8w float32 clipped to [0,255] (code/autoencoder.py:60-63)."""
-        if is_training:
-            raise NotImplementedError('is_training=True is not built yet')
         self._need_handle()
+        if is_training:
+            return self._training_net().decode_forward(q.contiguous().float(), is_training=True)
         return self._decode(q.contiguous().float(), is_training)
+
+    # -- is_training=True: batch-statistics batch norm (code/autoencoder.py:115-125), the forward of code/train.py:101-102
+    def _training_net(self):
+        """The training-mode forward lives in trainer.Trainer (batch-norm batch statistics, float32 NHWC primitives /
+        tcgen05 3x3 convs); built lazily over this network's variables.  Forward only: gradients and the optimiser are
+        trainer.Trainer.step (train.get_train_op)."""
+        if self._train is None:
+            from . import config as config_mod, trainer, weights as weights_mod
+            pc_cfg = config_mod.pc_config('cvpr/res_shallow')
+            W = weights_mod.synthetic_weights(self.config.num_chan_bn, self.config.num_centers, pc_cfg.arch_param__k,
+                                              self.config.arch_param_B)      # context-model slots of the Trainer: unused here
+            W.update(self._weights)
+            self._train = trainer.Trainer(self.config, pc_cfg, W, mode='fp32' if self.mode == _lib.IC_MODE_FP32 else 'exact')
+        return self._train
+
+    def _encode_training(self, x):
+        enc = self._training_net().encode_forward(x, is_training=True)
+        self.extra = {'qsoft': enc['qsoft']}
+        return EncoderOutput(enc['qbar'], enc['qhard'], enc['symbols'], enc['z'], enc['heatmap'])
 
     def centers_tensor(self):
         """the loaded centers (L,) float32 CUDA; unlike get_centers_variable it needs no encode() first --
@@ -127,6 +167,49 @@ class _Network(object):
         if self._centers is None:
             raise ValueError('Call -encode(...) before trying to access centers')      # autoencoder.py:66-67
         return self._centers
+
+    @staticmethod
+    def _get_trainable_vars_assert_non_empty(scope):
+        """code/autoencoder.py:81-88"""
+        v = [Variable(n, a) for n, a in _GRAPH['variables'].items() if n.startswith(scope + '/') and _trainable(n)]
+        assert len(v) > 0, 'No trainable vars in scope {}. All: {}'.format(scope, sorted(_GRAPH['variables']))
+        return v
+
+    @staticmethod
+    def encoder_variables():
+        """ Includes center variable (code/autoencoder.py:71-74) """
+        return _Network._get_trainable_vars_assert_non_empty(scope=SCOPE_AE_ENC)
+
+    @staticmethod
+    def decoder_variables():
+        """code/autoencoder.py:76-78"""
+        return _Network._get_trainable_vars_assert_non_empty(scope=SCOPE_AE_DEC)
+
+    @staticmethod
+    def _regularization_loss(scope):
+        """tf.losses.get_regularization_loss(scope): slim.l2_regularizer(regularization_factor) on every conv weight of
+        the scope (code/autoencoder.py:98-102) + regularization_factor_centers * l2_loss(centers) (code/quantizer.py:18-24)"""
+        cfg = _GRAPH['config']
+        assert cfg is not None, 'no variables: load weights first'
+        total = 0.0
+        for n, a in _GRAPH['variables'].items():
+            if not n.startswith(scope + '/'):
+                continue
+            if n.endswith('/weights'):
+                total += cfg.regularization_factor * _l2_loss(a)
+            elif n.endswith('/centers') and cfg.regularization_factor_centers != 0:
+                total += cfg.regularization_factor_centers * _l2_loss(a)
+        return total
+
+    @staticmethod
+    def encoder_regularization_loss():
+        """ includes centers regularization (code/autoencoder.py:80-83) """
+        return _Network._regularization_loss(SCOPE_AE_ENC)
+
+    @staticmethod
+    def decoder_regularization_loss():
+        """code/autoencoder.py:85-87"""
+        return _Network._regularization_loss(SCOPE_AE_DEC)
 
 
 class _CVPR(_Network):

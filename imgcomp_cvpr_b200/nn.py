@@ -17,11 +17,18 @@ _ws_cache = {}
 
 
 def _workspace(nbytes):
+    """Process-wide scratch buffer, grown on demand.  Growing REPLACES the tensor: whoever baked its address into a CUDA
+    graph must hold a reference to the old one (trainer.Trainer.enable_cuda_graph does, via current_workspace()), so the
+    block cannot return to the allocator while replays still write to it."""
     ws = _ws_cache.get('ws')
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device='cuda')
         _ws_cache['ws'] = ws
     return ws
+
+
+def current_workspace():
+    return _ws_cache.get('ws')
 
 
 def _geo(x_shape, w_shape, stride, transposed, valid):

@@ -89,6 +89,22 @@ class _Network3D(object):
         if self._handle is not None:
             L.ic_pc_destroy(self._handle)
         self._handle = h
+        self._weights = dict(zip(self.variable_names(), arrays))
+
+    def variables(self):
+        """tf.trainable_variables('probclass3d') (code/probclass.py:109-114) as (name, value) pairs"""
+        from .autoencoder import Variable
+        trainable_vars = [Variable(n, a) for n, a in getattr(self, '_weights', {}).items()]
+        assert len(trainable_vars) > 0, 'No trainable variables found in scope {}.'.format(self._PROBCLASS_SCOPE)
+        return trainable_vars
+
+    def regularization_loss(self):
+        """code/probclass.py:116-120: None unless pc_config.regularization_factor is set; then
+        regularization_factor * sum l2_loss(conv3d weights) (the regulariser of :249-251)"""
+        if self.config.regularization_factor is None:
+            return None
+        return self.config.regularization_factor * sum(
+            float(np.sum(np.asarray(a, np.float64) ** 2) / 2) for n, a in self._weights.items() if n.endswith('/weights'))
 
     def __del__(self):
         try:
@@ -112,8 +128,8 @@ class _Network3D(object):
         """Pads q, runs the context model, cross entropy against target_symbols.
         q NCHW float32, target_symbols NCHW int64 -> bitcost per symbol NCHW
         (code/probclass.py:63-106)."""
-        if is_training:
-            raise NotImplementedError('is_training=True is not built yet')
+        # is_training only reaches _logits, whose conv3d layers have no batch norm / dropout (code/probclass.py:214-261):
+        # the training-mode forward IS this forward.  Gradients: trainer.Trainer.step (train.get_train_op).
         assert q.dim() == 4                                                      # tf_helpers.assert_ndims(q, 4), :71
         self._need_handle()
         self.reuse = True

@@ -31,9 +31,13 @@ def regularization_losses(ae_config, pc_config, weights):
     return enc, dec, pcr
 
 
-def get_loss(config, ae, pc, d_loss_scaled, bc, heatmap, reg=(0.0, 0.0, None)):
-    """code/train.py:303-336.  bc, heatmap: NCHW float32 CUDA tensors.  `reg` = regularization_losses(...).
+def get_loss(config, ae, pc, d_loss_scaled, bc, heatmap, reg=None):
+    """code/train.py:303-336.  bc, heatmap: NCHW float32 CUDA tensors.  The regularisation terms come from
+    pc.regularization_loss() / ae.encoder_regularization_loss() / ae.decoder_regularization_loss() as in the reference
+    (:321-326) unless `reg` = regularization_losses(...) is given.
     -> (total_loss, H_real, pc_comps, ae_comps) as Python floats."""
+    if reg is None:
+        reg = (ae.encoder_regularization_loss(), ae.decoder_regularization_loss(), pc.regularization_loss())
     assert config.H_target
     bc = bc.contiguous().float()
     hm = heatmap.contiguous().float() if heatmap is not None else None

@@ -465,6 +465,19 @@ class Trainer(object):
         net = self._bias_act(c2, S[2], False, res1=skip)
         return self._bias_act(self._conv3d(net, S[3]), S[3], True)
 
+    # ------------------------------------------------------------------ forward-only entry points (autoencoder.py mirror)
+    def encode_forward(self, x, is_training=True, update_moving=False):
+        """ae.encode(x, is_training) of code/train.py:101 without a tape: batch-statistics batch norm when is_training.
+        -> dict(qbar, qhard, qsoft, symbols, z, heatmap) NCHW"""
+        assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0
+        self.is_training, self.update_moving, self.tape = is_training, update_moving, None
+        return self._encode(x.contiguous())
+
+    def decode_forward(self, q, is_training=True, update_moving=False):
+        """ae.decode(q, is_training) of code/train.py:102; q NCHW float32 -> x_out NCHW float32 clipped to [0, 255]"""
+        self.is_training, self.update_moving, self.tape = is_training, update_moving, None
+        return self._decode(nn.nchw_to_nhwc(q.contiguous().float()))
+
     # ------------------------------------------------------------------ the graph of code/train.py:86-132
     def _enqueue(self, x, is_training, update_moving, backward):
         """Enqueues forward (+ backward) without any host read-back: the loss scalars stay in self._sums / self._val, the
@@ -611,6 +624,9 @@ class Trainer(object):
             self._graph_tensors = self._enqueue(self._x_static, True, True, True)
             self._enqueue_adam()
         self._graph = graph
+        # the captured launches hold raw pointers into the shared scratch buffer of nn.py: keep THAT tensor alive for as
+        # long as the graph is, whatever a later, larger call elsewhere replaces the shared one with
+        self._graph_ws = nn.current_workspace()
         return self
 
 

@@ -87,6 +87,39 @@ def test_decode_golden_image_symbols(gpu_models):
     assert torch.equal(x0, x1)
 
 
+def test_codec_tables_and_stream_against_reference_run_golden(gpu_models):
+    """The tables a real stream is coded with (codec=True: the float32 chain the decoder re-derives) against the tables the
+    reference's own per-symbol loop produced for the same symbols (tests/golden/make_golden.py: PredictionNetwork.get_freqs
+    through code/bit_counter.py:103-134): within 256 of 1e9 counts (the numpy oracle is within 128: float32 softmax
+    rounding), the stream within 2 bytes of the reference's, byte-identical whenever every table is."""
+    from imgcomp_cvpr_b200 import arithmetic_coding as ac
+    ae, pc, W = gpu_models('cvpr/low')
+    g = load_golden('tiny_low_1x64x64')
+    centers = torch.from_numpy(W['autoencoder/encoder/centers']).cuda()
+    sym = torch.from_numpy(g['symbols'].astype(np.int64)).cuda()
+    f, bits = pc.freqs(sym, centers, codec=True)
+    f = f[0].cpu().numpy()
+    d = np.abs(f - g['freqs'])
+    print('codec tables vs reference-run golden: max |df| %d, tables differing %d / %d' % (d.max(), (d.max(-1) > 0).sum(), d[..., 0].size))
+    assert d.max() <= 256
+    assert abs(bits.item() - float(g['theory_bits'])) < 0.05
+    enc = ac.ArithmeticEncoder()
+    s_flat = g['symbols'].reshape(-1).astype(np.int64)
+    enc.write(f.reshape(-1, 6)[1:], s_flat[1:])
+    stream = np.frombuffer(enc.finish()[0], np.uint8)
+    assert abs(len(stream) - len(g['bitstream'])) <= 2
+    if d.max() == 0:
+        assert np.array_equal(stream, g['bitstream'])
+    # the reference's stream itself (coded with the reference's tables) decodes on the device up to the first position
+    # whose table differs; with identical tables it decodes completely
+    if d.max() == 0:
+        out = pc.decode_streams([g['bitstream'].tobytes()], [int(s_flat[0])], (32, 8, 8), centers)
+        assert np.array_equal(out[0].cpu().numpy().astype(np.int64), g['symbols'][0])
+    # default (tensor-core) tables: same distribution, hi/lo arithmetic instead of the float32 chain
+    fb, _ = pc.freqs(sym, centers)
+    assert np.abs(fb[0].cpu().numpy() - g['freqs']).max() <= 3e4
+
+
 def test_codec_tables_close_to_default_tables(gpu_models):
     """codec tables (float32 chain) vs the default tensor-core tables: same distribution"""
     ae, pc, W = gpu_models('cvpr/low')

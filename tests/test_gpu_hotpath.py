@@ -342,3 +342,45 @@ def test_training_loss_forward(gpu_models, synth):
     dm = train.Distortions(a, x160, y160, True)           # ms_ssim config on the training crop size
     assert abs(dm.d_loss_scaled - a.K_ms_ssim * (1 - dm.ms_ssim)) < 1e-3
     assert abs(dm.ms_ssim - O.ms_ssim_tf(x160.cpu().numpy(), y160.cpu().numpy())[0]) < 1e-4
+
+
+def test_training_mode_boundary_drops_in(gpu_models, synth):
+    """code/train.py:101-112 against the host mirror, call for call: ae.encode(x, is_training=True),
+    ae.decode(enc.qbar, True), pc.bitcost(qbar, symbols, True, pad) (batch-statistics batch norm), get_loss with the
+    regularisation terms taken from ae / pc as the reference does (:321-326), pc.variables()."""
+    from imgcomp_cvpr_b200 import autoencoder, bits, probclass, train, weights as wm
+    from oracle import train_oracle as T
+    a, p, W = synth('cvpr/low')
+    x = wm.synthetic_images(2, 64, 64, seed=22)
+    ref = T.training_step(x, W, a, p, dtype=torch.float64, training=True)
+    for mode in ('fp32', 'exact'):
+        ae = autoencoder.get_network_cls(a)(a, weights=W, mode=mode)
+        pc = probclass.get_network_cls(p)(p, num_centers=a.num_centers, weights=W)
+        xt = _cuda(x).float()
+        enc_out_train = ae.encode(xt, is_training=True)
+        x_out_train = ae.decode(enc_out_train.qbar, is_training=True)
+        bc_train = pc.bitcost(enc_out_train.qbar, enc_out_train.symbols, is_training=True, pad_value=pc.auto_pad_value(ae))
+        bpp_train = bits.bitcost_to_bpp(bc_train, xt).item()
+        sym = enc_out_train.symbols.cpu().numpy()
+        assert np.array_equal(sym, ref['tensors']['symbols']), mode
+        np.testing.assert_allclose(enc_out_train.heatmap.cpu().numpy(), ref['tensors']['heatmap'], atol=5e-4)
+        np.testing.assert_allclose(enc_out_train.qbar.cpu().numpy(), ref['tensors']['qbar'], atol=1e-5)
+        np.testing.assert_allclose(x_out_train.cpu().numpy(), ref['tensors']['x_out'], atol=3e-2)
+        np.testing.assert_allclose(bc_train.cpu().numpy(), ref['tensors']['bc'], atol=3e-3)
+        assert abs(bpp_train - ref['tensors']['bc'].sum() / (2 * 64 * 64)) < 1e-4
+        # the inference path of the same object is untouched by the training-mode calls
+        e_inf = ae.encode(_cuda(x), is_training=False)
+        assert e_inf.symbols.shape == enc_out_train.symbols.shape
+        a_mse = type(a)(**dict(a.__dict__, distortion_to_minimize='mse'))
+        d_train = train.Distortions(a_mse, xt, x_out_train, is_training=True)
+        total, H_real, pc_comps, ae_comps = train.get_loss(a, ae, pc, d_train.d_loss_scaled, bc_train, enc_out_train.heatmap)
+        assert abs(H_real - ref['H_real']) < 1e-4 and abs(dict(pc_comps)['H_mask'] - ref['H_mask']) < 1e-4
+        assert abs(dict(pc_comps)['pc_loss'] - ref['pc_loss']) < 1e-4 * max(1.0, ref['pc_loss'])
+        assert abs(dict(ae_comps)['reg_enc_dec'] + dict(pc_comps)['reg'] - ref['reg']) < 1e-6 * ref['reg']
+    reg = train.regularization_losses(a, p, W)
+    assert abs(ae.encoder_regularization_loss() - reg[0]) < 1e-9 and abs(ae.decoder_regularization_loss() - reg[1]) < 1e-9
+    assert pc.regularization_loss() is None                                   # pc_configs/base: regularization_factor = None
+    names = [v.name for v in ae.encoder_variables()]
+    assert 'autoencoder/encoder/centers' in names and not any('moving_' in n for n in names)      # trainable only
+    assert len(names) == 3 * 35 + 1 and len(ae.decoder_variables()) == 3 * 35
+    assert [v.name for v in pc.variables()] == pc.variable_names() and len(pc.variables()) == 8

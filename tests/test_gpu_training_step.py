@@ -255,3 +255,24 @@ def test_cuda_graph_step_is_the_eager_step(synth):
     We, Wg = tr_e.weights(), tr_g.weights()
     for k in We:
         assert np.array_equal(We[k], Wg[k]), k
+
+
+def test_cuda_graph_survives_growth_of_the_shared_workspace(synth):
+    """The captured step holds raw pointers into nn.py's shared scratch buffer; a later, larger call replaces that buffer.
+    The graph owner keeps the old block alive, so replays neither read nor corrupt memory handed to other tensors."""
+    from imgcomp_cvpr_b200 import nn, weights
+    ae_cfg, pc_cfg, Wt, x, tr_e = _setup(synth, 'cvpr/low', 2, 64, 64, seed=22, mode='exact')
+    _, _, _, _, tr_g = _setup(synth, 'cvpr/low', 2, 64, 64, seed=22, mode='exact')
+    xs = [torch.from_numpy(weights.synthetic_images(2, 64, 64, seed=40 + i)).cuda() for i in range(3)]
+    tr_g.enable_cuda_graph(xs[0])
+    ws_before = nn.current_workspace()
+    big = torch.from_numpy(weights.synthetic_images(4, 160, 160, seed=3)).cuda()
+    _, _, _, _, tr_big = _setup(synth, 'cvpr/low', 4, 160, 160, seed=3, mode='exact')
+    tr_big.forward_backward(big)                                  # needs a larger scratch buffer -> replaced
+    assert nn.current_workspace() is not ws_before and tr_g._graph_ws is ws_before
+    filler = [torch.full((1 << 20,), 7.0, device='cuda') for _ in range(64)]        # whatever the allocator hands out next
+    for xi in xs:
+        a, b = tr_e.step(xi), tr_g.step(xi)
+        for k in ('total_loss', 'd_loss_scaled', 'pc_loss', 'H_real', 'H_mask', 'ms_ssim', 'bpp'):
+            assert a[k] == b[k], (k, a[k], b[k])
+    assert all(float(f.min()) == 7.0 and float(f.max()) == 7.0 for f in filler)
