@@ -60,6 +60,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_pc_codec_freqs_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_pc_codec_freqs_u32_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_pc_decode_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
     'ic_pc_decode_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -117,6 +119,7 @@ SIGNATURES = {
     'ic_profile_get': (c_int, [c_int, POINTER(c_double), POINTER(c_longlong)]),
     'ic_ac_enc_create': (c_int, [POINTER(c_void_p)]),
     'ic_ac_enc_write': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64]),
+    'ic_ac_enc_write_u32': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64]),
     'ic_ac_enc_finish': (c_int, [c_void_p, POINTER(POINTER(c_uint8)), POINTER(c_int64), POINTER(c_int64)]),
     'ic_ac_enc_destroy': (None, [c_void_p]),
     'ic_ac_dec_create': (c_int, [c_void_p, c_int64, POINTER(c_void_p)]),

@@ -24,6 +24,17 @@ class ArithmeticEncoder(object):
             raise ValueError(_lib.lib().ic_last_error().decode())     # the reference raises ValueError (:94-97)
         _lib.check(rc)
 
+    def write_u32(self, freqs, symbols):
+        """the same over uint32 tables (n,L) and uint8 symbols (n,), e.g. views into pinned staging buffers: no copies"""
+        f = np.asarray(freqs)
+        s = np.asarray(symbols)
+        assert f.dtype == np.uint32 and s.dtype == np.uint8 and f.flags.c_contiguous and s.flags.c_contiguous
+        f = f.reshape(s.size, -1)
+        rc = _lib.lib().ic_ac_enc_write_u32(self._h, f.ctypes.data, f.shape[1], s.ctypes.data, s.size)
+        if rc == -1:
+            raise ValueError(_lib.lib().ic_last_error().decode())
+        _lib.check(rc)
+
     def finish(self):
         """-> (bytes, num_bits before byte padding)"""
         p = ctypes.POINTER(ctypes.c_uint8)()

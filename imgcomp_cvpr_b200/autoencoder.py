@@ -86,7 +86,8 @@ class _Network(object):
         if self._handle is not None:
             L.ic_ae_destroy(self._handle)
         self._handle = h
-        self._centers_value = torch.from_numpy(np.asarray(weights[SCOPE_AE_ENC + '/centers'], np.float32)).cuda()
+        self._centers_host = np.ascontiguousarray(np.asarray(weights[SCOPE_AE_ENC + '/centers'], np.float32))
+        self._centers_value = torch.from_numpy(self._centers_host).cuda()
         self._weights = {n: a for n, a in zip(names, arrays)}
         self._train = None
         _GRAPH['variables'] = self._weights
@@ -162,6 +163,11 @@ class _Network(object):
         a decoder process never encodes (codec.py)."""
         self._need_handle()
         return self._centers_value
+
+    def centers_host(self):
+        """the loaded centers as a host float32 array (the codec hands them to calls that must not synchronise)"""
+        self._need_handle()
+        return self._centers_host
 
     def get_centers_variable(self):
         if self._centers is None:

@@ -28,6 +28,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 MAGIC = b'ICB2'
+MAX_SIDE = 1 << 16
 VERSION = 1
 _HEADER = struct.Struct('<4sBBHIIB3xI')
 
@@ -51,6 +52,13 @@ def unpack(blob):
         raise ValueError('ICB2 container truncated: header says %d stream bytes, %d present' % (n, len(blob) - _HEADER.size))
     if not (0 <= first_sym < L) or C == 0 or H == 0 or W == 0:
         raise ValueError('ICB2 container: inconsistent header')
+    # sanity bounds BEFORE anything is allocated from header fields: image side <= 65536, and a range-coded stream of
+    # C*h*w symbols from L <= 8 centres cannot exceed ~4 bytes per symbol
+    if H > MAX_SIDE or W > MAX_SIDE or C > 1024:
+        raise ValueError('ICB2 container: implausible size %dx%d, C=%d' % (H, W, C))
+    hp, wp = padded_size(H, W)
+    if n > 4 * C * (hp // 8) * (wp // 8) + 64:
+        raise ValueError('ICB2 container: %d stream bytes for %d symbols' % (n, C * (hp // 8) * (wp // 8)))
     return {'stream': blob[_HEADER.size:], 'first_sym': first_sym, 'C': C, 'L': L, 'H': H, 'W': W}
 
 
@@ -66,15 +74,38 @@ def _as_hwc(im):
 
 
 def _encode_one(freqs, symbols):
+    """one image: uint32 tables (C*h*w, L) + uint8 symbols (C*h*w,) (views into pinned staging memory) -> stream bytes"""
     from . import arithmetic_coding as ac
     enc = ac.ArithmeticEncoder()
     L = freqs.shape[-1]
-    enc.write(freqs.reshape(-1, L)[1:], symbols.reshape(-1)[1:])      # first symbol is side information
+    enc.write_u32(freqs.reshape(-1, L)[1:], symbols.reshape(-1)[1:])      # first symbol is side information
     return enc.finish()[0]
 
 
+class _Staging(object):
+    """One of the two pinned host buffers of the compress pipeline (tables as uint32 + symbols as uint8) and the event
+    that says its device-to-host copies have landed."""
+
+    def __init__(self):
+        self.freqs = self.sym = self.event = None
+
+    def fit(self, n_freq, n_sym):
+        import torch
+        if self.freqs is None or self.freqs.numel() < n_freq:
+            self.freqs = torch.empty(n_freq, dtype=torch.int32).pin_memory()
+        if self.sym is None or self.sym.numel() < n_sym:
+            self.sym = torch.empty(n_sym, dtype=torch.uint8).pin_memory()
+        if self.event is None:
+            self.event = torch.cuda.Event()
+
+
 def compress(images, ae, pc, batch_size=8, threads=8):
-    """images: list of uint8 HWC (or CHW) arrays of any sizes -> list of container bytes."""
+    """images: list of uint8 HWC (or CHW) arrays of any sizes -> list of container bytes.
+
+    Pipeline: for every batch the GPU side -- autoencoder.encode, the codec tables of the whole latent
+    in one pass (uint32), asynchronous copies of tables + uint8 symbols into one of TWO pinned staging buffers -- is
+    enqueued without a single host synchronisation; the host range coder (one thread per image, the GIL is released
+    inside the C call) then works on batch i while the device already computes batch i+1."""
     import torch
     from .val import add_padding
     f = ae.get_subsampling_factor()
@@ -83,21 +114,42 @@ def compress(images, ae, pc, batch_size=8, threads=8):
     by_shape = {}
     for i, p in enumerate(padded):
         by_shape.setdefault(p.shape, []).append(i)
+    chunks = [idxs[s:s + batch_size] for idxs in by_shape.values() for s in range(0, len(idxs), batch_size)]
     out = [None] * len(images)
-    centers = ae.centers_tensor()
+    centers_host = ae.centers_host()
+    stage = [_Staging(), _Staging()]
+    L = pc.L
+
+    def enqueue(k, chunk):
+        x = torch.from_numpy(np.stack([padded[i] for i in chunk])).pin_memory().cuda(non_blocking=True)
+        enc = ae.encode(x, is_training=False)
+        sym8 = ae.extra['symbols_u8']
+        tables = pc.codec_freqs_u32(enc.symbols, centers_host)
+        st = stage[k & 1]
+        st.fit(tables.numel(), sym8.numel())
+        st.freqs[:tables.numel()].copy_(tables.view(-1), non_blocking=True)
+        st.sym[:sym8.numel()].copy_(sym8.view(-1), non_blocking=True)
+        st.event.record()
+        return st, tuple(enc.symbols.shape)
+
+    def finish(pool, chunk, st, shape):
+        st.event.synchronize()
+        N, C, h, w = shape
+        fr = st.freqs[:N * C * h * w * L].numpy().view(np.uint32).reshape(N, C * h * w, L)
+        sy = st.sym[:N * C * h * w].numpy().reshape(N, C * h * w)
+        streams = list(pool.map(_encode_one, fr, sy))
+        for k, i in enumerate(chunk):
+            out[i] = pack(streams[k], int(sy[k, 0]), C, L, hwc[i].shape[0], hwc[i].shape[1])
+
     with ThreadPoolExecutor(max_workers=max(1, threads)) as pool:
-        for shape, idxs in by_shape.items():
-            for s in range(0, len(idxs), batch_size):
-                chunk = idxs[s:s + batch_size]
-                x = torch.from_numpy(np.stack([padded[i] for i in chunk])).cuda()
-                sym = ae.encode(x, is_training=False).symbols
-                freqs, _ = pc.freqs(sym, centers, codec=True)
-                freqs, sym = freqs.cpu().numpy(), sym.cpu().numpy()
-                # the host coder releases the GIL (ctypes): one image per thread
-                streams = list(pool.map(_encode_one, freqs, sym))
-                for k, i in enumerate(chunk):
-                    out[i] = pack(streams[k], int(sym[k].reshape(-1)[0]), sym.shape[1], freqs.shape[-1],
-                                  hwc[i].shape[0], hwc[i].shape[1])
+        pending = None
+        for k, chunk in enumerate(chunks):
+            cur = (chunk,) + enqueue(k, chunk)        # device work of batch k is in flight ...
+            if pending is not None:
+                finish(pool, *pending)                # ... while the host codes batch k-1
+            pending = cur
+        if pending is not None:
+            finish(pool, *pending)
     return out
 
 
@@ -135,7 +187,8 @@ def _models(args):
     from . import autoencoder, config, probclass, weights
     a, p = config.ae_config(args.ae_config), config.pc_config(args.pc_config)
     if args.weights:
-        W = dict(np.load(args.weights))
+        from . import tf_checkpoint
+        W = tf_checkpoint.load_weights(args.weights)          # .npz or a TensorFlow checkpoint prefix / directory
     else:
         W = weights.synthetic_weights(a.num_chan_bn, a.num_centers, p.arch_param__k, a.arch_param_B)
     ae = autoencoder.get_network_cls(a)(a, weights=W, mode=args.mode)

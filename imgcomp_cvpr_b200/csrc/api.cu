@@ -99,6 +99,8 @@ struct DevLayer {
     // divided by the power-of-two weight pre-scale
     __half* w_tc = nullptr;
     __half* w_tc_pair = nullptr;   // pair-packed copy for the cta_group::2 kernel (IC_CONV_PAIR=1)
+    __half* w_tc_cat = nullptr;    // B-concatenated copy for conv_cat_kernel (EXACT mode; IC_CONV_CAT=0 disables, =2: CTA pairs)
+    __half* w_tc_cat_pair = nullptr;
     float* scale_tc = nullptr;
     tc::GroupTable gt;
     int nout_tc = 0;
@@ -272,6 +274,17 @@ static int ae_build(ic_ae* ae, const ic_ae_config* cfg, const float* const* h_te
                         IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc_pair, pp.size() * sizeof(__half)));
                         IC_CHECK_CUDA(cudaMemcpy(d.w_tc_pair, pp.data(), pp.size() * sizeof(__half), cudaMemcpyHostToDevice));
                     }
+                    // opt-in (IC_CONV_CAT=1: one CTA, =2: CTA pairs): measured slower than conv_tc_kernel on B200 because the
+                    // single-buffered accumulators expose the epilogue (profiles/r2_summary.md)
+                    const int cat_mode = getenv("IC_CONV_CAT") ? atoi(getenv("IC_CONV_CAT")) : 0;
+                    if (d.nout_tc == 128 && cat_mode) {
+                        std::vector<__half> pc_;
+                        if (cat_mode == 2) tc::repack_cat_pair(packed, d.gt.nstages, pc_);
+                        else tc::repack_cat(packed, d.gt.nstages, pc_);
+                        __half** dst = cat_mode == 2 ? &d.w_tc_cat_pair : &d.w_tc_cat;
+                        IC_CHECK_CUDA(cudaMalloc((void**)dst, pc_.size() * sizeof(__half)));
+                        IC_CHECK_CUDA(cudaMemcpy(*dst, pc_.data(), pc_.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                    }
                     rc = upload(sct, &d.scale_tc);
                     if (rc == IC_OK) {       // padded shift for the tensor-core epilogue
                         cudaFree(d.shift);
@@ -321,6 +334,8 @@ void ic_ae_destroy(ic_ae_t* ae) {
             cudaFree(l.shift);
             cudaFree(l.w_tc);
             cudaFree(l.w_tc_pair);
+            cudaFree(l.w_tc_cat);
+            cudaFree(l.w_tc_cat_pair);
             cudaFree(l.w_tc_b);
             cudaFree(l.scale_tc);
         }
@@ -434,6 +449,8 @@ int conv_tc_layer(const DevLayer& L, const __half* in, int in_chunks, int Hin, i
     a.Win = Win;
     a.weights = L.w_tc;
     a.weights_pair = L.w_tc_pair;
+    a.weights_cat = L.w_tc_cat;
+    a.weights_cat_pair = L.w_tc_cat_pair;
     a.groups = &L.gt;
     a.scale = L.scale_tc;
     a.shift = L.shift;
@@ -883,6 +900,21 @@ int ic_pc_codec_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const flo
     IC_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, d_freqs, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream,
                       /*canonical=*/true);
+}
+
+int ic_pc_codec_freqs_u32_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* h_centers, int N, int C, int h, int w,
+                              uint32_t* d_freqs, double* d_bits_sum, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(pc && d_symbols && h_centers && d_freqs && d_workspace, IC_ERR_INVALID, "ic_pc_codec_freqs_u32_fwd: NULL argument");
+    IC_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0, IC_ERR_INVALID, "ic_pc_codec_freqs_u32_fwd: bad shape");
+    PcInput in;
+    memset(&in, 0, sizeof(in));
+    in.N = N; in.D = C; in.H = h; in.W = w;
+    in.pad_d = 4; in.pad_hw = 4;
+    in.symbols = d_symbols;
+    in.target_symbols = d_symbols;
+    for (int i = 0; i < pc->cfg.num_centers; ++i) in.centers_host[i] = h_centers[i];     // host copy: nothing to wait for
+    return pc_forward(pc->w, in, PC_HEAD_FREQS, nullptr, nullptr, d_bits_sum, d_workspace, workspace_bytes, (cudaStream_t)stream,
+                      /*canonical=*/true, d_freqs);
 }
 
 size_t ic_pc_decode_workspace_bytes(const ic_pc_t* pc, int N, int C, int h, int w) {

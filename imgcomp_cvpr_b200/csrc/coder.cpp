@@ -164,6 +164,34 @@ int ic_ac_enc_write(ic_ac_enc_t* e, const int64_t* h_freqs, int L, const int64_t
     return IC_OK;
 }
 
+int ic_ac_enc_write_u32(ic_ac_enc_t* e, const uint32_t* h_freqs, int L, const uint8_t* h_symbols, int64_t n) {
+    if (!e || !h_freqs || !h_symbols || L <= 0 || n < 0) {
+        ic::set_error("ic_ac_enc_write_u32: bad argument");
+        return IC_ERR_INVALID;
+    }
+    if (e->finished) {
+        ic::set_error("ic_ac_enc_write_u32: encoder already finished");
+        return IC_ERR_STATE;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t* f = h_freqs + i * L;
+        const int sym = h_symbols[i];
+        uint64_t c = 0, lo = 0, hi = 0;
+        for (int j = 0; j < L; ++j) {
+            if (j == sym) lo = c;
+            c += f[j];
+            if (j == sym) hi = c;
+        }
+        if (sym >= L || c > kMaxTotal || hi <= lo) {
+            ic::set_error("ic_ac_enc_write_u32: symbol %d of entry %lld not codable (zero frequency, out of range, or total > 2^30+2)",
+                          sym, (long long)i);
+            return IC_ERR_INVALID;
+        }
+        e->update(lo, hi, c);
+    }
+    return IC_OK;
+}
+
 int ic_ac_enc_finish(ic_ac_enc_t* e, const uint8_t** h_bytes, int64_t* n_bytes, int64_t* n_bits) {
     if (!e || !h_bytes || !n_bytes || !n_bits) return IC_ERR_INVALID;
     if (!e->finished) {

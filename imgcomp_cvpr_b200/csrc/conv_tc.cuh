@@ -56,6 +56,8 @@ struct ConvTcArgs {
     int Nimg, in_chunks, Hin, Win;
     const __half* weights;
     const __half* weights_pair;   // pair-packed copy (cta_group::2 path) or nullptr
+    const __half* weights_cat;    // B-concatenated copy (conv_cat_kernel) or nullptr
+    const __half* weights_cat_pair;   // B-concatenated, pair-packed copy (conv_cat_kernel<PAIR>) or nullptr
     const GroupTable* groups;
     const float *scale, *shift;
     const __half *res1, *res2;
@@ -89,6 +91,8 @@ int pack_weights_tconv(const float* w, int k, int cin, int cout, const int* phas
                        std::vector<__half>& packed, GroupTable& gt, float* inv_scale_out);
 int launch_split_from_nchw(const float* in, int N, int C, int H, int W, __half* out, int write_lo, cudaStream_t s);
 void repack_pair(const std::vector<__half>& packed, int nstages, std::vector<__half>& out);
+void repack_cat(const std::vector<__half>& packed, int nstages, std::vector<__half>& out);
+void repack_cat_pair(const std::vector<__half>& packed, int nstages, std::vector<__half>& out);
 int pack_weights_h1(const float* w_hwio, int cin, int cout, int nout, std::vector<__half>& packed, GroupTable& gt,
                     float* inv_scale_out);
 int pack_weights_pc(const float* w, int ci, int co, int nout, std::vector<__half>& packed, GroupTable& gt,

@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(128) pc_final_kernel(const float* __restrict__
                                                        const float* __restrict__ bias, int L,
                                                        const int64_t* __restrict__ symbols,   // N,Do,Ho,Wo
                                                        int64_t total, float* __restrict__ out_f,
-                                                       int64_t* __restrict__ out_freqs, double* __restrict__ bits_sum) {
+                                                       int64_t* __restrict__ out_freqs, double* __restrict__ bits_sum,
+                                                       uint32_t* __restrict__ out_freqs32 = nullptr) {
     extern __shared__ float swf[];      // 14*KC*L + L
     const int nw = 14 * KC * L;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) swf[i] = wgt[i];
@@ -272,7 +273,9 @@ __global__ void __launch_bounds__(128) pc_final_kernel(const float* __restrict__
                     if (l < L) {
                         float pr = __fdiv_rn(e[l], s);
                         long long f = (long long)__fmul_rn(pr, 1e9f);
-                        out_freqs[v * L + l] = f < 1 ? 1 : f;
+                        f = f < 1 ? 1 : f;
+                        if (out_freqs32) out_freqs32[v * L + l] = (uint32_t)f;        // <= 1e9 < 2^30: fits
+                        else out_freqs[v * L + l] = f;
                     }
             }
         }
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(128) pc_final_kernel(const float* __restrict__
 
 template <int KC>
 int run_pc(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs, double* bits_sum,
-           void* ws, size_t ws_bytes, cudaStream_t s) {
+           void* ws, size_t ws_bytes, cudaStream_t s, uint32_t* out_freqs32 = nullptr) {
     const int N = in.N, D = in.D, H = in.H, W = in.W, pd = in.pad_d, ph = in.pad_hw, L = w.L;
     const int Dp = D + pd, Hp = H + 2 * ph, Wp = W + 2 * ph;
     IC_REQUIRE(Dp >= 5 && Hp >= 9 && Wp >= 9, IC_ERR_INVALID, "probclass: volume %dx%dx%d smaller than the 5x9x9 context",
@@ -337,7 +340,8 @@ int run_pc(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_
     else if (head == HEAD_BITCOST)
         pc_final_kernel<KC, HEAD_BITCOST><<<cdiv(t3, 128), 128, smem, s>>>(a2, D2, H2, W2, w.w3, w.b3, L, in.target_symbols, t3, out_f, nullptr, bits_sum);
     else
-        pc_final_kernel<KC, HEAD_FREQS><<<cdiv(t3, 128), 128, smem, s>>>(a2, D2, H2, W2, w.w3, w.b3, L, in.target_symbols, t3, nullptr, out_freqs, bits_sum);
+        pc_final_kernel<KC, HEAD_FREQS><<<cdiv(t3, 128), 128, smem, s>>>(a2, D2, H2, W2, w.w3, w.b3, L, in.target_symbols, t3, nullptr, out_freqs, bits_sum,
+                                                                         out_freqs32);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -454,10 +458,11 @@ size_t pc_workspace_bytes(int KC, int N, int D, int H, int W, int pad_d, int pad
 }
 
 int pc_forward(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs,
-               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s, bool canonical) {
+               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s, bool canonical, uint32_t* out_freqs32) {
+    IC_REQUIRE(!out_freqs32 || canonical, IC_ERR_INVALID, "probclass: 32-bit tables are the codec (float32 chain) tables");
     if (w.K == 24 && w.tc && !canonical) return run_pc_tc(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
-    if (w.K == 24) return run_pc<24>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
-    if (w.K == 64) return run_pc<64>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s);
+    if (w.K == 24) return run_pc<24>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s, out_freqs32);
+    if (w.K == 64) return run_pc<64>(w, in, head, out_f, out_freqs, bits_sum, ws, ws_bytes, s, out_freqs32);
     set_error("probclass: arch_param__k = %d not built (24 and 64 are)", w.K);
     return IC_ERR_UNSUPPORTED;
 }

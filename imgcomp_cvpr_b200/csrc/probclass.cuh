@@ -35,8 +35,10 @@ enum { PC_HEAD_LOGITS = 0, PC_HEAD_BITCOST = 1, PC_HEAD_FREQS = 2 };
 size_t pc_workspace_bytes(int KC, int N, int D, int H, int W, int pad_d, int pad_hw);
 // canonical = true: always the float32 FFMA kernels, whose per-output fmaf chain the sequential
 // decoder (pc_decode.cu) reproduces bit for bit
+// out_freqs32 (canonical only): write the tables as uint32 instead of int64 (every entry is <= 1e9)
 int pc_forward(const PcWeights& w, const PcInput& in, int head, float* out_f, int64_t* out_freqs,
-               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s, bool canonical = false);
+               double* bits_sum, void* ws, size_t ws_bytes, cudaStream_t s, bool canonical = false,
+               uint32_t* out_freqs32 = nullptr);
 
 // sequential decode of N bitstreams (pc_decode.cu); all pointers are device pointers
 struct PcDecodeInput {

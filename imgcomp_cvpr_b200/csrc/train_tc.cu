@@ -177,13 +177,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // the whole warp walks the loop, one elected lane issues: warp-uniform control flow keeps the descriptors in uniform
+        // registers (see the MMA issuer of conv_tc.cu)
+        {
             constexpr uint32_t kXSbo = WG_ROWS * (WG_COLS + 2) * 16, kYSbo = WG_ROWS * WG_COLS * 16, kLbo = 128;
             for (int it = 0; it < my_tiles; ++it) {
                 const uint32_t slot = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
                 mbar_wait(smem_u32(&bars->full[slot]), ph);
                 tc_fence_after();
                 const uint32_t xs = smem_u32(smem + slot * WG_STAGE_BYTES), ys = xs + 2 * WG_X_PLANE;
+                if (elect_one()) {
 #pragma unroll
                 for (int r = 0; r < WG_ROWS; ++r) {
                     const uint64_t b_hi = make_desc(ys + r * WG_COLS * 16, kLbo, kYSbo);
@@ -200,8 +203,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     }
                 }
                 umma_commit(smem_u32(&bars->empty[slot]));
+                if (it == my_tiles - 1) umma_commit(smem_u32(&bars->acc_full));
+                }
+                __syncwarp();
             }
-            if (my_tiles > 0) umma_commit(smem_u32(&bars->acc_full));
         }
     } else {
         // epilogue: TMEM lane = cin row, columns = (kx, cout)

@@ -178,6 +178,22 @@ class _Network3D(object):
                       _lib.ptr(sums), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         return out, sums
 
+    def codec_freqs_u32(self, symbols, centers_host, out=None):
+        """The tables of a real bitstream (freqs(codec=True)) as uint32, enqueued without any host synchronisation:
+        centers_host is a HOST array (L floats).  symbols NCHW int64 CUDA -> N,C,h,w,L uint32 CUDA (`out` if given)."""
+        self._need_handle()
+        sym = symbols.contiguous().to(torch.int64)
+        N, C, h, w = sym.shape
+        if out is None:
+            out = torch.empty((N, C, h, w, self.L), dtype=torch.int32, device=sym.device)
+        assert out.is_cuda and out.numel() == sym.numel() * self.L and out.element_size() == 4
+        ch = np.ascontiguousarray(np.asarray(centers_host, np.float32))
+        assert ch.size == self.L
+        ws = self._workspace(N, C, h, w)
+        _lib.check(_lib.lib().ic_pc_codec_freqs_u32_fwd(self._handle, _lib.ptr(sym), ch.ctypes.data, N, C, h, w, _lib.ptr(out),
+                                                        None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return out
+
     def decode_streams(self, streams, first_syms, shape, centers, force_symbols=None, return_freqs=False):
         """The decoder half of --real_bpp (code/bit_counter.py:137-163), for N images at once:
         streams = list of N byte strings written by ArithmeticEncoder over freqs(codec=True) tables,

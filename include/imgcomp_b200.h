@@ -167,6 +167,13 @@ int ic_pc_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_
 int ic_pc_codec_freqs_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* d_centers,
                           int N, int C, int h, int w, int64_t* d_freqs, double* d_bits_sum,
                           void* d_workspace, size_t workspace_bytes, void* stream);
+/* The same codec tables as 32-bit words (every entry is <= 1e9 < 2^30, code/probclass.py:443-444,473): half the bytes
+ * that cross PCIe per image (4.7 MB instead of 9.4 MB for a Kodak latent).  Takes the centres as a HOST array
+ * (L floats), so the call neither reads back nor synchronises: a compress pipeline can enqueue the next batch while
+ * host threads code the previous one (code/bit_counter.py:103-134 is the loop this feeds). */
+int ic_pc_codec_freqs_u32_fwd(const ic_pc_t* pc, const int64_t* d_symbols, const float* h_centers,
+                              int N, int C, int h, int w, uint32_t* d_freqs, double* d_bits_sum,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
 size_t ic_pc_decode_workspace_bytes(const ic_pc_t* pc, int N, int C, int h, int w);
 int ic_pc_decode_fwd(const ic_pc_t* pc, const uint8_t* d_stream, const int64_t* d_stream_offsets,
                      const int32_t* d_first_sym, const float* d_centers, int N, int C, int h, int w,
@@ -361,6 +368,8 @@ int ic_ac_enc_create(ic_ac_enc_t** out);
 int ic_ac_enc_write(ic_ac_enc_t* e, const int64_t* h_freqs, int L, const int64_t* h_symbols, int64_t n);
 /* finish(): flushes like ArithmeticEncoder.finish + BitOutputStream.close; returns the byte
  * stream (owned by the encoder until destroy) and the exact bit count before byte padding. */
+/* the same over 32-bit tables and 8-bit symbols (what ic_pc_codec_freqs_u32_fwd / ic_encode_fwd's uint8 symbols give) */
+int ic_ac_enc_write_u32(ic_ac_enc_t* e, const uint32_t* h_freqs, int L, const uint8_t* h_symbols, int64_t n);
 int ic_ac_enc_finish(ic_ac_enc_t* e, const uint8_t** h_bytes, int64_t* n_bytes, int64_t* n_bits);
 void ic_ac_enc_destroy(ic_ac_enc_t* e);
 int ic_ac_dec_create(const uint8_t* h_bytes, int64_t n_bytes, ic_ac_dec_t** out);

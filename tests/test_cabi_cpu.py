@@ -179,3 +179,20 @@ def test_library_sass_has_tcgen05_and_tma_and_no_legacy_mma():
     for k in conv + wgrad:
         assert {'UTCHMMA', 'LDTM', 'UTMALDG'} <= per_kernel[k], (k, per_kernel[k])
     assert not [k for k, v in per_kernel.items() if 'HMMA' in v]
+
+
+def test_coder_u32_tables_give_the_same_stream():
+    """ic_ac_enc_write_u32 (uint32 tables + uint8 symbols: what the compress pipeline stages in pinned memory) codes
+    exactly what ic_ac_enc_write codes from int64 tables, including the golden bitstream of the reference's coder"""
+    from imgcomp_cvpr_b200 import arithmetic_coding as ac
+    g = load_golden('tiny_low_1x64x64')
+    syms = g['symbols'].reshape(-1).astype(np.int64)
+    freqs = g['freqs'].reshape(-1, 6)
+    enc = ac.ArithmeticEncoder()
+    enc.write_u32(np.ascontiguousarray(freqs[1:].astype(np.uint32)), np.ascontiguousarray(syms[1:].astype(np.uint8)))
+    stream, nbits = enc.finish()
+    assert np.array_equal(np.frombuffer(stream, np.uint8), g['bitstream']) and (nbits + 7) // 8 * 8 == int(g['real_bits'])
+    bad = freqs[1:3].astype(np.uint32).copy()
+    bad[0, int(syms[1])] = 0
+    with pytest.raises(ValueError):
+        ac.ArithmeticEncoder().write_u32(bad, np.ascontiguousarray(syms[1:3].astype(np.uint8)))

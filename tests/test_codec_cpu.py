@@ -42,3 +42,15 @@ def test_padding_offsets_match_add_padding():
         t, l = (Hp - H) // 2, (Wp - W) // 2
         assert np.array_equal(p[t:t + H, l:l + W], im)
         assert np.array_equal(undo(p), im)
+
+
+def test_header_fields_are_bounded_before_anything_is_allocated():
+    """H / W / stream length come from an untrusted blob: implausible values are rejected in unpack()"""
+    import struct
+    with pytest.raises(ValueError):
+        codec.unpack(codec.pack(b'\0' * 8, first_sym=0, C=32, L=6, H=1 << 20, W=64))          # side > 65536
+    with pytest.raises(ValueError):
+        codec.unpack(codec.pack(b'\0' * 8, first_sym=0, C=2000, L=6, H=64, W=64))             # channels
+    with pytest.raises(ValueError):
+        codec.unpack(codec.pack(b'\0' * (4 * 32 * 8 * 8 + 65), first_sym=0, C=32, L=6, H=64, W=64))   # > 4 bytes / symbol
+    assert codec.unpack(codec.pack(b'\0' * (4 * 32 * 8 * 8 + 64), first_sym=0, C=32, L=6, H=64, W=64))['C'] == 32

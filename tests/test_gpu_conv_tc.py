@@ -60,6 +60,43 @@ def test_layer_against_float64(gpu_models):
     assert e_fast < 1e-2
 
 
+def test_accumulate_gain_against_float64(synth, monkeypatch):
+    """The epilogue multiplies the main (hi*hi) accumulator by 1 + 1.606e-8 * accumulate steps to undo the MEAN of the
+    tensor core's round-toward-zero fp32 accumulate (conv_tc.cu: launch_cat; IC_TC_ACC_GAIN=0 switches it off).  The
+    correction is exact in the mean when the running sum keeps the sign of the final sum and over-corrects by at most its
+    own size (1.2e-6 relative for a 3x3 layer) when it does not.  Measured against float64 on a layer without ReLU (the
+    accumulator can be backed out of the output) for sign-mixed inputs (randn x 20), one-sided inputs (ReLU'd) and a
+    large-offset input: the signed mean error must shrink and the mean magnitude may not grow by more than 1e-6."""
+    from imgcomp_cvpr_b200 import autoencoder
+    a, p, W = synth('cvpr/low')
+    scope = 'autoencoder/encoder/res_block_enc_0/enc_0_1/conv2'         # layer index 1: activation_fn=None
+    w = torch.from_numpy(W[scope + '/weights']).double().cuda().permute(3, 2, 0, 1)
+    bn = {k: torch.from_numpy(W[scope + '/BatchNorm/' + k]).double().cuda() for k in ('gamma', 'beta', 'moving_mean', 'moving_variance')}
+    sc = bn['gamma'] / torch.sqrt(bn['moving_variance'] + 1e-5)
+    g = torch.Generator(device='cuda').manual_seed(11)
+    inputs = {'mixed': torch.randn((1, 64, 64, 128), device='cuda', generator=g) * 20,
+              'relu': torch.relu(torch.randn((1, 64, 64, 128), device='cuda', generator=g)) * 1.5,
+              'offset': torch.randn((1, 64, 64, 128), device='cuda', generator=g) * 2 + 30}
+    res = {}
+    for gain in ('1', '0'):
+        monkeypatch.setenv('IC_TC_ACC_GAIN', gain)
+        ae = autoencoder.get_network_cls(a)(a, weights=W, mode='exact')
+        for name, x in inputs.items():
+            pre = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+            out = _conv(ae, 0, 1, x, None, None, 'exact').double()
+            acc = (out - bn['beta']) / sc + bn['moving_mean']
+            m = pre.abs() > 0.2 * pre.pow(2).mean().sqrt()
+            rel = ((acc - pre) / pre)[m]
+            res[(name, gain)] = (rel.mean().item(), rel.abs().mean().item())
+        del ae
+    for name in inputs:
+        on, off = res[(name, '1')], res[(name, '0')]
+        print('%-6s exact vs float64, (mean signed rel err, mean |rel err|): compensation on (%.2e, %.2e)  off (%.2e, %.2e)' % (
+            (name,) + on + off))
+        assert abs(on[0]) <= abs(off[0]) + 2e-7, name
+        assert on[1] <= off[1] + 1e-6, name
+
+
 @pytest.mark.parametrize('name,ae_name', [('cfg1_low_1x128x128', 'cvpr/low'), ('ragged_low_2x48x72', 'cvpr/low'),
                                           ('tiny_hi_1x40x24', 'cvpr/hi')])
 def test_fast_mode_flip_rate_is_reported(name, ae_name, gpu_models):

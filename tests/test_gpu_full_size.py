@@ -81,8 +81,11 @@ def test_full_size_val_graph_against_oracle(name, mode, gpu_models):
     print('   bpp %.6f oracle %.6f   ' % (bpp, ref['bpp'][0]))
     assert abs(bpp - ref['bpp'][0]) < 1e-4                                            # north star: 1e-4
     assert abs(pc.last_bits_per_image[0].item() / (x.shape[2] * x.shape[3]) - ref['bpp'][0]) < 1e-4
-    same = ~mism
-    np.testing.assert_allclose(bc.cpu().numpy()[same], ref['bitcost'][same], atol=2e-3)
+    # a flipped symbol changes the context of every position whose 5x9x9 causal window contains it: compare the rest
+    near = np.zeros_like(mism)
+    for n, c, y, x_ in np.argwhere(mism):
+        near[n, c:c + 5, max(y - 4, 0):y + 5, max(x_ - 4, 0):x_ + 5] = True
+    np.testing.assert_allclose(bc.cpu().numpy()[~near], ref['bitcost'][~near], atol=2e-3)
     ms = ms_ssim_np.MultiScaleSSIM_batch(xc, ae.extra['x_out_u8'], data_format='NCHW').cpu().numpy()
     print('   ms-ssim %.6f oracle %.6f' % (ms[0], ref['ms_ssim'][0]))
     np.testing.assert_allclose(ms, ref['ms_ssim'], atol=1e-4)                      # north star: 1e-4
