@@ -161,6 +161,69 @@ __global__ void heatmap_quantize_kernel(const float* __restrict__ bn, int h, int
     if (sym8_out) sym8_out[i] = (uint8_t)sym;
 }
 
+// The same, tiled for the memory system: a block stages the to_bn rows of 64 consecutive latent pixels (64 x CB floats,
+// contiguous in the NHWC input: coalesced 16-byte loads) in shared memory, then every thread produces FOUR consecutive
+// pixels of one channel, so each NCHW output row is written as 16-byte (32-byte for the int64 symbols) stores, 256
+// contiguous bytes per channel and tile.  29 B written per symbol against ~2 B read: the kernel is write-bound.
+// Requires h*w % 4 == 0 (a quad may not straddle two images); arithmetic identical to heatmap_quantize_kernel.
+constexpr int kHqTile = 64;
+
+__global__ void __launch_bounds__(256) heatmap_quantize_tiled_kernel(
+    const float* __restrict__ bn, int64_t hw, int C, int heatmap, const float* __restrict__ centers, int L, int64_t npix,
+    float* __restrict__ z_out, float* __restrict__ hm_out, float* __restrict__ qbar_out, float* __restrict__ qhard_out,
+    int64_t* __restrict__ sym_out, uint8_t* __restrict__ sym8_out, float* __restrict__ qsoft_out, int CB) {
+    extern __shared__ __align__(16) float tile[];          // [kHqTile][CB + 1] (odd pitch: conflict-free column reads)
+    __shared__ float sc[kMaxL];
+    __shared__ float s_hm2d[kHqTile];
+    if (threadIdx.x < L) sc[threadIdx.x] = centers[threadIdx.x];
+    const int64_t p0 = (int64_t)blockIdx.x * kHqTile;
+    const int np = (int)min((int64_t)kHqTile, npix - p0);
+    const int pitch = CB | 1;
+    const float* src = bn + p0 * CB;
+    for (int i = threadIdx.x; i < np * CB; i += blockDim.x) tile[(i / CB) * pitch + i % CB] = src[i];
+    __syncthreads();
+    if (heatmap && threadIdx.x < np) {
+        // tf.nn.sigmoid(x) * C   (code/autoencoder.py:183-186)
+        const float sg = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-tile[threadIdx.x * pitch])));
+        s_hm2d[threadIdx.x] = __fmul_rn(sg, (float)C);
+    }
+    __syncthreads();
+    const int quads = kHqTile / 4;
+    for (int item = threadIdx.x; item < C * quads; item += blockDim.x) {
+        const int c = item / quads, qd = item - c * quads;
+        const int px = qd * 4;
+        if (px >= np) continue;
+        const int64_t p = p0 + px;                  // first pixel of the quad; hw % 4 == 0: all four in one image
+        const int64_t n = p / hw, r = p - n * hw;
+        const int64_t o = (n * C + c) * hw + r;
+        float z[4], hm[4], qs[4], qh[4], qb[4];
+        int sy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float* px_row = tile + (px + k) * pitch;
+            hm[k] = 1.f;
+            if (heatmap) {
+                hm[k] = fmaxf(fminf(__fsub_rn(s_hm2d[px + k], (float)c), 1.f), 0.f);    // heatmap3D = max(min(hm2D - c, 1), 0)
+                z[k] = __fmul_rn(hm[k], px_row[1 + c]);
+            } else {
+                z[k] = px_row[c];
+            }
+            quantize_one<kMaxL>(z[k], sc, L, 1.f, qs[k], qh[k], sy[k]);
+            qb[k] = __fadd_rn(qs[k], __fsub_rn(qh[k], qs[k]));            // qbar (code/autoencoder.py:133)
+        }
+        if (z_out) *reinterpret_cast<float4*>(z_out + o) = make_float4(z[0], z[1], z[2], z[3]);
+        if (hm_out) *reinterpret_cast<float4*>(hm_out + o) = make_float4(hm[0], hm[1], hm[2], hm[3]);
+        if (qsoft_out) *reinterpret_cast<float4*>(qsoft_out + o) = make_float4(qs[0], qs[1], qs[2], qs[3]);
+        if (qhard_out) *reinterpret_cast<float4*>(qhard_out + o) = make_float4(qh[0], qh[1], qh[2], qh[3]);
+        if (qbar_out) *reinterpret_cast<float4*>(qbar_out + o) = make_float4(qb[0], qb[1], qb[2], qb[3]);
+        if (sym_out) {
+            *reinterpret_cast<longlong2*>(sym_out + o) = make_longlong2(sy[0], sy[1]);
+            *reinterpret_cast<longlong2*>(sym_out + o + 2) = make_longlong2(sy[2], sy[3]);
+        }
+        if (sym8_out) *reinterpret_cast<uchar4*>(sym8_out + o) = make_uchar4((uint8_t)sy[0], (uint8_t)sy[1], (uint8_t)sy[2], (uint8_t)sy[3]);
+    }
+}
+
 __global__ void quantize_kernel(const float* __restrict__ x, const float* __restrict__ centers, int L, float sigma,
                                 int64_t n, float* __restrict__ qsoft_out, float* __restrict__ qhard_out,
                                 int64_t* __restrict__ sym_out) {
@@ -218,6 +281,17 @@ int launch_heatmap_quantize(const float* bn_nhwc, int N, int h, int w, int C, in
     IC_REQUIRE(L <= kMaxL, IC_ERR_UNSUPPORTED, "num_centers %d > %d", L, kMaxL);
     int64_t total = (int64_t)N * C * h * w;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    const int CB = cb_stride > 0 ? cb_stride : (heatmap ? C + 1 : C);
+    const int64_t hw = (int64_t)h * w, npix = (int64_t)N * hw;
+    const size_t tile_bytes = (size_t)kHqTile * (CB | 1) * sizeof(float);
+    auto al = [](const void* q, size_t a) { return q == nullptr || ((uintptr_t)q & (a - 1)) == 0; };
+    if (hw % 4 == 0 && tile_bytes <= 40 * 1024 && al(z, 16) && al(hm, 16) && al(qbar, 16) && al(qhard, 16) && al(qsoft, 16) &&
+        al(sym, 16) && al(sym8, 4)) {
+        heatmap_quantize_tiled_kernel<<<cdiv(npix, kHqTile), 256, tile_bytes, s>>>(bn_nhwc, hw, C, heatmap, centers, L, npix, z, hm, qbar,
+                                                                                  qhard, sym, sym8, qsoft, CB);
+        IC_CHECK_LAUNCH();
+        return IC_OK;
+    }
     heatmap_quantize_kernel<<<cdiv(total, 256), 256, 0, s>>>(bn_nhwc, h, w, C, heatmap, centers, L, total, z, hm,
                                                              qbar, qhard, sym, sym8, qsoft, cb_stride);
     IC_CHECK_LAUNCH();
