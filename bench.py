@@ -255,9 +255,12 @@ def measure_encode_pc(workload, mode, steps, warmup, world, rank, local, with_pa
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device='cuda')
     metric = torch.zeros(2, dtype=torch.float64, device='cuda')
     bits_host = torch.empty(N, dtype=torch.float64).pin_memory()
+    sym_host = torch.empty((N, C, H // 8, Wd // 8), dtype=torch.uint8).pin_memory()
+    last = {}
 
     def step(x):
         enc = ae.encode(x, is_training=False)
+        last['sym8'] = ae.extra['symbols_u8']
         pc.bitcost(enc.qbar, enc.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
         if world > 1:      # the final metric all-reduce of a sharded val run: [sum bits, sum pixels]
             metric[0] = pc.last_bits_per_image.sum()
@@ -316,7 +319,8 @@ def measure_encode_pc(workload, mode, steps, warmup, world, rank, local, with_pa
         t, n = _lib.c_double(), _lib.c_longlong()
         _lib.check(L.ic_profile_get(cls, t, n))
         prof[name] = (t.value, n.value)
-    # ---- end to end: pinned host uint8 -> H2D -> step -> D2H of the per-image bit sums
+    # ---- end to end: pinned host uint8 -> H2D -> step -> D2H of the per-image bit sums AND the symbols (uint8: what a
+    # codec-style consumer of the path needs on the host)
     # Double-buffered like a streaming val driver: the H2D copy of batch i+1 (copy stream) overlaps the compute of
     # batch i; every step still copies its own inputs from pinned host memory and reads its result back, all inside
     # the timed region.  (No explicit L2 flush here: each step touches > 2 GB of activations, far beyond the 126 MB L2.)
@@ -347,6 +351,7 @@ def measure_encode_pc(workload, mode, steps, warmup, world, rank, local, with_pa
             bits = step(dev_bufs[b])
             consumed[b].record(main_s)
             bits_host.copy_(bits, non_blocking=True)
+            sym_host.copy_(last['sym8'], non_blocking=True)
     e2e_run(2)
     barrier()
     a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -378,7 +383,8 @@ def measure_encode_pc(workload, mode, steps, warmup, world, rank, local, with_pa
                    'H': H, 'W': Wd, 'mode': mode, 'parallelism': 'batch-shard x%d' % world,
                    'l2': 'flushed between timed iterations (%d MiB write)' % (L2_FLUSH_BYTES >> 20)},
         'e2e': {'value': world * pix / (ms_e2e * 1e-3) / 1e6, 'unit': 'MPix/s', 'h2d_bytes_per_step': int(x_host.numel()),
-                'd2h_bytes_per_step': int(bits_host.numel() * 8), 'ms_per_step': ms_e2e},
+                'd2h_bytes_per_step': int(bits_host.numel() * 8 + sym_host.numel()), 'ms_per_step': ms_e2e,
+                'd2h': 'per-image bit sums (float64) + symbols (uint8)'},
         'gpu_launches': int(launches), 'clocks': clocks,
         'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_128x128 (%s)' % mode, 'achieved': achieved,
                      'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,

@@ -73,6 +73,10 @@ SIGNATURES = {
     'ic_nn_conv2d_bwd_filter': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_conv3x3_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'ic_nn_conv3x3_tc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_conv3x3_tc_ex': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
+    'ic_nn_conv3x3_tc_bwd_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
     'ic_nn_conv3x3_tc_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'ic_nn_conv3x3_tc_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_bn_workspace_bytes': (c_size_t, [c_int64, c_int]),
@@ -117,6 +121,7 @@ SIGNATURES = {
     'ic_profile_enable': (None, [c_int]),
     'ic_profile_reset': (None, []),
     'ic_profile_get': (c_int, [c_int, POINTER(c_double), POINTER(c_longlong)]),
+    'ic_crc32c': (ctypes.c_uint32, [c_void_p, c_int64]),
     'ic_ac_enc_create': (c_int, [POINTER(c_void_p)]),
     'ic_ac_enc_write': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64]),
     'ic_ac_enc_write_u32': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64]),

@@ -99,6 +99,8 @@ struct DevLayer {
     // divided by the power-of-two weight pre-scale
     __half* w_tc = nullptr;
     __half* w_tc_pair = nullptr;   // pair-packed copy for the cta_group::2 kernel (IC_CONV_PAIR=1)
+    __half* w_h1 = nullptr;        // h1 only: im2col-packed weights of the dedicated kernel (conv_h1.cu)
+    float* scale_h1 = nullptr;
     __half* w_tc_cat = nullptr;    // B-concatenated copy for conv_cat_kernel (EXACT mode; IC_CONV_CAT=0 disables, =2: CTA pairs)
     __half* w_tc_cat_pair = nullptr;
     float* scale_tc = nullptr;
@@ -254,6 +256,17 @@ static int ae_build(ic_ae* ae, const ic_ae_config* cfg, const float* const* h_te
                 }
             }
             const bool tc_h1 = l.k == 5 && l.stride == 2 && !l.transposed && l.cin == 3 && l.cout == 64;
+            if (rc == IC_OK && tc_h1) {
+                std::vector<__half> ph1;
+                float inv1 = 1.f;
+                if (tc::pack_weights_h1_im2col(w, l.cin, l.cout, ph1, &inv1) == IC_OK) {
+                    std::vector<float> s1(64, 0.f);
+                    for (int co = 0; co < l.cout; ++co) s1[co] = sc[co] * inv1;         // exact: inv1 is a power of two
+                    IC_CHECK_CUDA(cudaMalloc((void**)&d.w_h1, ph1.size() * sizeof(__half)));
+                    IC_CHECK_CUDA(cudaMemcpy(d.w_h1, ph1.data(), ph1.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                    rc = upload(s1, &d.scale_h1);
+                }
+            }
             if (rc == IC_OK && (tc_res || tc_s2 || tc_h1)) {
                 std::vector<__half> packed;
                 float inv = 1.f;
@@ -335,6 +348,8 @@ void ic_ae_destroy(ic_ae_t* ae) {
             cudaFree(l.w_tc);
             cudaFree(l.w_tc_pair);
             cudaFree(l.w_tc_cat);
+            cudaFree(l.w_h1);
+            cudaFree(l.scale_h1);
             cudaFree(l.w_tc_cat_pair);
             cudaFree(l.w_tc_b);
             cudaFree(l.scale_tc);
@@ -578,13 +593,23 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
         const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
         __half* hp[5];
         for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
-        // image -> normalised, space-to-depth hi/lo planes [pl][N][4][H/2][W/2][8]  (fits in `a1`)
-        __half* x2 = reinterpret_cast<__half*>(a1);
-        rc = launch_prep_input_s2d(d_x, x_is_u8, N, H, W, c.normalization, x2, exact, s);
-        if (rc != IC_OK) return rc;
-        // h1 on tensor cores, output (64 ch at H/2) written space-to-depth [pl][N][32][H/4][W/4][8] into pool[1..2]
-        rc = conv_tc_layer(L[0], x2, 4, H2, W2, hp[1], nullptr, nullptr, nullptr, N, H2, W2, exact, s, 1);
-        if (rc != IC_OK) return rc;
+        const char* h1_env = getenv("IC_H1_GENERIC");          // =1: the round-1 path (prep pass + generic grouped-tap kernel)
+        const bool h1_generic = h1_env && atoi(h1_env);
+        if (L[0].w_h1 && !h1_generic) {
+            // h1 from the image itself: normalisation, im2col and the conv in one kernel (conv_h1.cu), output (64 ch at
+            // H/2) written space-to-depth [pl][N][32][H/4][W/4][8] into pool[1..2]
+            rc = tc::launch_conv_h1(d_x, x_is_u8, N, H, W, c.normalization, L[0].w_h1, L[0].scale_h1, L[0].shift, L[0].spec.relu,
+                                    hp[1], exact, s);
+            if (rc != IC_OK) return rc;
+        } else {
+            // image -> normalised, space-to-depth hi/lo planes [pl][N][4][H/2][W/2][8]  (fits in `a1`), then h1 as 9
+            // stride-1 taps over one 32-channel group on the generic kernel
+            __half* x2 = reinterpret_cast<__half*>(a1);
+            rc = launch_prep_input_s2d(d_x, x_is_u8, N, H, W, c.normalization, x2, exact, s);
+            if (rc != IC_OK) return rc;
+            rc = conv_tc_layer(L[0], x2, 4, H2, W2, hp[1], nullptr, nullptr, nullptr, N, H2, W2, exact, s, 1);
+            if (rc != IC_OK) return rc;
+        }
         rc = conv_tc_layer(L[1], hp[1], 32, H4, W4, hp[0], nullptr, nullptr, nullptr, N, H4, W4, exact, s);   // h2
         if (rc != IC_OK) return rc;
         int ti = 0;

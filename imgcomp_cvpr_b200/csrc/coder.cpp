@@ -136,6 +136,37 @@ struct ic_ac_dec {
 
 extern "C" {
 
+/* CRC-32C (Castagnoli, reflected polynomial 0x82F63B78) of a host buffer: what TensorFlow's tensor bundle stores (masked)
+ * per tensor; imgcomp_cvpr_b200/tf_checkpoint.py verifies checkpoints with it. */
+uint32_t ic_crc32c(const void* h_data, int64_t n) {
+    static uint32_t table[8][256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+            table[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFF];
+        ready = true;
+    }
+    const uint8_t* p = (const uint8_t*)h_data;
+    uint32_t c = 0xFFFFFFFFu;
+    while (n >= 8) {               // slicing-by-8
+        uint32_t lo, hi;
+        memcpy(&lo, p, 4);
+        memcpy(&hi, p + 4, 4);
+        lo ^= c;
+        c = table[7][lo & 0xFF] ^ table[6][(lo >> 8) & 0xFF] ^ table[5][(lo >> 16) & 0xFF] ^ table[4][lo >> 24] ^
+            table[3][hi & 0xFF] ^ table[2][(hi >> 8) & 0xFF] ^ table[1][(hi >> 16) & 0xFF] ^ table[0][hi >> 24];
+        p += 8;
+        n -= 8;
+    }
+    while (n-- > 0) c = (c >> 8) ^ table[0][(c ^ *p++) & 0xFF];
+    return c ^ 0xFFFFFFFFu;
+}
+
 int ic_ac_enc_create(ic_ac_enc_t** out) {
     if (!out) return IC_ERR_INVALID;
     *out = new (std::nothrow) ic_ac_enc();

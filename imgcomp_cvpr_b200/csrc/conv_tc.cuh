@@ -95,6 +95,9 @@ void repack_cat(const std::vector<__half>& packed, int nstages, std::vector<__ha
 void repack_cat_pair(const std::vector<__half>& packed, int nstages, std::vector<__half>& out);
 int pack_weights_h1(const float* w_hwio, int cin, int cout, int nout, std::vector<__half>& packed, GroupTable& gt,
                     float* inv_scale_out);
+int launch_conv_h1(const void* x, int x_is_u8, int N, int H, int W, int normalize, const __half* weights, const float* scale,
+                   const float* shift, int relu, __half* out, int exact, cudaStream_t s);
+int pack_weights_h1_im2col(const float* w_hwio, int cin, int cout, std::vector<__half>& packed, float* inv_scale_out);
 int pack_weights_pc(const float* w, int ci, int co, int nout, std::vector<__half>& packed, GroupTable& gt,
                     float* inv_scale_out);
 int pack_weights(const float* w_hwio, int k, int stride, int cin, int cout, int nout, std::vector<__half>& packed,

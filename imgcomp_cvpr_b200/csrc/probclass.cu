@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) pc_conv0_kernel(Src src, int D, int H, in
                                                        const float* __restrict__ bias,  // [KC]
                                                        int D0, int H0, int W0, int64_t total,
                                                        float* __restrict__ out, __half* __restrict__ out_split) {
-    __shared__ float sw[13 * KC + KC];
+    __shared__ __align__(16) float sw[13 * KC + KC];
     for (int i = threadIdx.x; i < 13 * KC; i += blockDim.x) sw[i] = wgt[i];
     for (int i = threadIdx.x; i < KC; i += blockDim.x) sw[13 * KC + i] = bias[i];
     __syncthreads();
@@ -72,15 +72,29 @@ __global__ void __launch_bounds__(128) pc_conv0_kernel(Src src, int D, int H, in
                     val = src.at(((n * D + zd) * H + zy) * (int64_t)W + zx);
                 in[t++] = val;
             }
+    // Weights are read as float4 (4 output channels per LDS.128): with one LDS.32 per FMA the kernel was bound by the
+    // shared-memory pipe (312 broadcast loads per voxel), not by its 128 B / voxel store stream.  Every output still
+    // sums its 13 taps in raster order with fmaf, then adds the bias: bit-identical to the scalar form.
+    static_assert(KC % 8 == 0, "8 output channels per step");
     if (!SPLIT) {
         float* o = out + v * KC;
-#pragma unroll 4
-        for (int co = 0; co < KC; ++co) {
-            float acc = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < KC / 8; ++c) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < 13; ++k) acc = fmaf(in[k], sw[k * KC + co], acc);
-            acc += sw[13 * KC + co];
-            o[co] = fmaxf(acc, 0.f);
+            for (int k = 0; k < 13; ++k) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sw + k * KC + c * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(sw + k * KC + c * 8 + 4);
+                acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
+                acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
+                acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
+                acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
+            }
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = fmaxf(acc[j] + sw[13 * KC + c * 8 + j], 0.f);
+            *reinterpret_cast<float4*>(o + c * 8) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(o + c * 8 + 4) = make_float4(r[4], r[5], r[6], r[7]);
         }
     } else {
         const size_t cs = (size_t)H0 * W0 * 8;                         // chunk stride (elements)
@@ -88,25 +102,28 @@ __global__ void __launch_bounds__(128) pc_conv0_kernel(Src src, int D, int H, in
         const size_t base = (((size_t)(n * D0 + d) * 4) * H0 + y) * W0 * 8 + (size_t)x * 8;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (c * 8 < KC) {
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sw + k * KC + c * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sw + k * KC + c * 8 + 4);
+                    acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
+                    acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
+                    acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
+                    acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = fmaxf(acc[j] + sw[13 * KC + c * 8 + j], 0.f);
+            }
             __align__(16) __half2 hi[4];
             __align__(16) __half2 lo[4];
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
-                float r[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int co = c * 8 + e2 * 2 + u;
-                    float acc = 0.f;
-                    if (co < KC) {
-#pragma unroll
-                        for (int k = 0; k < 13; ++k) acc = fmaf(in[k], sw[k * KC + co], acc);
-                        acc = fmaxf(acc + sw[13 * KC + co], 0.f);
-                    }
-                    r[u] = acc;
-                }
-                hi[e2] = __floats2half2_rn(r[0], r[1]);
+                hi[e2] = __floats2half2_rn(r[2 * e2], r[2 * e2 + 1]);
                 float2 hf = __half22float2(hi[e2]);
-                lo[e2] = __floats2half2_rn(r[0] - hf.x, r[1] - hf.y);
+                lo[e2] = __floats2half2_rn(r[2 * e2] - hf.x, r[2 * e2 + 1] - hf.y);
             }
             *reinterpret_cast<float4*>(out_split + base + c * cs) = *reinterpret_cast<const float4*>(hi);
             *reinterpret_cast<float4*>(out_split + plane + base + c * cs) = *reinterpret_cast<const float4*>(lo);

@@ -237,8 +237,10 @@ struct ColArgs {
 __device__ __forceinline__ void col_terms(const ColArgs& a, int64_t row, int c, float& q1, float& q2) {
     const float x = a.x[row * a.C + c];
     if (a.mode == 0) {
-        q1 = x;
-        q2 = x * x;
+        // shifted sums: x - pivot with pivot = the channel's value in row 0.  E[x^2] - mean^2 on raw float32 sums cancels
+        // catastrophically when |mean| >> std; around a data point of the channel the sums stay O(std)
+        q1 = x - a.x[c];
+        q2 = q1 * q1;
     } else {
         const float xh = (x - a.mean[c]) * a.invstd[c];
         float dy = a.dy[row * a.C + c];
@@ -290,7 +292,8 @@ __global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __r
 // mode 0: mean, invstd (+ moving averages); mode 1: dbeta, dgamma.  One block per channel, fixed-order tree.
 __global__ void __launch_bounds__(128) col_finalize_kernel(const double* __restrict__ partial, int blocks, int C, int64_t M, int mode,
                                                            float eps, float* __restrict__ o1, float* __restrict__ o2,
-                                                           float* __restrict__ mov_mean, float* __restrict__ mov_var, float decay) {
+                                                           float* __restrict__ mov_mean, float* __restrict__ mov_var, float decay,
+                                                           const float* __restrict__ pivot_row /* mode 0: x row 0 */) {
     __shared__ double r1[128], r2[128];
     const int c = blockIdx.x;
     double s1 = 0, s2 = 0;
@@ -312,8 +315,9 @@ __global__ void __launch_bounds__(128) col_finalize_kernel(const double* __restr
     s1 = r1[0];
     s2 = r2[0];
     if (mode == 0) {
-        const double mean = s1 / (double)M;
-        double var = s2 / (double)M - mean * mean;
+        const double dm = s1 / (double)M;                       // mean of (x - pivot)
+        const double mean = (double)pivot_row[c] + dm;
+        double var = s2 / (double)M - dm * dm;
         if (var < 0) var = 0;
         o1[c] = (float)mean;
         o2[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -780,7 +784,7 @@ int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma,
         col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
         IC_CHECK_LAUNCH();
         col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 0, eps, d_mean, d_invstd,
-                                                         d_mov_mean, d_mov_var, 0.9f);
+                                                         d_mov_mean, d_mov_var, 0.9f, d_x);
         IC_CHECK_LAUNCH();
     }
     bn_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_mean, d_invstd, d_gamma, d_beta, relu, d_res1, d_res2, M * C, C, d_out);
@@ -804,7 +808,7 @@ int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, co
     col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
     IC_CHECK_LAUNCH();
     col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 1, 0.f, d_dbeta, d_dgamma, nullptr,
-                                                     nullptr, 0.f);
+                                                     nullptr, 0.f, nullptr);
     IC_CHECK_LAUNCH();
     bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_dy, d_mean, d_invstd, d_gamma, d_beta, d_dbeta, d_dgamma, relu,
                                                        use_stats ? 0 : 1, M * C, C, 1.f / (float)M, d_dx);

@@ -58,10 +58,17 @@ struct ScaleArgs {
 };
 
 __global__ void __launch_bounds__(256) finalize_scales_kernel(ScaleArgs a, float* __restrict__ params, float* __restrict__ scale,
-                                                              float* __restrict__ shift) {
+                                                              float* __restrict__ shift, const float* __restrict__ kept = nullptr) {
     __shared__ float red[256];
     __shared__ float sc[3];
-    for (int k = 0; k < a.ntens; ++k) {
+    if (kept && threadIdx.x == 0) {        // forward-pass scales of the weights (tensor 0) and of x (tensor 2)
+        sc[0] = kept[0];
+        params[0] = kept[0];
+        params[4] = kept[2];
+        params[2] = kept[1];
+        params[6] = kept[3];
+    }
+    for (int k = kept ? 1 : 0; k < a.ntens; ++k) {
         float m = 0.f;
         for (int i = threadIdx.x; i < a.count[k]; i += 256) m = fmaxf(m, a.partial[k][i]);
         red[threadIdx.x] = m;
@@ -332,6 +339,15 @@ size_t ic_nn_conv3x3_tc_workspace_bytes(int N, int H, int W) {
 
 int ic_nn_conv3x3_tc(const float* d_x, const float* d_w, int N, int H, int W, int data_grad, float* d_y, void* d_workspace,
                      size_t workspace_bytes, void* stream) {
+    return ic_nn_conv3x3_tc_ex(d_x, d_w, N, H, W, data_grad, d_y, nullptr, nullptr, d_workspace, workspace_bytes, stream);
+}
+
+/* d_x_planes_keep (optional, 2 * N*H*W*128 halves): the fp16 hi/lo planes of the pre-scaled input are written THERE
+ * instead of into the workspace, and d_scales_keep (optional, 4 floats) receives {scale_w, scale_x, 1/scale_w, 1/scale_x}:
+ * what ic_nn_conv3x3_tc_bwd_ex needs to skip re-deriving them (the weights and x do not change between the forward and
+ * the backward pass of one training step). */
+int ic_nn_conv3x3_tc_ex(const float* d_x, const float* d_w, int N, int H, int W, int data_grad, float* d_y, void* d_x_planes_keep,
+                        float* d_scales_keep, void* d_workspace, size_t workspace_bytes, void* stream) {
     IC_REQUIRE(d_x && d_w && d_y && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc: NULL argument");
     IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc: bad shape");
     IC_REQUIRE(workspace_bytes >= ic_nn_conv3x3_tc_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc: workspace too small");
@@ -349,6 +365,7 @@ int ic_nn_conv3x3_tc(const float* d_x, const float* d_w, int N, int H, int W, in
     float* pw = ar.get<float>(kMaxBlocks);
     float* px = ar.get<float>(kMaxBlocks);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc: workspace too small");
+    if (d_x_planes_keep) bi = reinterpret_cast<__half*>(d_x_planes_keep);
     ScaleArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.ntens = 2;
@@ -364,6 +381,10 @@ int ic_nn_conv3x3_tc(const float* d_x, const float* d_w, int N, int H, int W, in
     }
     rc = tc::launch_split_from_nhwc(d_x, N, H, W, kC, 0, bi, 1, s, params + 1);
     if (rc != IC_OK) return rc;
+    if (d_scales_keep) {
+        IC_CHECK_CUDA(cudaMemcpyAsync(d_scales_keep, params, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        IC_CHECK_CUDA(cudaMemcpyAsync(d_scales_keep + 2, params + 4, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
     return conv_planes(bi, d_w, data_grad, params, params + 5, scale, shift, wp, bo, N, H, W, d_y, s);
 }
 
@@ -377,7 +398,15 @@ size_t ic_nn_conv3x3_tc_bwd_workspace_bytes(int N, int H, int W) {
 /* backward of y = conv3x3(x, w): d_dx (optional) = data gradient, d_dw = filter gradient [3][3][128][128] */
 int ic_nn_conv3x3_tc_bwd(const float* d_x, const float* d_dy, const float* d_w, int N, int H, int W, float* d_dx, float* d_dw,
                          void* d_workspace, size_t workspace_bytes, void* stream) {
-    IC_REQUIRE(d_x && d_dy && d_w && d_dw && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd: NULL argument");
+    return ic_nn_conv3x3_tc_bwd_ex(d_x, d_dy, d_w, N, H, W, d_dx, d_dw, nullptr, nullptr, d_workspace, workspace_bytes, stream);
+}
+
+/* d_x_planes / d_scales (both or neither): what ic_nn_conv3x3_tc_ex kept of the forward pass; d_x may then be NULL */
+int ic_nn_conv3x3_tc_bwd_ex(const float* d_x, const float* d_dy, const float* d_w, int N, int H, int W, float* d_dx, float* d_dw,
+                            const void* d_x_planes, const float* d_scales, void* d_workspace, size_t workspace_bytes,
+                            void* stream) {
+    const bool cached = d_x_planes != nullptr && d_scales != nullptr;
+    IC_REQUIRE((d_x || cached) && d_dy && d_w && d_dw && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd: NULL argument");
     IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd: bad shape");
     IC_REQUIRE(workspace_bytes >= ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_bwd: workspace too small");
     int rc = ensure_group_table();
@@ -401,22 +430,29 @@ int ic_nn_conv3x3_tc_bwd(const float* d_x, const float* d_dy, const float* d_w, 
     const int64_t n_act = (int64_t)N * H * W * kC;
     ScaleArgs sa;
     memset(&sa, 0, sizeof(sa));
-    sa.ntens = 3;
+    sa.ntens = cached ? 2 : 3;
     sa.partial[0] = pw;
     sa.partial[1] = pdy;
     sa.partial[2] = px;
     {
-        ProfScope ps(IC_PROF_ELEMENTWISE, s, 4);
-        rc = maxabs(d_w, kW, pw, &sa.count[0], s);
-        if (rc == IC_OK) rc = maxabs(d_dy, n_act, pdy, &sa.count[1], s);
-        if (rc == IC_OK) rc = maxabs(d_x, n_act, px, &sa.count[2], s);
+        ProfScope ps(IC_PROF_ELEMENTWISE, s, cached ? 2 : 4);
+        if (cached) {
+            // scale_w from the forward pass: a one-element "partial maximum" whose pow2_scale is that scale again
+            rc = maxabs(d_dy, n_act, pdy, &sa.count[1], s);
+            sa.count[0] = 0;
+        } else {
+            rc = maxabs(d_w, kW, pw, &sa.count[0], s);
+            if (rc == IC_OK) rc = maxabs(d_dy, n_act, pdy, &sa.count[1], s);
+            if (rc == IC_OK) rc = maxabs(d_x, n_act, px, &sa.count[2], s);
+        }
         if (rc != IC_OK) return rc;
-        finalize_scales_kernel<<<1, 256, 0, s>>>(sa, params, scale, shift);
+        finalize_scales_kernel<<<1, 256, 0, s>>>(sa, params, scale, shift, cached ? d_scales : nullptr);
         IC_CHECK_LAUNCH();
     }
     rc = tc::launch_split_from_nhwc(d_dy, N, H, W, kC, 0, bdy, 1, s, params + 1);
-    if (rc == IC_OK) rc = tc::launch_split_from_nhwc(d_x, N, H, W, kC, 0, bx, 1, s, params + 2);
+    if (rc == IC_OK && !cached) rc = tc::launch_split_from_nhwc(d_x, N, H, W, kC, 0, bx, 1, s, params + 2);
     if (rc != IC_OK) return rc;
+    if (cached) bx = reinterpret_cast<__half*>(const_cast<void*>(d_x_planes));
     // filter gradient
     CUtensorMap xmap, ymap;
     rc = tc::encode_planes_map(&xmap, bx, 2, N, kC / 8, H, W, WG_COLS + 2, WG_ROWS, kC / 8);

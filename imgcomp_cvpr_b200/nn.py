@@ -73,28 +73,43 @@ def conv2d_bwd_filter(x, dy, w_shape, stride=1, transposed=False, valid=False, o
     return dw
 
 
-def conv3x3_tc(x, w, data_grad=False):
+def conv3x3_tc(x, w, data_grad=False, keep=False):
     """3x3 stride-1 SAME 128 -> 128 convolution (data_grad: its data gradient, x = dy) on the tcgen05 kernel, EXACT mode;
-    x N,H,W,128 float32, w [3][3][128][128] float32 (both on the device)"""
+    x N,H,W,128 float32, w [3][3][128][128] float32 (both on the device).  keep=True: -> (y, cache) where cache holds the
+    pre-scaled fp16 hi/lo planes of x and the scales of w and x for conv3x3_tc_bwd (no second maximum search / split)."""
     N, H, W, C = x.shape
     assert C == 128 and tuple(w.shape) == (3, 3, 128, 128)
     y = torch.empty_like(x)
     ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_workspace_bytes(N, H, W))
-    _lib.check(_lib.lib().ic_nn_conv3x3_tc(_lib.ptr(_f32(x)), _lib.ptr(_f32(w)), N, H, W, int(bool(data_grad)), _lib.ptr(y),
-                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
-    return y
+    if not keep:
+        _lib.check(_lib.lib().ic_nn_conv3x3_tc(_lib.ptr(_f32(x)), _lib.ptr(_f32(w)), N, H, W, int(bool(data_grad)), _lib.ptr(y),
+                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return y
+    planes = torch.empty(2 * x.numel(), dtype=torch.float16, device=x.device)
+    scales = torch.empty(4, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ic_nn_conv3x3_tc_ex(_lib.ptr(_f32(x)), _lib.ptr(_f32(w)), N, H, W, int(bool(data_grad)), _lib.ptr(y),
+                                             _lib.ptr(planes), _lib.ptr(scales), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return y, (planes, scales)
 
 
-def conv3x3_tc_bwd(x, dy, w, need_dx=True, dw_out=None):
-    """backward of conv3x3_tc(x, w): -> (dx or None, dw [3][3][128][128]); both gradients on the tcgen05 kernels"""
+def conv3x3_tc_bwd(x, dy, w, need_dx=True, dw_out=None, cache=None):
+    """backward of conv3x3_tc(x, w): -> (dx or None, dw [3][3][128][128]); both gradients on the tcgen05 kernels.
+    cache: what conv3x3_tc(..., keep=True) returned for this x and w"""
     N, H, W, C = x.shape
     assert C == 128 and tuple(w.shape) == (3, 3, 128, 128) and tuple(dy.shape) == tuple(x.shape)
     dx = torch.empty_like(x) if need_dx else None
     dw = torch.empty_like(w) if dw_out is None else dw_out
     assert tuple(dw.shape) == (3, 3, 128, 128)
     ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W))
-    _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
-                                              _lib.ptr(_f32(dw)), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    if cache is None:
+        _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
+                                                  _lib.ptr(_f32(dw)), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    else:
+        planes, scales = cache
+        assert planes.numel() == 2 * x.numel() and planes.dtype == torch.float16
+        _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd_ex(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
+                                                     _lib.ptr(_f32(dw)), _lib.ptr(planes), _lib.ptr(scales), _lib.ptr(ws), ws.numel(),
+                                                     _lib.stream_ptr()))
     return dx, dw
 
 

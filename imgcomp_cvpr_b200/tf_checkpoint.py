@@ -18,6 +18,7 @@ download): tests/test_tf_checkpoint_cpu.py round-trips files produced by a write
 """
 import glob
 import os
+import re
 import struct
 
 import numpy as np
@@ -141,8 +142,26 @@ def _signed64(v):
     return v - (1 << 64) if v >= (1 << 63) else v
 
 
+# optimizer slots and counters tf.train.Saver stores beside the model variables.  The reference names its optimizers
+# 'Adam_AE' / 'Adam_PC' (code/train.py:339-349), so the slots are '<var>/Adam_AE', '<var>/Adam_AE_1', '<var>/Adam_PC[_1]',
+# and the second optimizer's accumulators 'beta1_power_1' / 'beta2_power_1'.
+_NOT_A_MODEL_VARIABLE = re.compile(r'/(Adam\w*|Momentum\w*|RMSProp\w*)(_\d+)?$|^beta\d_power(_\d+)?$|^global_step$|ExponentialMovingAverage')
+
+
+def is_model_variable(name):
+    return _NOT_A_MODEL_VARIABLE.search(name) is None
+
+
+def masked_crc32c(raw):
+    """tensorflow/core/lib/hash/crc32c.h Mask(): what BundleEntryProto.crc32c holds for the tensor's bytes"""
+    from . import _lib
+    buf = np.frombuffer(raw, np.uint8)
+    crc = int(_lib.lib().ic_crc32c(buf.ctypes.data, buf.size)) & 0xFFFFFFFF
+    return (((crc >> 15) | (crc << 17)) + 0xa282ead8) & 0xFFFFFFFF
+
+
 def _parse_entry(buf):
-    e = {'dtype': 0, 'shape': [], 'shard_id': 0, 'offset': 0, 'size': 0, 'slices': 0}
+    e = {'dtype': 0, 'shape': [], 'shard_id': 0, 'offset': 0, 'size': 0, 'slices': 0, 'crc32c': None}
     for field, wt, v in _proto_fields(buf):
         if field == 1:
             e['dtype'] = v
@@ -160,6 +179,8 @@ def _parse_entry(buf):
             e['offset'] = v
         elif field == 5:
             e['size'] = v
+        elif field == 6:
+            e['crc32c'] = struct.unpack('<I', v)[0] if wt == 5 else int(v)
         elif field == 7:
             e['slices'] += 1
     return e
@@ -208,15 +229,14 @@ def resolve_prefix(path):
     return path[:-len('.index')] if path.endswith('.index') else path
 
 
-def load(path, include=None):
-    """-> dict tensor name -> ndarray.  include: optional predicate on the name (default: model variables only, i.e.
-    without optimizer slots '/Adam', '/Adam_1', 'beta*_power', 'global_step' that tf.train.Saver stores beside them)."""
+def load(path, include=None, verify_crc=True):
+    """-> dict tensor name -> ndarray.  include: optional predicate on the name (default: is_model_variable, i.e. without
+    the optimizer slots and counters tf.train.Saver stores beside the variables).  verify_crc: check every tensor's
+    bytes against the masked CRC-32C of its index entry (when the writer stored one)."""
     prefix = resolve_prefix(path)
     header, entries = read_index(prefix + '.index')
     if include is None:
-        def include(name):
-            return not (name.endswith('/Adam') or name.endswith('/Adam_1') or name.endswith('_power') or name == 'global_step'
-                        or '/Momentum' in name or '/ExponentialMovingAverage' in name)
+        include = is_model_variable
     shards = {}
     out = {}
     for name, e in sorted(entries.items()):
@@ -236,6 +256,8 @@ def load(path, include=None):
         n = int(np.prod(e['shape'])) if e['shape'] else 1
         if len(raw) != e['size'] or n * dt.itemsize != e['size']:
             raise ValueError('%s: %d bytes in the data file, shape %s of %s needs %d' % (name, len(raw), e['shape'], dt, n * dt.itemsize))
+        if verify_crc and e['crc32c'] is not None and masked_crc32c(raw) != e['crc32c']:
+            raise ValueError('%s: CRC-32C mismatch (checkpoint data corrupted)' % name)
         out[name] = np.frombuffer(raw, dtype=dt.newbyteorder('<')).astype(dt).reshape(e['shape'])
     for f in shards.values():
         f.close()

@@ -296,7 +296,11 @@ class Trainer(object):
     # ------------------------------------------------------------------ ops (forward + recorded backward)
     def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None):
         tc = (self.mode == 'exact' and tuple(w.shape) == (3, 3, 128, 128) and stride == 1 and not transposed and not valid)
-        y = nn.conv3x3_tc(x, w) if tc else nn.conv2d_fwd(x, w, stride, transposed, valid)
+        cache = None
+        if tc and self.tape is not None:        # keep the input's fp16 planes and the scales for the filter gradient
+            y, cache = nn.conv3x3_tc(x, w, keep=True)
+        else:
+            y = nn.conv3x3_tc(x, w) if tc else nn.conv2d_fwd(x, w, stride, transposed, valid)
         if self.tape is not None:
             tape = self.tape
 
@@ -305,7 +309,7 @@ class Trainer(object):
                 if dy is None:
                     return
                 if tc:        # both gradients on tensor cores (filter gradient: GEMM over pixels, csrc/train_tc.cu)
-                    dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw)
+                    dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
                     if need_dx:
                         tape.acc(x, dx, owned=True)
                     return

@@ -220,9 +220,19 @@ int ic_nn_conv3x3_tc(const float* d_x, const float* d_w, int N, int H, int W, in
  * pre-scaled by per-tensor powers of two so that small gradients keep float32-class precision in the fp16 hi/lo split):
  * d_dx (optional) = ic_nn_conv2d_bwd_data, d_dw = ic_nn_conv2d_bwd_filter [3][3][128][128].  The filter gradient is a
  * GEMM over pixels on MN-major operands (see csrc/train_tc.cu) with a fixed-order reduction over pixel splits. */
+/* ic_nn_conv3x3_tc with the forward pass kept for the backward pass: d_x_planes_keep (optional, 2*N*H*W*128 fp16
+ * elements, device memory) receives the pre-scaled hi/lo planes of x, d_scales_keep (optional, 4 floats) {scale_w, scale_x, 1/scale_w,
+ * 1/scale_x}.  Handing both to ic_nn_conv3x3_tc_bwd_ex saves it the maximum search over w and x and the split of x
+ * (tf.gradients reuses the forward activations the same way; code/train.py:339-349). */
+int ic_nn_conv3x3_tc_ex(const float* d_x, const float* d_w, int N, int H, int W, int data_grad, float* d_y,
+                        void* d_x_planes_keep, float* d_scales_keep, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
 size_t ic_nn_conv3x3_tc_bwd_workspace_bytes(int N, int H, int W);
 int ic_nn_conv3x3_tc_bwd(const float* d_x, const float* d_dy, const float* d_w, int N, int H, int W, float* d_dx, float* d_dw,
                          void* d_workspace, size_t workspace_bytes, void* stream);
+int ic_nn_conv3x3_tc_bwd_ex(const float* d_x, const float* d_dy, const float* d_w, int N, int H, int W, float* d_dx,
+                            float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
+                            size_t workspace_bytes, void* stream);
 /* slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125): batch mean / biased variance over
  * the M = N*H*W rows, out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2); d_mean / d_invstd are
  * kept for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update with
@@ -361,6 +371,9 @@ int ic_profile_get(int cls, double* total_ms, long long* launches);
  * restates: arithmetic_coding.ArithmeticEncoder / ArithmeticDecoder with
  * SimpleFrequencyTable (code/arithmetic_coding.py:39-222,323-424), 32-bit state.
  * Pure host code (the north star keeps the coder on the host). */
+/* CRC-32C of a host buffer (TensorFlow tensor bundles store it, masked, per tensor: code/saver.py restores such files) */
+uint32_t ic_crc32c(const void* h_data, int64_t n);
+
 typedef struct ic_ac_enc ic_ac_enc_t;
 typedef struct ic_ac_dec ic_ac_dec_t;
 int ic_ac_enc_create(ic_ac_enc_t** out);

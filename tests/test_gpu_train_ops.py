@@ -107,6 +107,22 @@ def test_batch_norm_train(C, relu, res):
     np.testing.assert_allclose(dbeta.cpu().numpy(), P['s/BatchNorm/beta'].grad.numpy(), rtol=1e-4, atol=1e-4)
 
 
+def test_batch_norm_statistics_with_large_mean():
+    """|mean| >> std in a channel (never the case with the synthetic weights): E[x^2] - mean^2 on float32 sums would
+    lose the variance to cancellation; the kernel sums (x - pivot) and (x - pivot)^2 around a data point instead"""
+    from imgcomp_cvpr_b200 import nn
+    rng = np.random.RandomState(0)
+    M, C = 4096, 64
+    x = (rng.standard_normal((M, C)) * 0.05 + 100.0 * (1 + np.arange(C))[None, :]).astype(np.float32)
+    xg = _cuda(x.reshape(1, 64, 64, C))
+    ones, zeros = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
+    out, mean, invstd = nn.bn_train_fwd(xg, ones, zeros, False)
+    x64 = x.astype(np.float64)
+    np.testing.assert_allclose(mean.cpu().numpy(), x64.mean(0), rtol=1e-7)
+    np.testing.assert_allclose(invstd.cpu().numpy(), 1.0 / np.sqrt(x64.var(0) + 1e-5), rtol=2e-3)
+    np.testing.assert_allclose(out.cpu().numpy().reshape(M, C), (x64 - x64.mean(0)) / np.sqrt(x64.var(0) + 1e-5), atol=2e-2)
+
+
 def test_affine_relu_layer():
     """use_stats = 0: y = relu(x + bias), the bias + ReLU of the context model's conv3d (code/probclass.py:259-261)"""
     from imgcomp_cvpr_b200 import nn

@@ -99,6 +99,11 @@ def test_conv3x3_tensor_core_backward(N, H, W, gscale):
         assert np.abs(dw.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
     _, dw_only = nn.conv3x3_tc_bwd(x, dy, w, need_dx=False)
     assert torch.equal(dw_only, dw)
+    # the forward pass kept for the backward pass (input planes + scales): no second maximum search / split, same bits
+    y_keep, cache = nn.conv3x3_tc(x, w, keep=True)
+    assert torch.equal(y_keep, nn.conv3x3_tc(x, w))
+    dx_c, dw_c = nn.conv3x3_tc_bwd(x, dy, w, cache=cache)
+    assert torch.equal(dx_c, dx) and torch.equal(dw_c, dw)
 
 
 def test_exact_mode_step_matches_fp32_mode(synth):

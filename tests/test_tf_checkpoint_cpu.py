@@ -32,7 +32,7 @@ def _field(num, wt, payload):
 def _entry_proto(arr, offset):
     shape = b''.join(_field(2, 2, _vi(len(d)) + d) for d in (_field(1, 0, _vi(s)) for s in arr.shape))
     return (_field(1, 0, _vi(DT_ENUM[arr.dtype])) + _field(2, 2, _vi(len(shape)) + shape) + _field(4, 0, _vi(offset)) +
-            _field(5, 0, _vi(arr.nbytes)) + _field(6, 5, struct.pack('<I', 0)))
+            _field(5, 0, _vi(arr.nbytes)) + _field(6, 5, struct.pack('<I', tf_checkpoint.masked_crc32c(arr.tobytes()))))
 
 
 def _block(items, restart_interval=16):
@@ -118,3 +118,47 @@ def test_snappy_blocks_and_errors(tmp_path):
     empty.mkdir()
     with pytest.raises(FileNotFoundError):
         tf_checkpoint.resolve_prefix(str(empty))
+
+
+def test_crc32c_known_answers_and_corruption_is_detected(tmp_path):
+    """CRC-32C (Castagnoli) check values: RFC 3720 B.4 / the usual "123456789" vector; a flipped byte in the data shard
+    must be caught by the per-tensor checksum of the index"""
+    from imgcomp_cvpr_b200 import _lib
+
+    def crc(b):
+        a = np.frombuffer(b, np.uint8)
+        return int(_lib.lib().ic_crc32c(a.ctypes.data, a.size)) & 0xFFFFFFFF
+    assert crc(b'123456789') == 0xE3069283
+    assert crc(bytes(32)) == 0x8A9136AA and crc(b'\xff' * 32) == 0x62A8AB43
+    assert crc(bytes(range(32))) == 0x46DD794E
+    W = {'a/weights': np.arange(1000, dtype=np.float32), 'b/biases': np.ones(7, np.float32)}
+    prefix = str(tmp_path / 'ckpt-1')
+    write_checkpoint(prefix, W)
+    assert np.array_equal(tf_checkpoint.load(prefix)['a/weights'], W['a/weights'])
+    data = prefix + '.data-00000-of-00001'
+    raw = bytearray(open(data, 'rb').read())
+    raw[100] ^= 0x40
+    open(data, 'wb').write(bytes(raw))
+    with pytest.raises(ValueError, match='CRC'):
+        tf_checkpoint.load(prefix)
+    assert tf_checkpoint.load(prefix, verify_crc=False)['a/weights'].shape == (1000,)
+
+
+def test_reference_optimizer_slot_names_are_filtered(tmp_path):
+    """code/train.py:339-349 names its optimizers Adam_AE / Adam_PC: slots '<var>/Adam_AE', '<var>/Adam_AE_1',
+    '<var>/Adam_PC[_1]' and the accumulators 'beta1_power[_1]', 'beta2_power[_1]' are not model variables"""
+    W = {'autoencoder/encoder/h1/weights': np.ones((5, 5, 3, 64), np.float32),
+         'probclass3d/logits/conv3d_conv0_mask/biases': np.zeros(24, np.float32)}
+    extra = {}
+    for k, v in W.items():
+        opt = 'Adam_AE' if k.startswith('autoencoder') else 'Adam_PC'
+        extra[k + '/' + opt] = np.zeros_like(v)
+        extra[k + '/' + opt + '_1'] = np.zeros_like(v)
+    for n in ('beta1_power', 'beta2_power', 'beta1_power_1', 'beta2_power_1'):
+        extra[n] = np.asarray(0.5, np.float32)
+    extra['global_step'] = np.asarray(7, np.int64)
+    prefix = str(tmp_path / 'ckpt-7')
+    write_checkpoint(prefix, dict(W, **extra))
+    assert sorted(tf_checkpoint.load(prefix)) == sorted(W)
+    assert all(not tf_checkpoint.is_model_variable(n) for n in extra)
+    assert all(tf_checkpoint.is_model_variable(n) for n in weights.synthetic_weights())
