@@ -237,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                 for (int g = 0; g < gt.ngroups; ++g, ++gi) {
                     const uint32_t slot = gi & 1, ph = (gi >> 1) & 1;
                     mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
-                    const int img = n * p.img_mul + (p.img_div > 0 ? (n / p.img_div) * p.img_div_mul : 0) + gt.img_off[g];
+                    const int img = n * p.img_mul + (p.img_div > 0 ? (n / p.img_div) * p.img_div_mul : 0) + gt.img_off[g] * p.img_off_mul + p.img_base;
                     if (PAIR) {
                         const uint32_t full = mapa_rank(smem_u32(&bars->a_full[slot]), 0);     // the leader's barrier
                         if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[slot]), 2 * NPL * C::A_PLANE_BYTES);   // both tiles
@@ -578,6 +578,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                     for (int cc = 0; cc < NOUT / 16; ++cc) {
                         uint32_t rr[16];
                         tmem_ld16(taddr + cc * 16, rr);
+                        if (CAT) {          // main sum (gain: see launch_t) + cross sum
+                            uint32_t rx[16];
+                            tmem_ld16(taddr + NOUT + cc * 16, rx);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                rr[e] = __float_as_uint(fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
+                        }
                         tmem_ld_wait();
                         if (inside) {
 #pragma unroll
@@ -1085,6 +1093,8 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.img_mul = a.img_mul;
     p.img_div = a.img_div;
     p.img_div_mul = a.img_div_mul;
+    p.img_off_mul = a.img_off_mul ? a.img_off_mul : 1;
+    p.img_base = a.img_base;
     p.res_H = a.res_H ? a.res_H : a.H;
     p.res_W = a.res_W ? a.res_W : a.W;
     p.res_dy = a.res_dy;
@@ -1324,6 +1334,10 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     if (a.nout == 64 && a.out) return launch_n<64, 0>(a, s);
     if (a.nout == 256 && a.out && a.d2s_cch)      // depth-to-space transposed convs: one 256-column tile, T = 1
         return a.exact ? launch_t<1, 2, 256, 0, 4, false>(a, s) : launch_t<1, 1, 256, 0, 4, false>(a, s);
+    if (a.pc_f32) {        // training: context-model layers with float32 NHWC output (forward and data gradient)
+        IC_REQUIRE(a.exact && a.out_f32 && (a.nout == 32 || a.nout == 16), IC_ERR_UNSUPPORTED, "conv_tc: pc_f32 needs nout 32 / 16");
+        return a.nout == 32 ? launch_pc<32, 1>(a, s) : launch_pc<16, 1>(a, s);
+    }
     if (a.nout == 16 && a.head < 0 && a.out_f32) return launch_n<16, 3>(a, s);
     if (a.nout == 48 && a.out_f32) return launch_n<48, 1>(a, s);
     if (a.nout == 80 && a.out_f32) return launch_n<80, 1>(a, s);

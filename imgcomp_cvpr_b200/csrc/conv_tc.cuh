@@ -35,6 +35,9 @@ struct ConvTcParams {
     int halo0;                  // origin of the halo tile relative to the output tile (-1: SAME 3x3-like, 0: VALID)
     // input image coordinate = n * img_mul + (n / img_div) * img_div_mul + img_off[group]   (img_div = 0: off)
     int img_mul, img_div, img_div_mul;
+    // ... + img_base, with img_off[group] multiplied by img_off_mul (depth-major training volumes: one depth slice = N images;
+    // the data gradient reads slice s - 1, i.e. img_base = -N: negative image coordinates are TMA zero fill)
+    int img_off_mul, img_base;
     // geometry of res1 (context model: a crop of a larger tensor); res2 always has the output geometry
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;
@@ -68,6 +71,8 @@ struct ConvTcArgs {
     int N, H, W;                // output tile grid
     int relu, cout, nout;       // nout: padded output channels the weights were packed for (128 or 48)
     int halo0, img_mul, img_div, img_div_mul;
+    int img_off_mul, img_base;  // see ConvTcParams (img_off_mul = 0 means 1)
+    int pc_f32;                 // context-model layer (resident weights, B-concatenation) with float32 NHWC output (training)
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;
     int out_s2d, d2s_cch, d2s_ph0, denorm;

@@ -6,6 +6,7 @@
 // downsample kernel feeds the next level.  All reductions are deterministic
 // (fixed-order partial sums, no atomics).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -114,6 +115,132 @@ __global__ void __launch_bounds__(TW* TH) ssim_level_kernel(const TIn* __restric
     if (tid == 0) {
         double a0 = 0, a1 = 0;
         for (int i = 0; i < TW * TH / 32; ++i) {
+            a0 += red[0][i];
+            a1 += red[1][i];
+        }
+        int64_t blk = ((int64_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partial[2 * blk] = a0;
+        partial[2 * blk + 1] = a1;
+    }
+}
+
+// Row-streaming form of ssim_level_kernel for the common case (K taps, no REFLECT padding): a block owns SW output
+// columns (one per thread) and marches down `rows_per_block` output rows.  Every input row is staged once in shared
+// memory (coalesced loads, prefetched one row ahead), its horizontal blur of (x, y, xx, yy, xy) goes into a K-deep
+// register ring, and the vertical blur reads the ring: per output pixel 2 K shared-memory reads and 10 K FMAs instead of
+// the 16x16 tile's 2.6x halo re-reads and shared-memory round trip of the half-blurred maps.  Same per-pixel operation
+// order as ssim_level_kernel (taps ascending, horizontal pass first), so the per-pixel values are identical.
+constexpr int SW = 128;        // output columns (= threads) per block
+constexpr int SROWS_MAX = 64;  // output rows per block (the launch halves it until the grid fills the GPU)
+
+template <typename T, typename TIn, int K>
+__global__ void __launch_bounds__(SW) ssim_level_stream_kernel(const TIn* __restrict__ a, const TIn* __restrict__ b,
+                                                               LevelParams<T> p, int srows, double* __restrict__ partial) {
+    __shared__ T sx[2][SW + K - 1];
+    __shared__ T sy[2][SW + K - 1];
+    __shared__ double red[2][SW / 32];
+    const int plane = blockIdx.z, tid = threadIdx.x;
+    const int ox0 = blockIdx.x * SW, oy0 = blockIdx.y * srows;
+    const int nout = min(srows, p.Ho - oy0), nin = nout + K - 1;       // input rows oy0 .. oy0 + nin - 1 (< H)
+    const TIn* pa = a + ((int64_t)plane * p.H + oy0) * p.W;
+    const TIn* pb = b + ((int64_t)plane * p.H + oy0) * p.W;
+    const int c0 = ox0 + tid, c1 = ox0 + SW + tid;
+    const bool v0 = c0 < p.W, v1 = tid < K - 1 && c1 < p.W;
+    const bool out_ok = c0 < p.Wo;
+    T taps[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) taps[t] = p.taps[t];
+    T ring[K][5];
+    T nx0 = 0, ny0 = 0, nx1 = 0, ny1 = 0;
+    if (v0) {
+        nx0 = (T)pa[c0];
+        ny0 = (T)pb[c0];
+    }
+    if (v1) {
+        nx1 = (T)pa[c1];
+        ny1 = (T)pb[c1];
+    }
+    double s_ssim = 0.0, s_cs = 0.0;
+    for (int r0 = 0; r0 < nin; r0 += K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int r = r0 + j;
+            if (r < nin) {                      // block-uniform
+                const int buf = r & 1;          // two row buffers: one barrier per row
+                sx[buf][tid] = nx0;
+                sy[buf][tid] = ny0;
+                if (tid < K - 1) {
+                    sx[buf][SW + tid] = nx1;
+                    sy[buf][SW + tid] = ny1;
+                }
+                if (r + 1 < nin) {              // next row's loads fly during this row's arithmetic
+                    const int64_t o = (int64_t)(r + 1) * p.W;
+                    if (v0) {
+                        nx0 = (T)pa[o + c0];
+                        ny0 = (T)pb[o + c0];
+                    }
+                    if (v1) {
+                        nx1 = (T)pa[o + c1];
+                        ny1 = (T)pb[o + c1];
+                    }
+                }
+                __syncthreads();
+                T h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+#pragma unroll
+                for (int t = 0; t < K; ++t) {
+                    T x = sx[buf][tid + t], y = sy[buf][tid + t], k = taps[t];
+                    T xx = x * x, yy = y * y, xy = x * y;
+                    h0 += x * k;
+                    h1 += y * k;
+                    h2 += xx * k;
+                    h3 += yy * k;
+                    h4 += xy * k;
+                }
+                ring[j][0] = h0;
+                ring[j][1] = h1;
+                ring[j][2] = h2;
+                ring[j][3] = h3;
+                ring[j][4] = h4;
+                if (r >= K - 1) {               // output row r - (K-1): input rows r-K+1 .. r = ring slots (j+1+t) % K
+                    T mu1 = 0, mu2 = 0, s11 = 0, s22 = 0, s12 = 0;
+#pragma unroll
+                    for (int t = 0; t < K; ++t) {
+                        const int q = (j + 1 + t) % K;
+                        T k = taps[t];
+                        mu1 += ring[q][0] * k;
+                        mu2 += ring[q][1] * k;
+                        s11 += ring[q][2] * k;
+                        s22 += ring[q][3] * k;
+                        s12 += ring[q][4] * k;
+                    }
+                    T mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
+                    s11 -= mu11;
+                    s22 -= mu22;
+                    s12 -= mu12;
+                    T v1n = (T)2.0 * s12 + p.c2;
+                    T v2n = s11 + s22 + p.c2;
+                    T ssim = (((T)2.0 * mu12 + p.c1) * v1n) / ((mu11 + mu22 + p.c1) * v2n);
+                    T cs = v1n / v2n;
+                    if (out_ok) {
+                        s_ssim += (double)ssim;
+                        s_cs += (double)cs;
+                    }
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s_ssim += __shfl_down_sync(0xffffffffu, s_ssim, o);
+        s_cs += __shfl_down_sync(0xffffffffu, s_cs, o);
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = s_ssim;
+        red[1][tid >> 5] = s_cs;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a0 = 0, a1 = 0;
+        for (int i = 0; i < SW / 32; ++i) {
             a0 += red[0][i];
             a1 += red[1][i];
         }
@@ -279,11 +406,27 @@ int run_msssim(const TIn* img1, const TIn* img2, int N, int H, int W, void* ws, 
         IC_REQUIRE(rc == IC_OK, IC_ERR_INVALID,
                    "ms-ssim: level %d is %dx%d, too small for the %d-tap blur (the reference raises here)", l, hs[l],
                    wsz[l], p.K);
+        // large full 11-tap levels without REFLECT padding: row-streaming kernel;
+        // IC_MSSSIM_TILED=1 forces the 16x16-tile kernel everywhere (A/B in tests)
+        const bool force_tiled = getenv("IC_MSSSIM_TILED") && atoi(getenv("IC_MSSSIM_TILED"));
+        // (below ~0.4 M output pixels per level the 16x16 tiles win: the row march is a serial chain of Ho barriers.
+        //  B200, 72 planes, float: 192x128 59 -> 35 us, 96x64 19 -> 19 us, 48x32 8 -> 18 us; profiles/r2_summary.md)
+        const bool stream = p.K == MAXK && p.p1 == 0 && p.p2 == 0 && !force_tiled && (int64_t)P * p.Ho * p.Wo >= 400000;
         dim3 grid(cdiv(p.Wo, TW), cdiv(p.Ho, TH), P), block(TW, TH);
-        if (l == 0)
+        if (stream) {
+            // rows per block: as many as keep >= 8 blocks per SM in flight (each extra block re-reads K-1 halo rows)
+            int srows = SROWS_MAX;
+            while (srows > 16 && (int64_t)cdiv(p.Wo, SW) * cdiv(p.Ho, srows) * P < 8 * 148) srows >>= 1;
+            grid = dim3(cdiv(p.Wo, SW), cdiv(p.Ho, srows), P);
+            if (l == 0)
+                ssim_level_stream_kernel<T, TIn, MAXK><<<grid, SW, 0, s>>>(img1, img2, p, srows, partial);
+            else
+                ssim_level_stream_kernel<T, T, MAXK><<<grid, SW, 0, s>>>(bufA[l], bufB[l], p, srows, partial);
+        } else if (l == 0) {
             ssim_level_kernel<T, TIn><<<grid, block, 0, s>>>(img1, img2, p, partial);
-        else
+        } else {
             ssim_level_kernel<T, T><<<grid, block, 0, s>>>(bufA[l], bufB[l], p, partial);
+        }
         IC_CHECK_LAUNCH();
         int bpp = grid.x * grid.y;
         double inv = 1.0 / ((double)p.Ho * p.Wo * (TF ? P : 3));

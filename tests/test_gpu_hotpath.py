@@ -185,6 +185,26 @@ def test_msssim_pairs(gpu_models):
     assert abs(ms_ssim_np.MultiScaleSSIM_batch(x, x).item() - 1.0) < 1e-12
 
 
+def test_msssim_stream_kernel_matches_tiled_kernel(gpu_models, monkeypatch):
+    """row-streaming level kernel (11-tap levels without REFLECT padding) against the 16x16-tile kernel it replaces there:
+    identical per-pixel arithmetic, only the (double) partial-sum order differs.  Odd sizes: ragged last blocks in x and y."""
+    from imgcomp_cvpr_b200 import ms_ssim, ms_ssim_np
+    rng = np.random.RandomState(7)
+    for shape in ((2, 3, 200, 333), (1, 3, 176, 176), (1, 3, 305, 190)):
+        x = rng.randint(0, 256, shape).astype(np.uint8)
+        y = np.clip(x.astype(np.int32) + rng.randint(-12, 13, shape), 0, 255).astype(np.uint8)
+        x, y = _cuda(x), _cuda(y)
+        monkeypatch.delenv('IC_MSSSIM_TILED', raising=False)
+        v_np = ms_ssim_np.MultiScaleSSIM_batch(x, y).cpu().numpy()
+        v_tf = ms_ssim.MultiScaleSSIM(x.float(), y.float(), data_format='NCHW').item()
+        monkeypatch.setenv('IC_MSSSIM_TILED', '1')
+        w_np = ms_ssim_np.MultiScaleSSIM_batch(x, y).cpu().numpy()
+        w_tf = ms_ssim.MultiScaleSSIM(x.float(), y.float(), data_format='NCHW').item()
+        monkeypatch.delenv('IC_MSSSIM_TILED', raising=False)
+        np.testing.assert_allclose(v_np, w_np, rtol=0, atol=1e-13)
+        assert abs(v_tf - w_tf) < 1e-6
+
+
 def test_api_errors_mirror_reference(gpu_models, synth):
     from imgcomp_cvpr_b200 import autoencoder, probclass
     a, p, W = synth('cvpr/low')
