@@ -79,6 +79,11 @@ SIGNATURES = {
                                         c_void_p, c_size_t, c_void_p]),
     'ic_nn_conv3x3_tc_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'ic_nn_conv3x3_tc_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_tc_plan_create': (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    'ic_nn_tc_plan_destroy': (None, [c_void_p]),
+    'ic_nn_tc_plan_map': (c_int64, [c_void_p, c_void_p, c_int64]),
+    'ic_nn_tc_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    'ic_nn_tc_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_bn_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'ic_nn_bn_train_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -115,6 +120,7 @@ SIGNATURES = {
     'ic_loss_workspace_bytes': (c_size_t, []),
     'ic_masked_sums_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_mse_per_image_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    'ic_nn_distortion_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     'ic_debug_conv3x3': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_void_p, c_size_t, c_int, c_void_p]),
     'ic_launch_count': (c_longlong, []),

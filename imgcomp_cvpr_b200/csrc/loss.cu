@@ -68,6 +68,19 @@ __global__ void __launch_bounds__(RT) mse_per_image_kernel(const float* __restri
     if (threadIdx.x == 0) out[blockIdx.x] = (float)(s0[0] / (double)per_img);
 }
 
+// d/dx_out of the distortion the reference minimises when distortion_to_minimize is 'mse' or 'psnr' (code/train.py:381-397,
+// float32 branch of get_mse_per_img):  mse: mean_n mse_n -> 2 (x_out - x) / (N CHW);
+// psnr: K_psnr - mean_n 10 log10(255^2 / mse_n) -> (10 / (ln 10 N mse_n)) 2 (x_out - x) / CHW.   mse: per-image MSE (device).
+__global__ void dist_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x_out, const float* __restrict__ mse, int N,
+                                int64_t per_img, int psnr, float* __restrict__ d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * per_img) return;
+    const int n = (int)(i / per_img);
+    const double base = 2.0 / ((double)N * (double)per_img);
+    const double c = psnr ? base * 10.0 / (2.302585092994046 * (double)mse[n]) : base;
+    d[i] = (float)(c * ((double)x_out[i] - (double)x[i]));
+}
+
 }  // namespace
 }  // namespace ic
 
@@ -98,6 +111,17 @@ int ic_mse_per_image_fwd(const float* d_x, const float* d_x_out, int N, int64_t 
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
     mse_per_image_kernel<<<N, RT, 0, s>>>(d_x, d_x_out, per_image, cast_to_int, d_out);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+/* gradient of the 'mse' / 'psnr' distortion loss w.r.t. x_out (see dist_bwd_kernel); d_mse: ic_mse_per_image_fwd(..., 0, ...) */
+int ic_nn_distortion_bwd(const float* d_x, const float* d_x_out, const float* d_mse, int N, int64_t per_image, int psnr,
+                         float* d_dx_out, void* stream) {
+    IC_REQUIRE(d_x && d_x_out && d_mse && d_dx_out && N > 0 && per_image > 0, IC_ERR_INVALID, "ic_nn_distortion_bwd: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    dist_bwd_kernel<<<cdiv((int64_t)N * per_image, 256), 256, 0, s>>>(d_x, d_x_out, d_mse, N, per_image, psnr, d_dx_out);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

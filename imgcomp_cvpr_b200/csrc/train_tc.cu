@@ -58,7 +58,8 @@ struct ScaleArgs {
 };
 
 __global__ void __launch_bounds__(256) finalize_scales_kernel(ScaleArgs a, float* __restrict__ params, float* __restrict__ scale,
-                                                              float* __restrict__ shift, const float* __restrict__ kept = nullptr) {
+                                                              float* __restrict__ shift, const float* __restrict__ kept = nullptr,
+                                                              int both = 0) {
     __shared__ float red[256];
     __shared__ float sc[3];
     if (kept && threadIdx.x == 0) {        // forward-pass scales of the weights (tensor 0) and of x (tensor 2)
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) finalize_scales_kernel(ScaleArgs a, float
         __syncthreads();
     }
     if (scale && threadIdx.x < kC) {
-        scale[threadIdx.x] = 1.f / sc[0];                  // powers of two: exact
+        // powers of two: exact.  both: the conv writes float32 itself, so it also undoes the input's pre-scale
+        scale[threadIdx.x] = both ? (1.f / sc[0]) * (1.f / sc[1]) : 1.f / sc[0];
         shift[threadIdx.x] = 0.f;
     }
 }
@@ -323,6 +325,101 @@ int conv_planes(const __half* in, const float* d_w, int data_grad, const float* 
     return tc::launch_merge_to_nhwc(bo, N, H, W, kC, d_y, 1, s, unscale);
 }
 
+
+// ------------------------------------------------------------------ planned tensor-core convs (other layers of the step)
+// The stride-2 convs / transposed convs around the residual trunks (h2, h12, h13) and the context-model layers run on the
+// same tcgen05 kernels as at inference (conv_tc.cu: space-to-depth groups, depth-to-space columns, resident-weight
+// B-concatenated context model), forward AND data gradient:
+//     d/dx of conv2d(x, W, stride 2)            = conv2d_transpose(dy, W)        (the same filter array)
+//     d/dx of conv2d_transpose(x, W, stride 2)  = conv2d(dy, W, stride 2)        (channel roles swapped)
+//     d/dx of the VALID (2,3,3) conv3d          = the FULL correlation with flipped taps, filter depth 1 reading slice s-1
+// Weights change every step, so what is fixed per layer is the MAP packed element -> element of the trainer's weight
+// buffer.  It is derived from the host packers of conv_tc.cu themselves (no second copy of their layout rules): they
+// are run on two synthetic filters whose values are the base-2047 digits (+1) of the source index -- integers <= 2048
+// survive the power-of-two scaling and the fp16 hi/lo split exactly -- and the packed digits are read back.
+struct TcPlan {
+    int kind, data_grad;
+    int cin_pad, cout_pad;        // channel strides of the float32 NHWC input / output of THIS conv
+    int cout;                     // real output channels
+    int nout;                     // kernel columns
+    int w_elems;                  // elements of the trainer's weight buffer (maximum search)
+    int half;                     // packed layout: element i is a lo part iff (i % (2 half)) >= half, its hi part is i - half
+    size_t n_packed;
+    tc::GroupTable gt;
+    int* d_map;
+};
+
+enum { TCK_CONV5S2 = 0, TCK_TCONV5S2 = 1, TCK_TCONV5S2_IMG = 2, TCK_PC = 3 };
+
+__global__ void __launch_bounds__(256) pack_map_kernel(const float* __restrict__ w, const int* __restrict__ map, int total, int half,
+                                                       const float* __restrict__ sc, __half* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const bool is_lo = (i % (2 * half)) >= half;
+    const int src = map[is_lo ? i - half : i];
+    const float v = src >= 0 ? w[src] * sc[0] : 0.f;
+    const __half hi = __float2half_rn(v);
+    packed[i] = is_lo ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+
+template <class PackFn>
+int build_map_by_digits(size_t n_expected, const std::vector<int>& src_of, PackFn pack, std::vector<int>& map, tc::GroupTable& gt) {
+    std::vector<float> w(n_expected);
+    std::vector<__half> p[2];
+    float inv[2];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (size_t e = 0; e < n_expected; ++e) w[e] = (float)((pass == 0 ? src_of[e] % 2047 : src_of[e] / 2047) + 1);
+        int rc = pack(w.data(), p[pass], gt, &inv[pass]);
+        if (rc != IC_OK) return rc;
+    }
+    IC_REQUIRE(p[0].size() == p[1].size(), IC_ERR_STATE, "tc plan: packer sizes differ");
+    map.assign(p[0].size(), -1);
+    for (size_t i = 0; i < p[0].size(); ++i) {
+        const float a = __half2float(p[0][i]) * inv[0], b = __half2float(p[1][i]) * inv[1];
+        if (a == 0.f && b == 0.f) continue;
+        IC_REQUIRE(a >= 1.f && b >= 1.f && a == floorf(a) && b == floorf(b), IC_ERR_STATE, "tc plan: digit %g / %g at %zu", a, b, i);
+        map[i] = ((int)b - 1) * 2047 + ((int)a - 1);
+    }
+    return IC_OK;
+}
+
+// context-model layer, trainer weights [2][3][3][ci_pad][co_pad] ("other" mask: taps (1, fy > 1) and (1, 1, fx > 1) unused).
+// forward: input channels = ci, columns = co.  data gradient: input = dy (co channels), columns = ci, taps flipped.
+int build_pc_map(int ci, int co, int ci_pad, int co_pad, int nout, int data_grad, std::vector<int>& map, tc::GroupTable& gt) {
+    const int cin_e = data_grad ? co : ci, cout_e = data_grad ? ci : co;
+    IC_REQUIRE(cin_e <= 32 && cout_e <= nout, IC_ERR_UNSUPPORTED, "tc plan: context-model layer %d -> %d", cin_e, cout_e);
+    memset(&gt, 0, sizeof(gt));
+    gt.ngroups = 2;
+    const size_t plane_elems = (size_t)4 * nout * 8;
+    map.clear();
+    int nst = 0;
+    for (int g = 0; g < 2; ++g) {
+        const int fd = g;                           // group 0: filter depth 0 (9 taps), group 1: depth 1 (5 taps)
+        gt.img_off[g] = (uint8_t)(data_grad ? 1 - fd : fd);     // data gradient: depth 0 reads slice s, depth 1 slice s - 1
+        gt.chunk0[g] = 0;
+        int nt = 0;
+        for (int ty = 0; ty < 3; ++ty)
+            for (int tx = 0; tx < 3; ++tx) {
+                const int fy = data_grad ? 2 - ty : ty, fx = data_grad ? 2 - tx : tx;
+                if (fd == 1 && (fy > 1 || (fy == 1 && fx > 1))) continue;
+                gt.taps[g][nt++] = (uint8_t)(ty * 3 + tx);
+                const size_t base = map.size();
+                map.resize(base + 2 * plane_elems, -1);
+                for (int c = 0; c < cin_e; ++c)
+                    for (int o = 0; o < cout_e; ++o) {
+                        const int wc = data_grad ? o : c, wo = data_grad ? c : o;      // [ci][co] position in the filter
+                        const int src = ((((fd * 3 + fy) * 3 + fx) * ci_pad) + wc) * co_pad + wo;
+                        map[base + ((size_t)(c / 8) * 2 * nout + o) * 8 + (c % 8)] = src;
+                    }
+                ++nst;
+            }
+        gt.ntaps[g] = (uint8_t)nt;
+    }
+    gt.nstages = nst;
+    gt.eff_ksteps = nst * ((cin_e + 15) / 16);
+    return IC_OK;
+}
+
 }  // namespace
 
 }  // namespace ic
@@ -473,6 +570,240 @@ int ic_nn_conv3x3_tc_bwd_ex(const float* d_x, const float* d_dy, const float* d_
     }
     if (!d_dx) return IC_OK;
     return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s);
+}
+
+
+/* ---- planned tensor-core convs of the training step (see TcPlan above).  op_kind: the op of the forward graph
+ * (0: conv2d 5x5 stride 2 SAME, 1: conv2d_transpose 5x5 stride 2 SAME, 3: masked (2,3,3) VALID conv3d of the context model on
+ * a depth-major volume), data_grad: its data gradient instead.  Weights as the trainer stores them: [5][5][ceil4 Cin][ceil4
+ * Cout] in the orientation of the op, [2][3][3][ceil4 Cin][ceil4 Cout] for the context model.  Returns IC_ERR_UNSUPPORTED for
+ * shapes the tensor-core kernels do not cover (the caller keeps its FFMA path). */
+struct ic_tc_plan {
+    TcPlan p;
+};
+
+int ic_nn_tc_plan_create(int op_kind, int data_grad, int op_cin, int op_cout, ic_tc_plan_t** out) {
+    IC_REQUIRE(out, IC_ERR_INVALID, "ic_nn_tc_plan_create: NULL argument");
+    *out = nullptr;
+    IC_REQUIRE(op_cin > 0 && op_cout > 0 && (op_kind == 0 || op_kind == 1 || op_kind == 3), IC_ERR_INVALID, "ic_nn_tc_plan_create: bad op");
+    const int ci_pad = (int)align_up(op_cin, 4), co_pad = (int)align_up(op_cout, 4);
+    TcPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.data_grad = data_grad ? 1 : 0;
+    std::vector<int> map;
+    int rc = IC_OK;
+    if (op_kind == 3) {
+        pl.kind = TCK_PC;
+        const int cin_e = data_grad ? co_pad : ci_pad, cout_e = data_grad ? op_cin : op_cout;
+        if (cin_e % 8 != 0 || cin_e > 32 || cout_e > 32) return IC_ERR_UNSUPPORTED;
+        pl.nout = cout_e <= 16 ? 16 : 32;
+        pl.cin_pad = cin_e;
+        pl.cout_pad = data_grad ? ci_pad : co_pad;
+        pl.cout = pl.cout_pad;            // padded channels are written too (zero weights -> zeros)
+        pl.w_elems = 18 * ci_pad * co_pad;
+        pl.half = pl.nout * 8;
+        rc = build_pc_map(op_cin, op_cout, ci_pad, co_pad, pl.nout, pl.data_grad, map, pl.gt);
+        if (rc != IC_OK) return rc;
+    } else {
+        // effective conv: a strided conv (forward of conv2d, data gradient of conv2d_transpose) or a transposed one
+        const bool eff_strided = (op_kind == 0) != (data_grad != 0);
+        const int cin_e = data_grad ? op_cout : op_cin, cout_e = data_grad ? op_cin : op_cout;
+        pl.cin_pad = data_grad ? co_pad : ci_pad;
+        pl.cout_pad = data_grad ? ci_pad : co_pad;
+        pl.cout = cout_e;
+        pl.w_elems = 25 * ci_pad * co_pad;
+        if (cin_e % 32 != 0 || pl.cin_pad != cin_e) return IC_ERR_UNSUPPORTED;
+        std::vector<int> src((size_t)25 * cin_e * cout_e);
+        if (eff_strided) {
+            if (cin_e % 64 != 0 || cout_e != 128) return IC_ERR_UNSUPPORTED;
+            pl.kind = TCK_CONV5S2;
+            pl.nout = 128;
+            for (int t = 0; t < 25; ++t)
+                for (int i = 0; i < cin_e; ++i)
+                    for (int o = 0; o < cout_e; ++o)      // expected HWIO [t][i][o]
+                        src[((size_t)t * cin_e + i) * cout_e + o] = data_grad ? (t * ci_pad + o) * co_pad + i : (t * ci_pad + i) * co_pad + o;
+            rc = build_map_by_digits(src.size(), src, [&](const float* w, std::vector<__half>& packed, tc::GroupTable& gt, float* inv) {
+                return tc::pack_weights(w, 5, 2, cin_e, cout_e, pl.nout, packed, gt, inv);
+            }, map, pl.gt);
+        } else {
+            if (!(cout_e == 64 || cout_e == 3)) return IC_ERR_UNSUPPORTED;
+            pl.kind = cout_e == 3 ? TCK_TCONV5S2_IMG : TCK_TCONV5S2;
+            pl.nout = cout_e == 3 ? 16 : 256;
+            for (int t = 0; t < 25; ++t)
+                for (int o = 0; o < cout_e; ++o)
+                    for (int i = 0; i < cin_e; ++i)       // expected [t][cout][cin] (TF conv2d_transpose filter)
+                        src[((size_t)t * cout_e + o) * cin_e + i] = data_grad ? (t * ci_pad + o) * co_pad + i : (t * ci_pad + i) * co_pad + o;
+            const int all[4] = {0, 1, 2, 3};
+            rc = build_map_by_digits(src.size(), src, [&](const float* w, std::vector<__half>& packed, tc::GroupTable& gt, float* inv) {
+                return tc::pack_weights_tconv(w, 5, cin_e, cout_e, all, 4, pl.nout, packed, gt, inv);
+            }, map, pl.gt);
+        }
+        if (rc != IC_OK) return rc;
+        pl.half = 4 * pl.nout * 8;
+    }
+    pl.n_packed = map.size();
+    IC_CHECK_CUDA(cudaMalloc((void**)&pl.d_map, map.size() * sizeof(int)));
+    IC_CHECK_CUDA(cudaMemcpy(pl.d_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ic_tc_plan* h = new ic_tc_plan;
+    h->p = pl;
+    *out = h;
+    return IC_OK;
+}
+
+void ic_nn_tc_plan_destroy(ic_tc_plan_t* plan) {
+    if (!plan) return;
+    cudaFree(plan->p.d_map);
+    delete plan;
+}
+
+/* host copy of the pack map (tests): n_packed entries, -1 = zero */
+int64_t ic_nn_tc_plan_map(const ic_tc_plan_t* plan, int* h_map_out, int64_t capacity) {
+    if (!plan) return -1;
+    if (h_map_out && capacity >= (int64_t)plan->p.n_packed)
+        if (cudaMemcpy(h_map_out, plan->p.d_map, plan->p.n_packed * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)plan->p.n_packed;
+}
+
+namespace {
+struct PlanGeo {
+    int64_t in_imgs, out_imgs;
+    int Hi, Wi, Ho, Wo;
+};
+PlanGeo plan_geo(const TcPlan& p, int D, int N, int H, int W) {
+    PlanGeo g;
+    if (p.kind == TCK_PC) {
+        g.in_imgs = (int64_t)D * N;
+        g.out_imgs = (int64_t)(p.data_grad ? D + 1 : D - 1) * N;
+        g.Hi = H; g.Wi = W;
+        g.Ho = p.data_grad ? H + 2 : H - 2;
+        g.Wo = p.data_grad ? W + 2 : W - 2;
+    } else {
+        g.in_imgs = g.out_imgs = N;
+        g.Hi = H; g.Wi = W;
+        g.Ho = p.kind == TCK_CONV5S2 ? H / 2 : 2 * H;
+        g.Wo = p.kind == TCK_CONV5S2 ? W / 2 : 2 * W;
+    }
+    return g;
+}
+}  // namespace
+
+size_t ic_nn_tc_plan_workspace_bytes(const ic_tc_plan_t* plan, int D, int N, int H, int W) {
+    if (!plan || N <= 0 || H <= 0 || W <= 0) return 0;
+    const TcPlan& p = plan->p;
+    const PlanGeo g = plan_geo(p, D, N, H, W);
+    if (g.out_imgs <= 0 || g.Ho <= 0 || g.Wo <= 0) return 0;
+    size_t b = align_up((size_t)g.in_imgs * g.Hi * g.Wi * p.cin_pad * 2 * sizeof(__half), 256);
+    if (p.kind == TCK_CONV5S2 || p.kind == TCK_TCONV5S2) b += align_up((size_t)g.out_imgs * g.Ho * g.Wo * p.cout * 2 * sizeof(__half), 256);
+    if (p.kind == TCK_TCONV5S2_IMG) b += align_up((size_t)g.out_imgs * g.Ho * g.Wo * 3 * sizeof(float), 256);
+    return b + align_up(p.n_packed * sizeof(__half), 256) + 3 * kMaxBlocks * sizeof(float) + 8192;
+}
+
+/* d_x: float32 NHWC input of THIS conv (the output gradient when the plan is a data gradient), dims (N, H, W, C) or, context
+ * model, (D, N, H, W, C) depth-major; d_y: its float32 NHWC output (context model forward: (D-1, N, H-2, W-2, C'), data
+ * gradient: (D+1, N, H+2, W+2, C')). */
+int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d_w, int D, int N, int H, int W, float* d_y,
+                      void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(plan && d_x && d_w && d_y && d_workspace, IC_ERR_INVALID, "ic_nn_tc_plan_run: NULL argument");
+    const TcPlan& p = plan->p;
+    IC_REQUIRE(N > 0 && H > 0 && W > 0 && (p.kind != TCK_PC || D > (p.data_grad ? 0 : 1)), IC_ERR_INVALID, "ic_nn_tc_plan_run: bad shape");
+    IC_REQUIRE(p.kind != TCK_CONV5S2 || (H % 2 == 0 && W % 2 == 0), IC_ERR_INVALID, "ic_nn_tc_plan_run: odd size for a stride-2 conv");
+    IC_REQUIRE(workspace_bytes >= ic_nn_tc_plan_workspace_bytes(plan, D, N, H, W), IC_ERR_WORKSPACE, "ic_nn_tc_plan_run: workspace too small");
+    const PlanGeo g = plan_geo(p, D, N, H, W);
+    IC_REQUIRE(g.Ho > 0 && g.Wo > 0 && g.out_imgs > 0, IC_ERR_INVALID, "ic_nn_tc_plan_run: empty output");
+    cudaStream_t s = (cudaStream_t)stream;
+    Arena ar(d_workspace, workspace_bytes);
+    const size_t in_elems = (size_t)g.in_imgs * g.Hi * g.Wi * p.cin_pad;
+    __half* bi = ar.get<__half>(2 * in_elems);
+    __half* bo = nullptr;
+    float* img = nullptr;
+    if (p.kind == TCK_CONV5S2 || p.kind == TCK_TCONV5S2) bo = ar.get<__half>((size_t)g.out_imgs * g.Ho * g.Wo * p.cout * 2);
+    if (p.kind == TCK_TCONV5S2_IMG) img = ar.get<float>((size_t)g.out_imgs * g.Ho * g.Wo * 3);
+    __half* wp = ar.get<__half>(p.n_packed);
+    float* scale = ar.get<float>(kC);
+    float* shift = ar.get<float>(kC);
+    float* params = ar.get<float>(8);
+    float* pw = ar.get<float>(kMaxBlocks);
+    float* px = ar.get<float>(kMaxBlocks);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_tc_plan_run: workspace too small");
+    const bool f32_out = p.kind == TCK_PC || p.kind == TCK_TCONV5S2_IMG;
+    ScaleArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.ntens = 2;
+    sa.partial[0] = pw;
+    sa.partial[1] = px;
+    int rc;
+    {
+        ProfScope ps(IC_PROF_ELEMENTWISE, s, 4);
+        rc = maxabs(d_w, p.w_elems, pw, &sa.count[0], s);
+        if (rc == IC_OK) rc = maxabs(d_x, (int64_t)in_elems, px, &sa.count[1], s);
+        if (rc != IC_OK) return rc;
+        finalize_scales_kernel<<<1, 256, 0, s>>>(sa, params, scale, shift, nullptr, f32_out ? 1 : 0);
+        IC_CHECK_LAUNCH();
+        pack_map_kernel<<<cdiv((int64_t)p.n_packed, 256), 256, 0, s>>>(d_w, p.d_map, (int)p.n_packed, p.half, params, wp);
+        IC_CHECK_LAUNCH();
+    }
+    // float32 NHWC (x sx) -> fp16 hi/lo planes; the strided conv reads its input in space-to-depth form
+    rc = tc::launch_split_from_nhwc(d_x, (int)g.in_imgs, g.Hi, g.Wi, p.cin_pad, p.kind == TCK_CONV5S2 ? 1 : 0, bi, 1, s, params + 1);
+    if (rc != IC_OK) return rc;
+    tc::ConvTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = bi;
+    a.weights = wp;
+    a.groups = &p.gt;
+    a.scale = scale;
+    a.shift = shift;
+    a.N = (int)g.out_imgs;
+    a.relu = 0;
+    a.cout = p.cout;
+    a.nout = p.nout;
+    a.img_mul = 1;
+    a.head = -1;
+    a.cpg = 4;
+    a.exact = 1;
+    a.prof_class = p.kind == TCK_PC ? IC_PROF_PROBCLASS : IC_PROF_CONV_OTHER;
+    if (p.kind == TCK_CONV5S2) {
+        a.Nimg = N;
+        a.in_chunks = 4 * p.cin_pad / 8;
+        a.Hin = H / 2;
+        a.Win = W / 2;
+        a.H = g.Ho;
+        a.W = g.Wo;
+        a.halo0 = -1;
+        a.out = bo;
+    } else if (p.kind == TCK_PC) {
+        a.Nimg = (int)g.in_imgs;
+        a.in_chunks = p.cin_pad / 8;
+        a.Hin = H;
+        a.Win = W;
+        a.H = g.Ho;
+        a.W = g.Wo;
+        a.halo0 = p.data_grad ? -2 : 0;
+        a.img_off_mul = N;
+        a.img_base = p.data_grad ? -N : 0;
+        a.pc_f32 = 1;
+        a.out_f32 = d_y;
+    } else {
+        a.Nimg = N;
+        a.in_chunks = p.cin_pad / 8;
+        a.Hin = H;
+        a.Win = W;
+        a.H = H;                 // depth-to-space: the tile grid is the INPUT grid, columns = (output phase, channel)
+        a.W = W;
+        a.halo0 = -1;
+        if (p.kind == TCK_TCONV5S2) {
+            a.out = bo;
+            a.d2s_cch = p.cout / 8;
+            a.d2s_ph0 = 0;
+        } else {
+            a.out_f32 = img;     // NCHW (N, 3, 2H, 2W), no denormalisation
+            a.denorm = 0;
+        }
+    }
+    rc = tc::launch_conv_tc(a, s);
+    if (rc != IC_OK) return rc;
+    if (bo) return tc::launch_merge_to_nhwc(bo, (int)g.out_imgs, g.Ho, g.Wo, p.cout, d_y, 1, s, params + 5);
+    if (img) return ic_nn_nchw_to_nhwc(img, N, 3, p.cout_pad, (int64_t)g.Ho * g.Wo, d_y, stream);
+    return IC_OK;
 }
 
 }  // extern "C"

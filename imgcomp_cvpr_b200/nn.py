@@ -113,6 +113,56 @@ def conv3x3_tc_bwd(x, dy, w, need_dx=True, dw_out=None, cache=None):
     return dx, dw
 
 
+class TcPlan(object):
+    """One conv of the training step on the tcgen05 kernels (ic_nn_tc_plan_*): op_kind 'conv5s2' (slim.conv2d 5x5 stride 2),
+    'tconv5s2' (slim.conv2d_transpose 5x5 stride 2) or 'pc' (masked (2,3,3) conv3d, depth-major volume); data_grad selects
+    the gradient w.r.t. the op's input.  TcPlan.get(...) -> None when no tensor-core kernel covers the shape."""
+    KINDS = {'conv5s2': 0, 'tconv5s2': 1, 'pc': 3}
+    _cache = {}
+
+    def __init__(self, handle, kind, data_grad, cin, cout):
+        self.h, self.kind, self.data_grad, self.cin, self.cout = handle, kind, bool(data_grad), cin, cout
+
+    @classmethod
+    def get(cls, kind, data_grad, cin, cout):
+        key = (kind, bool(data_grad), cin, cout)
+        if key not in cls._cache:
+            import ctypes
+            h = ctypes.c_void_p()
+            rc = _lib.lib().ic_nn_tc_plan_create(cls.KINDS[kind], int(bool(data_grad)), cin, cout, ctypes.byref(h))
+            if rc == -4:        # IC_ERR_UNSUPPORTED
+                cls._cache[key] = None
+            else:
+                _lib.check(rc)
+                cls._cache[key] = cls(h, kind, data_grad, cin, cout)
+        return cls._cache[key]
+
+    def out_shape(self, x_shape):
+        c4 = lambda n: (n + 3) // 4 * 4
+        co = c4(self.cin if self.data_grad else self.cout)
+        if self.kind == 'pc':
+            D, N, H, W, _ = x_shape
+            return (D + 1, N, H + 2, W + 2, co) if self.data_grad else (D - 1, N, H - 2, W - 2, co)
+        N, H, W, _ = x_shape
+        strided = (self.kind == 'conv5s2') != self.data_grad
+        return (N, H // 2, W // 2, co) if strided else (N, 2 * H, 2 * W, co)
+
+    def run(self, x, w, out=None):
+        """x: float32 NHWC input of this conv (dy for a data gradient); w: the op's weight buffer -> float32 NHWC output"""
+        if self.kind == 'pc':
+            D, N, H, W, _ = x.shape
+        else:
+            (N, H, W, _), D = x.shape, 1
+        oshape = self.out_shape(x.shape)
+        y = torch.empty(oshape, dtype=torch.float32, device=x.device) if out is None else _f32(out)
+        assert tuple(y.shape) == tuple(oshape), (tuple(y.shape), oshape)
+        L = _lib.lib()
+        ws = _workspace(L.ic_nn_tc_plan_workspace_bytes(self.h, D, N, H, W))
+        _lib.check(L.ic_nn_tc_plan_run(self.h, _lib.ptr(_f32(x)), _lib.ptr(_f32(w)), D, N, H, W, _lib.ptr(y), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr()))
+        return y
+
+
 def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None):
     """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics."""
     C = x.shape[-1]
@@ -312,3 +362,15 @@ def msssim_tf_bwd(img1, img2, grad_out):
     _lib.check(_lib.lib().ic_msssim_tf_bwd(_lib.ptr(_f32(img1)), _lib.ptr(_f32(img2)), N, H, W, float(grad_out), _lib.ptr(d),
                                           _lib.ptr(val), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return d, val
+
+
+def distortion_bwd(x, x_out, psnr=False):
+    """distortion_to_minimize 'mse' / 'psnr' (code/train.py:381-397, float32 branch): -> (d loss / d x_out, per-image MSE)"""
+    N = x.shape[0]
+    per = x[0].numel()
+    mse = torch.empty(N, dtype=torch.float32, device=x.device)
+    d = torch.empty_like(x_out)
+    L = _lib.lib()
+    _lib.check(L.ic_mse_per_image_fwd(_lib.ptr(_f32(x)), _lib.ptr(_f32(x_out)), N, per, 0, _lib.ptr(mse), _lib.stream_ptr()))
+    _lib.check(L.ic_nn_distortion_bwd(_lib.ptr(x), _lib.ptr(x_out), _lib.ptr(mse), N, per, int(bool(psnr)), _lib.ptr(d), _lib.stream_ptr()))
+    return d, mse

@@ -14,6 +14,7 @@ closures in the order of the reference graph, parameters / gradients / Adam mome
 (one Adam launch per group).  torch tensors are containers only.  No CPU fallback.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -182,8 +183,10 @@ class Trainer(object):
         self.groups['ae_centers'].add('autoencoder/encoder/centers', np.asarray(weights['autoencoder/encoder/centers'], np.float32))
         first, other = _pc_masks()
         cin = 1
+        self._pc_chans = {}
         for i, (s, mk) in enumerate(PC_LAYERS):
             cout = self.k if i < 3 else self.L
+            self._pc_chans[s] = (cin, cout)
             w = np.asarray(weights[s + '/weights'], np.float32)
             assert w.shape == (2, 3, 3, cin, cout), (s, w.shape)
             wp = np.zeros((2, 3, 3, _ceil4(cin), _ceil4(cout)), np.float32)
@@ -294,11 +297,23 @@ class Trainer(object):
         return self._export('g')
 
     # ------------------------------------------------------------------ ops (forward + recorded backward)
-    def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None):
+    def _tc_plans(self, kind, cin, cout):
+        """(forward plan, data-gradient plan) of a non-3x3 conv on the tcgen05 kernels, None where no kernel covers the shape
+        or outside mode 'exact' (IC_TRAIN_TC_EXTRA=0 keeps these layers on the FFMA kernels: A/B in tests)"""
+        if self.mode != 'exact' or os.environ.get('IC_TRAIN_TC_EXTRA', '1') == '0':
+            return None, None
+        return nn.TcPlan.get(kind, False, cin, cout), nn.TcPlan.get(kind, True, cin, cout)
+
+    def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None, chans=None):
         tc = (self.mode == 'exact' and tuple(w.shape) == (3, 3, 128, 128) and stride == 1 and not transposed and not valid)
+        plan_f = plan_d = None
+        if not tc and chans is not None and w.shape[0] == 5 and stride == 2 and not valid:
+            plan_f, plan_d = self._tc_plans('tconv5s2' if transposed else 'conv5s2', *chans)
         cache = None
         if tc and self.tape is not None:        # keep the input's fp16 planes and the scales for the filter gradient
             y, cache = nn.conv3x3_tc(x, w, keep=True)
+        elif plan_f is not None:
+            y = plan_f.run(x, w)
         else:
             y = nn.conv3x3_tc(x, w) if tc else nn.conv2d_fwd(x, w, stride, transposed, valid)
         if self.tape is not None:
@@ -317,7 +332,8 @@ class Trainer(object):
                 if mask is not None:
                     nn.mul(gw, mask, out=gw)
                 if need_dx:
-                    tape.acc(x, nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid), owned=True)
+                    dx = plan_d.run(dy, w) if plan_d is not None else nn.conv2d_bwd_data(dy, w, x.shape, stride, transposed, valid)
+                    tape.acc(x, dx, owned=True)
             tape.add(bwd)
         return y
 
@@ -351,7 +367,7 @@ class Trainer(object):
     def _slim_conv(self, x, scope, relu, res1=None, res2=None, need_dx=True):
         """slim.conv2d / conv2d_transpose under _batch_norm_scope: conv (no bias) -> BN -> activation (+ fused adds)"""
         y = self._conv(x, self._w(scope + '/weights'), self._g(scope + '/weights'), self._stride[scope], self._tr[scope],
-                       need_dx=need_dx)
+                       need_dx=need_dx, chans=self._shape[scope][1:])
         return self._bn(y, scope, relu, res1, res2)
 
     def _res_stack(self, net, prefix, tag, final_scope):
@@ -403,9 +419,14 @@ class Trainer(object):
         weff = nn.mul(w, mask)
         D, N, H, W, Ci = x.shape
         xa, xb = x[:D - 1].reshape(-1, H, W, Ci), x[1:].reshape(-1, H, W, Ci)
-        y = nn.conv2d_fwd(xa, weff[0], valid=True)
-        y = nn.axpby(1.0, y, 1.0, nn.conv2d_fwd(xb, weff[1], valid=True), out=y)
-        y = y.view(D - 1, N, H - 2, W - 2, w.shape[-1])
+        # layers 1-3 ("other" mask, 24 input channels): both depth passes as ONE tcgen05 conv, forward and data gradient
+        plan_f, plan_d = self._tc_plans('pc', *self._pc_chans[scope]) if scope != PC_LAYERS[0][0] else (None, None)
+        if plan_f is not None:
+            y = plan_f.run(x, weff)
+        else:
+            y = nn.conv2d_fwd(xa, weff[0], valid=True)
+            y = nn.axpby(1.0, y, 1.0, nn.conv2d_fwd(xb, weff[1], valid=True), out=y)
+            y = y.view(D - 1, N, H - 2, W - 2, w.shape[-1])
         if self.tape is not None:
             tape = self.tape
 
@@ -417,7 +438,9 @@ class Trainer(object):
                 nn.conv2d_bwd_filter(xa, dy4, weff[0].shape, valid=True, out=gw[0])
                 nn.conv2d_bwd_filter(xb, dy4, weff[1].shape, valid=True, out=gw[1])
                 nn.mul(gw, mask, out=gw)
-                if need_dx:
+                if need_dx and plan_d is not None:
+                    tape.acc(x, plan_d.run(dy.contiguous(), weff), owned=True)
+                elif need_dx:
                     dx = torch.empty_like(x)
                     nn.conv2d_bwd_data(dy4, weff[0], xa.shape, valid=True, out=dx[:D - 1].reshape(-1, H, W, Ci))
                     db = nn.conv2d_bwd_data(dy4, weff[1], xb.shape, valid=True).view(D - 1, N, H, W, Ci)
@@ -513,9 +536,10 @@ class Trainer(object):
         masked_sums(bc, hm, bc.numel(), sums)
         for i, g in enumerate((self.groups['ae_w'], self.groups['pc_w'], self.groups['ae_centers'])):
             masked_sums(g.w, g.w, g.w.numel(), sums[2 + 2 * i:])
-        if cfg.distortion_to_minimize != 'ms_ssim':
-            raise NotImplementedError('only distortion_to_minimize = ms_ssim (the published configs) has a backward kernel')
-        d_xout, self._val = nn.msssim_tf_bwd(xf, x_out, -float(cfg.K_ms_ssim))    # d/dx_out of K (1 - MS-SSIM)
+        if cfg.distortion_to_minimize == 'ms_ssim':
+            d_xout, self._val = nn.msssim_tf_bwd(xf, x_out, -float(cfg.K_ms_ssim))    # d/dx_out of K (1 - MS-SSIM)
+        else:       # 'mse' / 'psnr' (code/train.py:381-397): self._val = per-image float MSE
+            d_xout, self._val = nn.distortion_bwd(xf, x_out, psnr=cfg.distortion_to_minimize == 'psnr')
         tensors = dict(bc=bc, heatmap=hm, x_out=x_out, symbols=enc['symbols'], qbar=enc['qbar'], z=enc['z'])
         if not backward:
             return tensors
@@ -543,12 +567,17 @@ class Trainer(object):
         cfg = self.ae_config
         N, _, H, W = shape
         host = self._sums.cpu().tolist()
-        msssim = float(self._val.item())
+        if cfg.distortion_to_minimize == 'ms_ssim':
+            msssim = float(self._val.item())
+            d_loss = cfg.K_ms_ssim * (1.0 - msssim)
+        else:
+            msssim = None
+            mse = self._val.double().cpu().numpy()
+            d_loss = float(mse.mean()) if cfg.distortion_to_minimize == 'mse' else cfg.K_psnr - float((10 * np.log10(255.0 * 255.0 / mse)).mean())
         H_real = host[0] / n_symbols
         H_mask = host[1] / n_symbols if self.heatmap else H_real
         H_soft = 0.5 * (H_mask + H_real)
         pc_loss = cfg.beta * max(H_soft - cfg.H_target, 0.0)
-        d_loss = cfg.K_ms_ssim * (1.0 - msssim)
         reg_enc_dec = cfg.regularization_factor * 0.5 * host[3]
         if cfg.regularization_factor_centers != 0:
             reg_enc_dec += cfg.regularization_factor_centers * 0.5 * host[7]

@@ -233,6 +233,23 @@ int ic_nn_conv3x3_tc_bwd(const float* d_x, const float* d_dy, const float* d_w, 
 int ic_nn_conv3x3_tc_bwd_ex(const float* d_x, const float* d_dy, const float* d_w, int N, int H, int W, float* d_dx,
                             float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
                             size_t workspace_bytes, void* stream);
+/* The other convolutions of the training step on the tcgen05 kernels (EXACT arithmetic), forward and data gradient, with
+ * the weights re-packed on the device per call through a per-layer index map (built once: a "plan"):
+ *   op_kind 0  slim.conv2d 5x5 stride 2 SAME        (code/autoencoder.py:223 h2)
+ *   op_kind 1  slim.conv2d_transpose 5x5 stride 2   (code/autoencoder.py:264-265 h12, h13)
+ *   op_kind 3  masked (2,3,3) VALID conv3d          (code/probclass.py:227-261; "other" mask, depth-major volume (D,N,H,W,C))
+ * data_grad = 1 plans the gradient w.r.t. the op's input.  d_w is the op's float32 weight array as ic_nn_conv2d_* take it
+ * ([5][5][ceil4 Cin][ceil4 Cout], [2][3][3][ceil4 Cin][ceil4 Cout]).  ic_nn_tc_plan_create returns IC_ERR_UNSUPPORTED for
+ * shapes without a tensor-core kernel (h1, to_bn, from_bn, the context model's first layer): use ic_nn_conv2d_* there.
+ * ic_nn_tc_plan_run: D, N, H, W are the dimensions of d_x (D only for op_kind 3); d_y is (N, H/2, W/2, C') / (N, 2H, 2W, C')
+ * / (D-1, N, H-2, W-2, C') forward, (D+1, N, H+2, W+2, C') context-model data gradient. */
+typedef struct ic_tc_plan ic_tc_plan_t;
+int ic_nn_tc_plan_create(int op_kind, int data_grad, int op_cin, int op_cout, ic_tc_plan_t** out);
+void ic_nn_tc_plan_destroy(ic_tc_plan_t* plan);
+int64_t ic_nn_tc_plan_map(const ic_tc_plan_t* plan, int* h_map_out, int64_t capacity);
+size_t ic_nn_tc_plan_workspace_bytes(const ic_tc_plan_t* plan, int D, int N, int H, int W);
+int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d_w, int D, int N, int H, int W, float* d_y,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
 /* slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125): batch mean / biased variance over
  * the M = N*H*W rows, out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2); d_mean / d_invstd are
  * kept for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update with
@@ -340,6 +357,10 @@ int ic_masked_sums_fwd(const float* d_bc, const float* d_heatmap, int64_t n, dou
  * NCHW batches, optionally after the int32 cast (truncation) the reference applies outside of training. */
 int ic_mse_per_image_fwd(const float* d_x, const float* d_x_out, int N, int64_t per_image, int cast_to_int,
                          float* d_out, void* stream);
+/* Gradient w.r.t. x_out of the distortion term when config.distortion_to_minimize is 'mse' (psnr = 0) or 'psnr' (psnr = 1)
+ * (code/train.py:381-397): d_mse = ic_mse_per_image_fwd(x, x_out, ..., cast_to_int = 0) on the device, N floats. */
+int ic_nn_distortion_bwd(const float* d_x, const float* d_x_out, const float* d_mse, int N, int64_t per_image, int psnr,
+                         float* d_dx_out, void* stream);
 
 /* ------------------------------------------------------------- test hooks
  * One fused 3x3 128->128 residual conv (conv + BN + ReLU + residual adds) of the

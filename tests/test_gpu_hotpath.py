@@ -190,7 +190,7 @@ def test_msssim_stream_kernel_matches_tiled_kernel(gpu_models, monkeypatch):
     identical per-pixel arithmetic, only the (double) partial-sum order differs.  Odd sizes: ragged last blocks in x and y."""
     from imgcomp_cvpr_b200 import ms_ssim, ms_ssim_np
     rng = np.random.RandomState(7)
-    for shape in ((2, 3, 200, 333), (1, 3, 176, 176), (1, 3, 305, 190)):
+    for shape in ((4, 3, 200, 333), (1, 3, 176, 176), (3, 3, 305, 190), (2, 3, 400, 520)):
         x = rng.randint(0, 256, shape).astype(np.uint8)
         y = np.clip(x.astype(np.int32) + rng.randint(-12, 13, shape), 0, 255).astype(np.uint8)
         x, y = _cuda(x), _cuda(y)

@@ -195,3 +195,111 @@ def test_adam_and_axpby():
     np.testing.assert_allclose(wg.cpu().numpy(), wr, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(nn.axpby(2.0, _cuda(w), -1.0, _cuda(g)).cpu().numpy(), 2 * w - g, rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(nn.mul(_cuda(w), _cuda(g)).cpu().numpy(), w * g, rtol=1e-6)
+
+
+# ---- planned tensor-core convs (ic_nn_tc_plan_*): forward and data gradient against float64 autograd
+def _rel(a, ref):
+    return float(np.abs(a - ref).max() / np.abs(ref).max())
+
+
+@pytest.mark.parametrize('case', [
+    # op kind, N, H, W, Cin, Cout, gradient scale
+    ('conv5s2', 2, 24, 40, 64, 128, 1.0),        # h2
+    ('conv5s2', 1, 16, 16, 64, 128, 3e-5),       # tiny gradients: the per-tensor power-of-two pre-scale keeps float32-class precision
+    ('tconv5s2', 2, 12, 20, 128, 64, 1.0),       # h12
+    ('tconv5s2', 3, 10, 8, 128, 64, 2e-4),
+    ('tconv5s2', 2, 20, 36, 64, 3, 1.0),         # h13 (forward only: its data gradient has 3 input channels)
+])
+def test_tc_plan_strided_convs(case):
+    from imgcomp_cvpr_b200 import nn
+    kind, N, H, W, Cin, Cout, gs = case
+    tr = kind == 'tconv5s2'
+    x = _rnd((N, Cin, H, W), 11)
+    w = _rnd((5, 5, Cin, Cout), 12, 0.05)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64)
+    y = T.conv2d_transpose_same(xt, wt.permute(0, 1, 3, 2), 2) if tr else T.conv2d_same(xt, wt, 2)
+    dy = _rnd(tuple(y.shape), 13, gs)
+    (y * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    c4 = lambda n: (n + 3) // 4 * 4
+    wp = np.zeros((5, 5, c4(Cin), c4(Cout)), np.float32)
+    wp[:, :, :Cin, :Cout] = w
+    xg, wg = _cuda(x.transpose(0, 2, 3, 1)), _cuda(wp)
+    pf, pd = nn.TcPlan.get(kind, False, Cin, Cout), nn.TcPlan.get(kind, True, Cin, Cout)
+    assert pf is not None
+    yg = pf.run(xg, wg).cpu().numpy()
+    ref = _nhwc(y)
+    assert yg.shape[-1] == c4(Cout)
+    err = _rel(yg[..., :Cout], ref)
+    print('tc plan %s fwd %d->%d: rel err %.2e' % (kind, Cin, Cout, err))
+    assert err < 2e-5
+    assert not yg[..., Cout:].any()
+    if Cout == 3:
+        assert pd is None
+        return
+    assert pd is not None
+    dyp = np.zeros(tuple(ref.shape[:3]) + (c4(Cout),), np.float32)
+    dyp[..., :Cout] = dy.transpose(0, 2, 3, 1)
+    dx = pd.run(_cuda(dyp), wg).cpu().numpy()
+    refd = _nhwc(xt.grad)
+    err = _rel(dx[..., :Cin], refd)
+    print('tc plan %s dgrad: rel err %.2e (gradient scale %g)' % (kind, err, gs))
+    assert err < 2e-5
+    # and against the FFMA kernels the trainer used before
+    y32 = nn.conv2d_fwd(xg, wg, 2, tr).cpu().numpy()
+    assert _rel(yg, y32) < 2e-5
+
+
+@pytest.mark.parametrize('case', [
+    # D, N, H, W, Cin, Cout, gradient scale
+    (7, 3, 13, 11, 24, 24, 1.0),
+    (5, 2, 30, 21, 24, 24, 1e-5),
+    (6, 2, 12, 19, 24, 6, 1.0),
+    (2, 1, 3, 3, 24, 6, 1.0),                    # one output voxel per image
+])
+def test_tc_plan_context_model_layers(case):
+    """masked (2,3,3) VALID conv3d on the depth-major volume, forward + data gradient, against float64 autograd of
+    F.conv3d with the "other" mask (code/probclass.py:164-176)"""
+    from imgcomp_cvpr_b200 import nn
+    D, N, H, W, Ci, Co, gs = case
+    c4 = lambda n: (n + 3) // 4 * 4
+    mask = np.ones((2, 3, 3), np.float32)
+    mask[1, 1, 2] = 0
+    mask[1, 2, :] = 0
+    x = _rnd((D, N, H, W, Ci), 21)
+    w = _rnd((2, 3, 3, Ci, Co), 22, 0.1)                     # raw weights: masked entries are NOT zero here
+    xt = torch.tensor(x.transpose(1, 4, 0, 2, 3), dtype=torch.float64, requires_grad=True)          # N, C, D, H, W
+    wt = torch.tensor((w * mask[..., None, None]).transpose(4, 3, 0, 1, 2), dtype=torch.float64)    # Co, Ci, 2, 3, 3
+    y = F.conv3d(xt, wt)
+    dy = _rnd(tuple(y.shape), 23, gs)
+    (y * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    wp = np.zeros((2, 3, 3, c4(Ci), c4(Co)), np.float32)
+    wp[..., :Ci, :Co] = w * mask[..., None, None]
+    pf, pd = nn.TcPlan.get('pc', False, Ci, Co), nn.TcPlan.get('pc', True, Ci, Co)
+    assert pf is not None and pd is not None
+    yg = pf.run(_cuda(x), _cuda(wp)).cpu().numpy()                                                   # D-1, N, H-2, W-2, c4(Co)
+    ref = y.detach().numpy().transpose(2, 0, 3, 4, 1)
+    assert yg.shape == ref.shape[:4] + (c4(Co),)
+    err = _rel(yg[..., :Co], ref)
+    print('tc plan pc fwd %d->%d: rel err %.2e' % (Ci, Co, err))
+    assert err < 2e-5
+    assert not yg[..., Co:].any()
+    dyp = np.zeros(ref.shape[:4] + (c4(Co),), np.float32)
+    dyp[..., :Co] = dy.transpose(2, 0, 3, 4, 1)
+    dx = pd.run(_cuda(dyp), _cuda(wp)).cpu().numpy()
+    refd = xt.grad.numpy().transpose(2, 0, 3, 4, 1)
+    assert dx.shape == refd.shape
+    err = _rel(dx, refd)
+    print('tc plan pc dgrad: rel err %.2e (gradient scale %g)' % (err, gs))
+    assert err < 2e-5
+    # unmasked raw weights give the same result: the plan never reads the masked taps
+    wraw = np.zeros_like(wp)
+    wraw[..., :Ci, :Co] = w
+    assert np.array_equal(pf.run(_cuda(x), _cuda(wraw)).cpu().numpy(), yg) or _rel(pf.run(_cuda(x), _cuda(wraw)).cpu().numpy(), yg) < 1e-6
+
+
+def test_tc_plan_unsupported_shapes_fall_back():
+    from imgcomp_cvpr_b200 import nn
+    assert nn.TcPlan.get('conv5s2', False, 3, 64) is None          # h1
+    assert nn.TcPlan.get('conv5s2', False, 128, 33) is None        # to_bn
+    assert nn.TcPlan.get('pc', False, 1, 24) is None               # first context-model layer (one input channel)

@@ -281,3 +281,37 @@ def test_cuda_graph_survives_growth_of_the_shared_workspace(synth):
         for k in ('total_loss', 'd_loss_scaled', 'pc_loss', 'H_real', 'H_mask', 'ms_ssim', 'bpp'):
             assert a[k] == b[k], (k, a[k], b[k])
     assert all(float(f.min()) == 7.0 and float(f.max()) == 7.0 for f in filler)
+
+
+@pytest.mark.parametrize('minimize_for', ['mse', 'psnr'])
+def test_training_step_mse_and_psnr_distortions_match_oracle(synth, minimize_for):
+    """config.distortion_to_minimize = 'mse' / 'psnr' (code/train.py:381-397: float32 squared error while training; the
+    psnr variant minimises K_psnr - mean_n 10 log10(255^2 / mse_n)): loss components and every gradient against the
+    float64 oracle, same gates as the MS-SSIM step."""
+    from imgcomp_cvpr_b200 import config as cfgmod, trainer, weights
+    ae_cfg, pc_cfg, Wt = synth('cvpr/low')
+    ae_cfg = cfgmod.Config(**dict(vars(ae_cfg), distortion_to_minimize=minimize_for))
+    x = weights.synthetic_images(2, 48, 40, seed=22)          # below the 11-tap MS-SSIM's minimum size: MS-SSIM is never evaluated
+    tr = trainer.Trainer(ae_cfg, pc_cfg, Wt, num_itr_per_epoch=100, mode='fp32')
+    ref = T.training_step(x, Wt, ae_cfg, pc_cfg, dtype=torch.float64, training=True)
+    out = tr.forward_backward(torch.from_numpy(x).cuda(), is_training=True, update_moving=False)
+    mism = int((out['tensors']['symbols'].cpu().numpy() != ref['tensors']['symbols']).sum())
+    assert mism == 0, 'a symbol flipped between the float32 kernels and the float64 oracle: pick another seed'
+    assert out['ms_ssim'] is None
+    for k in ('total_loss', 'd_loss_scaled', 'pc_loss', 'H_real', 'H_mask', 'reg'):
+        print('  %-14s gpu %.6f  oracle %.6f' % (k, out[k], ref[k]))
+        assert abs(out[k] - ref[k]) <= 1e-4 * max(1.0, abs(ref[k])), k
+    G = tr.gradients()
+    errs = []
+    for name, g_ref in ref['grads'].items():
+        g = G[name].astype(np.float64)
+        w = np.asarray(Wt[name], np.float64)
+        if name.startswith('autoencoder/') and name.endswith('/weights'):
+            g = g + ae_cfg.regularization_factor * w
+        elif name.endswith('/centers'):
+            g = g + ae_cfg.regularization_factor_centers * w
+        errs.append((_rel(g, g_ref), name))
+    errs.sort(reverse=True)
+    print('  %s: worst gradient error %.2e (%s), median %.2e' % (minimize_for, errs[0][0], errs[0][1], errs[len(errs) // 2][0]))
+    assert errs[0][0] < 2e-3, errs[:8]
+    assert errs[len(errs) // 2][0] < 2e-4
