@@ -260,22 +260,79 @@ __global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __r
     const int64_t r0 = (int64_t)blockIdx.x * CR_ROWS;
     const int64_t r1 = min(a.M, r0 + CR_ROWS);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = r0 + warp; r < r1; r += 8) {
+    if (a.C == 128) {
+        // the 128-channel trunk layers: a lane owns channels 4 lane .. 4 lane + 3 and reads them as one 16-byte load per
+        // row (a warp = one 512-byte row per instruction, all of a thread's rows in flight at once).  Every channel is still
+        // summed by ONE thread over the same rows in the same order as in the scalar loop below: same bits.
+        const int c0 = 4 * lane;
+        float pv[4] = {0.f, 0.f, 0.f, 0.f}, mu[4], is[4], ga[4], be[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int c = lane + 32 * u;
-            if (c < a.C) {
-                float q1, q2;
-                col_terms(a, r, c, q1, q2);
-                s1[u] += q1;
-                s2[u] += q2;
+            if (a.mode == 0) {
+                pv[u] = a.x[c0 + u];
+            } else {
+                mu[u] = a.mean[c0 + u];
+                is[u] = a.invstd[c0 + u];
+                ga[u] = a.gamma[c0 + u];
+                be[u] = a.beta[c0 + u];
             }
         }
-    }
+        float4 xv[CR_ROWS / 8], dv[CR_ROWS / 8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        red[warp][lane + 32 * u][0] = s1[u];
-        red[warp][lane + 32 * u][1] = s2[u];
+        for (int k = 0; k < CR_ROWS / 8; ++k) {
+            const int64_t r = r0 + warp + 8 * k;
+            if (r < r1) {
+                xv[k] = *reinterpret_cast<const float4*>(a.x + r * 128 + c0);
+                if (a.mode != 0) dv[k] = *reinterpret_cast<const float4*>(a.dy + r * 128 + c0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CR_ROWS / 8; ++k) {
+            const int64_t r = r0 + warp + 8 * k;
+            if (r < r1) {
+                const float xe[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+                const float de[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float q1, q2;
+                    if (a.mode == 0) {
+                        q1 = xe[u] - pv[u];
+                        q2 = q1 * q1;
+                    } else {
+                        const float xh = (xe[u] - mu[u]) * is[u];
+                        float dy = de[u];
+                        if (a.relu && fmaf(xh, ga[u], be[u]) <= 0.f) dy = 0.f;
+                        q1 = dy;
+                        q2 = dy * xh;
+                    }
+                    s1[u] += q1;
+                    s2[u] += q2;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            red[warp][c0 + u][0] = s1[u];
+            red[warp][c0 + u][1] = s2[u];
+        }
+    } else {
+        for (int64_t r = r0 + warp; r < r1; r += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = lane + 32 * u;
+                if (c < a.C) {
+                    float q1, q2;
+                    col_terms(a, r, c, q1, q2);
+                    s1[u] += q1;
+                    s2[u] += q2;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            red[warp][lane + 32 * u][0] = s1[u];
+            red[warp][lane + 32 * u][1] = s2[u];
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < a.C; c += 256) {
@@ -344,6 +401,58 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
         if (res1) v += res1[i];
         if (res2) v += res2[i];
         out[i] = v;
+    }
+}
+
+// C % 4 == 0 (every layer of the step): four channels per thread, 16-byte accesses; per element the same operations as above
+__global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict__ x, const float* __restrict__ mean,
+                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int relu, const float4* __restrict__ res1,
+                                                        const float4* __restrict__ res2, int64_t total4, int C4,
+                                                        float4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = 4 * (int)(i % C4);
+        const float4 xv = x[i];
+        const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = fmaf((xe[u] - mean[c + u]) * invstd[c + u], gamma[c + u], beta[c + u]);
+            if (relu) v[u] = fmaxf(v[u], 0.f);
+        }
+        if (res1) {
+            const float4 r = res1[i];
+            v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        if (res2) {
+            const float4 r = res2[i];
+            v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        out[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ dbeta, const float* __restrict__ dgamma, int relu,
+                                                            int affine_only, int64_t total4, int C4, float inv_m,
+                                                            float4* __restrict__ dx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = 4 * (int)(i % C4);
+        const float4 xv = x[i], dv = dy[i];
+        const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float de[4] = {dv.x, dv.y, dv.z, dv.w};
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xh = (xe[u] - mean[c + u]) * invstd[c + u];
+            float d = de[u];
+            if (relu && fmaf(xh, gamma[c + u], beta[c + u]) <= 0.f) d = 0.f;
+            if (!affine_only) d = d - dbeta[c + u] * inv_m - xh * dgamma[c + u] * inv_m;
+            o[u] = gamma[c + u] * invstd[c + u] * d;
+        }
+        dx[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -787,7 +896,12 @@ int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma,
                                                          d_mov_mean, d_mov_var, 0.9f, d_x);
         IC_CHECK_LAUNCH();
     }
-    bn_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_mean, d_invstd, d_gamma, d_beta, relu, d_res1, d_res2, M * C, C, d_out);
+    const bool vec4 = C % 4 == 0 && (((uintptr_t)d_x | (uintptr_t)d_out | (uintptr_t)d_res1 | (uintptr_t)d_res2) & 15) == 0;
+    if (vec4)
+        bn_apply4_kernel<<<ew_grid(M * C / 4), 256, 0, s>>>((const float4*)d_x, d_mean, d_invstd, d_gamma, d_beta, relu,
+                                                            (const float4*)d_res1, (const float4*)d_res2, M * C / 4, C / 4, (float4*)d_out);
+    else
+        bn_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_mean, d_invstd, d_gamma, d_beta, relu, d_res1, d_res2, M * C, C, d_out);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
@@ -810,8 +924,14 @@ int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, co
     col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 1, 0.f, d_dbeta, d_dgamma, nullptr,
                                                      nullptr, 0.f, nullptr);
     IC_CHECK_LAUNCH();
-    bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_dy, d_mean, d_invstd, d_gamma, d_beta, d_dbeta, d_dgamma, relu,
-                                                       use_stats ? 0 : 1, M * C, C, 1.f / (float)M, d_dx);
+    const bool vec4 = C % 4 == 0 && (((uintptr_t)d_x | (uintptr_t)d_dy | (uintptr_t)d_dx) & 15) == 0;
+    if (vec4)
+        bn_bwd_apply4_kernel<<<ew_grid(M * C / 4), 256, 0, s>>>((const float4*)d_x, (const float4*)d_dy, d_mean, d_invstd, d_gamma, d_beta,
+                                                                d_dbeta, d_dgamma, relu, use_stats ? 0 : 1, M * C / 4, C / 4,
+                                                                1.f / (float)M, (float4*)d_dx);
+    else
+        bn_bwd_apply_kernel<<<ew_grid(M * C), 256, 0, s>>>(d_x, d_dy, d_mean, d_invstd, d_gamma, d_beta, d_dbeta, d_dgamma, relu,
+                                                           use_stats ? 0 : 1, M * C, C, 1.f / (float)M, d_dx);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

@@ -291,7 +291,10 @@ def test_training_step_mse_and_psnr_distortions_match_oracle(synth, minimize_for
     from imgcomp_cvpr_b200 import config as cfgmod, trainer, weights
     ae_cfg, pc_cfg, Wt = synth('cvpr/low')
     ae_cfg = cfgmod.Config(**dict(vars(ae_cfg), distortion_to_minimize=minimize_for))
-    x = weights.synthetic_images(2, 48, 40, seed=22)          # below the 11-tap MS-SSIM's minimum size: MS-SSIM is never evaluated
+    # 48 x 40 is below the 11-tap MS-SSIM's minimum size: MS-SSIM is never evaluated.  Seed: tools/dist_seed_sweep.py (7 of 10
+    # seeds have every gradient within 3e-5; seeds 22, 25, 29 have a ReLU / clip decision that differs between float32 and
+    # float64, a discrete event that moves one layer by ~1e-2 -- see test_training_step_matches_oracle)
+    x = weights.synthetic_images(2, 48, 40, seed=23)
     tr = trainer.Trainer(ae_cfg, pc_cfg, Wt, num_itr_per_epoch=100, mode='fp32')
     ref = T.training_step(x, Wt, ae_cfg, pc_cfg, dtype=torch.float64, training=True)
     out = tr.forward_backward(torch.from_numpy(x).cuda(), is_training=True, update_moving=False)
@@ -313,5 +316,22 @@ def test_training_step_mse_and_psnr_distortions_match_oracle(synth, minimize_for
         errs.append((_rel(g, g_ref), name))
     errs.sort(reverse=True)
     print('  %s: worst gradient error %.2e (%s), median %.2e' % (minimize_for, errs[0][0], errs[0][1], errs[len(errs) // 2][0]))
-    assert errs[0][0] < 2e-3, errs[:8]
-    assert errs[len(errs) // 2][0] < 2e-4
+    assert errs[0][0] < 1e-3, errs[:8]
+    assert errs[len(errs) // 2][0] < 1e-4
+
+
+def test_distortion_backward_kernel():
+    """ic_nn_distortion_bwd against the closed form in float64 (code/train.py:381-397,420-425)"""
+    from imgcomp_cvpr_b200 import nn
+    rng = np.random.RandomState(9)
+    x = rng.uniform(0, 255, size=(3, 3, 24, 40)).astype(np.float32)
+    y = np.clip(x + rng.normal(0, 20, size=x.shape), 0, 255).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64)
+    for psnr in (False, True):
+        yt = torch.tensor(y, dtype=torch.float64, requires_grad=True)
+        mse = ((yt - xt) ** 2).mean(dim=(1, 2, 3))
+        loss = (100.0 - (10 * torch.log10(255.0 * 255.0 / mse)).mean()) if psnr else mse.mean()
+        loss.backward()
+        d, m = nn.distortion_bwd(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), psnr=psnr)
+        np.testing.assert_allclose(m.cpu().numpy(), mse.detach().numpy(), rtol=1e-6)
+        assert _rel(d.cpu().numpy(), yt.grad.numpy()) < 1e-6
