@@ -84,6 +84,10 @@ SIGNATURES = {
     'ic_nn_tc_plan_map': (c_int64, [c_void_p, c_void_p, c_int64]),
     'ic_nn_tc_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
     'ic_nn_tc_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_tc_wgrad_plan_create': (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    'ic_nn_tc_wgrad_plan_destroy': (None, [c_void_p]),
+    'ic_nn_tc_wgrad_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    'ic_nn_tc_wgrad_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_bn_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'ic_nn_bn_train_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

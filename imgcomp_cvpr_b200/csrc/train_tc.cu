@@ -248,6 +248,140 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 
+// ---- the same GEMM over pixels for the other layers (strided convs through their space-to-depth form, context model):
+// a CTA "kind" fixes the tap row ky, the 128-channel block of A (first chunk) and the image offset of A (context model:
+// filter depth 1 reads the next depth slice); it accumulates the taps (ky, 0..2) in 3 x NB TMEM columns.  A has up to 128
+// channels (missing chunks are TMA zero fill: M stays 128), B has NB = 32 or 128 columns.
+constexpr int WG_MAX_KINDS = 8;
+struct WgGenParams {
+    int N, Ho, Wo;                 // B (output-gradient) grid: N images of Ho x Wo
+    int ox, oy;                    // A tile origin relative to the B tile: -1 (SAME 3x3 on the s2d grid) or 0 (VALID)
+    int nkinds, n_splits;
+    int ky[WG_MAX_KINDS], chunk0[WG_MAX_KINDS], img_off[WG_MAX_KINDS];
+};
+
+template <int NB>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_gen_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap dy_map, const WgGenParams p,
+                    float* __restrict__ partial) {
+    using namespace tc;
+    constexpr int Y_PLANE = (NB / 8) * WG_ROWS * WG_COLS * 16;
+    constexpr int STAGE_BYTES = 2 * WG_X_PLANE + 2 * Y_PLANE;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t TCOLS = NB == 128 ? 512 : 128;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    WgBars* bars = reinterpret_cast<WgBars*>(smem + WG_STAGES * STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kind = blockIdx.x % p.nkinds, split = blockIdx.x / p.nkinds;
+    const int ky = p.ky[kind], chunk0 = p.chunk0[kind], img_off = p.img_off[kind];
+    const int tiles_x = (p.Wo + WG_COLS - 1) / WG_COLS, tiles_y = (p.Ho + WG_ROWS - 1) / WG_ROWS;
+    const int n_tiles = p.N * tiles_y * tiles_x;
+    const int my_tiles = split < n_tiles ? (n_tiles - split + p.n_splits - 1) / p.n_splits : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) {
+            mbar_init(smem_u32(&bars->full[i]), 1);
+            mbar_init(smem_u32(&bars->empty[i]), 1);
+        }
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = split + it * p.n_splits;
+                const int n = tile / (tiles_y * tiles_x), r = tile - n * tiles_y * tiles_x;
+                const int y0 = (r / tiles_x) * WG_ROWS, x0 = (r % tiles_x) * WG_COLS;
+                const uint32_t slot = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+                mbar_wait(smem_u32(&bars->empty[slot]), ph ^ 1);
+                const uint32_t full = smem_u32(&bars->full[slot]);
+                mbar_expect_tx(full, STAGE_BYTES);
+                const uint32_t xs = smem_u32(smem + slot * STAGE_BYTES), ys = xs + 2 * WG_X_PLANE;
+                for (int pl = 0; pl < 2; ++pl) {
+                    tma_load_5d(xs + pl * WG_X_PLANE, &x_map, full, (x0 + p.ox) * 8, y0 + ky + p.oy, chunk0, n + img_off, pl);
+                    tma_load_5d(ys + pl * Y_PLANE, &dy_map, full, x0 * 8, y0, 0, n, pl);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t kXSbo = WG_ROWS * (WG_COLS + 2) * 16, kYSbo = WG_ROWS * WG_COLS * 16, kLbo = 128;
+        for (int it = 0; it < my_tiles; ++it) {
+            const uint32_t slot = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+            mbar_wait(smem_u32(&bars->full[slot]), ph);
+            tc_fence_after();
+            const uint32_t xs = smem_u32(smem + slot * STAGE_BYTES), ys = xs + 2 * WG_X_PLANE;
+            if (elect_one()) {
+#pragma unroll
+                for (int r = 0; r < WG_ROWS; ++r) {
+                    const uint64_t b_hi = make_desc(ys + r * WG_COLS * 16, kLbo, kYSbo);
+                    const uint64_t b_lo = make_desc(ys + Y_PLANE + r * WG_COLS * 16, kLbo, kYSbo);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const uint32_t a_addr = xs + (r * (WG_COLS + 2) + kx) * 16;
+                        const uint64_t a_hi = make_desc(a_addr, kLbo, kXSbo);
+                        const uint64_t a_lo = make_desc(a_addr + WG_X_PLANE, kLbo, kXSbo);
+                        const uint32_t d = tmem_base + kx * NB;
+                        umma_f16(d, a_hi, b_hi, IDESC, (it | r) == 0 ? 0u : 1u);
+                        umma_f16(d, a_hi, b_lo, IDESC, 1u);
+                        umma_f16(d, a_lo, b_hi, IDESC, 1u);
+                    }
+                }
+                umma_commit(smem_u32(&bars->empty[slot]));
+                if (it == my_tiles - 1) umma_commit(smem_u32(&bars->acc_full));
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int ci = q * 32 + lane;
+        if (my_tiles > 0) {
+            mbar_wait(smem_u32(&bars->acc_full), 0);
+            tc_fence_after();
+        }
+        for (int kx = 0; kx < 3; ++kx) {
+            float* dst = partial + ((((size_t)split * p.nkinds + kind) * 3 + kx) * 128 + ci) * NB;
+            for (int cc = 0; cc < NB / 16; ++cc) {
+                uint32_t rr[16];
+                if (my_tiles > 0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kx * NB + cc * 16, rr);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) rr[e] = 0u;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    reinterpret_cast<float4*>(dst + cc * 16)[e] = make_float4(__uint_as_float(rr[4 * e]), __uint_as_float(rr[4 * e + 1]),
+                                                                              __uint_as_float(rr[4 * e + 2]), __uint_as_float(rr[4 * e + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+}
+
+// dw[i] = (sum over splits, fixed order, of partial[split][map[i]]) / (scale_a * scale_b); map[i] < 0: no gradient (masked tap)
+__global__ void __launch_bounds__(256) wgrad_gather_kernel(const float* __restrict__ partial, int n_splits, int64_t split_stride,
+                                                           const int* __restrict__ map, int n, const float* __restrict__ params,
+                                                           float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    float s = 0.f;
+    if (m >= 0)
+        for (int k = 0; k < n_splits; ++k) s += partial[(size_t)k * split_stride + m];
+    dw[i] = m >= 0 ? s / (params[0] * params[1]) : 0.f;
+}
+
 // dW = (sum over splits, fixed order) / (scale_x * scale_dy)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, const float* __restrict__ params,
                                                            float* __restrict__ dw) {
@@ -803,6 +937,211 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
     if (rc != IC_OK) return rc;
     if (bo) return tc::launch_merge_to_nhwc(bo, (int)g.out_imgs, g.Ho, g.Wo, p.cout, d_y, 1, s, params + 5);
     if (img) return ic_nn_nchw_to_nhwc(img, N, 3, p.cout_pad, (int64_t)g.Ho * g.Wo, d_y, stream);
+    return IC_OK;
+}
+
+
+/* ---- filter gradients of the same layers on tcgen05 (wgrad_tc_gen_kernel): op_kind as in ic_nn_tc_plan_create.
+ * d_x: the op's float32 NHWC input, d_dy: the gradient w.r.t. its output, D/N/H/W: dimensions of d_x;
+ * d_dw: the gradient in the layout of the op's weight array (masked taps of the context model: 0). */
+struct ic_tc_wgrad_plan {
+    int op_kind;
+    int a_ch, b_ch;               // channel strides of the A source / B source tensors (float32 NHWC)
+    int nb;                       // B columns (32 or 128)
+    int a_s2d;                    // A source goes through space-to-depth (strided / transposed convs)
+    int a_is_dy;                  // transposed conv: A = output gradient, B = input
+    int n_dw;
+    WgGenParams gp;               // kinds (N / Ho / Wo / n_splits / img_off scale filled per call)
+    int* d_map;
+};
+
+int ic_nn_tc_wgrad_plan_create(int op_kind, int op_cin, int op_cout, ic_tc_wgrad_plan_t** out) {
+    IC_REQUIRE(out, IC_ERR_INVALID, "ic_nn_tc_wgrad_plan_create: NULL argument");
+    *out = nullptr;
+    IC_REQUIRE(op_cin > 0 && op_cout > 0 && (op_kind == 0 || op_kind == 1 || op_kind == 3), IC_ERR_INVALID, "ic_nn_tc_wgrad_plan_create: bad op");
+    const int ci_pad = (int)align_up(op_cin, 4), co_pad = (int)align_up(op_cout, 4);
+    ic_tc_wgrad_plan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.op_kind = op_kind;
+    std::vector<int> map;
+    if (op_kind == 3) {
+        if (ci_pad % 8 != 0 || ci_pad > 128 || co_pad % 8 != 0 || co_pad > 32) return IC_ERR_UNSUPPORTED;
+        pl.a_ch = ci_pad;
+        pl.b_ch = co_pad;
+        pl.nb = 32;
+        pl.n_dw = 18 * ci_pad * co_pad;
+        pl.gp.nkinds = 5;
+        for (int k = 0; k < 5; ++k) {
+            pl.gp.ky[k] = k % 3;
+            pl.gp.chunk0[k] = 0;
+            pl.gp.img_off[k] = k / 3;          // x N per call: filter depth 1 reads the next depth slice
+        }
+        map.assign(pl.n_dw, -1);
+        for (int fd = 0; fd < 2; ++fd)
+            for (int fy = 0; fy < 3; ++fy)
+                for (int fx = 0; fx < 3; ++fx) {
+                    if (fd == 1 && (fy > 1 || (fy == 1 && fx > 1))) continue;          // "other" mask (code/probclass.py:164-176)
+                    const int kind = fd * 3 + fy;
+                    for (int c = 0; c < op_cin; ++c)
+                        for (int o = 0; o < op_cout; ++o)
+                            map[((((fd * 3 + fy) * 3 + fx) * ci_pad) + c) * co_pad + o] = ((kind * 3 + fx) * 128 + c) * 32 + o;
+                }
+    } else {
+        // A = the 2x finer tensor in space-to-depth form (conv2d: the input; conv2d_transpose: the output gradient)
+        const int fine = op_kind == 0 ? op_cin : op_cout, coarse = op_kind == 0 ? op_cout : op_cin;
+        if (fine % 32 != 0 || 4 * fine > 256 || coarse != 128 || fine != (op_kind == 0 ? ci_pad : co_pad)) return IC_ERR_UNSUPPORTED;
+        const int nhalves = 4 * fine / 128;
+        pl.a_ch = fine;
+        pl.b_ch = coarse;
+        pl.nb = 128;
+        pl.a_s2d = 1;
+        pl.a_is_dy = op_kind == 1;
+        pl.n_dw = 25 * ci_pad * co_pad;
+        pl.gp.nkinds = 3 * nhalves;
+        pl.gp.ox = pl.gp.oy = -1;
+        for (int ty = 0; ty < 3; ++ty)
+            for (int h = 0; h < nhalves; ++h) {
+                pl.gp.ky[ty * nhalves + h] = ty;
+                pl.gp.chunk0[ty * nhalves + h] = h * 16;
+            }
+        map.assign(pl.n_dw, -1);
+        for (int ky = 0; ky < 5; ++ky)
+            for (int kx = 0; kx < 5; ++kx) {
+                const int ty = ((ky - 1) >> 1) + 1, py = (ky - 1) & 1, tx = ((kx - 1) >> 1) + 1, px = (kx - 1) & 1;
+                for (int f = 0; f < fine; ++f)
+                    for (int c = 0; c < coarse; ++c) {
+                        const int sc = (py * 2 + px) * fine + f;                 // channel of the space-to-depth tensor
+                        const int kind = ty * nhalves + sc / 128;
+                        const int off = ((kind * 3 + tx) * 128 + sc % 128) * 128 + c;
+                        // conv2d weights [t][cin = f][cout = c]; conv2d_transpose (op orientation) [t][cin = c][cout = f]
+                        const int wi = op_kind == 0 ? ((ky * 5 + kx) * ci_pad + f) * co_pad + c : ((ky * 5 + kx) * ci_pad + c) * co_pad + f;
+                        map[wi] = off;
+                    }
+            }
+    }
+    IC_CHECK_CUDA(cudaMalloc((void**)&pl.d_map, map.size() * sizeof(int)));
+    IC_CHECK_CUDA(cudaMemcpy(pl.d_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+    *out = new ic_tc_wgrad_plan(pl);
+    return IC_OK;
+}
+
+void ic_nn_tc_wgrad_plan_destroy(ic_tc_wgrad_plan_t* plan) {
+    if (!plan) return;
+    cudaFree(plan->d_map);
+    delete plan;
+}
+
+namespace {
+struct WgGeo {
+    int64_t a_imgs, b_imgs;
+    int Ha, Wa, Hb, Wb;           // A source / B source spatial sizes (float32 tensors)
+    int S;
+};
+WgGeo wgrad_geo(const ic_tc_wgrad_plan& p, int D, int N, int H, int W) {
+    WgGeo g;
+    if (p.op_kind == 3) {
+        g.a_imgs = (int64_t)D * N; g.b_imgs = (int64_t)(D - 1) * N;
+        g.Ha = H; g.Wa = W; g.Hb = H - 2; g.Wb = W - 2;
+    } else if (p.op_kind == 0) {
+        g.a_imgs = g.b_imgs = N;
+        g.Ha = H; g.Wa = W; g.Hb = H / 2; g.Wb = W / 2;
+    } else {
+        g.a_imgs = g.b_imgs = N;
+        g.Ha = 2 * H; g.Wa = 2 * W; g.Hb = H; g.Wb = W;
+    }
+    const int64_t n_tiles = g.b_imgs * ((g.Hb + WG_ROWS - 1) / WG_ROWS) * ((g.Wb + WG_COLS - 1) / WG_COLS);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    g.S = (int)std::max<int64_t>(1, std::min<int64_t>(sms / p.gp.nkinds, n_tiles));
+    return g;
+}
+}  // namespace
+
+size_t ic_nn_tc_wgrad_plan_workspace_bytes(const ic_tc_wgrad_plan_t* plan, int D, int N, int H, int W) {
+    if (!plan || N <= 0 || H <= 0 || W <= 0) return 0;
+    const WgGeo g = wgrad_geo(*plan, D, N, H, W);
+    if (g.b_imgs <= 0 || g.Hb <= 0 || g.Wb <= 0) return 0;
+    return align_up((size_t)g.a_imgs * g.Ha * g.Wa * plan->a_ch * 2 * sizeof(__half), 256) +
+           align_up((size_t)g.b_imgs * g.Hb * g.Wb * plan->b_ch * 2 * sizeof(__half), 256) +
+           align_up((size_t)g.S * plan->gp.nkinds * 3 * 128 * plan->nb * sizeof(float), 256) + 3 * kMaxBlocks * sizeof(float) + 8192;
+}
+
+int ic_nn_tc_wgrad_plan_run(const ic_tc_wgrad_plan_t* plan, const float* d_x, const float* d_dy, int D, int N, int H, int W,
+                            float* d_dw, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(plan && d_x && d_dy && d_dw && d_workspace, IC_ERR_INVALID, "ic_nn_tc_wgrad_plan_run: NULL argument");
+    const ic_tc_wgrad_plan& p = *plan;
+    IC_REQUIRE(N > 0 && H > 0 && W > 0 && (p.op_kind != 3 || D > 1), IC_ERR_INVALID, "ic_nn_tc_wgrad_plan_run: bad shape");
+    IC_REQUIRE(p.op_kind != 0 || (H % 2 == 0 && W % 2 == 0), IC_ERR_INVALID, "ic_nn_tc_wgrad_plan_run: odd size for a stride-2 conv");
+    IC_REQUIRE(workspace_bytes >= ic_nn_tc_wgrad_plan_workspace_bytes(plan, D, N, H, W), IC_ERR_WORKSPACE, "ic_nn_tc_wgrad_plan_run: workspace too small");
+    const WgGeo g = wgrad_geo(p, D, N, H, W);
+    IC_REQUIRE(g.Hb > 0 && g.Wb > 0 && g.b_imgs > 0, IC_ERR_INVALID, "ic_nn_tc_wgrad_plan_run: empty output grid");
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* a_src = p.a_is_dy ? d_dy : d_x;
+    const float* b_src = p.a_is_dy ? d_x : d_dy;
+    const size_t a_elems = (size_t)g.a_imgs * g.Ha * g.Wa * p.a_ch, b_elems = (size_t)g.b_imgs * g.Hb * g.Wb * p.b_ch;
+    const size_t split_stride = (size_t)p.gp.nkinds * 3 * 128 * p.nb;
+    Arena ar(d_workspace, workspace_bytes);
+    __half* ba = ar.get<__half>(2 * a_elems);
+    __half* bb = ar.get<__half>(2 * b_elems);
+    float* partial = ar.get<float>((size_t)g.S * split_stride);
+    float* params = ar.get<float>(8);
+    float* pa = ar.get<float>(kMaxBlocks);
+    float* pb = ar.get<float>(kMaxBlocks);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_tc_wgrad_plan_run: workspace too small");
+    ScaleArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.ntens = 2;
+    sa.partial[0] = pa;
+    sa.partial[1] = pb;
+    int rc;
+    {
+        ProfScope ps(IC_PROF_ELEMENTWISE, s, 3);
+        rc = maxabs(a_src, (int64_t)a_elems, pa, &sa.count[0], s);
+        if (rc == IC_OK) rc = maxabs(b_src, (int64_t)b_elems, pb, &sa.count[1], s);
+        if (rc != IC_OK) return rc;
+        finalize_scales_kernel<<<1, 256, 0, s>>>(sa, params, nullptr, nullptr);
+        IC_CHECK_LAUNCH();
+    }
+    rc = tc::launch_split_from_nhwc(a_src, (int)g.a_imgs, g.Ha, g.Wa, p.a_ch, p.a_s2d, ba, 1, s, params + 0);
+    if (rc == IC_OK) rc = tc::launch_split_from_nhwc(b_src, (int)g.b_imgs, g.Hb, g.Wb, p.b_ch, 0, bb, 1, s, params + 1);
+    if (rc != IC_OK) return rc;
+    // A planes as the kernel sees them: space-to-depth -> [pl][N][4 a_ch / 8][Ha/2][Wa/2][8]
+    const int a_chunks = (p.a_s2d ? 4 : 1) * p.a_ch / 8, Hs = p.a_s2d ? g.Ha / 2 : g.Ha, Ws = p.a_s2d ? g.Wa / 2 : g.Wa;
+    CUtensorMap xmap, ymap;
+    rc = tc::encode_planes_map(&xmap, ba, 2, (int)g.a_imgs, a_chunks, Hs, Ws, WG_COLS + 2, WG_ROWS, 16);
+    if (rc == IC_OK) rc = tc::encode_planes_map(&ymap, bb, 2, (int)g.b_imgs, p.b_ch / 8, g.Hb, g.Wb, WG_COLS, WG_ROWS, p.nb / 8);
+    if (rc != IC_OK) return rc;
+    WgGenParams gp = p.gp;
+    gp.N = (int)g.b_imgs;
+    gp.Ho = g.Hb;
+    gp.Wo = g.Wb;
+    gp.n_splits = g.S;
+    if (p.op_kind == 3)
+        for (int k = 0; k < gp.nkinds; ++k) gp.img_off[k] *= N;
+    {
+        ProfScope ps(p.op_kind == 3 ? IC_PROF_PROBCLASS : IC_PROF_CONV_OTHER, s, 2);
+        if (p.nb == 128) {
+            const size_t smem = (size_t)WG_STAGES * (2 * WG_X_PLANE + 2 * 16 * WG_ROWS * WG_COLS * 16) + sizeof(WgBars) + 64;
+            static bool attr_set = false;
+            if (!attr_set) {
+                IC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_gen_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            wgrad_tc_gen_kernel<128><<<gp.nkinds * g.S, WG_THREADS, smem, s>>>(xmap, ymap, gp, partial);
+        } else {
+            const size_t smem = (size_t)WG_STAGES * (2 * WG_X_PLANE + 2 * 4 * WG_ROWS * WG_COLS * 16) + sizeof(WgBars) + 64;
+            static bool attr_set = false;
+            if (!attr_set) {
+                IC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_gen_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            wgrad_tc_gen_kernel<32><<<gp.nkinds * g.S, WG_THREADS, smem, s>>>(xmap, ymap, gp, partial);
+        }
+        IC_CHECK_LAUNCH();
+        wgrad_gather_kernel<<<cdiv(p.n_dw, 256), 256, 0, s>>>(partial, g.S, (int64_t)split_stride, p.d_map, p.n_dw, params, d_dw);
+        IC_CHECK_LAUNCH();
+    }
     return IC_OK;
 }
 

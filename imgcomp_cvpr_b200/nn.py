@@ -163,6 +163,40 @@ class TcPlan(object):
         return y
 
 
+class TcWgradPlan(object):
+    """Filter gradient of one of TcPlan's ops on the tcgen05 GEMM-over-pixels kernel (ic_nn_tc_wgrad_plan_*)."""
+    _cache = {}
+
+    def __init__(self, handle, kind):
+        self.h, self.kind = handle, kind
+
+    @classmethod
+    def get(cls, kind, cin, cout):
+        key = (kind, cin, cout)
+        if key not in cls._cache:
+            import ctypes
+            h = ctypes.c_void_p()
+            rc = _lib.lib().ic_nn_tc_wgrad_plan_create(TcPlan.KINDS[kind], cin, cout, ctypes.byref(h))
+            if rc == -4:        # IC_ERR_UNSUPPORTED
+                cls._cache[key] = None
+            else:
+                _lib.check(rc)
+                cls._cache[key] = cls(h, kind)
+        return cls._cache[key]
+
+    def run(self, x, dy, dw_out):
+        """x: the op's input, dy: gradient w.r.t. its output (float32 NHWC; depth-major 5-D for 'pc') -> dw_out (filled)"""
+        if self.kind == 'pc':
+            D, N, H, W, _ = x.shape
+        else:
+            (N, H, W, _), D = x.shape, 1
+        L = _lib.lib()
+        ws = _workspace(L.ic_nn_tc_wgrad_plan_workspace_bytes(self.h, D, N, H, W))
+        _lib.check(L.ic_nn_tc_wgrad_plan_run(self.h, _lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), D, N, H, W, _lib.ptr(_f32(dw_out)), _lib.ptr(ws),
+                                             ws.numel(), _lib.stream_ptr()))
+        return dw_out
+
+
 def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None):
     """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics."""
     C = x.shape[-1]

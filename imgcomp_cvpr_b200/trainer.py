@@ -298,17 +298,17 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ ops (forward + recorded backward)
     def _tc_plans(self, kind, cin, cout):
-        """(forward plan, data-gradient plan) of a non-3x3 conv on the tcgen05 kernels, None where no kernel covers the shape
+        """(forward, data-gradient, filter-gradient plan) of a non-3x3 conv on the tcgen05 kernels, None where no kernel covers the shape
         or outside mode 'exact' (IC_TRAIN_TC_EXTRA=0 keeps these layers on the FFMA kernels: A/B in tests)"""
         if self.mode != 'exact' or os.environ.get('IC_TRAIN_TC_EXTRA', '1') == '0':
-            return None, None
-        return nn.TcPlan.get(kind, False, cin, cout), nn.TcPlan.get(kind, True, cin, cout)
+            return None, None, None
+        return nn.TcPlan.get(kind, False, cin, cout), nn.TcPlan.get(kind, True, cin, cout), nn.TcWgradPlan.get(kind, cin, cout)
 
     def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None, chans=None):
         tc = (self.mode == 'exact' and tuple(w.shape) == (3, 3, 128, 128) and stride == 1 and not transposed and not valid)
-        plan_f = plan_d = None
+        plan_f = plan_d = plan_w = None
         if not tc and chans is not None and w.shape[0] == 5 and stride == 2 and not valid:
-            plan_f, plan_d = self._tc_plans('tconv5s2' if transposed else 'conv5s2', *chans)
+            plan_f, plan_d, plan_w = self._tc_plans('tconv5s2' if transposed else 'conv5s2', *chans)
         cache = None
         if tc and self.tape is not None:        # keep the input's fp16 planes and the scales for the filter gradient
             y, cache = nn.conv3x3_tc(x, w, keep=True)
@@ -328,7 +328,10 @@ class Trainer(object):
                     if need_dx:
                         tape.acc(x, dx, owned=True)
                     return
-                nn.conv2d_bwd_filter(x, dy, w.shape, stride, transposed, valid, out=gw)
+                if plan_w is not None:
+                    plan_w.run(x, dy, gw)
+                else:
+                    nn.conv2d_bwd_filter(x, dy, w.shape, stride, transposed, valid, out=gw)
                 if mask is not None:
                     nn.mul(gw, mask, out=gw)
                 if need_dx:
@@ -420,7 +423,7 @@ class Trainer(object):
         D, N, H, W, Ci = x.shape
         xa, xb = x[:D - 1].reshape(-1, H, W, Ci), x[1:].reshape(-1, H, W, Ci)
         # layers 1-3 ("other" mask, 24 input channels): both depth passes as ONE tcgen05 conv, forward and data gradient
-        plan_f, plan_d = self._tc_plans('pc', *self._pc_chans[scope]) if scope != PC_LAYERS[0][0] else (None, None)
+        plan_f, plan_d, plan_w = self._tc_plans('pc', *self._pc_chans[scope]) if scope != PC_LAYERS[0][0] else (None, None, None)
         if plan_f is not None:
             y = plan_f.run(x, weff)
         else:
@@ -435,9 +438,12 @@ class Trainer(object):
                 if dy is None:
                     return
                 dy4 = dy.reshape(-1, H - 2, W - 2, w.shape[-1])
-                nn.conv2d_bwd_filter(xa, dy4, weff[0].shape, valid=True, out=gw[0])
-                nn.conv2d_bwd_filter(xb, dy4, weff[1].shape, valid=True, out=gw[1])
-                nn.mul(gw, mask, out=gw)
+                if plan_w is not None:          # masked taps come out as zeros
+                    plan_w.run(x, dy.contiguous(), gw)
+                else:
+                    nn.conv2d_bwd_filter(xa, dy4, weff[0].shape, valid=True, out=gw[0])
+                    nn.conv2d_bwd_filter(xb, dy4, weff[1].shape, valid=True, out=gw[1])
+                    nn.mul(gw, mask, out=gw)
                 if need_dx and plan_d is not None:
                     tape.acc(x, plan_d.run(dy.contiguous(), weff), owned=True)
                 elif need_dx:

@@ -250,6 +250,16 @@ int64_t ic_nn_tc_plan_map(const ic_tc_plan_t* plan, int* h_map_out, int64_t capa
 size_t ic_nn_tc_plan_workspace_bytes(const ic_tc_plan_t* plan, int D, int N, int H, int W);
 int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d_w, int D, int N, int H, int W, float* d_y,
                       void* d_workspace, size_t workspace_bytes, void* stream);
+/* Filter gradients of the same ops on tcgen05 (a GEMM whose reduction runs over pixels, MN-major operands; the stride-2 ops
+ * through the space-to-depth form of their finer tensor).  d_x: the op's input, d_dy: the gradient w.r.t. its output,
+ * D/N/H/W: dimensions of d_x; d_dw in the layout of the op's weight array (masked context-model taps: 0).
+ * IC_ERR_UNSUPPORTED from _create: use ic_nn_conv2d_bwd_filter. */
+typedef struct ic_tc_wgrad_plan ic_tc_wgrad_plan_t;
+int ic_nn_tc_wgrad_plan_create(int op_kind, int op_cin, int op_cout, ic_tc_wgrad_plan_t** out);
+void ic_nn_tc_wgrad_plan_destroy(ic_tc_wgrad_plan_t* plan);
+size_t ic_nn_tc_wgrad_plan_workspace_bytes(const ic_tc_wgrad_plan_t* plan, int D, int N, int H, int W);
+int ic_nn_tc_wgrad_plan_run(const ic_tc_wgrad_plan_t* plan, const float* d_x, const float* d_dy, int D, int N, int H, int W,
+                            float* d_dw, void* d_workspace, size_t workspace_bytes, void* stream);
 /* slim.batch_norm(is_training=True, fused) (code/autoencoder.py:115-125): batch mean / biased variance over
  * the M = N*H*W rows, out = relu?((x - mean) * invstd * gamma + beta) (+ res1) (+ res2); d_mean / d_invstd are
  * kept for the backward pass; d_mov_mean / d_mov_var (optional) get the decay-0.9 moving-average update with

@@ -205,6 +205,28 @@ def test_msssim_stream_kernel_matches_tiled_kernel(gpu_models, monkeypatch):
         assert abs(v_tf - w_tf) < 1e-6
 
 
+def test_res_shallow_64_context_model_against_oracle(gpu_models):
+    """pc_configs/cvpr/res_shallow_64 (arch_param__k = 64, code/pc_configs/cvpr/res_shallow_64:8): bit cost, logits and coder
+    tables of the 64-channel context model against the oracle (float32 chain on the FFMA kernels: no tensor-core packing
+    exists for k = 64)."""
+    ae, pc, W = gpu_models('cvpr/low', 'fp32', 'cvpr/res_shallow_64')
+    assert W['probclass3d/logits/res1/conv3d_conv1_mask/weights'].shape == (2, 3, 3, 64, 64)
+    rng = np.random.RandomState(11)
+    sym = rng.randint(0, 6, (2, 32, 7, 9)).astype(np.int64)
+    centers = W['autoencoder/encoder/centers'].astype(np.float32)
+    q = centers[sym]
+    bc = pc.bitcost(_cuda(q), _cuda(sym), False, pad_value=float(centers[0])).cpu().numpy()
+    bc_ref, logits_ref = O.pc_bitcost(q, sym, W, centers[0], np.float64)
+    np.testing.assert_allclose(bc, bc_ref, atol=2e-4, rtol=1e-4)
+    assert abs(bc.sum() / bc_ref.sum() - 1) < 1e-5                                 # bpp: 1e-4 is the north-star bound
+    f, bits = pc.freqs(_cuda(sym[:1]), _cuda(centers), codec=True)
+    f_ref = O.pc_freqs_volume(sym[0], W, centers)
+    assert np.abs(f[0].cpu().numpy() - f_ref).max() <= 256                          # float32 softmax * 1e9, like the k = 24 tables
+    qpad = _cuda(O.pad_for_probclass3d(q, 9, centers[0]).astype(np.float32))
+    lg = pc.logits(qpad).cpu().numpy()
+    np.testing.assert_allclose(lg, logits_ref, atol=5e-4)
+
+
 def test_api_errors_mirror_reference(gpu_models, synth):
     from imgcomp_cvpr_b200 import autoencoder, probclass
     a, p, W = synth('cvpr/low')

@@ -217,7 +217,7 @@ def test_tc_plan_strided_convs(case):
     x = _rnd((N, Cin, H, W), 11)
     w = _rnd((5, 5, Cin, Cout), 12, 0.05)
     xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
-    wt = torch.tensor(w, dtype=torch.float64)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
     y = T.conv2d_transpose_same(xt, wt.permute(0, 1, 3, 2), 2) if tr else T.conv2d_same(xt, wt, 2)
     dy = _rnd(tuple(y.shape), 13, gs)
     (y * torch.tensor(dy, dtype=torch.float64)).sum().backward()
@@ -234,8 +234,9 @@ def test_tc_plan_strided_convs(case):
     print('tc plan %s fwd %d->%d: rel err %.2e' % (kind, Cin, Cout, err))
     assert err < 2e-5
     assert not yg[..., Cout:].any()
+    pw = nn.TcWgradPlan.get(kind, Cin, Cout)
     if Cout == 3:
-        assert pd is None
+        assert pd is None and pw is None
         return
     assert pd is not None
     dyp = np.zeros(tuple(ref.shape[:3]) + (c4(Cout),), np.float32)
@@ -248,6 +249,14 @@ def test_tc_plan_strided_convs(case):
     # and against the FFMA kernels the trainer used before
     y32 = nn.conv2d_fwd(xg, wg, 2, tr).cpu().numpy()
     assert _rel(yg, y32) < 2e-5
+    # filter gradient: GEMM over pixels on the space-to-depth form of the finer tensor
+    assert pw is not None
+    dw = pw.run(xg, _cuda(dyp), torch.full((5, 5, c4(Cin), c4(Cout)), 7.0, device='cuda')).cpu().numpy()
+    err = _rel(dw[:, :, :Cin, :Cout], wt.grad.numpy())
+    print('tc plan %s wgrad: rel err %.2e' % (kind, err))
+    assert err < 2e-5
+    dw32 = nn.conv2d_bwd_filter(xg, _cuda(dyp), wg.shape, 2, tr).cpu().numpy()
+    assert _rel(dw, dw32) < 2e-5
 
 
 @pytest.mark.parametrize('case', [
@@ -269,7 +278,7 @@ def test_tc_plan_context_model_layers(case):
     x = _rnd((D, N, H, W, Ci), 21)
     w = _rnd((2, 3, 3, Ci, Co), 22, 0.1)                     # raw weights: masked entries are NOT zero here
     xt = torch.tensor(x.transpose(1, 4, 0, 2, 3), dtype=torch.float64, requires_grad=True)          # N, C, D, H, W
-    wt = torch.tensor((w * mask[..., None, None]).transpose(4, 3, 0, 1, 2), dtype=torch.float64)    # Co, Ci, 2, 3, 3
+    wt = torch.tensor((w * mask[..., None, None]).transpose(4, 3, 0, 1, 2), dtype=torch.float64, requires_grad=True)    # Co, Ci, 2, 3, 3
     y = F.conv3d(xt, wt)
     dy = _rnd(tuple(y.shape), 23, gs)
     (y * torch.tensor(dy, dtype=torch.float64)).sum().backward()
@@ -292,6 +301,15 @@ def test_tc_plan_context_model_layers(case):
     err = _rel(dx, refd)
     print('tc plan pc dgrad: rel err %.2e (gradient scale %g)' % (err, gs))
     assert err < 2e-5
+    # filter gradient; the masked taps get exact zeros (code/probclass.py:252-253: the mask multiplies the variable)
+    pw = nn.TcWgradPlan.get('pc', Ci, Co)
+    assert pw is not None
+    dw = pw.run(_cuda(x), _cuda(dyp), torch.full((2, 3, 3, c4(Ci), c4(Co)), 7.0, device='cuda')).cpu().numpy()
+    refw = wt.grad.numpy().transpose(2, 3, 4, 1, 0) * mask[..., None, None]
+    err = _rel(dw[..., :Ci, :Co], refw)
+    print('tc plan pc wgrad: rel err %.2e' % err)
+    assert err < 2e-5
+    assert not dw[1, 2].any() and not dw[1, 1, 2].any() and not dw[..., Ci:, :].any() and not dw[..., Co:].any()
     # unmasked raw weights give the same result: the plan never reads the masked taps
     wraw = np.zeros_like(wp)
     wraw[..., :Ci, :Co] = w
