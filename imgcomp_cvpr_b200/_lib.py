@@ -91,6 +91,13 @@ SIGNATURES = {
     'ic_nn_bn_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'ic_nn_bn_train_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_weight_scales': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    'ic_nn_conv3x3_tc_fused_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'ic_nn_bn_partial_bytes': (c_size_t, [c_int64]),
+    'ic_nn_conv3x3_tc_fused': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_bn_train_fwd_ex': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
+                                      c_void_p]),
     'ic_nn_bn_train_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_hq_workspace_bytes': (c_size_t, [c_int64]),

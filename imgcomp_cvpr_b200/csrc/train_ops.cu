@@ -17,6 +17,8 @@
 
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ic {
@@ -429,6 +431,51 @@ __global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict
             v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
         }
         out[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// C % 8 == 0: eight channels per thread; besides the float32 output the kernel writes its fp16 hi/lo planes
+// [plane][n][C/8][hw][8] -- the input format of the next tensor-core conv (conv_tc.cu), which then needs no split pass
+__global__ void __launch_bounds__(256) bn_apply8_planes_kernel(const float4* __restrict__ x, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int relu, const float4* __restrict__ res1,
+                                                               const float4* __restrict__ res2, int64_t total8, int CH, int64_t hw,
+                                                               float4* __restrict__ out, __half* __restrict__ planes, int64_t plane) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i % CH);
+        const int64_t r = i / CH;
+        const int c = 8 * chunk;
+        const float4 xa = x[2 * i], xb = x[2 * i + 1];
+        const float xe[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v[u] = fmaf((xe[u] - mean[c + u]) * invstd[c + u], gamma[c + u], beta[c + u]);
+            if (relu) v[u] = fmaxf(v[u], 0.f);
+        }
+        if (res1) {
+            const float4 a = res1[2 * i], b = res1[2 * i + 1];
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        if (res2) {
+            const float4 a = res2[2 * i], b = res2[2 * i + 1];
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        out[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        out[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        float4 hi4, lo4;
+        __half2* hi = reinterpret_cast<__half2*>(&hi4);
+        __half2* lo = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            hi[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            const float2 hf = __half22float2(hi[e]);
+            lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        }
+        const int64_t n = r / hw, rr = r - n * hw;
+        const size_t off = (((size_t)n * CH + chunk) * hw + rr) * 8;
+        *reinterpret_cast<float4*>(planes + off) = hi4;
+        *reinterpret_cast<float4*>(planes + plane + off) = lo4;
     }
 }
 
@@ -881,20 +928,45 @@ size_t ic_nn_bn_workspace_bytes(int64_t M, int C) {
 int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps, int relu,
                        int use_stats, const float* d_res1, const float* d_res2, float* d_mean, float* d_invstd,
                        float* d_mov_mean, float* d_mov_var, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    return ic_nn_bn_train_fwd_ex(d_x, M, C, d_gamma, d_beta, eps, relu, use_stats, d_res1, d_res2, d_mean, d_invstd, d_mov_mean,
+                                 d_mov_var, d_out, nullptr, nullptr, 0, d_workspace, workspace_bytes, stream);
+}
+
+/* ic_nn_bn_train_fwd with the two fusions of the tensor-core trunk: d_partial_in (optional) = the statistics partial sums
+ * ic_nn_conv3x3_tc_fused accumulated while it wrote d_x (skips the statistics pass over d_x); d_planes_out (optional, C % 8 == 0,
+ * 2 M C fp16 elements) receives the fp16 hi/lo planes [plane][M / hw][C / 8][hw][8] of d_out for the next conv. */
+int ic_nn_bn_train_fwd_ex(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps, int relu,
+                          int use_stats, const float* d_res1, const float* d_res2, float* d_mean, float* d_invstd,
+                          float* d_mov_mean, float* d_mov_var, float* d_out, const double* d_partial_in, void* d_planes_out,
+                          int64_t hw, void* d_workspace, size_t workspace_bytes, void* stream) {
     IC_REQUIRE(d_x && d_gamma && d_beta && d_mean && d_invstd && d_out, IC_ERR_INVALID, "ic_nn_bn_train_fwd: NULL argument");
     IC_REQUIRE(M > 0 && C > 0 && C <= 128, IC_ERR_INVALID, "ic_nn_bn_train_fwd: bad shape (C <= 128)");
+    IC_REQUIRE(!d_partial_in || C == 128, IC_ERR_INVALID, "ic_nn_bn_train_fwd_ex: partial sums are those of a 128-channel conv");
+    IC_REQUIRE(!d_planes_out || (C % 8 == 0 && hw > 0 && M % hw == 0), IC_ERR_INVALID, "ic_nn_bn_train_fwd_ex: planes need C % 8 == 0 and M = n hw");
     cudaStream_t s = (cudaStream_t)stream;
     if (use_stats) {
-        IC_REQUIRE(d_workspace && workspace_bytes >= ic_nn_bn_workspace_bytes(M, C), IC_ERR_WORKSPACE, "ic_nn_bn_train_fwd: workspace");
         const int blocks = (int)((M + CR_ROWS - 1) / CR_ROWS);
-        ColArgs a;
-        memset(&a, 0, sizeof(a));
-        a.x = d_x; a.M = M; a.C = C; a.mode = 0;
-        col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
+        const double* partial = d_partial_in;
+        if (!partial) {
+            IC_REQUIRE(d_workspace && workspace_bytes >= ic_nn_bn_workspace_bytes(M, C), IC_ERR_WORKSPACE, "ic_nn_bn_train_fwd: workspace");
+            ColArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x = d_x; a.M = M; a.C = C; a.mode = 0;
+            col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
+            IC_CHECK_LAUNCH();
+            partial = (const double*)d_workspace;
+        }
+        col_finalize_kernel<<<C, 128, 0, s>>>(partial, blocks, C, M, 0, eps, d_mean, d_invstd, d_mov_mean, d_mov_var, 0.9f, d_x);
         IC_CHECK_LAUNCH();
-        col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 0, eps, d_mean, d_invstd,
-                                                         d_mov_mean, d_mov_var, 0.9f, d_x);
+    }
+    if (d_planes_out) {
+        IC_REQUIRE((((uintptr_t)d_x | (uintptr_t)d_out | (uintptr_t)d_res1 | (uintptr_t)d_res2 | (uintptr_t)d_planes_out) & 15) == 0,
+                   IC_ERR_INVALID, "ic_nn_bn_train_fwd_ex: unaligned tensor");
+        bn_apply8_planes_kernel<<<ew_grid(M * C / 8), 256, 0, s>>>((const float4*)d_x, d_mean, d_invstd, d_gamma, d_beta, relu,
+                                                                   (const float4*)d_res1, (const float4*)d_res2, M * C / 8, C / 8, hw,
+                                                                   (float4*)d_out, (__half*)d_planes_out, M * C);
         IC_CHECK_LAUNCH();
+        return IC_OK;
     }
     const bool vec4 = C % 4 == 0 && (((uintptr_t)d_x | (uintptr_t)d_out | (uintptr_t)d_res1 | (uintptr_t)d_res2) & 15) == 0;
     if (vec4)

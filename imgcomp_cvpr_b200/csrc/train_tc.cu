@@ -95,8 +95,13 @@ __global__ void __launch_bounds__(256) finalize_scales_kernel(ScaleArgs a, float
 // Same stage order as tc::pack_weights (k = 3, stride 1): stage = (cin quarter q, tap), within a stage
 // [plane hi|lo][4 chunks][128 cout rows][8 cin]; values pre-scaled by sc[0] (a power of two).
 __global__ void __launch_bounds__(256) pack3x3_kernel(const float* __restrict__ w, int data_grad, const float* __restrict__ sc,
-                                                      __half* __restrict__ packed) {
+                                                      __half* __restrict__ packed, float* __restrict__ scale_out = nullptr,
+                                                      float* __restrict__ shift_out = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over (stage, chunk, cout row, cin-in-chunk)
+    if (scale_out && i < kC) {             // epilogue of the conv: undo the weight pre-scale (a power of two: exact)
+        scale_out[i] = 1.f / sc[0];
+        shift_out[i] = 0.f;
+    }
     if (i >= kStages * kPlaneElems) return;
     const int ei = i & 7, co = (i >> 3) & (kC - 1), ch = (i >> 10) & 3, s = i >> 12;
     const int q = s / kTaps, tap = s - q * kTaps;
@@ -390,6 +395,106 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     float s = 0.f;
     for (int k = 0; k < n_splits; ++k) s += partial[(size_t)k * kW + i];
     dw[i] = s / (params[0] * params[1]);
+}
+
+// ---- fused forward of a trunk layer (training): the conv reads the fp16 planes the previous batch-norm kernel wrote
+// (no maximum search, no split pass), and the pass that merges its output planes to float32 also accumulates the batch-norm
+// statistics of that output, in exactly the grouping of col_partial_kernel (train_ops.cu): 64 rows per block, a thread adds
+// 8 rows (r0 + g, r0 + g + 8, ...) in float32 around the channel's row-0 value, the 8 row groups of a block are added in
+// double -> the same mean / variance bits as the unfused path.
+__global__ void __launch_bounds__(256) weight_scales_kernel(const float* __restrict__ base, const int64_t* __restrict__ offsets,
+                                                            int64_t count, float* __restrict__ scales /* [n][4] */) {
+    __shared__ float red[8];
+    const float* w = base + offsets[blockIdx.x];
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < count; i += 256) m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        const float sc = pow2_scale(m, 8);
+        float* o = scales + 4 * blockIdx.x;        // {scale_w, scale_x, 1/scale_w, 1/scale_x}: the layout conv3x3_tc_bwd_ex takes
+        o[0] = sc;
+        o[1] = 1.f;
+        o[2] = 1.f / sc;
+        o[3] = 1.f;
+    }
+}
+
+constexpr int MS_ROWS = 64;       // = CR_ROWS of train_ops.cu
+
+__global__ void __launch_bounds__(128) merge_stats_kernel(const __half* __restrict__ in, int64_t hw, int64_t M, int64_t plane,
+                                                          float* __restrict__ out, double* __restrict__ partial /* [blocks][128][2] */) {
+    __shared__ float red[8][128][2];
+    const int g = threadIdx.x >> 4, chunk = threadIdx.x & 15;       // row group (a warp of col_partial_kernel), 8-channel chunk
+    const int64_t r0 = (int64_t)blockIdx.x * MS_ROWS;
+    float piv[8];
+    {
+        const float4 h4 = *reinterpret_cast<const float4*>(in + (size_t)chunk * hw * 8);          // row 0 = image 0, pixel 0
+        const float4 l4 = *reinterpret_cast<const float4*>(in + plane + (size_t)chunk * hw * 8);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&h4);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(h2[e]), b = __half22float2(l2[e]);
+            piv[2 * e] = a.x + b.x;
+            piv[2 * e + 1] = a.y + b.y;
+        }
+    }
+    float4 hv[MS_ROWS / 8], lv[MS_ROWS / 8];
+#pragma unroll
+    for (int k = 0; k < MS_ROWS / 8; ++k) {
+        const int64_t r = r0 + g + 8 * k;
+        if (r < M) {
+            const int64_t n = r / hw, rr = r - n * hw;
+            const size_t off = (((size_t)n * 16 + chunk) * hw + rr) * 8;
+            hv[k] = *reinterpret_cast<const float4*>(in + off);
+            lv[k] = *reinterpret_cast<const float4*>(in + plane + off);
+        }
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < MS_ROWS / 8; ++k) {
+        const int64_t r = r0 + g + 8 * k;
+        if (r < M) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&hv[k]);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&lv[k]);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 a = __half22float2(h2[e]), b = __half22float2(l2[e]);
+                v[2 * e] = a.x + b.x;
+                v[2 * e + 1] = a.y + b.y;
+            }
+            float4* dst = reinterpret_cast<float4*>(out + ((size_t)r * 16 + chunk) * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float q1 = v[e] - piv[e];
+                const float q2 = q1 * q1;
+                s1[e] += q1;
+                s2[e] += q2;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        red[g][chunk * 8 + e][0] = s1[e];
+        red[g][chunk * 8 + e][1] = s2[e];
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    double t1 = 0, t2 = 0;
+    for (int w = 0; w < 8; ++w) {
+        t1 += (double)red[w][c][0];
+        t2 += (double)red[w][c][1];
+    }
+    partial[((int64_t)blockIdx.x * 128 + c) * 2 + 0] = t1;
+    partial[((int64_t)blockIdx.x * 128 + c) * 2 + 1] = t2;
 }
 
 tc::GroupTable g_gt;
@@ -1142,6 +1247,80 @@ int ic_nn_tc_wgrad_plan_run(const ic_tc_wgrad_plan_t* plan, const float* d_x, co
         wgrad_gather_kernel<<<cdiv(p.n_dw, 256), 256, 0, s>>>(partial, g.S, (int64_t)split_stride, p.d_map, p.n_dw, params, d_dw);
         IC_CHECK_LAUNCH();
     }
+    return IC_OK;
+}
+
+
+/* ---- fused forward of the trunk layers in the training step (see merge_stats_kernel) */
+/* scales of n equally sized weight tensors at d_base + d_offsets[i] (count floats each): d_scales[4 i ..] = {2^e, 1, 2^-e, 1} with
+ * 2^e the power of two that brings the largest magnitude into [2^7, 2^8) -- the rule of ic_nn_conv3x3_tc; one launch per step */
+int ic_nn_weight_scales(const float* d_base, const int64_t* d_offsets, int n, int64_t count, float* d_scales, void* stream) {
+    IC_REQUIRE(d_base && d_offsets && d_scales && n > 0 && count > 0, IC_ERR_INVALID, "ic_nn_weight_scales: bad argument");
+    ProfScope ps(IC_PROF_ELEMENTWISE, (cudaStream_t)stream);
+    weight_scales_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(d_base, d_offsets, count, d_scales);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
+size_t ic_nn_conv3x3_tc_fused_workspace_bytes(int N, int H, int W) {
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    return align_up((size_t)N * H * W * kC * 2 * sizeof(__half), 256) + align_up((size_t)kStages * 2 * kPlaneElems * sizeof(__half), 256) + 8192;
+}
+
+size_t ic_nn_bn_partial_bytes(int64_t M) { return M > 0 ? (size_t)((M + MS_ROWS - 1) / MS_ROWS) * kC * 2 * sizeof(double) : 0; }
+
+/* y = conv3x3(x, w) for the 128 -> 128 trunk convs: d_x_planes = the UNSCALED fp16 hi/lo planes of x (what
+ * ic_nn_bn_train_fwd_ex wrote), d_wscale4 = this layer's row of ic_nn_weight_scales.  d_bn_partial (ic_nn_bn_partial_bytes(N H W))
+ * receives the batch-norm partial sums of y for ic_nn_bn_train_fwd_ex. */
+int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float* d_wscale4, int N, int H, int W, float* d_y,
+                           double* d_bn_partial, void* d_workspace, size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_x_planes && d_w && d_wscale4 && d_y && d_bn_partial && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_fused: NULL argument");
+    IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc_fused: bad shape");
+    IC_REQUIRE(workspace_bytes >= ic_nn_conv3x3_tc_fused_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_fused: workspace too small");
+    int rc = ensure_group_table();
+    if (rc != IC_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Arena ar(d_workspace, workspace_bytes);
+    const size_t elems = (size_t)N * H * W * kC;
+    __half* bo = ar.get<__half>(2 * elems);
+    __half* wp = ar.get<__half>((size_t)kStages * 2 * kPlaneElems);
+    float* scale = ar.get<float>(kC);
+    float* shift = ar.get<float>(kC);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_fused: workspace too small");
+    {
+        ProfScope ps(IC_PROF_ELEMENTWISE, s);
+        pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, 0, d_wscale4, wp, scale, shift);
+        IC_CHECK_LAUNCH();
+    }
+    tc::ConvTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = reinterpret_cast<const __half*>(d_x_planes);
+    a.Nimg = N;
+    a.in_chunks = kC / 8;
+    a.Hin = H;
+    a.Win = W;
+    a.weights = wp;
+    a.groups = &g_gt;
+    a.scale = scale;
+    a.shift = shift;
+    a.out = bo;
+    a.N = N;
+    a.H = H;
+    a.W = W;
+    a.cout = kC;
+    a.nout = kC;
+    a.halo0 = -1;
+    a.img_mul = 1;
+    a.head = -1;
+    a.cpg = 4;
+    a.exact = 1;
+    a.prof_class = IC_PROF_CONV3X3;
+    rc = tc::launch_conv_tc(a, s);
+    if (rc != IC_OK) return rc;
+    const int64_t M = (int64_t)N * H * W;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    merge_stats_kernel<<<(unsigned)((M + MS_ROWS - 1) / MS_ROWS), 128, 0, s>>>(bo, (int64_t)H * W, M, (int64_t)elems, d_y, d_bn_partial);
+    IC_CHECK_LAUNCH();
     return IC_OK;
 }
 

@@ -197,8 +197,11 @@ class TcWgradPlan(object):
         return dw_out
 
 
-def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None):
-    """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics."""
+def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None, partial=None,
+                 planes_out=None):
+    """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics.
+    partial: statistics partial sums of x from conv3x3_tc_fused (no statistics pass over x); planes_out (x N,H,W,C with
+    C % 8 == 0): float16 tensor of 2 * x.numel() elements that receives the hi/lo planes of out for the next 3x3 conv."""
     C = x.shape[-1]
     M = x.numel() // C
     out = torch.empty_like(x)
@@ -208,11 +211,43 @@ def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None
     else:
         mean, invstd = stats
     ws = _workspace(_lib.lib().ic_nn_bn_workspace_bytes(M, C))
-    _lib.check(_lib.lib().ic_nn_bn_train_fwd(_lib.ptr(_f32(x)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)), BN_EPS,
-                                            int(relu), int(stats is None), _lib.ptr(res1), _lib.ptr(res2), _lib.ptr(mean),
-                                            _lib.ptr(invstd), _lib.ptr(mov_mean), _lib.ptr(mov_var), _lib.ptr(out),
-                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    hw = 0
+    if planes_out is not None:
+        assert x.dim() == 4 and planes_out.dtype == torch.float16 and planes_out.numel() == 2 * x.numel()
+        hw = x.shape[1] * x.shape[2]
+    _lib.check(_lib.lib().ic_nn_bn_train_fwd_ex(_lib.ptr(_f32(x)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)), BN_EPS,
+                                               int(relu), int(stats is None), _lib.ptr(res1), _lib.ptr(res2), _lib.ptr(mean),
+                                               _lib.ptr(invstd), _lib.ptr(mov_mean), _lib.ptr(mov_var), _lib.ptr(out),
+                                               _lib.ptr(partial if stats is None else None), _lib.ptr(planes_out), hw,
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return out, mean, invstd
+
+
+def weight_scales(base, offsets, count, out):
+    """power-of-two scales of the len(offsets) weight tensors base[offsets[i] : offsets[i] + count] -> out (n, 4) float32:
+    row i = (scale, 1, 1 / scale, 1), the `scales` of conv3x3_tc_bwd's cache.  One launch."""
+    assert offsets.dtype == torch.int64 and out.shape == (offsets.numel(), 4)
+    _lib.check(_lib.lib().ic_nn_weight_scales(_lib.ptr(_f32(base)), _lib.ptr(offsets), offsets.numel(), count, _lib.ptr(_f32(out)),
+                                             _lib.stream_ptr()))
+    return out
+
+
+def bn_partial_buffer(M, device):
+    return torch.empty(_lib.lib().ic_nn_bn_partial_bytes(M) // 8, dtype=torch.float64, device=device)
+
+
+def conv3x3_tc_fused(x_planes, w, wscale, shape, partial):
+    """conv3x3_tc for an input that already exists as UNSCALED fp16 hi/lo planes (bn_train_fwd(planes_out=...)): no maximum
+    search, no split; -> y (float32 NHWC) and the batch-norm partial sums of y in `partial` (bn_partial_buffer)."""
+    N, H, W, C = shape
+    assert C == 128 and tuple(w.shape) == (3, 3, 128, 128) and x_planes.numel() == 2 * N * H * W * C
+    y = torch.empty(shape, dtype=torch.float32, device=w.device)
+    L = _lib.lib()
+    assert partial.numel() * 8 >= L.ic_nn_bn_partial_bytes(N * H * W)
+    ws = _workspace(L.ic_nn_conv3x3_tc_fused_workspace_bytes(N, H, W))
+    _lib.check(L.ic_nn_conv3x3_tc_fused(_lib.ptr(x_planes), _lib.ptr(_f32(w)), _lib.ptr(_f32(wscale)), N, H, W, _lib.ptr(y), _lib.ptr(partial),
+                                        _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return y
 
 
 def bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu=False, use_stats=True, dgamma=None, dbeta=None):

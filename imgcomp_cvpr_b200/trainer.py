@@ -207,6 +207,17 @@ class Trainer(object):
         for gname, g in self.groups.items():
             for key in g.slots:
                 self._group_of[key] = gname
+        # the 3x3 128 -> 128 trunk convs: their power-of-two weight scales are computed by ONE launch per step
+        self._trunk = [s for s, k, _, ci, co, _ in self.table if (k, ci, co) == (3, 128, 128)]
+        self._trunk_row = {s: i for i, s in enumerate(self._trunk)}
+        if self.device.type == 'cuda' and self._trunk:
+            g = self.groups['ae_w']
+            offs = [g.view(g.w, s + '/weights').data_ptr() - g.w.data_ptr() for s in self._trunk]
+            self._trunk_off = torch.tensor([o // 4 for o in offs], dtype=torch.int64, device=self.device)
+            self._trunk_scales = torch.zeros(len(self._trunk), 4, dtype=torch.float32, device=self.device)
+        self._planes_of = {}
+        self._stats_of = None
+        self._bn_partial = None
         self.tape = None
         self._adam_t = 0
         self._graph = None
@@ -304,13 +315,35 @@ class Trainer(object):
             return None, None, None
         return nn.TcPlan.get(kind, False, cin, cout), nn.TcPlan.get(kind, True, cin, cout), nn.TcWgradPlan.get(kind, cin, cout)
 
-    def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None, chans=None):
+    def _fused(self):
+        """trunk layers fused (batch norm writes the next conv's planes, the conv accumulates the next batch norm's
+        statistics); IC_TRAIN_FUSED=0 keeps the unfused sequence (A/B in tests)"""
+        return self.mode == 'exact' and os.environ.get('IC_TRAIN_FUSED', '1') != '0'
+
+    def _begin_pass(self):
+        """start of a forward pass: forget the planes of the previous pass, refresh the trunk convs' weight scales"""
+        self._planes_of = {}
+        self._stats_of = None
+        if self._fused() and self._trunk:
+            nn.weight_scales(self.groups['ae_w'].w, self._trunk_off, 9 * 128 * 128, self._trunk_scales)
+
+    def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None, chans=None, scope=None):
         tc = (self.mode == 'exact' and tuple(w.shape) == (3, 3, 128, 128) and stride == 1 and not transposed and not valid)
         plan_f = plan_d = plan_w = None
         if not tc and chans is not None and w.shape[0] == 5 and stride == 2 and not valid:
             plan_f, plan_d, plan_w = self._tc_plans('tconv5s2' if transposed else 'conv5s2', *chans)
         cache = None
-        if tc and self.tape is not None:        # keep the input's fp16 planes and the scales for the filter gradient
+        held = self._planes_of.get(x.data_ptr()) if (tc and scope in self._trunk_row and self._fused()) else None
+        if held is not None and held[0] is x:
+            # x exists as unscaled hi/lo planes (written by its batch norm): conv + merge-with-statistics, nothing else
+            M = x.numel() // 128
+            if self._bn_partial is None or self._bn_partial.numel() * 8 < _lib.lib().ic_nn_bn_partial_bytes(M):
+                self._bn_partial = nn.bn_partial_buffer(M, x.device)
+            wscale = self._trunk_scales[self._trunk_row[scope]]
+            y = nn.conv3x3_tc_fused(held[1], w, wscale, tuple(x.shape), self._bn_partial)
+            cache = (held[1], wscale)
+            self._stats_of = y
+        elif tc and self.tape is not None:        # keep the input's fp16 planes and the scales for the filter gradient
             y, cache = nn.conv3x3_tc(x, w, keep=True)
         elif plan_f is not None:
             y = plan_f.run(x, w)
@@ -344,12 +377,20 @@ class Trainer(object):
         gamma, beta = self._w(scope + '/BatchNorm/gamma'), self._w(scope + '/BatchNorm/beta')
         mm = self.stats.view(self.stats.w, scope + '/BatchNorm/moving_mean')
         mv = self.stats.view(self.stats.w, scope + '/BatchNorm/moving_variance')
+        planes = None
+        if self._fused() and x.dim() == 4 and x.shape[-1] == 128:
+            planes = torch.empty(2 * x.numel(), dtype=torch.float16, device=x.device)      # for the 3x3 conv that reads `out`
+        partial = self._bn_partial if self._stats_of is x else None
+        self._stats_of = None
         if self.is_training:
             upd = self.update_moving
-            out, mean, invstd = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, mm if upd else None, mv if upd else None)
+            out, mean, invstd = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, mm if upd else None, mv if upd else None,
+                                                partial=partial, planes_out=planes)
         else:           # moving statistics (code/autoencoder.py:115-125 with is_training=False)
             mean, invstd = mm, torch.rsqrt(mv + nn.BN_EPS)
-            out, _, _ = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, stats=(mean, invstd))
+            out, _, _ = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, stats=(mean, invstd), planes_out=planes)
+        if planes is not None:
+            self._planes_of[out.data_ptr()] = (out, planes)       # holds `out`: its address cannot be reused within the step
         if self.tape is not None:
             tape, training = self.tape, self.is_training
 
@@ -370,7 +411,7 @@ class Trainer(object):
     def _slim_conv(self, x, scope, relu, res1=None, res2=None, need_dx=True):
         """slim.conv2d / conv2d_transpose under _batch_norm_scope: conv (no bias) -> BN -> activation (+ fused adds)"""
         y = self._conv(x, self._w(scope + '/weights'), self._g(scope + '/weights'), self._stride[scope], self._tr[scope],
-                       need_dx=need_dx, chans=self._shape[scope][1:])
+                       need_dx=need_dx, chans=self._shape[scope][1:], scope=scope)
         return self._bn(y, scope, relu, res1, res2)
 
     def _res_stack(self, net, prefix, tag, final_scope):
@@ -504,11 +545,13 @@ class Trainer(object):
         -> dict(qbar, qhard, qsoft, symbols, z, heatmap) NCHW"""
         assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0
         self.is_training, self.update_moving, self.tape = is_training, update_moving, None
+        self._begin_pass()
         return self._encode(x.contiguous())
 
     def decode_forward(self, q, is_training=True, update_moving=False):
         """ae.decode(q, is_training) of code/train.py:102; q NCHW float32 -> x_out NCHW float32 clipped to [0, 255]"""
         self.is_training, self.update_moving, self.tape = is_training, update_moving, None
+        self._begin_pass()
         return self._decode(nn.nchw_to_nhwc(q.contiguous().float()))
 
     # ------------------------------------------------------------------ the graph of code/train.py:86-132
@@ -522,6 +565,7 @@ class Trainer(object):
         assert H % 8 == 0 and W % 8 == 0
         self.is_training, self.update_moving = is_training, update_moving
         self.tape = tape = _Tape() if backward else None
+        self._begin_pass()
         centers = self._w('autoencoder/encoder/centers')
         # pc.auto_pad_value(ae) = centers[0] (code/probclass.py:59-61), read on the device
         pad_value = centers if self.pc_config.use_centers_for_padding else 0.0
@@ -566,6 +610,7 @@ class Trainer(object):
         tape.fns.insert(n_enc, hq_bwd)
         tape.backward()
         self.tape = None
+        self._planes_of = {}
         return tensors
 
     def _read_losses(self, shape, n_symbols, tensors):

@@ -270,6 +270,20 @@ int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma,
                        int relu, int use_stats, const float* d_res1, const float* d_res2, float* d_mean,
                        float* d_invstd, float* d_mov_mean, float* d_mov_var, float* d_out,
                        void* d_workspace, size_t workspace_bytes, void* stream);
+/* The trunk layers of the training step fused: the batch norm writes the fp16 hi/lo planes the next 3x3 conv reads
+ * (d_planes_out), the conv's output pass accumulates the next batch norm's statistics (d_bn_partial -> d_partial_in), and the
+ * power-of-two weight scales of all trunk convs come from ONE launch per step (ic_nn_weight_scales; d_scales n x 4 floats,
+ * row i = {scale, 1, 1/scale, 1} = the d_scales argument of ic_nn_conv3x3_tc_bwd_ex).  Same arithmetic as the unfused
+ * sequence ic_nn_conv3x3_tc + ic_nn_bn_train_fwd, except that the activations are split unscaled (as at inference). */
+int ic_nn_weight_scales(const float* d_base, const int64_t* d_offsets, int n, int64_t count, float* d_scales, void* stream);
+size_t ic_nn_conv3x3_tc_fused_workspace_bytes(int N, int H, int W);
+size_t ic_nn_bn_partial_bytes(int64_t M);
+int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float* d_wscale4, int N, int H, int W, float* d_y,
+                           double* d_bn_partial, void* d_workspace, size_t workspace_bytes, void* stream);
+int ic_nn_bn_train_fwd_ex(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps, int relu,
+                          int use_stats, const float* d_res1, const float* d_res2, float* d_mean, float* d_invstd,
+                          float* d_mov_mean, float* d_mov_var, float* d_out, const double* d_partial_in, void* d_planes_out,
+                          int64_t hw, void* d_workspace, size_t workspace_bytes, void* stream);
 int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, const float* d_gamma,
                        const float* d_beta, int relu, int use_stats, const float* d_mean, const float* d_invstd,
                        float* d_dx, float* d_dgamma, float* d_dbeta,

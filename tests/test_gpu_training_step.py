@@ -335,3 +335,24 @@ def test_distortion_backward_kernel():
         d, m = nn.distortion_bwd(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), psnr=psnr)
         np.testing.assert_allclose(m.cpu().numpy(), mse.detach().numpy(), rtol=1e-6)
         assert _rel(d.cpu().numpy(), yt.grad.numpy()) < 1e-6
+
+
+def test_fused_trunk_matches_unfused_sequence(synth, monkeypatch):
+    """mode='exact' with the trunk fusions (batch norm writes the next conv's fp16 planes, the conv's output pass accumulates
+    the next batch norm's statistics, one weight-scale launch per step) against the unfused sequence of the same kernels
+    (IC_TRAIN_FUSED=0).  The statistics are summed in the same grouping, so the only difference is that activations are
+    split unscaled instead of pre-scaled by a power of two: identical symbols, losses to 1e-6, gradients to 1e-4."""
+    outs, grads = [], []
+    for fused in ('0', '1'):
+        monkeypatch.setenv('IC_TRAIN_FUSED', fused)
+        ae_cfg, pc_cfg, Wt, x, tr = _setup(synth, 'cvpr/low', 2, 64, 64, seed=22, mode='exact')
+        outs.append(tr.forward_backward(torch.from_numpy(x).cuda()))
+        grads.append(tr.gradients())
+    monkeypatch.delenv('IC_TRAIN_FUSED', raising=False)
+    a, b = outs
+    assert torch.equal(a['tensors']['symbols'], b['tensors']['symbols'])
+    for k in ('total_loss', 'd_loss_scaled', 'pc_loss', 'ms_ssim'):
+        assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    errs = sorted((_rel(grads[1][k], grads[0][k]), k) for k in grads[0])
+    print('fused vs unfused trunk: worst gradient difference %.2e (%s), median %.2e' % (errs[-1][0], errs[-1][1], errs[len(errs) // 2][0]))
+    assert errs[-1][0] < 1e-4
