@@ -256,7 +256,7 @@ constexpr int CR_ROWS = 64;       // rows per block (8 per warp): enough blocks 
 
 // A thread adds its 8 rows in float32 (8 terms: ~1e-7 relative), everything above that -- the 8 warps of the block,
 // the blocks -- is summed in double in a fixed order.
-__global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __restrict__ partial /* [blocks][C][2] */) {
+__global__ void __launch_bounds__(256, 3) col_partial_kernel(ColArgs a, double* __restrict__ partial /* [blocks][C][2] */) {
     __shared__ float red[8][128][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * CR_ROWS;
@@ -279,18 +279,22 @@ __global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __r
                 be[u] = a.beta[c0 + u];
             }
         }
-        float4 xv[CR_ROWS / 8], dv[CR_ROWS / 8];
+        // two batches of 4 rows: 8 (mode 0) / 16 (mode 1) 16-byte loads in flight per thread at 64 registers, 4 blocks per SM
 #pragma unroll
-        for (int k = 0; k < CR_ROWS / 8; ++k) {
-            const int64_t r = r0 + warp + 8 * k;
+        for (int kb = 0; kb < CR_ROWS / 8; kb += 4) {
+        float4 xv[4], dv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t r = r0 + warp + 8 * (kb + k);
+            dv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < r1) {
                 xv[k] = *reinterpret_cast<const float4*>(a.x + r * 128 + c0);
                 if (a.mode != 0) dv[k] = *reinterpret_cast<const float4*>(a.dy + r * 128 + c0);
             }
         }
 #pragma unroll
-        for (int k = 0; k < CR_ROWS / 8; ++k) {
-            const int64_t r = r0 + warp + 8 * k;
+        for (int k = 0; k < 4; ++k) {
+            const int64_t r = r0 + warp + 8 * (kb + k);
             if (r < r1) {
                 const float xe[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
                 const float de[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(256) col_partial_kernel(ColArgs a, double* __r
                     s2[u] += q2;
                 }
             }
+        }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

@@ -46,7 +46,8 @@ def test_layer_against_float64(gpu_models):
     x = torch.randn((1, 32, 32, 128), device='cuda', generator=g)
     scope = 'autoencoder/encoder/res_block_enc_0/enc_0_1/conv1'
     w = torch.from_numpy(W[scope + '/weights']).double().cuda().permute(3, 2, 0, 1)
-    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w, padding=1)
+    # float64 reference on the CPU: the first float64 cuDNN convolution of a process can spend minutes in cuDNN's own set-up
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2).cpu(), w.cpu(), padding=1).cuda()
     bn = {k: torch.from_numpy(W[scope + '/BatchNorm/' + k]).double().cuda() for k in
           ('gamma', 'beta', 'moving_mean', 'moving_variance')}
     y = (y - bn['moving_mean'][None, :, None, None]) / torch.sqrt(bn['moving_variance'] + 1e-5)[None, :, None, None] \
@@ -82,7 +83,7 @@ def test_accumulate_gain_against_float64(synth, monkeypatch):
         monkeypatch.setenv('IC_TC_ACC_GAIN', gain)
         ae = autoencoder.get_network_cls(a)(a, weights=W, mode='exact')
         for name, x in inputs.items():
-            pre = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+            pre = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2).cpu(), w.cpu(), padding=1).cuda().permute(0, 2, 3, 1)
             out = _conv(ae, 0, 1, x, None, None, 'exact').double()
             acc = (out - bn['beta']) / sc + bn['moving_mean']
             m = pre.abs() > 0.2 * pre.pow(2).mean().sqrt()
