@@ -8,6 +8,7 @@
 // call (148 K weights: two tiny kernels); activations go fp32 NHWC -> hi/lo planes -> conv -> planes -> fp32 NHWC
 // because the batch-norm kernels around the conv work on float32 NHWC.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -94,9 +95,10 @@ __global__ void __launch_bounds__(256) finalize_scales_kernel(ScaleArgs a, float
 
 // Same stage order as tc::pack_weights (k = 3, stride 1): stage = (cin quarter q, tap), within a stage
 // [plane hi|lo][4 chunks][128 cout rows][8 cin]; values pre-scaled by sc[0] (a power of two).
+// pair = 1: the layout of tc::repack_pair, [stage][cout half][plane][4 chunks][64 rows][8 cin] (CTA-pair kernel, cta_group::2)
 __global__ void __launch_bounds__(256) pack3x3_kernel(const float* __restrict__ w, int data_grad, const float* __restrict__ sc,
                                                       __half* __restrict__ packed, float* __restrict__ scale_out = nullptr,
-                                                      float* __restrict__ shift_out = nullptr) {
+                                                      float* __restrict__ shift_out = nullptr, int pair = 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over (stage, chunk, cout row, cin-in-chunk)
     if (scale_out && i < kC) {             // epilogue of the conv: undo the weight pre-scale (a power of two: exact)
         scale_out[i] = 1.f / sc[0];
@@ -115,6 +117,12 @@ __global__ void __launch_bounds__(256) pack3x3_kernel(const float* __restrict__ 
     v *= sc[0];
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
+    if (pair) {
+        const size_t base = (size_t)s * 2 * kPlaneElems + ((((size_t)(co >> 6) * 2 + 0) * 4 + ch) * 64 + (co & 63)) * 8 + ei;
+        packed[base] = hi;
+        packed[base + 4 * 64 * 8] = lo;       // next plane of the same half
+        return;
+    }
     const size_t base = (size_t)s * 2 * kPlaneElems + (size_t)(ch * kC + co) * 8 + ei;
     packed[base] = hi;
     packed[base + kPlaneElems] = lo;
@@ -526,13 +534,20 @@ int wgrad_splits(int N, int H, int W) {
     return std::max(1, std::min(sms / 3, n_tiles));
 }
 
+// CTA pairs (cta_group::2) like the inference path (api.cu): IC_CONV_PAIR=0 selects the single-CTA kernel
+bool use_pair(int W) {
+    const char* e = getenv("IC_CONV_PAIR");
+    return W > 8 && !(e && atoi(e) == 0);
+}
+
 // conv over planes `in` (already split and pre-scaled) with weights d_w scaled by params[0] -> float32 NHWC, multiplied
 // by unscale[0] (the inverse of the input's pre-scale) when the planes are merged back
 int conv_planes(const __half* in, const float* d_w, int data_grad, const float* params, const float* unscale, const float* scale,
                 const float* shift, __half* wp, __half* bo, int N, int H, int W, float* d_y, cudaStream_t s) {
+    const bool pair = use_pair(W);
     {
         ProfScope ps(IC_PROF_ELEMENTWISE, s);
-        pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, data_grad, params, wp);
+        pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, data_grad, params, wp, nullptr, nullptr, pair ? 1 : 0);
         IC_CHECK_LAUNCH();
     }
     tc::ConvTcArgs a;
@@ -543,6 +558,7 @@ int conv_planes(const __half* in, const float* d_w, int data_grad, const float* 
     a.Hin = H;
     a.Win = W;
     a.weights = wp;
+    a.weights_pair = pair ? wp : nullptr;
     a.groups = &g_gt;
     a.scale = scale;
     a.shift = shift;
@@ -1287,9 +1303,10 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
     float* scale = ar.get<float>(kC);
     float* shift = ar.get<float>(kC);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_fused: workspace too small");
+    const bool pair = use_pair(W);
     {
         ProfScope ps(IC_PROF_ELEMENTWISE, s);
-        pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, 0, d_wscale4, wp, scale, shift);
+        pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, 0, d_wscale4, wp, scale, shift, pair ? 1 : 0);
         IC_CHECK_LAUNCH();
     }
     tc::ConvTcArgs a;
@@ -1300,6 +1317,7 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
     a.Hin = H;
     a.Win = W;
     a.weights = wp;
+    a.weights_pair = pair ? wp : nullptr;
     a.groups = &g_gt;
     a.scale = scale;
     a.shift = shift;
