@@ -340,12 +340,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                         const uint64_t a_t = a_g + (uint64_t)(dy * C::HALO_W + dx);
                         const uint64_t w_t = w_desc0 + (uint64_t)slot * (NPL * kWPlane);
                         const uint32_t first0 = (g | ti) == 0 ? 0u : 1u;
+                        // context model, <= 24 input channels (3 chunks): k-step 1 of a tap holds one real chunk and one
+                        // all-zero chunk.  With pair_c2 the real chunks of taps 2j and 2j+1 share one k-step instead: A's two
+                        // K core matrices are then (tap 2j, chunk 2) and (tap 2j+1, chunk 2), i.e. LBO = the tap shift, and
+                        // B's are chunk 2 of the two taps' resident stages, LBO = the stage pitch -- descriptor fields only,
+                        // no other layout.  22 instead of 28 k-steps per tile for these A-fetch-bound MMAs.
+                        const bool pairing = CAT && p.pair_c2;
+                        const bool do_ks1 = !pairing || ((ti & 1) == 0 && ti == nt - 1);      // unpaired last tap of an odd group
+                        uint64_t a_pr = 0, w_pr = 0;
+                        if (pairing && (ti & 1)) {
+                            const int tp = gt.taps[g][ti - 1];
+                            const uint64_t a_prev = a_g + (uint64_t)((tp / 3) * C::HALO_W + (tp % 3));
+                            const uint64_t w_prev = w_t - (uint64_t)(NPL * kWPlane);
+                            constexpr uint64_t kALboF = (uint64_t)(kALbo >> 4), kWLboF = (uint64_t)(((CAT ? 2 : 1) * W_ROWS * 16) >> 4);
+                            a_pr = a_prev + kAKs - (kALboF << 16) + ((a_t - a_prev) << 16);
+                            w_pr = w_prev + kWKs - (kWLboF << 16) + ((uint64_t)(NPL * kWPlane) << 16);
+                        }
                         if (elect_one()) {
 #pragma unroll
                             for (int t = 0; t < T; ++t) {
                                 const uint32_t d_tmem = tmem_base + (set * T + t) * C::NCOL;
+                                if (CAT && pairing && (ti & 1)) {
+                                    umma_f16(d_tmem, a_pr + (uint64_t)(t * TW), w_pr, IDESC_CAT, 1u);
+                                    umma_f16(d_tmem + NOUT, a_pr + (uint64_t)(t * TW) + kAPlane, w_pr, IDESC, 1u);
+                                }
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks) {
+                                    if (ks == 1 && !do_ks1) continue;
                                     const uint64_t a_hi = a_t + (uint64_t)(t * TW) + ks * kAKs;
                                     const uint64_t w_hi = w_t + ks * kWKs;
                                     const uint32_t first = ks == 0 ? first0 : 1u;
@@ -1095,6 +1116,10 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.img_div_mul = a.img_div_mul;
     p.img_off_mul = a.img_off_mul ? a.img_off_mul : 1;
     p.img_base = a.img_base;
+    {
+        const char* pe = getenv("IC_PC_PAIR_CHUNKS");
+        p.pair_c2 = (WRES && a.pair_c2 && !(pe && atoi(pe) == 0)) ? 1 : 0;
+    }
     p.res_H = a.res_H ? a.res_H : a.H;
     p.res_W = a.res_W ? a.res_W : a.W;
     p.res_dy = a.res_dy;
@@ -1108,7 +1133,12 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     // IC_TC_ACC_GAIN=0 switches the compensation off (tests/test_gpu_conv_tc.py measures both against float64)
     const char* gain_env = getenv("IC_TC_ACC_GAIN");
     // (B-concatenated instantiations apply it to the main accumulator alone: eff_ksteps accumulate steps)
-    p.acc_gain = (gain_env && atoi(gain_env) == 0) ? 1.0f : 1.0f + 1.606e-8f * (float)(a.groups->eff_ksteps * ((NPL == 2 && !WRES) ? 3 : 1));
+    int acc_steps = a.groups->eff_ksteps * ((NPL == 2 && !WRES) ? 3 : 1);
+    if (WRES && a.pair_c2 && a.groups->eff_ksteps == 2 * a.groups->nstages) {       // paired third chunks: fewer accumulate steps
+        acc_steps = a.groups->nstages;
+        for (int g = 0; g < a.groups->ngroups; ++g) acc_steps += (a.groups->ntaps[g] + 1) / 2;
+    }
+    p.acc_gain = (gain_env && atoi(gain_env) == 0) ? 1.0f : 1.0f + 1.606e-8f * (float)acc_steps;
     p.out_s2d = a.out_s2d;
     p.d2s_cch = a.d2s_cch;
     p.d2s_ph0 = a.d2s_ph0;

@@ -38,6 +38,9 @@ struct ConvTcParams {
     // ... + img_base, with img_off[group] multiplied by img_off_mul (depth-major training volumes: one depth slice = N images;
     // the data gradient reads slice s - 1, i.e. img_base = -N: negative image coordinates are TMA zero fill)
     int img_off_mul, img_base;
+    // resident-weight (context model) kernels with <= 24 real input channels: the third 8-channel chunk of two consecutive
+    // taps forms ONE k-step (see the issue loop) instead of two half-empty ones
+    int pair_c2;
     // geometry of res1 (context model: a crop of a larger tensor); res2 always has the output geometry
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;
@@ -72,6 +75,7 @@ struct ConvTcArgs {
     int relu, cout, nout;       // nout: padded output channels the weights were packed for (128 or 48)
     int halo0, img_mul, img_div, img_div_mul;
     int img_off_mul, img_base;  // see ConvTcParams (img_off_mul = 0 means 1)
+    int pair_c2;                // see ConvTcParams (the input has <= 24 channels: chunk 3 is all zero)
     int pc_f32;                 // context-model layer (resident weights, B-concatenation) with float32 NHWC output (training)
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;

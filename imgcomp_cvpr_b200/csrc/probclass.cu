@@ -427,6 +427,7 @@ int run_pc_tc(const PcWeights& w, const PcInput& in, int head, float* out_f, int
         c.cpg = 4;
         c.exact = 1;
         c.head = -1;
+        c.pair_c2 = 1;                          // 24 channels: chunk 3 of every input voxel is zero
         c.prof_class = IC_PROF_PROBCLASS;
         if (l < 3) {
             c.out = a[l];

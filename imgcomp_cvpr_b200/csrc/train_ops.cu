@@ -234,6 +234,7 @@ struct ColArgs {
     const float *mean, *invstd, *gamma, *beta;
     int64_t M;
     int C, relu, mode;
+    float* maxout;      // mode 1, C == 128, optional: [blocks][128][2] = max |dyr|, max |xhat| per block and channel
 };
 
 __device__ __forceinline__ void col_terms(const ColArgs& a, int64_t row, int c, float& q1, float& q2) {
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(256, 3) col_partial_kernel(ColArgs a, double* 
         // summed by ONE thread over the same rows in the same order as in the scalar loop below: same bits.
         const int c0 = 4 * lane;
         float pv[4] = {0.f, 0.f, 0.f, 0.f}, mu[4], is[4], ga[4], be[4];
+        float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (a.mode == 0) {
@@ -310,6 +312,8 @@ __global__ void __launch_bounds__(256, 3) col_partial_kernel(ColArgs a, double* 
                         if (a.relu && fmaf(xh, ga[u], be[u]) <= 0.f) dy = 0.f;
                         q1 = dy;
                         q2 = dy * xh;
+                        m1[u] = fmaxf(m1[u], fabsf(dy));
+                        m2[u] = fmaxf(m2[u], fabsf(xh));
                     }
                     s1[u] += q1;
                     s2[u] += q2;
@@ -321,6 +325,24 @@ __global__ void __launch_bounds__(256, 3) col_partial_kernel(ColArgs a, double* 
         for (int u = 0; u < 4; ++u) {
             red[warp][c0 + u][0] = s1[u];
             red[warp][c0 + u][1] = s2[u];
+        }
+        if (a.maxout) {          // block maxima through the same buffer, before the sums are consumed
+            __shared__ float redm[8][128][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                redm[warp][c0 + u][0] = m1[u];
+                redm[warp][c0 + u][1] = m2[u];
+            }
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                float a1 = 0.f, a2 = 0.f;
+                for (int w = 0; w < 8; ++w) {
+                    a1 = fmaxf(a1, redm[w][threadIdx.x][0]);
+                    a2 = fmaxf(a2, redm[w][threadIdx.x][1]);
+                }
+                a.maxout[((int64_t)blockIdx.x * 128 + threadIdx.x) * 2 + 0] = a1;
+                a.maxout[((int64_t)blockIdx.x * 128 + threadIdx.x) * 2 + 1] = a2;
+            }
         }
     } else {
         for (int64_t r = r0 + warp; r < r1; r += 8) {
@@ -357,9 +379,21 @@ __global__ void __launch_bounds__(256, 3) col_partial_kernel(ColArgs a, double* 
 __global__ void __launch_bounds__(128) col_finalize_kernel(const double* __restrict__ partial, int blocks, int C, int64_t M, int mode,
                                                            float eps, float* __restrict__ o1, float* __restrict__ o2,
                                                            float* __restrict__ mov_mean, float* __restrict__ mov_var, float decay,
-                                                           const float* __restrict__ pivot_row /* mode 0: x row 0 */) {
+                                                           const float* __restrict__ pivot_row /* mode 0: x row 0 */,
+                                                           const float* __restrict__ maxin = nullptr, const float* __restrict__ gamma = nullptr,
+                                                           const float* __restrict__ invstd = nullptr, float* __restrict__ bound = nullptr) {
     __shared__ double r1[128], r2[128];
+    __shared__ float rm[128][2];
     const int c = blockIdx.x;
+    if (maxin) {        // mode 1: channel maxima of |dyr| and |xhat| over the blocks (order independent)
+        float a1 = 0.f, a2 = 0.f;
+        for (int b = threadIdx.x; b < blocks; b += 128) {
+            a1 = fmaxf(a1, maxin[((int64_t)b * C + c) * 2 + 0]);
+            a2 = fmaxf(a2, maxin[((int64_t)b * C + c) * 2 + 1]);
+        }
+        rm[threadIdx.x][0] = a1;
+        rm[threadIdx.x][1] = a2;
+    }
     double s1 = 0, s2 = 0;
     for (int b = threadIdx.x; b < blocks; b += 128) {
         s1 += partial[((int64_t)b * C + c) * 2 + 0];
@@ -372,12 +406,21 @@ __global__ void __launch_bounds__(128) col_finalize_kernel(const double* __restr
         if (threadIdx.x < o) {
             r1[threadIdx.x] += r1[threadIdx.x + o];
             r2[threadIdx.x] += r2[threadIdx.x + o];
+            if (maxin) {
+                rm[threadIdx.x][0] = fmaxf(rm[threadIdx.x][0], rm[threadIdx.x + o][0]);
+                rm[threadIdx.x][1] = fmaxf(rm[threadIdx.x][1], rm[threadIdx.x + o][1]);
+            }
         }
         __syncthreads();
     }
     if (threadIdx.x != 0) return;
     s1 = r1[0];
     s2 = r2[0];
+    if (maxin) {
+        // |dx| = |gamma invstd (dyr - dbeta / M - xhat dgamma / M)| <= this, for every element of the channel
+        const float inv_m = 1.f / (float)M;
+        bound[c] = fabsf(gamma[c] * invstd[c]) * (rm[0][0] + fabsf((float)s1) * inv_m + rm[0][1] * fabsf((float)s2) * inv_m);
+    }
     if (mode == 0) {
         const double dm = s1 / (double)M;                       // mean of (x - pivot)
         const double mean = (double)pivot_row[c] + dm;
@@ -505,6 +548,73 @@ __global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const float4* __rest
             o[u] = gamma[c + u] * invstd[c + u] * d;
         }
         dx[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// The backward of a trunk layer's batch norm feeds exactly one consumer, the 3x3 conv's backward on tensor cores, which reads
+// fp16 hi/lo planes pre-scaled by a power of two: this variant writes THOSE (no float32 dx, no maximum search, no split
+// pass).  The scale comes from the per-channel bounds of col_finalize_kernel (>= the true maximum, typically within a few
+// percent: the same binade or the next one) and is stored in scale_out = {s, 1/s} for the conv.
+__global__ void __launch_bounds__(256) bn_bwd_apply8_planes_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                                   const float* __restrict__ bound, int relu, int64_t total8, int64_t hw,
+                                                                   float inv_m, __half* __restrict__ planes, int64_t plane,
+                                                                   float* __restrict__ scale_out) {
+    __shared__ float sred[4];
+    __shared__ float s_scale;
+    if (threadIdx.x < 128) {
+        float m = bound[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float mx = fmaxf(fmaxf(sred[0], sred[1]), fmaxf(sred[2], sred[3]));
+        float sc = 1.f;
+        if (mx > 0.f && isfinite(mx)) {         // largest magnitude into [2^5, 2^6): the rule of train_tc.cu for gradients
+            int ex;
+            frexpf(mx, &ex);
+            sc = ldexpf(1.f, 6 - ex);
+        }
+        s_scale = sc;
+        if (blockIdx.x == 0) {
+            scale_out[0] = sc;
+            scale_out[1] = 1.f / sc;
+        }
+    }
+    __syncthreads();
+    const float g = s_scale;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i & 15);
+        const int64_t r = i >> 4;
+        const int c = 8 * chunk;
+        const float4 xa = x[2 * i], xb = x[2 * i + 1], da = dy[2 * i], db = dy[2 * i + 1];
+        const float xe[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float de[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float xh = (xe[u] - mean[c + u]) * invstd[c + u];
+            float d = de[u];
+            if (relu && fmaf(xh, gamma[c + u], beta[c + u]) <= 0.f) d = 0.f;
+            d = d - dbeta[c + u] * inv_m - xh * dgamma[c + u] * inv_m;
+            v[u] = gamma[c + u] * invstd[c + u] * d * g;
+        }
+        float4 hi4, lo4;
+        __half2* hi = reinterpret_cast<__half2*>(&hi4);
+        __half2* lo = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            hi[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            const float2 hf = __half22float2(hi[e]);
+            lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        }
+        const int64_t n = r / hw, rr = r - n * hw;
+        const size_t off = (((size_t)n * 16 + chunk) * hw + rr) * 8;
+        *reinterpret_cast<float4*>(planes + off) = hi4;
+        *reinterpret_cast<float4*>(planes + plane + off) = lo4;
     }
 }
 
@@ -922,7 +1032,8 @@ int ic_nn_conv2d_bwd_filter(const float* d_x, const float* d_dy, int N, int Hi, 
 size_t ic_nn_bn_workspace_bytes(int64_t M, int C) {
     if (M <= 0 || C <= 0 || C > 128) return 0;
     const int64_t blocks = (M + CR_ROWS - 1) / CR_ROWS;
-    return (size_t)blocks * C * 2 * sizeof(double) + 256;
+    // partial sums (double) + the block maxima and channel bounds of ic_nn_bn_train_bwd_ex (float, C = 128)
+    return (size_t)blocks * C * 2 * sizeof(double) + (size_t)blocks * 128 * 2 * sizeof(float) + 128 * sizeof(float) + 256;
 }
 
 /* slim.batch_norm(is_training=True): statistics of x (M rows, C channels), then
@@ -987,20 +1098,44 @@ int ic_nn_bn_train_fwd_ex(const float* d_x, int64_t M, int C, const float* d_gam
 int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, const float* d_gamma, const float* d_beta, int relu,
                        int use_stats, const float* d_mean, const float* d_invstd, float* d_dx, float* d_dgamma, float* d_dbeta,
                        void* d_workspace, size_t workspace_bytes, void* stream) {
-    IC_REQUIRE(d_x && d_dy && d_gamma && d_beta && d_mean && d_invstd && d_dx && d_dgamma && d_dbeta && d_workspace,
+    return ic_nn_bn_train_bwd_ex(d_x, d_dy, M, C, d_gamma, d_beta, relu, use_stats, d_mean, d_invstd, d_dx, d_dgamma, d_dbeta, nullptr,
+                                 nullptr, 0, d_workspace, workspace_bytes, stream);
+}
+
+/* ic_nn_bn_train_bwd whose dx goes to a tensor-core conv backward: d_dx_planes (C = 128, batch statistics; 2 M C fp16
+ * elements) receives the fp16 hi/lo planes [plane][M / hw][16][hw][8] of dx * s, d_scale_out = {s, 1/s} with s the power of
+ * two that brings an upper bound of max |dx| into [2^5, 2^6); d_dx may then be NULL (no float32 copy is written). */
+int ic_nn_bn_train_bwd_ex(const float* d_x, const float* d_dy, int64_t M, int C, const float* d_gamma, const float* d_beta, int relu,
+                          int use_stats, const float* d_mean, const float* d_invstd, float* d_dx, float* d_dgamma, float* d_dbeta,
+                          void* d_dx_planes, float* d_scale_out, int64_t hw, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+    IC_REQUIRE(d_x && d_dy && d_gamma && d_beta && d_mean && d_invstd && (d_dx || d_dx_planes) && d_dgamma && d_dbeta && d_workspace,
                IC_ERR_INVALID, "ic_nn_bn_train_bwd: NULL argument");
     IC_REQUIRE(M > 0 && C > 0 && C <= 128, IC_ERR_INVALID, "ic_nn_bn_train_bwd: bad shape (C <= 128)");
     IC_REQUIRE(workspace_bytes >= ic_nn_bn_workspace_bytes(M, C), IC_ERR_WORKSPACE, "ic_nn_bn_train_bwd: workspace");
+    IC_REQUIRE(!d_dx_planes || (C == 128 && use_stats && d_scale_out && hw > 0 && M % hw == 0 && !d_dx), IC_ERR_INVALID,
+               "ic_nn_bn_train_bwd_ex: planes need C = 128, batch statistics, M = n hw and no float32 dx");
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = (int)((M + CR_ROWS - 1) / CR_ROWS);
+    // workspace: [blocks][C][2] double partial sums | (planes) [blocks][128][2] float maxima | [128] float bounds
+    float* maxbuf = d_dx_planes ? (float*)((char*)d_workspace + (size_t)blocks * C * 2 * sizeof(double)) : nullptr;
+    float* bound = d_dx_planes ? maxbuf + (size_t)blocks * 128 * 2 : nullptr;
     ColArgs a;
     a.x = d_x; a.dy = d_dy; a.mean = d_mean; a.invstd = d_invstd; a.gamma = d_gamma; a.beta = d_beta;
-    a.M = M; a.C = C; a.relu = relu; a.mode = 1;
+    a.M = M; a.C = C; a.relu = relu; a.mode = 1; a.maxout = maxbuf;
     col_partial_kernel<<<blocks, 256, 0, s>>>(a, (double*)d_workspace);
     IC_CHECK_LAUNCH();
     col_finalize_kernel<<<C, 128, 0, s>>>((const double*)d_workspace, blocks, C, M, 1, 0.f, d_dbeta, d_dgamma, nullptr,
-                                                     nullptr, 0.f, nullptr);
+                                                     nullptr, 0.f, nullptr, maxbuf, d_gamma, d_invstd, bound);
     IC_CHECK_LAUNCH();
+    if (d_dx_planes) {
+        IC_REQUIRE((((uintptr_t)d_x | (uintptr_t)d_dy | (uintptr_t)d_dx_planes) & 15) == 0, IC_ERR_INVALID, "ic_nn_bn_train_bwd_ex: unaligned tensor");
+        bn_bwd_apply8_planes_kernel<<<ew_grid(M * 16), 256, 0, s>>>((const float4*)d_x, (const float4*)d_dy, d_mean, d_invstd, d_gamma, d_beta,
+                                                                    d_dbeta, d_dgamma, bound, relu, M * 16, hw, 1.f / (float)M,
+                                                                    (__half*)d_dx_planes, M * 128, d_scale_out);
+        IC_CHECK_LAUNCH();
+        return IC_OK;
+    }
     const bool vec4 = C % 4 == 0 && (((uintptr_t)d_x | (uintptr_t)d_dy | (uintptr_t)d_dx) & 15) == 0;
     if (vec4)
         bn_bwd_apply4_kernel<<<ew_grid(M * C / 4), 256, 0, s>>>((const float4*)d_x, (const float4*)d_dy, d_mean, d_invstd, d_gamma, d_beta,

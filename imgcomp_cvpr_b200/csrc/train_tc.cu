@@ -430,6 +430,22 @@ __global__ void __launch_bounds__(256) weight_scales_kernel(const float* __restr
     }
 }
 
+// params / epilogue scale of a backward pass whose three scales are all known: kept = {s_w, s_x, 1/s_w, 1/s_x} (forward
+// pass), dys = {s_dy, 1/s_dy} (ic_nn_bn_train_bwd_ex).  Same slots as finalize_scales_kernel: [0] w, [1] dy, [2] x, [4 + k] inverses.
+__global__ void __launch_bounds__(128) set_params_kernel(const float* __restrict__ kept, const float* __restrict__ dys,
+                                                         float* __restrict__ params, float* __restrict__ scale, float* __restrict__ shift) {
+    if (threadIdx.x == 0) {
+        params[0] = kept[0];
+        params[4] = kept[2];
+        params[2] = kept[1];
+        params[6] = kept[3];
+        params[1] = dys[0];
+        params[5] = dys[1];
+    }
+    scale[threadIdx.x] = 1.f / kept[0];
+    shift[threadIdx.x] = 0.f;
+}
+
 constexpr int MS_ROWS = 64;       // = CR_ROWS of train_ops.cu
 
 __global__ void __launch_bounds__(128) merge_stats_kernel(const __half* __restrict__ in, int64_t hw, int64_t M, int64_t plane,
@@ -1036,6 +1052,7 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
         a.img_off_mul = N;
         a.img_base = p.data_grad ? -N : 0;
         a.pc_f32 = 1;
+        a.pair_c2 = p.cin_pad <= 24 ? 1 : 0;      // chunks past the tensor's channel count are TMA zero fill
         a.out_f32 = d_y;
     } else {
         a.Nimg = N;
@@ -1340,6 +1357,57 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
     merge_stats_kernel<<<(unsigned)((M + MS_ROWS - 1) / MS_ROWS), 128, 0, s>>>(bo, (int64_t)H * W, M, (int64_t)elems, d_y, d_bn_partial);
     IC_CHECK_LAUNCH();
     return IC_OK;
+}
+
+
+/* ic_nn_conv3x3_tc_bwd_ex for an output gradient that already exists as pre-scaled fp16 planes (ic_nn_bn_train_bwd_ex):
+ * d_dy_planes with d_dy_scale = {s, 1/s}; d_x_planes / d_scales as in ic_nn_conv3x3_tc_bwd_ex (required).  No maximum
+ * search, no split pass. */
+int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, int N, int H, int W, float* d_dx,
+                                float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
+                                size_t workspace_bytes, void* stream) {
+    IC_REQUIRE(d_dy_planes && d_dy_scale && d_w && d_dw && d_x_planes && d_scales && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd_planes: NULL argument");
+    IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd_planes: bad shape");
+    IC_REQUIRE(workspace_bytes >= ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_bwd_planes: workspace too small");
+    int rc = ensure_group_table();
+    if (rc != IC_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int S = wgrad_splits(N, H, W);
+    Arena ar(d_workspace, workspace_bytes);
+    const size_t elems = (size_t)N * H * W * kC * 2;
+    __half* bo = ar.get<__half>(elems);
+    __half* wp = ar.get<__half>((size_t)kStages * 2 * kPlaneElems);
+    float* partial = ar.get<float>((size_t)S * kW);
+    float* scale = ar.get<float>(kC);
+    float* shift = ar.get<float>(kC);
+    float* params = ar.get<float>(8);
+    IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_bwd_planes: workspace too small");
+    {
+        ProfScope ps(IC_PROF_ELEMENTWISE, s);
+        set_params_kernel<<<1, 128, 0, s>>>(d_scales, d_dy_scale, params, scale, shift);
+        IC_CHECK_LAUNCH();
+    }
+    const __half* bx = reinterpret_cast<const __half*>(d_x_planes);
+    const __half* bdy = reinterpret_cast<const __half*>(d_dy_planes);
+    CUtensorMap xmap, ymap;
+    rc = tc::encode_planes_map(&xmap, bx, 2, N, kC / 8, H, W, WG_COLS + 2, WG_ROWS, kC / 8);
+    if (rc == IC_OK) rc = tc::encode_planes_map(&ymap, bdy, 2, N, kC / 8, H, W, WG_COLS, WG_ROWS, kC / 8);
+    if (rc != IC_OK) return rc;
+    const size_t smem = (size_t)WG_STAGES * WG_STAGE_BYTES + sizeof(WgBars) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    {
+        ProfScope ps(IC_PROF_CONV3X3, s, 2);
+        wgrad_tc_kernel<<<3 * S, WG_THREADS, smem, s>>>(xmap, ymap, N, H, W, S, partial);
+        IC_CHECK_LAUNCH();
+        wgrad_reduce_kernel<<<cdiv(kW, 256), 256, 0, s>>>(partial, S, params + 1, d_dw);     // / (s_dy * s_x)
+        IC_CHECK_LAUNCH();
+    }
+    if (!d_dx) return IC_OK;
+    return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s);
 }
 
 }  // extern "C"

@@ -264,6 +264,45 @@ def bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu=False, use_stats=True, d
     return dx, dgamma, dbeta
 
 
+class PlanesGrad(object):
+    """An output gradient that exists only as pre-scaled fp16 hi/lo planes (bn_train_bwd(..., as_planes=True)): what the
+    tensor-core backward of the conv before the batch norm consumes (conv3x3_tc_bwd_planes)."""
+
+    def __init__(self, planes, scale, shape):
+        self.planes, self.scale, self.shape = planes, scale, tuple(shape)
+
+
+def bn_train_bwd_planes(x, dy, gamma, beta, mean, invstd, relu=False, dgamma=None, dbeta=None):
+    """bn_train_bwd (batch statistics, x N,H,W,128) whose dx is written as fp16 planes scaled by a power of two ->
+    (PlanesGrad, dgamma, dbeta); no float32 dx exists."""
+    N, H, W, C = x.shape
+    assert C == 128
+    M = N * H * W
+    planes = torch.empty(2 * x.numel(), dtype=torch.float16, device=x.device)
+    scale = torch.empty(2, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if dgamma is None else dgamma
+    dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if dbeta is None else dbeta
+    ws = _workspace(_lib.lib().ic_nn_bn_workspace_bytes(M, C))
+    _lib.check(_lib.lib().ic_nn_bn_train_bwd_ex(_lib.ptr(_f32(x)), _lib.ptr(_f32(dy)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)),
+                                               int(relu), 1, _lib.ptr(mean), _lib.ptr(invstd), None, _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                               _lib.ptr(planes), _lib.ptr(scale), H * W, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return PlanesGrad(planes, scale, x.shape), dgamma, dbeta
+
+
+def conv3x3_tc_bwd_planes(dy, w, need_dx=True, dw_out=None, cache=None):
+    """conv3x3_tc_bwd for dy given as a PlanesGrad; cache = (x planes, scales) of the forward pass (required)"""
+    N, H, W, C = dy.shape
+    planes, scales = cache
+    assert C == 128 and planes.numel() == dy.planes.numel()
+    dx = torch.empty(dy.shape, dtype=torch.float32, device=w.device) if need_dx else None
+    dw = torch.empty_like(w) if dw_out is None else dw_out
+    ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W))
+    _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd_planes(_lib.ptr(dy.planes), _lib.ptr(dy.scale), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
+                                                     _lib.ptr(_f32(dw)), _lib.ptr(planes), _lib.ptr(scales), _lib.ptr(ws), ws.numel(),
+                                                     _lib.stream_ptr()))
+    return dx, dw
+
+
 def normalize_fwd(x):
     """x N,3,H,W uint8 or float32 in [0,255] -> normalised N,H,W,4 (code/autoencoder.py:136-144)"""
     assert x.is_cuda and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3 and x.dtype in (torch.uint8, torch.float32)

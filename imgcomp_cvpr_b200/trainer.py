@@ -357,7 +357,10 @@ class Trainer(object):
                 if dy is None:
                     return
                 if tc:        # both gradients on tensor cores (filter gradient: GEMM over pixels, csrc/train_tc.cu)
-                    dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
+                    if isinstance(dy, nn.PlanesGrad):       # the batch norm's backward wrote the conv's operand directly
+                        dx, _ = nn.conv3x3_tc_bwd_planes(dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
+                    else:
+                        dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
                     if need_dx:
                         tape.acc(x, dx, owned=True)
                     return
@@ -381,6 +384,9 @@ class Trainer(object):
         if self._fused() and x.dim() == 4 and x.shape[-1] == 128:
             planes = torch.empty(2 * x.numel(), dtype=torch.float16, device=x.device)      # for the 3x3 conv that reads `out`
         partial = self._bn_partial if self._stats_of is x else None
+        # x is the output of a fused trunk conv: this batch norm is its only consumer, so in the backward pass dx can go to
+        # that conv as pre-scaled fp16 planes (no float32 dx, no maximum search, no split pass)
+        grad_as_planes = partial is not None and self.is_training and os.environ.get('IC_TRAIN_FUSED_BWD', '1') != '0'
         self._stats_of = None
         if self.is_training:
             upd = self.update_moving
@@ -398,8 +404,13 @@ class Trainer(object):
                 dy = tape.pop(out)
                 if dy is None:
                     return
-                dx, _, _ = nn.bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu, use_stats=training,
-                                           dgamma=self._g(scope + '/BatchNorm/gamma'), dbeta=self._g(scope + '/BatchNorm/beta'))
+                if grad_as_planes:
+                    dx, _, _ = nn.bn_train_bwd_planes(x, dy, gamma, beta, mean, invstd, relu, dgamma=self._g(scope + '/BatchNorm/gamma'),
+                                                      dbeta=self._g(scope + '/BatchNorm/beta'))
+                    assert id(x) not in tape.grads
+                else:
+                    dx, _, _ = nn.bn_train_bwd(x, dy, gamma, beta, mean, invstd, relu, use_stats=training,
+                                               dgamma=self._g(scope + '/BatchNorm/gamma'), dbeta=self._g(scope + '/BatchNorm/beta'))
                 tape.acc(x, dx, owned=True)
                 if res1 is not None:
                     tape.acc(res1, dy)

@@ -288,6 +288,16 @@ int ic_nn_bn_train_bwd(const float* d_x, const float* d_dy, int64_t M, int C, co
                        const float* d_beta, int relu, int use_stats, const float* d_mean, const float* d_invstd,
                        float* d_dx, float* d_dgamma, float* d_dbeta,
                        void* d_workspace, size_t workspace_bytes, void* stream);
+/* Backward of a trunk layer fused the same way: the batch norm's dx goes out as pre-scaled fp16 planes (d_dx_planes, C = 128,
+ * batch statistics; d_scale_out = {s, 1/s}, s = the power of two that brings an upper bound of max |dx| -- from per-channel
+ * maxima gathered in the statistics pass -- into [2^5, 2^6); d_dx NULL), and ic_nn_conv3x3_tc_bwd_planes consumes them. */
+int ic_nn_bn_train_bwd_ex(const float* d_x, const float* d_dy, int64_t M, int C, const float* d_gamma, const float* d_beta, int relu,
+                          int use_stats, const float* d_mean, const float* d_invstd, float* d_dx, float* d_dgamma, float* d_dbeta,
+                          void* d_dx_planes, float* d_scale_out, int64_t hw, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, int N, int H, int W, float* d_dx,
+                                float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
+                                size_t workspace_bytes, void* stream);
 /* backward of _get_heatmap3D + _mask_with_heatmap + the soft quantizer with
  * qbar = qsoft + stop_gradient(qhard - qsoft) (code/autoencoder.py:127-134,171-200; quantizer.py:60-100):
  * d_bn N,h,w,Cb (channel 0 = heatmap logit, 1..C = features), d_dq N,h,w,C = gradient w.r.t. qbar,
