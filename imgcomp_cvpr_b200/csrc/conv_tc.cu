@@ -37,6 +37,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
@@ -50,11 +52,17 @@ constexpr int TH = 16, TW = 8;             // one UMMA tile: 16 rows x 8 pixels 
 constexpr int MAX_WSTAGES = 16;
 static_assert(MAX_WSTAGES >= 8, "Cfg::WSTAGES must fit the barrier arrays");
 constexpr int MAX_RES_STAGES = 14;          // resident-weight mode: the context model has 14 non-masked taps
+// activation-tile slots: 2 for the streamed-weight kernels (a group's MMAs take longer than a load), 6 for the context
+// model: its tiles have two short groups (9 + 5 narrow MMAs, ~1k tensor cycles per tile) and a load from L2 / HBM takes
+// 2-3k cycles, so three tiles must be in flight.  ncu (profiles/r2x_pc_raw.csv) with 2 slots and two CTAs per SM: tensor pipe
+// 32 %, operand pipe 57 %, DRAM 26 %, i.e. nothing busy -- the issuer waited for a_full.
+constexpr int MAX_ASLOTS = 6;
 // epilogue warps: 4 (one per TMEM lane quarter), or 8 for the 128-column plane-output kernels (two per quarter, half of the
 // output channels each): with the issue loop and the pair's operand traffic out of the way the EPILOGUE paced the 3x3
 // convs (IC_TC_DBG: the issuer waited 20 % of its time on acc_empty) -- its residual loads are latency bound, and twice
 // the warps keep twice the loads in flight
-constexpr int epi_warps(int nout, int outmode) { return (nout == 128 && outmode == 0) ? 8 : 4; }
+// (also the context model's plane-output layers: layer 2 reads a residual, IC_TC_DBG=2 showed its issuer waiting 24 % on acc_empty)
+constexpr int epi_warps(int nout, int outmode) { return ((nout == 128 || nout == 32) && outmode == 0) ? 8 : 4; }
 constexpr int nthreads(int nout, int outmode) { return (3 + epi_warps(nout, outmode)) * 32; }
 
 template <int T, int NOUT, int CPG>
@@ -74,7 +82,7 @@ __constant__ float c_img_mean[3] = {121.853699f, 113.588608f, 100.637154f};
 __constant__ float c_img_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};   // float32 sqrt(var + 1e-10)
 
 struct __align__(8) Barriers {
-    uint64_t a_full[2], a_empty[2], w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES], acc_full[2], acc_empty[2];
+    uint64_t a_full[MAX_ASLOTS], a_empty[MAX_ASLOTS], w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
@@ -177,7 +185,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     uint8_t* a_buf = smem;                                              // [2 slots][NPL][A_PLANE_BYTES]
     // pair mode: a stage is half the size per CTA and its hand-over crosses the cluster, so twice the stages are in flight
     constexpr int WSTAGES = WRES ? MAX_RES_STAGES : (PAIR ? 2 * C::WSTAGES : C::WSTAGES);
-    uint8_t* w_buf = a_buf + 2 * NPL * C::A_PLANE_BYTES;                // [WSTAGES][NPL][W_PLANE]
+    const uint32_t ASLOTS = (uint32_t)p.aslots;
+    uint8_t* w_buf = a_buf + ASLOTS * NPL * C::A_PLANE_BYTES;           // [WSTAGES][NPL][W_PLANE]
     float* s_scale = reinterpret_cast<float*>(w_buf + WSTAGES * NPL * W_PLANE);
     float* s_shift = s_scale + 128;
     Barriers* bars = reinterpret_cast<Barriers*>(s_shift + 128);
@@ -185,17 +194,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (p.W + TW * T - 1) / (TW * T), tiles_y = (p.H + TH - 1) / TH;
     const int n_super = p.N * tiles_y * tiles_x;
-    const int n_work = PAIR ? (n_super + 1) / 2 : n_super;        // pair mode: one work item = two super tiles
+    int n_work = PAIR ? (n_super + 1) / 2 : n_super;              // pair mode: one work item = two super tiles
     constexpr uint32_t kTmemCols = (2 * T * C::NCOL <= 32) ? 32 : (2 * T * C::NCOL <= 64) ? 64 :
                                    (2 * T * C::NCOL <= 128) ? 128 : (2 * T * C::NCOL <= 256) ? 256 : 512;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < (int)ASLOTS; ++i) {
             // pair: ONE arrival (the leader's producer, which announces the bytes of BOTH CTAs); the peer's TMA only adds
             // its complete_tx.  A remote arrive.expect_tx per stage from the peer's producer thread (release.cluster) made
             // that thread the bottleneck: IC_TC_DBG showed the issuer waiting on w_full 74 % of the time.
             mbar_init(smem_u32(&bars->a_full[i]), 1);
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
             mbar_init(smem_u32(&bars->acc_empty[i]), (PAIR ? 2 : 1) * 32 * epi_warps(NOUT, OUTMODE));
         }
@@ -235,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                 const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
                 const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW * T;
                 for (int g = 0; g < gt.ngroups; ++g, ++gi) {
-                    const uint32_t slot = gi & 1, ph = (gi >> 1) & 1;
+                    const uint32_t slot = gi % ASLOTS, ph = (gi / ASLOTS) & 1;
                     mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
                     const int img = n * p.img_mul + (p.img_div > 0 ? (n / p.img_div) * p.img_div_mul : 0) + gt.img_off[g] * p.img_off_mul + p.img_base;
                     if (PAIR) {
@@ -309,6 +320,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
             }
             long long dbg_t[3] = {0, 0, 0}, dbg_c = 0;
             const long long dbg_start = p.dbg ? clock64() : 0;
+            if constexpr (CAT && T == 1) {
+                // Context-model layers ("other" mask): the schedule of a tile is the same for every tile -- group 0 = the 9
+                // taps of filter depth 0, group 1 = 5 consecutive taps (0..4 forward, 4..8 data gradient) -- so it is spelled
+                // out at compile time.  The table-driven loop below cost ~500 cycles PER TAP in this instantiation (tap table in
+                // vector registers: LDC / IMAD / a dozen R2UR per tap; IC_TC_DBG=2: the issuer never waited, it was busy
+                // 7.6 k cycles per tile for ~1 k tensor cycles of narrow MMAs): profiles/r2z_issuer_pc.txt.
+                if (p.pc_static) {
+                    auto issue_group = [&](auto nt_c, auto tap0_c, uint64_t a_g, uint64_t w_g, uint32_t d_tmem, bool first_group) {
+                        constexpr int NT = decltype(nt_c)::value, TAP0 = decltype(tap0_c)::value;
+                        constexpr uint64_t kStage = (uint64_t)(NPL * kWPlane);
+                        constexpr uint64_t kALboF = (uint64_t)(kALbo >> 4), kWLboF = (uint64_t)((2 * W_ROWS * 16) >> 4);
+#pragma unroll
+                        for (int ti = 0; ti < NT; ++ti) {
+                            const int tap = TAP0 + ti;
+                            const uint64_t a_t = a_g + (uint64_t)((tap / 3) * C::HALO_W + (tap % 3));
+                            const uint64_t w_t = w_g + (uint64_t)ti * kStage;
+                            if (p.pair_c2 && (ti & 1)) {          // chunk 2 of taps ti-1 and ti as one k-step (see below)
+                                const int tp = tap - 1;
+                                const uint64_t a_prev = a_g + (uint64_t)((tp / 3) * C::HALO_W + (tp % 3));
+                                const uint64_t a_pr = a_prev + kAKs - (kALboF << 16) + ((a_t - a_prev) << 16);
+                                const uint64_t w_pr = (w_t - kStage) + kWKs - (kWLboF << 16) + (kStage << 16);
+                                umma_f16(d_tmem, a_pr, w_pr, IDESC_CAT, 1u);
+                                umma_f16(d_tmem + NOUT, a_pr + kAPlane, w_pr, IDESC, 1u);
+                            }
+                            umma_f16(d_tmem, a_t, w_t, IDESC_CAT, (first_group && ti == 0) ? 0u : 1u);
+                            umma_f16(d_tmem + NOUT, a_t + kAPlane, w_t, IDESC, 1u);
+                            if (!p.pair_c2 || ((ti & 1) == 0 && ti == NT - 1)) {
+                                umma_f16(d_tmem, a_t + kAKs, w_t + kWKs, IDESC_CAT, 1u);
+                                umma_f16(d_tmem + NOUT, a_t + kAKs + kAPlane, w_t + kWKs, IDESC, 1u);
+                            }
+                        }
+                    };
+                    for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
+                        const uint32_t set = it & 1;
+                        if (p.dbg) dbg_c = clock64();
+                        mbar_wait(smem_u32(&bars->acc_empty[set]), ((it >> 1) & 1) ^ 1);
+                        if (p.dbg) dbg_t[0] += clock64() - dbg_c;
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + set * C::NCOL;
+                        for (int g = 0; g < 2; ++g, ++gi) {
+                            const uint32_t aslot = gi % ASLOTS;
+                            if (p.dbg) dbg_c = clock64();
+                            mbar_wait(smem_u32(&bars->a_full[aslot]), (gi / ASLOTS) & 1);
+                            if (p.dbg) dbg_t[1] += clock64() - dbg_c;
+                            tc_fence_after();
+                            const uint64_t a_g = a_desc0 + (uint64_t)aslot * (NPL * kAPlane);
+                            if (elect_one()) {
+                                if (g == 0) {
+                                    issue_group(std::integral_constant<int, 9>{}, std::integral_constant<int, 0>{}, a_g, w_desc0, d_tmem, true);
+                                } else {
+                                    const uint64_t w_g = w_desc0 + 9ull * (uint64_t)(NPL * kWPlane);
+                                    if (p.pc_static == 1) issue_group(std::integral_constant<int, 5>{}, std::integral_constant<int, 0>{}, a_g, w_g, d_tmem, false);
+                                    else issue_group(std::integral_constant<int, 5>{}, std::integral_constant<int, 4>{}, a_g, w_g, d_tmem, false);
+                                }
+                                umma_commit(smem_u32(&bars->a_empty[aslot]));
+                                if (g == 1) umma_commit(smem_u32(&bars->acc_full[set]));
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    n_work = 0;       // the generic loop below has nothing left to do
+                }
+            }
             for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
                 const uint32_t set = it & 1;
                 if (p.dbg) dbg_c = clock64();
@@ -317,9 +391,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                 tc_fence_after();
                 uint32_t sidx = 0;      // stage index within the layer (resident mode)
                 for (int g = 0; g < gt.ngroups; ++g, ++gi) {
-                    const uint32_t aslot = gi & 1;
+                    const uint32_t aslot = gi % ASLOTS;
                     if (p.dbg) dbg_c = clock64();
-                    mbar_wait(smem_u32(&bars->a_full[aslot]), (gi >> 1) & 1);
+                    mbar_wait(smem_u32(&bars->a_full[aslot]), (gi / ASLOTS) & 1);
                     if (p.dbg) dbg_t[1] += clock64() - dbg_c;
                     tc_fence_after();
                     const uint64_t a_g = a_desc0 + (uint64_t)aslot * (NPL * kAPlane);
@@ -1119,6 +1193,16 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     {
         const char* pe = getenv("IC_PC_PAIR_CHUNKS");
         p.pair_c2 = (WRES && a.pair_c2 && !(pe && atoi(pe) == 0)) ? 1 : 0;
+        // compile-time schedule when the group table is the context model's: 9 taps 0..8, then 5 consecutive taps from 0 or 4
+        p.pc_static = 0;
+        const GroupTable& g = *a.groups;
+        const char* se = getenv("IC_PC_STATIC");
+        if (WRES && T == 1 && !(se && atoi(se) == 0) && g.ngroups == 2 && g.ntaps[0] == 9 && g.ntaps[1] == 5 && (g.taps[1][0] == 0 || g.taps[1][0] == 4)) {
+            bool ok = true;
+            for (int i = 0; i < 9; ++i) ok = ok && g.taps[0][i] == i;
+            for (int i = 0; i < 5; ++i) ok = ok && g.taps[1][i] == g.taps[1][0] + i;
+            if (ok) p.pc_static = g.taps[1][0] == 0 ? 1 : 2;
+        }
     }
     p.res_H = a.res_H ? a.res_H : a.H;
     p.res_W = a.res_W ? a.res_W : a.W;
@@ -1150,13 +1234,20 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.dbg = nullptr;
     static unsigned long long* dbg_buf = nullptr;
     const char* dbg_env = getenv("IC_TC_DBG");
-    const bool dbg_on = dbg_env && atoi(dbg_env) && NOUT == 128 && OUTMODE == 0;
+    const bool dbg_on = dbg_env && atoi(dbg_env) && ((NOUT == 128 && OUTMODE == 0) || (WRES && atoi(dbg_env) == 2));
     if (dbg_on) {
         if (!dbg_buf) IC_CHECK_CUDA(cudaMalloc((void**)&dbg_buf, 4096 * 4 * sizeof(unsigned long long)));
         IC_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 4096 * 4 * sizeof(unsigned long long), s));
         p.dbg = dbg_buf;
     }
-    const size_t smem = 2 * NPL * C::A_PLANE_BYTES +
+    // activation-tile slots (2 ... MAX_ASLOTS; IC_PC_ASLOTS overrides the context-model kernels' count)
+    p.aslots = 2;
+    if (WRES) {
+        const char* se = getenv("IC_PC_ASLOTS");
+        const int v = se ? atoi(se) : 2;
+        p.aslots = v < 2 ? 2 : (v > MAX_ASLOTS ? MAX_ASLOTS : v);
+    }
+    const size_t smem = p.aslots * NPL * C::A_PLANE_BYTES +
                         (WRES ? MAX_RES_STAGES : (PAIR ? 2 * C::WSTAGES : C::WSTAGES)) * NPL * (C::W_PLANE_BYTES / (PAIR ? 2 : 1)) + 1024 +
                         sizeof(Barriers) + 64;
     CUtensorMap wmap = map;        // placeholder unless PAIR
@@ -1172,11 +1263,11 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         IC_REQUIRE(wr == CUDA_SUCCESS, IC_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: %d", (int)wr);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
         IC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, NPL, NOUT, OUTMODE, CPG, WRES, PAIR>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_smem = smem;
     }
     const int tiles_x = (a.W + TW * T - 1) / (TW * T), tiles_y = (a.H + TH - 1) / TH;
     const int n_super = a.N * tiles_y * tiles_x;

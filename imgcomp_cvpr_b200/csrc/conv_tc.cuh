@@ -41,6 +41,8 @@ struct ConvTcParams {
     // resident-weight (context model) kernels with <= 24 real input channels: the third 8-channel chunk of two consecutive
     // taps forms ONE k-step (see the issue loop) instead of two half-empty ones
     int pair_c2;
+    int aslots;                 // activation-tile slots in shared memory (2 ... 6)
+    int pc_static;              // context model: compile-time tap schedule (1: group 1 = taps 0..4, 2: taps 4..8), 0: table-driven
     // geometry of res1 (context model: a crop of a larger tensor); res2 always has the output geometry
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;

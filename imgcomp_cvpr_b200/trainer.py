@@ -343,6 +343,8 @@ class Trainer(object):
             y = nn.conv3x3_tc_fused(held[1], w, wscale, tuple(x.shape), self._bn_partial)
             cache = (held[1], wscale)
             self._stats_of = y
+            if self.tape is None:           # forward only: nothing reads these planes again
+                del self._planes_of[x.data_ptr()]
         elif tc and self.tape is not None:        # keep the input's fp16 planes and the scales for the filter gradient
             y, cache = nn.conv3x3_tc(x, w, keep=True)
         elif plan_f is not None:
@@ -696,6 +698,7 @@ class Trainer(object):
             self._stage_step_sizes()
             self._graph.replay()
             self.global_step += 1
+            self._val = self._graph_val          # the distortion scalar the graph writes (an eager call in between re-binds _val)
             return self._read_losses(x.shape, self._graph_tensors['bc'].numel(), self._graph_tensors)
         tensors = self._enqueue(x, True, True, True)
         self.apply_gradients()
@@ -722,6 +725,9 @@ class Trainer(object):
         # the captured launches hold raw pointers into the shared scratch buffer of nn.py: keep THAT tensor alive for as
         # long as the graph is, whatever a later, larger call elsewhere replaces the shared one with
         self._graph_ws = nn.current_workspace()
+        # same for the batch-norm partial-sum buffer of the fused trunk (a later, larger eager call replaces self._bn_partial)
+        self._graph_partial = self._bn_partial
+        self._graph_val = self._val
         return self
 
 

@@ -275,6 +275,11 @@ def test_cuda_graph_survives_growth_of_the_shared_workspace(synth):
     _, _, _, _, tr_big = _setup(synth, 'cvpr/low', 4, 160, 160, seed=3, mode='exact')
     tr_big.forward_backward(big)                                  # needs a larger scratch buffer -> replaced
     assert nn.current_workspace() is not ws_before and tr_g._graph_ws is ws_before
+    # the graph owner's OWN larger eager call: replaces its batch-norm partial-sum buffer (fused trunk), which the captured
+    # launches also point into; the graph keeps the captured one
+    partial_before = tr_g._bn_partial
+    tr_g.forward_backward(big)
+    assert tr_g._bn_partial is not partial_before and tr_g._graph_partial is partial_before
     filler = [torch.full((1 << 20,), 7.0, device='cuda') for _ in range(64)]        # whatever the allocator hands out next
     for xi in xs:
         a, b = tr_e.step(xi), tr_g.step(xi)
