@@ -103,7 +103,7 @@ SIGNATURES = {
     'ic_nn_bn_train_bwd_ex': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     'ic_nn_conv3x3_tc_bwd_planes': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                            c_void_p, c_size_t, c_void_p]),
+                                            c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_hq_workspace_bytes': (c_size_t, [c_int64]),
     'ic_nn_hq_bwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

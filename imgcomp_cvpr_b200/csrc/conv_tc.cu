@@ -62,7 +62,8 @@ constexpr int MAX_ASLOTS = 6;
 // convs (IC_TC_DBG: the issuer waited 20 % of its time on acc_empty) -- its residual loads are latency bound, and twice
 // the warps keep twice the loads in flight
 // (also the context model's plane-output layers: layer 2 reads a residual, IC_TC_DBG=2 showed its issuer waiting 24 % on acc_empty)
-constexpr int epi_warps(int nout, int outmode) { return ((nout == 128 || nout == 32) && outmode == 0) ? 8 : 4; }
+// and the decoder's depth-to-space convs (256 columns: their issuer waited 75-83 % on acc_empty, profiles/r2z5_issuer_all.txt)
+constexpr int epi_warps(int nout, int outmode) { return ((nout == 128 || nout == 32 || nout == 256) && outmode == 0) ? 8 : 4; }
 constexpr int nthreads(int nout, int outmode) { return (3 + epi_warps(nout, outmode)) * 32; }
 
 template <int T, int NOUT, int CPG>
@@ -1082,7 +1083,8 @@ __global__ void split_from_nchw_kernel(const float* __restrict__ in, int CH, int
 
 // planes [pl][N][CH][H][W][8] -> fp32 NHWC.  One thread per (pixel, chunk), chunk fastest (coalesced writes).
 __global__ void merge_to_nhwc_kernel(const __half* __restrict__ in, int H, int W, int CH, int64_t total, int64_t plane,
-                                     float* __restrict__ out, int has_lo, const float* __restrict__ mul) {
+                                     float* __restrict__ out, int has_lo, const float* __restrict__ mul,
+                                     const float* __restrict__ add = nullptr) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int chunk = (int)(i % CH);
@@ -1096,6 +1098,11 @@ __global__ void merge_to_nhwc_kernel(const __half* __restrict__ in, int H, int W
         const float g = mul[0];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] *= g;
+    }
+    if (add) {          // gradient accumulation fused into the merge: out = merged + add (same sum as a separate axpby pass)
+        const float4 a0 = reinterpret_cast<const float4*>(add + (pix * CH + chunk) * 8)[0];
+        const float4 a1 = reinterpret_cast<const float4*>(add + (pix * CH + chunk) * 8)[1];
+        v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
     }
     float4* dst = reinterpret_cast<float4*>(out + (pix * CH + chunk) * 8);
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -1234,7 +1241,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     p.dbg = nullptr;
     static unsigned long long* dbg_buf = nullptr;
     const char* dbg_env = getenv("IC_TC_DBG");
-    const bool dbg_on = dbg_env && atoi(dbg_env) && ((NOUT == 128 && OUTMODE == 0) || (WRES && atoi(dbg_env) == 2));
+    const bool dbg_on = dbg_env && atoi(dbg_env) && ((NOUT == 128 && OUTMODE == 0) || (WRES && atoi(dbg_env) == 2) || atoi(dbg_env) == 3);
     if (dbg_on) {
         if (!dbg_buf) IC_CHECK_CUDA(cudaMalloc((void**)&dbg_buf, 4096 * 4 * sizeof(unsigned long long)));
         IC_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 4096 * 4 * sizeof(unsigned long long), s));
@@ -1313,7 +1320,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
                 ++n;
             }
         if (n && printed++ < 40)
-            fprintf(stderr, "[IC_TC_DBG] pair=%d issuers=%d  wait acc_empty %.1f%%  a_full %.1f%%  w_full %.1f%%  of %.0f cycles\n", (int)PAIR, n,
+            fprintf(stderr, "[IC_TC_DBG] T=%d nout=%d outmode=%d pair=%d issuers=%d  wait acc_empty %.1f%%  a_full %.1f%%  w_full %.1f%%  of %.0f cycles\n", T, NOUT, OUTMODE, (int)PAIR, n,
                     100 * w[0] / w[3], 100 * w[1] / w[3], 100 * w[2] / w[3], w[3] / n);
     }
     return IC_OK;
@@ -1488,10 +1495,11 @@ int launch_split_from_nchw(const float* in, int N, int C, int H, int W, __half* 
     return IC_OK;
 }
 
-int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s, const float* d_mul) {
+int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s, const float* d_mul,
+                         const float* d_add) {
     int64_t total = (int64_t)N * H * W * (C / 8), plane = (int64_t)N * H * W * C;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
-    merge_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, total, plane, out, has_lo, d_mul);
+    merge_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, H, W, C / 8, total, plane, out, has_lo, d_mul, d_add);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }

@@ -98,7 +98,7 @@ int launch_split_from_nhwc(const float* in, int N, int H, int W, int C, int s2d,
 int encode_planes_map(CUtensorMap* map, const __half* base, int planes, int Nimg, int chunks, int H, int W, int box_w, int box_h,
                       int box_chunks);
 int launch_merge_to_nhwc(const __half* in, int N, int H, int W, int C, float* out, int has_lo, cudaStream_t s,
-                         const float* d_mul = nullptr);
+                         const float* d_mul = nullptr, const float* d_add = nullptr);
 int launch_s2d_planes(const __half* in, int N, int H, int W, int C, int planes, __half* out, cudaStream_t s);
 int pack_weights_tconv(const float* w, int k, int cin, int cout, const int* phases, int nphases, int nout,
                        std::vector<__half>& packed, GroupTable& gt, float* inv_scale_out);

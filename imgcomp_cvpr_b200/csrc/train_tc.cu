@@ -559,7 +559,8 @@ bool use_pair(int W) {
 // conv over planes `in` (already split and pre-scaled) with weights d_w scaled by params[0] -> float32 NHWC, multiplied
 // by unscale[0] (the inverse of the input's pre-scale) when the planes are merged back
 int conv_planes(const __half* in, const float* d_w, int data_grad, const float* params, const float* unscale, const float* scale,
-                const float* shift, __half* wp, __half* bo, int N, int H, int W, float* d_y, cudaStream_t s) {
+                const float* shift, __half* wp, __half* bo, int N, int H, int W, float* d_y, cudaStream_t s,
+                const float* d_add = nullptr) {
     const bool pair = use_pair(W);
     {
         ProfScope ps(IC_PROF_ELEMENTWISE, s);
@@ -593,7 +594,7 @@ int conv_planes(const __half* in, const float* d_w, int data_grad, const float* 
     a.prof_class = IC_PROF_CONV3X3;
     int rc = tc::launch_conv_tc(a, s);
     if (rc != IC_OK) return rc;
-    return tc::launch_merge_to_nhwc(bo, N, H, W, kC, d_y, 1, s, unscale);
+    return tc::launch_merge_to_nhwc(bo, N, H, W, kC, d_y, 1, s, unscale, d_add);
 }
 
 
@@ -1362,9 +1363,10 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
 
 /* ic_nn_conv3x3_tc_bwd_ex for an output gradient that already exists as pre-scaled fp16 planes (ic_nn_bn_train_bwd_ex):
  * d_dy_planes with d_dy_scale = {s, 1/s}; d_x_planes / d_scales as in ic_nn_conv3x3_tc_bwd_ex (required).  No maximum
- * search, no split pass. */
+ * search, no split pass.  d_dx_add (optional, same shape as d_dx): d_dx = data gradient + d_dx_add, the gradient the input
+ * already received through a residual connection (saves the separate accumulation pass). */
 int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, int N, int H, int W, float* d_dx,
-                                float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
+                                const float* d_dx_add, float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
                                 size_t workspace_bytes, void* stream) {
     IC_REQUIRE(d_dy_planes && d_dy_scale && d_w && d_dw && d_x_planes && d_scales && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd_planes: NULL argument");
     IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd_planes: bad shape");
@@ -1407,7 +1409,7 @@ int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale
         IC_CHECK_LAUNCH();
     }
     if (!d_dx) return IC_OK;
-    return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s);
+    return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s, d_dx_add);
 }
 
 }  // extern "C"

@@ -289,17 +289,19 @@ def bn_train_bwd_planes(x, dy, gamma, beta, mean, invstd, relu=False, dgamma=Non
     return PlanesGrad(planes, scale, x.shape), dgamma, dbeta
 
 
-def conv3x3_tc_bwd_planes(dy, w, need_dx=True, dw_out=None, cache=None):
-    """conv3x3_tc_bwd for dy given as a PlanesGrad; cache = (x planes, scales) of the forward pass (required)"""
+def conv3x3_tc_bwd_planes(dy, w, need_dx=True, dw_out=None, cache=None, dx_add=None):
+    """conv3x3_tc_bwd for dy given as a PlanesGrad; cache = (x planes, scales) of the forward pass (required);
+    dx_add: gradient the input already has (residual path) -> dx = data gradient + dx_add in the same pass"""
     N, H, W, C = dy.shape
     planes, scales = cache
     assert C == 128 and planes.numel() == dy.planes.numel()
     dx = torch.empty(dy.shape, dtype=torch.float32, device=w.device) if need_dx else None
     dw = torch.empty_like(w) if dw_out is None else dw_out
     ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W))
+    assert dx_add is None or (need_dx and tuple(dx_add.shape) == tuple(dy.shape))
     _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd_planes(_lib.ptr(dy.planes), _lib.ptr(dy.scale), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
-                                                     _lib.ptr(_f32(dw)), _lib.ptr(planes), _lib.ptr(scales), _lib.ptr(ws), ws.numel(),
-                                                     _lib.stream_ptr()))
+                                                     _lib.ptr(None if dx_add is None else _f32(dx_add)), _lib.ptr(_f32(dw)), _lib.ptr(planes),
+                                                     _lib.ptr(scales), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return dx, dw
 
 

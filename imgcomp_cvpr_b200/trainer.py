@@ -97,6 +97,14 @@ class _Tape(object):
         e = self.grads.pop(id(t), None)
         return None if e is None else e[1]
 
+    def take(self, t):
+        """the float32 gradient accumulated for t so far (removed from the tape), or None"""
+        e = self.grads.get(id(t))
+        if e is None or not torch.is_tensor(e[1]):
+            return None
+        del self.grads[id(t)]
+        return e[1]
+
     def backward(self):
         for fn in reversed(self.fns):
             fn()
@@ -360,7 +368,9 @@ class Trainer(object):
                     return
                 if tc:        # both gradients on tensor cores (filter gradient: GEMM over pixels, csrc/train_tc.cu)
                     if isinstance(dy, nn.PlanesGrad):       # the batch norm's backward wrote the conv's operand directly
-                        dx, _ = nn.conv3x3_tc_bwd_planes(dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
+                        # the gradient x already has (residual path) is added in the conv's own output pass
+                        had = tape.take(x) if need_dx else None
+                        dx, _ = nn.conv3x3_tc_bwd_planes(dy, w, need_dx=need_dx, dw_out=gw, cache=cache, dx_add=had)
                     else:
                         dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
                     if need_dx:

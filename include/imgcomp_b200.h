@@ -296,8 +296,9 @@ int ic_nn_bn_train_bwd_ex(const float* d_x, const float* d_dy, int64_t M, int C,
                           void* d_dx_planes, float* d_scale_out, int64_t hw, void* d_workspace, size_t workspace_bytes,
                           void* stream);
 int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, int N, int H, int W, float* d_dx,
-                                float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
-                                size_t workspace_bytes, void* stream);
+                                const float* d_dx_add /* optional: d_dx = gradient + d_dx_add */, float* d_dw,
+                                const void* d_x_planes, const float* d_scales, void* d_workspace, size_t workspace_bytes,
+                                void* stream);
 /* backward of _get_heatmap3D + _mask_with_heatmap + the soft quantizer with
  * qbar = qsoft + stop_gradient(qhard - qsoft) (code/autoencoder.py:127-134,171-200; quantizer.py:60-100):
  * d_bn N,h,w,Cb (channel 0 = heatmap logit, 1..C = features), d_dq N,h,w,C = gradient w.r.t. qbar,
