@@ -509,8 +509,10 @@ __global__ void __launch_bounds__(256) bn_apply8_planes_kernel(const float4* __r
             const float4 a = res2[2 * i], b = res2[2 * i + 1];
             v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
         }
-        out[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
-        out[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (out) {          // NULL: the only consumer is the next tensor-core conv, which reads the planes
+            out[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+            out[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
         float4 hi4, lo4;
         __half2* hi = reinterpret_cast<__half2*>(&hi4);
         __half2* lo = reinterpret_cast<__half2*>(&lo4);
@@ -1050,12 +1052,13 @@ int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma,
 
 /* ic_nn_bn_train_fwd with the two fusions of the tensor-core trunk: d_partial_in (optional) = the statistics partial sums
  * ic_nn_conv3x3_tc_fused accumulated while it wrote d_x (skips the statistics pass over d_x); d_planes_out (optional, C % 8 == 0,
- * 2 M C fp16 elements) receives the fp16 hi/lo planes [plane][M / hw][C / 8][hw][8] of d_out for the next conv. */
+ * 2 M C fp16 elements) receives the fp16 hi/lo planes [plane][M / hw][C / 8][hw][8] of d_out for the next conv; d_out may
+ * then be NULL (no float32 copy is written: for an output whose only consumer is that conv). */
 int ic_nn_bn_train_fwd_ex(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps, int relu,
                           int use_stats, const float* d_res1, const float* d_res2, float* d_mean, float* d_invstd,
                           float* d_mov_mean, float* d_mov_var, float* d_out, const double* d_partial_in, void* d_planes_out,
                           int64_t hw, void* d_workspace, size_t workspace_bytes, void* stream) {
-    IC_REQUIRE(d_x && d_gamma && d_beta && d_mean && d_invstd && d_out, IC_ERR_INVALID, "ic_nn_bn_train_fwd: NULL argument");
+    IC_REQUIRE(d_x && d_gamma && d_beta && d_mean && d_invstd && (d_out || d_planes_out), IC_ERR_INVALID, "ic_nn_bn_train_fwd: NULL argument");
     IC_REQUIRE(M > 0 && C > 0 && C <= 128, IC_ERR_INVALID, "ic_nn_bn_train_fwd: bad shape (C <= 128)");
     IC_REQUIRE(!d_partial_in || C == 128, IC_ERR_INVALID, "ic_nn_bn_train_fwd_ex: partial sums are those of a 128-channel conv");
     IC_REQUIRE(!d_planes_out || (C % 8 == 0 && hw > 0 && M % hw == 0), IC_ERR_INVALID, "ic_nn_bn_train_fwd_ex: planes need C % 8 == 0 and M = n hw");

@@ -198,10 +198,12 @@ class TcWgradPlan(object):
 
 
 def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None, mov_var=None, stats=None, partial=None,
-                 planes_out=None):
+                 planes_out=None, write_out=True):
     """x (..., C) -> (out, mean, invstd).  stats = (mean, invstd): plain affine layer with the given statistics.
     partial: statistics partial sums of x from conv3x3_tc_fused (no statistics pass over x); planes_out (x N,H,W,C with
-    C % 8 == 0): float16 tensor of 2 * x.numel() elements that receives the hi/lo planes of out for the next 3x3 conv."""
+    C % 8 == 0): float16 tensor of 2 * x.numel() elements that receives the hi/lo planes of out for the next 3x3 conv;
+    write_out=False (with planes_out): `out` is returned as an UNWRITTEN placeholder (only the planes are produced)."""
+    assert write_out or planes_out is not None
     C = x.shape[-1]
     M = x.numel() // C
     out = torch.empty_like(x)
@@ -217,7 +219,7 @@ def bn_train_fwd(x, gamma, beta, relu=False, res1=None, res2=None, mov_mean=None
         hw = x.shape[1] * x.shape[2]
     _lib.check(_lib.lib().ic_nn_bn_train_fwd_ex(_lib.ptr(_f32(x)), M, C, _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)), BN_EPS,
                                                int(relu), int(stats is None), _lib.ptr(res1), _lib.ptr(res2), _lib.ptr(mean),
-                                               _lib.ptr(invstd), _lib.ptr(mov_mean), _lib.ptr(mov_var), _lib.ptr(out),
+                                               _lib.ptr(invstd), _lib.ptr(mov_mean), _lib.ptr(mov_var), _lib.ptr(out if write_out else None),
                                                _lib.ptr(partial if stats is None else None), _lib.ptr(planes_out), hw,
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return out, mean, invstd

@@ -342,6 +342,7 @@ class Trainer(object):
             plan_f, plan_d, plan_w = self._tc_plans('tconv5s2' if transposed else 'conv5s2', *chans)
         cache = None
         held = self._planes_of.get(x.data_ptr()) if (tc and scope in self._trunk_row and self._fused()) else None
+        assert not getattr(x, '_ic_unwritten', False) or (held is not None and held[0] is x), 'float32 copy of this activation was not written'
         if held is not None and held[0] is x:
             # x exists as unscaled hi/lo planes (written by its batch norm): conv + merge-with-statistics, nothing else
             M = x.numel() // 128
@@ -388,7 +389,7 @@ class Trainer(object):
             tape.add(bwd)
         return y
 
-    def _bn(self, x, scope, relu, res1=None, res2=None):
+    def _bn(self, x, scope, relu, res1=None, res2=None, f32_out=True):
         gamma, beta = self._w(scope + '/BatchNorm/gamma'), self._w(scope + '/BatchNorm/beta')
         mm = self.stats.view(self.stats.w, scope + '/BatchNorm/moving_mean')
         mv = self.stats.view(self.stats.w, scope + '/BatchNorm/moving_variance')
@@ -400,15 +401,18 @@ class Trainer(object):
         # that conv as pre-scaled fp16 planes (no float32 dx, no maximum search, no split pass)
         grad_as_planes = partial is not None and self.is_training and os.environ.get('IC_TRAIN_FUSED_BWD', '1') != '0'
         self._stats_of = None
+        write_out = f32_out or planes is None      # f32_out=False: `out` only feeds the next 3x3 conv, which reads the planes
         if self.is_training:
             upd = self.update_moving
             out, mean, invstd = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, mm if upd else None, mv if upd else None,
-                                                partial=partial, planes_out=planes)
+                                                partial=partial, planes_out=planes, write_out=write_out)
         else:           # moving statistics (code/autoencoder.py:115-125 with is_training=False)
             mean, invstd = mm, torch.rsqrt(mv + nn.BN_EPS)
-            out, _, _ = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, stats=(mean, invstd), planes_out=planes)
+            out, _, _ = nn.bn_train_fwd(x, gamma, beta, relu, res1, res2, stats=(mean, invstd), planes_out=planes, write_out=write_out)
         if planes is not None:
             self._planes_of[out.data_ptr()] = (out, planes)       # holds `out`: its address cannot be reused within the step
+        if not write_out:
+            out._ic_unwritten = True                # placeholder: only its planes exist
         if self.tape is not None:
             tape, training = self.tape, self.is_training
 
@@ -431,11 +435,11 @@ class Trainer(object):
             tape.add(bwd)
         return out
 
-    def _slim_conv(self, x, scope, relu, res1=None, res2=None, need_dx=True):
+    def _slim_conv(self, x, scope, relu, res1=None, res2=None, need_dx=True, f32_out=True):
         """slim.conv2d / conv2d_transpose under _batch_norm_scope: conv (no bias) -> BN -> activation (+ fused adds)"""
         y = self._conv(x, self._w(scope + '/weights'), self._g(scope + '/weights'), self._stride[scope], self._tr[scope],
                        need_dx=need_dx, chans=self._shape[scope][1:], scope=scope)
-        return self._bn(y, scope, relu, res1, res2)
+        return self._bn(y, scope, relu, res1, res2, f32_out=f32_out)
 
     def _res_stack(self, net, prefix, tag, final_scope):
         """15 residual blocks with a skip every 3, a final block without ReLU and the long skip
@@ -445,9 +449,9 @@ class Trainer(object):
             rb = net
             for i in (1, 2, 3):
                 s = '{}/res_block_{}_{}/{}_{}_{}'.format(prefix, tag, b, tag, b, i)
-                y = self._slim_conv(net, s + '/conv1', True)
+                y = self._slim_conv(net, s + '/conv1', True, f32_out=False)      # conv1's output feeds conv2 only
                 net = self._slim_conv(y, s + '/conv2', False, res1=net, res2=rb if i == 3 else None)
-        y = self._slim_conv(net, prefix + '/' + final_scope + '/conv1', False)
+        y = self._slim_conv(net, prefix + '/' + final_scope + '/conv1', False, f32_out=False)
         return self._slim_conv(y, prefix + '/' + final_scope + '/conv2', False, res1=net, res2=r0)
 
     def _encode(self, x):
