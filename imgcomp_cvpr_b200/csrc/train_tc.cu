@@ -521,6 +521,113 @@ __global__ void __launch_bounds__(128) merge_stats_kernel(const __half* __restri
     partial[((int64_t)blockIdx.x * 128 + c) * 2 + 1] = t2;
 }
 
+
+// ---- tile-transposing forms of the planes -> float32 NHWC passes (C = 128; see bn_apply_planes_tt_kernel in train_ops.cu):
+// phase 1 reads the planes with a warp per chunk (32 pixels = 512 contiguous bytes), phase 2 writes float32 with a warp per
+// pixel (512 contiguous bytes).  A block moves 64 rows (two tiles of 32): warp g owns the rows r0 + g + 8 k, k = 0..7, in
+// ascending order -- col_partial_kernel's grouping, so the batch-norm partial sums keep their bits.
+constexpr int TT_PITCH = 264, TT_SMEM_FLOATS = 16 * TT_PITCH;
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) merge_tt_kernel(const __half* __restrict__ in, int64_t hw, int64_t M, int64_t plane,
+                                                       float* __restrict__ out, const float* __restrict__ mul,
+                                                       const float* __restrict__ add, double* __restrict__ partial) {
+    __shared__ __align__(16) float tile[2][TT_SMEM_FLOATS];
+    __shared__ float red[STATS ? 8 : 1][128][2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 64;
+    const float g = mul ? mul[0] : 1.f;
+    // phase 1: both tiles (64 rows x 16 chunks = 1024 (chunk, row) items, 4 per thread)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int item = threadIdx.x + 256 * j, tl = item >> 9, c = (item >> 5) & 15, p = item & 31;
+        const int64_t r = r0 + tl * 32 + p;
+        if (r < M) {
+            const int64_t n = r / hw, rr = r - n * hw;
+            const size_t off = (((size_t)n * 16 + c) * hw + rr) * 8;
+            const float4 h4 = *reinterpret_cast<const float4*>(in + off);
+            const float4 l4 = *reinterpret_cast<const float4*>(in + plane + off);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&h4);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&l4);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 a = __half22float2(h2[e]), b = __half22float2(l2[e]);
+                v[2 * e] = a.x + b.x;
+                v[2 * e + 1] = a.y + b.y;
+            }
+            float* t = tile[tl] + c * TT_PITCH + p * 8;
+            *reinterpret_cast<float4*>(t) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(t + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    __syncthreads();
+    // phase 2: warp w writes rows r0 + w + 8 k (k ascending); lane = channels 4 lane .. 4 lane + 3
+    float piv[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (STATS) {        // pivot = the tensor's row 0 (image 0, pixel 0), as col_partial_kernel's mode 0
+        const size_t off = ((size_t)(lane >> 1) * hw) * 8 + (lane & 1) * 4;
+        const uint2 hq = *reinterpret_cast<const uint2*>(in + off), lq = *reinterpret_cast<const uint2*>(in + plane + off);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&hq);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&lq);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float2 a = __half22float2(h2[e]), b = __half22float2(l2[e]);
+            piv[2 * e] = a.x + b.x;
+            piv[2 * e + 1] = a.y + b.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int row = w + 8 * k, tl = row >> 5, p = row & 31;
+        const int64_t r = r0 + row;
+        if (r < M) {
+            const float4 q = *reinterpret_cast<const float4*>(tile[tl] + (lane >> 1) * TT_PITCH + p * 8 + (lane & 1) * 4);
+            float v[4] = {q.x, q.y, q.z, q.w};
+            if (STATS) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float q1 = v[u] - piv[u];
+                    const float q2 = q1 * q1;
+                    s1[u] += q1;
+                    s2[u] += q2;
+                }
+            }
+            if (mul) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] *= g;
+            }
+            if (add) {
+                const float4 a = reinterpret_cast<const float4*>(add)[r * 32 + lane];
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            }
+            reinterpret_cast<float4*>(out)[r * 32 + lane] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    if (STATS) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            red[w][4 * lane + u][0] = s1[u];
+            red[w][4 * lane + u][1] = s2[u];
+        }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int c = threadIdx.x;
+            double t1 = 0, t2 = 0;
+            for (int ww = 0; ww < 8; ++ww) {
+                t1 += (double)red[ww][c][0];
+                t2 += (double)red[ww][c][1];
+            }
+            partial[((int64_t)blockIdx.x * 128 + c) * 2 + 0] = t1;
+            partial[((int64_t)blockIdx.x * 128 + c) * 2 + 1] = t2;
+        }
+    }
+}
+
+bool use_tt() {
+    static const bool tt = !(getenv("IC_TRAIN_TT") && atoi(getenv("IC_TRAIN_TT")) == 0);
+    return tt;
+}
+
 tc::GroupTable g_gt;
 bool g_gt_ready = false;
 
@@ -594,6 +701,13 @@ int conv_planes(const __half* in, const float* d_w, int data_grad, const float* 
     a.prof_class = IC_PROF_CONV3X3;
     int rc = tc::launch_conv_tc(a, s);
     if (rc != IC_OK) return rc;
+    if (use_tt()) {
+        const int64_t M = (int64_t)N * H * W;
+        ProfScope ps(IC_PROF_ELEMENTWISE, s);
+        merge_tt_kernel<false><<<(unsigned)((M + 63) / 64), 256, 0, s>>>(bo, (int64_t)H * W, M, M * kC, d_y, unscale, d_add, nullptr);
+        IC_CHECK_LAUNCH();
+        return IC_OK;
+    }
     return tc::launch_merge_to_nhwc(bo, N, H, W, kC, d_y, 1, s, unscale, d_add);
 }
 
@@ -1355,7 +1469,10 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
     if (rc != IC_OK) return rc;
     const int64_t M = (int64_t)N * H * W;
     ProfScope ps(IC_PROF_ELEMENTWISE, s);
-    merge_stats_kernel<<<(unsigned)((M + MS_ROWS - 1) / MS_ROWS), 128, 0, s>>>(bo, (int64_t)H * W, M, (int64_t)elems, d_y, d_bn_partial);
+    if (use_tt())
+        merge_tt_kernel<true><<<(unsigned)((M + 63) / 64), 256, 0, s>>>(bo, (int64_t)H * W, M, (int64_t)elems, d_y, nullptr, nullptr, d_bn_partial);
+    else
+        merge_stats_kernel<<<(unsigned)((M + MS_ROWS - 1) / MS_ROWS), 128, 0, s>>>(bo, (int64_t)H * W, M, (int64_t)elems, d_y, d_bn_partial);
     IC_CHECK_LAUNCH();
     return IC_OK;
 }
