@@ -446,7 +446,7 @@ def measure_train_step(steps):
     torch.cuda.empty_cache()
     return {'workload': 'cfg3: B=32 160x160 cvpr/med + res_shallow, forward + loss + backward + Adam (one CUDA graph replay)',
             'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'MPix_per_s': pix / (ms * 1e-3) / 1e6,
-            'dtype': 'f32 + f16x3 tcgen05 3x3 convs (forward, data gradient, filter gradient)', 'steps': steps,
+            'dtype': 'f32 + f16x3 tcgen05 convs (3x3 trunk, h2, h12, h13, context-model layers 1-3: forward, data gradient, filter gradient)', 'steps': steps,
             'gpu_launches_per_step': int(per_step), 'loss': out['total_loss'], 'bpp': out['bpp'], 'ms_ssim': out['ms_ssim'],
             'roofline': {'bound': 'tensor', 'achieved': tflop / (ms * 1e-3), 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': tflop / (ms * 1e-3) / peak if peak else None, 'peak_source': '%s bf16_tflops_sustained' % peak_src,

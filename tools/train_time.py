@@ -50,7 +50,7 @@ def main():
     pix = args.batch * args.size * args.size
     res = {'workload': 'cfg3 training step', 'ae': args.ae, 'batch': args.batch, 'H': args.size, 'W': args.size,
            'ms_per_step': ms, 'cuda_graph': bool(args.graph), 'wall_ms_per_step': wall, 'images_per_s': args.batch / (ms * 1e-3), 'MPix_per_s': pix / (ms * 1e-3) / 1e6,
-           'dtype': {'fp32': 'f32 (FFMA kernels)', 'exact': 'f32 + f16x3 tensor-core 3x3 convs (fwd, dgrad)'}[args.mode], 'loss': out['total_loss'], 'bpp': out['bpp'], 'ms_ssim': out['ms_ssim'],
+           'dtype': {'fp32': 'f32 (FFMA kernels)', 'exact': 'f32 + f16x3 tensor-core convs (fwd, dgrad, wgrad)'}[args.mode], 'loss': out['total_loss'], 'bpp': out['bpp'], 'ms_ssim': out['ms_ssim'],
            'counted_launches_per_step': (L.ic_launch_count() - n0) / args.steps,
            # forward FLOPs of SURVEY.md 8(d) x 3 (forward + data gradient + filter gradient)
            'algorithmic_tflop_per_step': 3 * 2 * (310562 + 309488 + 10470) * pix / 1e12}
