@@ -94,7 +94,10 @@ SIGNATURES = {
     'ic_nn_weight_scales': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'ic_nn_conv3x3_tc_fused_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'ic_nn_bn_partial_bytes': (c_size_t, [c_int64]),
-    'ic_nn_conv3x3_tc_fused': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_conv3x3_tc_prepared_bytes': (c_size_t, []),
+    'ic_nn_pack3x3_all': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'ic_nn_conv3x3_tc_fused': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
     'ic_nn_bn_train_fwd_ex': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
                                       c_void_p]),
@@ -102,8 +105,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_bn_train_bwd_ex': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
-    'ic_nn_conv3x3_tc_bwd_planes': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                            c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ic_nn_conv3x3_tc_bwd_planes': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ic_nn_hq_workspace_bytes': (c_size_t, [c_int64]),
     'ic_nn_hq_bwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -96,10 +96,9 @@ __global__ void __launch_bounds__(256) finalize_scales_kernel(ScaleArgs a, float
 // Same stage order as tc::pack_weights (k = 3, stride 1): stage = (cin quarter q, tap), within a stage
 // [plane hi|lo][4 chunks][128 cout rows][8 cin]; values pre-scaled by sc[0] (a power of two).
 // pair = 1: the layout of tc::repack_pair, [stage][cout half][plane][4 chunks][64 rows][8 cin] (CTA-pair kernel, cta_group::2)
-__global__ void __launch_bounds__(256) pack3x3_kernel(const float* __restrict__ w, int data_grad, const float* __restrict__ sc,
-                                                      __half* __restrict__ packed, float* __restrict__ scale_out = nullptr,
-                                                      float* __restrict__ shift_out = nullptr, int pair = 0) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over (stage, chunk, cout row, cin-in-chunk)
+__device__ __forceinline__ void pack3x3_elem(const float* __restrict__ w, int data_grad, const float* __restrict__ sc,
+                                             __half* __restrict__ packed, float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                             int pair, int i) {
     if (scale_out && i < kC) {             // epilogue of the conv: undo the weight pre-scale (a power of two: exact)
         scale_out[i] = 1.f / sc[0];
         shift_out[i] = 0.f;
@@ -126,6 +125,28 @@ __global__ void __launch_bounds__(256) pack3x3_kernel(const float* __restrict__ 
     const size_t base = (size_t)s * 2 * kPlaneElems + (size_t)(ch * kC + co) * 8 + ei;
     packed[base] = hi;
     packed[base + kPlaneElems] = lo;
+}
+
+__global__ void __launch_bounds__(256) pack3x3_kernel(const float* __restrict__ w, int data_grad, const float* __restrict__ sc,
+                                                      __half* __restrict__ packed, float* __restrict__ scale_out = nullptr,
+                                                      float* __restrict__ shift_out = nullptr, int pair = 0) {
+    pack3x3_elem(w, data_grad, sc, packed, scale_out, shift_out, pair, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// "prepared" weights of one trunk conv in one direction: the packed fp16 image followed by the epilogue's scale / shift vectors
+constexpr size_t kPackedBytes = (size_t)kStages * 2 * kPlaneElems * sizeof(__half);
+constexpr size_t kPreparedBytes = kPackedBytes + 2 * kC * sizeof(float);
+
+// every trunk conv of the step, both directions, in ONE launch (the weights do not change between the forward and the
+// backward pass of a step): blockIdx.y = layer * 2 + direction
+__global__ void __launch_bounds__(256) pack3x3_all_kernel(const float* __restrict__ base, const int64_t* __restrict__ offsets,
+                                                          const float* __restrict__ scales /* [n][4] */, uint8_t* __restrict__ prepared,
+                                                          int pair) {
+    const int layer = blockIdx.y >> 1, dir = blockIdx.y & 1;
+    uint8_t* dst = prepared + (size_t)blockIdx.y * kPreparedBytes;
+    float* sc = reinterpret_cast<float*>(dst + kPackedBytes);
+    pack3x3_elem(base + offsets[layer], dir, scales + 4 * layer, reinterpret_cast<__half*>(dst), sc, sc + kC, pair,
+                 blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ------------------------------------------------------------------ filter gradient on tcgen05
@@ -667,9 +688,13 @@ bool use_pair(int W) {
 // by unscale[0] (the inverse of the input's pre-scale) when the planes are merged back
 int conv_planes(const __half* in, const float* d_w, int data_grad, const float* params, const float* unscale, const float* scale,
                 const float* shift, __half* wp, __half* bo, int N, int H, int W, float* d_y, cudaStream_t s,
-                const float* d_add = nullptr) {
+                const float* d_add = nullptr, const void* prepared = nullptr) {
     const bool pair = use_pair(W);
-    {
+    if (prepared) {          // packed once per step by ic_nn_pack3x3_all
+        wp = reinterpret_cast<__half*>(const_cast<void*>(prepared));
+        scale = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(prepared) + kPackedBytes);
+        shift = scale + kC;
+    } else {
         ProfScope ps(IC_PROF_ELEMENTWISE, s);
         pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, data_grad, params, wp, nullptr, nullptr, pair ? 1 : 0);
         IC_CHECK_LAUNCH();
@@ -1417,11 +1442,27 @@ size_t ic_nn_conv3x3_tc_fused_workspace_bytes(int N, int H, int W) {
 
 size_t ic_nn_bn_partial_bytes(int64_t M) { return M > 0 ? (size_t)((M + MS_ROWS - 1) / MS_ROWS) * kC * 2 * sizeof(double) : 0; }
 
+/* every trunk conv's weights packed for the kernel, forward and data-gradient direction, in one launch per step:
+ * d_prepared receives n x 2 entries of ic_nn_conv3x3_tc_prepared_bytes() (entry 2 i = forward of tensor i, 2 i + 1 = its data
+ * gradient); W = the width of the images the convs will run on (selects the CTA-pair weight layout like the convs do) */
+size_t ic_nn_conv3x3_tc_prepared_bytes(void) { return kPreparedBytes; }
+
+int ic_nn_pack3x3_all(const float* d_base, const int64_t* d_offsets, const float* d_scales, int n, int W, void* d_prepared, void* stream) {
+    IC_REQUIRE(d_base && d_offsets && d_scales && d_prepared && n > 0, IC_ERR_INVALID, "ic_nn_pack3x3_all: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(IC_PROF_ELEMENTWISE, s);
+    pack3x3_all_kernel<<<dim3(cdiv(kStages * kPlaneElems, 256), 2 * n), 256, 0, s>>>(d_base, d_offsets, d_scales, (uint8_t*)d_prepared,
+                                                                                   use_pair(W) ? 1 : 0);
+    IC_CHECK_LAUNCH();
+    return IC_OK;
+}
+
 /* y = conv3x3(x, w) for the 128 -> 128 trunk convs: d_x_planes = the UNSCALED fp16 hi/lo planes of x (what
- * ic_nn_bn_train_fwd_ex wrote), d_wscale4 = this layer's row of ic_nn_weight_scales.  d_bn_partial (ic_nn_bn_partial_bytes(N H W))
+ * ic_nn_bn_train_fwd_ex wrote), d_wscale4 = this layer's row of ic_nn_weight_scales, d_prepared (optional) = its forward
+ * entry of ic_nn_pack3x3_all (else the weights are packed here).  d_bn_partial (ic_nn_bn_partial_bytes(N H W))
  * receives the batch-norm partial sums of y for ic_nn_bn_train_fwd_ex. */
-int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float* d_wscale4, int N, int H, int W, float* d_y,
-                           double* d_bn_partial, void* d_workspace, size_t workspace_bytes, void* stream) {
+int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float* d_wscale4, const void* d_prepared, int N, int H,
+                           int W, float* d_y, double* d_bn_partial, void* d_workspace, size_t workspace_bytes, void* stream) {
     IC_REQUIRE(d_x_planes && d_w && d_wscale4 && d_y && d_bn_partial && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_fused: NULL argument");
     IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc_fused: bad shape");
     IC_REQUIRE(workspace_bytes >= ic_nn_conv3x3_tc_fused_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_fused: workspace too small");
@@ -1436,7 +1477,11 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
     float* shift = ar.get<float>(kC);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_fused: workspace too small");
     const bool pair = use_pair(W);
-    {
+    if (d_prepared) {
+        wp = reinterpret_cast<__half*>(const_cast<void*>(d_prepared));
+        scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(const_cast<void*>(d_prepared)) + kPackedBytes);
+        shift = scale + kC;
+    } else {
         ProfScope ps(IC_PROF_ELEMENTWISE, s);
         pack3x3_kernel<<<cdiv(kStages * kPlaneElems, 256), 256, 0, s>>>(d_w, 0, d_wscale4, wp, scale, shift, pair ? 1 : 0);
         IC_CHECK_LAUNCH();
@@ -1482,9 +1527,9 @@ int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float
  * d_dy_planes with d_dy_scale = {s, 1/s}; d_x_planes / d_scales as in ic_nn_conv3x3_tc_bwd_ex (required).  No maximum
  * search, no split pass.  d_dx_add (optional, same shape as d_dx): d_dx = data gradient + d_dx_add, the gradient the input
  * already received through a residual connection (saves the separate accumulation pass). */
-int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, int N, int H, int W, float* d_dx,
-                                const float* d_dx_add, float* d_dw, const void* d_x_planes, const float* d_scales, void* d_workspace,
-                                size_t workspace_bytes, void* stream) {
+int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, const void* d_prepared_dgrad,
+                                int N, int H, int W, float* d_dx, const float* d_dx_add, float* d_dw, const void* d_x_planes,
+                                const float* d_scales, void* d_workspace, size_t workspace_bytes, void* stream) {
     IC_REQUIRE(d_dy_planes && d_dy_scale && d_w && d_dw && d_x_planes && d_scales && d_workspace, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd_planes: NULL argument");
     IC_REQUIRE(N > 0 && H > 0 && W > 0, IC_ERR_INVALID, "ic_nn_conv3x3_tc_bwd_planes: bad shape");
     IC_REQUIRE(workspace_bytes >= ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_bwd_planes: workspace too small");
@@ -1526,7 +1571,7 @@ int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale
         IC_CHECK_LAUNCH();
     }
     if (!d_dx) return IC_OK;
-    return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s, d_dx_add);
+    return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s, d_dx_add, d_prepared_dgrad);
 }
 
 }  // extern "C"

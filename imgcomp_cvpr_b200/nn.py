@@ -238,7 +238,19 @@ def bn_partial_buffer(M, device):
     return torch.empty(_lib.lib().ic_nn_bn_partial_bytes(M) // 8, dtype=torch.float64, device=device)
 
 
-def conv3x3_tc_fused(x_planes, w, wscale, shape, partial):
+def pack3x3_all(base, offsets, scales, W, out=None):
+    """packed weight images of all trunk convs (forward + data gradient) in one launch -> uint8 tensor (n, 2, entry bytes);
+    row [i, 0] / [i, 1] is the `prepared` argument of conv3x3_tc_fused / conv3x3_tc_bwd_planes for tensor i"""
+    L = _lib.lib()
+    n, eb = offsets.numel(), L.ic_nn_conv3x3_tc_prepared_bytes()
+    if out is None:
+        out = torch.empty((n, 2, eb), dtype=torch.uint8, device=base.device)
+    assert out.shape == (n, 2, eb) and out.is_contiguous()
+    _lib.check(L.ic_nn_pack3x3_all(_lib.ptr(_f32(base)), _lib.ptr(offsets), _lib.ptr(_f32(scales)), n, int(W), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def conv3x3_tc_fused(x_planes, w, wscale, shape, partial, prepared=None):
     """conv3x3_tc for an input that already exists as UNSCALED fp16 hi/lo planes (bn_train_fwd(planes_out=...)): no maximum
     search, no split; -> y (float32 NHWC) and the batch-norm partial sums of y in `partial` (bn_partial_buffer)."""
     N, H, W, C = shape
@@ -247,7 +259,7 @@ def conv3x3_tc_fused(x_planes, w, wscale, shape, partial):
     L = _lib.lib()
     assert partial.numel() * 8 >= L.ic_nn_bn_partial_bytes(N * H * W)
     ws = _workspace(L.ic_nn_conv3x3_tc_fused_workspace_bytes(N, H, W))
-    _lib.check(L.ic_nn_conv3x3_tc_fused(_lib.ptr(x_planes), _lib.ptr(_f32(w)), _lib.ptr(_f32(wscale)), N, H, W, _lib.ptr(y), _lib.ptr(partial),
+    _lib.check(L.ic_nn_conv3x3_tc_fused(_lib.ptr(x_planes), _lib.ptr(_f32(w)), _lib.ptr(_f32(wscale)), _lib.ptr(prepared), N, H, W, _lib.ptr(y), _lib.ptr(partial),
                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return y
 
@@ -291,7 +303,7 @@ def bn_train_bwd_planes(x, dy, gamma, beta, mean, invstd, relu=False, dgamma=Non
     return PlanesGrad(planes, scale, x.shape), dgamma, dbeta
 
 
-def conv3x3_tc_bwd_planes(dy, w, need_dx=True, dw_out=None, cache=None, dx_add=None):
+def conv3x3_tc_bwd_planes(dy, w, need_dx=True, dw_out=None, cache=None, dx_add=None, prepared=None):
     """conv3x3_tc_bwd for dy given as a PlanesGrad; cache = (x planes, scales) of the forward pass (required);
     dx_add: gradient the input already has (residual path) -> dx = data gradient + dx_add in the same pass"""
     N, H, W, C = dy.shape
@@ -301,7 +313,7 @@ def conv3x3_tc_bwd_planes(dy, w, need_dx=True, dw_out=None, cache=None, dx_add=N
     dw = torch.empty_like(w) if dw_out is None else dw_out
     ws = _workspace(_lib.lib().ic_nn_conv3x3_tc_bwd_workspace_bytes(N, H, W))
     assert dx_add is None or (need_dx and tuple(dx_add.shape) == tuple(dy.shape))
-    _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd_planes(_lib.ptr(dy.planes), _lib.ptr(dy.scale), _lib.ptr(_f32(w)), N, H, W, _lib.ptr(dx),
+    _lib.check(_lib.lib().ic_nn_conv3x3_tc_bwd_planes(_lib.ptr(dy.planes), _lib.ptr(dy.scale), _lib.ptr(_f32(w)), _lib.ptr(prepared), N, H, W, _lib.ptr(dx),
                                                      _lib.ptr(None if dx_add is None else _f32(dx_add)), _lib.ptr(_f32(dw)), _lib.ptr(planes),
                                                      _lib.ptr(scales), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return dx, dw

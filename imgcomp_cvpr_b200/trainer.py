@@ -226,6 +226,8 @@ class Trainer(object):
         self._planes_of = {}
         self._stats_of = None
         self._bn_partial = None
+        self._prep = self._prep_buf = None
+        self._prep_w = -1
         self.tape = None
         self._adam_t = 0
         self._graph = None
@@ -332,12 +334,14 @@ class Trainer(object):
         """start of a forward pass: forget the planes of the previous pass, refresh the trunk convs' weight scales"""
         self._planes_of = {}
         self._stats_of = None
+        self._prep = None           # packed trunk weights of this pass (filled at the first trunk conv: needs the image width)
         if self._fused() and self._trunk:
             nn.weight_scales(self.groups['ae_w'].w, self._trunk_off, 9 * 128 * 128, self._trunk_scales)
 
     def _conv(self, x, w, gw, stride=1, transposed=False, valid=False, need_dx=True, mask=None, chans=None, scope=None):
         tc = (self.mode == 'exact' and tuple(w.shape) == (3, 3, 128, 128) and stride == 1 and not transposed and not valid)
         plan_f = plan_d = plan_w = None
+        prep_d = None
         if not tc and chans is not None and w.shape[0] == 5 and stride == 2 and not valid:
             plan_f, plan_d, plan_w = self._tc_plans('tconv5s2' if transposed else 'conv5s2', *chans)
         cache = None
@@ -348,8 +352,13 @@ class Trainer(object):
             M = x.numel() // 128
             if self._bn_partial is None or self._bn_partial.numel() * 8 < _lib.lib().ic_nn_bn_partial_bytes(M):
                 self._bn_partial = nn.bn_partial_buffer(M, x.device)
-            wscale = self._trunk_scales[self._trunk_row[scope]]
-            y = nn.conv3x3_tc_fused(held[1], w, wscale, tuple(x.shape), self._bn_partial)
+            row = self._trunk_row[scope]
+            wscale = self._trunk_scales[row]
+            if self._prep is None or self._prep_w != x.shape[2]:      # all trunk weights packed once per pass
+                self._prep = nn.pack3x3_all(self.groups['ae_w'].w, self._trunk_off, self._trunk_scales, x.shape[2], self._prep_buf)
+                self._prep_buf, self._prep_w = self._prep, x.shape[2]
+            prep_d = self._prep[row, 1]
+            y = nn.conv3x3_tc_fused(held[1], w, wscale, tuple(x.shape), self._bn_partial, prepared=self._prep[row, 0])
             cache = (held[1], wscale)
             self._stats_of = y
             if self.tape is None:           # forward only: nothing reads these planes again
@@ -371,7 +380,7 @@ class Trainer(object):
                     if isinstance(dy, nn.PlanesGrad):       # the batch norm's backward wrote the conv's operand directly
                         # the gradient x already has (residual path) is added in the conv's own output pass
                         had = tape.take(x) if need_dx else None
-                        dx, _ = nn.conv3x3_tc_bwd_planes(dy, w, need_dx=need_dx, dw_out=gw, cache=cache, dx_add=had)
+                        dx, _ = nn.conv3x3_tc_bwd_planes(dy, w, need_dx=need_dx, dw_out=gw, cache=cache, dx_add=had, prepared=prep_d)
                     else:
                         dx, _ = nn.conv3x3_tc_bwd(x, dy, w, need_dx=need_dx, dw_out=gw, cache=cache)
                     if need_dx:

@@ -278,8 +278,13 @@ int ic_nn_bn_train_fwd(const float* d_x, int64_t M, int C, const float* d_gamma,
 int ic_nn_weight_scales(const float* d_base, const int64_t* d_offsets, int n, int64_t count, float* d_scales, void* stream);
 size_t ic_nn_conv3x3_tc_fused_workspace_bytes(int N, int H, int W);
 size_t ic_nn_bn_partial_bytes(int64_t M);
-int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float* d_wscale4, int N, int H, int W, float* d_y,
-                           double* d_bn_partial, void* d_workspace, size_t workspace_bytes, void* stream);
+/* ic_nn_pack3x3_all: the packed weight images of all n trunk convs, forward (entry 2 i) and data gradient (2 i + 1), in one
+ * launch per step; entries of ic_nn_conv3x3_tc_prepared_bytes() bytes, handed to the two calls below as d_prepared
+ * (optional: NULL = pack per call). */
+size_t ic_nn_conv3x3_tc_prepared_bytes(void);
+int ic_nn_pack3x3_all(const float* d_base, const int64_t* d_offsets, const float* d_scales, int n, int W, void* d_prepared, void* stream);
+int ic_nn_conv3x3_tc_fused(const void* d_x_planes, const float* d_w, const float* d_wscale4, const void* d_prepared, int N, int H,
+                           int W, float* d_y, double* d_bn_partial, void* d_workspace, size_t workspace_bytes, void* stream);
 int ic_nn_bn_train_fwd_ex(const float* d_x, int64_t M, int C, const float* d_gamma, const float* d_beta, float eps, int relu,
                           int use_stats, const float* d_res1, const float* d_res2, float* d_mean, float* d_invstd,
                           float* d_mov_mean, float* d_mov_var, float* d_out, const double* d_partial_in, void* d_planes_out,
@@ -295,7 +300,8 @@ int ic_nn_bn_train_bwd_ex(const float* d_x, const float* d_dy, int64_t M, int C,
                           int use_stats, const float* d_mean, const float* d_invstd, float* d_dx, float* d_dgamma, float* d_dbeta,
                           void* d_dx_planes, float* d_scale_out, int64_t hw, void* d_workspace, size_t workspace_bytes,
                           void* stream);
-int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, int N, int H, int W, float* d_dx,
+int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale, const float* d_w, const void* d_prepared_dgrad,
+                                int N, int H, int W, float* d_dx,
                                 const float* d_dx_add /* optional: d_dx = gradient + d_dx_add */, float* d_dw,
                                 const void* d_x_planes, const float* d_scales, void* d_workspace, size_t workspace_bytes,
                                 void* stream);
