@@ -418,12 +418,12 @@ __global__ void __launch_bounds__(256) wgrad_gather_kernel(const float* __restri
 
 // dW = (sum over splits, fixed order) / (scale_x * scale_dy)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, const float* __restrict__ params,
-                                                           float* __restrict__ dw) {
+                                                           float* __restrict__ dw, const float* __restrict__ scale_b = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kW) return;
     float s = 0.f;
     for (int k = 0; k < n_splits; ++k) s += partial[(size_t)k * kW + i];
-    dw[i] = s / (params[0] * params[1]);
+    dw[i] = s / (params[0] * (scale_b ? scale_b[0] : params[1]));       // the two operand scales (adjacent, or from two places)
 }
 
 // ---- fused forward of a trunk layer (training): the conv reads the fp16 planes the previous batch-norm kernel wrote
@@ -1546,7 +1546,7 @@ int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale
     float* shift = ar.get<float>(kC);
     float* params = ar.get<float>(8);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_conv3x3_tc_bwd_planes: workspace too small");
-    {
+    if (!d_prepared_dgrad) {      // with prepared weights every scale is read where it lives: no parameter block to set up
         ProfScope ps(IC_PROF_ELEMENTWISE, s);
         set_params_kernel<<<1, 128, 0, s>>>(d_scales, d_dy_scale, params, scale, shift);
         IC_CHECK_LAUNCH();
@@ -1567,11 +1567,13 @@ int ic_nn_conv3x3_tc_bwd_planes(const void* d_dy_planes, const float* d_dy_scale
         ProfScope ps(IC_PROF_CONV3X3, s, 2);
         wgrad_tc_kernel<<<3 * S, WG_THREADS, smem, s>>>(xmap, ymap, N, H, W, S, partial);
         IC_CHECK_LAUNCH();
-        wgrad_reduce_kernel<<<cdiv(kW, 256), 256, 0, s>>>(partial, S, params + 1, d_dw);     // / (s_dy * s_x)
+        if (d_prepared_dgrad) wgrad_reduce_kernel<<<cdiv(kW, 256), 256, 0, s>>>(partial, S, d_dy_scale, d_dw, d_scales + 1);
+        else wgrad_reduce_kernel<<<cdiv(kW, 256), 256, 0, s>>>(partial, S, params + 1, d_dw);     // / (s_dy * s_x)
         IC_CHECK_LAUNCH();
     }
     if (!d_dx) return IC_OK;
-    return conv_planes(bdy, d_w, 1, params, params + 5, scale, shift, wp, bo, N, H, W, d_dx, s, d_dx_add, d_prepared_dgrad);
+    return conv_planes(bdy, d_w, 1, params, d_prepared_dgrad ? d_dy_scale + 1 : params + 5, scale, shift, wp, bo, N, H, W, d_dx, s, d_dx_add,
+                       d_prepared_dgrad);
 }
 
 }  // extern "C"
