@@ -321,3 +321,23 @@ def test_tc_plan_unsupported_shapes_fall_back():
     assert nn.TcPlan.get('conv5s2', False, 3, 64) is None          # h1
     assert nn.TcPlan.get('conv5s2', False, 128, 33) is None        # to_bn
     assert nn.TcPlan.get('pc', False, 1, 24) is None               # first context-model layer (one input channel)
+
+
+def test_tc_plan_pack_map_covers_every_weight_once():
+    """the pack map of a plan (derived from the host packers through base-2047 digits) sends every real weight of the op to
+    exactly one hi element of the packed image; everything else is zero padding"""
+    from imgcomp_cvpr_b200 import _lib, nn
+    for kind, data_grad, cin, cout, n_w in (('conv5s2', False, 64, 128, 25 * 64 * 128), ('conv5s2', True, 64, 128, 25 * 64 * 128),
+                                            ('tconv5s2', False, 128, 64, 25 * 128 * 64), ('tconv5s2', True, 128, 64, 25 * 128 * 64),
+                                            ('tconv5s2', False, 64, 3, 25 * 64 * 3), ('pc', False, 24, 24, 14 * 24 * 24),
+                                            ('pc', True, 24, 6, 14 * 24 * 6)):
+        plan = nn.TcPlan.get(kind, data_grad, cin, cout)
+        L = _lib.lib()
+        n = L.ic_nn_tc_plan_map(plan.h, None, 0)
+        m = np.empty(n, np.int32)
+        assert L.ic_nn_tc_plan_map(plan.h, m.ctypes.data, n) == n
+        used = m[m >= 0]
+        assert used.size == n_w and np.unique(used).size == n_w, (kind, data_grad, used.size, n_w)
+        c4 = lambda v: (v + 3) // 4 * 4
+        taps = 18 if kind == 'pc' else 25
+        assert used.max() < taps * c4(cin) * c4(cout)
