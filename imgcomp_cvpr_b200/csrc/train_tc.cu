@@ -760,7 +760,8 @@ struct TcPlan {
     int* d_map;
 };
 
-enum { TCK_CONV5S2 = 0, TCK_TCONV5S2 = 1, TCK_TCONV5S2_IMG = 2, TCK_PC = 3 };
+enum { TCK_CONV5S2 = 0, TCK_TCONV5S2 = 1, TCK_TCONV5S2_IMG = 2, TCK_PC = 3, TCK_CONV5S2_F32 = 4 };
+__host__ __device__ inline bool tck_strided(int k) { return k == TCK_CONV5S2 || k == TCK_CONV5S2_F32; }
 
 __global__ void __launch_bounds__(256) pack_map_kernel(const float* __restrict__ w, const int* __restrict__ map, int total, int half,
                                                        const float* __restrict__ sc, __half* __restrict__ packed) {
@@ -1026,9 +1027,12 @@ int ic_nn_tc_plan_create(int op_kind, int data_grad, int op_cin, int op_cout, ic
         if (cin_e % 32 != 0 || pl.cin_pad != cin_e) return IC_ERR_UNSUPPORTED;
         std::vector<int> src((size_t)25 * cin_e * cout_e);
         if (eff_strided) {
-            if (cin_e % 64 != 0 || cout_e != 128) return IC_ERR_UNSUPPORTED;
-            pl.kind = TCK_CONV5S2;
-            pl.nout = 128;
+            if (cin_e % 64 != 0 || !(cout_e == 128 || cout_e <= 80)) return IC_ERR_UNSUPPORTED;
+            // 128 columns: plane output + merge pass; narrower (to_bn: 33 -> 48 columns): the kernel writes float32 NHWC itself,
+            // all cout_pad channels (the padding columns have zero weights)
+            pl.kind = cout_e == 128 ? TCK_CONV5S2 : TCK_CONV5S2_F32;
+            pl.nout = cout_e == 128 ? 128 : (cout_e <= 48 ? 48 : 80);
+            if (pl.kind == TCK_CONV5S2_F32) pl.cout = pl.cout_pad;
             for (int t = 0; t < 25; ++t)
                 for (int i = 0; i < cin_e; ++i)
                     for (int o = 0; o < cout_e; ++o)      // expected HWIO [t][i][o]
@@ -1091,8 +1095,8 @@ PlanGeo plan_geo(const TcPlan& p, int D, int N, int H, int W) {
     } else {
         g.in_imgs = g.out_imgs = N;
         g.Hi = H; g.Wi = W;
-        g.Ho = p.kind == TCK_CONV5S2 ? H / 2 : 2 * H;
-        g.Wo = p.kind == TCK_CONV5S2 ? W / 2 : 2 * W;
+        g.Ho = tck_strided(p.kind) ? H / 2 : 2 * H;
+        g.Wo = tck_strided(p.kind) ? W / 2 : 2 * W;
     }
     return g;
 }
@@ -1117,7 +1121,7 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
     IC_REQUIRE(plan && d_x && d_w && d_y && d_workspace, IC_ERR_INVALID, "ic_nn_tc_plan_run: NULL argument");
     const TcPlan& p = plan->p;
     IC_REQUIRE(N > 0 && H > 0 && W > 0 && (p.kind != TCK_PC || D > (p.data_grad ? 0 : 1)), IC_ERR_INVALID, "ic_nn_tc_plan_run: bad shape");
-    IC_REQUIRE(p.kind != TCK_CONV5S2 || (H % 2 == 0 && W % 2 == 0), IC_ERR_INVALID, "ic_nn_tc_plan_run: odd size for a stride-2 conv");
+    IC_REQUIRE(!tck_strided(p.kind) || (H % 2 == 0 && W % 2 == 0), IC_ERR_INVALID, "ic_nn_tc_plan_run: odd size for a stride-2 conv");
     IC_REQUIRE(workspace_bytes >= ic_nn_tc_plan_workspace_bytes(plan, D, N, H, W), IC_ERR_WORKSPACE, "ic_nn_tc_plan_run: workspace too small");
     const PlanGeo g = plan_geo(p, D, N, H, W);
     IC_REQUIRE(g.Ho > 0 && g.Wo > 0 && g.out_imgs > 0, IC_ERR_INVALID, "ic_nn_tc_plan_run: empty output");
@@ -1136,7 +1140,7 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
     float* pw = ar.get<float>(kMaxBlocks);
     float* px = ar.get<float>(kMaxBlocks);
     IC_REQUIRE(ar.ok(), IC_ERR_WORKSPACE, "ic_nn_tc_plan_run: workspace too small");
-    const bool f32_out = p.kind == TCK_PC || p.kind == TCK_TCONV5S2_IMG;
+    const bool f32_out = p.kind == TCK_PC || p.kind == TCK_TCONV5S2_IMG || p.kind == TCK_CONV5S2_F32;
     ScaleArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.ntens = 2;
@@ -1154,7 +1158,7 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
         IC_CHECK_LAUNCH();
     }
     // float32 NHWC (x sx) -> fp16 hi/lo planes; the strided conv reads its input in space-to-depth form
-    rc = tc::launch_split_from_nhwc(d_x, (int)g.in_imgs, g.Hi, g.Wi, p.cin_pad, p.kind == TCK_CONV5S2 ? 1 : 0, bi, 1, s, params + 1);
+    rc = tc::launch_split_from_nhwc(d_x, (int)g.in_imgs, g.Hi, g.Wi, p.cin_pad, tck_strided(p.kind) ? 1 : 0, bi, 1, s, params + 1);
     if (rc != IC_OK) return rc;
     tc::ConvTcArgs a;
     memset(&a, 0, sizeof(a));
@@ -1172,7 +1176,7 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
     a.cpg = 4;
     a.exact = 1;
     a.prof_class = p.kind == TCK_PC ? IC_PROF_PROBCLASS : IC_PROF_CONV_OTHER;
-    if (p.kind == TCK_CONV5S2) {
+    if (tck_strided(p.kind)) {
         a.Nimg = N;
         a.in_chunks = 4 * p.cin_pad / 8;
         a.Hin = H / 2;
@@ -1180,7 +1184,8 @@ int ic_nn_tc_plan_run(const ic_tc_plan_t* plan, const float* d_x, const float* d
         a.H = g.Ho;
         a.W = g.Wo;
         a.halo0 = -1;
-        a.out = bo;
+        if (p.kind == TCK_CONV5S2) a.out = bo;
+        else a.out_f32 = d_y;
     } else if (p.kind == TCK_PC) {
         a.Nimg = (int)g.in_imgs;
         a.in_chunks = p.cin_pad / 8;

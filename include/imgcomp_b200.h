@@ -240,7 +240,8 @@ int ic_nn_conv3x3_tc_bwd_ex(const float* d_x, const float* d_dy, const float* d_
  *   op_kind 3  masked (2,3,3) VALID conv3d          (code/probclass.py:227-261; "other" mask, depth-major volume (D,N,H,W,C))
  * data_grad = 1 plans the gradient w.r.t. the op's input.  d_w is the op's float32 weight array as ic_nn_conv2d_* take it
  * ([5][5][ceil4 Cin][ceil4 Cout], [2][3][3][ceil4 Cin][ceil4 Cout]).  ic_nn_tc_plan_create returns IC_ERR_UNSUPPORTED for
- * shapes without a tensor-core kernel (h1, to_bn, from_bn, the context model's first layer): use ic_nn_conv2d_* there.
+ * shapes without a tensor-core kernel (h1, from_bn, the gradients of to_bn, the context model's first layer): use
+ * ic_nn_conv2d_* there.
  * ic_nn_tc_plan_run: D, N, H, W are the dimensions of d_x (D only for op_kind 3); d_y is (N, H/2, W/2, C') / (N, 2H, 2W, C')
  * / (D-1, N, H-2, W-2, C') forward, (D+1, N, H+2, W+2, C') context-model data gradient. */
 typedef struct ic_tc_plan ic_tc_plan_t;

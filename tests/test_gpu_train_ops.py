@@ -209,6 +209,8 @@ def _rel(a, ref):
     ('tconv5s2', 2, 12, 20, 128, 64, 1.0),       # h12
     ('tconv5s2', 3, 10, 8, 128, 64, 2e-4),
     ('tconv5s2', 2, 20, 36, 64, 3, 1.0),         # h13 (forward only: its data gradient has 3 input channels)
+    ('conv5s2', 2, 24, 40, 128, 33, 1.0),        # to_bn, cvpr/low (forward only: 48 columns, float32 output from the kernel)
+    ('conv5s2', 1, 16, 32, 128, 65, 1.0),        # to_bn, cvpr/hi (80 columns)
 ])
 def test_tc_plan_strided_convs(case):
     from imgcomp_cvpr_b200 import nn
@@ -235,7 +237,7 @@ def test_tc_plan_strided_convs(case):
     assert err < 2e-5
     assert not yg[..., Cout:].any()
     pw = nn.TcWgradPlan.get(kind, Cin, Cout)
-    if Cout == 3:
+    if Cout in (3, 33, 65):
         assert pd is None and pw is None
         return
     assert pd is not None
@@ -319,7 +321,7 @@ def test_tc_plan_context_model_layers(case):
 def test_tc_plan_unsupported_shapes_fall_back():
     from imgcomp_cvpr_b200 import nn
     assert nn.TcPlan.get('conv5s2', False, 3, 64) is None          # h1
-    assert nn.TcPlan.get('conv5s2', False, 128, 33) is None        # to_bn
+    assert nn.TcPlan.get('conv5s2', True, 128, 33) is None         # to_bn's data gradient (33 input channels)
     assert nn.TcPlan.get('pc', False, 1, 24) is None               # first context-model layer (one input channel)
 
 
