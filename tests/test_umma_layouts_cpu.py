@@ -136,3 +136,53 @@ def test_b_concatenation_layout_for_exact_mode():
         k = slice(ks * 16, ks * 16 + 16)
         assert np.array_equal(b[:rows], w_hi[k].T) and np.array_equal(b[rows:], w_lo[k].T)
         assert np.array_equal(operand(smem, ks * 2 * (2 * rows * 16), lbo=2 * rows * 16, sbo=128, rows=rows, major='K'), w_hi[k].T)
+
+
+def test_context_model_third_chunks_of_two_taps_share_one_k_step():
+    """conv_tc.cu, context-model kernels (pair_c2): 24 input channels are 3 chunks, so k-step 1 of a tap would hold one real
+    chunk and one all-zero chunk.  The third chunks of taps 2j and 2j+1 form ONE k-step instead: A's two K core matrices are
+    (tap 2j, chunk 2) and (tap 2j+1, chunk 2) -- LBO = the tap shift, 16 bytes for horizontally adjacent taps, i.e. overlapping
+    core matrices -- and B's are chunk 2 of the two taps' resident stages, LBO = the stage pitch.  The emulated schedule
+    (22 k-steps for the 14 taps) must equal the VALID masked conv."""
+    rng = np.random.RandomState(3)
+    Hh, Ww, K, NO = 18, 10, 24, 32                      # one 16 x 8 tile with its VALID halo; 24 channels, 32 columns
+    x = _ints(rng, (2, Hh, Ww, 32))                     # two depth slices, channels padded to 32
+    x[..., K:] = 0
+    w = _ints(rng, (2, 3, 3, 32, NO), -2, 3)
+    w[:, :, :, K:, :] = 0
+    halo_w, halo_pix = Ww, Hh * Ww
+    groups = [[(0, fy, fx) for fy in range(3) for fx in range(3)],
+              [(1, fy, fx) for fy in range(3) for fx in range(3) if not (fy > 1 or (fy == 1 and fx > 1))]]
+    acc = np.zeros((128, NO), np.float64)
+    nks = 0
+    for g, taps in enumerate(groups):
+        a_smem = tma_tile(to_planes(x[g:g + 1]), 0, 0, 4, 0, 0, Hh, Ww).reshape(4, halo_pix, 8).view(np.uint8).reshape(-1)
+        # resident weight stages of the group, one per tap: [4 chunks][NO rows][8 cin]
+        stages = np.zeros((len(taps), 4, NO, 8), np.float16)
+        for ti, (fd, fy, fx) in enumerate(taps):
+            for ch in range(4):
+                stages[ti, ch] = w[fd, fy, fx, ch * 8:(ch + 1) * 8, :].T
+        w_smem = stages.view(np.uint8).reshape(-1)
+        stage_pitch, chunk_pitch = 4 * NO * 16, NO * 16
+        shift = lambda t: (t[1] * halo_w + t[2]) * 16
+        for ti, tap in enumerate(taps):
+            if ti & 1:                                   # chunk 2 of taps ti-1 and ti
+                prev = taps[ti - 1]
+                a = operand(a_smem, shift(prev) + 2 * halo_pix * 16, lbo=shift(tap) - shift(prev), sbo=halo_w * 16, rows=128, major='K')
+                b = operand(w_smem, (ti - 1) * stage_pitch + 2 * chunk_pitch, lbo=stage_pitch, sbo=128, rows=NO, major='K')
+                acc += a.astype(np.float64) @ b.astype(np.float64).T
+                nks += 1
+            a = operand(a_smem, shift(tap), lbo=halo_pix * 16, sbo=halo_w * 16, rows=128, major='K')      # chunks 0, 1
+            b = operand(w_smem, ti * stage_pitch, lbo=chunk_pitch, sbo=128, rows=NO, major='K')
+            acc += a.astype(np.float64) @ b.astype(np.float64).T
+            nks += 1
+            if (ti & 1) == 0 and ti == len(taps) - 1:    # unpaired last tap: chunk 2 with the all-zero chunk 3
+                a = operand(a_smem, shift(tap) + 2 * halo_pix * 16, lbo=halo_pix * 16, sbo=halo_w * 16, rows=128, major='K')
+                b = operand(w_smem, ti * stage_pitch + 2 * chunk_pitch, lbo=chunk_pitch, sbo=128, rows=NO, major='K')
+                acc += a.astype(np.float64) @ b.astype(np.float64).T
+                nks += 1
+    assert nks == 22
+    for m in range(128):
+        ty, tx = m >> 3, m & 7
+        ref = sum(x[fd, ty + fy, tx + fx].astype(np.float64) @ w[fd, fy, fx] for taps in groups for (fd, fy, fx) in taps)
+        assert np.array_equal(acc[m], ref), m
