@@ -550,6 +550,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
 #pragma unroll
                             for (int hc = 0; hc < 2; ++hc) {
                                 const int chunk = cc * 2 + hc;
+                                if (p.store_chunks && chunk >= p.store_chunks) continue;      // all-zero padding channels
                                 // depth-to-space output (transposed convs): column block = (output phase, channel chunk)
                                 const int sch = p.d2s_cch ? chunk % p.d2s_cch : chunk;
                                 float v[8];
@@ -1168,8 +1169,8 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     IC_REQUIRE(enc, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap map;
     const cuuint64_t hw16 = (cuuint64_t)a.Hin * a.Win * 16;
-    const cuuint64_t dims[5] = {(cuuint64_t)a.Win * 8, (cuuint64_t)a.Hin, (cuuint64_t)a.in_chunks, (cuuint64_t)a.Nimg,
-                                (cuuint64_t)NPL};
+    const cuuint64_t dims[5] = {(cuuint64_t)a.Win * 8, (cuuint64_t)a.Hin, (cuuint64_t)(a.in_chunks_valid ? a.in_chunks_valid : a.in_chunks),
+                                (cuuint64_t)a.Nimg, (cuuint64_t)NPL};
     const cuuint64_t strides[4] = {(cuuint64_t)a.Win * 16, hw16, hw16 * a.in_chunks, hw16 * a.in_chunks * a.Nimg};
     const cuuint32_t box[5] = {(cuuint32_t)C::HALO_W * 8, (cuuint32_t)C::HALO_H, (cuuint32_t)CPG, 1, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -1231,6 +1232,7 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     }
     p.acc_gain = (gain_env && atoi(gain_env) == 0) ? 1.0f : 1.0f + 1.606e-8f * (float)acc_steps;
     p.out_s2d = a.out_s2d;
+    p.store_chunks = a.store_chunks;
     p.d2s_cch = a.d2s_cch;
     p.d2s_ph0 = a.d2s_ph0;
     p.denorm = a.denorm;

@@ -51,6 +51,7 @@ struct ConvTcParams {
     const int64_t* symbols;
     int64_t* out_freqs;
     double* bits_sum;
+    int store_chunks;           // OUTMODE 0: chunks >= store_chunks are not stored (0: store all)
     int out_s2d;                // OUTMODE 0: write the output in space-to-depth form [plane][N][4*NOUT/8][H/2][W/2][8]
     // OUTMODE 0 depth-to-space (transposed convs): column block = (phase, chunk); output [plane][N][d2s_cch][2H][2W][8]
     int d2s_cch, d2s_ph0;
@@ -64,6 +65,8 @@ struct ConvTcParams {
 struct ConvTcArgs {
     const __half* in;           // [planes][Nimg][in_chunks][Hin][Win][8]
     int Nimg, in_chunks, Hin, Win;
+    int in_chunks_valid;        // chunks that hold data (0 = in_chunks): the rest of a group's box is TMA zero fill, never read
+    int store_chunks;           // OUTMODE 0: output chunks that are stored (0 = all NOUT / 8): all-zero padding chunks are skipped
     const __half* weights;
     const __half* weights_pair;   // pair-packed copy (cta_group::2 path) or nullptr
     const __half* weights_cat;    // B-concatenated copy (conv_cat_kernel) or nullptr

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) pc_conv0_kernel(Src src, int D, int H, in
         const size_t plane = (size_t)(total / ((int64_t)H0 * W0)) * 4 * cs;
         const size_t base = (((size_t)(n * D0 + d) * 4) * H0 + y) * W0 * 8 + (size_t)x * 8;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < (KC + 7) / 8; ++c) {          // the padding chunk (channels 24..31) is never read: not written
             float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (c * 8 < KC) {
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -410,7 +410,9 @@ int run_pc_tc(const PcWeights& w, const PcInput& in, int head, float* out_f, int
         memset(&c, 0, sizeof(c));
         c.in = a[l - 1];
         c.Nimg = N * Dl[l - 1];
-        c.in_chunks = 4;
+        c.in_chunks = 4;                        // pitch of the planes; only 3 chunks (24 channels) are ever written or read:
+        c.in_chunks_valid = 3;                  // the 4th chunk of a group's box is TMA zero fill
+        c.store_chunks = 3;
         c.Hin = Hl[l - 1];
         c.Win = Wl[l - 1];
         c.weights = w.wt[l - 1];
