@@ -83,8 +83,8 @@ __constant__ float c_img_mean[3] = {121.853699f, 113.588608f, 100.637154f};
 __constant__ float c_img_std[3] = {68.8939514f, 66.7393417f, 69.3702698f};   // float32 sqrt(var + 1e-10)
 
 struct __align__(8) Barriers {
-    uint64_t a_full[MAX_ASLOTS], a_empty[MAX_ASLOTS], w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES], acc_full[2], acc_empty[2];
-    uint32_t tmem_base;
+    uint64_t a_full[MAX_ASLOTS], a_empty[MAX_ASLOTS], w_full[MAX_WSTAGES], w_empty[MAX_WSTAGES], acc_full[4], acc_empty[4];
+    uint32_t tmem_base;      // (4 accumulator barriers: the context model's depth walk keeps a ring of 4 tiles, everything else 2)
 };
 
 __device__ __forceinline__ float4 ld16(const void* p) { return *reinterpret_cast<const float4*>(p); }
@@ -158,6 +158,21 @@ __device__ __forceinline__ void add_h8_pair(const float4& qh, const float4& ql, 
     }
 }
 
+// depth walk of the context model (ConvTcParams::walk): work item w = (image, tile, depth segment); the segment produces
+// output slices [da, db) from input slices da .. db
+struct WalkItem {
+    int img, r, da, db;
+};
+__device__ __forceinline__ WalkItem walk_item(int w, int tiles, const ConvTcParams& p) {
+    const int seg = w % p.walk_nseg, col = w / p.walk_nseg;
+    WalkItem it;
+    it.r = col % tiles;
+    it.img = col / tiles;
+    it.da = seg * p.walk;
+    it.db = min(p.img_div, it.da + p.walk);
+    return it;
+}
+
 // OUTMODE 0: fp16 hi/lo planes [plane][N][NOUT/8][H][W][8]; 1: float32 NHWC [N][H][W][cout];
 // 2: context-model head (ReLU logits -> bit cost / coder frequencies / logits), code/probclass.py:100-104,443-444
 // WRES: all weight stages of the layer stay resident in shared memory (loaded once per CTA; context model)
@@ -196,8 +211,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     const int tiles_x = (p.W + TW * T - 1) / (TW * T), tiles_y = (p.H + TH - 1) / TH;
     const int n_super = p.N * tiles_y * tiles_x;
     int n_work = PAIR ? (n_super + 1) / 2 : n_super;              // pair mode: one work item = two super tiles
-    constexpr uint32_t kTmemCols = (2 * T * C::NCOL <= 32) ? 32 : (2 * T * C::NCOL <= 64) ? 64 :
-                                   (2 * T * C::NCOL <= 128) ? 128 : (2 * T * C::NCOL <= 256) ? 256 : 512;
+    const int n_walk = (CAT && T == 1 && p.walk) ? (p.N / p.img_div) * tiles_y * tiles_x * p.walk_nseg : 0;
+    // (context model: room for the depth walk's ring of 4 accumulators of 2 NOUT columns; two CTAs per SM still fit 512)
+    constexpr uint32_t kAccCols = (WRES && T == 1 && 8 * NOUT > 2 * T * C::NCOL) ? 8 * NOUT : 2 * T * C::NCOL;
+    constexpr uint32_t kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < (int)ASLOTS; ++i) {
@@ -207,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
             mbar_init(smem_u32(&bars->a_full[i]), 1);
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
             mbar_init(smem_u32(&bars->acc_empty[i]), (PAIR ? 2 : 1) * 32 * epi_warps(NOUT, OUTMODE));
         }
@@ -242,6 +259,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         // ===================== activation producer =====================
         if (lane == 0) {
             uint32_t gi = 0;     // running group counter -> A slot / phase
+            if constexpr (CAT && T == 1) {
+                if (p.walk) {       // depth walk: one load per input slice of the segment
+                    for (int wi = cta_id; wi < n_walk; wi += cta_stride) {
+                        const WalkItem w = walk_item(wi, tiles_y * tiles_x, p);
+                        const int y0 = (w.r / tiles_x) * TH, x0 = (w.r % tiles_x) * TW;
+                        for (int j = w.da; j <= w.db; ++j, ++gi) {
+                            const uint32_t slot = gi % ASLOTS, ph = (gi / ASLOTS) & 1;
+                            mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
+                            const int img = w.img * (p.img_div + p.img_div_mul) + j + p.img_base;
+                            const uint32_t full = smem_u32(&bars->a_full[slot]);
+                            mbar_expect_tx(full, NPL * C::A_PLANE_BYTES);
+                            for (int pl = 0; pl < NPL; ++pl)
+                                tma_load_5d(smem_u32(a_buf + (slot * NPL + pl) * C::A_PLANE_BYTES), &in_map, full,
+                                            (x0 + p.halo0) * 8, y0 + p.halo0, 0, img, pl);
+                        }
+                    }
+                    n_work = 0;
+                }
+            }
             for (int wi = cta_id; wi < n_work; wi += cta_stride) {
                 const int st = PAIR ? 2 * wi + (int)rank : wi;      // past-the-end super tiles load zeros (TMA OOB)
                 const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
@@ -273,6 +309,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                 // every stage of the layer fits: one load, one barrier (w_full[0]), never refilled
                 const uint32_t full = smem_u32(&bars->w_full[0]);
                 mbar_expect_tx(full, gt.nstages * NPL * C::W_PLANE_BYTES);
+                bool walk_layout = false;
+                if constexpr (CAT && T == 1) walk_layout = p.walk != 0;
+                if (walk_layout) {
+                    // depth walk: taps 0..4 are stored as ONE operand per tap for both filter depths,
+                    //   [4 chunks][W1 lo | W1 hi | W0 hi | W0 lo rows][8 cin]       (W0 = filter depth 0 = global stage t,
+                    //                                                                W1 = filter depth 1 = global stage 9 + t)
+                    // so that a_hi * (all 4 NOUT rows) and a_lo * (the middle 2 NOUT rows) are one MMA each; taps 5..8 exist at
+                    // depth 0 only and keep the [4 chunks][hi | lo][8] stage.  Built from the global stages by bulk copies.
+                    constexpr uint32_t kStage1 = NPL * C::W_PLANE_BYTES, kRows = NOUT * 16;      // bytes: one stage, NOUT rows of a chunk
+                    for (int t = 0; t < 5; ++t)
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t dst = smem_u32(w_buf + t * 2 * kStage1 + c * 4 * kRows);
+                            const uint8_t* w0 = p.weights + (size_t)t * kStage1 + c * 2 * kRows;
+                            const uint8_t* w1 = p.weights + (size_t)(9 + t) * kStage1 + c * 2 * kRows;
+                            bulk_load(dst, w1 + kRows, kRows, full);
+                            bulk_load(dst + kRows, w1, kRows, full);
+                            bulk_load(dst + 2 * kRows, w0, 2 * kRows, full);
+                        }
+                    for (int t = 5; t < 9; ++t)
+                        bulk_load(smem_u32(w_buf + 10 * kStage1 + (t - 5) * kStage1), p.weights + (size_t)t * kStage1, kStage1, full);
+                } else
                 for (int s = 0; s < gt.nstages; ++s)
                     bulk_load(smem_u32(w_buf + s * NPL * C::W_PLANE_BYTES), p.weights + (size_t)s * 2 * C::W_PLANE_BYTES,
                               NPL * C::W_PLANE_BYTES, full);
@@ -327,7 +384,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                 // out at compile time.  The table-driven loop below cost ~500 cycles PER TAP in this instantiation (tap table in
                 // vector registers: LDC / IMAD / a dozen R2UR per tap; IC_TC_DBG=2: the issuer never waited, it was busy
                 // 7.6 k cycles per tile for ~1 k tensor cycles of narrow MMAs): profiles/r2z_issuer_pc.txt.
-                if (p.pc_static) {
+                if (p.walk) {
+                    // ---- depth walk.  Step j of a segment holds input slice j: it FINISHES output slice j - 1 (filter depth 1,
+                    // taps 0..4) and STARTS output slice j (filter depth 0, taps 5..8 first, then 0..4).  Accumulators live in a
+                    // ring of 4 tiles of [X | Y] = 2 NOUT columns; an output is X + Y (added in the epilogue) with
+                    //     start   X += a_hi W0hi + a_lo W0hi     Y += a_hi W0lo
+                    //     finish  X += a_hi W1lo                 Y += a_hi W1hi + a_lo W1hi
+                    // so when the finishing tile sits right below the starting one, taps 0..4 are ONE a_hi MMA of N = 4 NOUT over
+                    // [X_f | Y_f | X_s | Y_s] with B rows [W1lo | W1hi | W0hi | W0lo] and ONE a_lo MMA of N = 2 NOUT over the middle
+                    // [Y_f | X_s] with rows [W1hi | W0hi]: 14 A fetches per plane and slice instead of 22.  Where the ring wraps
+                    // (and at the ends of a segment) the two halves are issued separately on the same operands, in the same
+                    // order per column -- every output sees the same sequence of accumulations whatever its ring position.
+                    constexpr uint64_t kS1 = (uint64_t)(NPL * kWPlane);                  // single stage, 16-byte units
+                    constexpr uint32_t IDESC_N4 = (C::IDESC & ~(0x3Fu << 17)) | ((uint32_t)((4 * NOUT) >> 3) << 17);
+                    const uint64_t w2_desc0 = make_desc(smem_u32(w_buf), 4 * NOUT * 16, 128);                          // taps 0..4
+                    const uint64_t w1_desc0 = make_desc(smem_u32(w_buf) + 10 * NPL * W_PLANE, 2 * NOUT * 16, 128);     // taps 5..8
+                    auto issue_taps = [&](auto nt_c, auto tap0_c, auto cat2_c, uint64_t a_g, uint64_t w_g, uint32_t d_hi, uint32_t idesc_hi,
+                                          uint32_t d_lo, uint64_t w_lo_off, uint32_t idesc_lo, bool first) {
+                        constexpr int NT = decltype(nt_c)::value, TAP0 = decltype(tap0_c)::value;
+                        constexpr bool CAT2 = decltype(cat2_c)::value;
+                        constexpr uint64_t kStage = CAT2 ? 2 * kS1 : kS1;
+                        constexpr uint64_t kWLboF = (uint64_t)(((CAT2 ? 4 : 2) * NOUT * 16) >> 4), kWKs2 = 2 * kWLboF;
+                        constexpr uint64_t kALboF = (uint64_t)(kALbo >> 4);
+#pragma unroll
+                        for (int ti = 0; ti < NT; ++ti) {
+                            const int tap = TAP0 + ti;
+                            const uint64_t a_t = a_g + (uint64_t)((tap / 3) * C::HALO_W + (tap % 3));
+                            const uint64_t w_t = w_g + (uint64_t)ti * kStage;
+                            if (p.pair_c2 && (ti & 1)) {          // chunk 2 of taps ti-1 and ti as one k-step (see the generic loop)
+                                const int tp = tap - 1;
+                                const uint64_t a_prev = a_g + (uint64_t)((tp / 3) * C::HALO_W + (tp % 3));
+                                const uint64_t a_pr = a_prev + kAKs - (kALboF << 16) + ((a_t - a_prev) << 16);
+                                const uint64_t w_pr = (w_t - kStage) + kWKs2 - (kWLboF << 16) + (kStage << 16);
+                                umma_f16(d_hi, a_pr, w_pr, idesc_hi, 1u);
+                                umma_f16(d_lo, a_pr + kAPlane, w_pr + w_lo_off, idesc_lo, 1u);
+                            }
+                            umma_f16(d_hi, a_t, w_t, idesc_hi, (first && ti == 0) ? 0u : 1u);
+                            umma_f16(d_lo, a_t + kAPlane, w_t + w_lo_off, idesc_lo, 1u);
+                            if (!p.pair_c2 || ((ti & 1) == 0 && ti == NT - 1)) {
+                                umma_f16(d_hi, a_t + kAKs, w_t + kWKs2, idesc_hi, 1u);
+                                umma_f16(d_lo, a_t + kAKs + kAPlane, w_t + kWKs2 + w_lo_off, idesc_lo, 1u);
+                            }
+                        }
+                    };
+                    const std::integral_constant<int, 4> c4{};
+                    const std::integral_constant<int, 5> c5{};
+                    const std::integral_constant<int, 0> c0{};
+                    const std::true_type cat2{};
+                    const std::false_type cat1{};
+                    uint32_t nacc = 0;          // accumulators started so far: ring position = nacc & 3, use count = nacc >> 2
+                    for (int wi = cta_id; wi < n_walk; wi += cta_stride) {
+                        const WalkItem w = walk_item(wi, tiles_y * tiles_x, p);
+                        for (int j = w.da; j <= w.db; ++j, ++gi) {
+                            const bool start = j < w.db, finish = j > w.da;
+                            const uint32_t ss = nacc & 3, sf = (nacc - 1) & 3;
+                            if (start) {
+                                if (p.dbg) dbg_c = clock64();
+                                mbar_wait(smem_u32(&bars->acc_empty[ss]), ((nacc >> 2) & 1) ^ 1);
+                                if (p.dbg) dbg_t[0] += clock64() - dbg_c;
+                            }
+                            const uint32_t aslot = gi % ASLOTS;
+                            if (p.dbg) dbg_c = clock64();
+                            mbar_wait(smem_u32(&bars->a_full[aslot]), (gi / ASLOTS) & 1);
+                            if (p.dbg) dbg_t[1] += clock64() - dbg_c;
+                            tc_fence_after();
+                            const uint64_t a_g = a_desc0 + (uint64_t)aslot * (NPL * kAPlane);
+                            const uint32_t d_s = tmem_base + ss * (2 * NOUT), d_f = tmem_base + sf * (2 * NOUT);
+                            if (elect_one()) {
+                                if (start) issue_taps(c4, c5, cat1, a_g, w1_desc0, d_s, IDESC_CAT, d_s, 0ull, IDESC, true);
+                                if (start && finish && ss != 0) {
+                                    issue_taps(c5, c0, cat2, a_g, w2_desc0, d_f, IDESC_N4, d_f + NOUT, (uint64_t)NOUT, IDESC_CAT, false);
+                                } else {
+                                    if (start)
+                                        issue_taps(c5, c0, cat2, a_g, w2_desc0 + (uint64_t)(2 * NOUT), d_s, IDESC_CAT, d_s, 0ull, IDESC, false);
+                                    if (finish)
+                                        issue_taps(c5, c0, cat2, a_g, w2_desc0, d_f, IDESC_CAT, d_f + NOUT, (uint64_t)NOUT, IDESC, false);
+                                }
+                                umma_commit(smem_u32(&bars->a_empty[aslot]));
+                                if (finish) umma_commit(smem_u32(&bars->acc_full[sf]));
+                            }
+                            __syncwarp();
+                            if (start) ++nacc;
+                        }
+                    }
+                    n_work = 0;       // the loops below have nothing left to do
+                } else if (p.pc_static) {
                     auto issue_group = [&](auto nt_c, auto tap0_c, uint64_t a_g, uint64_t w_g, uint32_t d_tmem, bool first_group) {
                         constexpr int NT = decltype(nt_c)::value, TAP0 = decltype(tap0_c)::value;
                         constexpr uint64_t kStage = (uint64_t)(NPL * kWPlane);
@@ -497,19 +638,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         constexpr int NCC = NOUT / 16 / (epi_warps(NOUT, OUTMODE) / 4);      // 16-column steps per warp
         const int cc0 = ((warp - 3) >> 2) * NCC;      // first step of this warp (8 epilogue warps: second half of the channels)
         const size_t plane = (size_t)p.N * NCH * p.H * p.W * 8;     // elements per hi/lo plane
-        uint32_t it = 0;
-        for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
-            const uint32_t set = it & 1;
-            const int st = PAIR ? 2 * wi + (int)rank : wi;
-            const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
+        // one accumulator set (T tiles from TMEM column tcol) -> output pixels of super tile r of image n
+        // (walk: the depth walk's [X | Y] accumulators, output = (X + Y) gain; otherwise [main | cross] = main gain + cross)
+        auto drain = [&](const int n, const int r, const uint32_t tcol, const bool walk) {
             const int y = (r / tiles_x) * TH + ty;
-            mbar_wait(smem_u32(&bars->acc_full[set]), (it >> 1) & 1);
-            tc_fence_after();
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int x = (r % tiles_x) * TW * T + t * TW + tx;
                 const bool inside = y < p.H && x < p.W && n < p.N;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (set * T + t) * C::NCOL;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tcol + t * C::NCOL;
                 if (OUTMODE == 0) {
                     // chunk-0 offset of this pixel; optionally written in space-to-depth form for the next stride-2 conv
                     size_t pix_off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;
@@ -540,7 +677,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                             tmem_ld_wait();
 #pragma unroll
                             for (int e = 0; e < 16; ++e)
-                                rr[e] = __float_as_uint(fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
+                                rr[e] = __float_as_uint(walk ? (__uint_as_float(rr[e]) + __uint_as_float(rx[e])) * p.acc_gain
+                                                             : fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
                         }
                         if (inside && has_res && cc + 1 < cc0 + NCC)
                             load_res<NPL>(nxt, p, roff + (size_t)(cc + 1) * 2 * rstride, rstride, p.res_plane,
@@ -599,7 +737,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                         tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 16; ++e)
-                            rr[e] = __float_as_uint(fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
+                            rr[e] = __float_as_uint(walk ? (__uint_as_float(rr[e]) + __uint_as_float(rx[e])) * p.acc_gain
+                                                         : fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
                     }
                     tmem_ld_wait();
                     const int L = p.cout;
@@ -681,7 +820,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                             tmem_ld_wait();
 #pragma unroll
                             for (int e = 0; e < 16; ++e)
-                                rr[e] = __float_as_uint(fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
+                                rr[e] = __float_as_uint(walk ? (__uint_as_float(rr[e]) + __uint_as_float(rx[e])) * p.acc_gain
+                                                             : fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
                         }
                         tmem_ld_wait();
                         if (inside) {
@@ -697,6 +837,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                     }
                 }
             }
+        };
+        if constexpr (CAT && T == 1) {
+            if (p.walk) {       // depth walk: outputs arrive in the order the issuer starts them, ring of 4 accumulators
+                uint32_t nacc = 0;
+                for (int wi = cta_id; wi < n_walk; wi += cta_stride) {
+                    const WalkItem w = walk_item(wi, tiles_y * tiles_x, p);
+                    for (int d = w.da; d < w.db; ++d, ++nacc) {
+                        const uint32_t set = nacc & 3;
+                        mbar_wait(smem_u32(&bars->acc_full[set]), (nacc >> 2) & 1);
+                        tc_fence_after();
+                        drain(w.img * p.img_div + d, w.r, set * (2 * NOUT), true);
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(&bars->acc_empty[set]));
+                    }
+                }
+                n_work = 0;
+            }
+        }
+        uint32_t it = 0;
+        for (int wi = cta_id; wi < n_work; wi += cta_stride, ++it) {
+            const uint32_t set = it & 1;
+            const int st = PAIR ? 2 * wi + (int)rank : wi;
+            const int n = st / (tiles_y * tiles_x), r = st - n * tiles_y * tiles_x;
+            mbar_wait(smem_u32(&bars->acc_full[set]), (it >> 1) & 1);
+            tc_fence_after();
+            drain(n, r, set * T * C::NCOL, false);
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&bars->acc_empty[set]), 0));    // the leader waits for both epilogues
             else mbar_arrive(smem_u32(&bars->acc_empty[set]));
@@ -1211,6 +1377,8 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
             for (int i = 0; i < 5; ++i) ok = ok && g.taps[1][i] == g.taps[1][0] + i;
             if (ok) p.pc_static = g.taps[1][0] == 0 ? 1 : 2;
         }
+        p.walk = 0;
+        p.walk_nseg = 1;
     }
     p.res_H = a.res_H ? a.res_H : a.H;
     p.res_W = a.res_W ? a.res_W : a.W;
@@ -1287,6 +1455,21 @@ int launch_t(const ConvTcArgs& a, cudaStream_t s) {
     const int tmem_cols = 2 * T * C::NCOL;
     const int ctas = (2 * (smem + 1024) <= 232448 && tmem_cols <= 256) ? 2 * sms : sms;
     int grid = n_super < ctas ? n_super : ctas;
+    if (WRES && T == 1 && OUTMODE != 1 && p.pc_static == 1 && a.img_div >= 1 && a.img_mul == 1 && a.img_div_mul == 1 && p.img_off_mul == 1 &&
+        a.img_base == 0 && a.N % a.img_div == 0 && a.groups->img_off[0] == 0 && a.groups->img_off[1] == 1) {
+        // depth walk (inference layers of the context model): (image, tile) columns, cut into depth segments only when there
+        // are too few columns to fill the machine (a segment of s outputs loads s + 1 input slices)
+        const char* we = getenv("IC_PC_WALK");
+        if (!(we && atoi(we) == 0)) {
+            const int dout = a.img_div, ncols = (a.N / dout) * tiles_y * tiles_x;
+            int nseg = (2 * ctas + ncols - 1) / ncols;
+            nseg = nseg < 1 ? 1 : (nseg > dout ? dout : nseg);
+            p.walk = (dout + nseg - 1) / nseg;
+            p.walk_nseg = (dout + p.walk - 1) / p.walk;
+            const int n_items = ncols * p.walk_nseg;
+            grid = n_items < ctas ? n_items : ctas;
+        }
+    }
     ProfScope ps(a.prof_class, s);
     if (PAIR) {
         const int n_work = (n_super + 1) / 2;

@@ -43,6 +43,11 @@ struct ConvTcParams {
     int pair_c2;
     int aslots;                 // activation-tile slots in shared memory (2 ... 6)
     int pc_static;              // context model: compile-time tap schedule (1: group 1 = taps 0..4, 2: taps 4..8), 0: table-driven
+    // context model, depth walk (inference layers): a CTA follows one (image, tile) along the depth axis and fetches every
+    // input slice ONCE -- its A tile feeds the 5 taps of filter depth 1 (finishing output slice j - 1) and the 9 taps of
+    // filter depth 0 (starting output slice j) in the same MMAs, N = 4 NOUT over two adjacent accumulators of a 4-deep
+    // TMEM ring.  walk = outputs per depth segment (0: off), walk_nseg = segments per column.
+    int walk, walk_nseg;
     // geometry of res1 (context model: a crop of a larger tensor); res2 always has the output geometry
     int res_H, res_W, res_dy, res_dx, res_div_mul, res_img_off;
     size_t res_plane;

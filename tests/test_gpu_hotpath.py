@@ -144,6 +144,37 @@ def test_probclass_batched_freqs_match_reference_loop_and_are_causal(gpu_models)
     assert not np.array_equal(f2[p + 1:], f.reshape(-1, 6)[p + 1:])
 
 
+@pytest.mark.parametrize('shape', [(1, 4, 9, 9), (1, 32, 8, 8), (2, 9, 21, 37), (5, 32, 40, 24)])
+def test_context_model_depth_walk_against_two_group_schedule(shape, gpu_models, monkeypatch):
+    """csrc/conv_tc.cu, ConvTcParams::walk (the default of the inference layers): every input slice is fetched once and
+    feeds the output slices on both sides of it, accumulators in a ring of four [X | Y] tiles.  Against the two-group
+    schedule (IC_PC_WALK=0: each output slice loads its two input slices) on the same weights and symbols: same sums in
+    another order, so logits / bit costs agree to float32 rounding, tables to a few hundred counts of 1e9; every table is
+    positive and the walk is deterministic.  Shapes: fewer columns than CTAs (depth segments of 1..3 outputs), a ring
+    that wraps several times, ragged tiles, and a batch with more columns than twice the CTA count (whole columns)."""
+    ae, pc, W = gpu_models('cvpr/low')
+    N, C, H, Wd = shape
+    rng = np.random.RandomState(7)
+    sym = _cuda(rng.randint(0, 6, size=(N, C, H, Wd)).astype(np.int64))
+    centers = _cuda(W['autoencoder/encoder/centers'])
+    q = centers[sym]
+    f1, b1 = pc.freqs(sym, centers)
+    bc1 = pc.bitcost(q, sym, False, pad_value=float(centers[0]))
+    f1b, _ = pc.freqs(sym, centers)
+    assert torch.equal(f1, f1b)
+    monkeypatch.setenv('IC_PC_WALK', '0')
+    f0, b0 = pc.freqs(sym, centers)
+    bc0 = pc.bitcost(q, sym, False, pad_value=float(centers[0]))
+    monkeypatch.delenv('IC_PC_WALK')
+    assert int(f1.min()) >= 1
+    df = int((f1 - f0).abs().max())
+    db = float((bc1 - bc0).abs().max())
+    print('  depth walk %s: max table difference %d / 1e9, max bit-cost difference %.2e' % (shape, df, db))
+    assert df <= 2000, df
+    assert db <= 2e-5 * max(1.0, float(bc0.abs().max())), db
+    assert torch.allclose(b1, b0, rtol=1e-6, atol=1e-3)
+
+
 def test_real_bpp_round_trip(gpu_models):
     """--real_bpp (val.py:161-175): coded bits ~ theoretical bits ~ loss bpp; stream decodes."""
     from imgcomp_cvpr_b200 import bit_counter, bpp_helpers, probclass

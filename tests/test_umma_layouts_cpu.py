@@ -186,3 +186,129 @@ def test_context_model_third_chunks_of_two_taps_share_one_k_step():
         ty, tx = m >> 3, m & 7
         ref = sum(x[fd, ty + fy, tx + fx].astype(np.float64) @ w[fd, fy, fx] for taps in groups for (fd, fy, fx) in taps)
         assert np.array_equal(acc[m], ref), m
+
+
+def _fast_operand(smem, start, lbo, sbo, rows):
+    """operand(..., major='K') vectorised (the walk test issues a few hundred MMAs)"""
+    h = smem.view(np.float16)
+    r = np.arange(rows)[:, None]
+    k = np.arange(16)[None, :]
+    a = start + (r // 8) * sbo + (k // 8) * lbo + (r % 8) * 16 + (k % 8) * 2
+    return h[a // 2]
+
+
+def test_context_model_depth_walk_schedule():
+    """conv_tc.cu, ConvTcParams::walk: a CTA follows one (image, tile) along the depth axis; input slice j FINISHES output
+    j - 1 (filter depth 1, taps 0..4) and STARTS output j (filter depth 0: taps 5..8, then 0..4) from ONE activation tile.
+    Accumulators: ring of 4 tiles [X | Y] of 2 NO TMEM columns, output = X + Y.  Taps 0..4 are stored
+    [4 chunks][W1lo | W1hi | W0hi | W0lo rows][8] (built from the global per-tap stages [4 chunks][hi | lo][8] by the same
+    copies as the kernel's weight producer), so a_hi x all 4 NO rows lands on [X_f | Y_f | X_s | Y_s] and a_lo x the middle
+    2 NO rows on [Y_f | X_s].  The emulation issues exactly the kernel's descriptors (tap shifts, paired third chunks, row
+    offsets, separate halves where the ring wraps and at segment ends) and must reproduce
+    a_hi w_hi + a_hi w_lo + a_lo w_hi of the VALID masked 3-D conv for every output slice."""
+    rng = np.random.RandomState(5)
+    NO, K, Din = 32, 24, 8                              # 7 output slices: the ring of 4 wraps once
+    Hh, Ww = 18, 10
+    halo_w, halo_pix = Ww, Hh * Ww
+    a_plane = 4 * halo_pix * 16
+    xh = _ints(rng, (Din, Hh, Ww, 32)); xl = _ints(rng, (Din, Hh, Ww, 32), -2, 3)
+    xh[..., K:] = 0; xl[..., K:] = 0
+    wh = _ints(rng, (2, 3, 3, 32, NO), -2, 3); wl = _ints(rng, (2, 3, 3, 32, NO), -1, 2)
+    wh[:, :, :, K:, :] = 0; wl[:, :, :, K:, :] = 0
+    taps_fd = [[(fy, fx) for fy in range(3) for fx in range(3)], [(fy, fx) for fy in range(3) for fx in range(3)][:5]]
+    # global stages as pack_weights_pc writes them: 9 stages of filter depth 0, 5 of depth 1; [4 chunks][hi rows | lo rows][8]
+    S1 = 4 * 2 * NO * 16
+    gl = np.zeros((14, 4, 2 * NO, 8), np.float16)
+    for fd in range(2):
+        for ti, (fy, fx) in enumerate(taps_fd[fd]):
+            for ch in range(4):
+                gl[fd * 9 + ti, ch, :NO] = wh[fd, fy, fx, ch * 8:(ch + 1) * 8, :].T
+                gl[fd * 9 + ti, ch, NO:] = wl[fd, fy, fx, ch * 8:(ch + 1) * 8, :].T
+    g8 = gl.view(np.uint8).reshape(14, S1)
+    # the weight producer's bulk copies
+    w_smem = np.zeros(14 * S1, np.uint8)
+    rows = NO * 16
+    for t in range(5):
+        for c in range(4):
+            dst = t * 2 * S1 + c * 4 * rows
+            w0, w1 = g8[t, c * 2 * rows:], g8[9 + t, c * 2 * rows:]
+            w_smem[dst:dst + rows] = w1[rows:2 * rows]
+            w_smem[dst + rows:dst + 2 * rows] = w1[:rows]
+            w_smem[dst + 2 * rows:dst + 4 * rows] = w0[:2 * rows]
+    for t in range(5, 9):
+        w_smem[10 * S1 + (t - 5) * S1:10 * S1 + (t - 4) * S1] = g8[t]
+    tmem = np.zeros((128, 8 * NO), np.float64)
+    nmma = [0]
+
+    def umma(d, n, a_start, a_lbo, b_start, b_lbo, acc, a_smem):
+        a = _fast_operand(a_smem, a_start, a_lbo, halo_w * 16, 128).astype(np.float64)
+        b = _fast_operand(w_smem, b_start, b_lbo, 128, n).astype(np.float64)
+        assert d + n <= tmem.shape[1]
+        tmem[:, d:d + n] = (tmem[:, d:d + n] if acc else 0) + a @ b.T
+        nmma[0] += 1
+
+    def issue_taps(nt, tap0, cat2, a_smem, w_g, d_hi, n_hi, d_lo, w_lo_off, n_lo, first):
+        stage = 2 * S1 if cat2 else S1
+        wlbo = (4 if cat2 else 2) * NO * 16
+        wks, aks, albo = 2 * wlbo, 2 * halo_pix * 16, halo_pix * 16
+        for ti in range(nt):
+            tap = tap0 + ti
+            a_t = ((tap // 3) * halo_w + tap % 3) * 16
+            w_t = w_g + ti * stage
+            if ti & 1:
+                a_prev = (((tap - 1) // 3) * halo_w + (tap - 1) % 3) * 16
+                umma(d_hi, n_hi, a_prev + aks, a_t - a_prev, w_t - stage + wks, stage, True, a_smem)
+                umma(d_lo, n_lo, a_prev + aks + a_plane, a_t - a_prev, w_t - stage + wks + w_lo_off * 16, stage, True, a_smem)
+            umma(d_hi, n_hi, a_t, albo, w_t, wlbo, not (first and ti == 0), a_smem)
+            umma(d_lo, n_lo, a_t + a_plane, albo, w_t + w_lo_off * 16, wlbo, True, a_smem)
+            if (ti & 1) == 0 and ti == nt - 1:
+                umma(d_hi, n_hi, a_t + aks, albo, w_t + wks, wlbo, True, a_smem)
+                umma(d_lo, n_lo, a_t + aks + a_plane, albo, w_t + wks + w_lo_off * 16, wlbo, True, a_smem)
+
+    def reference(d):
+        out = np.zeros((128, NO), np.float64)
+        for m in range(128):
+            ty, tx = m >> 3, m & 7
+            for fd in range(2):
+                for (fy, fx) in taps_fd[fd]:
+                    ah, al = xh[d + fd, ty + fy, tx + fx].astype(np.float64), xl[d + fd, ty + fy, tx + fx].astype(np.float64)
+                    out[m] += ah @ wh[fd, fy, fx] + ah @ wl[fd, fy, fx] + al @ wh[fd, fy, fx]
+        return out
+
+    w2, w1 = 0, 10 * S1
+    results = {}
+    for seg_len in (7, 3):                               # one segment per column; three segments (3 + 3 + 1 outputs)
+        tmem[:] = np.nan                                 # a start must overwrite, never accumulate onto stale columns
+        nacc, done = 0, []
+        for da in range(0, Din - 1, seg_len):
+            db = min(Din - 1, da + seg_len)
+            for j in range(da, db + 1):
+                start, finish = j < db, j > da
+                ss, sf = nacc & 3, (nacc - 1) & 3
+                tile = np.concatenate([tma_tile(to_planes(v[j:j + 1]), 0, 0, 4, 0, 0, Hh, Ww).reshape(-1) for v in (xh, xl)])
+                a_smem = tile.view(np.uint8)
+                d_s, d_f = ss * 2 * NO, sf * 2 * NO
+                if start:
+                    issue_taps(4, 5, False, a_smem, w1, d_s, 2 * NO, d_s, 0, NO, True)
+                if start and finish and ss != 0:
+                    issue_taps(5, 0, True, a_smem, w2, d_f, 4 * NO, d_f + NO, NO, 2 * NO, False)
+                else:
+                    if start:
+                        issue_taps(5, 0, True, a_smem, w2 + 2 * NO * 16, d_s, 2 * NO, d_s, 0, NO, False)
+                    if finish:
+                        issue_taps(5, 0, True, a_smem, w2, d_f, 2 * NO, d_f + NO, NO, NO, False)
+                if finish:
+                    done.append((j - 1, (tmem[:, d_f:d_f + NO] + tmem[:, d_f + NO:d_f + 2 * NO]).copy()))
+                if start:
+                    nacc += 1
+        assert [d for d, _ in done] == list(range(Din - 1))
+        for d, got in done:
+            assert np.array_equal(got, reference(d)), (seg_len, d)
+        results[seg_len] = nmma[0]
+        nmma[0] = 0
+    # k-steps (x 2 planes): start half 14, finish half 8, fused step 14, wrapped step 14 + 8 -- against 22 per output of the
+    # two-group schedule.  One segment of 7 outputs: start + 5 fused + 1 wrapped + finish; three segments: 3 starts, 3 finishes,
+    # 3 fused + 1 wrapped (the ring position carries over from segment to segment)
+    assert results[7] == 2 * (14 + 5 * 14 + 22 + 8), results
+    assert results[3] == 2 * (3 * 14 + 3 * 8 + 3 * 14 + 22), results
+    assert results[7] < 2 * 22 * 7
