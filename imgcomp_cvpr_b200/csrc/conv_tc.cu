@@ -120,7 +120,7 @@ struct ResRegs {
     float4 v[2][4];
 };
 
-template <int NPL>
+template <int NPL, bool RES2 = true>
 __device__ __forceinline__ void load_res(ResRegs& r, const ConvTcParams& p, size_t off1, size_t stride1, size_t plane1,
                                          size_t off2, size_t stride2, size_t plane2) {
 #pragma unroll
@@ -129,7 +129,7 @@ __device__ __forceinline__ void load_res(ResRegs& r, const ConvTcParams& p, size
             r.v[hc][0] = ldg16(p.res1 + off1 + hc * stride1);
             if (NPL == 2) r.v[hc][1] = ldg16(p.res1 + plane1 + off1 + hc * stride1);
         }
-        if (p.res2) {
+        if (RES2 && p.res2) {
             r.v[hc][2] = ldg16(p.res2 + off2 + hc * stride2);
             if (NPL == 2) r.v[hc][3] = ldg16(p.res2 + plane2 + off2 + hc * stride2);
         }
@@ -640,6 +640,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         const size_t plane = (size_t)p.N * NCH * p.H * p.W * 8;     // elements per hi/lo plane
         // one accumulator set (T tiles from TMEM column tcol) -> output pixels of super tile r of image n
         // (walk: the depth walk's [X | Y] accumulators, output = (X + Y) gain; otherwise [main | cross] = main gain + cross)
+        // (resident-weight kernels have no second residual operand: its registers are compiled out)
+        constexpr bool RES2 = !WRES;
         auto drain = [&](const int n, const int r, const uint32_t tcol, const bool walk) {
             const int y = (r / tiles_x) * TH + ty;
 #pragma unroll 1
@@ -656,7 +658,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                         chunk_stride = (size_t)(p.H >> 1) * (p.W >> 1) * 8;
                         pix_off = (((size_t)n * 4 * NCH + ph * NCH) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) * 8 + (size_t)(x >> 1) * 8;
                     }
-                    const bool has_res = (p.res1 != nullptr) || (p.res2 != nullptr);
+                    const bool has_res = (p.res1 != nullptr) || (RES2 && p.res2 != nullptr);
                     // res1 may live in a larger tensor (context model: conv0 output cropped [2:, 2:-2, 2:-2])
                     const int rimg = n + (p.img_div > 0 ? (n / p.img_div) * p.res_div_mul : 0) + p.res_img_off;
                     const size_t rstride = (size_t)p.res_H * p.res_W * 8;
@@ -665,8 +667,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                     const size_t r2off = ((size_t)n * NCH * p.H + y) * p.W * 8 + (size_t)x * 8;     // res2: output geometry
                     const size_t r2stride = (size_t)p.H * p.W * 8;
                     if (inside && has_res)
-                        load_res<NPL>(cur, p, roff + (size_t)cc0 * 2 * rstride, rstride, p.res_plane, r2off + (size_t)cc0 * 2 * r2stride,
-                                      r2stride, plane);
+                        load_res<NPL, RES2>(cur, p, roff + (size_t)cc0 * 2 * rstride, rstride, p.res_plane, r2off + (size_t)cc0 * 2 * r2stride,
+                                            r2stride, plane);
 #pragma unroll 1
                     for (int cc = cc0; cc < cc0 + NCC; ++cc) {
                         uint32_t rr[16];
@@ -681,8 +683,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                                                              : fmaf(__uint_as_float(rr[e]), p.acc_gain, __uint_as_float(rx[e])));
                         }
                         if (inside && has_res && cc + 1 < cc0 + NCC)
-                            load_res<NPL>(nxt, p, roff + (size_t)(cc + 1) * 2 * rstride, rstride, p.res_plane,
-                                          r2off + (size_t)(cc + 1) * 2 * r2stride, r2stride, plane);
+                            load_res<NPL, RES2>(nxt, p, roff + (size_t)(cc + 1) * 2 * rstride, rstride, p.res_plane,
+                                                r2off + (size_t)(cc + 1) * 2 * r2stride, r2stride, plane);
                         tmem_ld_wait();
                         if (inside) {
 #pragma unroll
@@ -702,7 +704,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                                     if (NPL == 2) add_h8_pair(cur.v[hc][0], cur.v[hc][1], v);
                                     else add_h8(cur.v[hc][0], v);
                                 }
-                                if (p.res2) {
+                                if (RES2 && p.res2) {
                                     if (NPL == 2) add_h8_pair(cur.v[hc][2], cur.v[hc][3], v);
                                     else add_h8(cur.v[hc][2], v);
                                 }
@@ -840,16 +842,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         };
         if constexpr (CAT && T == 1) {
             if (p.walk) {       // depth walk: outputs arrive in the order the issuer starts them, ring of 4 accumulators
+                const int tiles = tiles_y * tiles_x;
                 uint32_t nacc = 0;
-                for (int wi = cta_id; wi < n_walk; wi += cta_stride) {
-                    const WalkItem w = walk_item(wi, tiles_y * tiles_x, p);
-                    for (int d = w.da; d < w.db; ++d, ++nacc) {
+                int wi = cta_id, d = 0;
+                bool more = wi < n_walk, ins = false;
+                WalkItem w;
+                // element offsets of this thread's pixel in the output / residual tensors (first chunk of this warp), advanced by
+                // one (n, depth) image per output: the divisions run once per work item, not once per accumulator
+                const size_t chunk_stride = (size_t)p.H * p.W * 8, rchunk = (size_t)p.res_H * p.res_W * 8;
+                const int wc0 = (OUTMODE == 0 && NCC == 1) ? 2 * cc0 : 0;
+                size_t ooff = 0, roff = 0;
+                auto enter = [&]() {        // first output of work item wi
+                    w = walk_item(wi, tiles, p);
+                    d = w.da;
+                    const int y = (w.r / tiles_x) * TH + ty, x = (w.r % tiles_x) * TW + tx;
+                    ins = y < p.H && x < p.W;
+                    ooff = ((size_t)(w.img * p.img_div + d) * NCH * p.H + y) * p.W * 8 + (size_t)x * 8 + (size_t)wc0 * chunk_stride;
+                    const int rimg = w.img * (p.img_div + p.res_div_mul) + d + p.res_img_off;
+                    roff = ((size_t)rimg * NCH * p.res_H + y + p.res_dy) * p.res_W * 8 + (size_t)(x + p.res_dx) * 8 + (size_t)wc0 * rchunk;
+                };
+                auto advance = [&]() {      // -> the output after the current one
+                    if (++d < w.db) {
+                        ooff += NCH * chunk_stride;
+                        roff += NCH * rchunk;
+                    } else {
+                        wi += cta_stride;
+                        more = wi < n_walk;
+                        if (more) enter();
+                    }
+                };
+                if (more) enter();
+                if constexpr (OUTMODE == 0 && NCC == 1) {
+                    // Plane-output layers: a lean drain.  ncu (profiles/r2u3_pc_walk_raw.csv): these kernels run at the issue rate
+                    // of their epilogue warps -- 4.7 k (layer 1) / 6.6 k (layer 2) warp instructions per accumulator through the
+                    // generic drain, 0.46 IPC per scheduler, time proportional to the instruction count -- not at the tensor pipe's.
+                    // Here: this warp's two channel chunks one at a time (8 + 8 TMEM columns live instead of 32), chunks past
+                    // store_chunks never read, incremental addresses, and the residual of the NEXT output requested into the
+                    // registers the current one has just consumed.  Same operations per value as the generic drain.
+                    const int nch = p.store_chunks ? max(0, min(2, p.store_chunks - 2 * cc0)) : 2;
+                    const bool has_res = p.res1 != nullptr;
+                    const float gain = p.acc_gain;
+                    float4 rh[2], rl[2];
+                    if (more && has_res && ins) {
+                        const __half* rp = p.res1 + roff;
+#pragma unroll
+                        for (int hc = 0; hc < 2; ++hc)
+                            if (hc < nch) {
+                                rh[hc] = ldg16(rp + hc * rchunk);
+                                rl[hc] = ldg16(rp + p.res_plane + hc * rchunk);
+                            }
+                    }
+                    while (more) {
+                        const bool inside = ins;
+                        __half* op = p.out + ooff;
+                        advance();
+                        const __half* rnext = (more && has_res && ins) ? p.res1 + roff : nullptr;
                         const uint32_t set = nacc & 3;
                         mbar_wait(smem_u32(&bars->acc_full[set]), (nacc >> 2) & 1);
                         tc_fence_after();
-                        drain(w.img * p.img_div + d, w.r, set * (2 * NOUT), true);
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * NOUT) + cc0 * 16;
+#pragma unroll
+                        for (int hc = 0; hc < 2; ++hc) {
+                            if (hc < nch) {
+                                uint32_t ax[8], ay[8];
+                                tmem_ld8(taddr + hc * 8, ax);
+                                tmem_ld8(taddr + NOUT + hc * 8, ay);
+                                tmem_ld_wait();
+                                if (inside) {
+                                    const int c0 = (2 * cc0 + hc) * 8;
+                                    const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c0), s1 = *reinterpret_cast<const float4*>(s_scale + c0 + 4);
+                                    const float4 h0 = *reinterpret_cast<const float4*>(s_shift + c0), h1 = *reinterpret_cast<const float4*>(s_shift + c0 + 4);
+                                    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                                    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                                    float v[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        float a = (__uint_as_float(ax[e]) + __uint_as_float(ay[e])) * gain;
+                                        a = fmaf(a, sc[e], sh[e]);
+                                        v[e] = p.relu ? fmaxf(a, 0.f) : a;
+                                    }
+                                    if (has_res) add_h8_pair(rh[hc], rl[hc], v);
+                                    __align__(16) __half2 hi[4];
+                                    __align__(16) __half2 lo[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        hi[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                                        const float2 hf = __half22float2(hi[e]);
+                                        lo[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                                    }
+                                    *reinterpret_cast<float4*>(op + hc * chunk_stride) = *reinterpret_cast<const float4*>(hi);
+                                    *reinterpret_cast<float4*>(op + plane + hc * chunk_stride) = *reinterpret_cast<const float4*>(lo);
+                                }
+                                if (rnext) {
+                                    rh[hc] = ldg16(rnext + hc * rchunk);
+                                    rl[hc] = ldg16(rnext + p.res_plane + hc * rchunk);
+                                }
+                            }
+                        }
                         tc_fence_before();
                         mbar_arrive(smem_u32(&bars->acc_empty[set]));
+                        ++nacc;
+                    }
+                } else {
+                    while (more) {
+                        const int n = w.img * p.img_div + d, r = w.r;
+                        advance();
+                        const uint32_t set = nacc & 3;
+                        mbar_wait(smem_u32(&bars->acc_full[set]), (nacc >> 2) & 1);
+                        tc_fence_after();
+                        drain(n, r, set * (2 * NOUT), true);
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(&bars->acc_empty[set]));
+                        ++nacc;
                     }
                 }
                 n_work = 0;

@@ -54,7 +54,11 @@ __device__ __forceinline__ void issue_pattern(uint32_t tmem, uint64_t ah, uint64
 }
 
 template <int P>
-__global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned long long* cycles) {
+// amode: layout of the A operand.  0: dense tile (core matrices 128-byte aligned, SBO = 128).  1 / 2: as conv_tc.cu reads it out
+// of a halo tile -- 8-pixel core matrices at the pitch of a 10- / 18-pixel halo row (SBO = 160 / 288 bytes) and a start address
+// that moves by the tap shift (dx 16 bytes + dy one halo row), i.e. core matrices that straddle 128-byte lines.  3: dense
+// pitch, start shifted by dx 16 bytes only.
+__global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned long long* cycles, int amode) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // [A hi x kBufs][A lo x kBufs][B (hi | lo interleaved per 16-byte row group: N up to 256) x kBufs]
     uint8_t* a_hi = smem;
@@ -80,15 +84,18 @@ __global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned
     if (threadIdx.x == 0) {
         // K-major no-swizzle: 8 rows x 16 B core matrices; LBO = stride between the two 16-byte K chunks, SBO = 128 B.
         // Descriptors of buffer s = base + s * constant: the issue loop is integer adds + MMAs, like conv_tc.cu's.
-        const uint32_t lbo_a = 128 * 16, lbo_b = 256 * 16;
-        const uint64_t ah0 = make_desc(smem_u32(a_hi), lbo_a, 128), al0 = make_desc(smem_u32(a_lo), lbo_a, 128);
+        const uint32_t sbo_a = amode == 1 ? 160 : (amode == 2 ? 288 : 128);
+        const uint32_t lbo_a = amode == 1 ? 18 * 160 : (amode == 2 ? 18 * 288 : 128 * 16), lbo_b = 256 * 16;
+        const uint64_t ah0 = make_desc(smem_u32(a_hi), lbo_a, sbo_a), al0 = make_desc(smem_u32(a_lo), lbo_a, sbo_a);
         const uint64_t bh0 = make_desc(smem_u32(b), lbo_b, 128), bl0 = make_desc(smem_u32(b) + 128 * 16, lbo_b, 128);
         const unsigned long long t0 = clock64();
         uint32_t ph = 0;
         for (int it = 0; it < iters; it += 32) {
 #pragma unroll
             for (int u = 0; u < 32; ++u) {
-                const uint64_t sa = (uint64_t)((u % kBufs) * (kTile >> 4)), sb = (uint64_t)((u % kBufs) * (2 * kTile >> 4));
+                const uint64_t sb = (uint64_t)((u % kBufs) * (2 * kTile >> 4));
+                const uint64_t sa = amode == 0 ? (uint64_t)((u % kBufs) * (kTile >> 4))
+                                               : (uint64_t)((u % kBufs) * (1024 >> 4) + (u % 3) + (amode == 3 ? 0 : ((u / 3) % 3) * (sbo_a >> 4)));
                 issue_pattern<P>(tmem, ah0 + sa, al0 + sa, bh0 + sb, bl0 + sb, (it | u) ? 1u : 0u);
             }
             umma_commit(smem_u32(&bar));          // bound the number of MMAs in flight like a stage hand-over does
@@ -182,13 +189,13 @@ mma_pattern_pair_kernel(int iters, unsigned long long* cycles) {
 }
 
 template <int P>
-void launch_pattern(int grid, size_t smem, int iters, unsigned long long* d_cycles) {
+void launch_pattern(int grid, size_t smem, int iters, unsigned long long* d_cycles, int amode = 0) {
     if (P >= 6) {
         cudaFuncSetAttribute(mma_pattern_pair_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         mma_pattern_pair_kernel<P><<<grid, 128, smem>>>(iters, d_cycles);
     } else {
         cudaFuncSetAttribute(mma_pattern_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mma_pattern_kernel<P><<<grid, 128, smem>>>(iters, d_cycles);
+        mma_pattern_kernel<P><<<grid, 128, smem>>>(iters, d_cycles, amode);
     }
 }
 
@@ -202,7 +209,12 @@ void launch_any(int p, int grid, size_t smem, int iters, unsigned long long* d) 
         case 5: launch_pattern<5>(grid, smem, iters, d); break;
         case 6: launch_pattern<6>(grid, smem, iters, d); break;
         case 7: launch_pattern<7>(grid, smem, iters, d); break;
-        default: launch_pattern<8>(grid, smem, iters, d); break;
+        case 8: launch_pattern<8>(grid, smem, iters, d); break;
+        case 9: launch_pattern<4>(grid, smem, iters, d, 1); break;
+        case 10: launch_pattern<5>(grid, smem, iters, d, 1); break;
+        case 11: launch_pattern<0>(grid, smem, iters, d, 2); break;
+        case 12: launch_pattern<4>(grid, smem, iters, d, 3); break;
+        default: launch_pattern<2>(grid, smem, iters, d, 2); break;
     }
 }
 
@@ -216,12 +228,15 @@ int main(int argc, char** argv) {
     unsigned long long* d_cycles;
     cudaMalloc(&d_cycles, sizeof(unsigned long long) * sms);
     // algorithmic MACs per k-step: one (pixels x cout x 16) product; patterns 3-5: cout = 24 of 32 (x2 slices for 5)
-    const double macs[9] = {128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 24 * 16, 128.0 * 24 * 16, 2 * 128.0 * 24 * 16,
-                            128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16};
-    const char* names[9] = {"exact 3 x N128 (today)", "exact N256 + N128 (B-concat)", "fast 1 x N128", "pc 3 x N32 (today)",
-                            "pc N64 + N32 (B-concat)", "pc N128 + N64 (2 slices + B-concat)",
-                            "pair exact 3 x M256 N128", "pair exact M256 N256 + N128 (B-concat)", "pair fast 1 x M256 N128"};
-    for (int p = 0; p < 9; ++p) {
+    const double macs[14] = {128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 24 * 16, 128.0 * 24 * 16, 2 * 128.0 * 24 * 16,
+                             128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 24 * 16, 2 * 128.0 * 24 * 16, 128.0 * 128 * 16,
+                             128.0 * 24 * 16, 128.0 * 128 * 16};
+    const char* names[14] = {"exact 3 x N128 (today)", "exact N256 + N128 (B-concat)", "fast 1 x N128", "pc 3 x N32 (today)",
+                             "pc N64 + N32 (B-concat)", "pc N128 + N64 (2 slices + B-concat)",
+                             "pair exact 3 x M256 N128", "pair exact M256 N256 + N128 (B-concat)", "pair fast 1 x M256 N128",
+                             "pc N64 + N32, A from a 10-px halo", "pc N128 + N64, A from a 10-px halo", "exact 3 x N128, A from an 18-px halo",
+                             "pc N64 + N32, dense A shifted by dx", "fast 1 x N128, A from an 18-px halo"};
+    for (int p = 0; p < 14; ++p) {
         if (only >= 0 && p != only) continue;
         const bool pair = p >= 6;
         const int grid = pair ? (sms / 2) * 2 : sms;
