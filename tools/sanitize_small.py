@@ -16,6 +16,13 @@ xo = ae.decode(enc.qhard, is_training=False)
 f, _ = pc.freqs(enc.symbols, ae.get_centers_variable())
 torch.cuda.synchronize()
 print('inference ok', float(bc.sum()), float(xo.mean()), int(f.sum() > 0))
+if os.environ.get('IC_SANITIZE_INFER_ONLY') == '1':      # the context model's depth walk on a second, ragged batch (segments of 1..3 outputs)
+    x2 = torch.from_numpy(weights.synthetic_images(3, 40, 104, seed=5)).cuda()
+    e2 = ae.encode(x2, is_training=False)
+    bc2 = pc.bitcost(e2.qbar, e2.symbols, is_training=False, pad_value=pc.auto_pad_value(ae))
+    torch.cuda.synchronize()
+    print('second batch ok', float(bc2.sum()))
+    sys.exit(0)
 tr = trainer.Trainer(a, p, W, mode='exact')
 xt = torch.from_numpy(weights.synthetic_images(2, 64, 64, seed=4)).cuda()
 out = tr.step(xt)
