@@ -53,12 +53,16 @@ __device__ __forceinline__ void issue_pattern(uint32_t tmem, uint64_t ah, uint64
     }
 }
 
-template <int P>
+// OCC: CTAs per SM (2: half the operand buffers and 256 TMEM columns each).  chains: accumulator regions the k-steps rotate
+// through (1: every MMA accumulates onto the columns the previous one wrote; 2: two independent chains in one CTA).
 // amode: layout of the A operand.  0: dense tile (core matrices 128-byte aligned, SBO = 128).  1 / 2: as conv_tc.cu reads it out
 // of a halo tile -- 8-pixel core matrices at the pitch of a 10- / 18-pixel halo row (SBO = 160 / 288 bytes) and a start address
 // that moves by the tap shift (dx 16 bytes + dy one halo row), i.e. core matrices that straddle 128-byte lines.  3: dense
 // pitch, start shifted by dx 16 bytes only.
-__global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned long long* cycles, int amode) {
+template <int P, int OCC = 1>
+__global__ void __launch_bounds__(128, OCC) mma_pattern_kernel(int iters, unsigned long long* cycles, int amode, int chains) {
+    constexpr int kBufs = OCC == 2 ? 4 : ::kBufs;
+    constexpr int kCols = OCC == 2 ? 256 : 512;
     extern __shared__ __align__(1024) uint8_t smem[];
     // [A hi x kBufs][A lo x kBufs][B (hi | lo interleaved per 16-byte row group: N up to 256) x kBufs]
     uint8_t* a_hi = smem;
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned
                 const uint64_t sb = (uint64_t)((u % kBufs) * (2 * kTile >> 4));
                 const uint64_t sa = amode == 0 ? (uint64_t)((u % kBufs) * (kTile >> 4))
                                                : (uint64_t)((u % kBufs) * (1024 >> 4) + (u % 3) + (amode == 3 ? 0 : ((u / 3) % 3) * (sbo_a >> 4)));
-                issue_pattern<P>(tmem, ah0 + sa, al0 + sa, bh0 + sb, bl0 + sb, (it | u) ? 1u : 0u);
+                issue_pattern<P>(tmem + (uint32_t)(u & (chains - 1)) * (kCols / 2), ah0 + sa, al0 + sa, bh0 + sb, bl0 + sb, (it | (u >> (chains - 1))) ? 1u : 0u);
             }
             umma_commit(smem_u32(&bar));          // bound the number of MMAs in flight like a stage hand-over does
             mbar_wait(smem_u32(&bar), ph);
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, unsigned
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kCols));
 }
 
 // ---- the same question for 2-CTA pairs (cta_group::2: M = 256 over both CTAs, each CTA holds half of the B rows)
@@ -188,14 +192,15 @@ mma_pattern_pair_kernel(int iters, unsigned long long* cycles) {
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
-template <int P>
-void launch_pattern(int grid, size_t smem, int iters, unsigned long long* d_cycles, int amode = 0) {
+template <int P, int OCC = 1>
+void launch_pattern(int grid, size_t smem, int iters, unsigned long long* d_cycles, int amode = 0, int chains = 1) {
     if (P >= 6) {
         cudaFuncSetAttribute(mma_pattern_pair_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         mma_pattern_pair_kernel<P><<<grid, 128, smem>>>(iters, d_cycles);
     } else {
-        cudaFuncSetAttribute(mma_pattern_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mma_pattern_kernel<P><<<grid, 128, smem>>>(iters, d_cycles, amode);
+        const size_t sm = OCC == 2 ? (2 * 4 * kTile + 4 * 2 * kTile + 1024) : smem;
+        cudaFuncSetAttribute(mma_pattern_kernel<P, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        mma_pattern_kernel<P, OCC><<<grid * OCC, 128, sm>>>(iters, d_cycles, amode, chains);
     }
 }
 
@@ -214,7 +219,13 @@ void launch_any(int p, int grid, size_t smem, int iters, unsigned long long* d) 
         case 10: launch_pattern<5>(grid, smem, iters, d, 1); break;
         case 11: launch_pattern<0>(grid, smem, iters, d, 2); break;
         case 12: launch_pattern<4>(grid, smem, iters, d, 3); break;
-        default: launch_pattern<2>(grid, smem, iters, d, 2); break;
+        case 13: launch_pattern<2>(grid, smem, iters, d, 2); break;
+        case 14: launch_pattern<5, 2>(grid, smem, iters, d, 1); break;
+        case 15: launch_pattern<5>(grid, smem, iters, d, 1, 2); break;
+        case 16: launch_pattern<4, 2>(grid, smem, iters, d, 1); break;
+        case 17: launch_pattern<4>(grid, smem, iters, d, 1, 2); break;
+        case 18: launch_pattern<0>(grid, smem, iters, d, 2, 2); break;
+        default: launch_pattern<5, 2>(grid, smem, iters, d, 1, 2); break;
     }
 }
 
@@ -226,17 +237,22 @@ int main(int argc, char** argv) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const size_t smem = 2 * kBufs * kTile + kBufs * 2 * kTile + 1024;
     unsigned long long* d_cycles;
-    cudaMalloc(&d_cycles, sizeof(unsigned long long) * sms);
+    cudaMalloc(&d_cycles, sizeof(unsigned long long) * sms * 2);
     // algorithmic MACs per k-step: one (pixels x cout x 16) product; patterns 3-5: cout = 24 of 32 (x2 slices for 5)
-    const double macs[14] = {128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 24 * 16, 128.0 * 24 * 16, 2 * 128.0 * 24 * 16,
+    const int occ[20] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 2, 1, 1, 2};
+    const double macs[20] = {128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 24 * 16, 128.0 * 24 * 16, 2 * 128.0 * 24 * 16,
                              128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 128 * 16, 128.0 * 24 * 16, 2 * 128.0 * 24 * 16, 128.0 * 128 * 16,
-                             128.0 * 24 * 16, 128.0 * 128 * 16};
-    const char* names[14] = {"exact 3 x N128 (today)", "exact N256 + N128 (B-concat)", "fast 1 x N128", "pc 3 x N32 (today)",
+                             128.0 * 24 * 16, 128.0 * 128 * 16, 2 * 128.0 * 24 * 16, 2 * 128.0 * 24 * 16, 128.0 * 24 * 16, 128.0 * 24 * 16,
+                             128.0 * 128 * 16, 2 * 128.0 * 24 * 16};
+    const char* names[20] = {"exact 3 x N128 (today)", "exact N256 + N128 (B-concat)", "fast 1 x N128", "pc 3 x N32 (today)",
                              "pc N64 + N32 (B-concat)", "pc N128 + N64 (2 slices + B-concat)",
                              "pair exact 3 x M256 N128", "pair exact M256 N256 + N128 (B-concat)", "pair fast 1 x M256 N128",
                              "pc N64 + N32, A from a 10-px halo", "pc N128 + N64, A from a 10-px halo", "exact 3 x N128, A from an 18-px halo",
-                             "pc N64 + N32, dense A shifted by dx", "fast 1 x N128, A from an 18-px halo"};
-    for (int p = 0; p < 14; ++p) {
+                             "pc N64 + N32, dense A shifted by dx", "fast 1 x N128, A from an 18-px halo",
+                             "pc N128 + N64 halo A, TWO CTAs per SM", "pc N128 + N64 halo A, two chains in one CTA",
+                             "pc N64 + N32 halo A, TWO CTAs per SM", "pc N64 + N32 halo A, two chains in one CTA",
+                             "exact 3 x N128 halo A, two chains in one CTA", "pc N128 + N64 halo A, two CTAs x two chains"};
+    for (int p = 0; p < 20; ++p) {
         if (only >= 0 && p != only) continue;
         const bool pair = p >= 6;
         const int grid = pair ? (sms / 2) * 2 : sms;
@@ -257,9 +273,9 @@ int main(int argc, char** argv) {
         }
         unsigned long long cyc = 0;
         cudaMemcpy(&cyc, d_cycles, sizeof(cyc), cudaMemcpyDeviceToHost);
-        const double ksteps = (double)reps * iters;
+        const double ksteps = (double)reps * iters * occ[p];      // per SM
         const double us = ms * 1e3;
-        printf("%-40s %7.3f k-steps/us/SM  %6.1f SM-cycles/k-step (last launch)  %7.1f algorithmic TFLOP/s (%d SMs)  %.0f ms\n", names[p],
+        printf("%-46s %7.3f k-steps/us/SM  %6.1f CTA-cycles/k-step (last launch)  %7.1f algorithmic TFLOP/s (%d SMs)  %.0f ms\n", names[p],
                ksteps / us, (double)cyc / iters, 2.0 * macs[p] * ksteps * grid / (us * 1e-6) / 1e12, grid, ms);
         fflush(stdout);
     }
