@@ -11,6 +11,7 @@ numpy: the 3x3 conv (tap = 16-byte shift of A's start address), its weights stag
 pixels on MN-major operands, and the B-concatenation layout planned in DESIGN.md section 7 (so the next kernel can be
 desk-checked before it sees a GPU)."""
 import numpy as np
+import pytest
 
 
 def operand(smem, start, lbo, sbo, rows, major, kdim=16):
@@ -197,7 +198,8 @@ def _fast_operand(smem, start, lbo, sbo, rows):
     return h[a // 2]
 
 
-def test_context_model_depth_walk_schedule():
+@pytest.mark.parametrize('NO,pairing', [(32, True), (16, True), (32, False)])
+def test_context_model_depth_walk_schedule(NO, pairing):
     """conv_tc.cu, ConvTcParams::walk: a CTA follows one (image, tile) along the depth axis; input slice j FINISHES output
     j - 1 (filter depth 1, taps 0..4) and STARTS output j (filter depth 0: taps 5..8, then 0..4) from ONE activation tile.
     Accumulators: ring of 4 tiles [X | Y] of 2 NO TMEM columns, output = X + Y.  Taps 0..4 are stored
@@ -207,7 +209,7 @@ def test_context_model_depth_walk_schedule():
     offsets, separate halves where the ring wraps and at segment ends) and must reproduce
     a_hi w_hi + a_hi w_lo + a_lo w_hi of the VALID masked 3-D conv for every output slice."""
     rng = np.random.RandomState(5)
-    NO, K, Din = 32, 24, 8                              # 7 output slices: the ring of 4 wraps once
+    K, Din = 24, 8                                      # 7 output slices: the ring of 4 wraps once; NO = 32: layers 1-2, 16: the head
     Hh, Ww = 18, 10
     halo_w, halo_pix = Ww, Hh * Ww
     a_plane = 4 * halo_pix * 16
@@ -255,13 +257,13 @@ def test_context_model_depth_walk_schedule():
             tap = tap0 + ti
             a_t = ((tap // 3) * halo_w + tap % 3) * 16
             w_t = w_g + ti * stage
-            if ti & 1:
+            if pairing and (ti & 1):
                 a_prev = (((tap - 1) // 3) * halo_w + (tap - 1) % 3) * 16
                 umma(d_hi, n_hi, a_prev + aks, a_t - a_prev, w_t - stage + wks, stage, True, a_smem)
                 umma(d_lo, n_lo, a_prev + aks + a_plane, a_t - a_prev, w_t - stage + wks + w_lo_off * 16, stage, True, a_smem)
             umma(d_hi, n_hi, a_t, albo, w_t, wlbo, not (first and ti == 0), a_smem)
             umma(d_lo, n_lo, a_t + a_plane, albo, w_t + w_lo_off * 16, wlbo, True, a_smem)
-            if (ti & 1) == 0 and ti == nt - 1:
+            if not pairing or ((ti & 1) == 0 and ti == nt - 1):
                 umma(d_hi, n_hi, a_t + aks, albo, w_t + wks, wlbo, True, a_smem)
                 umma(d_lo, n_lo, a_t + aks + a_plane, albo, w_t + wks + w_lo_off * 16, wlbo, True, a_smem)
 
@@ -309,6 +311,9 @@ def test_context_model_depth_walk_schedule():
     # k-steps (x 2 planes): start half 14, finish half 8, fused step 14, wrapped step 14 + 8 -- against 22 per output of the
     # two-group schedule.  One segment of 7 outputs: start + 5 fused + 1 wrapped + finish; three segments: 3 starts, 3 finishes,
     # 3 fused + 1 wrapped (the ring position carries over from segment to segment)
-    assert results[7] == 2 * (14 + 5 * 14 + 22 + 8), results
-    assert results[3] == 2 * (3 * 14 + 3 * 8 + 3 * 14 + 22), results
-    assert results[7] < 2 * 22 * 7
+    if pairing:
+        assert results[7] == 2 * (14 + 5 * 14 + 22 + 8), results
+        assert results[3] == 2 * (3 * 14 + 3 * 8 + 3 * 14 + 22), results
+        assert results[7] < 2 * 22 * 7
+    else:       # IC_PC_PAIR_CHUNKS=0: two k-steps per tap, 18 per fused step, 18 + 10 where the halves are separate
+        assert results[7] == 2 * (18 + 5 * 18 + 28 + 10), results
