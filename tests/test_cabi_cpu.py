@@ -181,6 +181,27 @@ def test_library_sass_has_tcgen05_and_tma_and_no_legacy_mma():
     assert not [k for k, v in per_kernel.items() if 'HMMA' in v]
 
 
+@pytest.mark.parametrize('case', ['rare', 'half', 'jitter', 'maxtotal', 'single', 'collapse', 'underflow'])
+def test_coder_stress_goldens(case):
+    """Streams the reference's own coder (code/arithmetic_coding.py, run by tests/golden/make_coder_stress.py) wrote for
+    tables that reach the corners of ArithmeticCoderBase.update (:80-115) -- up to 30 bits per symbol, intervals collapsing
+    to one value (32 shared leading bits), underflow runs of hundreds of bits, total = 2^30 + 2, a one-symbol alphabet --
+    against the closed-form / branch-free update of csrc/coder.cpp: both encoder entry points byte for byte, chunked
+    writes, and the decoder."""
+    g = load_golden('coder_stress')
+    f, s, want = g[case + '_freqs'], g[case + '_symbols'], g[case + '_stream'].tobytes()
+    e = ac.ArithmeticEncoder()
+    for lo in range(0, len(s), 333):
+        e.write(np.ascontiguousarray(f[lo:lo + 333]), np.ascontiguousarray(s[lo:lo + 333]))
+    got, nbits = e.finish()
+    assert bytes(got) == want and (nbits + 7) // 8 == len(want)
+    e = ac.ArithmeticEncoder()
+    e.write_u32(np.ascontiguousarray(f.astype(np.uint32)), np.ascontiguousarray(s.astype(np.uint8)))
+    got32, nbits32 = e.finish()
+    assert bytes(got32) == want and nbits32 == nbits
+    assert np.array_equal(ac.ArithmeticDecoder(want).read(np.ascontiguousarray(f)), s)
+
+
 def test_coder_u32_tables_give_the_same_stream():
     """ic_ac_enc_write_u32 (uint32 tables + uint8 symbols: what the compress pipeline stages in pinned memory) codes
     exactly what ic_ac_enc_write codes from int64 tables, including the golden bitstream of the reference's coder"""
