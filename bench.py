@@ -567,16 +567,27 @@ def main():
     out['decode'] = None if decode_ms is None else {'ms_per_step': decode_ms, 'MPix_per_s': world * N * H * Wd / (decode_ms * 1e-3) / 1e6}
     if world == 1 and not args.no_extras:
         # the other BASELINE.json configs, each with its own numbers (N = 1 only: they are not part of the scaling run)
+        # (a failure in one of them must not cost the headline line: it is recorded in place of the sub-record)
         k = max(3, min(args.steps, 5))
-        if args.workload != 'b64_512':
+
+        def headline():
             h, _ = measure_encode_pc('b64_512', args.mode, k, 3, 1, 0, local, with_parity=not args.no_parity, sample_clocks=False)
-            out['headline'] = {'note': 'north-star target shape B=64 512x512 cvpr/low (BASELINE.json north_star)', 'steps': k,
-                               'value': h['value'], 'unit': 'MPix/s', 'ms_per_step': h['ms_per_step'], 'e2e': h['e2e'],
-                               'roofline': h['roofline'], 'kernel_ms_per_step': h['kernel_ms_per_step'], 'parity': h['parity']}
-            torch.cuda.empty_cache()
+            return {'note': 'north-star target shape B=64 512x512 cvpr/low (BASELINE.json north_star)', 'steps': k,
+                    'value': h['value'], 'unit': 'MPix/s', 'ms_per_step': h['ms_per_step'], 'e2e': h['e2e'],
+                    'roofline': h['roofline'], 'kernel_ms_per_step': h['kernel_ms_per_step'], 'parity': h['parity']}
+
+        extras = []
+        if args.workload != 'b64_512':
+            extras.append(('headline', headline))
         if args.mode == 'exact':
-            out['train_step'] = measure_train_step(k)
-            out['real_bpp'] = measure_real_bpp()
+            extras += [('train_step', lambda: measure_train_step(k)), ('real_bpp', measure_real_bpp)]
+        for name, fn in extras:
+            try:
+                out[name] = fn()
+            except Exception as e:      # noqa: BLE001 -- reported, not swallowed
+                out[name] = {'error': '%s: %s' % (type(e).__name__, e)}
+                print('bench.py: sub-record %s failed: %r' % (name, e), file=sys.stderr)
+            torch.cuda.empty_cache()
     if not args.no_cpu_baseline:
         from oracle import imgcomp_oracle as O
         O.set_backend('torch')
