@@ -587,7 +587,10 @@ def main():
             except Exception as e:      # noqa: BLE001 -- reported, not swallowed
                 out[name] = {'error': '%s: %s' % (type(e).__name__, e)}
                 print('bench.py: sub-record %s failed: %r' % (name, e), file=sys.stderr)
-            torch.cuda.empty_cache()
+            try:
+                torch.cuda.empty_cache()
+            except Exception:           # noqa: BLE001 -- a poisoned context has already been reported above
+                pass
     if not args.no_cpu_baseline:
         from oracle import imgcomp_oracle as O
         O.set_backend('torch')
